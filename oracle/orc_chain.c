@@ -1,0 +1,100 @@
+/*
+ * oracle/orc_chain.c -- TEST INFRASTRUCTURE ONLY (see orc_types.h).
+ * Instantiates orc_core.inc for the three arithmetic modes and exports the C API.
+ * Small decision rules restated here:
+ *   UpdateTexParams           Source/DX11VideoProcessor.cpp:1143-1155
+ *   UpdatePostScaleTexures    Source/DX11VideoProcessor.cpp:2894-2907
+ *   ResizeShaderPass scaler   Source/DX11VideoProcessor.cpp:3106-3127
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <omp.h>
+#include "orc_types.h"
+#include "orc_api.h"
+#include "orc_math.h"
+
+int orc_internal_fmt(int iTexFormat, int cdepth)
+{
+    switch (iTexFormat) {
+    case ORC_TEXFMT_8INT:    return ORC_SURF_BGRA8;
+    case ORC_TEXFMT_10INT:   return ORC_SURF_RGB10A2;
+    case ORC_TEXFMT_16FLOAT: return ORC_SURF_RGBA16F;
+    default:                 return cdepth > 8 ? ORC_SURF_RGB10A2 : ORC_SURF_BGRA8;
+    }
+}
+
+int orc_need_final_pass(int backbuffer_fmt, int internal_fmt, int bUseDither)
+{
+    const int need = (backbuffer_fmt == ORC_SURF_BGRA8 && internal_fmt != ORC_SURF_BGRA8)
+                  || (backbuffer_fmt == ORC_SURF_RGB10A2 && internal_fmt == ORC_SURF_RGBA16F);
+    return bUseDither && need;
+}
+
+int orc_scaler_kind(int src, int dst, int bInterpolateAt50pct)
+{
+    const int k = bInterpolateAt50pct ? 2 : 1;
+    if (src == dst) return 0;
+    return (src > k * dst) ? 2 : 1;
+}
+
+#define ORC_MODE 0
+#define ORC_SUFFIX _spec
+#include "orc_core.inc"
+#undef ORC_MODE
+#undef ORC_SUFFIX
+
+#define ORC_MODE 1
+#define ORC_SUFFIX _lit
+#include "orc_core.inc"
+#undef ORC_MODE
+#undef ORC_SUFFIX
+
+#define ORC_MODE 2
+#define ORC_SUFFIX _f64
+#include "orc_core.inc"
+#undef ORC_MODE
+#undef ORC_SUFFIX
+
+int orc_num_threads(void) { return omp_get_max_threads(); }
+
+int orc_process(const orc_config* cfg, const void* const planes[3], const int32_t pitches[3],
+                void* out, int32_t out_pitch, orc_debug* dbg, int mode, int threads)
+{
+    if (threads <= 0) threads = omp_get_max_threads();
+    switch (mode) {
+    case ORC_MODE_SPEC:    return process_spec(cfg, planes, pitches, out, out_pitch, dbg, threads);
+    case ORC_MODE_LITERAL: return process_lit(cfg, planes, pitches, out, out_pitch, dbg, threads);
+    case ORC_MODE_F64:     return process_f64(cfg, planes, pitches, out, out_pitch, dbg, threads);
+    }
+    return -100;
+}
+
+int orc_process_from_convert(const orc_config* cfg, const void* convert_surf, int32_t pitch,
+                             void* out, int32_t out_pitch, orc_debug* dbg, int mode, int threads)
+{
+    if (threads <= 0) threads = omp_get_max_threads();
+    switch (mode) {
+    case ORC_MODE_SPEC:    return process_from_convert_spec(cfg, convert_surf, pitch, out, out_pitch, dbg, threads);
+    case ORC_MODE_LITERAL: return process_from_convert_lit(cfg, convert_surf, pitch, out, out_pitch, dbg, threads);
+    case ORC_MODE_F64:     return process_from_convert_f64(cfg, convert_surf, pitch, out, out_pitch, dbg, threads);
+    }
+    return -100;
+}
+
+int orc_axis_taps(int kind, int filter, int variant, int src_origin, int src_len, int dst_len,
+                  int i, int* base, float* weights, float* wsum)
+{
+    return axis_taps_export_spec(kind, filter, variant, src_origin, src_len, dst_len, i, base, weights, wsum);
+}
+
+float orc_test_lg2(float x) { return orc_lg2_spec(x); }
+float orc_test_ex2(float x) { return orc_ex2_spec(x); }
+float orc_test_pow(float x, float y, int mode)
+{
+    switch (mode) {
+    case ORC_MODE_SPEC:    return orc_pow_spec(x, y);
+    case ORC_MODE_LITERAL: return orc_pow_literal(x, y);
+    default:               return (float)orc_pow_f64(x, y);
+    }
+}
