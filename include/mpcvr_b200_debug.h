@@ -1,0 +1,55 @@
+/*
+ * mpcvr_b200_debug.h -- test/inspection hooks of libmpcvr_b200.so.  NOT part of the drop-in
+ * boundary (include/mpcvr_b200.h is); used by tests/ and bench.py to look inside the pass chain
+ * the way the reference's DumpTexture2D debugging aid does (Source/DX11Helper.cpp:114-170).
+ */
+#ifndef MPCVR_B200_DEBUG_H
+#define MPCVR_B200_DEBUG_H
+#include "mpcvr_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* which kernel family Process() uses */
+enum { MPCVR_PATH_AUTO = 0,       /* planner decides                                                   */
+       MPCVR_PATH_MULTIPASS = 1,  /* one kernel per reference pass, intermediates in HBM               */
+       MPCVR_PATH_FUSED = 2 };    /* single fused kernel per frame (fails if the plan has no fused form) */
+
+typedef struct mpcvr_plan_info {
+    int32_t internal_fmt;        /* m_InternalTexFmt as mpcvr_surface_format                             */
+    int32_t final_pass;          /* m_bFinalPass                                                         */
+    int32_t scaler_x, scaler_y;  /* 0 none, 1 interpolation, 2 convolution, 3 nearest stretch            */
+    int32_t filter_x, filter_y;  /* UPSCALE_* / DOWNSCALE_* value used                                   */
+    int32_t taps_x, taps_y;      /* max taps per output on each axis                                     */
+    int32_t path;                /* MPCVR_PATH_* actually selected                                       */
+    int32_t transfer;            /* 0 matrix only, 1 PQ->SDR, 2 HLG->SDR, 3 BT.2020 SDR gamut           */
+    uint32_t src_exfmt;          /* m_srcExFmt.value after SpecifyExtendedFormat                         */
+    int32_t src_pitch, src_lines;/* m_srcPitch, m_srcLines                                               */
+    int32_t variant;             /* 0 D3D11 shader set, 1 D3D9 shader set (Settings_t::bUseD3D11)        */
+} mpcvr_plan_info;
+
+int32_t mpcvr_debug_set_path(mpcvr* vp, int32_t path);
+int32_t mpcvr_debug_get_plan(mpcvr* vp, mpcvr_plan_info* info);
+/* PS_COLOR_TRANSFORM cm_r,cm_g,cm_b (row-major 3x3) + cm_c, and matrix_conv_prim */
+int32_t mpcvr_debug_get_color_params(mpcvr* vp, float m9[9], float c3[3], float gamut9[9], float* luminance_scale);
+/* per-axis resize table entry of output index i (host table the kernels consume) */
+int32_t mpcvr_debug_axis_taps(mpcvr* vp, int32_t axis, int32_t i, int32_t* base, float* weights, int32_t max_w, float* wsum);
+
+/* surfaces of the multipass chain (valid after a frame ran with MPCVR_PATH_MULTIPASS) */
+enum { MPCVR_DBG_SURF_CONVERT = 0,   /* m_TexConvertOutput, internal fmt                   */
+       MPCVR_DBG_SURF_RESIZE_X = 1,  /* m_TexResize, RGBA16F                               */
+       MPCVR_DBG_SURF_POSTSCALE = 2, /* m_TexsPostScale[0], internal fmt                   */
+       MPCVR_DBG_SURF_CONVERT_F32 = 3 /* convert shader output before the RT write: float4 per pixel (capture must be on) */ };
+int32_t mpcvr_debug_capture_f32(mpcvr* vp, int32_t enable);
+int32_t mpcvr_debug_read_surface(mpcvr* vp, int32_t which, void* host_dst, size_t dst_pitch, int32_t* w, int32_t* h, int32_t* fmt);
+/* run Process() downstream of ConvertColorPass on a caller-supplied m_TexConvertOutput (host memory, internal fmt) */
+int32_t mpcvr_debug_render_from_convert(mpcvr* vp, const void* host_surf, size_t pitch);
+
+/* device scalar math of the arithmetic contract, elementwise on host arrays (GPU required):
+ * op 0 LG2(x), 1 EX2(x), 2 POW(x,y), 3 UNORM16 read code/65535 (x = code), 4 UNORM10 read, 5 UNORM8 read */
+int32_t mpcvr_debug_math(int32_t cuda_device, int32_t op, const float* x, const float* y, float* out, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,214 @@
+"""Shared test harness: synthetic frames, one config description driving both the CPU
+oracle (tests/orclib.py) and the product (videorenderer_b200 through the C ABI)."""
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+import orclib as O  # noqa: E402
+
+
+def fmt(cf):
+    f = O.lib().orc_get_fmt(cf)
+    return f.contents if f else None
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic content
+# ------------------------------------------------------------------------------------------------
+def _legal_ranges(bits):
+    sh = bits - 8
+    return (16 << sh, 235 << sh), (16 << sh, 240 << sh)
+
+
+def make_codes(cf, w, h, kind="noise", seed=0):
+    """Y/U/V code planes in the format's nominal bit depth (8, 10 or 16), before memory packing."""
+    f = fmt(cf)
+    name = f.name.decode()
+    bits = 8 if f.bytes == 1 else (10 if (name in ("P010", "Y210", "Y410") or f.lsb_shift) else 16)
+    if name in ("P016", "P216", "Y216", "Y416") or (f.bytes == 2 and not f.lsb_shift and name.endswith("16")):
+        bits = 16
+    cw, ch = w // f.div_w, h // f.div_h
+    maxc = (1 << bits) - 1
+    (ylo, yhi), (clo, chi) = _legal_ranges(bits)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if kind == "ramp":
+        Y = np.broadcast_to(np.round(np.linspace(0, maxc, w)).astype(np.int64)[None, :], (h, w)).copy()
+        U = np.broadcast_to(np.round(np.linspace(0, maxc, ch)).astype(np.int64)[:, None], (ch, cw)).copy()
+        V = np.broadcast_to(np.round(np.linspace(maxc, 0, ch)).astype(np.int64)[:, None], (ch, cw)).copy()
+    elif kind == "noise":
+        Y = rng.integers(ylo, yhi + 1, (h, w)); U = rng.integers(clo, chi + 1, (ch, cw)); V = rng.integers(clo, chi + 1, (ch, cw))
+    elif kind == "fullnoise":
+        Y = rng.integers(0, maxc + 1, (h, w)); U = rng.integers(0, maxc + 1, (ch, cw)); V = rng.integers(0, maxc + 1, (ch, cw))
+    else:  # natural-ish: 5 seeded sinusoids + 5 % noise
+        def field(hh, ww, lo, hi):
+            yy, xx = np.mgrid[0:hh, 0:ww].astype(np.float64)
+            acc = np.zeros((hh, ww))
+            for _ in range(5):
+                fx, fy = rng.uniform(0.5, 6, 2) * 2 * np.pi / max(ww, hh)
+                acc += rng.uniform(0.3, 1) * np.sin(fx * xx + fy * yy + rng.uniform(0, 6.28))
+            acc = acc / 5 * 0.5 + 0.5 + rng.normal(0, 0.05, (hh, ww))
+            return np.clip(np.round(lo + acc * (hi - lo)), lo, hi).astype(np.int64)
+        Y = field(h, w, ylo, yhi); U = field(ch, cw, clo, chi); V = field(ch, cw, clo, chi)
+    return dict(Y=Y, U=U, V=V, bits=bits)
+
+
+def pack(cf, w, h, codes, pitch=None):
+    """Pack code planes into the caller's frame buffer exactly as the reference expects it
+    (layout walked by MemCopyToTexSrcVideo, Source/DX11VideoProcessor.cpp:1213-1252).
+    Returns (buffer uint8[...], pitch, planes[list of np views], pitches)."""
+    f = fmt(cf)
+    name = f.name.decode()
+    Y, U, V, bits = codes["Y"], codes["U"], codes["V"], codes["bits"]
+    layout = f.layout
+    cw, ch = w // f.div_w, h // f.div_h
+    if f.bytes == 1:
+        dt = np.uint8; up = 0
+    else:
+        dt = np.uint16
+        up = 6 if name in ("P010", "P210", "Y210") else 0          # MSB-aligned 10-bit containers
+        if name in ("P210",):
+            up = 6
+    if layout == 1:      # biplanar
+        base_pitch = w * f.packsize
+        if name == "NV12":
+            base_pitch = (base_pitch + 3) // 4 * 4
+        pitch = pitch or base_pitch
+        buf = np.zeros(pitch * (h + ch), np.uint8)
+        yv = buf[:pitch * h].reshape(h, pitch)[:, :w * f.bytes].view(dt)
+        yv[:] = (Y << up).astype(dt)
+        cv = buf[pitch * h:].reshape(ch, pitch)[:, :cw * 2 * f.bytes].view(dt)
+        cv[:, 0::2] = (U << up).astype(dt); cv[:, 1::2] = (V << up).astype(dt)
+        planes = [buf[:pitch * h], buf[pitch * h:]]
+        return buf, pitch, planes, [pitch, pitch]
+    if layout == 2:      # planar3
+        pitch = pitch or w * f.packsize
+        cp = pitch // f.div_w
+        buf = np.zeros(pitch * h + 2 * cp * ch, np.uint8)
+        buf[:pitch * h].reshape(h, pitch)[:, :w * f.bytes].view(dt)[:] = Y.astype(dt)
+        p1 = buf[pitch * h:pitch * h + cp * ch]; p2 = buf[pitch * h + cp * ch:]
+        first, second = (V, U) if f.vu_swapped else (U, V)
+        p1.reshape(ch, cp)[:, :cw * f.bytes].view(dt)[:] = first.astype(dt)
+        p2.reshape(ch, cp)[:, :cw * f.bytes].view(dt)[:] = second.astype(dt)
+        return buf, pitch, [buf[:pitch * h], p1, p2], [pitch, cp, cp]
+    if layout == 3:      # packed 4:2:2
+        pitch = pitch or w * f.packsize
+        buf = np.zeros(pitch * h, np.uint8)
+        row = buf.reshape(h, pitch)[:, :w * 2 * f.bytes].view(dt)     # [h, w*2] components
+        if f.packed_kind == 0:
+            row[:, 0::4] = (Y[:, 0::2] << up).astype(dt); row[:, 1::4] = (U << up).astype(dt)
+            row[:, 2::4] = (Y[:, 1::2] << up).astype(dt); row[:, 3::4] = (V << up).astype(dt)
+        else:
+            row[:, 0::4] = U.astype(dt); row[:, 1::4] = Y[:, 0::2].astype(dt); row[:, 2::4] = V.astype(dt); row[:, 3::4] = Y[:, 1::2].astype(dt)
+        return buf, pitch, [buf], [pitch]
+    # packed 4:4:4
+    pitch = pitch or w * f.packsize
+    buf = np.zeros(pitch * h, np.uint8)
+    if f.packed_kind == 0:       # AYUV bytes V U Y A
+        r = buf.reshape(h, pitch)[:, :w * 4].reshape(h, w, 4)
+        r[..., 0] = V; r[..., 1] = U; r[..., 2] = Y; r[..., 3] = 255
+    elif f.packed_kind == 1:     # Y410
+        r = buf.reshape(h, pitch)[:, :w * 4].view(np.uint32)
+        r[:] = (U.astype(np.uint32) | (Y.astype(np.uint32) << 10) | (V.astype(np.uint32) << 20) | (3 << 30))
+    else:                        # Y416
+        r = buf.reshape(h, pitch)[:, :w * 8].view(np.uint16).reshape(h, w, 4)
+        r[..., 0] = U; r[..., 1] = Y; r[..., 2] = V; r[..., 3] = 65535
+    return buf, pitch, [buf], [pitch]
+
+
+# ------------------------------------------------------------------------------------------------
+# one config description for both implementations
+# ------------------------------------------------------------------------------------------------
+class Case:
+    def __init__(self, cf, w, h, dst_w, dst_h, ex, backbuffer=O.SURF_BGRA8, tex=O.TEXFMT_AUTOINT, chroma=O.CHROMA_Bilinear,
+                 up=O.UPSCALE["CatmullRom"], down=O.DOWNSCALE["Hamming"], interp50=1, dither=1, to_sdr=1, nits=125,
+                 src_rect=None, dst_rect=None, win=None, variant=O.VARIANT_D3D11, procamp=None, interlaced=0, deint_blend=0,
+                 name=None):
+        self.__dict__.update(locals()); del self.__dict__["self"]
+        self.name = name or "case"
+
+    def orc_config(self):
+        pa = self.procamp or {}
+        return O.make_config(self.cf, self.w, self.h, self.dst_w, self.dst_h, self.ex, backbuffer=self.backbuffer,
+                             src_rect=self.src_rect, dst_rect=self.dst_rect, win=self.win, tex=self.tex, chroma=self.chroma,
+                             up=self.up, down=self.down, interp50=self.interp50, dither=self.dither, to_sdr=self.to_sdr,
+                             nits=self.nits, deint_blend=int(bool(self.deint_blend and self.interlaced)),
+                             brightness=pa.get("brightness", 0.0), contrast=pa.get("contrast", 1.0), hue=pa.get("hue", 0.0),
+                             saturation=pa.get("saturation", 1.0), variant=self.variant)
+
+    def settings(self):
+        import videorenderer_b200 as V
+        s = V.Settings.default()
+        s.bUseD3D11 = 1 if self.variant == O.VARIANT_D3D11 else 0
+        s.iTexFormat = self.tex; s.iChromaScaling = self.chroma; s.iUpscaling = self.up; s.iDownscaling = self.down
+        s.bInterpolateAt50pct = self.interp50; s.bUseDither = self.dither; s.bConvertToSdr = self.to_sdr
+        s.iSDRDisplayNits = self.nits; s.bDeintBlend = self.deint_blend
+        return s
+
+    def make_processor(self, device=0, path=None):
+        import videorenderer_b200 as V
+        vp = V.VideoProcessor(self.settings(), device=device)
+        mt = V.VideoProcessor.media_type(self.cf, self.w, self.h, self.ex, src_rect=self.src_rect, interlaced=self.interlaced)
+        assert vp.InitMediaType(mt), "InitMediaType failed: " + vp.last_error()
+        if self.procamp:
+            vp.SetProcAmpValues(**self.procamp)
+        win = self.win or (self.dst_w, self.dst_h)
+        vp.SetBackbufferFormat(self.backbuffer)
+        vp.SetWindowRect((0, 0, win[0], win[1]))
+        vp.SetVideoRect(self.dst_rect or (0, 0, self.dst_w, self.dst_h))
+        if path is not None:
+            vp.debug_set_path(path)
+        return vp
+
+
+def run_oracle(case, planes, pitches, mode=O.MODE_SPEC, want_debug=False, threads=0):
+    return O.process(case.orc_config(), planes, pitches, mode=mode, want_debug=want_debug, threads=threads)
+
+
+def rgb_view(buf, fmt_):
+    """decode a packed surface [h, w*bpp] uint8 into integer/float RGB [h, w, 3] (alpha dropped)"""
+    h = buf.shape[0]
+    if fmt_ == O.SURF_BGRA8:
+        a = buf.reshape(h, -1, 4)
+        return a[..., [2, 1, 0]].astype(np.int32)
+    if fmt_ == O.SURF_RGB10A2:
+        v = buf.view(np.uint32)
+        return np.stack([v & 1023, (v >> 10) & 1023, (v >> 20) & 1023], -1).astype(np.int32)
+    a = buf.view(np.float16).reshape(h, -1, 4)
+    return a[..., :3]
+
+
+def compare(a, b, fmt_):
+    """returns (mismatching channel values, max abs code delta)"""
+    ra, rb = rgb_view(a, fmt_), rgb_view(b, fmt_)
+    if fmt_ == O.SURF_RGBA16F:
+        ia = ra.view(np.int16).astype(np.int32); ib = rb.view(np.int16).astype(np.int32)
+        d = np.abs(ia - ib)
+        same = (ra == rb) | (d == 0)
+        return int((~same).sum()), int(d.max())
+    d = np.abs(ra - rb)
+    return int((d != 0).sum()), int(d.max())
+
+
+EX_709 = O.exfmt(chroma=5, range_=2, matrix=1, prim=2, trc=5)
+EX_2020_PQ = O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=15)
+EX_2020_HLG = O.exfmt(chroma=0, range_=2, matrix=4, prim=9, trc=16)
+EX_2020_SDR = O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=5)
+
+
+def baseline_cases(scale=1.0):
+    """The four single-GPU BASELINE.json configs, optionally scaled down (scale divides both source axes)."""
+    def s(v, m=2):
+        return max(m, int(round(v * scale / m)) * m)
+    return [
+        Case(O.CF["NV12"], s(1920), s(1080), s(1920), s(1080), EX_709, up=O.UPSCALE["Nearest"], name="C1_nv12_709_copy"),
+        Case(O.CF["P010"], s(3840), s(2160), 2 * s(3840), 2 * s(2160), EX_2020_PQ, up=O.UPSCALE["Lanczos3"], name="C2_p010_pq_lanczos3_2x"),
+        Case(O.CF["YUY2"], s(1920, 4), s(1080, 4), s(1920, 4) * 3 // 2, s(1080, 4) * 3 // 2, EX_2020_HLG, backbuffer=O.SURF_RGB10A2,
+             tex=O.TEXFMT_16FLOAT, up=O.UPSCALE["CatmullRom"], name="C3_yuy2_hlg_catmull_1.5x"),
+        Case(O.CF["P016"], s(7680, 4), s(4320, 4), s(7680, 4) // 2, s(4320, 4) // 2, EX_2020_SDR, backbuffer=O.SURF_RGBA16F,
+             tex=O.TEXFMT_16FLOAT, down=O.DOWNSCALE["Bicubic"], interp50=0, dither=0, name="C4_p016_bicubic_0.5x"),
+    ]

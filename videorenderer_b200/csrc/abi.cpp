@@ -1,0 +1,121 @@
+// abi.cpp -- the extern "C" surface declared in include/mpcvr_b200.h and include/mpcvr_b200_debug.h.
+// Thin: argument checks, then CB200VideoProcessor.  No exception crosses this boundary.
+#include <cstring>
+#include <new>
+#include "video_processor.h"
+
+using b200vr::CB200VideoProcessor;
+using b200vr::CRect;
+
+struct mpcvr { CB200VideoProcessor vp; };
+
+#define VP_OR(ret) if (!h) return (ret); CB200VideoProcessor& vp = h->vp
+#define GUARD(expr) try { return (expr); } catch (...) { return MPCVR_E_FAIL; }
+
+extern "C" {
+
+void mpcvr_settings_default(mpcvr_settings* s)
+{
+    if (!s) return;
+    memset(s, 0, sizeof(*s));
+    s->bUseD3D11 = 1;                       // IsWindows8OrGreater()
+    s->bShowStats = 0; s->iResizeStats = 0;
+    s->iTexFormat = MPCVR_TEXFMT_AUTOINT;
+    s->VPFmts_bNV12 = s->VPFmts_bP01x = s->VPFmts_bYUY2 = s->VPFmts_bOther = 1;
+    s->iVPDeinterlacing = 1; s->bDeintDouble = 1; s->bVPScaling = 1; s->iVPSuperRes = 0; s->bVPRTXVideoHDR = 0;
+    s->iChromaScaling = MPCVR_CHROMA_Bilinear;
+    s->iUpscaling = MPCVR_UPSCALE_CatmullRom;
+    s->iDownscaling = MPCVR_DOWNSCALE_Hamming;
+    s->bInterpolateAt50pct = 1; s->bUseDither = 1; s->bDeintBlend = 0;
+    s->iSwapEffect = 1; s->bExclusiveFS = 0; s->bVBlankBeforePresent = 0; s->bAdjustPresentTime = 1;
+    s->bReinitByDisplay = 0; s->bHdrPreferDoVi = 0;
+    s->bHdrPassthrough = 1; s->bHdrLocalToneMapping = 0; s->iHdrLocalToneMappingType = 1; s->iHdrDisplayMaxNits = 1000;
+    s->iHdrToggleDisplay = 0; s->bConvertToSdr = 1; s->iHdrOsdBrightness = 0; s->iSDRDisplayNits = MPCVR_SDR_NITS_DEF;
+}
+
+int32_t mpcvr_abi_version(void) { return MPCVR_ABI_VERSION; }
+
+int32_t mpcvr_create(const mpcvr_settings* settings, int32_t cuda_device, void* stream, mpcvr** out)
+{
+    if (!out) return MPCVR_E_POINTER;
+    *out = nullptr;
+    mpcvr* h = new (std::nothrow) mpcvr;
+    if (!h) return MPCVR_E_OUTOFMEMORY;
+    int32_t hr;
+    try { hr = h->vp.Init(settings, cuda_device, stream); } catch (...) { hr = MPCVR_E_FAIL; }
+    if (hr != MPCVR_S_OK) { delete h; return hr; }
+    *out = h;
+    return MPCVR_S_OK;
+}
+
+void mpcvr_destroy(mpcvr* h) { delete h; }
+
+const char* mpcvr_last_error(const mpcvr* h) { return h ? h->vp.LastError() : "null instance"; }
+
+int32_t mpcvr_verify_media_type(mpcvr* h, const mpcvr_media_type* mt) { VP_OR(0); GUARD(vp.VerifyMediaType(mt)); }
+int32_t mpcvr_init_media_type(mpcvr* h, const mpcvr_media_type* mt)   { VP_OR(0); GUARD(vp.InitMediaType(mt)); }
+int32_t mpcvr_get_alignment_size(mpcvr* h, const mpcvr_media_type* mt, int32_t* cx, int32_t* cy) { VP_OR(0); GUARD(vp.GetAlignmentSize(mt, cx, cy)); }
+
+int32_t mpcvr_process_sample(mpcvr* h, const mpcvr_sample* s) { VP_OR(MPCVR_E_POINTER); GUARD(vp.ProcessSample(s)); }
+int32_t mpcvr_render(mpcvr* h, int32_t field, int64_t t)      { VP_OR(MPCVR_E_POINTER); GUARD(vp.Render(field, t)); }
+int32_t mpcvr_fill_black(mpcvr* h)                            { VP_OR(MPCVR_E_POINTER); GUARD(vp.FillBlack()); }
+void    mpcvr_flush(mpcvr* h)                                 { if (h) h->vp.Flush(); }
+int32_t mpcvr_reset(mpcvr* h, int32_t dm)                     { VP_OR(MPCVR_E_POINTER); GUARD(vp.Reset(dm != 0)); }
+int32_t mpcvr_wait_idle(mpcvr* h)                             { VP_OR(MPCVR_E_POINTER); GUARD(vp.WaitIdle()); }
+
+static void to_rect(const CRect& c, mpcvr_rect* r) { if (r) { r->left = c.left; r->top = c.top; r->right = c.right; r->bottom = c.bottom; } }
+void mpcvr_get_source_rect(mpcvr* h, mpcvr_rect* r) { if (!h) return; CRect c; h->vp.GetSourceRect(c); to_rect(c, r); }
+void mpcvr_get_video_rect(mpcvr* h, mpcvr_rect* r)  { if (!h) return; CRect c; h->vp.GetVideoRect(c); to_rect(c, r); }
+void mpcvr_set_video_rect(mpcvr* h, const mpcvr_rect* r) { if (h && r) h->vp.SetVideoRect(CRect(r->left, r->top, r->right, r->bottom)); }
+int32_t mpcvr_set_window_rect(mpcvr* h, const mpcvr_rect* r) { VP_OR(MPCVR_E_POINTER); if (!r) return MPCVR_E_POINTER; GUARD(vp.SetWindowRect(CRect(r->left, r->top, r->right, r->bottom))); }
+int32_t mpcvr_set_rotation(mpcvr* h, int32_t d) { VP_OR(MPCVR_E_POINTER); return vp.SetRotation(d); }
+int32_t mpcvr_set_flip(mpcvr* h, int32_t f)     { VP_OR(MPCVR_E_POINTER); return vp.SetFlip(f != 0); }
+void mpcvr_get_video_size(mpcvr* h, int32_t* w, int32_t* hh) { if (!h || !w || !hh) return; h->vp.GetVideoSize(*w, *hh); }
+void mpcvr_get_aspect_ratio(mpcvr* h, int32_t* ax, int32_t* ay) { if (!h || !ax || !ay) return; h->vp.GetAspectRatio(*ax, *ay); }
+
+void mpcvr_get_settings(mpcvr* h, mpcvr_settings* s) { if (h && s) h->vp.GetSettings(*s); }
+void mpcvr_configure(mpcvr* h, const mpcvr_settings* s) { if (h && s) { try { h->vp.Configure(*s); } catch (...) {} } }
+int32_t mpcvr_get_active(mpcvr* h) { return h && h->vp.GetActive() ? 1 : 0; }
+int32_t mpcvr_set_procamp(mpcvr* h, uint32_t flags, const mpcvr_procamp* v) { VP_OR(MPCVR_E_POINTER); GUARD(vp.SetProcAmpValues(flags, v)); }
+int32_t mpcvr_get_procamp(mpcvr* h, uint32_t flags, mpcvr_procamp* v) { VP_OR(MPCVR_E_POINTER); return vp.GetProcAmpValues(flags, v); }
+
+int32_t mpcvr_set_backbuffer_format(mpcvr* h, int32_t fmt) { VP_OR(MPCVR_E_POINTER); GUARD(vp.SetBackbufferFormat(fmt)); }
+int32_t mpcvr_bind_backbuffer(mpcvr* h, void* p, size_t pitch) { VP_OR(MPCVR_E_POINTER); GUARD(vp.BindBackbuffer(p, pitch)); }
+int32_t mpcvr_get_backbuffer(mpcvr* h, void** p, size_t* pitch, int32_t* w, int32_t* hh, int32_t* fmt) { VP_OR(MPCVR_E_POINTER); return vp.GetBackbuffer(p, pitch, w, hh, fmt); }
+int32_t mpcvr_read_backbuffer(mpcvr* h, void* dst, size_t pitch) { VP_OR(MPCVR_E_POINTER); GUARD(vp.ReadBackbuffer(dst, pitch)); }
+int32_t mpcvr_get_current_image(mpcvr* h, void* dst, size_t pitch, int32_t* w, int32_t* hh) { VP_OR(MPCVR_E_POINTER); GUARD(vp.GetCurentImage(dst, pitch, w, hh)); }
+int32_t mpcvr_get_displayed_image(mpcvr* h, void* dst, size_t pitch, int32_t* w, int32_t* hh) { VP_OR(MPCVR_E_POINTER); GUARD(vp.GetDisplayedImage(dst, pitch, w, hh)); }
+int32_t mpcvr_get_vp_info(mpcvr* h, char* dst, size_t n) { VP_OR(MPCVR_E_POINTER); GUARD(vp.GetVPInfo(dst, n)); }
+
+int32_t mpcvr_set_sub_callback(mpcvr* h, mpcvr_sub_render_fn r, mpcvr_sub_set_device_fn d, void* user) { VP_OR(MPCVR_E_POINTER); return vp.SetSubCallback(r, d, user); }
+int32_t mpcvr_activate_device_decoding(mpcvr* h, int32_t dev, void* st, uint32_t flags) { VP_OR(MPCVR_E_POINTER); return vp.ActivateDeviceDecoding(dev, st, flags); }
+int32_t mpcvr_get_device_index(mpcvr* h) { return h ? h->vp.GetDeviceIndex() : -1; }
+int32_t mpcvr_get_stream(mpcvr* h, void** st) { VP_OR(MPCVR_E_POINTER); if (!st) return MPCVR_E_POINTER; *st = (void*)vp.Stream(); return MPCVR_S_OK; }
+int32_t mpcvr_get_last_frame_kernels(mpcvr* h, int32_t* n) { VP_OR(MPCVR_E_POINTER); if (!n) return MPCVR_E_POINTER; *n = vp.LastFrameKernels(); return MPCVR_S_OK; }
+
+// ---- debug surface
+int32_t mpcvr_debug_set_path(mpcvr* h, int32_t path) { VP_OR(MPCVR_E_POINTER); return vp.DebugSetPath(path); }
+int32_t mpcvr_debug_get_plan(mpcvr* h, mpcvr_plan_info* info) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugGetPlan(info)); }
+int32_t mpcvr_debug_get_color_params(mpcvr* h, float m9[9], float c3[3], float g9[9], float* lum) { VP_OR(MPCVR_E_POINTER); return vp.DebugGetColorParams(m9, c3, g9, lum); }
+int32_t mpcvr_debug_axis_taps(mpcvr* h, int32_t axis, int32_t i, int32_t* base, float* w, int32_t maxw, float* wsum) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugAxisTaps(axis, i, base, w, maxw, wsum)); }
+int32_t mpcvr_debug_capture_f32(mpcvr* h, int32_t en) { VP_OR(MPCVR_E_POINTER); return vp.DebugCaptureF32(en != 0); }
+int32_t mpcvr_debug_read_surface(mpcvr* h, int32_t which, void* dst, size_t pitch, int32_t* w, int32_t* hh, int32_t* fmt) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugReadSurface(which, dst, pitch, w, hh, fmt)); }
+int32_t mpcvr_debug_render_from_convert(mpcvr* h, const void* surf, size_t pitch) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugRenderFromConvert(surf, pitch)); }
+
+int32_t mpcvr_debug_math(int32_t dev, int32_t op, const float* x, const float* y, float* out, int64_t n)
+{
+    if (!x || !out || n <= 0) return MPCVR_E_POINTER;
+    if (cudaSetDevice(dev) != cudaSuccess) return MPCVR_E_FAIL;
+    float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    int32_t hr = MPCVR_E_FAIL;
+    if (cudaMalloc(&dx, n * 4) == cudaSuccess && cudaMalloc(&dout, n * 4) == cudaSuccess && (!y || cudaMalloc(&dy, n * 4) == cudaSuccess)) {
+        cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice);
+        if (y) cudaMemcpy(dy, y, n * 4, cudaMemcpyHostToDevice);
+        if (b200vr::LaunchMathProbe(op, dx, dy ? dy : dx, dout, n, 0) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess &&
+            cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess) hr = MPCVR_S_OK;
+    }
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return hr;
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+// frame_plan.h -- plain structs handed from the host-side processor to the CUDA kernels.
+// One FramePlan describes what CDX11VideoProcessor::Process (Source/DX11VideoProcessor.cpp:3285-3424)
+// would do for the current media type / rects / settings.
+#pragma once
+#include <cstdint>
+
+namespace b200vr {
+
+enum Transfer : int32_t {           // which body GetShaderConvertColor emits, Source/Shaders.cpp:861-923
+    TRANSFER_NONE = 0,              // matrix only
+    TRANSFER_PQ_TO_SDR = 1,         // :870-884
+    TRANSFER_HLG_TO_SDR = 2,        // :862-868 then :870-884
+    TRANSFER_SDR_2020 = 3,          // :892-915
+};
+
+struct SrcDesc {                    // the source "texture views" (Source/DX11Helper.h:87-170)
+    const uint8_t* pl[3];           // Y | Y,UV | Y,U,V (U/V already ordered) | packed
+    int32_t pitch[3];
+    int32_t W, H;                   // luma size in pixels
+    int32_t cw, ch;                 // chroma plane size in texels
+    int32_t layout;                 // SrcLayout
+    int32_t bytes;                  // per component
+    int32_t lsb_shift;
+    int32_t packed_kind;
+    int32_t subsampling;            // 420/422/444
+    int32_t chroma_mode;            // MPCVR_CHROMA_*
+    int32_t siting;                 // ChromaSub_*
+    int32_t deint_blend;
+    int32_t rect_l, rect_t, rect_w, rect_h;   // m_srcRect
+};
+
+struct ColorParams {
+    float cm[3][3];
+    float cc[3];
+    float gamut[3][3];
+    float lum_scale;                // 10000 / iSDRDisplayNits
+    float sdr_gamma;                // toLinear exponent of the BT.2020 SDR branch
+    int32_t transfer;               // Transfer
+};
+
+struct SurfDesc {                   // a render target / shader resource of the pass chain
+    void*   ptr;
+    int32_t pitch;                  // bytes
+    int32_t w, h;
+    int32_t fmt;                    // mpcvr_surface_format
+};
+
+enum ScalerKind : int32_t { SCALER_NONE = 0, SCALER_INTERP = 1, SCALER_CONV = 2, SCALER_NEAREST = 3 };
+
+struct AxisTable {                  // per output index i of one resize axis (TextureResizeShader, :332-377)
+    const int32_t* base;            // first source texel of the tap window
+    const float*   w;               // [dst_len][ntaps] weights (zero padded)
+    const float*   wsum;            // convolution: sum of weights (divide), else unused
+    int32_t ntaps;
+    int32_t kind;                   // ScalerKind
+    int32_t dup_q1;                 // D3D11 ps_interpolation_lanczos3.hlsl:33-34: tap 1 re-reads tap 0's texel
+    int32_t dst0, dst_len;          // destination range on this axis
+    int32_t src0, src_len;          // source rect on this axis (for the point-sampled case)
+};
+
+}  // namespace b200vr

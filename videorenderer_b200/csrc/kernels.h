@@ -1,0 +1,43 @@
+// kernels.h -- host-callable launchers of the CUDA kernels (kernels_multipass.cu, kernel_fused.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "frame_plan.h"
+
+namespace b200vr {
+
+// ---- multipass family: one kernel per reference pass (Process, Source/DX11VideoProcessor.cpp:3285-3424)
+// ConvertColorPass (:3048-3101). dbg_f32 (optional): float4 per pixel, shader output before the RT write.
+cudaError_t LaunchConvertPass(const SrcDesc& src, const ColorParams& color, const SurfDesc& out, float4* dbg_f32, cudaStream_t st);
+// TextureResizeShader (:332-377) along `axis` (0 = X, 1 = Y); `other` maps the other axis (point sample).
+cudaError_t LaunchResizePass(const SurfDesc& in, const SurfDesc& out, const AxisTable& table, int axis,
+                             const int32_t* other_idx, int other_dst0, int other_dst_len, cudaStream_t st);
+// TextureCopyRect with ps_simple (:300-330, :3178-3181): point-sampled copy / stretch.
+cudaError_t LaunchCopyPass(const SurfDesc& in, const SurfDesc& out, const int32_t* idx_x, const int32_t* idx_y,
+                           int dst_x0, int dst_y0, int dst_w, int dst_h, cudaStream_t st);
+// FinalPass (:3189-3233): ordered dither + quantise inside rect.
+cudaError_t LaunchFinalPass(const SurfDesc& in, const SurfDesc& out, int x0, int y0, int x1, int y1, float Q, cudaStream_t st);
+cudaError_t LaunchClear(const SurfDesc& s, cudaStream_t st);
+// any surface -> B8G8R8X8 (GetDisplayedImage)
+cudaError_t LaunchToBGRX(const SurfDesc& in, const SurfDesc& out, cudaStream_t st);
+
+// ---- fused family: the whole chain in one kernel per frame
+struct FusedPlan {
+    SrcDesc     src;
+    ColorParams color;
+    AxisTable   ax, ay;          // device tables
+    SurfDesc    out;             // back buffer
+    int32_t     internal_fmt;    // m_InternalTexFmt: rounding of the convert output and of the post-scale surface
+    int32_t     final_pass;      // dither + quantise at the end
+    int32_t     two_pass;        // both axes resample -> fp16 intermediate (m_TexResize)
+    float       Q;               // 255 / 1023
+};
+bool        FusedSupported(const FusedPlan& p, const char** why);
+cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches);
+
+// ---- scalar math probe (mpcvr_debug_math)
+cudaError_t LaunchMathProbe(int op, const float* x, const float* y, float* out, long long n, cudaStream_t st);
+
+// upload of the dither thresholds into constant memory (once per device)
+cudaError_t UploadDitherTable();
+
+}  // namespace b200vr

@@ -1,0 +1,298 @@
+// pixel_ops.cuh -- device building blocks of the frame path, shared by the multipass kernels
+// (one kernel per reference pass) and the fused per-frame kernel.
+//
+// What each block replaces in the reference:
+//   fetch_yuv()      the pixel-fetch half of the generated convert shader, ShaderGetPixels
+//                    (Source/Shaders.cpp:82-329, DX11 branches) incl. chroma reconstruction
+//   convert_color()  the body GetShaderConvertColor emits (Source/Shaders.cpp:819-923) with
+//                    Shaders/convert/{st2084,hlg,hdr_tone_mapping}.hlsl
+//   surf_load/store  the D3D11 render-target write / shader-resource read conversions between passes
+// Arithmetic: fp32, fused multiply-add exactly where fxc emits mad/dp3 (DESIGN.md "Arithmetic contract").
+#pragma once
+#include <cuda_fp16.h>
+#include "frame_plan.h"
+#include "fmt_table.h"
+#include "mpcvr_math.cuh"
+
+namespace b200vr {
+
+struct f3 { float x, y, z; };
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// ---------------------------------------------------------------------------------------------
+// surfaces
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ f3 surf_load(const SurfDesc& s, int x, int y)
+{
+    const uint8_t* row = (const uint8_t*)s.ptr + (size_t)y * s.pitch;
+    f3 r;
+    if (s.fmt == MPCVR_SURF_RGB10A2) {
+        const uint32_t v = __ldg((const uint32_t*)row + x);
+        r.x = unorm10(v & 1023u); r.y = unorm10((v >> 10) & 1023u); r.z = unorm10((v >> 20) & 1023u);
+    } else if (s.fmt == MPCVR_SURF_BGRA8) {
+        const uint32_t v = __ldg((const uint32_t*)row + x);
+        r.z = unorm8(v & 255u); r.y = unorm8((v >> 8) & 255u); r.x = unorm8((v >> 16) & 255u);
+    } else {
+        const uint2 v = __ldg((const uint2*)row + x);
+        const __half2 a = *reinterpret_cast<const __half2*>(&v.x), b = *reinterpret_cast<const __half2*>(&v.y);
+        r.x = __low2float(a); r.y = __high2float(a); r.z = __low2float(b);
+    }
+    return r;
+}
+
+__device__ __forceinline__ void surf_store(const SurfDesc& s, int x, int y, f3 v)
+{
+    uint8_t* row = (uint8_t*)s.ptr + (size_t)y * s.pitch;
+    if (s.fmt == MPCVR_SURF_RGB10A2) {
+        ((uint32_t*)row)[x] = qunorm(v.x, 1023.0f) | (qunorm(v.y, 1023.0f) << 10) | (qunorm(v.z, 1023.0f) << 20) | (3u << 30);
+    } else if (s.fmt == MPCVR_SURF_BGRA8) {
+        ((uint32_t*)row)[x] = qunorm(v.z, 255.0f) | (qunorm(v.y, 255.0f) << 8) | (qunorm(v.x, 255.0f) << 16) | (255u << 24);
+    } else {
+        const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, 1.0f);
+        uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
+        ((uint2*)row)[x] = o;
+    }
+}
+
+// the value a later pass reads back after `v` went through a render target of format fmt
+__device__ __forceinline__ float rt_roundtrip(int fmt, float v)
+{
+    if (fmt == MPCVR_SURF_RGB10A2) return unorm10(qunorm(v, 1023.0f));
+    if (fmt == MPCVR_SURF_BGRA8)   return unorm8(qunorm(v, 255.0f));
+    return f16_roundtrip(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// source fetch
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float src_comp(const SrcDesc& S, int plane, int x, int y, int comp, int ncomp)
+{
+    const uint8_t* p = S.pl[plane] + (size_t)y * S.pitch[plane];
+    if (S.bytes == 1) return unorm8(__ldg(p + x * ncomp + comp));
+    const uint32_t v = __ldg((const uint16_t*)p + x * ncomp + comp);
+    return unorm16((v << S.lsb_shift) & 0xFFFFu);
+}
+
+struct f2 { float u, v; };
+
+// chroma texel with CLAMP addressing (sampler state Source/DX11VideoProcessor.cpp:1308-1319)
+__device__ __forceinline__ f2 chroma_texel(const SrcDesc& S, int cx, int cy)
+{
+    cx = clampi(cx, 0, S.cw - 1); cy = clampi(cy, 0, S.ch - 1);
+    f2 r;
+    if (S.layout == LAYOUT_BIPLANAR) { r.u = src_comp(S, 1, cx, cy, 0, 2); r.v = src_comp(S, 1, cx, cy, 1, 2); }
+    else                             { r.u = src_comp(S, 1, cx, cy, 0, 1); r.v = src_comp(S, 2, cx, cy, 0, 1); }
+    return r;
+}
+
+__device__ __forceinline__ float lerp_mad(float a, float b, float f) { return fma_rn(f, __fsub_rn(b, a), a); }
+
+// code_CatmullRom_weights, Source/Shaders.cpp:66-72; t is a multiple of 1/4 so every term is exact
+__device__ __forceinline__ void catmull_weights(float t, float w[4])
+{
+    const float t2 = t * t, t3 = t * t2;
+    w[0] = t2 - (t3 + t) * 0.5f;
+    w[1] = t3 * 1.5f + 1.0f - t2 * 2.5f;
+    w[2] = t2 * 2.0f + t * 0.5f - t3 * 1.5f;
+    w[3] = (t3 - t2) * 0.5f;
+}
+
+// CATMULLROM_05, Source/Shaders.cpp:145
+__device__ __forceinline__ float catmull05(float c0, float c1, float c2, float c3)
+{
+    return __fmul_rn(fma_rn(9.0f, __fadd_rn(c1, c2), -__fadd_rn(c0, c3)), 0.0625f);
+}
+
+__device__ __forceinline__ f3 fetch_planar(const SrcDesc& S, int sx, int sy)
+{
+    f3 r;
+    r.x = src_comp(S, 0, sx, sy, 0, 1);
+    if (S.deint_blend && S.subsampling == 420) {                       // Source/Shaders.cpp:232-237
+        const float y1 = src_comp(S, 0, sx, max(sy - 1, 0), 0, 1);
+        const float y2 = src_comp(S, 0, sx, min(sy + 1, S.H - 1), 0, 1);
+        r.x = __fmul_rn(__fadd_rn(fma_rn(r.x, 2.0f, y1), y2), 0.25f);
+    }
+    f2 c;
+    if (S.chroma_mode == MPCVR_CHROMA_Nearest || S.subsampling == 444) {                 // :239-241
+        c = chroma_texel(S, S.subsampling == 444 ? sx : (sx >> 1), S.subsampling == 420 ? (sy >> 1) : sy);
+    } else if (S.chroma_mode == MPCVR_CHROMA_CatmullRom && S.subsampling == 420) {       // :242-251
+        float ox, oy;
+        if (S.siting == ChromaSub_Cosited)    { ox = -0.25f; oy = -0.25f; }
+        else if (S.siting == ChromaSub_MPEG1) { ox = -0.5f;  oy = -0.5f;  }
+        else                                  { ox = -0.25f; oy = -0.5f;  }
+        float wx[4], wy[4];
+        catmull_weights(((sx & 1) ? 0.75f : 0.25f) + ox, wx);
+        catmull_weights(((sy & 1) ? 0.75f : 0.25f) + oy, wy);
+        const int cx = sx >> 1, cy = sy >> 1;
+        float qu[4], qv[4];
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {                                                    // code_Bicubic_UV :74-79
+            const f2 c0 = chroma_texel(S, cx - 1, cy + j - 1), c1 = chroma_texel(S, cx, cy + j - 1);
+            const f2 c2 = chroma_texel(S, cx + 1, cy + j - 1), c3 = chroma_texel(S, cx + 2, cy + j - 1);
+            qu[j] = fma_rn(c3.u, wx[3], fma_rn(c2.u, wx[2], fma_rn(c1.u, wx[1], __fmul_rn(c0.u, wx[0]))));
+            qv[j] = fma_rn(c3.v, wx[3], fma_rn(c2.v, wx[2], fma_rn(c1.v, wx[1], __fmul_rn(c0.v, wx[0]))));
+        }
+        c.u = fma_rn(qu[3], wy[3], fma_rn(qu[2], wy[2], fma_rn(qu[1], wy[1], __fmul_rn(qu[0], wy[0]))));
+        c.v = fma_rn(qv[3], wy[3], fma_rn(qv[2], wy[2], fma_rn(qv[1], wy[1], __fmul_rn(qv[0], wy[0]))));
+    } else if (S.chroma_mode == MPCVR_CHROMA_CatmullRom && S.subsampling == 422) {       // :252-264
+        if ((sx & 1) == 0) c = chroma_texel(S, sx >> 1, sy);
+        else {
+            const int j = sx >> 1;
+            const f2 c0 = chroma_texel(S, j - 1, sy), c1 = chroma_texel(S, j, sy), c2 = chroma_texel(S, j + 1, sy), c3 = chroma_texel(S, j + 2, sy);
+            c.u = catmull05(c0.u, c1.u, c2.u, c3.u);
+            c.v = catmull05(c0.v, c1.v, c2.v, c3.v);
+        }
+    } else {                                                                             // CHROMA_Bilinear :265-270
+        // sample point in quarter chroma texels: strChromaPos (:118-142) through the MIN_POINT_MAG_LINEAR sampler
+        int qx, qy;
+        if (S.subsampling == 420) {
+            if (S.siting == ChromaSub_Cosited)    { qx = 2 * sx;     qy = 2 * sy;     }
+            else if (S.siting == ChromaSub_MPEG1) { qx = 2 * sx - 1; qy = 2 * sy - 1; }
+            else                                  { qx = 2 * sx;     qy = 2 * sy - 1; }
+        } else { qx = 2 * sx; qy = 4 * sy; }
+        const int ix = qx >> 2, iy = qy >> 2;
+        const float fx = (float)(qx & 3) * 0.25f, fy = (float)(qy & 3) * 0.25f;
+        const f2 c00 = chroma_texel(S, ix, iy), c10 = chroma_texel(S, ix + 1, iy);
+        const f2 c01 = chroma_texel(S, ix, iy + 1), c11 = chroma_texel(S, ix + 1, iy + 1);
+        c.u = lerp_mad(lerp_mad(c00.u, c10.u, fx), lerp_mad(c01.u, c11.u, fx), fy);
+        c.v = lerp_mad(lerp_mad(c00.v, c10.v, fx), lerp_mad(c01.v, c11.v, fx), fy);
+    }
+    r.y = c.u; r.z = c.v;
+    return r;
+}
+
+// packed 4:2:2 (Source/Shaders.cpp:195-228): one RGBA texel holds two pixels
+__device__ __forceinline__ f3 fetch_packed422(const SrcDesc& S, int sx, int sy)
+{
+    const int mw = S.W >> 1, mx = sx >> 1;
+    const bool uyvy = S.packed_kind == 1;
+    const int iy0 = uyvy ? 1 : 0, iu = uyvy ? 0 : 1, iy1 = uyvy ? 3 : 2, iv = uyvy ? 2 : 3;
+    f3 r;
+    if ((sx & 1) == 0) {
+        r.x = src_comp(S, 0, mx, sy, iy0, 4); r.y = src_comp(S, 0, mx, sy, iu, 4); r.z = src_comp(S, 0, mx, sy, iv, 4);
+    } else {
+        r.x = src_comp(S, 0, mx, sy, iy1, 4);
+        const int m0 = max(mx - 1, 0), m2 = min(mx + 1, mw - 1), m3 = min(mx + 2, mw - 1);
+        if (S.chroma_mode == MPCVR_CHROMA_CatmullRom) {
+            r.y = catmull05(src_comp(S, 0, m0, sy, iu, 4), src_comp(S, 0, mx, sy, iu, 4), src_comp(S, 0, m2, sy, iu, 4), src_comp(S, 0, m3, sy, iu, 4));
+            r.z = catmull05(src_comp(S, 0, m0, sy, iv, 4), src_comp(S, 0, mx, sy, iv, 4), src_comp(S, 0, m2, sy, iv, 4), src_comp(S, 0, m3, sy, iv, 4));
+        } else {
+            r.y = __fmul_rn(__fadd_rn(src_comp(S, 0, mx, sy, iu, 4), src_comp(S, 0, m2, sy, iu, 4)), 0.5f);
+            r.z = __fmul_rn(__fadd_rn(src_comp(S, 0, mx, sy, iv, 4), src_comp(S, 0, m2, sy, iv, 4)), 0.5f);
+        }
+    }
+    return r;
+}
+
+// packed 4:4:4 (Source/Shaders.cpp:183-194)
+__device__ __forceinline__ f3 fetch_packed444(const SrcDesc& S, int sx, int sy)
+{
+    const uint8_t* row = S.pl[0] + (size_t)sy * S.pitch[0];
+    f3 r;
+    if (S.packed_kind == 0) {          // AYUV: V U Y A
+        const uint32_t v = __ldg((const uint32_t*)row + sx);
+        r.z = unorm8(v & 255u); r.y = unorm8((v >> 8) & 255u); r.x = unorm8((v >> 16) & 255u);
+    } else if (S.packed_kind == 1) {   // Y410: U:10 Y:10 V:10 A:2
+        const uint32_t v = __ldg((const uint32_t*)row + sx);
+        r.y = unorm10(v & 1023u); r.x = unorm10((v >> 10) & 1023u); r.z = unorm10((v >> 20) & 1023u);
+    } else {                           // Y416: U Y V A, 16 bit
+        const uint2 v = __ldg((const uint2*)row + sx);
+        r.y = unorm16(v.x & 0xFFFFu); r.x = unorm16(v.x >> 16); r.z = unorm16(v.y & 0xFFFFu);
+    }
+    return r;
+}
+
+__device__ __forceinline__ f3 fetch_yuv(const SrcDesc& S, int sx, int sy)
+{
+    if (S.layout == LAYOUT_PACKED422) return fetch_packed422(S, sx, sy);
+    if (S.layout == LAYOUT_PACKED444) return fetch_packed444(S, sx, sy);
+    return fetch_planar(S, sx, sy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// colour conversion
+// ---------------------------------------------------------------------------------------------
+// Shaders/convert/st2084.hlsl:1-5 (exactly representable)
+#define ST2084_M1 0.1593017578125f
+#define ST2084_M2 78.84375f
+#define ST2084_C1 0.8359375f
+#define ST2084_C2 18.8515625f
+#define ST2084_C3 18.6875f
+
+__device__ __forceinline__ float st2084_to_linear(float v, float factor)          // st2084.hlsl:9-16
+{
+    const float a   = powr(v, __fdiv_rn(1.0f, ST2084_M2));
+    const float num = fmaxf(__fsub_rn(a, ST2084_C1), 0.0f);
+    const float den = fma_rn(-ST2084_C3, a, ST2084_C2);
+    const float b   = __fdiv_rn(num, den);
+    return __fmul_rn(powr(b, __fdiv_rn(1.0f, ST2084_M1)), factor);
+}
+
+__device__ __forceinline__ float linear_to_st2084(float v, float divider)         // st2084.hlsl:18-25
+{
+    v = __fmul_rn(v, __fdiv_rn(1.0f, divider));
+    const float p = powr(v, ST2084_M1);
+    const float q = __fdiv_rn(fma_rn(ST2084_C2, p, ST2084_C1), fma_rn(ST2084_C3, p, 1.0f));
+    return powr(q, ST2084_M2);
+}
+
+__device__ __forceinline__ float hable(float x)                                   // hdr_tone_mapping.hlsl:1-6
+{
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    const float CB = __fmul_rn(C, B), DE = __fmul_rn(D, E), DF = __fmul_rn(D, F), EF = __fdiv_rn(E, F);
+    return __fsub_rn(__fdiv_rn(fma_rn(x, fma_rn(A, x, CB), DE), fma_rn(x, fma_rn(A, x, B), DF)), EF);
+}
+
+__device__ __forceinline__ float inverse_hlg(float x)                             // hlg.hlsl:1-11
+{
+    const float a = 0.17883277f, b = 0.28466892f, c = 0.55991073f;
+    if (x <= 0.5f) return __fmul_rn(__fmul_rn(x, x), 4.0f);
+    return __fadd_rn(ex2(__fmul_rn(__fmul_rn(__fsub_rn(x, c), __fdiv_rn(1.0f, a)), 1.44269504f)), b);
+}
+
+__device__ __forceinline__ f3 mat3_apply(const float m[3][3], f3 v)               // mul(float3x3, float3): three dp3
+{
+    f3 r;
+    r.x = fma_rn(m[0][2], v.z, fma_rn(m[0][1], v.y, __fmul_rn(m[0][0], v.x)));
+    r.y = fma_rn(m[1][2], v.z, fma_rn(m[1][1], v.y, __fmul_rn(m[1][0], v.x)));
+    r.z = fma_rn(m[2][2], v.z, fma_rn(m[2][1], v.y, __fmul_rn(m[2][0], v.x)));
+    return r;
+}
+
+// convert shader body; returns the value before the render-target write
+__device__ __forceinline__ f3 convert_color(const ColorParams& P, f3 yuv)
+{
+    f3 c = mat3_apply(P.cm, yuv);                                                   // Source/Shaders.cpp:820
+    c.x = __fadd_rn(c.x, P.cc[0]); c.y = __fadd_rn(c.y, P.cc[1]); c.z = __fadd_rn(c.z, P.cc[2]);
+    if (P.transfer == TRANSFER_NONE) return c;
+    if (P.transfer == TRANSFER_SDR_2020) {                                          // :892-915
+        f3 l; l.x = powr(sat(c.x), P.sdr_gamma); l.y = powr(sat(c.y), P.sdr_gamma); l.z = powr(sat(c.z), P.sdr_gamma);
+        c = mat3_apply(P.gamut, l);
+    } else {
+        if (P.transfer == TRANSFER_HLG_TO_SDR) {                                    // :862-868
+            f3 l; l.x = inverse_hlg(sat(c.x)); l.y = inverse_hlg(sat(c.y)); l.z = inverse_hlg(sat(c.z));
+            const float dt = fma_rn(0.0593f, l.z, fma_rn(0.6780f, l.y, __fmul_rn(0.2627f, l.x)));   // hlg.hlsl:16-17
+            const float g  = powr(__fmul_rn(2000.0f, dt), 0.2f);
+            c.x = linear_to_st2084(__fmul_rn(l.x, g), 1000.0f);
+            c.y = linear_to_st2084(__fmul_rn(l.y, g), 1000.0f);
+            c.z = linear_to_st2084(__fmul_rn(l.z, g), 1000.0f);
+        }
+        const float rdiv = __fdiv_rn(1.0f, hable(4.8f));                            // x / HABLE_DIV, hdr_tone_mapping.hlsl:10-12
+        f3 h;
+        h.x = __fmul_rn(hable(st2084_to_linear(sat(c.x), P.lum_scale)), rdiv);      // :870-880
+        h.y = __fmul_rn(hable(st2084_to_linear(sat(c.y), P.lum_scale)), rdiv);
+        h.z = __fmul_rn(hable(st2084_to_linear(sat(c.z), P.lum_scale)), rdiv);
+        c = mat3_apply(P.gamut, h);                                                 // :881
+    }
+    const float ig = __fdiv_rn(1.0f, 2.2f);                                         // :917-923
+    c.x = powr(sat(c.x), ig); c.y = powr(sat(c.y), ig); c.z = powr(sat(c.z), ig);
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// final pass, Shaders/d3d11/ps_final_pass.hlsl:23-31: floor(pixel*Q + dither)/Q written to a UNORM target
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float final_quant(float p, float Q, float d) { return __fdiv_rn(floorf(fma_rn(p, Q, d)), Q); }
+
+}  // namespace b200vr

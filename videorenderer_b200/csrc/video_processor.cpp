@@ -1,0 +1,835 @@
+// video_processor.cpp -- see video_processor.h.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include "video_processor.h"
+
+namespace b200vr {
+
+static inline int AlignUp(int v, int a) { return (v + a - 1) / a * a; }
+static inline int SurfBpp(int fmt) { return fmt == MPCVR_SURF_RGBA16F ? 8 : 4; }
+
+// ------------------------------------------------------------------------------------------------
+// Tex2D / DeviceAxis
+// ------------------------------------------------------------------------------------------------
+void Tex2D::Release()
+{
+    if (ptr && owned) cudaFree(ptr);
+    ptr = nullptr; pitch = 0; w = h = 0; bytes = 0; owned = true;
+}
+
+cudaError_t Tex2D::CheckCreate(int f, int width, int height)
+{
+    if (ptr && owned && fmt == f && w == width && h == height) return cudaSuccess;
+    Release();
+    if (width <= 0 || height <= 0) return cudaErrorInvalidValue;
+    const size_t p = (size_t)AlignUp(width * SurfBpp(f), 256);
+    cudaError_t e = cudaMalloc(&ptr, p * height);
+    if (e != cudaSuccess) { ptr = nullptr; return e; }
+    pitch = p; w = width; h = height; fmt = f; bytes = p * height; owned = true;
+    return cudaSuccess;
+}
+
+AxisTable DeviceAxis::table() const
+{
+    AxisTable t;
+    t.base = base.ptr; t.w = w.ptr; t.wsum = wsum.ptr;
+    t.ntaps = host.ntaps; t.kind = host.kind; t.dup_q1 = host.dup_q1 ? 1 : 0;
+    t.dst0 = host.dst0; t.dst_len = host.dst_len; t.src0 = host.src0; t.src_len = host.src_len;
+    return t;
+}
+
+cudaError_t DeviceAxis::Upload(cudaStream_t st)
+{
+    cudaError_t e = base.Upload(host.base, st);
+    if (e == cudaSuccess) e = w.Upload(host.w, st);
+    if (e == cudaSuccess) e = wsum.Upload(host.wsum, st);
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+CB200VideoProcessor::CB200VideoProcessor() { mpcvr_settings_default(&m_settings); ApplySettings(m_settings); }
+
+CB200VideoProcessor::~CB200VideoProcessor()
+{
+    if (m_device >= 0) {
+        cudaSetDevice(m_device);
+        if (m_stream) cudaStreamSynchronize(m_stream);
+        for (auto& t : m_TexSrcVideo) t.Release();
+        m_TexConvertOutput.Release(); m_TexResize.Release(); m_TexsPostScale.Release(); m_BackBuffer.Release(); m_TexImage.Release();
+        m_dbgConvertF32.Release();
+        m_axisX.Release(); m_axisY.Release(); m_pointX.Release(); m_pointY.Release(); m_pointRX.Release(); m_pointRY.Release();
+        if (m_ownStream && m_stream) cudaStreamDestroy(m_stream);
+    }
+}
+
+int32_t CB200VideoProcessor::Fail(int32_t hr, const char* what, cudaError_t e)
+{
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    else snprintf(buf, sizeof(buf), "%s", what);
+    m_lastError = buf;
+    return hr;
+}
+
+bool CB200VideoProcessor::Cuda(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return true;
+    Fail(MPCVR_E_FAIL, what, e);
+    return false;
+}
+
+void CB200VideoProcessor::ApplySettings(const mpcvr_settings& s)
+{
+    m_settings = s;
+    m_bUseD3D11 = s.bUseD3D11 != 0;
+    m_iTexFormat = s.iTexFormat;
+    m_iChromaScaling = s.iChromaScaling;
+    m_iUpscaling = s.iUpscaling;
+    m_iDownscaling = s.iDownscaling;
+    m_bInterpolateAt50pct = s.bInterpolateAt50pct != 0;
+    m_bUseDither = s.bUseDither != 0;
+    m_bDeintBlend = s.bDeintBlend != 0;
+    m_bConvertToSdr = s.bConvertToSdr != 0;
+    m_iSDRDisplayNits = s.iSDRDisplayNits;
+    if (m_iSDRDisplayNits < MPCVR_SDR_NITS_MIN || m_iSDRDisplayNits > MPCVR_SDR_NITS_MAX) m_iSDRDisplayNits = MPCVR_SDR_NITS_DEF;
+}
+
+int32_t CB200VideoProcessor::Init(const mpcvr_settings* s, int device, void* stream)
+{
+    if (s) ApplySettings(*s);
+    m_device = device;
+    if (device < 0) { m_device = -1; return MPCVR_S_OK; }         // planning-only instance
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device >= count) {
+        m_device = -1;
+        return Fail(MPCVR_E_FAIL, "mpcvr_create: no such CUDA device (this library has no CPU path)", e);
+    }
+    if (!Cuda(cudaSetDevice(device), "cudaSetDevice")) { m_device = -1; return MPCVR_E_FAIL; }
+    if (stream) { m_stream = (cudaStream_t)stream; m_ownStream = false; }
+    else {
+        if (!Cuda(cudaStreamCreateWithFlags(&m_stream, cudaStreamNonBlocking), "cudaStreamCreate")) { m_device = -1; return MPCVR_E_FAIL; }
+        m_ownStream = true;
+    }
+    if (m_subSetDevice) m_subSetDevice(m_subUser, m_device);
+    return MPCVR_S_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// media type
+// ------------------------------------------------------------------------------------------------
+int32_t CB200VideoProcessor::VerifyMediaType(const mpcvr_media_type* mt)
+{
+    if (!mt) return 0;
+    const FmtConvParams& p = GetFmtConvParams(mt->cformat);
+    if (p.cformat == MPCVR_CF_NONE || !FormatSupported(p)) return 0;      // VerifyMediaType: known format + a usable VP
+    if (mt->width <= 0 || mt->height <= 0) return 0;
+    return 1;
+}
+
+int32_t CB200VideoProcessor::InitMediaType(const mpcvr_media_type* mt)
+{
+    if (!VerifyMediaType(mt)) return 0;
+    const FmtConvParams FmtParams = GetFmtConvParams(mt->cformat);
+
+    m_decExFmt.value = 0;
+    m_srcRect = CRect(mt->src_rect.left, mt->src_rect.top, mt->src_rect.right, mt->src_rect.bottom);
+    m_srcAspectRatioX = mt->aspect_x; m_srcAspectRatioY = mt->aspect_y;
+    if (FmtParams.CSType == CS_YUV && mt->ext_format) {
+        // m_decExFmt.value = dwControlFlags; SampleFormat = AMCONTROL_USED | AMCONTROL_COLORINFO_PRESENT  (:1765-1768)
+        m_decExFmt.value = (mt->ext_format & ~0xFFu) | 0x3u;
+    }
+    m_bInterlaced = mt->interlaced != 0;
+    m_rtAvgTimePerFrame = mt->avg_time_per_frame;
+
+    const unsigned biWidth = (unsigned)mt->width, biHeight = (unsigned)std::abs(mt->height);
+    m_srcLines = biHeight * FmtParams.PitchCoeff / 2;                       // :1789-1803
+    m_srcPitch = biWidth * FmtParams.Packsize;
+    switch (FmtParams.cformat) {
+    case MPCVR_CF_Y8: case MPCVR_CF_NV12: case MPCVR_CF_RGB24: case MPCVR_CF_BGR48:
+        m_srcPitch = AlignUp(m_srcPitch, 4); break;
+    case MPCVR_CF_V210:
+        m_srcPitch = AlignUp((biWidth + 5) / 6 * 16, 128); break;
+    default: break;
+    }
+    unsigned origW = biWidth, origH = biHeight;                             // VR_Extradata, :1805-1813
+    if (mt->frame_width > 0 && mt->frame_height != 0) { origW = (unsigned)mt->frame_width; origH = (unsigned)std::abs(mt->frame_height); }
+
+    if (m_srcRect.IsRectNull()) m_srcRect = CRect(0, 0, (int)origW, (int)origH);
+    if (m_srcRect.left < 0 || m_srcRect.top < 0 || m_srcRect.right > (int)origW || m_srcRect.bottom > (int)origH || m_srcRect.IsRectEmpty())
+        return 0;
+    m_srcRectWidth = m_srcRect.Width(); m_srcRectHeight = m_srcRect.Height();
+
+    m_srcExFmt = SpecifyExtendedFormat(m_decExFmt, FmtParams, m_srcRectWidth, m_srcRectHeight);
+
+    const unsigned g = std::gcd(m_srcRectWidth, m_srcRectHeight);           // :1842-1856
+    const unsigned srcFrameARX = m_srcRectWidth / g, srcFrameARY = m_srcRectHeight / g;
+    if (!m_srcAspectRatioX || !m_srcAspectRatioY) { m_srcAspectRatioX = srcFrameARX; m_srcAspectRatioY = srcFrameARY; m_srcAnamorphic = false; }
+    else {
+        const unsigned ag = std::gcd(m_srcAspectRatioX, m_srcAspectRatioY);
+        m_srcAspectRatioX /= ag; m_srcAspectRatioY /= ag;
+        m_srcAnamorphic = (srcFrameARX != m_srcAspectRatioX || srcFrameARY != m_srcAspectRatioY);
+    }
+
+    UpdateTexParams(FmtParams.CDepth);
+
+    // InitializeTexVP, :2018-2047: the source texture is origW x origH
+    m_srcWidth = origW; m_srcHeight = origH; m_srcParams = FmtParams;
+    m_haveFrame = false;
+    if (m_device >= 0) {
+        cudaSetDevice(m_device);
+        for (auto& t : m_TexSrcVideo) t.Release();
+        // plane buffers (bytes addressed as R8 "textures" of the right byte width)
+        int nplanes = 1, pw[3] = {0, 0, 0}, ph[3] = {0, 0, 0};
+        const int bpc = FmtParams.bytes;
+        switch (FmtParams.layout) {
+        case LAYOUT_BIPLANAR:
+            nplanes = 2; pw[0] = origW * bpc; ph[0] = origH;
+            pw[1] = (origW / FmtParams.div_chroma_w) * 2 * bpc; ph[1] = origH / FmtParams.div_chroma_h; break;
+        case LAYOUT_PLANAR3:
+            nplanes = 3; pw[0] = origW * bpc; ph[0] = origH;
+            pw[1] = pw[2] = (origW / FmtParams.div_chroma_w) * bpc; ph[1] = ph[2] = origH / FmtParams.div_chroma_h; break;
+        case LAYOUT_PACKED422: pw[0] = (origW / 2) * 4 * bpc; ph[0] = origH; break;
+        default:               pw[0] = origW * FmtParams.Packsize; ph[0] = origH; break;
+        }
+        for (int i = 0; i < nplanes; i++) {
+            Tex2D& t = m_TexSrcVideo[i];
+            const size_t p = (size_t)AlignUp(pw[i], 256);
+            if (!Cuda(cudaMalloc(&t.ptr, p * ph[i]), "cudaMalloc(m_TexSrcVideo)")) return 0;
+            t.pitch = p; t.w = pw[i]; t.h = ph[i]; t.bytes = p * ph[i]; t.owned = true;
+            cudaMemsetAsync(t.ptr, 0, t.bytes, m_stream);
+        }
+    }
+    SetShaderConvertColorParams();
+    SetShaderLuminanceParams();
+    m_bInit = true;
+    m_planDirty = true;
+    if (m_videoRect.IsRectEmpty()) m_videoRect = CRect(0, 0, (int)m_srcRectWidth, (int)m_srcRectHeight);
+    if (m_windowRect.IsRectEmpty()) m_windowRect = m_videoRect;
+    UpdateRenderRect();
+    if (UpdateTexures() != MPCVR_S_OK) return 0;
+    if (UpdatePostScaleTexures() != MPCVR_S_OK) return 0;
+    return 1;
+}
+
+int32_t CB200VideoProcessor::GetAlignmentSize(const mpcvr_media_type* mt, int32_t* cx, int32_t* cy)
+{
+    // The reference returns RowPitch/Packsize of a mapped probe texture so that the upload is one memcpy
+    // (:2055-2141).  Here the preferred row pitch is a multiple of 256 bytes (coalesced 128-bit loads, TMA
+    // tensor-map stride granularity).
+    if (!VerifyMediaType(mt) || !cx || !cy) return 0;
+    const FmtConvParams& p = GetFmtConvParams(mt->cformat);
+    *cx = AlignUp(mt->width * p.Packsize, 256) / p.Packsize;
+    *cy = std::abs(mt->height);
+    return 1;
+}
+
+void CB200VideoProcessor::UpdateTexParams(int cdepth)
+{
+    switch (m_iTexFormat) {
+    case MPCVR_TEXFMT_8INT:    m_InternalTexFmt = MPCVR_SURF_BGRA8; break;
+    case MPCVR_TEXFMT_10INT:   m_InternalTexFmt = MPCVR_SURF_RGB10A2; break;
+    case MPCVR_TEXFMT_16FLOAT: m_InternalTexFmt = MPCVR_SURF_RGBA16F; break;
+    case MPCVR_TEXFMT_AUTOINT:
+    default:                   m_InternalTexFmt = (cdepth > 8) ? MPCVR_SURF_RGB10A2 : MPCVR_SURF_BGRA8; break;
+    }
+}
+
+int CB200VideoProcessor::Transfer() const
+{
+    // GetShaderConvertColor, Source/Shaders.cpp:613-616, :861-915; convertType per UpdateConvertColorShader (:2948-2950)
+    // with no HDR display: SHADER_CONVERT_TO_SDR iff m_bConvertToSdr.
+    const uint32_t trc = m_srcExFmt.TransferFunction();
+    if (m_bConvertToSdr && trc == Trc_2084) return TRANSFER_PQ_TO_SDR;
+    if (m_bConvertToSdr && trc == Trc_HLG)  return TRANSFER_HLG_TO_SDR;
+    if (m_srcExFmt.Primaries() == Prim_BT2020) {
+        switch (trc) {
+        case Trc_18: case Trc_20: case Trc_HLG: case Trc_22: case Trc_709: case Trc_240M: case Trc_sRGB: case Trc_28: case Trc_26:
+            return TRANSFER_SDR_2020;
+        default: break;   // incl. TransFunc_10: the generated HLSL does not compile ("\\nothing", :895) -> matrix-only fallback
+        }
+    }
+    return TRANSFER_NONE;
+}
+
+void CB200VideoProcessor::SetShaderConvertColorParams()
+{
+    BuildColorTransform(m_srcExFmt, m_srcParams, m_ProcAmp, m_PSConvColorData);
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) m_color.cm[i][j] = m_PSConvColorData.m[i][j]; m_color.cc[i] = m_PSConvColorData.c[i]; }
+    BuildGamutMatrix(CHR_BT2020, CHR_BT709, m_color.gamut);               // Source/Shaders.cpp:634-645
+    m_color.transfer = Transfer();
+    float g = 1.0f;
+    switch (m_srcExFmt.TransferFunction()) {                                // Source/Shaders.cpp:894-905
+    case Trc_18: g = 1.8f; break; case Trc_20: g = 2.0f; break; case Trc_28: g = 2.8f; break; case Trc_26: g = 2.6f; break;
+    default: g = 2.2f; break;
+    }
+    m_color.sdr_gamma = g;
+    m_planDirty = true;
+}
+
+void CB200VideoProcessor::SetShaderLuminanceParams()
+{
+    m_color.lum_scale = 10000.0f / m_iSDRDisplayNits;                       // :891
+}
+
+void CB200VideoProcessor::UpdateRenderRect() { m_renderRect.IntersectRect(m_videoRect, m_windowRect); }
+
+int32_t CB200VideoProcessor::UpdateTexures()
+{
+    if (!m_srcWidth || !m_srcHeight) return MPCVR_S_OK;
+    m_planDirty = true;
+    if (m_device < 0) return MPCVR_S_OK;
+    cudaSetDevice(m_device);
+    if (!Cuda(m_TexConvertOutput.CheckCreate(m_InternalTexFmt, m_srcRectWidth, m_srcRectHeight), "m_TexConvertOutput")) return MPCVR_E_FAIL;
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::UpdatePostScaleTexures()
+{
+    const bool needDither =
+        (m_SwapChainFmt == MPCVR_SURF_BGRA8 && m_InternalTexFmt != MPCVR_SURF_BGRA8)
+        || (m_SwapChainFmt == MPCVR_SURF_RGB10A2 && m_InternalTexFmt == MPCVR_SURF_RGBA16F);
+    m_bFinalPass = m_bUseDither && needDither;
+    m_planDirty = true;
+    if (m_device < 0 || m_windowRect.IsRectEmpty()) return MPCVR_S_OK;
+    cudaSetDevice(m_device);
+    if (m_bFinalPass) {
+        if (!Cuda(m_TexsPostScale.CheckCreate(m_InternalTexFmt, m_windowRect.Width(), m_windowRect.Height()), "m_TexsPostScale")) return MPCVR_E_FAIL;
+    } else m_TexsPostScale.Release();
+    if (!Cuda(m_BackBuffer.CheckCreate(m_SwapChainFmt, m_windowRect.Width(), m_windowRect.Height()), "back buffer")) return MPCVR_E_FAIL;
+    return MPCVR_S_OK;
+}
+
+void CB200VideoProcessor::SetVideoRect(const CRect& r)
+{
+    m_videoRect = r;
+    UpdateRenderRect();
+    UpdateTexures();
+}
+
+int32_t CB200VideoProcessor::SetWindowRect(const CRect& r)
+{
+    m_windowRect = r;
+    UpdateRenderRect();
+    return UpdatePostScaleTexures();
+}
+
+int32_t CB200VideoProcessor::SetRotation(int v)
+{
+    if (v == 0) { m_iRotation = 0; return MPCVR_S_OK; }
+    return Fail(MPCVR_E_NOTIMPL, "rotation is not implemented on this path (SURVEY 8f-4)");
+}
+int32_t CB200VideoProcessor::SetFlip(bool v)
+{
+    if (!v) { m_bFlip = false; return MPCVR_S_OK; }
+    return Fail(MPCVR_E_NOTIMPL, "flip is not implemented on this path (SURVEY 8f-4)");
+}
+
+void CB200VideoProcessor::GetVideoSize(int32_t& w, int32_t& h) const
+{
+    w = m_srcRectWidth; h = m_srcRectHeight;                                // CVideoProcessor::GetVideoSize, Source/VideoProcessor.cpp
+}
+void CB200VideoProcessor::GetAspectRatio(int32_t& ax, int32_t& ay) const
+{
+    ax = m_srcAspectRatioX; ay = m_srcAspectRatioY;
+}
+
+void CB200VideoProcessor::Configure(const mpcvr_settings& s)
+{
+    // diff and rebuild the minimum, like Source/DX11VideoProcessor.cpp:3800-4050
+    const int oldTex = m_iTexFormat; const bool oldSdr = m_bConvertToSdr; const int oldNits = m_iSDRDisplayNits;
+    ApplySettings(s);
+    if (!m_bInit) return;
+    if (oldTex != m_iTexFormat) { UpdateTexParams(m_srcParams.CDepth); UpdateTexures(); }
+    if (oldSdr != m_bConvertToSdr) SetShaderConvertColorParams();
+    if (oldNits != m_iSDRDisplayNits) SetShaderLuminanceParams();
+    UpdatePostScaleTexures();
+    m_planDirty = true;
+}
+
+int32_t CB200VideoProcessor::SetProcAmpValues(uint32_t flags, const mpcvr_procamp* v)
+{
+    if (!v) return MPCVR_E_POINTER;
+    // ranges of SetDefaultDXVA2ProcAmpRanges: brightness -100..100, contrast 0..2, hue -180..180, saturation 0..2
+    auto clampf = [](float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); };
+    if (flags & MPCVR_PROCAMP_BRIGHTNESS) m_ProcAmp.brightness = clampf(v->brightness, -100.f, 100.f);
+    if (flags & MPCVR_PROCAMP_CONTRAST)   m_ProcAmp.contrast   = clampf(v->contrast, 0.f, 2.f);
+    if (flags & MPCVR_PROCAMP_HUE)        m_ProcAmp.hue        = clampf(v->hue, -180.f, 180.f);
+    if (flags & MPCVR_PROCAMP_SATURATION) m_ProcAmp.saturation = clampf(v->saturation, 0.f, 2.f);
+    if (m_bInit) SetShaderConvertColorParams();
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::GetProcAmpValues(uint32_t flags, mpcvr_procamp* v) const
+{
+    if (!v) return MPCVR_E_POINTER;
+    (void)flags;
+    v->brightness = m_ProcAmp.brightness; v->contrast = m_ProcAmp.contrast; v->hue = m_ProcAmp.hue; v->saturation = m_ProcAmp.saturation;
+    return MPCVR_S_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// output surfaces
+// ------------------------------------------------------------------------------------------------
+int32_t CB200VideoProcessor::SetBackbufferFormat(int fmt)
+{
+    if (fmt != MPCVR_SURF_BGRA8 && fmt != MPCVR_SURF_RGB10A2 && fmt != MPCVR_SURF_RGBA16F) return MPCVR_E_INVALIDARG;
+    m_SwapChainFmt = fmt;
+    m_UserBackBuffer = Tex2D();
+    return UpdatePostScaleTexures();
+}
+
+int32_t CB200VideoProcessor::BindBackbuffer(void* dev, size_t pitch)
+{
+    if (!dev) { m_UserBackBuffer = Tex2D(); return MPCVR_S_OK; }
+    if (m_windowRect.IsRectEmpty()) return Fail(MPCVR_E_UNEXPECTED, "bind_backbuffer: window rect not set");
+    if (pitch < (size_t)m_windowRect.Width() * SurfBpp(m_SwapChainFmt) || (pitch & 15)) return Fail(MPCVR_E_INVALIDARG, "bind_backbuffer: pitch too small or not 16-byte aligned");
+    m_UserBackBuffer.ptr = dev; m_UserBackBuffer.pitch = pitch; m_UserBackBuffer.w = m_windowRect.Width(); m_UserBackBuffer.h = m_windowRect.Height();
+    m_UserBackBuffer.fmt = m_SwapChainFmt; m_UserBackBuffer.owned = false;
+    m_planDirty = true;
+    return MPCVR_S_OK;
+}
+
+Tex2D& CB200VideoProcessor::CurrentTarget() { return m_UserBackBuffer.ptr ? m_UserBackBuffer : m_BackBuffer; }
+
+int32_t CB200VideoProcessor::GetBackbuffer(void** dev, size_t* pitch, int32_t* w, int32_t* h, int32_t* fmt)
+{
+    Tex2D& t = CurrentTarget();
+    if (!t.ptr) return Fail(MPCVR_E_UNEXPECTED, "no back buffer yet");
+    if (dev) *dev = t.ptr; if (pitch) *pitch = t.pitch; if (w) *w = t.w; if (h) *h = t.h; if (fmt) *fmt = t.fmt;
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::ReadBackbuffer(void* host, size_t pitch)
+{
+    if (m_device < 0) return Fail(MPCVR_E_UNEXPECTED, "no CUDA device (planning-only instance)");
+    Tex2D& t = CurrentTarget();
+    if (!t.ptr || !host) return Fail(MPCVR_E_POINTER, "read_backbuffer: nothing to read");
+    cudaSetDevice(m_device);
+    if (!Cuda(cudaMemcpy2DAsync(host, pitch, t.ptr, t.pitch, (size_t)t.w * SurfBpp(t.fmt), t.h, cudaMemcpyDeviceToHost, m_stream), "D2H back buffer")) return MPCVR_E_FAIL;
+    if (!Cuda(cudaStreamSynchronize(m_stream), "sync")) return MPCVR_E_FAIL;
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::WaitIdle()
+{
+    if (m_device < 0) return MPCVR_S_OK;
+    cudaSetDevice(m_device);
+    return Cuda(cudaStreamSynchronize(m_stream), "cudaStreamSynchronize") ? MPCVR_S_OK : MPCVR_E_FAIL;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frames
+// ------------------------------------------------------------------------------------------------
+int32_t CB200VideoProcessor::MemCopyToTexSrcVideo(const uint8_t* data, int pitch)
+{
+    // plane walk of MemCopyToTexSrcVideo, :1213-1252
+    const FmtConvParams& f = m_srcParams;
+    const int H = (int)m_srcHeight;
+    auto copy = [&](Tex2D& t, const uint8_t* src, int spitch, int lines) {
+        return cudaMemcpy2DAsync(t.ptr, t.pitch, src, spitch, (size_t)t.w, lines, cudaMemcpyHostToDevice, m_stream);
+    };
+    if (f.layout == LAYOUT_BIPLANAR || f.layout == LAYOUT_PLANAR3) {
+        if (!Cuda(copy(m_TexSrcVideo[0], data, pitch, H), "H2D luma")) return MPCVR_E_FAIL;
+        const int chromaH = H / f.div_chroma_h;
+        const int chromaPitch = (f.layout == LAYOUT_PLANAR3) ? pitch / f.div_chroma_w : pitch;
+        const uint8_t* p = data + (size_t)pitch * H;
+        if (!Cuda(copy(m_TexSrcVideo[1], p, chromaPitch, chromaH), "H2D chroma")) return MPCVR_E_FAIL;
+        if (f.layout == LAYOUT_PLANAR3) {
+            p += (size_t)chromaPitch * chromaH;
+            if (!Cuda(copy(m_TexSrcVideo[2], p, chromaPitch, chromaH), "H2D chroma 2")) return MPCVR_E_FAIL;
+        }
+    } else {
+        if (!Cuda(copy(m_TexSrcVideo[0], data, pitch, H), "H2D packed")) return MPCVR_E_FAIL;
+    }
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::CopySample(const mpcvr_sample* s)
+{
+    const FmtConvParams& f = m_srcParams;
+    SrcDesc& S = m_src;
+    memset(&S, 0, sizeof(S));
+    S.W = m_srcWidth; S.H = m_srcHeight;
+    S.cw = m_srcWidth / f.div_chroma_w; S.ch = m_srcHeight / f.div_chroma_h;
+    S.layout = f.layout; S.bytes = f.bytes; S.lsb_shift = f.lsb_shift; S.packed_kind = f.packed_kind; S.subsampling = f.Subsampling;
+    S.chroma_mode = m_iChromaScaling; S.siting = m_srcExFmt.ChromaSubsampling();
+    S.deint_blend = (m_bDeintBlend && m_bInterlaced && f.Subsampling == 420) ? 1 : 0;   // :2965, :3075
+    S.rect_l = m_srcRect.left; S.rect_t = m_srcRect.top; S.rect_w = m_srcRectWidth; S.rect_h = m_srcRectHeight;
+
+    if (s->flags & MPCVR_SAMPLE_DEVICE_MEMORY) {
+        // IMediaSampleD3D11 path (:2528-2570): the decoder's planes are read in place
+        const int np = f.layout == LAYOUT_BIPLANAR ? 2 : (f.layout == LAYOUT_PLANAR3 ? 3 : 1);
+        for (int i = 0; i < np; i++) {
+            if (!s->planes[i] || s->pitches[i] <= 0) return Fail(MPCVR_E_POINTER, "device sample: missing plane");
+            S.pl[i] = (const uint8_t*)s->planes[i]; S.pitch[i] = s->pitches[i];
+        }
+        if (s->ready_event && !Cuda(cudaStreamWaitEvent(m_stream, (cudaEvent_t)s->ready_event, 0), "cudaStreamWaitEvent")) return MPCVR_E_FAIL;
+    } else {
+        if (!s->data) return Fail(MPCVR_E_POINTER, "host sample: null data");
+        const int pitch = s->pitch ? s->pitch : m_srcPitch;
+        if (pitch <= 0) return Fail(MPCVR_E_NOTIMPL, "bottom-up (negative pitch) samples are RGB only");
+        if (s->size > 0 && s->size < (int64_t)pitch * (int64_t)m_srcLines) return Fail(MPCVR_E_FAIL, "host sample smaller than pitch*lines (:2579)");
+        const int32_t hr = MemCopyToTexSrcVideo((const uint8_t*)s->data, pitch);
+        if (hr != MPCVR_S_OK) return hr;
+        for (int i = 0; i < 3; i++) { S.pl[i] = (const uint8_t*)m_TexSrcVideo[i].ptr; S.pitch[i] = (int32_t)m_TexSrcVideo[i].pitch; }
+    }
+    if (f.layout == LAYOUT_PLANAR3 && f.v_before_u) { std::swap(S.pl[1], S.pl[2]); std::swap(S.pitch[1], S.pitch[2]); }   // texV:t1, texU:t2
+    m_rtStart = s->rt_start; m_rtEnd = s->rt_end;
+    m_haveFrame = true;
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::ProcessSample(const mpcvr_sample* s)
+{
+    if (m_device < 0) return Fail(MPCVR_E_UNEXPECTED, "no CUDA device: this library has no CPU path (planning-only instance)");
+    if (!m_bInit) return Fail(MPCVR_E_UNEXPECTED, "ProcessSample before InitMediaType");
+    if (!s) return MPCVR_E_POINTER;
+    cudaSetDevice(m_device);
+    int32_t hr = CopySample(s);
+    if (hr != MPCVR_S_OK) return hr;
+    return Render(1, s->rt_start);
+}
+
+int32_t CB200VideoProcessor::Render(int field, int64_t frameStartTime)
+{
+    (void)field; (void)frameStartTime;
+    if (m_device < 0) return Fail(MPCVR_E_UNEXPECTED, "no CUDA device: this library has no CPU path (planning-only instance)");
+    if (!m_bInit || !m_haveFrame) return Fail(MPCVR_E_UNEXPECTED, "Render without a frame");
+    if (m_windowRect.IsRectEmpty() || m_videoRect.IsRectEmpty()) return MPCVR_S_FALSE;     // nothing visible: frame skipped
+    cudaSetDevice(m_device);
+    m_lastLaunches = 0;
+    Tex2D& target = CurrentTarget();
+    if (!target.ptr) { int32_t hr = UpdatePostScaleTexures(); if (hr != MPCVR_S_OK) return hr; }
+    int32_t hr = Process(CurrentTarget(), m_srcRect, m_videoRect, false);
+    if (hr != MPCVR_S_OK) return hr;
+    return DrawSubtitles(CurrentTarget());
+}
+
+int32_t CB200VideoProcessor::DrawSubtitles(const Tex2D& rt)
+{
+    if (!m_subRender) return MPCVR_S_OK;
+    // arguments as at Source/DX11VideoProcessor.cpp:3262-3282
+    mpcvr_rect cropped = {m_videoRect.left, m_videoRect.top, m_videoRect.right, m_videoRect.bottom};
+    mpcvr_rect original = cropped;
+    mpcvr_rect viewport = {0, 0, m_windowRect.Width(), m_windowRect.Height()};
+    m_subRender(m_subUser, m_rtStart, m_rtEnd, m_rtAvgTimePerFrame, cropped, original, viewport, 1.0, 0, 0,
+                (void*)m_stream, rt.ptr, rt.pitch, rt.fmt);
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::FillBlack()
+{
+    if (m_device < 0) return Fail(MPCVR_E_UNEXPECTED, "no CUDA device");
+    Tex2D& t = CurrentTarget();
+    if (!t.ptr) return MPCVR_S_OK;
+    cudaSetDevice(m_device);
+    return Cuda(LaunchClear(t.desc(), m_stream), "clear") ? MPCVR_S_OK : MPCVR_E_FAIL;
+}
+
+void CB200VideoProcessor::Flush() { m_haveFrame = false; m_rtStart = 0; }
+
+int32_t CB200VideoProcessor::Reset(bool) { m_planDirty = true; return MPCVR_S_OK; }
+
+// ------------------------------------------------------------------------------------------------
+// plan: everything Process() needs that depends only on media type / rects / settings
+// ------------------------------------------------------------------------------------------------
+int32_t CB200VideoProcessor::UpdatePlan()
+{
+    if (!m_planDirty) return MPCVR_S_OK;
+    const CRect rSrc(0, 0, (int)m_srcRectWidth, (int)m_srcRectHeight);       // after ConvertColorPass, :3319
+    const CRect& dst = m_videoRect;
+    const int w1 = rSrc.Width(), h1 = rSrc.Height(), w2 = dst.Width(), h2 = dst.Height();
+    int kx = ChooseScaler(w1, w2, m_bInterpolateAt50pct), ky = ChooseScaler(h1, h2, m_bInterpolateAt50pct);
+    // UPSCALE_Nearest has no shader (m_pShaderUpscaleX == nullptr, :94-95, :2919): that axis is point sampled
+    if (kx == SCALER_INTERP && m_iUpscaling == MPCVR_UPSCALE_Nearest) kx = SCALER_NEAREST;
+    if (ky == SCALER_INTERP && m_iUpscaling == MPCVR_UPSCALE_Nearest) ky = SCALER_NEAREST;
+    const int fx = kx == SCALER_CONV ? m_iDownscaling : m_iUpscaling, fy = ky == SCALER_CONV ? m_iDownscaling : m_iUpscaling;
+    const bool d3d9 = !m_bUseD3D11;
+    if (!BuildAxisTable(kx, fx, d3d9, rSrc.left, w1, dst.left, w2, m_axisX.host)) return Fail(MPCVR_E_NOTIMPL, "X scaler not available (Jinc2 is a 'next' row)");
+    if (!BuildAxisTable(ky, fy, d3d9, rSrc.top, h1, dst.top, h2, m_axisY.host)) return Fail(MPCVR_E_NOTIMPL, "Y scaler not available (Jinc2 is a 'next' row)");
+    // point-sampled maps: other axis of a single-axis resize, and plain copies
+    BuildAxisTable(SCALER_NEAREST, 0, d3d9, rSrc.left, w1, dst.left, w2, m_pointX.host);
+    BuildAxisTable(SCALER_NEAREST, 0, d3d9, rSrc.top, h1, dst.top, h2, m_pointY.host);
+    // two-pass: X pass keeps rows (h1 -> h1), Y pass keeps columns (w2 -> w2)
+    BuildAxisTable(SCALER_NEAREST, 0, d3d9, rSrc.top, h1, 0, h1, m_pointRY.host);
+    BuildAxisTable(SCALER_NEAREST, 0, d3d9, dst.left, w2, dst.left, w2, m_pointRX.host);
+    if (m_device >= 0) {
+        cudaSetDevice(m_device);
+        if (!Cuda(m_axisX.Upload(m_stream), "upload X table") || !Cuda(m_axisY.Upload(m_stream), "upload Y table") ||
+            !Cuda(m_pointX.Upload(m_stream), "upload") || !Cuda(m_pointY.Upload(m_stream), "upload") ||
+            !Cuda(m_pointRX.Upload(m_stream), "upload") || !Cuda(m_pointRY.Upload(m_stream), "upload")) return MPCVR_E_FAIL;
+    }
+    m_planDirty = false;
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::ConvertColorPass(const Tex2D& rt)
+{
+    float4* dbg = nullptr;
+    if (m_captureF32) {
+        const size_t n = (size_t)rt.w * rt.h;
+        if (m_dbgConvertF32.n < n) { m_dbgConvertF32.Release(); if (!Cuda(cudaMalloc(&m_dbgConvertF32.ptr, n * sizeof(float4)), "dbg alloc")) return MPCVR_E_FAIL; m_dbgConvertF32.n = n; }
+        dbg = m_dbgConvertF32.ptr;
+    }
+    m_lastLaunches++;
+    return Cuda(LaunchConvertPass(m_src, m_color, rt.desc(), dbg, m_stream), "ConvertColorPass") ? MPCVR_S_OK : MPCVR_E_FAIL;
+}
+
+int32_t CB200VideoProcessor::ResizeShaderPass(const Tex2D& tex, const Tex2D& rt, const CRect& srcRect, const CRect& dstRect)
+{
+    (void)srcRect;
+    const int kx = m_axisX.host.kind, ky = m_axisY.host.kind;
+    const bool shaderX = (kx == SCALER_INTERP || kx == SCALER_CONV), shaderY = (ky == SCALER_INTERP || ky == SCALER_CONV);
+    const int h1 = m_axisY.host.src_len;
+    if (shaderX && shaderY) {
+        // two passes through m_TexResize: RGBA16F, width = render-target width, height = h1 (:3143-3167)
+        if (!Cuda(m_TexResize.CheckCreate(MPCVR_SURF_RGBA16F, rt.w, h1), "m_TexResize")) return MPCVR_E_FAIL;
+        m_lastLaunches += 2;
+        if (!Cuda(LaunchResizePass(tex.desc(), m_TexResize.desc(), m_axisX.table(), 0, m_pointRY.base.ptr, 0, h1, m_stream), "resize X")) return MPCVR_E_FAIL;
+        if (!Cuda(LaunchResizePass(m_TexResize.desc(), rt.desc(), m_axisY.table(), 1, m_pointRX.base.ptr, dstRect.left, dstRect.Width(), m_stream), "resize Y")) return MPCVR_E_FAIL;
+    } else if (shaderX) {
+        m_lastLaunches++;
+        if (!Cuda(LaunchResizePass(tex.desc(), rt.desc(), m_axisX.table(), 0, m_pointY.base.ptr, dstRect.top, dstRect.Height(), m_stream), "resize X")) return MPCVR_E_FAIL;
+    } else if (shaderY) {
+        m_lastLaunches++;
+        if (!Cuda(LaunchResizePass(tex.desc(), rt.desc(), m_axisY.table(), 1, m_pointX.base.ptr, dstRect.left, dstRect.Width(), m_stream), "resize Y")) return MPCVR_E_FAIL;
+    } else {
+        m_lastLaunches++;
+        if (!Cuda(LaunchCopyPass(tex.desc(), rt.desc(), m_pointX.base.ptr, m_pointY.base.ptr, dstRect.left, dstRect.top, dstRect.Width(), dstRect.Height(), m_stream), "copy")) return MPCVR_E_FAIL;
+    }
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::FinalPass(const Tex2D& tex, const Tex2D& rt, const CRect& rect)
+{
+    m_lastLaunches++;
+    const float Q = (rt.fmt == MPCVR_SURF_RGB10A2) ? 1023.0f : 255.0f;
+    return Cuda(LaunchFinalPass(tex.desc(), rt.desc(), rect.left, rect.top, rect.right, rect.bottom, Q, m_stream), "FinalPass") ? MPCVR_S_OK : MPCVR_E_FAIL;
+}
+
+int32_t CB200VideoProcessor::Process(const Tex2D& target, const CRect& srcRect, const CRect& dstRect, bool skipConvert)
+{
+    (void)srcRect;
+    int32_t hr = UpdatePlan();
+    if (hr != MPCVR_S_OK) return hr;
+    m_bDitherUsed = false;
+
+    const bool covers = dstRect.left <= 0 && dstRect.top <= 0 && dstRect.right >= target.w && dstRect.bottom >= target.h;
+
+    // ---- fused family
+    if (!skipConvert && m_forcePath != MPCVR_PATH_MULTIPASS) {
+        FusedPlan fp; const char* why = nullptr;
+        if (PlanFused(target, dstRect, fp, &why)) {
+            if (!covers) { m_lastLaunches++; if (!Cuda(LaunchClear(target.desc(), m_stream), "clear")) return MPCVR_E_FAIL; }
+            int launches = 0;
+            if (!Cuda(LaunchFused(fp, m_stream, &launches), "fused frame kernel")) return MPCVR_E_FAIL;
+            m_lastLaunches += launches;
+            m_path = MPCVR_PATH_FUSED; m_bDitherUsed = fp.final_pass != 0;
+            return MPCVR_S_OK;
+        }
+        if (m_forcePath == MPCVR_PATH_FUSED) return Fail(MPCVR_E_NOTIMPL, why ? why : "plan has no fused form");
+    }
+    m_path = MPCVR_PATH_MULTIPASS;
+
+    // ---- multipass family: the reference's passes, one kernel each
+    if (!covers) { m_lastLaunches++; if (!Cuda(LaunchClear(target.desc(), m_stream), "clear")) return MPCVR_E_FAIL; }   // ClearRenderTargetView, :2617
+    if (!skipConvert) { hr = ConvertColorPass(m_TexConvertOutput); if (hr != MPCVR_S_OK) return hr; }
+    const Tex2D* pInputTexture = &m_TexConvertOutput;
+    const CRect rSrc(0, 0, m_TexConvertOutput.w, m_TexConvertOutput.h);
+
+    if (m_bFinalPass) {                                                       // numSteps == 1, :3325-3416
+        if (!m_TexsPostScale.ptr || m_TexsPostScale.w != target.w || m_TexsPostScale.h != target.h || m_TexsPostScale.fmt != m_InternalTexFmt) {
+            if (!Cuda(m_TexsPostScale.CheckCreate(m_InternalTexFmt, target.w, target.h), "m_TexsPostScale")) return MPCVR_E_FAIL;
+        }
+        const Tex2D* pTex = &m_TexsPostScale;
+        CRect rect; rect.IntersectRect(dstRect, CRect(0, 0, pTex->w, pTex->h));
+        if (rSrc != dstRect) { hr = ResizeShaderPass(*pInputTexture, *pTex, rSrc, dstRect); if (hr != MPCVR_S_OK) return hr; }
+        else pTex = pInputTexture;                                            // "Hmm", :3351
+        hr = FinalPass(*pTex, target, rect);
+        m_bDitherUsed = true;
+        return hr;
+    }
+    return ResizeShaderPass(*pInputTexture, target, rSrc, dstRect);           // :3418
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused planning
+// ------------------------------------------------------------------------------------------------
+bool CB200VideoProcessor::PlanFused(const Tex2D& target, const CRect& dstRect, FusedPlan& fp, const char** why)
+{
+    memset(&fp, 0, sizeof(fp));
+    fp.src = m_src; fp.color = m_color;
+    fp.ax = m_axisX.table(); fp.ay = m_axisY.table();
+    fp.out = target.desc();
+    fp.internal_fmt = m_InternalTexFmt;
+    fp.final_pass = m_bFinalPass ? 1 : 0;
+    const int kx = m_axisX.host.kind, ky = m_axisY.host.kind;
+    fp.two_pass = ((kx == SCALER_INTERP || kx == SCALER_CONV) && (ky == SCALER_INTERP || ky == SCALER_CONV)) ? 1 : 0;
+    fp.Q = (target.fmt == MPCVR_SURF_RGB10A2) ? 1023.0f : 255.0f;
+    (void)dstRect;
+    return FusedSupported(fp, why);
+}
+
+// ------------------------------------------------------------------------------------------------
+// images
+// ------------------------------------------------------------------------------------------------
+int32_t CB200VideoProcessor::GetCurentImage(void* host, size_t pitch, int32_t* pw, int32_t* ph)
+{
+    if (m_device < 0) return Fail(MPCVR_E_UNEXPECTED, "no CUDA device");
+    if (!m_bInit || !m_haveFrame) return Fail(MPCVR_E_UNEXPECTED, "no frame");
+    unsigned w = m_srcRectWidth, h = m_srcRectHeight;                          // :3495-3503
+    if (m_srcAnamorphic) w = (unsigned)(((int64_t)h * m_srcAspectRatioX + m_srcAspectRatioY / 2) / m_srcAspectRatioY);   // MulDiv rounds to nearest
+    if (pw) *pw = (int32_t)w; if (ph) *ph = (int32_t)h;
+    if (!host) return MPCVR_S_OK;                                              // size query
+    if (pitch < (size_t)w * 4) return MPCVR_E_INVALIDARG;
+    cudaSetDevice(m_device);
+    const CRect imageRect(0, 0, (int)w, (int)h);
+    // temporarily m_videoRect = m_windowRect = imageRect, swap chain format B8G8R8X8 (:3519, :3547-3557)
+    const CRect backupVid = m_videoRect, backupWnd = m_windowRect; const int backupFmt = m_SwapChainFmt; const Tex2D backupUser = m_UserBackBuffer;
+    const bool backupFinal = m_bFinalPass;
+    m_videoRect = imageRect; m_windowRect = imageRect; m_SwapChainFmt = MPCVR_SURF_BGRA8; m_UserBackBuffer = Tex2D();
+    m_bFinalPass = m_bUseDither && (m_InternalTexFmt != MPCVR_SURF_BGRA8);
+    m_planDirty = true;
+    int32_t hr = MPCVR_S_OK;
+    if (!Cuda(m_TexImage.CheckCreate(MPCVR_SURF_BGRA8, (int)w, (int)h), "image target")) hr = MPCVR_E_FAIL;
+    if (hr == MPCVR_S_OK) hr = Process(m_TexImage, m_srcRect, imageRect, false);
+    if (hr == MPCVR_S_OK && !Cuda(cudaMemcpy2DAsync(host, pitch, m_TexImage.ptr, m_TexImage.pitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost, m_stream), "D2H image")) hr = MPCVR_E_FAIL;
+    if (hr == MPCVR_S_OK && !Cuda(cudaStreamSynchronize(m_stream), "sync")) hr = MPCVR_E_FAIL;
+    m_videoRect = backupVid; m_windowRect = backupWnd; m_SwapChainFmt = backupFmt; m_UserBackBuffer = backupUser; m_bFinalPass = backupFinal;
+    m_planDirty = true;
+    return hr;
+}
+
+int32_t CB200VideoProcessor::GetDisplayedImage(void* host, size_t pitch, int32_t* pw, int32_t* ph)
+{
+    if (m_device < 0) return Fail(MPCVR_E_UNEXPECTED, "no CUDA device");
+    Tex2D& t = CurrentTarget();
+    if (!t.ptr) return Fail(MPCVR_E_UNEXPECTED, "nothing displayed");
+    if (pw) *pw = t.w; if (ph) *ph = t.h;
+    if (!host) return MPCVR_S_OK;
+    if (pitch < (size_t)t.w * 4) return MPCVR_E_INVALIDARG;
+    cudaSetDevice(m_device);
+    const Tex2D* src = &t;
+    if (t.fmt != MPCVR_SURF_BGRA8) {
+        if (!Cuda(m_TexImage.CheckCreate(MPCVR_SURF_BGRA8, t.w, t.h), "image target")) return MPCVR_E_FAIL;
+        if (!Cuda(LaunchToBGRX(t.desc(), m_TexImage.desc(), m_stream), "to BGRX")) return MPCVR_E_FAIL;
+        src = &m_TexImage;
+    }
+    if (!Cuda(cudaMemcpy2DAsync(host, pitch, src->ptr, src->pitch, (size_t)t.w * 4, t.h, cudaMemcpyDeviceToHost, m_stream), "D2H")) return MPCVR_E_FAIL;
+    return Cuda(cudaStreamSynchronize(m_stream), "sync") ? MPCVR_S_OK : MPCVR_E_FAIL;
+}
+
+int32_t CB200VideoProcessor::GetVPInfo(char* dst, size_t n)
+{
+    if (!dst || !n) return MPCVR_E_POINTER;
+    static const char* up[] = {"Nearest-neighbor", "Mitchell-Netravali", "Catmull-Rom", "Lanczos2", "Lanczos3", "Jinc2m"};
+    static const char* down[] = {"Box", "Bilinear", "Hamming", "Bicubic", "Bicubic sharp", "Lanczos"};
+    static const char* surf[] = {"B8G8R8A8_UNORM", "R10G10B10A2_UNORM", "R16G16B16A16_FLOAT"};
+    cudaDeviceProp prop; memset(&prop, 0, sizeof(prop));
+    if (m_device >= 0) cudaGetDeviceProperties(&prop, m_device);
+    snprintf(dst, n,
+             "MPC VR B200 frame path (ABI %d)\nGraphics adapter: %s\nVideoProcessor: CUDA shaders (%s)\n"
+             "Input format : %s %ux%u\nInternalFormat: %s\nUpscaling : %s\nDownscaling: %s\nPostProcessing:%s%s\n",
+             MPCVR_ABI_VERSION, m_device >= 0 ? prop.name : "none (planning only)",
+             m_path == MPCVR_PATH_FUSED ? "fused" : "multipass", m_srcParams.str, m_srcRectWidth, m_srcRectHeight,
+             surf[m_InternalTexFmt], up[std::min(std::max(m_iUpscaling, 0), 5)], down[std::min(std::max(m_iDownscaling, 0), 5)],
+             m_color.transfer == TRANSFER_PQ_TO_SDR ? " PQ to SDR," : (m_color.transfer == TRANSFER_HLG_TO_SDR ? " HLG to SDR," : ""),
+             m_bFinalPass ? " dither" : "");
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::SetSubCallback(mpcvr_sub_render_fn r, mpcvr_sub_set_device_fn d, void* user)
+{
+    if (m_subSetDevice && m_subUser) m_subSetDevice(m_subUser, -1);           // SetDevice11(NULL) on the outgoing consumer
+    m_subRender = r; m_subSetDevice = d; m_subUser = user;
+    if (m_subSetDevice) m_subSetDevice(m_subUser, m_device);
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::ActivateDeviceDecoding(int device, void* decodeStream, uint32_t)
+{
+    // ActivateD3D11Decoding -> SetDevice: the renderer adopts the decoder's device (Source/VideoRendererInputPin.cpp:186-197)
+    (void)decodeStream;
+    if (device != m_device) return Fail(MPCVR_E_FAIL, "decoder is on another CUDA device: create the renderer instance on the decoder's device");
+    return MPCVR_S_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// debug hooks
+// ------------------------------------------------------------------------------------------------
+int32_t CB200VideoProcessor::DebugSetPath(int path) { if (path < 0 || path > 2) return MPCVR_E_INVALIDARG; m_forcePath = path; return MPCVR_S_OK; }
+
+int32_t CB200VideoProcessor::DebugGetPlan(mpcvr_plan_info* info)
+{
+    if (!info) return MPCVR_E_POINTER;
+    if (!m_bInit) return Fail(MPCVR_E_UNEXPECTED, "no media type");
+    int32_t hr = UpdatePlan();
+    if (hr != MPCVR_S_OK) return hr;
+    memset(info, 0, sizeof(*info));
+    info->internal_fmt = m_InternalTexFmt; info->final_pass = m_bFinalPass;
+    info->scaler_x = m_axisX.host.kind; info->scaler_y = m_axisY.host.kind;
+    info->filter_x = m_axisX.host.filter; info->filter_y = m_axisY.host.filter;
+    info->taps_x = m_axisX.host.ntaps; info->taps_y = m_axisY.host.ntaps;
+    info->path = m_path; info->transfer = m_color.transfer; info->src_exfmt = m_srcExFmt.value;
+    info->src_pitch = m_srcPitch; info->src_lines = (int32_t)m_srcLines; info->variant = m_bUseD3D11 ? 0 : 1;
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::DebugGetColorParams(float m9[9], float c3[3], float g9[9], float* lum)
+{
+    if (!m_bInit) return Fail(MPCVR_E_UNEXPECTED, "no media type");
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) { if (m9) m9[i*3+j] = m_color.cm[i][j]; if (g9) g9[i*3+j] = m_color.gamut[i][j]; } if (c3) c3[i] = m_color.cc[i]; }
+    if (lum) *lum = m_color.lum_scale;
+    return MPCVR_S_OK;
+}
+
+int32_t CB200VideoProcessor::DebugAxisTaps(int axis, int i, int32_t* base, float* w, int maxw, float* wsum)
+{
+    int32_t hr = UpdatePlan();
+    if (hr != MPCVR_S_OK) return hr;
+    const HostAxisTable& T = axis == 0 ? m_axisX.host : m_axisY.host;
+    if (i < 0 || i >= T.dst_len) return MPCVR_E_INVALIDARG;
+    if (base) *base = T.base[i];
+    for (int k = 0; k < T.ntaps && k < maxw; k++) w[k] = T.w[(size_t)i * T.ntaps + k];
+    if (wsum) *wsum = T.wsum.empty() ? 1.0f : T.wsum[i];
+    return T.ntaps;
+}
+
+int32_t CB200VideoProcessor::DebugCaptureF32(bool enable) { m_captureF32 = enable; return MPCVR_S_OK; }
+
+int32_t CB200VideoProcessor::DebugReadSurface(int which, void* host, size_t pitch, int32_t* w, int32_t* h, int32_t* fmt)
+{
+    if (m_device < 0) return Fail(MPCVR_E_UNEXPECTED, "no CUDA device");
+    cudaSetDevice(m_device);
+    if (which == MPCVR_DBG_SURF_CONVERT_F32) {
+        if (!m_dbgConvertF32.ptr) return Fail(MPCVR_E_UNEXPECTED, "f32 capture is off");
+        if (w) *w = m_TexConvertOutput.w; if (h) *h = m_TexConvertOutput.h; if (fmt) *fmt = -1;
+        if (!host) return MPCVR_S_OK;
+        if (!Cuda(cudaMemcpy2DAsync(host, pitch, m_dbgConvertF32.ptr, (size_t)m_TexConvertOutput.w * 16, (size_t)m_TexConvertOutput.w * 16, m_TexConvertOutput.h, cudaMemcpyDeviceToHost, m_stream), "D2H")) return MPCVR_E_FAIL;
+        return Cuda(cudaStreamSynchronize(m_stream), "sync") ? MPCVR_S_OK : MPCVR_E_FAIL;
+    }
+    const Tex2D* t = which == MPCVR_DBG_SURF_CONVERT ? &m_TexConvertOutput : (which == MPCVR_DBG_SURF_RESIZE_X ? &m_TexResize : &m_TexsPostScale);
+    if (!t->ptr) return Fail(MPCVR_E_UNEXPECTED, "surface does not exist for this plan");
+    if (w) *w = t->w; if (h) *h = t->h; if (fmt) *fmt = t->fmt;
+    if (!host) return MPCVR_S_OK;
+    if (!Cuda(cudaMemcpy2DAsync(host, pitch, t->ptr, t->pitch, (size_t)t->w * SurfBpp(t->fmt), t->h, cudaMemcpyDeviceToHost, m_stream), "D2H")) return MPCVR_E_FAIL;
+    return Cuda(cudaStreamSynchronize(m_stream), "sync") ? MPCVR_S_OK : MPCVR_E_FAIL;
+}
+
+int32_t CB200VideoProcessor::DebugRenderFromConvert(const void* host, size_t pitch)
+{
+    if (m_device < 0) return Fail(MPCVR_E_UNEXPECTED, "no CUDA device");
+    if (!m_bInit || !m_TexConvertOutput.ptr) return Fail(MPCVR_E_UNEXPECTED, "no media type");
+    cudaSetDevice(m_device);
+    if (!Cuda(cudaMemcpy2DAsync(m_TexConvertOutput.ptr, m_TexConvertOutput.pitch, host, pitch, (size_t)m_TexConvertOutput.w * SurfBpp(m_TexConvertOutput.fmt),
+                                m_TexConvertOutput.h, cudaMemcpyHostToDevice, m_stream), "H2D convert surface")) return MPCVR_E_FAIL;
+    m_lastLaunches = 0;
+    if (!CurrentTarget().ptr) { int32_t hr = UpdatePostScaleTexures(); if (hr != MPCVR_S_OK) return hr; }
+    return Process(CurrentTarget(), m_srcRect, m_videoRect, true);
+}
+
+}  // namespace b200vr

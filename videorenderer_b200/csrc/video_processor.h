@@ -1,0 +1,212 @@
+// video_processor.h -- CB200VideoProcessor: the host-side object behind the C ABI.
+//
+// Mirrors the slice of CVideoProcessor / CDX11VideoProcessor that drives the shader chain
+// (Source/VideoProcessor.h:40-236, Source/DX11VideoProcessor.h:351-357): same member names where
+// a counterpart exists, same decision rules, CUDA buffers and kernels in place of D3D11 textures
+// and draw calls.  Everything about windows, swap chains, OSD, DXVA and DirectShow is absent
+// (out of scope).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/mpcvr_b200.h"
+#include "../../include/mpcvr_b200_debug.h"
+#include "fmt_table.h"
+#include "cspmath.h"
+#include "frame_plan.h"
+#include "resize_tables.h"
+#include "kernels.h"
+
+namespace b200vr {
+
+struct CRect {
+    int left = 0, top = 0, right = 0, bottom = 0;
+    CRect() = default;
+    CRect(int l, int t, int r, int b) : left(l), top(t), right(r), bottom(b) {}
+    int Width() const { return right - left; }
+    int Height() const { return bottom - top; }
+    bool IsRectNull() const { return left == 0 && top == 0 && right == 0 && bottom == 0; }
+    bool IsRectEmpty() const { return right <= left || bottom <= top; }
+    bool operator==(const CRect& o) const { return left == o.left && top == o.top && right == o.right && bottom == o.bottom; }
+    bool operator!=(const CRect& o) const { return !(*this == o); }
+    bool IntersectRect(const CRect& a, const CRect& b) {
+        left = a.left > b.left ? a.left : b.left; top = a.top > b.top ? a.top : b.top;
+        right = a.right < b.right ? a.right : b.right; bottom = a.bottom < b.bottom ? a.bottom : b.bottom;
+        if (IsRectEmpty()) { *this = CRect(); return false; }
+        return true;
+    }
+};
+
+// device allocation with a pitch (the role ID3D11Texture2D plays in the reference)
+struct Tex2D {
+    void*  ptr = nullptr;
+    size_t pitch = 0;
+    int    w = 0, h = 0, fmt = 0;
+    size_t bytes = 0;
+    bool   owned = true;
+    SurfDesc desc() const { SurfDesc d; d.ptr = ptr; d.pitch = (int32_t)pitch; d.w = w; d.h = h; d.fmt = fmt; return d; }
+    void Release();
+    cudaError_t CheckCreate(int fmt, int w, int h);     // Tex2D_t::CheckCreate, Source/DX11Helper.h
+};
+
+template <typename T>
+struct DevArray {
+    T* ptr = nullptr; size_t n = 0;
+    void Release() { if (ptr) cudaFree(ptr); ptr = nullptr; n = 0; }
+    cudaError_t Upload(const std::vector<T>& v, cudaStream_t st) {
+        if (v.size() > n) { Release(); cudaError_t e = cudaMalloc(&ptr, v.size() * sizeof(T)); if (e != cudaSuccess) return e; n = v.size(); }
+        if (v.empty()) return cudaSuccess;
+        return cudaMemcpyAsync(ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+};
+
+struct DeviceAxis {
+    HostAxisTable host;
+    DevArray<int32_t> base; DevArray<float> w, wsum;
+    AxisTable table() const;
+    cudaError_t Upload(cudaStream_t st);
+    void Release() { base.Release(); w.Release(); wsum.Release(); }
+};
+
+class CB200VideoProcessor {
+public:
+    CB200VideoProcessor();
+    ~CB200VideoProcessor();
+
+    int32_t Init(const mpcvr_settings* s, int device, void* stream);          // CVideoProcessor::Init
+
+    // Source/VideoProcessor.h:178-189
+    int32_t VerifyMediaType(const mpcvr_media_type* mt);
+    int32_t InitMediaType(const mpcvr_media_type* mt);
+    int32_t GetAlignmentSize(const mpcvr_media_type* mt, int32_t* cx, int32_t* cy);
+    int32_t ProcessSample(const mpcvr_sample* s);
+    int32_t Render(int field, int64_t frameStartTime);
+    int32_t FillBlack();
+    void    Flush();
+    int32_t Reset(bool displayModeChange);
+    int32_t WaitIdle();
+
+    void    GetSourceRect(CRect& r) const { r = m_srcRect; }
+    void    GetVideoRect(CRect& r) const { r = m_videoRect; }
+    void    SetVideoRect(const CRect& r);
+    int32_t SetWindowRect(const CRect& r);
+    int32_t SetRotation(int v);
+    int32_t SetFlip(bool v);
+    void    GetVideoSize(int32_t& w, int32_t& h) const;
+    void    GetAspectRatio(int32_t& ax, int32_t& ay) const;
+
+    void    GetSettings(mpcvr_settings& s) const { s = m_settings; }
+    void    Configure(const mpcvr_settings& s);                                // Source/DX11VideoProcessor.cpp:3800-4050
+    bool    GetActive() const { return m_bInit && m_device >= 0; }
+    int32_t SetProcAmpValues(uint32_t flags, const mpcvr_procamp* v);
+    int32_t GetProcAmpValues(uint32_t flags, mpcvr_procamp* v) const;
+
+    int32_t SetBackbufferFormat(int fmt);
+    int32_t BindBackbuffer(void* dev, size_t pitch);
+    int32_t GetBackbuffer(void** dev, size_t* pitch, int32_t* w, int32_t* h, int32_t* fmt);
+    int32_t ReadBackbuffer(void* host, size_t pitch);
+    int32_t GetCurentImage(void* host, size_t pitch, int32_t* w, int32_t* h);  // sic, Source/VideoProcessor.h:220
+    int32_t GetDisplayedImage(void* host, size_t pitch, int32_t* w, int32_t* h);
+    int32_t GetVPInfo(char* dst, size_t n);
+
+    int32_t SetSubCallback(mpcvr_sub_render_fn r, mpcvr_sub_set_device_fn d, void* user);
+    int32_t ActivateDeviceDecoding(int device, void* decodeStream, uint32_t flags);
+    int     GetDeviceIndex() const { return m_device; }
+    cudaStream_t Stream() const { return m_stream; }
+    int     LastFrameKernels() const { return m_lastLaunches; }
+    const char* LastError() const { return m_lastError.c_str(); }
+
+    // debug hooks (include/mpcvr_b200_debug.h)
+    int32_t DebugSetPath(int path);
+    int32_t DebugGetPlan(mpcvr_plan_info* info);
+    int32_t DebugGetColorParams(float m9[9], float c3[3], float g9[9], float* lum);
+    int32_t DebugAxisTaps(int axis, int i, int32_t* base, float* w, int maxw, float* wsum);
+    int32_t DebugCaptureF32(bool enable);
+    int32_t DebugReadSurface(int which, void* host, size_t pitch, int32_t* w, int32_t* h, int32_t* fmt);
+    int32_t DebugRenderFromConvert(const void* host, size_t pitch);
+
+private:
+    // ---- settings (names as in Source/VideoProcessor.h:48-73)
+    mpcvr_settings m_settings;
+    int  m_iTexFormat = MPCVR_TEXFMT_AUTOINT;
+    int  m_iChromaScaling = MPCVR_CHROMA_Bilinear;
+    int  m_iUpscaling = MPCVR_UPSCALE_CatmullRom;
+    int  m_iDownscaling = MPCVR_DOWNSCALE_Hamming;
+    bool m_bInterpolateAt50pct = true;
+    bool m_bUseDither = true;
+    bool m_bDeintBlend = false;
+    bool m_bConvertToSdr = true;
+    int  m_iSDRDisplayNits = MPCVR_SDR_NITS_DEF;
+    bool m_bUseD3D11 = true;                 // which shader set is restated (D3D11 / D3D9 twins)
+    void ApplySettings(const mpcvr_settings& s);
+
+    // ---- input parameters (Source/VideoProcessor.h:80-95)
+    FmtConvParams m_srcParams = GetFmtConvParams(MPCVR_CF_NONE);
+    unsigned m_srcWidth = 0, m_srcHeight = 0, m_srcRectWidth = 0, m_srcRectHeight = 0;
+    int      m_srcPitch = 0;
+    unsigned m_srcLines = 0;
+    uint32_t m_srcAspectRatioX = 0, m_srcAspectRatioY = 0;
+    bool     m_srcAnamorphic = false;
+    CRect    m_srcRect;
+    ExtendedFormat m_decExFmt, m_srcExFmt;
+    bool     m_bInterlaced = false;
+    int64_t  m_rtAvgTimePerFrame = 0;
+    CRect    m_videoRect, m_windowRect, m_renderRect;
+    int      m_iRotation = 0;
+    bool     m_bFlip = false;
+    bool     m_bFinalPass = false, m_bDitherUsed = false;
+    ProcAmp  m_ProcAmp;
+    int64_t  m_rtStart = 0, m_rtEnd = 0;
+
+    // ---- device state
+    int          m_device = -1;
+    cudaStream_t m_stream = nullptr;
+    bool         m_ownStream = false;
+    bool         m_bInit = false;
+    bool         m_haveFrame = false;
+    std::string  m_lastError;
+    int          m_lastLaunches = 0;
+
+    int m_InternalTexFmt = MPCVR_SURF_BGRA8;     // DXGI_FORMAT of intermediates, UpdateTexParams
+    int m_SwapChainFmt = MPCVR_SURF_BGRA8;
+
+    Tex2D m_TexSrcVideo[3];                      // plane buffers of the source "texture"
+    SrcDesc m_src = {};                          // what the kernels read (own planes or the sample's device planes)
+    Tex2D m_TexConvertOutput, m_TexResize, m_TexsPostScale, m_BackBuffer, m_TexImage;
+    Tex2D m_UserBackBuffer;                      // caller-bound target (not owned)
+    DevArray<float4> m_dbgConvertF32; bool m_captureF32 = false;
+
+    ColorTransform m_PSConvColorData = {};
+    ColorParams    m_color = {};
+    DeviceAxis m_axisX, m_axisY;                 // filtered axes
+    DeviceAxis m_pointX, m_pointY;               // point-sampled index maps (other axis / copies)
+    DeviceAxis m_pointRX, m_pointRY;             // second pass maps of the two-pass resize
+    bool m_planDirty = true;
+    int  m_forcePath = MPCVR_PATH_AUTO, m_path = MPCVR_PATH_MULTIPASS;
+
+    mpcvr_sub_render_fn m_subRender = nullptr; mpcvr_sub_set_device_fn m_subSetDevice = nullptr; void* m_subUser = nullptr;
+
+    // ---- helpers named after their reference counterparts
+    void    UpdateTexParams(int cdepth);                         // :1143-1155
+    void    SetShaderConvertColorParams();                       // :813-887
+    void    SetShaderLuminanceParams();                          // :889-905
+    void    UpdateRenderRect();
+    int32_t UpdateTexures();                                     // :2869-2892 (sic)
+    int32_t UpdatePostScaleTexures();                            // :2894-2912 (sic)
+    int32_t UpdatePlan();
+    int32_t CopySample(const mpcvr_sample* s);                   // :2202-2597
+    int32_t MemCopyToTexSrcVideo(const uint8_t* data, int pitch);// :1213-1252
+    int32_t Process(const Tex2D& target, const CRect& srcRect, const CRect& dstRect, bool skipConvert);   // :3285-3424
+    int32_t ConvertColorPass(const Tex2D& rt);                   // :3048-3101
+    int32_t ResizeShaderPass(const Tex2D& tex, const Tex2D& rt, const CRect& srcRect, const CRect& dstRect);  // :3103-3187
+    int32_t FinalPass(const Tex2D& tex, const Tex2D& rt, const CRect& rect);                                  // :3189-3233
+    int32_t ProcessFused(const Tex2D& target, const CRect& dstRect);
+    bool    PlanFused(const Tex2D& target, const CRect& dstRect, FusedPlan& fp, const char** why);
+    int32_t DrawSubtitles(const Tex2D& rt);                      // :3235-3282
+    Tex2D&  CurrentTarget();
+    int32_t Fail(int32_t hr, const char* what, cudaError_t e = cudaSuccess);
+    bool    Cuda(cudaError_t e, const char* what);
+    int     Transfer() const;
+};
+
+}  // namespace b200vr
