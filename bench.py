@@ -200,7 +200,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     case, frames = make_frames(N_FRAMES)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=local)          # the stream the frame kernels are launched on (events are recorded on it)
+    torch.cuda.set_stream(stream)
     s = case.settings()
     vp = V.VideoProcessor(s, device=local, stream=stream.cuda_stream)
     mt = V.VideoProcessor.media_type(case.cf, case.w, case.h, case.ex)

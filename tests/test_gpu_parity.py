@@ -205,3 +205,78 @@ def test_full_size_properties_c2():
     assert (2 * (y0 - halo)) % 32 == 0
     a = out[2 * y0:2 * y1]; b = ref[2 * halo:2 * halo + 2 * (y1 - y0)]
     assert H.compare(a, b, case.backbuffer) == (0, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused single-kernel family (exact 2x interpolation upscales)
+# ------------------------------------------------------------------------------------------------
+def _check_fused(case, kind="noise", seed=0):
+    vp = _check(case, kind, seed, path=PATH_FUSED)
+    assert vp.debug_plan().path == PATH_FUSED
+    assert vp.LastFrameKernels() <= 2          # the frame kernel (+ a clear when the video rect does not cover the window)
+    return vp
+
+
+@pytest.mark.parametrize("up", ["Mitchell", "CatmullRom", "Lanczos2", "Lanczos3"])
+@pytest.mark.parametrize("variant", [O.VARIANT_D3D11, O.VARIANT_D3D9])
+def test_fused_2x_filters(up, variant):
+    _check_fused(H.Case(O.CF["P010"], 150, 70, 300, 140, H.EX_2020_PQ, up=O.UPSCALE[up], variant=variant, name="fused_" + up), "noise", 31)
+
+
+@pytest.mark.parametrize("name", ["NV12", "P010", "P016", "YUY2", "UYVY", "Y210", "AYUV", "Y410", "Y416", "YV12", "YUV422P10", "YUV444P16", "P210"])
+def test_fused_2x_formats(name):
+    _check_fused(H.Case(O.CF[name], 72, 40, 144, 80, H.EX_709, up=O.UPSCALE["Lanczos3"], name="fused_" + name), "fullnoise", 32)
+
+
+@pytest.mark.parametrize("tex,bb", [(O.TEXFMT_8INT, O.SURF_BGRA8), (O.TEXFMT_10INT, O.SURF_BGRA8), (O.TEXFMT_16FLOAT, O.SURF_BGRA8),
+                                    (O.TEXFMT_10INT, O.SURF_RGB10A2), (O.TEXFMT_16FLOAT, O.SURF_RGB10A2),
+                                    (O.TEXFMT_16FLOAT, O.SURF_RGBA16F), (O.TEXFMT_8INT, O.SURF_RGB10A2)])
+@pytest.mark.parametrize("dither", [0, 1])
+def test_fused_2x_surface_formats(tex, bb, dither):
+    _check_fused(H.Case(O.CF["P010"], 66, 34, 132, 68, H.EX_2020_PQ, backbuffer=bb, tex=tex, dither=dither, up=O.UPSCALE["Lanczos3"], name="fused_fmt"), "natural", 33)
+    _check_fused(H.Case(O.CF["YUY2"], 64, 36, 128, 72, H.EX_2020_HLG, backbuffer=bb, tex=tex, dither=dither, up=O.UPSCALE["CatmullRom"], name="fused_fmt_hlg"), "natural", 34)
+
+
+def test_fused_2x_rects():
+    _check_fused(H.Case(O.CF["NV12"], 96, 64, 160, 104, H.EX_709, src_rect=(8, 6, 88, 58), up=O.UPSCALE["Lanczos3"], name="fused_crop"), "noise", 35)
+    _check_fused(H.Case(O.CF["P010"], 64, 36, 128, 72, H.EX_2020_PQ, dst_rect=(16, 11, 144, 83), win=(160, 100), up=O.UPSCALE["Lanczos3"], name="fused_letterbox"), "noise", 36)
+    # tile edges: sizes around the 64-pixel tile
+    for w, h in ((62, 66), (64, 64), (66, 62), (130, 10), (10, 130), (2, 2)):
+        c = H.Case(O.CF["NV12"], w, h, 2 * w, 2 * h, H.EX_709, up=O.UPSCALE["Lanczos3"], name="fused_edge_%dx%d" % (w, h))
+        _check_fused(c, "noise", 37)
+    # odd crop sizes (source rect may be odd even if the frame is even)
+    _check_fused(H.Case(O.CF["NV12"], 96, 64, 2 * 77, 2 * 51, H.EX_709, src_rect=(3, 5, 80, 56), up=O.UPSCALE["CatmullRom"], name="fused_oddcrop"), "noise", 38)
+
+
+def test_fused_falls_back_when_unsupported():
+    """plans outside the fused family must still render (multipass) under PATH_AUTO, and fail loudly under PATH_FUSED"""
+    import videorenderer_b200 as V
+    case = H.Case(O.CF["NV12"], 64, 36, 96, 54, H.EX_709, up=O.UPSCALE["Lanczos3"], name="not2x")
+    codes = H.make_codes(case.cf, case.w, case.h, "noise", 1)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    vp = case.make_processor(device=0, path=0)
+    vp.ProcessSample(data=buf, pitch=pitch)
+    assert vp.debug_plan().path == PATH_MULTIPASS
+    vp = case.make_processor(device=0, path=PATH_FUSED)
+    hr = vp.ProcessSample(data=buf, pitch=pitch, check=False)
+    assert hr == V.HRESULT.E_NOTIMPL
+
+
+@pytest.mark.parametrize("kind", ["ramp", "noise", "natural"])
+def test_fused_c2_scaled(kind):
+    _check_fused(H.baseline_cases(scale=0.25)[1], kind, 39)
+
+
+def test_full_size_c2_fused_equals_multipass_and_oracle_band():
+    case = H.baseline_cases(1.0)[1]
+    codes = H.make_codes(case.cf, case.w, case.h, "natural", 21)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    _, out_f = _run_gpu(case, buf, pitch, PATH_FUSED)
+    _, out_m = _run_gpu(case, buf, pitch, PATH_MULTIPASS)
+    assert H.compare(out_f, out_m, case.backbuffer) == (0, 0)
+    y0, y1, halo = 1000, 1064, 8
+    sub = H.Case(case.cf, case.w, case.h, case.dst_w, 2 * (y1 - y0 + 2 * halo), case.ex, up=case.up,
+                 src_rect=(0, y0 - halo, case.w, y1 + halo), name="band")
+    ref = H.run_oracle(sub, planes, pitches)
+    a = out_f[2 * y0:2 * y1]; b = ref[2 * halo:2 * halo + 2 * (y1 - y0)]
+    assert H.compare(a, b, case.backbuffer) == (0, 0)

@@ -1,6 +1,288 @@
-// kernel_fused.cu -- placeholder until the fused kernel lands (next commit).
+// kernel_fused.cu -- the whole per-frame chain in ONE kernel (sm_100a):
+//   source fetch + chroma reconstruction + YUV->RGB + PQ/HLG->SDR tone-map   (ConvertColorPass)
+//   -> internal-format rounding (m_TexConvertOutput)                          kept in shared memory
+//   -> X resample, fp16 rounding (m_TexResize)                               kept in shared memory
+//   -> Y resample -> internal-format rounding (m_TexsPostScale)               kept in registers
+//   -> ordered dither + quantise (FinalPass) -> packed 128-bit / 64-bit stores to the back buffer.
+// It replaces the 4 draw calls of CDX11VideoProcessor::Process (Source/DX11VideoProcessor.cpp:3285-3424)
+// for plans whose both axes are an exact 2x interpolation upscale (Mitchell / Catmull-Rom / Lanczos2 /
+// Lanczos3); HBM traffic is the algorithmic minimum (input read once with a small halo, output written once).
+// Other plans run the multipass family (kernels_multipass.cu).  Same device arithmetic (pixel_ops.cuh), so the
+// result is bit-identical to the multipass chain and to the CPU oracle.
+//
+// Tiling: one CTA per 64x64 block of convert-surface pixels (-> 128x128 output pixels).
+//   stage A  (64+NT)^2 pixels: fetch+convert+round -> sConv[3][TH][TWP] floats        (the expensive stage)
+//   stage B  rows x 8-output blocks: NT-tap X filter from registers -> fp16 -> sX[3][TH][128] halfs
+//   stage C  column pairs x 8-row blocks: NT-tap Y filter, rounding, dither, pack, coalesced stores
+// With a 2x ratio every output pair (2j, 2j+1) uses the source window [j+b0, j+b0+NT]; there are exactly two
+// weight vectors (phase t=3/4 and t=1/4), passed as kernel parameters.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include "kernels.h"
+#include "pixel_ops.cuh"
+#include "dither32.h"
+
 namespace b200vr {
-bool FusedSupported(const FusedPlan&, const char** why) { if (why) *why = "fused kernel not built yet"; return false; }
-cudaError_t LaunchFused(const FusedPlan&, cudaStream_t, int* launches) { if (launches) *launches = 0; return cudaErrorNotSupported; }
+
+__device__ const uint16_t g_dither32_fused[1024] = { MPCVR_DITHER32_VALUES };
+
+constexpr int kCore = 64;            // convert-surface pixels per tile side
+constexpr int kOut = 2 * kCore;      // output pixels per tile side
+constexpr int kThreads = 512;
+
+struct FusedParams {
+    SrcDesc     src;
+    ColorParams color;
+    SurfDesc    out;
+    float       wE[6], wO[6];        // weights of even / odd outputs
+    int32_t     b0;                  // window start relative to j (even output); odd = b0 + 1
+    int32_t     dup_q1;
+    int32_t     w1, h1;              // convert surface size
+    int32_t     dst_x0, dst_y0;      // video rect origin in the target
+    int32_t     internal_fmt, final_pass;
+    float       Q;
+    int32_t     tiles_x, tiles_y;
+};
+
+template <int NT> struct TileGeom {
+    static constexpr int TW = kCore + NT;          // window columns of a tile
+    static constexpr int TH = kCore + NT;
+    static constexpr int TWP = (TW + 3) / 4 * 4 + 4;   // padded row pitch (floats), 16-byte aligned rows
+    static constexpr size_t conv_bytes = (size_t)3 * TH * TWP * sizeof(float);
+    static constexpr size_t x_bytes = (size_t)3 * TH * kOut * sizeof(__half);
+    static constexpr size_t smem_bytes = conv_bytes + x_bytes + 1024 * sizeof(float);
+};
+
+// ---- stage A: shared by all instantiations -------------------------------------------------------------
+__device__ __noinline__ void convert_tile(const SrcDesc& S, const ColorParams& P, int ifmt, float* __restrict__ sConv,
+                                          int TW, int TH, int TWP, int cx0, int cy0, int w1, int h1)
+{
+    const int n = TW * TH;
+    for (int idx = threadIdx.x; idx < n; idx += kThreads) {
+        const int ty = idx / TW, tx = idx - ty * TW;
+        const int cx = clampi(cx0 + tx, 0, w1 - 1), cy = clampi(cy0 + ty, 0, h1 - 1);     // CLAMP addressing of the resize taps
+        const f3 rgb = convert_color(P, fetch_yuv(S, S.rect_l + cx, S.rect_t + cy));
+        float* d = sConv + ty * TWP + tx;
+        d[0]                 = rt_roundtrip(ifmt, rgb.x);
+        d[(size_t)TH * TWP]     = rt_roundtrip(ifmt, rgb.y);
+        d[(size_t)2 * TH * TWP] = rt_roundtrip(ifmt, rgb.z);
+    }
 }
+
+// floor of a non-negative float < 2^22 as an integer (FADD.RM: exact)
+__device__ __forceinline__ uint32_t floor_u(float z) { return __float_as_uint(__fadd_rd(z, 8388608.0f)) & 0x3FFFFFu; }
+
+template <int NT, int IFMT, int OFMT, bool FINAL>
+__global__ void __launch_bounds__(kThreads, 1)
+k_fused2x(const __grid_constant__ FusedParams prm)
+{
+    using G = TileGeom<NT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float*  sConv = reinterpret_cast<float*>(smem_raw);
+    __half* sX    = reinterpret_cast<__half*>(smem_raw + G::conv_bytes);
+    float*  sDith = reinterpret_cast<float*>(smem_raw + G::conv_bytes + G::x_bytes);
+
+    const int tile_x = blockIdx.x % prm.tiles_x, tile_y = blockIdx.x / prm.tiles_x;
+    const int jx0 = tile_x * kCore, jy0 = tile_y * kCore;        // first convert-surface pixel of the tile core
+
+    for (int i = threadIdx.x; i < 1024; i += kThreads) sDith[i] = (float)g_dither32_fused[i] * 0.0009765625f;
+
+    // ---- stage A
+    convert_tile(prm.src, prm.color, IFMT, sConv, G::TW, G::TH, G::TWP, jx0 + prm.b0, jy0 + prm.b0, prm.w1, prm.h1);
+    __syncthreads();
+
+    // ---- stage B: X pass.  item = (channel, row, block of 8 outputs)
+    {
+        float wE[NT], wO[NT];
+        #pragma unroll
+        for (int k = 0; k < NT; k++) { wE[k] = prm.wE[k]; wO[k] = prm.wO[k]; }
+        constexpr int items = 3 * G::TH * (kOut / 8);
+        for (int it = threadIdx.x; it < items; it += kThreads) {
+            const int b = it % (kOut / 8), rc = it / (kOut / 8);          // rc = c*TH + row
+            const float* src = sConv + rc * G::TWP + 4 * b;
+            float v[NT + 4];
+            {
+                const float4 a = *reinterpret_cast<const float4*>(src), c = *reinterpret_cast<const float4*>(src + 4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+                if (NT == 6) { const float2 e = *reinterpret_cast<const float2*>(src + 8); v[8] = e.x; v[9] = e.y; }
+            }
+            __half2 o[4];
+            #pragma unroll
+            for (int q = 0; q < 4; q++) {
+                float e = __fmul_rn(wE[0], v[q]), d = __fmul_rn(wO[0], v[q + 1]);
+                #pragma unroll
+                for (int k = 1; k < NT; k++) {
+                    const int ke = (NT == 6 && k == 1) ? (prm.dup_q1 ? 0 : 1) : k;      // D3D11 lanczos3 re-reads tap 0's texel
+                    e = fma_rn(wE[k], v[q + ke], e);
+                    d = fma_rn(wO[k], v[q + 1 + ke], d);
+                }
+                o[q] = __floats2half2_rn(e, d);                                   // m_TexResize is RGBA16F
+            }
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&o[0]); pk.y = *reinterpret_cast<uint32_t*>(&o[1]);
+            pk.z = *reinterpret_cast<uint32_t*>(&o[2]); pk.w = *reinterpret_cast<uint32_t*>(&o[3]);
+            *reinterpret_cast<uint4*>(sX + (size_t)rc * kOut + 8 * b) = pk;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage C: Y pass + post-scale rounding + final pass + store.  item = (column pair, block of 8 rows)
+    {
+        float wE[NT], wO[NT];
+        #pragma unroll
+        for (int k = 0; k < NT; k++) { wE[k] = prm.wE[k]; wO[k] = prm.wO[k]; }
+        constexpr int items = (kOut / 2) * (kOut / 8);
+        for (int it = threadIdx.x; it < items; it += kThreads) {
+            const int cp = it % (kOut / 2), rb = it / (kOut / 2);
+            const int ox = 2 * cp, oy = 8 * rb;                                    // tile-local output coordinates
+            const int gx = prm.dst_x0 + 2 * jx0 + ox, gy = prm.dst_y0 + 2 * jy0 + oy;   // target coordinates
+            if (2 * jx0 + ox >= 2 * prm.w1 || 2 * jy0 + oy >= 2 * prm.h1) continue;
+            float res[3][8][2];
+            #pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float2 v[NT + 4];
+                const __half* col = sX + ((size_t)c * G::TH + 4 * rb) * kOut + ox;
+                #pragma unroll
+                for (int r = 0; r < NT + 4; r++) v[r] = __half22float2(*reinterpret_cast<const __half2*>(col + (size_t)r * kOut));
+                #pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    float2 e, d;
+                    e.x = __fmul_rn(wE[0], v[q].x); e.y = __fmul_rn(wE[0], v[q].y);
+                    d.x = __fmul_rn(wO[0], v[q + 1].x); d.y = __fmul_rn(wO[0], v[q + 1].y);
+                    #pragma unroll
+                    for (int k = 1; k < NT; k++) {
+                        const int ke = (NT == 6 && k == 1) ? (prm.dup_q1 ? 0 : 1) : k;
+                        e.x = fma_rn(wE[k], v[q + ke].x, e.x); e.y = fma_rn(wE[k], v[q + ke].y, e.y);
+                        d.x = fma_rn(wO[k], v[q + 1 + ke].x, d.x); d.y = fma_rn(wO[k], v[q + 1 + ke].y, d.y);
+                    }
+                    res[c][2 * q][0] = e.x; res[c][2 * q][1] = e.y; res[c][2 * q + 1][0] = d.x; res[c][2 * q + 1][1] = d.y;
+                }
+            }
+            // rows of this block
+            #pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int y = gy + r;
+                if (2 * jy0 + oy + r >= 2 * prm.h1) break;
+                uint32_t code[2][3];
+                __half hv[2][3];
+                #pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    #pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        float val = res[c][r][s];
+                        if (FINAL) {
+                            // post-scale surface (internal format) then ps_final_pass: floor(p*Q + d), UNORM write clamps
+                            const float p = (IFMT == MPCVR_SURF_RGBA16F) ? f16_roundtrip(val)
+                                          : (IFMT == MPCVR_SURF_RGB10A2 ? div_by_const_exact((float)floor_u(fma_rn(sat(val), 1023.0f, 0.5f)), 1023.0f, 1.0f / 1023.0f)
+                                                                        : div_by_const_exact((float)floor_u(fma_rn(sat(val), 255.0f, 0.5f)), 255.0f, 1.0f / 255.0f));
+                            const float dth = sDith[((y & 31) << 5) + ((gx + s) & 31)];
+                            const float t = fma_rn(p, prm.Q, dth);
+                            if (IFMT == MPCVR_SURF_RGBA16F) code[s][c] = (uint32_t)min(max((int)floorf(t), 0), (int)prm.Q);
+                            else code[s][c] = floor_u(t);
+                        } else if (OFMT == MPCVR_SURF_RGBA16F) {
+                            hv[s][c] = __float2half_rn(val);
+                        } else {
+                            code[s][c] = floor_u(fma_rn(sat(val), OFMT == MPCVR_SURF_RGB10A2 ? 1023.0f : 255.0f, 0.5f));
+                        }
+                    }
+                }
+                uint8_t* row = (uint8_t*)prm.out.ptr + (size_t)y * prm.out.pitch;
+                if (OFMT == MPCVR_SURF_RGBA16F) {
+                    uint4 o;
+                    const __half2 a0 = __halves2half2(hv[0][0], hv[0][1]), a1 = __halves2half2(hv[0][2], __float2half_rn(1.0f));
+                    const __half2 b0 = __halves2half2(hv[1][0], hv[1][1]), b1 = __halves2half2(hv[1][2], __float2half_rn(1.0f));
+                    o.x = *reinterpret_cast<const uint32_t*>(&a0); o.y = *reinterpret_cast<const uint32_t*>(&a1);
+                    o.z = *reinterpret_cast<const uint32_t*>(&b0); o.w = *reinterpret_cast<const uint32_t*>(&b1);
+                    *reinterpret_cast<uint4*>(row + (size_t)gx * 8) = o;
+                } else {
+                    uint2 o;
+                    if (OFMT == MPCVR_SURF_RGB10A2) {
+                        o.x = code[0][0] | (code[0][1] << 10) | (code[0][2] << 20) | (3u << 30);
+                        o.y = code[1][0] | (code[1][1] << 10) | (code[1][2] << 20) | (3u << 30);
+                    } else {
+                        o.x = code[0][2] | (code[0][1] << 8) | (code[0][0] << 16) | (255u << 24);
+                        o.y = code[1][2] | (code[1][1] << 8) | (code[1][0] << 16) | (255u << 24);
+                    }
+                    *reinterpret_cast<uint2*>(row + (size_t)gx * 4) = o;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static bool Periodic2x(const AxisTable& t, const float*, int) { return t.kind == SCALER_INTERP && (t.ntaps == 4 || t.ntaps == 6) && t.src_len * 2 == t.dst_len; }
+
+bool FusedSupported(const FusedPlan& p, const char** why)
+{
+    auto no = [&](const char* w) { if (why) *why = w; return false; };
+    if (!p.two_pass) return no("fused kernel needs both axes resampled");
+    if (!Periodic2x(p.ax, nullptr, 0) || !Periodic2x(p.ay, nullptr, 0)) return no("fused kernel covers exact 2x interpolation upscales");
+    if (p.ax.ntaps != p.ay.ntaps || p.ax.dup_q1 != p.ay.dup_q1) return no("axes use different filters");
+    if (p.ax.src0 != 0 || p.ay.src0 != 0) return no("convert surface origin must be 0");
+    if (p.ax.dst0 < 0 || p.ay.dst0 < 0 || p.ax.dst0 + p.ax.dst_len > p.out.w || p.ay.dst0 + p.ay.dst_len > p.out.h) return no("video rect leaves the target: clipped plans run multipass");
+    if ((p.ax.dst0 & 1) || (p.out.pitch & 15) || ((uintptr_t)p.out.ptr & 15)) return no("target alignment");
+    if (p.final_pass && p.out.fmt == MPCVR_SURF_RGBA16F) return no("no final pass into a float target");
+    return true;
+}
+
+template <int NT, int IFMT, int OFMT, bool FINAL>
+static cudaError_t LaunchT(const FusedParams& prm, cudaStream_t st)
+{
+    using G = TileGeom<NT>;
+    auto kern = k_fused2x<NT, IFMT, OFMT, FINAL>;
+    static bool configured[64] = {};     // per instantiation and device
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    kern<<<prm.tiles_x * prm.tiles_y, kThreads, G::smem_bytes, st>>>(prm);
+    return cudaGetLastError();
+}
+
+template <int NT, int IFMT>
+static cudaError_t LaunchO(const FusedParams& prm, int ofmt, bool fin, cudaStream_t st)
+{
+    if (fin) {
+        if (ofmt == MPCVR_SURF_BGRA8)   return LaunchT<NT, IFMT, MPCVR_SURF_BGRA8, true>(prm, st);
+        if (ofmt == MPCVR_SURF_RGB10A2) return LaunchT<NT, IFMT, MPCVR_SURF_RGB10A2, true>(prm, st);
+        return cudaErrorNotSupported;
+    }
+    if (ofmt == MPCVR_SURF_BGRA8)   return LaunchT<NT, IFMT, MPCVR_SURF_BGRA8, false>(prm, st);
+    if (ofmt == MPCVR_SURF_RGB10A2) return LaunchT<NT, IFMT, MPCVR_SURF_RGB10A2, false>(prm, st);
+    return LaunchT<NT, IFMT, MPCVR_SURF_RGBA16F, false>(prm, st);
+}
+
+template <int NT>
+static cudaError_t LaunchI(const FusedParams& prm, int ifmt, int ofmt, bool fin, cudaStream_t st)
+{
+    if (ifmt == MPCVR_SURF_BGRA8)   return LaunchO<NT, MPCVR_SURF_BGRA8>(prm, ofmt, fin, st);
+    if (ifmt == MPCVR_SURF_RGB10A2) return LaunchO<NT, MPCVR_SURF_RGB10A2>(prm, ofmt, fin, st);
+    return LaunchO<NT, MPCVR_SURF_RGBA16F>(prm, ofmt, fin, st);
+}
+
+cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
+{
+    FusedParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.src = p.src; prm.color = p.color; prm.out = p.out;
+    const int nt = p.ax.ntaps;
+    // the two phase vectors and the window origin come from the host table (device copy is not needed here):
+    // the caller guarantees periodicity (FusedSupported); weights are read back from the host-side mirror
+    // through the plan's host pointers.
+    for (int k = 0; k < nt; k++) { prm.wE[k] = p.wE[k]; prm.wO[k] = p.wO[k]; }
+    prm.b0 = p.b0; prm.dup_q1 = p.ax.dup_q1;
+    prm.w1 = p.ax.src_len; prm.h1 = p.ay.src_len;
+    prm.dst_x0 = p.ax.dst0; prm.dst_y0 = p.ay.dst0;
+    prm.internal_fmt = p.internal_fmt; prm.final_pass = p.final_pass; prm.Q = p.Q;
+    prm.tiles_x = (prm.w1 + kCore - 1) / kCore; prm.tiles_y = (prm.h1 + kCore - 1) / kCore;
+    if (launches) *launches = 1;
+    if (nt == 6) return LaunchI<6>(prm, p.internal_fmt, p.out.fmt, p.final_pass != 0, st);
+    return LaunchI<4>(prm, p.internal_fmt, p.out.fmt, p.final_pass != 0, st);
+}
+
+}  // namespace b200vr

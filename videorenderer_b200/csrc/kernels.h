@@ -30,6 +30,9 @@ struct FusedPlan {
     int32_t     final_pass;      // dither + quantise at the end
     int32_t     two_pass;        // both axes resample -> fp16 intermediate (m_TexResize)
     float       Q;               // 255 / 1023
+    // exact-2x plans: the two weight vectors (even / odd outputs) and the window origin relative to j = i/2
+    float       wE[8], wO[8];
+    int32_t     b0;
 };
 bool        FusedSupported(const FusedPlan& p, const char** why);
 cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches);
