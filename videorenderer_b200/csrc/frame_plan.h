@@ -36,6 +36,12 @@ struct ColorParams {
     float lum_scale;                // 10000 / iSDRDisplayNits
     float sdr_gamma;                // toLinear exponent of the BT.2020 SDR branch
     int32_t transfer;               // Transfer
+    // compile-time constants of the HLSL (fxc folds them in fp32); evaluated once on the host in the same fp32 order
+    float inv_m1, inv_m2;           // 1.0/ST2084_m1, 1.0/ST2084_m2                      (st2084.hlsl:11,13)
+    float inv_gamma22;              // 1.0/2.2                                           (Source/Shaders.cpp:921)
+    float hable_cb, hable_de, hable_df, hable_ef, hable_rdiv;   // C*B, D*E, D*F, E/F, 1/hable(4.8)   (hdr_tone_mapping.hlsl:3-12)
+    float hlg_ra;                   // 1/B67_a                                           (hlg.hlsl:9)
+    float r1000;                    // 1/1000 (LinearToST2084 divider)                   (Source/Shaders.cpp:866)
 };
 
 struct SurfDesc {                   // a render target / shader resource of the pass chain

@@ -53,42 +53,115 @@ template <int NT> struct TileGeom {
     static constexpr size_t smem_bytes = conv_bytes + x_bytes + 1024 * sizeof(float);
 };
 
-// ---- stage A: shared by all instantiations -------------------------------------------------------------
-__device__ __noinline__ void convert_tile(const SrcDesc& S, const ColorParams& P, int ifmt, float* __restrict__ sConv,
-                                          int TW, int TH, int TWP, int cx0, int cy0, int w1, int h1)
+// ---- stage A -----------------------------------------------------------------------------------------
+// generic: any layout / chroma mode / transfer through the shared device functions (runtime switches)
+__device__ __forceinline__ void convert_tile_generic(const FusedParams& prm, const int ifmt, float* __restrict__ sConv,
+                                                     const int TW, const int TH, const int TWP, const int cx0, const int cy0)
 {
     const int n = TW * TH;
     for (int idx = threadIdx.x; idx < n; idx += kThreads) {
         const int ty = idx / TW, tx = idx - ty * TW;
-        const int cx = clampi(cx0 + tx, 0, w1 - 1), cy = clampi(cy0 + ty, 0, h1 - 1);     // CLAMP addressing of the resize taps
-        const f3 rgb = convert_color(P, fetch_yuv(S, S.rect_l + cx, S.rect_t + cy));
+        const int cx = clampi(cx0 + tx, 0, prm.w1 - 1), cy = clampi(cy0 + ty, 0, prm.h1 - 1);     // CLAMP addressing of the resize taps
+        const f3 rgb = convert_color<-1>(prm.color, fetch_yuv(prm.src, prm.src.rect_l + cx, prm.src.rect_t + cy));
         float* d = sConv + ty * TWP + tx;
-        d[0]                 = rt_roundtrip(ifmt, rgb.x);
-        d[(size_t)TH * TWP]     = rt_roundtrip(ifmt, rgb.y);
-        d[(size_t)2 * TH * TWP] = rt_roundtrip(ifmt, rgb.z);
+        d[0]            = rt_roundtrip(ifmt, rgb.x);
+        d[TH * TWP]     = rt_roundtrip(ifmt, rgb.y);
+        d[2 * TH * TWP] = rt_roundtrip(ifmt, rgb.z);
     }
 }
+
+// fast: bi-planar source (NV12 / P010 / P016 / P210 / P216) with bilinear chroma (the default, CHROMA_Bilinear):
+// the chroma texels a tile needs are converted to float once and staged in shared memory (aliasing the X-pass
+// buffer, which is idle during stage A); every pixel then does 4 shared-memory reads + 3 lerps per component.
+template <int BYTES, int TR>
+__device__ __forceinline__ void convert_tile_biplanar(const FusedParams& prm, const int ifmt, float* __restrict__ sConv,
+                                                      float2* __restrict__ sUV, const int TW, const int TH, const int TWP,
+                                                      const int cx0, const int cy0)
+{
+    const SrcDesc& S = prm.src;
+    // quarter-texel sample position of luma (sx, sy): qx = 2*sx + ox, qy = my*sy + oy  (pixel_ops.cuh fetch_planar, bilinear branch)
+    int ox, oy, my;
+    if (S.subsampling == 420) {
+        my = 2;
+        if (S.siting == ChromaSub_Cosited)    { ox = 0;  oy = 0;  }
+        else if (S.siting == ChromaSub_MPEG1) { ox = -1; oy = -1; }
+        else                                  { ox = 0;  oy = -1; }
+    } else { my = 4; ox = 0; oy = 0; }
+    const int lx_lo = S.rect_l + clampi(cx0, 0, prm.w1 - 1), lx_hi = S.rect_l + clampi(cx0 + TW - 1, 0, prm.w1 - 1);
+    const int ly_lo = S.rect_t + clampi(cy0, 0, prm.h1 - 1), ly_hi = S.rect_t + clampi(cy0 + TH - 1, 0, prm.h1 - 1);
+    const int ux0 = (2 * lx_lo + ox) >> 2, uw = (((2 * lx_hi + ox) >> 2) + 1) - ux0 + 1;
+    const int uy0 = (my * ly_lo + oy) >> 2, uh = (((my * ly_hi + oy) >> 2) + 1) - uy0 + 1;
+    const int uwp = uw | 1;                                          // odd pitch (in float2 units) spreads rows over banks
+    for (int i = threadIdx.x; i < uw * uh; i += kThreads) {
+        const int uy = i / uw, ux = i - uy * uw;
+        const int tx = clampi(ux0 + ux, 0, S.cw - 1), ty = clampi(uy0 + uy, 0, S.ch - 1);      // sampler CLAMP
+        const uint8_t* row = S.pl[1] + (uint32_t)(ty * S.pitch[1]);
+        float2 c;
+        if (BYTES == 1) { const uint32_t v = __ldg((const uint16_t*)row + tx); c.x = unorm8(v & 255u); c.y = unorm8(v >> 8); }
+        else            { const uint32_t v = __ldg((const uint32_t*)row + tx); c.x = unorm16(v & 0xFFFFu); c.y = unorm16(v >> 16); }
+        sUV[uy * uwp + ux] = c;
+    }
+    __syncthreads();
+    const int n = TW * TH;
+    for (int idx = threadIdx.x; idx < n; idx += kThreads) {
+        const int ty = idx / TW, tx = idx - ty * TW;
+        const int sx = S.rect_l + clampi(cx0 + tx, 0, prm.w1 - 1), sy = S.rect_t + clampi(cy0 + ty, 0, prm.h1 - 1);
+        f3 yuv;
+        {
+            const uint8_t* row = S.pl[0] + (uint32_t)(sy * S.pitch[0]);
+            yuv.x = (BYTES == 1) ? unorm8(__ldg(row + sx)) : unorm16(__ldg((const uint16_t*)row + sx));
+        }
+        const int qx = 2 * sx + ox, qy = my * sy + oy;
+        const float fx = (float)(qx & 3) * 0.25f, fy = (float)(qy & 3) * 0.25f;
+        const float2* t = sUV + ((qy >> 2) - uy0) * uwp + ((qx >> 2) - ux0);
+        const float2 c00 = t[0], c10 = t[1], c01 = t[uwp], c11 = t[uwp + 1];
+        yuv.y = lerp_mad(lerp_mad(c00.x, c10.x, fx), lerp_mad(c01.x, c11.x, fx), fy);
+        yuv.z = lerp_mad(lerp_mad(c00.y, c10.y, fx), lerp_mad(c01.y, c11.y, fx), fy);
+        const f3 rgb = convert_color<TR>(prm.color, yuv);
+        float* d = sConv + ty * TWP + tx;
+        d[0]            = rt_roundtrip(ifmt, rgb.x);
+        d[TH * TWP]     = rt_roundtrip(ifmt, rgb.y);
+        d[2 * TH * TWP] = rt_roundtrip(ifmt, rgb.z);
+    }
+}
+
+// which stage A a kernel instantiation carries
+enum { CONV_GENERIC = 0, CONV_BIPLANAR16_PQ = 1, CONV_BIPLANAR8_NONE = 2, CONV_BIPLANAR16_ANY = 3, CONV_BIPLANAR8_ANY = 4 };
+// which (internal, target, final) combination is fixed at compile time
+enum { SPEC_RUNTIME = 0, SPEC_10_BGRA8_DITHER = 1, SPEC_8_BGRA8 = 2 };
 
 // floor of a non-negative float < 2^22 as an integer (FADD.RM: exact)
 __device__ __forceinline__ uint32_t floor_u(float z) { return __float_as_uint(__fadd_rd(z, 8388608.0f)) & 0x3FFFFFu; }
 
-template <int NT, int IFMT, int OFMT, bool FINAL>
+template <int NT, int SPEC, int CONV>
 __global__ void __launch_bounds__(kThreads, 1)
 k_fused2x(const __grid_constant__ FusedParams prm)
 {
     using G = TileGeom<NT>;
+    const int  IFMT  = SPEC == SPEC_10_BGRA8_DITHER ? (int)MPCVR_SURF_RGB10A2 : (SPEC == SPEC_8_BGRA8 ? (int)MPCVR_SURF_BGRA8 : prm.internal_fmt);
+    const int  OFMT  = SPEC != SPEC_RUNTIME ? (int)MPCVR_SURF_BGRA8 : prm.out.fmt;
+    const bool FINAL = SPEC == SPEC_10_BGRA8_DITHER ? true : (SPEC == SPEC_8_BGRA8 ? false : prm.final_pass != 0);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float*  sConv = reinterpret_cast<float*>(smem_raw);
     __half* sX    = reinterpret_cast<__half*>(smem_raw + G::conv_bytes);
     float*  sDith = reinterpret_cast<float*>(smem_raw + G::conv_bytes + G::x_bytes);
 
+    const bool dup = prm.dup_q1 != 0;
     const int tile_x = blockIdx.x % prm.tiles_x, tile_y = blockIdx.x / prm.tiles_x;
     const int jx0 = tile_x * kCore, jy0 = tile_y * kCore;        // first convert-surface pixel of the tile core
 
     for (int i = threadIdx.x; i < 1024; i += kThreads) sDith[i] = (float)g_dither32_fused[i] * 0.0009765625f;
 
     // ---- stage A
-    convert_tile(prm.src, prm.color, IFMT, sConv, G::TW, G::TH, G::TWP, jx0 + prm.b0, jy0 + prm.b0, prm.w1, prm.h1);
+    {
+        float2* sUV = reinterpret_cast<float2*>(sX);                 // aliases the (still unused) X-pass buffer
+        const int cx0 = jx0 + prm.b0, cy0 = jy0 + prm.b0;
+        if (CONV == CONV_BIPLANAR16_PQ)        convert_tile_biplanar<2, TRANSFER_PQ_TO_SDR>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
+        else if (CONV == CONV_BIPLANAR8_NONE)  convert_tile_biplanar<1, TRANSFER_NONE>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
+        else if (CONV == CONV_BIPLANAR16_ANY)  convert_tile_biplanar<2, -1>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
+        else if (CONV == CONV_BIPLANAR8_ANY)   convert_tile_biplanar<1, -1>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
+        else                                   convert_tile_generic(prm, IFMT, sConv, G::TW, G::TH, G::TWP, cx0, cy0);
+    }
     __syncthreads();
 
     // ---- stage B: X pass.  item = (channel, row, block of 8 outputs)
@@ -112,9 +185,11 @@ k_fused2x(const __grid_constant__ FusedParams prm)
                 float e = __fmul_rn(wE[0], v[q]), d = __fmul_rn(wO[0], v[q + 1]);
                 #pragma unroll
                 for (int k = 1; k < NT; k++) {
-                    const int ke = (NT == 6 && k == 1) ? (prm.dup_q1 ? 0 : 1) : k;      // D3D11 lanczos3 re-reads tap 0's texel
-                    e = fma_rn(wE[k], v[q + ke], e);
-                    d = fma_rn(wO[k], v[q + 1 + ke], d);
+                    // D3D11 lanczos3 re-reads tap 0's texel for tap 1 (ps_interpolation_lanczos3.hlsl:33-34)
+                    const float te = (NT == 6 && k == 1) ? (dup ? v[q] : v[q + 1]) : v[q + k];
+                    const float to = (NT == 6 && k == 1) ? (dup ? v[q + 1] : v[q + 2]) : v[q + 1 + k];
+                    e = fma_rn(wE[k], te, e);
+                    d = fma_rn(wO[k], to, d);
                 }
                 o[q] = __floats2half2_rn(e, d);                                   // m_TexResize is RGBA16F
             }
@@ -151,9 +226,10 @@ k_fused2x(const __grid_constant__ FusedParams prm)
                     d.x = __fmul_rn(wO[0], v[q + 1].x); d.y = __fmul_rn(wO[0], v[q + 1].y);
                     #pragma unroll
                     for (int k = 1; k < NT; k++) {
-                        const int ke = (NT == 6 && k == 1) ? (prm.dup_q1 ? 0 : 1) : k;
-                        e.x = fma_rn(wE[k], v[q + ke].x, e.x); e.y = fma_rn(wE[k], v[q + ke].y, e.y);
-                        d.x = fma_rn(wO[k], v[q + 1 + ke].x, d.x); d.y = fma_rn(wO[k], v[q + 1 + ke].y, d.y);
+                        const float2 te = (NT == 6 && k == 1) ? (dup ? v[q] : v[q + 1]) : v[q + k];
+                        const float2 to = (NT == 6 && k == 1) ? (dup ? v[q + 1] : v[q + 2]) : v[q + 1 + k];
+                        e.x = fma_rn(wE[k], te.x, e.x); e.y = fma_rn(wE[k], te.y, e.y);
+                        d.x = fma_rn(wO[k], to.x, d.x); d.y = fma_rn(wO[k], to.y, d.y);
                     }
                     res[c][2 * q][0] = e.x; res[c][2 * q][1] = e.y; res[c][2 * q + 1][0] = d.x; res[c][2 * q + 1][1] = d.y;
                 }
@@ -228,11 +304,11 @@ bool FusedSupported(const FusedPlan& p, const char** why)
     return true;
 }
 
-template <int NT, int IFMT, int OFMT, bool FINAL>
+template <int NT, int SPEC, int CONV>
 static cudaError_t LaunchT(const FusedParams& prm, cudaStream_t st)
 {
     using G = TileGeom<NT>;
-    auto kern = k_fused2x<NT, IFMT, OFMT, FINAL>;
+    auto kern = k_fused2x<NT, SPEC, CONV>;
     static bool configured[64] = {};     // per instantiation and device
     int dev = 0; cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
@@ -244,25 +320,24 @@ static cudaError_t LaunchT(const FusedParams& prm, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int NT, int IFMT>
-static cudaError_t LaunchO(const FusedParams& prm, int ofmt, bool fin, cudaStream_t st)
+template <int NT, int SPEC>
+static cudaError_t LaunchC(const FusedParams& prm, int conv, cudaStream_t st)
 {
-    if (fin) {
-        if (ofmt == MPCVR_SURF_BGRA8)   return LaunchT<NT, IFMT, MPCVR_SURF_BGRA8, true>(prm, st);
-        if (ofmt == MPCVR_SURF_RGB10A2) return LaunchT<NT, IFMT, MPCVR_SURF_RGB10A2, true>(prm, st);
-        return cudaErrorNotSupported;
+    switch (conv) {
+    case CONV_BIPLANAR16_PQ:   return LaunchT<NT, SPEC, CONV_BIPLANAR16_PQ>(prm, st);
+    case CONV_BIPLANAR8_NONE:  return LaunchT<NT, SPEC, CONV_BIPLANAR8_NONE>(prm, st);
+    case CONV_BIPLANAR16_ANY:  return LaunchT<NT, SPEC, CONV_BIPLANAR16_ANY>(prm, st);
+    case CONV_BIPLANAR8_ANY:   return LaunchT<NT, SPEC, CONV_BIPLANAR8_ANY>(prm, st);
+    default:                   return LaunchT<NT, SPEC, CONV_GENERIC>(prm, st);
     }
-    if (ofmt == MPCVR_SURF_BGRA8)   return LaunchT<NT, IFMT, MPCVR_SURF_BGRA8, false>(prm, st);
-    if (ofmt == MPCVR_SURF_RGB10A2) return LaunchT<NT, IFMT, MPCVR_SURF_RGB10A2, false>(prm, st);
-    return LaunchT<NT, IFMT, MPCVR_SURF_RGBA16F, false>(prm, st);
 }
 
 template <int NT>
-static cudaError_t LaunchI(const FusedParams& prm, int ifmt, int ofmt, bool fin, cudaStream_t st)
+static cudaError_t LaunchS(const FusedParams& prm, int spec, int conv, cudaStream_t st)
 {
-    if (ifmt == MPCVR_SURF_BGRA8)   return LaunchO<NT, MPCVR_SURF_BGRA8>(prm, ofmt, fin, st);
-    if (ifmt == MPCVR_SURF_RGB10A2) return LaunchO<NT, MPCVR_SURF_RGB10A2>(prm, ofmt, fin, st);
-    return LaunchO<NT, MPCVR_SURF_RGBA16F>(prm, ofmt, fin, st);
+    if (spec == SPEC_10_BGRA8_DITHER) return LaunchC<NT, SPEC_10_BGRA8_DITHER>(prm, conv, st);
+    if (spec == SPEC_8_BGRA8)         return LaunchC<NT, SPEC_8_BGRA8>(prm, conv, st);
+    return LaunchC<NT, SPEC_RUNTIME>(prm, conv, st);
 }
 
 cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
@@ -281,8 +356,18 @@ cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
     prm.internal_fmt = p.internal_fmt; prm.final_pass = p.final_pass; prm.Q = p.Q;
     prm.tiles_x = (prm.w1 + kCore - 1) / kCore; prm.tiles_y = (prm.h1 + kCore - 1) / kCore;
     if (launches) *launches = 1;
-    if (nt == 6) return LaunchI<6>(prm, p.internal_fmt, p.out.fmt, p.final_pass != 0, st);
-    return LaunchI<4>(prm, p.internal_fmt, p.out.fmt, p.final_pass != 0, st);
+    int spec = SPEC_RUNTIME;
+    if (p.internal_fmt == MPCVR_SURF_RGB10A2 && p.out.fmt == MPCVR_SURF_BGRA8 && p.final_pass) spec = SPEC_10_BGRA8_DITHER;
+    else if (p.internal_fmt == MPCVR_SURF_BGRA8 && p.out.fmt == MPCVR_SURF_BGRA8 && !p.final_pass) spec = SPEC_8_BGRA8;
+    int conv = CONV_GENERIC;
+    const SrcDesc& S = p.src;
+    if (S.layout == LAYOUT_BIPLANAR && S.chroma_mode == MPCVR_CHROMA_Bilinear && !S.deint_blend && S.lsb_shift == 0 &&
+        (S.subsampling == 420 || S.subsampling == 422)) {
+        if (S.bytes == 2) conv = (p.color.transfer == TRANSFER_PQ_TO_SDR) ? CONV_BIPLANAR16_PQ : CONV_BIPLANAR16_ANY;
+        else              conv = (p.color.transfer == TRANSFER_NONE) ? CONV_BIPLANAR8_NONE : CONV_BIPLANAR8_ANY;
+    }
+    if (nt == 6) return LaunchS<6>(prm, spec, conv, st);
+    return LaunchS<4>(prm, spec, conv, st);
 }
 
 }  // namespace b200vr

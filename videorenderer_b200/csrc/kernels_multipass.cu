@@ -21,7 +21,7 @@ k_convert(const __grid_constant__ SrcDesc S, const __grid_constant__ ColorParams
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= out.w || y >= out.h) return;
     const f3 yuv = fetch_yuv(S, S.rect_l + x, S.rect_t + y);
-    const f3 rgb = convert_color(P, yuv);
+    const f3 rgb = convert_color<-1>(P, yuv);
     if (dbg) dbg[(size_t)y * out.w + x] = make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
     surf_store(out, x, y, rgb);
 }

@@ -220,35 +220,36 @@ __device__ __forceinline__ f3 fetch_yuv(const SrcDesc& S, int sx, int sy)
 #define ST2084_C2 18.8515625f
 #define ST2084_C3 18.6875f
 
-__device__ __forceinline__ float st2084_to_linear(float v, float factor)          // st2084.hlsl:9-16
+// quotients of the tone-map: operands are in safe exponent ranges (den in [0.16, 19], numerators in [0, 1e3])
+__device__ __forceinline__ float st2084_to_linear(const ColorParams& P, float v, float factor)          // st2084.hlsl:9-16
 {
-    const float a   = powr(v, __fdiv_rn(1.0f, ST2084_M2));
+    const float a   = powr(v, P.inv_m2);
     const float num = fmaxf(__fsub_rn(a, ST2084_C1), 0.0f);
     const float den = fma_rn(-ST2084_C3, a, ST2084_C2);
-    const float b   = __fdiv_rn(num, den);
-    return __fmul_rn(powr(b, __fdiv_rn(1.0f, ST2084_M1)), factor);
+    const float b   = div_rn_safe(num, den);
+    return __fmul_rn(powr(b, P.inv_m1), factor);
 }
 
-__device__ __forceinline__ float linear_to_st2084(float v, float divider)         // st2084.hlsl:18-25
+__device__ __forceinline__ float linear_to_st2084(float v, float rdivider)                              // st2084.hlsl:18-25
 {
-    v = __fmul_rn(v, __fdiv_rn(1.0f, divider));
+    v = __fmul_rn(v, rdivider);
     const float p = powr(v, ST2084_M1);
-    const float q = __fdiv_rn(fma_rn(ST2084_C2, p, ST2084_C1), fma_rn(ST2084_C3, p, 1.0f));
+    const float q = div_rn_safe(fma_rn(ST2084_C2, p, ST2084_C1), fma_rn(ST2084_C3, p, 1.0f));
     return powr(q, ST2084_M2);
 }
 
-__device__ __forceinline__ float hable(float x)                                   // hdr_tone_mapping.hlsl:1-6
+__device__ __forceinline__ float hable(const ColorParams& P, float x)                                   // hdr_tone_mapping.hlsl:1-6
 {
-    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
-    const float CB = __fmul_rn(C, B), DE = __fmul_rn(D, E), DF = __fmul_rn(D, F), EF = __fdiv_rn(E, F);
-    return __fsub_rn(__fdiv_rn(fma_rn(x, fma_rn(A, x, CB), DE), fma_rn(x, fma_rn(A, x, B), DF)), EF);
+    const float A = 0.15f, B = 0.50f;
+    return __fsub_rn(div_rn_safe(fma_rn(x, fma_rn(A, x, P.hable_cb), P.hable_de), fma_rn(x, fma_rn(A, x, B), P.hable_df)), P.hable_ef);
 }
 
-__device__ __forceinline__ float inverse_hlg(float x)                             // hlg.hlsl:1-11
+__device__ __forceinline__ float inverse_hlg(const ColorParams& P, float x)                             // hlg.hlsl:1-11
 {
-    const float a = 0.17883277f, b = 0.28466892f, c = 0.55991073f;
-    if (x <= 0.5f) return __fmul_rn(__fmul_rn(x, x), 4.0f);
-    return __fadd_rn(ex2(__fmul_rn(__fmul_rn(__fsub_rn(x, c), __fdiv_rn(1.0f, a)), 1.44269504f)), b);
+    const float b = 0.28466892f, c = 0.55991073f;
+    const float lo = __fmul_rn(__fmul_rn(x, x), 4.0f);
+    const float hi = __fadd_rn(ex2(__fmul_rn(__fmul_rn(__fsub_rn(x, c), P.hlg_ra), 1.44269504f)), b);
+    return (x <= 0.5f) ? lo : hi;
 }
 
 __device__ __forceinline__ f3 mat3_apply(const float m[3][3], f3 v)               // mul(float3x3, float3): three dp3
@@ -260,33 +261,33 @@ __device__ __forceinline__ f3 mat3_apply(const float m[3][3], f3 v)             
     return r;
 }
 
-// convert shader body; returns the value before the render-target write
+// convert shader body; returns the value before the render-target write.  TR >= 0 fixes the transfer at compile time.
+template <int TR = -1>
 __device__ __forceinline__ f3 convert_color(const ColorParams& P, f3 yuv)
 {
+    const int tr = (TR >= 0) ? TR : P.transfer;
     f3 c = mat3_apply(P.cm, yuv);                                                   // Source/Shaders.cpp:820
     c.x = __fadd_rn(c.x, P.cc[0]); c.y = __fadd_rn(c.y, P.cc[1]); c.z = __fadd_rn(c.z, P.cc[2]);
-    if (P.transfer == TRANSFER_NONE) return c;
-    if (P.transfer == TRANSFER_SDR_2020) {                                          // :892-915
+    if (tr == TRANSFER_NONE) return c;
+    if (tr == TRANSFER_SDR_2020) {                                                  // :892-915
         f3 l; l.x = powr(sat(c.x), P.sdr_gamma); l.y = powr(sat(c.y), P.sdr_gamma); l.z = powr(sat(c.z), P.sdr_gamma);
         c = mat3_apply(P.gamut, l);
     } else {
-        if (P.transfer == TRANSFER_HLG_TO_SDR) {                                    // :862-868
-            f3 l; l.x = inverse_hlg(sat(c.x)); l.y = inverse_hlg(sat(c.y)); l.z = inverse_hlg(sat(c.z));
+        if (tr == TRANSFER_HLG_TO_SDR) {                                            // :862-868
+            f3 l; l.x = inverse_hlg(P, sat(c.x)); l.y = inverse_hlg(P, sat(c.y)); l.z = inverse_hlg(P, sat(c.z));
             const float dt = fma_rn(0.0593f, l.z, fma_rn(0.6780f, l.y, __fmul_rn(0.2627f, l.x)));   // hlg.hlsl:16-17
             const float g  = powr(__fmul_rn(2000.0f, dt), 0.2f);
-            c.x = linear_to_st2084(__fmul_rn(l.x, g), 1000.0f);
-            c.y = linear_to_st2084(__fmul_rn(l.y, g), 1000.0f);
-            c.z = linear_to_st2084(__fmul_rn(l.z, g), 1000.0f);
+            c.x = linear_to_st2084(__fmul_rn(l.x, g), P.r1000);
+            c.y = linear_to_st2084(__fmul_rn(l.y, g), P.r1000);
+            c.z = linear_to_st2084(__fmul_rn(l.z, g), P.r1000);
         }
-        const float rdiv = __fdiv_rn(1.0f, hable(4.8f));                            // x / HABLE_DIV, hdr_tone_mapping.hlsl:10-12
-        f3 h;
-        h.x = __fmul_rn(hable(st2084_to_linear(sat(c.x), P.lum_scale)), rdiv);      // :870-880
-        h.y = __fmul_rn(hable(st2084_to_linear(sat(c.y), P.lum_scale)), rdiv);
-        h.z = __fmul_rn(hable(st2084_to_linear(sat(c.z), P.lum_scale)), rdiv);
+        f3 h;                                                                       // :870-880; x / HABLE_DIV -> x * (1/HABLE_DIV)
+        h.x = __fmul_rn(hable(P, st2084_to_linear(P, sat(c.x), P.lum_scale)), P.hable_rdiv);
+        h.y = __fmul_rn(hable(P, st2084_to_linear(P, sat(c.y), P.lum_scale)), P.hable_rdiv);
+        h.z = __fmul_rn(hable(P, st2084_to_linear(P, sat(c.z), P.lum_scale)), P.hable_rdiv);
         c = mat3_apply(P.gamut, h);                                                 // :881
     }
-    const float ig = __fdiv_rn(1.0f, 2.2f);                                         // :917-923
-    c.x = powr(sat(c.x), ig); c.y = powr(sat(c.y), ig); c.z = powr(sat(c.z), ig);
+    c.x = powr(sat(c.x), P.inv_gamma22); c.y = powr(sat(c.y), P.inv_gamma22); c.z = powr(sat(c.z), P.inv_gamma22);   // :917-923
     return c;
 }
 

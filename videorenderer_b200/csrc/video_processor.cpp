@@ -267,6 +267,16 @@ void CB200VideoProcessor::SetShaderConvertColorParams()
     default: g = 2.2f; break;
     }
     m_color.sdr_gamma = g;
+    // shader literals, folded in fp32 like fxc does (host code is built with -ffp-contract=off; fmaf = the shader's mad)
+    m_color.inv_m1 = 1.0f / 0.1593017578125f; m_color.inv_m2 = 1.0f / 78.84375f; m_color.inv_gamma22 = 1.0f / 2.2f;
+    {
+        const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+        m_color.hable_cb = C * B; m_color.hable_de = D * E; m_color.hable_df = D * F; m_color.hable_ef = E / F;
+        const float x = 4.8f;
+        const float hdiv = std::fmaf(x, std::fmaf(A, x, m_color.hable_cb), m_color.hable_de) / std::fmaf(x, std::fmaf(A, x, B), m_color.hable_df) - m_color.hable_ef;
+        m_color.hable_rdiv = 1.0f / hdiv;
+    }
+    m_color.hlg_ra = 1.0f / 0.17883277f; m_color.r1000 = 1.0f / 1000.0f;
     m_planDirty = true;
 }
 
