@@ -185,7 +185,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    from videorenderer_b200 import streams
+    rank, world, local = streams.rank_info()
     if args.impl == "reference":
         return impl_reference(args, rank, world)
 
@@ -230,10 +231,7 @@ def main():
         assert hr == 0
 
     def barrier():
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
+        streams.barrier(dist, torch.cuda.synchronize)
 
     def timed(fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -243,9 +241,7 @@ def main():
             fn(i)
         e1.record(stream)
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if dist:
-            t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        ms = streams.max_over_ranks(e0.elapsed_time(e1), dist, device="cuda")
         barrier()
         return ms
 
@@ -256,7 +252,7 @@ def main():
     sampler = ClockSampler(local); sampler.start(); time.sleep(0.15)
     ms = timed(step_device, args.steps)
     clocks = sampler.finish()
-    fps = args.steps * world / (ms * 1e-3)
+    fps = streams.aggregate_fps(args.steps, world, ms)
 
     e2e_steps = max(3, min(args.steps, 40))
     for i in range(3):
@@ -266,7 +262,7 @@ def main():
     wall_e2e = time.perf_counter() - t0
     ms_e2e = max(ms_e2e, 0.0)
     # the e2e loop synchronises every step (read back), so host wall clock and device events agree; use the events
-    e2e_fps = e2e_steps * world / (ms_e2e * 1e-3)
+    e2e_fps = streams.aggregate_fps(e2e_steps, world, ms_e2e)
 
     pk, pk_src = peaks()
     kernel_ms = ms / args.steps                       # one frame kernel per step on the fused path

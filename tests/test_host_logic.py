@@ -1,0 +1,182 @@
+"""Host-side logic of the product through the C ABI on a planning-only instance (no GPU needed):
+colour matrices, resize tables, pass-chain decisions, media-type rules -- against the oracle and the goldens."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+import orclib as O
+import videorenderer_b200 as V
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _bits(a):
+    return [int(v) for v in np.asarray(a, np.float32).ravel().view(np.uint32)]
+
+
+def _vp(case):
+    return case.make_processor(device=-1)
+
+
+def test_settings_default_matches_reference_SetDefault():
+    s = V.Settings.default()
+    # Settings_t::SetDefault, Source/IVideoRenderer.h:140-185 (Windows 10 branch)
+    exp = dict(bUseD3D11=1, bShowStats=0, iResizeStats=0, iTexFormat=0, VPFmts_bNV12=1, VPFmts_bP01x=1, VPFmts_bYUY2=1, VPFmts_bOther=1,
+               iVPDeinterlacing=1, bDeintDouble=1, bVPScaling=1, iVPSuperRes=0, bVPRTXVideoHDR=0, iChromaScaling=1, iUpscaling=2, iDownscaling=2,
+               bInterpolateAt50pct=1, bUseDither=1, bDeintBlend=0, iSwapEffect=1, bExclusiveFS=0, bVBlankBeforePresent=0, bAdjustPresentTime=1,
+               bReinitByDisplay=0, bHdrPreferDoVi=0, bHdrPassthrough=1, iHdrToggleDisplay=0, iHdrOsdBrightness=0, bConvertToSdr=1,
+               iSDRDisplayNits=125, bHdrLocalToneMapping=0, iHdrLocalToneMappingType=1, iHdrDisplayMaxNits=1000)
+    assert {n: getattr(s, n) for n, _ in s._fields_} == exp
+
+
+def test_color_transform_bits_equal_reference_golden_and_oracle():
+    kat = json.load(open(os.path.join(G, "kat_matrices.json")))
+    cases = {"bt709_tv_8": (O.CF["NV12"], H.EX_709), "bt2020nc_tv_16": (O.CF["P010"], H.EX_2020_PQ),
+             "bt601_tv_8": (O.CF["YUY2"], O.exfmt(range_=2, matrix=2, prim=2, trc=5)),
+             "bt709_pc_8": (O.CF["NV12"], O.exfmt(chroma=5, range_=1, matrix=1, prim=2, trc=5)),
+             "bt2020nc_tv_10": (O.CF["YUV420P10"], H.EX_2020_PQ), "ycgco_pc_8": (O.CF["YUV444P8"], O.exfmt(range_=1, matrix=7, prim=2, trc=5)),
+             "smpte240m_tv_8": (O.CF["NV12"], O.exfmt(chroma=5, range_=2, matrix=3, prim=2, trc=5))}
+    for name, (cf, ex) in cases.items():
+        vp = _vp(H.Case(cf, 64, 36, 64, 36, ex))
+        m, c, g, lum = vp.debug_color_params()
+        assert _bits(m) == kat["matrices"][name]["m_bits"], name
+        assert _bits(c) == kat["matrices"][name]["c_bits"], name
+        assert _bits(g) == kat["gamut_2020_to_709_bits"]
+        assert lum == 80.0
+    for name, e in kat["procamp_bt709_tv_8"].items():
+        vp = _vp(H.Case(O.CF["NV12"], 64, 36, 64, 36, H.EX_709, procamp=dict(brightness=e["brightness"], contrast=e["contrast"], hue=e["hue"], saturation=e["saturation"])))
+        m, c, _, _ = vp.debug_color_params()
+        assert _bits(m) == e["m_bits"] and _bits(c) == e["c_bits"], name
+    # random procamp against the oracle restatement
+    rng = np.random.Generator(np.random.PCG64(2))
+    for _ in range(20):
+        pa = dict(brightness=float(rng.uniform(-100, 100)), contrast=float(rng.uniform(0, 2)), hue=float(rng.uniform(-180, 180)), saturation=float(rng.uniform(0, 2)))
+        vp = _vp(H.Case(O.CF["P010"], 64, 36, 64, 36, H.EX_2020_PQ, procamp=pa))
+        m, c, _, _ = vp.debug_color_params()
+        om, oc = O.csp_matrix(H.EX_2020_PQ, 16, **{k: np.float32(v) for k, v in pa.items()})
+        assert _bits(m) == _bits(om) and _bits(c) == _bits(oc)
+
+
+def test_luminance_scale_follows_nits():
+    for nits in (25, 100, 125, 400):
+        vp = _vp(H.Case(O.CF["P010"], 64, 36, 64, 36, H.EX_2020_PQ, nits=nits))
+        assert vp.debug_color_params()[3] == np.float32(10000.0) / np.float32(nits)
+
+
+SCALE_CASES = [(1920, 2880, "CatmullRom", "Hamming", 1), (3840, 7680, "Lanczos3", "Hamming", 1), (100, 237, "Mitchell", "Box", 1),
+               (100, 233, "Lanczos2", "Box", 1), (7680, 3840, "Lanczos3", "Bicubic", 0), (1000, 333, "CatmullRom", "Lanczos", 1),
+               (500, 200, "CatmullRom", "Hamming", 1), (400, 100, "CatmullRom", "Box", 1), (640, 300, "CatmullRom", "Bilinear", 1),
+               (640, 320, "Lanczos3", "BicubicSharp", 1), (97, 97, "Lanczos3", "Hamming", 1)]
+
+
+@pytest.mark.parametrize("src,dst,up,down,i50", SCALE_CASES)
+@pytest.mark.parametrize("variant", [O.VARIANT_D3D11, O.VARIANT_D3D9])
+def test_axis_tables_equal_oracle(src, dst, up, down, i50, variant):
+    case = H.Case(O.CF["NV12"], src, 64, dst, 64, H.EX_709, up=O.UPSCALE[up], down=O.DOWNSCALE[down], interp50=i50, variant=variant)
+    vp = _vp(case)
+    plan = vp.debug_plan()
+    kind = O.lib().orc_scaler_kind(src, dst, i50)
+    assert plan.scaler_x == kind and plan.scaler_y == 0
+    if kind == 0:
+        return
+    filt = O.DOWNSCALE[down] if kind == 2 else O.UPSCALE[up]
+    for i in list(range(0, min(dst, 40))) + [dst // 2, dst - 2, dst - 1]:
+        base, w, wsum = vp.debug_axis_taps(0, i)
+        ob, ow, osum, n = O.axis_taps(kind, filt, variant, 0, src, dst, i)
+        assert base == ob
+        assert _bits(w[:n]) == _bits(ow), (i, w, ow)
+        assert np.all(w[n:] == 0)
+        if kind == 2:
+            assert _bits([wsum]) == _bits([osum])
+
+
+def test_plan_decisions_follow_reference_rules():
+    L = O.lib()
+    for cf, depth in ((O.CF["NV12"], 8), (O.CF["P010"], 16), (O.CF["YUV420P10"], 10)):
+        for tex in (O.TEXFMT_AUTOINT, O.TEXFMT_8INT, O.TEXFMT_10INT, O.TEXFMT_16FLOAT):
+            for bb in (O.SURF_BGRA8, O.SURF_RGB10A2, O.SURF_RGBA16F):
+                for dither in (0, 1):
+                    vp = _vp(H.Case(cf, 64, 36, 128, 72, H.EX_709, backbuffer=bb, tex=tex, dither=dither))
+                    p = vp.debug_plan()
+                    assert p.internal_fmt == L.orc_internal_fmt(tex, depth)
+                    assert p.final_pass == L.orc_need_final_pass(bb, p.internal_fmt, dither)
+    # transfer selection (Source/Shaders.cpp:613-616, :892-905)
+    def tr(ex, to_sdr=1):
+        return _vp(H.Case(O.CF["P010"], 64, 36, 64, 36, ex, to_sdr=to_sdr)).debug_plan().transfer
+    assert tr(H.EX_2020_PQ) == 1 and tr(H.EX_2020_PQ, 0) == 0
+    assert tr(O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=16)) == 2 and tr(O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=16), 0) == 3
+    assert tr(H.EX_2020_SDR) == 3 and tr(H.EX_709) == 0
+    assert tr(O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=1)) == 0       # linear transfer: quirk B4 -> matrix only
+    assert tr(O.exfmt(chroma=5, range_=2, matrix=1, prim=2, trc=15)) == 1      # PQ with 709 primaries still tone-maps
+    # Nearest upscaling has no shader: point-sampled axis
+    p = _vp(H.Case(O.CF["NV12"], 64, 36, 128, 72, H.EX_709, up=O.UPSCALE["Nearest"])).debug_plan()
+    assert p.scaler_x == 3 and p.scaler_y == 3
+    # variant follows Settings_t::bUseD3D11
+    assert _vp(H.Case(O.CF["NV12"], 64, 36, 128, 72, H.EX_709, variant=O.VARIANT_D3D9)).debug_plan().variant == 1
+
+
+def test_media_type_rules():
+    vp = V.VideoProcessor(device=-1)
+    mt = V.VideoProcessor.media_type(V.CF.NV12, 1918, 1080)
+    assert vp.InitMediaType(mt)
+    p = vp.debug_plan()
+    assert p.src_pitch == 1920 and p.src_lines == 1620                     # NV12 pitch ALIGN 4, lines = H*3/2 (:1789-1796)
+    assert p.src_exfmt == O.lib().orc_specify_extended_format(0, 0, 420, 1918, 1080)
+    assert vp.GetSourceRect() == (0, 0, 1918, 1080) and vp.GetVideoSize() == (1918, 1080) and vp.GetAspectRatio() == (959, 540)
+    mt = V.VideoProcessor.media_type(V.CF.P010, 3840, 2160, H.EX_2020_PQ, aspect=(16, 9))
+    assert vp.InitMediaType(mt)
+    p = vp.debug_plan()
+    assert p.src_pitch == 7680 and p.src_lines == 3240
+    assert (p.src_exfmt & 0xFF) == 3                                       # AMCONTROL_USED | AMCONTROL_COLORINFO_PRESENT
+    assert vp.GetAspectRatio() == (16, 9)
+    # SD default matrix is BT.601, HD BT.709 (SpecifyExtendedFormat)
+    assert vp.InitMediaType(V.VideoProcessor.media_type(V.CF.YUY2, 720, 576))
+    assert (vp.debug_plan().src_exfmt >> 15) & 7 == 2
+    # VR_Extradata: padded buffer width, true frame size
+    mt = V.VideoProcessor.media_type(V.CF.NV12, 2048, 1080, frame_size=(1920, 1080))
+    assert vp.InitMediaType(mt)
+    assert vp.GetSourceRect() == (0, 0, 1920, 1080) and vp.debug_plan().src_pitch == 2048
+    # rejects
+    assert not vp.VerifyMediaType(V.VideoProcessor.media_type(V.CF.RGB24, 64, 64))      # RGB inputs: next row
+    assert not vp.VerifyMediaType(V.VideoProcessor.media_type(V.CF.V210, 64, 64))
+    assert not vp.VerifyMediaType(V.VideoProcessor.media_type(V.CF.NONE, 64, 64))
+    assert not vp.VerifyMediaType(V.VideoProcessor.media_type(V.CF.NV12, 0, 64))
+    assert not vp.InitMediaType(V.VideoProcessor.media_type(V.CF.NV12, 64, 64, src_rect=(0, 0, 100, 64)))
+    ok, cx, cy = vp.GetAlignmentSize(V.VideoProcessor.media_type(V.CF.P010, 1918, 1080))
+    assert ok and (cx * 2) % 256 == 0 and cx >= 1918 and cy == 1080
+
+
+def test_no_cpu_fallback_and_error_convention():
+    vp = V.VideoProcessor(device=-1)
+    assert not vp.GetActive() and vp.GetDeviceIndex() == -1
+    assert vp.InitMediaType(V.VideoProcessor.media_type(V.CF.NV12, 64, 64))
+    hr = vp.ProcessSample(data=np.zeros(64 * 96, np.uint8), check=False)
+    assert hr == V.HRESULT.E_UNEXPECTED and "no CPU path" in vp.last_error()
+    assert vp._L.mpcvr_render(vp._h, 1, 0) == V.HRESULT.E_UNEXPECTED
+    assert vp.SetRotation(0) == 0 and vp.SetRotation(90) == V.HRESULT.E_NOTIMPL
+    assert vp.SetFlip(False) == 0 and vp.SetFlip(True) == V.HRESULT.E_NOTIMPL
+    assert vp._L.mpcvr_process_sample(None, None) == V.HRESULT.E_POINTER
+    with pytest.raises(V.MpcvrError):
+        V.VideoProcessor(device=12345)
+    s = vp.GetSettings(); s.iUpscaling = V.UPSCALE.Lanczos3; s.iSDRDisplayNits = 200; vp.Configure(s)
+    assert vp.GetSettings().iUpscaling == V.UPSCALE.Lanczos3
+    assert "Lanczos3" in vp.GetVPInfo()
+
+
+def test_unorm_read_sequence_is_exact():
+    """q = c*r; q += fma(-q, N, c)*r  equals the IEEE quotient c/N for every code of the three UNORM widths
+    (what mpcvr_math.cuh::div_by_const_exact relies on; re-checked on the device in the GPU tests)"""
+    import math
+    for n in (255, 1023, 65535):
+        N = np.float32(n); r = np.float32(1.0) / N
+        c = np.arange(n + 1, dtype=np.float32)
+        q = c * r
+        # fma emulated exactly in float64 (products of two float32 are exact in float64)
+        e = (c.astype(np.float64) - q.astype(np.float64) * np.float64(N)).astype(np.float32)
+        assert np.all(e.astype(np.float64) == c.astype(np.float64) - q.astype(np.float64) * np.float64(N)), "residual must be exact"
+        q2 = (q.astype(np.float64) + e.astype(np.float64) * np.float64(r)).astype(np.float32)
+        assert np.array_equal(q2, c / N)
