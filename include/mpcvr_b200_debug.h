@@ -45,6 +45,9 @@ int32_t mpcvr_debug_read_surface(mpcvr* vp, int32_t which, void* host_dst, size_
 /* run Process() downstream of ConvertColorPass on a caller-supplied m_TexConvertOutput (host memory, internal fmt) */
 int32_t mpcvr_debug_render_from_convert(mpcvr* vp, const void* host_surf, size_t pitch);
 
+/* the PQ->SDR convert body on n normalised (y,u,v) triples with the instance's colour parameters: mode 0 scalar form, mode 1 two-lane (FFMA2) form */
+int32_t mpcvr_debug_probe_pq(mpcvr* vp, const float* yuv3, float* rgb3, int32_t n, int32_t mode);
+
 /* device scalar math of the arithmetic contract, elementwise on host arrays (GPU required):
  * op 0 LG2(x), 1 EX2(x), 2 POW(x,y), 3 UNORM16 read code/65535 (x = code), 4 UNORM10 read, 5 UNORM8 read */
 int32_t mpcvr_debug_math(int32_t cuda_device, int32_t op, const float* x, const float* y, float* out, int64_t n);

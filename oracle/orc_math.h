@@ -13,7 +13,7 @@
  * algorithms built only from IEEE-754 correctly rounded operations (add, mul,
  * fma, integer bit moves), so that the CUDA path can reproduce them bit for bit.
  * Measured against libm over all fp32 inputs of interest: LG2 <= 2.1 ulp,
- * EX2 < 1 ulp (tests/test_oracle_math.py re-measures this).
+ * EX2 <= 1 ulp (tests/test_oracle_math.py re-measures this).
  *
  * Independent restatement: the CUDA implementation lives in
  * videorenderer_b200/csrc/mpcvr_math.cuh and shares only the numbers below
@@ -49,24 +49,30 @@ static inline float orc_lg2_spec(float x)
     return fmaf(f, p, (float)e);
 }
 
-static inline float orc_ex2_spec(float t)
+/* 2^(a*b) with the product folded into the range reduction (two fused multiply-adds):
+ *   z = fma(a, b, 1.5*2^23)  -> n = round(a*b) sits in the low mantissa bits
+ *   r = fma(a, b, -n)        -> a*b - n with a single rounding, |r| <= 1/2
+ * results below 2^-125 flush to 0, above 2^127 saturate to +inf. */
+static inline float orc_ex2p_spec(float a, float b)
 {
-    if (!(t >= -126.0f)) return 0.0f;                   /* underflow (and NaN) -> 0 */
-    if (t > 128.0f) t = 128.0f;                         /* -> +inf */
-    float    z  = t + 12582912.0f;                      /* 1.5*2^23: round to nearest integer */
-    int32_t  n  = (int32_t)orc_f2u(z) - 0x4b400000;
-    float    nf = z - 12582912.0f;
-    float    r  = t - nf;                               /* exact, |r| <= 0.5 */
-    float    p  = ORC_EX2_C[6];
+    const float z  = fmaf(a, b, 12582912.0f);
+    const float nf = z - 12582912.0f;                   /* exact */
+    const float r  = fmaf(a, b, -nf);
+    float p = ORC_EX2_C[6];
     for (int i = 5; i >= 0; i--) p = fmaf(p, r, ORC_EX2_C[i]);
+    if (z < 12582912.0f - 125.0f) return 0.0f;
+    if (z > 12582912.0f + 127.0f) return INFINITY;
+    const int32_t n = (int32_t)orc_f2u(z) - 0x4b400000;
     return orc_u2f(orc_f2u(p) + ((uint32_t)n << 23));
 }
+
+static inline float orc_ex2_spec(float t) { return orc_ex2p_spec(t, 1.0f); }
 
 /* HLSL pow(x,y) for x >= 0:  exp2(y*log2(x)); pow(0,y>0) = 0 (log2(0) = -inf). */
 static inline float orc_pow_spec(float x, float y)
 {
     if (!(x >= 1.17549435e-38f)) return 0.0f;
-    return orc_ex2_spec(y * orc_lg2_spec(x));
+    return orc_ex2p_spec(orc_lg2_spec(x), y);
 }
 
 static inline float orc_pow_literal(float x, float y)

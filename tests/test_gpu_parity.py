@@ -168,7 +168,7 @@ def test_math_contract_on_device():
     assert L.mpcvr_debug_math(0, 0, x.ctypes.data, None, out.ctypes.data, x.size) == 0
     exp = np.array([OL.orc_test_lg2(float(v)) for v in x[x > 1e-37][:50000]], np.float32)
     np.testing.assert_array_equal(out[x > 1e-37][:50000].view(np.uint32), exp.view(np.uint32))
-    t = np.concatenate([rng.uniform(-130, 5, 200000), [0.0, -126.0, -126.00001, -0.5, 0.5, 128.0]]).astype(np.float32)
+    t = np.concatenate([rng.uniform(-130, 5, 200000), [0.0, -126.0, -125.5, -125.49, -0.5, 0.5, 127.4, 128.0]]).astype(np.float32)
     out = np.empty_like(t)
     assert L.mpcvr_debug_math(0, 1, t.ctypes.data, None, out.ctypes.data, t.size) == 0
     exp = np.array([OL.orc_test_ex2(float(v)) for v in t[:50000]], np.float32)
@@ -280,3 +280,51 @@ def test_full_size_c2_fused_equals_multipass_and_oracle_band():
     ref = H.run_oracle(sub, planes, pitches)
     a = out_f[2 * y0:2 * y1]; b = ref[2 * halo:2 * halo + 2 * (y1 - y0)]
     assert H.compare(a, b, case.backbuffer) == (0, 0)
+
+
+def test_two_lane_math_equals_scalar_math():
+    """mpcvr_math2.cuh (FFMA2 forms) against mpcvr_math.cuh on the device, bit for bit, both lanes"""
+    import videorenderer_b200 as V
+    L = V.lib()
+    rng = np.random.Generator(np.random.PCG64(5))
+
+    def run(op, x, y=None):
+        out = np.empty_like(x)
+        assert L.mpcvr_debug_math(0, op, x.ctypes.data, None if y is None else y.ctypes.data, out.ctypes.data, x.size) == 0
+        return out.view(np.uint32)
+
+    x = np.concatenate([rng.uniform(0, 1, 300000), np.exp(rng.uniform(-80, 0, 100000)), [0.0, 1.0, 1e-38, 1.17549435e-38, 1e-40, 0.5]]).astype(np.float32)
+    np.testing.assert_array_equal(run(10, x[x > 1e-37]), run(0, x[x > 1e-37]))
+    np.testing.assert_array_equal(run(20, x[x > 1e-37]), run(0, x[x > 1e-37]))
+    t = np.concatenate([rng.uniform(-140, 10, 300000), [0.0, -126.0, -127.0, 128.0]]).astype(np.float32)
+    np.testing.assert_array_equal(run(11, t), run(1, t))
+    for yv in (1 / 78.84375, 1 / 2.2):
+        y = np.full_like(x, np.float32(yv))
+        np.testing.assert_array_equal(run(12, x, y), run(2, x, y))
+        np.testing.assert_array_equal(run(13, x, y), run(2, x, y))
+    y = np.full_like(x, np.float32(1.0) / np.float32(0.1593017578125))
+    np.testing.assert_array_equal(run(12, x, y), run(2, x, y))
+    np.testing.assert_array_equal(run(14, x, y), run(2, x, y))
+    np.testing.assert_array_equal(run(21, x, y), run(2, x, y))
+    # divisions on the tone-map operand ranges: fast exact sequence == IEEE division
+    num = np.concatenate([rng.uniform(0, 0.165, 200000), rng.uniform(0, 1000, 200000), [0.0]]).astype(np.float32)
+    den = np.concatenate([rng.uniform(0.16, 19, 200000), rng.uniform(0.05, 2000, 200000), [0.1640625]]).astype(np.float32)
+    ref = run(17, num, den)
+    np.testing.assert_array_equal(run(16, num, den), ref)
+    np.testing.assert_array_equal(run(15, num, den), ref)
+    v = rng.uniform(-0.2, 1.2, 300000).astype(np.float32)
+    np.testing.assert_array_equal(run(18, v), run(19, v))
+
+
+def test_two_lane_pq_convert_equals_scalar_convert():
+    """the FFMA2 form of the PQ->SDR shader body against the scalar form, bit for bit, on random yuv"""
+    case = H.baseline_cases(0.1)[1]
+    vp = case.make_processor(device=0)
+    rng = np.random.Generator(np.random.PCG64(9))
+    n = 200000
+    yuv = np.stack([rng.uniform(0, 1, n), rng.uniform(0, 1, n), rng.uniform(0, 1, n)], -1).astype(np.float32)
+    yuv[:1000, 0] = rng.uniform(0.06, 0.08, 1000)          # near black: the PQ curve is steepest there
+    a = np.empty_like(yuv); b = np.empty_like(yuv)
+    assert vp._L.mpcvr_debug_probe_pq(vp._h, yuv.ctypes.data, a.ctypes.data, n, 0) == 0
+    assert vp._L.mpcvr_debug_probe_pq(vp._h, yuv.ctypes.data, b.ctypes.data, n, 1) == 0
+    np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))

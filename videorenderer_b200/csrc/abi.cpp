@@ -102,6 +102,8 @@ int32_t mpcvr_debug_capture_f32(mpcvr* h, int32_t en) { VP_OR(MPCVR_E_POINTER); 
 int32_t mpcvr_debug_read_surface(mpcvr* h, int32_t which, void* dst, size_t pitch, int32_t* w, int32_t* hh, int32_t* fmt) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugReadSurface(which, dst, pitch, w, hh, fmt)); }
 int32_t mpcvr_debug_render_from_convert(mpcvr* h, const void* surf, size_t pitch) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugRenderFromConvert(surf, pitch)); }
 
+int32_t mpcvr_debug_probe_pq(mpcvr* h, const float* yuv3, float* rgb3, int32_t n, int32_t mode) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugProbePQ(yuv3, rgb3, n, mode)); }
+
 int32_t mpcvr_debug_math(int32_t dev, int32_t op, const float* x, const float* y, float* out, int64_t n)
 {
     if (!x || !out || n <= 0) return MPCVR_E_POINTER;

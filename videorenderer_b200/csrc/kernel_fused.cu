@@ -20,6 +20,7 @@
 #include <cuda_fp16.h>
 #include "kernels.h"
 #include "pixel_ops.cuh"
+#include "mpcvr_math2.cuh"
 #include "dither32.h"
 
 namespace b200vr {
@@ -125,6 +126,154 @@ __device__ __forceinline__ void convert_tile_biplanar(const FusedParams& prm, co
     }
 }
 
+// ---- two-lane (FFMA2) PQ->SDR convert: lanes = two horizontally adjacent pixels, same operations as convert_color<PQ>
+struct f3x2 { float2 x, y, z; };
+
+__device__ __forceinline__ float2 dp3_2(const float m[3], const f3x2& v) { return fma2(m[2], v.z, fma2(m[1], v.y, mul2(v.x, m[0]))); }
+
+__device__ __forceinline__ float2 pq_channel_to_hable2(const ColorParams& P, float2 c)
+{
+    const float2 a   = powr01_ylt1_2(sat2(c), P.inv_m2);                         // ST2084ToLinear, st2084.hlsl:9-16
+    const float2 num = max2(add2(a, -ST2084_C1), 0.0f);
+    const float2 den = fma2(-ST2084_C3, a, ST2084_C2);
+    const float2 lin = mul2(powr01_ygt1_2(div_rn_safe_2(num, den), P.inv_m1), P.lum_scale);
+    const float2 hn  = fma2(lin, fma2(0.15f, lin, P.hable_cb), P.hable_de);       // hable(), hdr_tone_mapping.hlsl:1-6
+    const float2 hd  = fma2(lin, fma2(0.15f, lin, 0.50f), P.hable_df);
+    return mul2(add2(div_rn_safe_2(hn, hd), -P.hable_ef), P.hable_rdiv);
+}
+
+__device__ __forceinline__ f3x2 convert_color_pq2(const ColorParams& P, const f3x2& yuv)
+{
+    f3x2 c;
+    c.x = add2(dp3_2(P.cm[0], yuv), P.cc[0]); c.y = add2(dp3_2(P.cm[1], yuv), P.cc[1]); c.z = add2(dp3_2(P.cm[2], yuv), P.cc[2]);
+    f3x2 h;
+    h.x = pq_channel_to_hable2(P, c.x); h.y = pq_channel_to_hable2(P, c.y); h.z = pq_channel_to_hable2(P, c.z);
+    f3x2 o;
+    o.x = powr01_ylt1_2(sat2(dp3_2(P.gamut[0], h)), P.inv_gamma22);
+    o.y = powr01_ylt1_2(sat2(dp3_2(P.gamut[1], h)), P.inv_gamma22);
+    o.z = powr01_ylt1_2(sat2(dp3_2(P.gamut[2], h)), P.inv_gamma22);
+    return o;
+}
+
+__device__ __forceinline__ float2 rt_roundtrip2(int fmt, float2 v)
+{
+    if (fmt == MPCVR_SURF_RGB10A2) return unorm_roundtrip2(v, 1023.0f, 1.0f / 1023.0f);
+    if (fmt == MPCVR_SURF_BGRA8)   return unorm_roundtrip2(v, 255.0f, 1.0f / 255.0f);
+    return make_float2(f16_roundtrip(v.x), f16_roundtrip(v.y));
+}
+
+// bi-planar 16-bit source, bilinear chroma, PQ->SDR, two pixels per work item
+__device__ __forceinline__ void convert_tile_biplanar16_pq2(const FusedParams& prm, const int ifmt, float* __restrict__ sConv,
+                                                            float2* __restrict__ sUV, const int TW, const int TH, const int TWP,
+                                                            const int cx0, const int cy0)
+{
+    const SrcDesc& S = prm.src;
+    int ox, oy, my;
+    if (S.subsampling == 420) {
+        my = 2;
+        if (S.siting == ChromaSub_Cosited)    { ox = 0;  oy = 0;  }
+        else if (S.siting == ChromaSub_MPEG1) { ox = -1; oy = -1; }
+        else                                  { ox = 0;  oy = -1; }
+    } else { my = 4; ox = 0; oy = 0; }
+    const int lx_lo = S.rect_l + clampi(cx0, 0, prm.w1 - 1), lx_hi = S.rect_l + clampi(cx0 + TW - 1, 0, prm.w1 - 1);
+    const int ly_lo = S.rect_t + clampi(cy0, 0, prm.h1 - 1), ly_hi = S.rect_t + clampi(cy0 + TH - 1, 0, prm.h1 - 1);
+    const int ux0 = (2 * lx_lo + ox) >> 2, uw = (((2 * lx_hi + ox) >> 2) + 1) - ux0 + 1;
+    const int uy0 = (my * ly_lo + oy) >> 2, uh = (((my * ly_hi + oy) >> 2) + 1) - uy0 + 1;
+    const int uwp = uw | 1;
+    for (int i = threadIdx.x; i < uw * uh; i += kThreads) {
+        const int uy = i / uw, ux = i - uy * uw;
+        const int tx = clampi(ux0 + ux, 0, S.cw - 1), ty = clampi(uy0 + uy, 0, S.ch - 1);
+        const uint32_t v = __ldg((const uint32_t*)(S.pl[1] + (uint32_t)(ty * S.pitch[1])) + tx);
+        sUV[uy * uwp + ux] = make_float2(unorm16(v & 0xFFFFu), unorm16(v >> 16));
+    }
+    __syncthreads();
+    const int half = TW >> 1, n = half * TH;
+    for (int idx = threadIdx.x; idx < n; idx += kThreads) {
+        const int ty = idx / half, tx = 2 * (idx - ty * half);
+        const int sy = S.rect_t + clampi(cy0 + ty, 0, prm.h1 - 1);
+        const int sx0 = S.rect_l + clampi(cx0 + tx, 0, prm.w1 - 1), sx1 = S.rect_l + clampi(cx0 + tx + 1, 0, prm.w1 - 1);
+        const uint16_t* yrow = (const uint16_t*)(S.pl[0] + (uint32_t)(sy * S.pitch[0]));
+        f3x2 yuv;
+        yuv.x = make_float2(unorm16(__ldg(yrow + sx0)), unorm16(__ldg(yrow + sx1)));
+        const int qy = my * sy + oy;
+        const float fy = (float)(qy & 3) * 0.25f;
+        const float2* trow = sUV + ((qy >> 2) - uy0) * uwp - ux0;
+        float2 uv[2];
+        #pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int qx = 2 * (s ? sx1 : sx0) + ox;
+            const float fx = (float)(qx & 3) * 0.25f;
+            const float2* t = trow + (qx >> 2);
+            const float2 c00 = t[0], c10 = t[1], c01 = t[uwp], c11 = t[uwp + 1];
+            const float2 top = fma2(fx, sub2(c10, c00), c00), bot = fma2(fx, sub2(c11, c01), c01);    // lerp_mad on (u,v) together
+            uv[s] = fma2(fy, sub2(bot, top), top);
+        }
+        yuv.y = make_float2(uv[0].x, uv[1].x); yuv.z = make_float2(uv[0].y, uv[1].y);
+        const f3x2 rgb = convert_color_pq2(prm.color, yuv);
+        float* d = sConv + ty * TWP + tx;
+        *reinterpret_cast<float2*>(d)                = rt_roundtrip2(ifmt, rgb.x);
+        *reinterpret_cast<float2*>(d + TH * TWP)     = rt_roundtrip2(ifmt, rgb.y);
+        *reinterpret_cast<float2*>(d + 2 * TH * TWP) = rt_roundtrip2(ifmt, rgb.z);
+    }
+}
+
+__global__ void k_probe_pq(const float* __restrict__ y, const float* __restrict__ u, const float* __restrict__ v, float* __restrict__ out,
+                           const __grid_constant__ ColorParams P, int n, int mode)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = (i + 1) % n;
+    if (mode == 0) {
+        f3 a; a.x = y[i]; a.y = u[i]; a.z = v[i];
+        const f3 r = convert_color<TRANSFER_PQ_TO_SDR>(P, a);
+        out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+    } else if (mode == 1) {
+        f3x2 a; a.x = make_float2(y[i], y[j]); a.y = make_float2(u[i], u[j]); a.z = make_float2(v[i], v[j]);
+        const f3x2 r = convert_color_pq2(P, a);
+        out[3 * i] = r.x.x; out[3 * i + 1] = r.y.x; out[3 * i + 2] = r.z.x;
+    } else if (mode >= 8) {
+        const float2 c = make_float2(y[i], y[j]);
+        const float2 a   = powr01_ylt1_2(sat2(c), P.inv_m2);
+        const float2 num = max2(add2(a, -ST2084_C1), 0.0f);
+        const float2 den = fma2(-ST2084_C3, a, ST2084_C2);
+        const float2 lin = mul2(powr01_ygt1_2(div_rn_safe_2(num, den), P.inv_m1), P.lum_scale);
+        const float2 hn  = fma2(lin, fma2(0.15f, lin, P.hable_cb), P.hable_de);
+        const float2 hd  = fma2(lin, fma2(0.15f, lin, 0.50f), P.hable_df);
+        const float2 q = div_rn_safe_2(hn, hd);
+        const float2 h = mul2(add2(q, -P.hable_ef), P.hable_rdiv);
+        if (mode == 8) { out[3 * i] = hn.x; out[3 * i + 1] = hd.x; out[3 * i + 2] = q.x; }
+        else if (mode == 9) { out[3 * i] = add2(q, -P.hable_ef).x; out[3 * i + 1] = h.x; out[3 * i + 2] = h.y; }
+        else { out[3 * i] = lin.x; out[3 * i + 1] = lin.y; out[3 * i + 2] = pq_channel_to_hable2(P, c).x; }
+    } else if (mode >= 5) {
+        f3x2 a; a.x = make_float2(y[i], y[j]); a.y = make_float2(u[i], u[j]); a.z = make_float2(v[i], v[j]);
+        f3x2 c;
+        c.x = add2(dp3_2(P.cm[0], a), P.cc[0]); c.y = add2(dp3_2(P.cm[1], a), P.cc[1]); c.z = add2(dp3_2(P.cm[2], a), P.cc[2]);
+        if (mode == 5) { out[3 * i] = c.x.x; out[3 * i + 1] = c.y.x; out[3 * i + 2] = c.z.x; }
+        else {
+            f3x2 h; h.x = pq_channel_to_hable2(P, c.x); h.y = pq_channel_to_hable2(P, c.y); h.z = pq_channel_to_hable2(P, c.z);
+            if (mode == 6) { out[3 * i] = h.x.x; out[3 * i + 1] = h.y.x; out[3 * i + 2] = h.z.x; }
+            else { const float2 g = dp3_2(P.gamut[0], h); out[3 * i] = g.x; out[3 * i + 1] = sat2(g).x; out[3 * i + 2] = powr01_ylt1_2(sat2(g), P.inv_gamma22).x; }
+        }
+    } else {
+        // stage dump of the two-lane chain on channel value c = y[i]
+        const float2 c = make_float2(y[i], y[j]);
+        const float2 a   = powr01_ylt1_2(sat2(c), P.inv_m2);
+        const float2 num = max2(add2(a, -ST2084_C1), 0.0f);
+        const float2 den = fma2(-ST2084_C3, a, ST2084_C2);
+        const float2 b = div_rn_safe_2(num, den);
+        const float2 lin = mul2(powr01_ygt1_2(b, P.inv_m1), P.lum_scale);
+        out[3 * i] = mode == 2 ? a.x : (mode == 3 ? num.x : lin.x);
+        out[3 * i + 1] = mode == 2 ? den.x : (mode == 3 ? b.x : P.inv_m1);
+        out[3 * i + 2] = mode == 2 ? P.inv_m2 : (mode == 3 ? P.lum_scale : powr01_ygt1_2(b, P.inv_m1).x);
+    }
+}
+
+cudaError_t LaunchProbePQ(const float* y, const float* u, const float* v, float* out, const ColorParams& P, int n, int mode, cudaStream_t st)
+{
+    k_probe_pq<<<(n + 255) / 256, 256, 0, st>>>(y, u, v, out, P, n, mode);
+    return cudaGetLastError();
+}
+
 // which stage A a kernel instantiation carries
 enum { CONV_GENERIC = 0, CONV_BIPLANAR16_PQ = 1, CONV_BIPLANAR8_NONE = 2, CONV_BIPLANAR16_ANY = 3, CONV_BIPLANAR8_ANY = 4 };
 // which (internal, target, final) combination is fixed at compile time
@@ -156,7 +305,7 @@ k_fused2x(const __grid_constant__ FusedParams prm)
     {
         float2* sUV = reinterpret_cast<float2*>(sX);                 // aliases the (still unused) X-pass buffer
         const int cx0 = jx0 + prm.b0, cy0 = jy0 + prm.b0;
-        if (CONV == CONV_BIPLANAR16_PQ)        convert_tile_biplanar<2, TRANSFER_PQ_TO_SDR>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
+        if (CONV == CONV_BIPLANAR16_PQ)        convert_tile_biplanar16_pq2(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
         else if (CONV == CONV_BIPLANAR8_NONE)  convert_tile_biplanar<1, TRANSFER_NONE>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
         else if (CONV == CONV_BIPLANAR16_ANY)  convert_tile_biplanar<2, -1>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
         else if (CONV == CONV_BIPLANAR8_ANY)   convert_tile_biplanar<1, -1>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
@@ -212,7 +361,7 @@ k_fused2x(const __grid_constant__ FusedParams prm)
             const int ox = 2 * cp, oy = 8 * rb;                                    // tile-local output coordinates
             const int gx = prm.dst_x0 + 2 * jx0 + ox, gy = prm.dst_y0 + 2 * jy0 + oy;   // target coordinates
             if (2 * jx0 + ox >= 2 * prm.w1 || 2 * jy0 + oy >= 2 * prm.h1) continue;
-            float res[3][8][2];
+            float2 res[3][8];
             #pragma unroll
             for (int c = 0; c < 3; c++) {
                 float2 v[NT + 4];
@@ -221,17 +370,15 @@ k_fused2x(const __grid_constant__ FusedParams prm)
                 for (int r = 0; r < NT + 4; r++) v[r] = __half22float2(*reinterpret_cast<const __half2*>(col + (size_t)r * kOut));
                 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    float2 e, d;
-                    e.x = __fmul_rn(wE[0], v[q].x); e.y = __fmul_rn(wE[0], v[q].y);
-                    d.x = __fmul_rn(wO[0], v[q + 1].x); d.y = __fmul_rn(wO[0], v[q + 1].y);
+                    float2 e = mul2(v[q], wE[0]), d = mul2(v[q + 1], wO[0]);
                     #pragma unroll
                     for (int k = 1; k < NT; k++) {
                         const float2 te = (NT == 6 && k == 1) ? (dup ? v[q] : v[q + 1]) : v[q + k];
                         const float2 to = (NT == 6 && k == 1) ? (dup ? v[q + 1] : v[q + 2]) : v[q + 1 + k];
-                        e.x = fma_rn(wE[k], te.x, e.x); e.y = fma_rn(wE[k], te.y, e.y);
-                        d.x = fma_rn(wO[k], to.x, d.x); d.y = fma_rn(wO[k], to.y, d.y);
+                        e = fma2(wE[k], te, e);
+                        d = fma2(wO[k], to, d);
                     }
-                    res[c][2 * q][0] = e.x; res[c][2 * q][1] = e.y; res[c][2 * q + 1][0] = d.x; res[c][2 * q + 1][1] = d.y;
+                    res[c][2 * q] = e; res[c][2 * q + 1] = d;
                 }
             }
             // rows of this block
@@ -241,25 +388,27 @@ k_fused2x(const __grid_constant__ FusedParams prm)
                 if (2 * jy0 + oy + r >= 2 * prm.h1) break;
                 uint32_t code[2][3];
                 __half hv[2][3];
+                float2 dth = make_float2(0.f, 0.f);
+                if (FINAL) dth = *reinterpret_cast<const float2*>(sDith + ((y & 31) << 5) + (gx & 31));
                 #pragma unroll
-                for (int s = 0; s < 2; s++) {
-                    #pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        float val = res[c][r][s];
-                        if (FINAL) {
-                            // post-scale surface (internal format) then ps_final_pass: floor(p*Q + d), UNORM write clamps
-                            const float p = (IFMT == MPCVR_SURF_RGBA16F) ? f16_roundtrip(val)
-                                          : (IFMT == MPCVR_SURF_RGB10A2 ? div_by_const_exact((float)floor_u(fma_rn(sat(val), 1023.0f, 0.5f)), 1023.0f, 1.0f / 1023.0f)
-                                                                        : div_by_const_exact((float)floor_u(fma_rn(sat(val), 255.0f, 0.5f)), 255.0f, 1.0f / 255.0f));
-                            const float dth = sDith[((y & 31) << 5) + ((gx + s) & 31)];
-                            const float t = fma_rn(p, prm.Q, dth);
-                            if (IFMT == MPCVR_SURF_RGBA16F) code[s][c] = (uint32_t)min(max((int)floorf(t), 0), (int)prm.Q);
-                            else code[s][c] = floor_u(t);
-                        } else if (OFMT == MPCVR_SURF_RGBA16F) {
-                            hv[s][c] = __float2half_rn(val);
+                for (int c = 0; c < 3; c++) {
+                    const float2 val = res[c][r];
+                    if (FINAL) {
+                        // post-scale surface (internal format) then ps_final_pass: floor(p*Q + d); the UNORM write clamps
+                        const float2 p = rt_roundtrip2(IFMT, val);
+                        const float2 t = fma2(p, prm.Q, dth);
+                        if (IFMT == MPCVR_SURF_RGBA16F) {
+                            code[0][c] = (uint32_t)min(max((int)floorf(t.x), 0), (int)prm.Q);
+                            code[1][c] = (uint32_t)min(max((int)floorf(t.y), 0), (int)prm.Q);
                         } else {
-                            code[s][c] = floor_u(fma_rn(sat(val), OFMT == MPCVR_SURF_RGB10A2 ? 1023.0f : 255.0f, 0.5f));
+                            const float2 fl = __fadd2_rd(t, bc2(8388608.0f));
+                            code[0][c] = __float_as_uint(fl.x) & 0x3FFFFFu; code[1][c] = __float_as_uint(fl.y) & 0x3FFFFFu;
                         }
+                    } else if (OFMT == MPCVR_SURF_RGBA16F) {
+                        hv[0][c] = __float2half_rn(val.x); hv[1][c] = __float2half_rn(val.y);
+                    } else {
+                        const float2 fl = __fadd2_rd(fma2(sat2(val), OFMT == MPCVR_SURF_RGB10A2 ? 1023.0f : 255.0f, 0.5f), bc2(8388608.0f));
+                        code[0][c] = __float_as_uint(fl.x) & 0x3FFFFFu; code[1][c] = __float_as_uint(fl.y) & 0x3FFFFFu;
                     }
                 }
                 uint8_t* row = (uint8_t*)prm.out.ptr + (size_t)y * prm.out.pitch;

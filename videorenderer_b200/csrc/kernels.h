@@ -37,6 +37,9 @@ struct FusedPlan {
 bool        FusedSupported(const FusedPlan& p, const char** why);
 cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches);
 
+// PQ->SDR convert body, scalar (mode 0) vs two-lane (mode 1) forms, on arrays of normalised y,u,v (test hook)
+cudaError_t LaunchProbePQ(const float* y, const float* u, const float* v, float* out, const ColorParams& P, int n, int mode, cudaStream_t st);
+
 // ---- scalar math probe (mpcvr_debug_math)
 cudaError_t LaunchMathProbe(int op, const float* x, const float* y, float* out, long long n, cudaStream_t st);
 

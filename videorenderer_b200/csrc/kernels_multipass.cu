@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include "kernels.h"
 #include "pixel_ops.cuh"
+#include "mpcvr_math2.cuh"
 #include "dither32.h"
 
 namespace b200vr {
@@ -112,7 +113,21 @@ __global__ void k_math_probe(int op, const float* __restrict__ x, const float* _
     case 2: r = powr(a, y[i]); break;
     case 3: r = unorm16((uint32_t)a); break;
     case 4: r = unorm10((uint32_t)a); break;
-    default: r = unorm8((uint32_t)a); break;
+    case 5: r = unorm8((uint32_t)a); break;
+    // two-lane forms (mpcvr_math2.cuh): lane x = this element, lane y = its successor; lane x is returned
+    case 10: r = lg2_2(make_float2(a, x[(i + 1) % n])).x; break;
+    case 11: r = ex2_2(make_float2(a, x[(i + 1) % n])).x; break;
+    case 12: r = powr_2(make_float2(a, x[(i + 1) % n]), y[i]).x; break;
+    case 13: r = powr01_ylt1_2(make_float2(a, x[(i + 1) % n]), y[i]).x; break;
+    case 14: r = powr01_ygt1_2(make_float2(a, x[(i + 1) % n]), y[i]).x; break;
+    case 15: r = div_rn_safe_2(make_float2(a, x[(i + 1) % n]), make_float2(y[i], y[(i + 1) % n])).x; break;
+    case 16: r = div_rn_safe(a, y[i]); break;
+    case 17: r = __fdiv_rn(a, y[i]); break;
+    case 18: r = unorm_roundtrip2(make_float2(a, x[(i + 1) % n]), 1023.0f, 1.0f / 1023.0f).x; break;
+    case 19: r = rt_roundtrip(MPCVR_SURF_RGB10A2, a); break;
+    case 20: r = lg2_2(make_float2(x[(i + 1) % n], a)).y; break;
+    case 21: r = powr01_ygt1_2(make_float2(x[(i + 1) % n], a), y[i]).y; break;
+    default: r = 0.f; break;
     }
     out[i] = r;
 }

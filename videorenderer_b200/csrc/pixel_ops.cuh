@@ -248,7 +248,7 @@ __device__ __forceinline__ float inverse_hlg(const ColorParams& P, float x)     
 {
     const float b = 0.28466892f, c = 0.55991073f;
     const float lo = __fmul_rn(__fmul_rn(x, x), 4.0f);
-    const float hi = __fadd_rn(ex2(__fmul_rn(__fmul_rn(__fsub_rn(x, c), P.hlg_ra), 1.44269504f)), b);
+    const float hi = __fadd_rn(ex2p(__fmul_rn(__fsub_rn(x, c), P.hlg_ra), 1.44269504f), b);
     return (x <= 0.5f) ? lo : hi;
 }
 

@@ -861,4 +861,21 @@ int32_t CB200VideoProcessor::DebugRenderFromConvert(const void* host, size_t pit
     return Process(CurrentTarget(), m_srcRect, m_videoRect, true);
 }
 
+int32_t CB200VideoProcessor::DebugProbePQ(const float* yuv3, float* rgb3, int n, int mode)
+{
+    if (m_device < 0) return Fail(MPCVR_E_UNEXPECTED, "no CUDA device");
+    cudaSetDevice(m_device);
+    float* d = nullptr;
+    if (!Cuda(cudaMalloc(&d, (size_t)n * 6 * sizeof(float)), "probe alloc")) return MPCVR_E_FAIL;
+    std::vector<float> planar((size_t)3 * n);
+    for (int i = 0; i < n; i++) { planar[i] = yuv3[3 * i]; planar[n + i] = yuv3[3 * i + 1]; planar[2 * n + i] = yuv3[3 * i + 2]; }
+    int32_t hr = MPCVR_E_FAIL;
+    if (Cuda(cudaMemcpyAsync(d, planar.data(), (size_t)3 * n * sizeof(float), cudaMemcpyHostToDevice, m_stream), "H2D") &&
+        Cuda(LaunchProbePQ(d, d + n, d + 2 * n, d + 3 * n, m_color, n, mode, m_stream), "probe") &&
+        Cuda(cudaMemcpyAsync(rgb3, d + 3 * n, (size_t)3 * n * sizeof(float), cudaMemcpyDeviceToHost, m_stream), "D2H") &&
+        Cuda(cudaStreamSynchronize(m_stream), "sync")) hr = MPCVR_S_OK;
+    cudaFree(d);
+    return hr;
+}
+
 }  // namespace b200vr

@@ -124,6 +124,7 @@ public:
     int32_t DebugCaptureF32(bool enable);
     int32_t DebugReadSurface(int which, void* host, size_t pitch, int32_t* w, int32_t* h, int32_t* fmt);
     int32_t DebugRenderFromConvert(const void* host, size_t pitch);
+    int32_t DebugProbePQ(const float* yuv3, float* rgb3, int n, int mode);
 
 private:
     // ---- settings (names as in Source/VideoProcessor.h:48-73)
