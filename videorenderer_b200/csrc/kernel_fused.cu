@@ -29,7 +29,7 @@ __device__ const uint16_t g_dither32_fused[1024] = { MPCVR_DITHER32_VALUES };
 
 constexpr int kCore = 64;            // convert-surface pixels per tile side
 constexpr int kOut = 2 * kCore;      // output pixels per tile side
-constexpr int kThreads = 512;
+constexpr int kThreads = 640;
 
 struct FusedParams {
     SrcDesc     src;
