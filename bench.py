@@ -98,6 +98,13 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def c2_case():
     import harness as H
     return H.baseline_cases(1.0)[1]
@@ -120,7 +127,8 @@ def run_cpu_sample(case, frame, budget_s=12.0, threads=0):
     import harness as H
     import orclib as O
     buf, pitch, planes, pitches = frame
-    cores = O.lib().orc_num_threads() if threads <= 0 else threads
+    cores = host_threads() if threads <= 0 else threads
+    threads = cores
     # warm-up on a band to estimate cost
     band_rows = 270                        # 1/8 of the frame height (+ halo rows) -> 7680x540 output band
     band = H.Case(case.cf, case.w, case.h, case.dst_w, 2 * band_rows, case.ex, up=case.up, src_rect=(0, 0, case.w, band_rows), name="band")
@@ -151,15 +159,15 @@ def impl_reference(args, rank, world):
     import orclib as O
     case, frames = make_frames(1)
     buf, pitch, planes, pitches = frames[0]
-    cores = O.lib().orc_num_threads()
-    t0 = time.time(); H.run_oracle(case, planes, pitches); t_full = time.time() - t0          # warm-up + cost probe
+    cores = host_threads()                                     # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
+    t0 = time.time(); H.run_oracle(case, planes, pitches, threads=cores); t_full = time.time() - t0          # warm-up + cost probe
     if t_full <= 3.0:
-        run, frac = (lambda: H.run_oracle(case, planes, pitches)), 1.0
+        run, frac = (lambda: H.run_oracle(case, planes, pitches, threads=cores)), 1.0
         sample = "each step = one full C2 frame; CPU port of the reference shaders (oracle, SPEC arithmetic), %d OpenMP threads" % cores
     else:
         band_rows = 270
         band = H.Case(case.cf, case.w, case.h, case.dst_w, 2 * band_rows, case.ex, up=case.up, src_rect=(0, 0, case.w, band_rows), name="band")
-        run, frac = (lambda: H.run_oracle(band, planes, pitches)), band_rows / case.h
+        run, frac = (lambda: H.run_oracle(band, planes, pitches, threads=cores)), band_rows / case.h
         sample = "each step = 1/8-frame band (%d source rows -> 7680x%d output) of C2, scaled to full frames; CPU port (oracle, SPEC), %d OpenMP threads" % (band_rows, 2 * band_rows, cores)
     for _ in range(max(0, min(args.warmup, 3) - 1)):
         run()
