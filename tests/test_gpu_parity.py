@@ -328,3 +328,20 @@ def test_two_lane_pq_convert_equals_scalar_convert():
     assert vp._L.mpcvr_debug_probe_pq(vp._h, yuv.ctypes.data, a.ctypes.data, n, 0) == 0
     assert vp._L.mpcvr_debug_probe_pq(vp._h, yuv.ctypes.data, b.ctypes.data, n, 1) == 0
     np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["NV12", "P010", "YUY2", "AYUV", "YV12", "YUV444P10", "Y210"])
+@pytest.mark.parametrize("tex,bb,dither", [(O.TEXFMT_AUTOINT, O.SURF_BGRA8, 1), (O.TEXFMT_16FLOAT, O.SURF_RGB10A2, 1), (O.TEXFMT_16FLOAT, O.SURF_RGBA16F, 0),
+                                           (O.TEXFMT_10INT, O.SURF_BGRA8, 0), (O.TEXFMT_8INT, O.SURF_RGB10A2, 1)])
+def test_fused_1x_plans(name, tex, bb, dither):
+    """no axis resampled: convert (+ final pass) runs as ONE kernel straight into the back buffer (BASELINE config 1 shape)"""
+    ex = H.EX_2020_PQ if name in ("P010", "YUV444P10", "Y210") else H.EX_709
+    _check_fused(H.Case(O.CF[name], 66, 38, 66, 38, ex, backbuffer=bb, tex=tex, dither=dither, name="fused1x_" + name), "fullnoise", 41)
+    # same size, offset inside a larger window (copy path of ResizeShaderPass)
+    _check_fused(H.Case(O.CF[name], 66, 38, 66, 38, ex, backbuffer=bb, tex=tex, dither=dither, dst_rect=(7, 5, 73, 43), win=(90, 50), name="fused1x_off_" + name), "fullnoise", 42)
+
+
+def test_fused_c1_full_size():
+    case = H.baseline_cases(1.0)[0]
+    vp = _check_fused(case, "natural", 43)
+    assert vp.LastFrameKernels() == 1

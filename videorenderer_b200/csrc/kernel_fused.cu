@@ -25,11 +25,16 @@
 
 namespace b200vr {
 
+// dither values d = k/1024 (exact in fp32), read through L1 in stage C
+#define MPCVR_DITHER_F(k) ((float)(k) * 0.0009765625f)
 __device__ const uint16_t g_dither32_fused[1024] = { MPCVR_DITHER32_VALUES };
+__device__ float g_dither32_f[1024];
+__global__ void k_init_dither() { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < 1024) g_dither32_f[i] = MPCVR_DITHER_F(g_dither32_fused[i]); }
 
 constexpr int kCore = 64;            // convert-surface pixels per tile side
 constexpr int kOut = 2 * kCore;      // output pixels per tile side
-constexpr int kThreads = 640;
+constexpr int kThreads = 512;
+constexpr int kCtasPerSm = 2;
 
 struct FusedParams {
     SrcDesc     src;
@@ -48,10 +53,10 @@ struct FusedParams {
 template <int NT> struct TileGeom {
     static constexpr int TW = kCore + NT;          // window columns of a tile
     static constexpr int TH = kCore + NT;
-    static constexpr int TWP = (TW + 3) / 4 * 4 + 4;   // padded row pitch (floats), 16-byte aligned rows
+    static constexpr int TWP = (TW + 3) / 4 * 4;       // padded row pitch (floats), 16-byte aligned rows
     static constexpr size_t conv_bytes = (size_t)3 * TH * TWP * sizeof(float);
     static constexpr size_t x_bytes = (size_t)3 * TH * kOut * sizeof(__half);
-    static constexpr size_t smem_bytes = conv_bytes + x_bytes + 1024 * sizeof(float);
+    static constexpr size_t smem_bytes = conv_bytes + x_bytes;
 };
 
 // ---- stage A -----------------------------------------------------------------------------------------
@@ -283,7 +288,7 @@ enum { SPEC_RUNTIME = 0, SPEC_10_BGRA8_DITHER = 1, SPEC_8_BGRA8 = 2 };
 __device__ __forceinline__ uint32_t floor_u(float z) { return __float_as_uint(__fadd_rd(z, 8388608.0f)) & 0x3FFFFFu; }
 
 template <int NT, int SPEC, int CONV>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 k_fused2x(const __grid_constant__ FusedParams prm)
 {
     using G = TileGeom<NT>;
@@ -293,13 +298,12 @@ k_fused2x(const __grid_constant__ FusedParams prm)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float*  sConv = reinterpret_cast<float*>(smem_raw);
     __half* sX    = reinterpret_cast<__half*>(smem_raw + G::conv_bytes);
-    float*  sDith = reinterpret_cast<float*>(smem_raw + G::conv_bytes + G::x_bytes);
+    const float* sDith = g_dither32_f;
 
     const bool dup = prm.dup_q1 != 0;
     const int tile_x = blockIdx.x % prm.tiles_x, tile_y = blockIdx.x / prm.tiles_x;
     const int jx0 = tile_x * kCore, jy0 = tile_y * kCore;        // first convert-surface pixel of the tile core
 
-    for (int i = threadIdx.x; i < 1024; i += kThreads) sDith[i] = (float)g_dither32_fused[i] * 0.0009765625f;
 
     // ---- stage A
     {
@@ -389,7 +393,7 @@ k_fused2x(const __grid_constant__ FusedParams prm)
                 uint32_t code[2][3];
                 __half hv[2][3];
                 float2 dth = make_float2(0.f, 0.f);
-                if (FINAL) dth = *reinterpret_cast<const float2*>(sDith + ((y & 31) << 5) + (gx & 31));
+                if (FINAL) dth = __ldg(reinterpret_cast<const float2*>(sDith + ((y & 31) << 5) + (gx & 31)));
                 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     const float2 val = res[c][r];
@@ -436,13 +440,52 @@ k_fused2x(const __grid_constant__ FusedParams prm)
 }
 
 // ------------------------------------------------------------------------------------------------
+// 1:1 plans (no axis resampled): ConvertColorPass -> m_TexConvertOutput rounding -> [FinalPass | TextureCopyRect]
+// in one kernel, one thread per pixel (Process() with rSrc == dstRect or a pure offset, :3348-3352, :3178-3181)
+// ------------------------------------------------------------------------------------------------
+struct Fused1xParams {
+    SrcDesc     src;
+    ColorParams color;
+    SurfDesc    out;
+    int32_t     w1, h1, dst_x0, dst_y0;
+    int32_t     internal_fmt, final_pass;
+    float       Q;
+};
+
+__global__ void __launch_bounds__(256)
+k_fused1x(const __grid_constant__ Fused1xParams prm)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= prm.w1 || y >= prm.h1) return;
+    const int gx = prm.dst_x0 + x, gy = prm.dst_y0 + y;
+    if (gx < 0 || gy < 0 || gx >= prm.out.w || gy >= prm.out.h) return;
+    const f3 rgb = convert_color<-1>(prm.color, fetch_yuv(prm.src, prm.src.rect_l + x, prm.src.rect_t + y));
+    f3 p;                                                  // what a later pass samples from m_TexConvertOutput
+    p.x = rt_roundtrip(prm.internal_fmt, rgb.x); p.y = rt_roundtrip(prm.internal_fmt, rgb.y); p.z = rt_roundtrip(prm.internal_fmt, rgb.z);
+    if (prm.final_pass) {
+        const float d = g_dither32_f[((gy & 31) << 5) + (gx & 31)];
+        p.x = final_quant(p.x, prm.Q, d); p.y = final_quant(p.y, prm.Q, d); p.z = final_quant(p.z, prm.Q, d);
+    }
+    surf_store(prm.out, gx, gy, p);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static bool Periodic2x(const AxisTable& t, const float*, int) { return t.kind == SCALER_INTERP && (t.ntaps == 4 || t.ntaps == 6) && t.src_len * 2 == t.dst_len; }
 
+static bool Is1x(const FusedPlan& p)
+{
+    return p.ax.kind == SCALER_NONE && p.ay.kind == SCALER_NONE && p.ax.src_len == p.ax.dst_len && p.ay.src_len == p.ay.dst_len;
+}
+
 bool FusedSupported(const FusedPlan& p, const char** why)
 {
     auto no = [&](const char* w) { if (why) *why = w; return false; };
+    if (Is1x(p)) {
+        if (p.final_pass && p.out.fmt == MPCVR_SURF_RGBA16F) return no("no final pass into a float target");
+        return true;
+    }
     if (!p.two_pass) return no("fused kernel needs both axes resampled");
     if (!Periodic2x(p.ax, nullptr, 0) || !Periodic2x(p.ay, nullptr, 0)) return no("fused kernel covers exact 2x interpolation upscales");
     if (p.ax.ntaps != p.ay.ntaps || p.ax.dup_q1 != p.ay.dup_q1) return no("axes use different filters");
@@ -462,6 +505,8 @@ static cudaError_t LaunchT(const FusedParams& prm, cudaStream_t st)
     int dev = 0; cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
@@ -489,8 +534,31 @@ static cudaError_t LaunchS(const FusedParams& prm, int spec, int conv, cudaStrea
     return LaunchC<NT, SPEC_RUNTIME>(prm, conv, st);
 }
 
+static cudaError_t EnsureDither(cudaStream_t st)
+{
+    static bool done[64] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    k_init_dither<<<4, 256, 0, st>>>();
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return cudaGetLastError();
+}
+
 cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
 {
+    cudaError_t de = EnsureDither(st);
+    if (de != cudaSuccess) return de;
+    if (Is1x(p)) {
+        Fused1xParams q;
+        memset(&q, 0, sizeof(q));
+        q.src = p.src; q.color = p.color; q.out = p.out;
+        q.w1 = p.ax.src_len; q.h1 = p.ay.src_len; q.dst_x0 = p.ax.dst0; q.dst_y0 = p.ay.dst0;
+        q.internal_fmt = p.internal_fmt; q.final_pass = p.final_pass; q.Q = p.Q;
+        if (launches) *launches = 1;
+        const dim3 b(32, 8), g((q.w1 + 31) / 32, (q.h1 + 7) / 8);
+        k_fused1x<<<g, b, 0, st>>>(q);
+        return cudaGetLastError();
+    }
     FusedParams prm;
     memset(&prm, 0, sizeof(prm));
     prm.src = p.src; prm.color = p.color; prm.out = p.out;

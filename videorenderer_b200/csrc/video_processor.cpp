@@ -682,6 +682,7 @@ bool CB200VideoProcessor::PlanFused(const Tex2D& target, const CRect& dstRect, F
     fp.Q = (target.fmt == MPCVR_SURF_RGB10A2) ? 1023.0f : 255.0f;
     (void)dstRect;
     if (!FusedSupported(fp, why)) return false;
+    if (kx == SCALER_NONE && ky == SCALER_NONE) return true;             // 1:1 plan: convert (+ final) in one kernel
     // the 2x kernel assumes the table is periodic: output i = 2j+ph reads [j + b0 + ph, ...) with one of two weight vectors
     auto periodic = [&](const HostAxisTable& T, float* wE, float* wO, int& b0) {
         const int nt = T.ntaps;
