@@ -213,6 +213,7 @@ int32_t mpcvr_set_backbuffer_format(mpcvr* vp, int32_t fmt);                    
 int32_t mpcvr_bind_backbuffer(mpcvr* vp, void* device_ptr, size_t pitch);             /* NULL = internal buffer */
 int32_t mpcvr_get_backbuffer(mpcvr* vp, void** device_ptr, size_t* pitch, int32_t* w, int32_t* h, int32_t* fmt);
 int32_t mpcvr_read_backbuffer(mpcvr* vp, void* host_dst, size_t dst_pitch);           /* D2H copy of the presented frame */
+int32_t mpcvr_read_backbuffer_async(mpcvr* vp, void* pinned_host_dst, size_t dst_pitch); /* same, enqueued on the instance's stream; complete after mpcvr_wait_idle */
 /* GetCurentImage: runs Process() at source-rect size into B8G8R8X8, top-down, row pitch = dst_pitch
  * (Source/DX11VideoProcessor.cpp:3493-3608; BITMAPINFOHEADER omitted, pixels only). */
 int32_t mpcvr_get_current_image(mpcvr* vp, void* host_dst, size_t dst_pitch, int32_t* w, int32_t* h);

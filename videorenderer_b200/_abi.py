@@ -163,6 +163,7 @@ SIGNATURES = {
     "mpcvr_bind_backbuffer": (C.c_int32, [vp, vp, C.c_size_t]),
     "mpcvr_get_backbuffer": (C.c_int32, [vp, P(vp), P(C.c_size_t), P(C.c_int32), P(C.c_int32), P(C.c_int32)]),
     "mpcvr_read_backbuffer": (C.c_int32, [vp, vp, C.c_size_t]),
+    "mpcvr_read_backbuffer_async": (C.c_int32, [vp, vp, C.c_size_t]),
     "mpcvr_get_current_image": (C.c_int32, [vp, vp, C.c_size_t, P(C.c_int32), P(C.c_int32)]),
     "mpcvr_get_displayed_image": (C.c_int32, [vp, vp, C.c_size_t, P(C.c_int32), P(C.c_int32)]),
     "mpcvr_get_vp_info": (C.c_int32, [vp, C.c_char_p, C.c_size_t]),

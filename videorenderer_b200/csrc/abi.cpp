@@ -82,7 +82,8 @@ int32_t mpcvr_get_procamp(mpcvr* h, uint32_t flags, mpcvr_procamp* v) { VP_OR(MP
 int32_t mpcvr_set_backbuffer_format(mpcvr* h, int32_t fmt) { VP_OR(MPCVR_E_POINTER); GUARD(vp.SetBackbufferFormat(fmt)); }
 int32_t mpcvr_bind_backbuffer(mpcvr* h, void* p, size_t pitch) { VP_OR(MPCVR_E_POINTER); GUARD(vp.BindBackbuffer(p, pitch)); }
 int32_t mpcvr_get_backbuffer(mpcvr* h, void** p, size_t* pitch, int32_t* w, int32_t* hh, int32_t* fmt) { VP_OR(MPCVR_E_POINTER); return vp.GetBackbuffer(p, pitch, w, hh, fmt); }
-int32_t mpcvr_read_backbuffer(mpcvr* h, void* dst, size_t pitch) { VP_OR(MPCVR_E_POINTER); GUARD(vp.ReadBackbuffer(dst, pitch)); }
+int32_t mpcvr_read_backbuffer(mpcvr* h, void* dst, size_t pitch) { VP_OR(MPCVR_E_POINTER); GUARD(vp.ReadBackbuffer(dst, pitch, true)); }
+int32_t mpcvr_read_backbuffer_async(mpcvr* h, void* dst, size_t pitch) { VP_OR(MPCVR_E_POINTER); GUARD(vp.ReadBackbuffer(dst, pitch, false)); }
 int32_t mpcvr_get_current_image(mpcvr* h, void* dst, size_t pitch, int32_t* w, int32_t* hh) { VP_OR(MPCVR_E_POINTER); GUARD(vp.GetCurentImage(dst, pitch, w, hh)); }
 int32_t mpcvr_get_displayed_image(mpcvr* h, void* dst, size_t pitch, int32_t* w, int32_t* hh) { VP_OR(MPCVR_E_POINTER); GUARD(vp.GetDisplayedImage(dst, pitch, w, hh)); }
 int32_t mpcvr_get_vp_info(mpcvr* h, char* dst, size_t n) { VP_OR(MPCVR_E_POINTER); GUARD(vp.GetVPInfo(dst, n)); }

@@ -413,14 +413,14 @@ int32_t CB200VideoProcessor::GetBackbuffer(void** dev, size_t* pitch, int32_t* w
     return MPCVR_S_OK;
 }
 
-int32_t CB200VideoProcessor::ReadBackbuffer(void* host, size_t pitch)
+int32_t CB200VideoProcessor::ReadBackbuffer(void* host, size_t pitch, bool sync)
 {
     if (m_device < 0) return Fail(MPCVR_E_UNEXPECTED, "no CUDA device (planning-only instance)");
     Tex2D& t = CurrentTarget();
     if (!t.ptr || !host) return Fail(MPCVR_E_POINTER, "read_backbuffer: nothing to read");
     cudaSetDevice(m_device);
     if (!Cuda(cudaMemcpy2DAsync(host, pitch, t.ptr, t.pitch, (size_t)t.w * SurfBpp(t.fmt), t.h, cudaMemcpyDeviceToHost, m_stream), "D2H back buffer")) return MPCVR_E_FAIL;
-    if (!Cuda(cudaStreamSynchronize(m_stream), "sync")) return MPCVR_E_FAIL;
+    if (sync && !Cuda(cudaStreamSynchronize(m_stream), "sync")) return MPCVR_E_FAIL;
     return MPCVR_S_OK;
 }
 

@@ -104,7 +104,7 @@ public:
     int32_t SetBackbufferFormat(int fmt);
     int32_t BindBackbuffer(void* dev, size_t pitch);
     int32_t GetBackbuffer(void** dev, size_t* pitch, int32_t* w, int32_t* h, int32_t* fmt);
-    int32_t ReadBackbuffer(void* host, size_t pitch);
+    int32_t ReadBackbuffer(void* host, size_t pitch, bool sync = true);
     int32_t GetCurentImage(void* host, size_t pitch, int32_t* w, int32_t* h);  // sic, Source/VideoProcessor.h:220
     int32_t GetDisplayedImage(void* host, size_t pitch, int32_t* w, int32_t* h);
     int32_t GetVPInfo(char* dst, size_t n);
