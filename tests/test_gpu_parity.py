@@ -10,7 +10,7 @@ import orclib as O
 
 pytestmark = pytest.mark.gpu
 
-PATH_MULTIPASS, PATH_FUSED = 1, 2
+PATH_AUTO, PATH_MULTIPASS, PATH_FUSED = 0, 1, 2
 
 
 def _run_gpu(case, buf, pitch, path=PATH_MULTIPASS, capture=False):
@@ -22,13 +22,16 @@ def _run_gpu(case, buf, pitch, path=PATH_MULTIPASS, capture=False):
     return vp, out
 
 
-def _check(case, kind="noise", seed=0, path=PATH_MULTIPASS):
+def _check(case, kind="noise", seed=0, path=None):
+    """path None: both kernel families (multipass, and whatever the planner picks = fused when the plan has a fused form)"""
     codes = H.make_codes(case.cf, case.w, case.h, kind, seed)
     buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
     ref = H.run_oracle(case, planes, pitches)
-    vp, out = _run_gpu(case, buf, pitch, path)
-    n, d = H.compare(out, ref, case.backbuffer)
-    assert n == 0, "%s/%s: %d channel values differ (max delta %d)" % (case.name, kind, n, d)
+    vp = None
+    for p in ((PATH_MULTIPASS, PATH_AUTO) if path is None else (path,)):
+        vp, out = _run_gpu(case, buf, pitch, p)
+        n, d = H.compare(out, ref, case.backbuffer)
+        assert n == 0, "%s/%s path %d(%d): %d channel values differ (max delta %d)" % (case.name, kind, p, vp.debug_plan().path, n, d)
     return vp
 
 
@@ -249,17 +252,26 @@ def test_fused_2x_rects():
 
 
 def test_fused_falls_back_when_unsupported():
-    """plans outside the fused family must still render (multipass) under PATH_AUTO, and fail loudly under PATH_FUSED"""
+    """plans whose tile window cannot fit in shared memory must still render (multipass) under PATH_AUTO, and fail loudly under PATH_FUSED"""
     import videorenderer_b200 as V
-    case = H.Case(O.CF["NV12"], 64, 36, 96, 54, H.EX_709, up=O.UPSCALE["Lanczos3"], name="not2x")
+    case = H.Case(O.CF["NV12"], 1024, 512, 64, 32, H.EX_709, down=O.DOWNSCALE["Lanczos"], name="huge_downscale")
     codes = H.make_codes(case.cf, case.w, case.h, "noise", 1)
     buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    ref = H.run_oracle(case, planes, pitches)
     vp = case.make_processor(device=0, path=0)
     vp.ProcessSample(data=buf, pitch=pitch)
     assert vp.debug_plan().path == PATH_MULTIPASS
+    assert H.compare(vp.ReadBackbuffer(), ref, case.backbuffer) == (0, 0)
     vp = case.make_processor(device=0, path=PATH_FUSED)
     hr = vp.ProcessSample(data=buf, pitch=pitch, check=False)
     assert hr == V.HRESULT.E_NOTIMPL
+
+
+def test_generic_fused_covers_the_baseline_configs():
+    """every single-GPU BASELINE config runs as ONE kernel per frame (C1: 1:1 kernel, C2: 2x kernel, C3/C4: generic kernel)"""
+    for case in H.baseline_cases(scale=0.125):
+        vp = _check_fused(case, "natural", 51)
+        assert vp.LastFrameKernels() == 1
 
 
 @pytest.mark.parametrize("kind", ["ramp", "noise", "natural"])

@@ -470,9 +470,139 @@ k_fused1x(const __grid_constant__ Fused1xParams prm)
 }
 
 // ------------------------------------------------------------------------------------------------
+// generic fused kernel: ANY plan (arbitrary ratios, interpolation / convolution / point-sampled axes, any tap count)
+// whose per-tile source window fits in shared memory.  Same three stages, table driven; no register blocking.
+// ------------------------------------------------------------------------------------------------
+struct FusedGenParams {
+    SrcDesc     src;
+    ColorParams color;
+    SurfDesc    out;
+    AxisTable   ax, ay;
+    int32_t     w1, h1;
+    int32_t     internal_fmt, final_pass, two_pass;
+    float       Q;
+    int32_t     otw, oth, tiles_x, tiles_y;
+    int32_t     win_w, win_h, win_wp;       // maximum source window of a tile (floats per row: win_wp)
+};
+
+__global__ void __launch_bounds__(256, 2)
+k_fused_generic(const __grid_constant__ FusedGenParams prm)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sConv = reinterpret_cast<float*>(smem_raw);                                   // [3][win_h][win_wp]
+    float* sX    = sConv + (size_t)3 * prm.win_h * prm.win_wp;                           // [3][win_h][otw]
+    const AxisTable& ax = prm.ax; const AxisTable& ay = prm.ay;
+    const int tile_x = blockIdx.x % prm.tiles_x, tile_y = blockIdx.x / prm.tiles_x;
+    const int ox0 = tile_x * prm.otw, oy0 = tile_y * prm.oth;
+    const int ow = min(prm.otw, ax.dst_len - ox0), oh = min(prm.oth, ay.dst_len - oy0);
+    const int sx_lo = __ldg(ax.base + ox0), sy_lo = __ldg(ay.base + oy0);
+    const int ww = __ldg(ax.base + ox0 + ow - 1) + ax.ntaps - sx_lo, wh = __ldg(ay.base + oy0 + oh - 1) + ay.ntaps - sy_lo;
+    const int plane = prm.win_h * prm.win_wp, xplane = prm.win_h * prm.otw;
+
+    // stage A: convert the window (CLAMP addressing of the taps)
+    for (int idx = threadIdx.x; idx < ww * wh; idx += blockDim.x) {
+        const int ty = idx / ww, tx = idx - ty * ww;
+        const int cx = clampi(sx_lo + tx, 0, prm.w1 - 1), cy = clampi(sy_lo + ty, 0, prm.h1 - 1);
+        const f3 rgb = convert_color<-1>(prm.color, fetch_yuv(prm.src, prm.src.rect_l + cx, prm.src.rect_t + cy));
+        float* d = sConv + ty * prm.win_wp + tx;
+        d[0] = rt_roundtrip(prm.internal_fmt, rgb.x); d[plane] = rt_roundtrip(prm.internal_fmt, rgb.y); d[2 * plane] = rt_roundtrip(prm.internal_fmt, rgb.z);
+    }
+    __syncthreads();
+
+    // stage B: X pass (TextureResizeShader AXIS 0), rows of the window x outputs of the tile
+    for (int idx = threadIdx.x; idx < wh * ow; idx += blockDim.x) {
+        const int row = idx / ow, x = idx - row * ow, i = ox0 + x;
+        const int b = __ldg(ax.base + i) - sx_lo;
+        const float* w = ax.w + (size_t)i * ax.ntaps;
+        const float* src = sConv + row * prm.win_wp + b;
+        f3 acc = {0.f, 0.f, 0.f};
+        for (int k = 0; k < ax.ntaps; k++) {
+            const int kk = (ax.dup_q1 && k == 1) ? 0 : k;
+            const float wk = __ldg(w + k);
+            const float p0 = src[kk], p1 = src[plane + kk], p2 = src[2 * plane + kk];
+            if (k == 0 && ax.kind != SCALER_CONV) { acc.x = __fmul_rn(wk, p0); acc.y = __fmul_rn(wk, p1); acc.z = __fmul_rn(wk, p2); }
+            else { acc.x = fma_rn(wk, p0, acc.x); acc.y = fma_rn(wk, p1, acc.y); acc.z = fma_rn(wk, p2, acc.z); }
+        }
+        if (ax.kind == SCALER_CONV) { const float s = __ldg(ax.wsum + i); acc.x = __fdiv_rn(acc.x, s); acc.y = __fdiv_rn(acc.y, s); acc.z = __fdiv_rn(acc.z, s); }
+        if (prm.two_pass) { acc.x = f16_roundtrip(acc.x); acc.y = f16_roundtrip(acc.y); acc.z = f16_roundtrip(acc.z); }   // m_TexResize
+        float* d = sX + row * prm.otw + x;
+        d[0] = acc.x; d[xplane] = acc.y; d[2 * xplane] = acc.z;
+    }
+    __syncthreads();
+
+    // stage C: Y pass, output rounding, final pass
+    for (int idx = threadIdx.x; idx < oh * ow; idx += blockDim.x) {
+        const int y = idx / ow, x = idx - y * ow, j = oy0 + y;
+        const int gx = ax.dst0 + ox0 + x, gy = ay.dst0 + j;
+        if (gx < 0 || gy < 0 || gx >= prm.out.w || gy >= prm.out.h) continue;
+        const int b = __ldg(ay.base + j) - sy_lo;
+        const float* w = ay.w + (size_t)j * ay.ntaps;
+        const float* src = sX + b * prm.otw + x;
+        f3 acc = {0.f, 0.f, 0.f};
+        for (int k = 0; k < ay.ntaps; k++) {
+            const int kk = ((ay.dup_q1 && k == 1) ? 0 : k) * prm.otw;
+            const float wk = __ldg(w + k);
+            const float p0 = src[kk], p1 = src[xplane + kk], p2 = src[2 * xplane + kk];
+            if (k == 0 && ay.kind != SCALER_CONV) { acc.x = __fmul_rn(wk, p0); acc.y = __fmul_rn(wk, p1); acc.z = __fmul_rn(wk, p2); }
+            else { acc.x = fma_rn(wk, p0, acc.x); acc.y = fma_rn(wk, p1, acc.y); acc.z = fma_rn(wk, p2, acc.z); }
+        }
+        if (ay.kind == SCALER_CONV) { const float s = __ldg(ay.wsum + j); acc.x = __fdiv_rn(acc.x, s); acc.y = __fdiv_rn(acc.y, s); acc.z = __fdiv_rn(acc.z, s); }
+        if (prm.final_pass) {
+            const float d = g_dither32_f[((gy & 31) << 5) + (gx & 31)];
+            acc.x = final_quant(rt_roundtrip(prm.internal_fmt, acc.x), prm.Q, d);
+            acc.y = final_quant(rt_roundtrip(prm.internal_fmt, acc.y), prm.Q, d);
+            acc.z = final_quant(rt_roundtrip(prm.internal_fmt, acc.z), prm.Q, d);
+        }
+        surf_store(prm.out, gx, gy, acc);
+    }
+}
+
+// per-tile source window bound of an axis table for output tiles of `ot` outputs
+static int MaxWindow(const int32_t* base, int ntaps, int dst_len, int ot)
+{
+    int m = 0;
+    for (int o0 = 0; o0 < dst_len; o0 += ot) {
+        const int o1 = (o0 + ot < dst_len ? o0 + ot : dst_len) - 1;
+        const int w = base[o1] + ntaps - base[o0];
+        if (w > m) m = w;
+    }
+    return m;
+}
+
+static bool PlanGeneric(const FusedPlan& p, FusedGenParams& g, size_t* smem)
+{
+    static const int cand[][2] = {{64, 32}, {32, 32}, {32, 16}, {16, 16}, {16, 8}};
+    if (!p.hbase_x || !p.hbase_y) return false;
+    for (const auto& c : cand) {
+        const int ww = MaxWindow(p.hbase_x, p.ax.ntaps, p.ax.dst_len, c[0]), wh = MaxWindow(p.hbase_y, p.ay.ntaps, p.ay.dst_len, c[1]);
+        const int wwp = (ww + 3) & ~3;
+        const size_t bytes = ((size_t)3 * wh * wwp + (size_t)3 * wh * c[0]) * sizeof(float);
+        if (bytes <= 110 * 1024) {
+            g.otw = c[0]; g.oth = c[1]; g.win_w = ww; g.win_h = wh; g.win_wp = wwp; *smem = bytes;
+            g.tiles_x = (p.ax.dst_len + c[0] - 1) / c[0]; g.tiles_y = (p.ay.dst_len + c[1] - 1) / c[1];
+            return true;
+        }
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static bool Periodic2x(const AxisTable& t, const float*, int) { return t.kind == SCALER_INTERP && (t.ntaps == 4 || t.ntaps == 6) && t.src_len * 2 == t.dst_len; }
+
+static bool Periodic2x(const AxisTable& t) { return t.kind == SCALER_INTERP && (t.ntaps == 4 || t.ntaps == 6) && t.src_len * 2 == t.dst_len; }
+
+// plans the register-blocked 2x kernel takes (the host additionally checks that the tables are 2-periodic: p.periodic2x)
+static bool Is2x(const FusedPlan& p)
+{
+    if (!p.two_pass || !p.periodic2x) return false;
+    if (!Periodic2x(p.ax) || !Periodic2x(p.ay)) return false;
+    if (p.ax.ntaps != p.ay.ntaps || p.ax.dup_q1 != p.ay.dup_q1) return false;
+    if (p.ax.src0 != 0 || p.ay.src0 != 0) return false;
+    if (p.ax.dst0 < 0 || p.ay.dst0 < 0 || p.ax.dst0 + p.ax.dst_len > p.out.w || p.ay.dst0 + p.ay.dst_len > p.out.h) return false;
+    if ((p.ax.dst0 & 1) || (p.out.pitch & 15) || ((uintptr_t)p.out.ptr & 15)) return false;
+    return true;
+}
 
 static bool Is1x(const FusedPlan& p)
 {
@@ -486,14 +616,11 @@ bool FusedSupported(const FusedPlan& p, const char** why)
         if (p.final_pass && p.out.fmt == MPCVR_SURF_RGBA16F) return no("no final pass into a float target");
         return true;
     }
-    if (!p.two_pass) return no("fused kernel needs both axes resampled");
-    if (!Periodic2x(p.ax, nullptr, 0) || !Periodic2x(p.ay, nullptr, 0)) return no("fused kernel covers exact 2x interpolation upscales");
-    if (p.ax.ntaps != p.ay.ntaps || p.ax.dup_q1 != p.ay.dup_q1) return no("axes use different filters");
-    if (p.ax.src0 != 0 || p.ay.src0 != 0) return no("convert surface origin must be 0");
-    if (p.ax.dst0 < 0 || p.ay.dst0 < 0 || p.ax.dst0 + p.ax.dst_len > p.out.w || p.ay.dst0 + p.ay.dst_len > p.out.h) return no("video rect leaves the target: clipped plans run multipass");
-    if ((p.ax.dst0 & 1) || (p.out.pitch & 15) || ((uintptr_t)p.out.ptr & 15)) return no("target alignment");
     if (p.final_pass && p.out.fmt == MPCVR_SURF_RGBA16F) return no("no final pass into a float target");
-    return true;
+    if (Is2x(p)) return true;
+    FusedGenParams g; size_t smem = 0;
+    if (PlanGeneric(p, g, &smem)) return true;
+    return no("the per-tile source window of this plan does not fit in shared memory: multipass");
 }
 
 template <int NT, int SPEC, int CONV>
@@ -557,6 +684,24 @@ cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
         if (launches) *launches = 1;
         const dim3 b(32, 8), g((q.w1 + 31) / 32, (q.h1 + 7) / 8);
         k_fused1x<<<g, b, 0, st>>>(q);
+        return cudaGetLastError();
+    }
+    if (!Is2x(p)) {
+        FusedGenParams g; size_t smem = 0;
+        memset(&g, 0, sizeof(g));
+        if (!PlanGeneric(p, g, &smem)) return cudaErrorNotSupported;
+        g.src = p.src; g.color = p.color; g.out = p.out; g.ax = p.ax; g.ay = p.ay;
+        g.w1 = p.ax.src_len; g.h1 = p.ay.src_len;
+        g.internal_fmt = p.internal_fmt; g.final_pass = p.final_pass; g.two_pass = p.two_pass; g.Q = p.Q;
+        static bool configured[64] = {};
+        int dev = 0; cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(k_fused_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) configured[dev] = true;
+        }
+        if (launches) *launches = 1;
+        k_fused_generic<<<g.tiles_x * g.tiles_y, 256, smem, st>>>(g);
         return cudaGetLastError();
     }
     FusedParams prm;

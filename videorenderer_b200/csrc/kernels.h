@@ -33,6 +33,9 @@ struct FusedPlan {
     // exact-2x plans: the two weight vectors (even / odd outputs) and the window origin relative to j = i/2
     float       wE[8], wO[8];
     int32_t     b0;
+    int32_t     periodic2x;      // host verified the tables are 2-periodic
+    // host copies of the per-output window origins (tile sizing of the generic fused kernel)
+    const int32_t* hbase_x; const int32_t* hbase_y;
 };
 bool        FusedSupported(const FusedPlan& p, const char** why);
 cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches);

@@ -681,12 +681,11 @@ bool CB200VideoProcessor::PlanFused(const Tex2D& target, const CRect& dstRect, F
     fp.two_pass = ((kx == SCALER_INTERP || kx == SCALER_CONV) && (ky == SCALER_INTERP || ky == SCALER_CONV)) ? 1 : 0;
     fp.Q = (target.fmt == MPCVR_SURF_RGB10A2) ? 1023.0f : 255.0f;
     (void)dstRect;
-    if (!FusedSupported(fp, why)) return false;
-    if (kx == SCALER_NONE && ky == SCALER_NONE) return true;             // 1:1 plan: convert (+ final) in one kernel
-    // the 2x kernel assumes the table is periodic: output i = 2j+ph reads [j + b0 + ph, ...) with one of two weight vectors
+    fp.hbase_x = m_axisX.host.base.data(); fp.hbase_y = m_axisY.host.base.data();
+    // the register-blocked 2x kernel assumes periodic tables: output i = 2j+ph reads [j + b0 + ph, ...) with one of two weight vectors
     auto periodic = [&](const HostAxisTable& T, float* wE, float* wO, int& b0) {
         const int nt = T.ntaps;
-        if (T.dst_len < 2) return false;
+        if (T.kind != SCALER_INTERP || T.dst_len < 2 || T.src_len * 2 != T.dst_len || nt > 8) return false;
         b0 = T.base[0];
         for (int k = 0; k < nt; k++) { wE[k] = T.w[k]; wO[k] = T.w[nt + k]; }
         for (int i = 0; i < T.dst_len; i++) {
@@ -696,12 +695,10 @@ bool CB200VideoProcessor::PlanFused(const Tex2D& target, const CRect& dstRect, F
         return true;
     };
     float wE2[8], wO2[8]; int b0y = 0;
-    if (!periodic(m_axisX.host, fp.wE, fp.wO, fp.b0) || !periodic(m_axisY.host, wE2, wO2, b0y) || b0y != fp.b0 ||
-        memcmp(fp.wE, wE2, m_axisX.host.ntaps * sizeof(float)) != 0 || memcmp(fp.wO, wO2, m_axisX.host.ntaps * sizeof(float)) != 0) {
-        if (why) *why = "resize table is not 2x-periodic";
-        return false;
-    }
-    return true;
+    fp.periodic2x = (periodic(m_axisX.host, fp.wE, fp.wO, fp.b0) && periodic(m_axisY.host, wE2, wO2, b0y) && b0y == fp.b0 &&
+                     m_axisX.host.ntaps == m_axisY.host.ntaps &&
+                     memcmp(fp.wE, wE2, m_axisX.host.ntaps * sizeof(float)) == 0 && memcmp(fp.wO, wO2, m_axisX.host.ntaps * sizeof(float)) == 0) ? 1 : 0;
+    return FusedSupported(fp, why);
 }
 
 // ------------------------------------------------------------------------------------------------
