@@ -28,8 +28,12 @@ def _check(case, kind="noise", seed=0, path=None):
     buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
     ref = H.run_oracle(case, planes, pitches)
     vp = None
-    for p in ((PATH_MULTIPASS, PATH_AUTO) if path is None else (path,)):
-        vp, out = _run_gpu(case, buf, pitch, p)
+    for p in ((PATH_MULTIPASS, PATH_AUTO, PATH_FUSED) if path is None else (path,)):
+        try:
+            vp, out = _run_gpu(case, buf, pitch, p)
+        except Exception as e:        # PATH_FUSED on a plan without a fused form must fail with E_NOTIMPL, nothing else
+            assert p == PATH_FUSED and path is None and "80004001" in str(e).lower(), e
+            continue
         n, d = H.compare(out, ref, case.backbuffer)
         assert n == 0, "%s/%s path %d(%d): %d channel values differ (max delta %d)" % (case.name, kind, p, vp.debug_plan().path, n, d)
     return vp

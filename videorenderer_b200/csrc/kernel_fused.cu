@@ -609,6 +609,12 @@ static bool Is1x(const FusedPlan& p)
     return p.ax.kind == SCALER_NONE && p.ay.kind == SCALER_NONE && p.ax.src_len == p.ax.dst_len && p.ay.src_len == p.ay.dst_len;
 }
 
+int FusedKind(const FusedPlan& p)
+{
+    if (!FusedSupported(p, nullptr)) return 0;
+    return Is1x(p) ? 1 : (Is2x(p) ? 2 : 3);
+}
+
 bool FusedSupported(const FusedPlan& p, const char** why)
 {
     auto no = [&](const char* w) { if (why) *why = w; return false; };

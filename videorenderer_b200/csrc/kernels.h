@@ -38,6 +38,8 @@ struct FusedPlan {
     const int32_t* hbase_x; const int32_t* hbase_y;
 };
 bool        FusedSupported(const FusedPlan& p, const char** why);
+// which fused kernel would run: 1 = 1:1 kernel, 2 = register-blocked 2x kernel, 3 = generic table-driven kernel, 0 = none
+int         FusedKind(const FusedPlan& p);
 cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches);
 
 // PQ->SDR convert body, scalar (mode 0) vs two-lane (mode 1) forms, on arrays of normalised y,u,v (test hook)

@@ -633,7 +633,9 @@ int32_t CB200VideoProcessor::Process(const Tex2D& target, const CRect& srcRect, 
     // ---- fused family
     if (!skipConvert && m_forcePath != MPCVR_PATH_MULTIPASS) {
         FusedPlan fp; const char* why = nullptr;
-        if (PlanFused(target, dstRect, fp, &why)) {
+        // PATH_AUTO takes the specialised fused kernels (1:1, 2x); the generic table-driven fused kernel is currently slower than
+        // the multipass chain on compute-bound plans (profiles/r01e_bench_all_configs.jsonl), so it runs only on request
+        if (PlanFused(target, dstRect, fp, &why) && (m_forcePath == MPCVR_PATH_FUSED || FusedKind(fp) != 3)) {
             if (!covers) { m_lastLaunches++; if (!Cuda(LaunchClear(target.desc(), m_stream), "clear")) return MPCVR_E_FAIL; }
             int launches = 0;
             if (!Cuda(LaunchFused(fp, m_stream, &launches), "fused frame kernel")) return MPCVR_E_FAIL;
