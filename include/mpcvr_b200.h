@@ -107,7 +107,9 @@ typedef struct mpcvr_rect { int32_t left, top, right, bottom; } mpcvr_rect;
 typedef enum mpcvr_surface_format {
     MPCVR_SURF_BGRA8 = 0,     /* DXGI_FORMAT_B8G8R8A8_UNORM: bytes B,G,R,A                */
     MPCVR_SURF_RGB10A2 = 1,   /* DXGI_FORMAT_R10G10B10A2_UNORM: R bits 0-9, G 10-19, B 20-29, A 30-31 */
-    MPCVR_SURF_RGBA16F = 2    /* DXGI_FORMAT_R16G16B16A16_FLOAT                           */
+    MPCVR_SURF_RGBA16F = 2,   /* DXGI_FORMAT_R16G16B16A16_FLOAT                           */
+    MPCVR_SURF_RGBA16 = 3     /* DXGI_FORMAT_R16G16B16A16_UNORM: internal only (16-bit RGB sources read without a convert
+                                 pass, Source/DX11VideoProcessor.cpp:3320-3322); not a back-buffer format */
 } mpcvr_surface_format;
 
 /* What CMediaType / VIDEOINFOHEADER2 carry into VerifyMediaType / InitMediaType
@@ -123,6 +125,9 @@ typedef struct mpcvr_media_type {
     uint32_t   ext_format;        /* DXVA2_ExtendedFormat.value taken from dwControlFlags (0 = none)  */
     int32_t    interlaced;        /* dwInterlaceFlags & AMINTERLACE_IsInterlaced                      */
     int64_t    avg_time_per_frame;/* REFERENCE_TIME, 100 ns units                                     */
+    int32_t    bottom_up;         /* biCompression == BI_RGB && biHeight > 0: rows are stored last-to-first and the
+                                     pitch is negated (Source/DX11VideoProcessor.cpp:1801-1803)                   */
+    int32_t    reserved;
 } mpcvr_media_type;
 
 /* IMediaSideData blobs (Include/IMediaSideData.h:35-60); layouts identical (pack 1). */

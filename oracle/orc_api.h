@@ -21,7 +21,7 @@ uint32_t orc_specify_extended_format(uint32_t ex, int cstype, int subsampling, i
 /* ---- format table (orc_fmt.c), Source/Helper.cpp:309-359 ---- */
 typedef struct orc_fmt {
     int32_t cformat;
-    int32_t layout;        /* 0 none, 1 biplanar, 2 planar3, 3 packed422, 4 packed444 */
+    int32_t layout;        /* 0 none, 1 biplanar, 2 planar3, 3 packed422, 4 packed444, 5 rgb texel, 6 gray plane */
     int32_t bytes;         /* bytes per stored component */
     int32_t cdepth;        /* CDepth column */
     int32_t cstype;        /* 0 YUV 1 RGB 2 GRAY */
@@ -34,6 +34,8 @@ typedef struct orc_fmt {
     const char* name;
 } orc_fmt;
 const orc_fmt* orc_get_fmt(int cformat);
+/* sample buffer -> source texture memory (the CopyFrame* family, Source/Helper.cpp:377-803); -1 = no repack for this format */
+int orc_repack(int cformat, int width, int lines, const uint8_t* src, int src_pitch, uint8_t* dst, int dst_pitch);
 
 /* ---- dither matrix (orc_dither.c): thresholds k with D[y][x] = k/1024 ---- */
 const uint16_t* orc_dither_thresholds(void);   /* 1024 entries, row-major 32x32 */

@@ -36,7 +36,8 @@ enum { ORC_DOWNSCALE_Box = 0, ORC_DOWNSCALE_Bilinear, ORC_DOWNSCALE_Hamming, ORC
        ORC_DOWNSCALE_BicubicSharp, ORC_DOWNSCALE_Lanczos };
 
 /* surface formats (DXGI names in the reference): m_InternalTexFmt / m_SwapChainFmt */
-enum { ORC_SURF_BGRA8 = 0, ORC_SURF_RGB10A2 = 1, ORC_SURF_RGBA16F = 2 };
+enum { ORC_SURF_BGRA8 = 0, ORC_SURF_RGB10A2 = 1, ORC_SURF_RGBA16F = 2,
+       ORC_SURF_RAW = 3 /* oracle-internal: values as sampled from the source texture (no render-target write) */ };
 
 /* shader variant: which twin of the HLSL files is restated */
 enum { ORC_VARIANT_D3D11 = 0, ORC_VARIANT_D3D9 = 1 };

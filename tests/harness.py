@@ -32,6 +32,8 @@ def make_codes(cf, w, h, kind="noise", seed=0):
     bits = 8 if f.bytes == 1 else (10 if (name in ("P010", "Y210", "Y410") or f.lsb_shift) else 16)
     if name in ("P016", "P216", "Y216", "Y416") or (f.bytes == 2 and not f.lsb_shift and name.endswith("16")):
         bits = 16
+    if name in ("v210", "r210"):
+        bits = 10
     cw, ch = w // f.div_w, h // f.div_h
     maxc = (1 << bits) - 1
     (ylo, yhi), (clo, chi) = _legal_ranges(bits)
@@ -57,7 +59,62 @@ def make_codes(cf, w, h, kind="noise", seed=0):
     return dict(Y=Y, U=U, V=V, bits=bits)
 
 
-def pack(cf, w, h, codes, pitch=None):
+def _pack_rgb_sample(name, w, h, R, G, B, bottom_up):
+    """RGB sample buffers as a DirectShow source hands them over (byte layouts per Source/Helper.cpp:345-354 comments and the
+    FOURCC definitions); returns (buf, pitch>0)."""
+    A8, A16 = 255, 65535
+    if name == "RGB24":
+        pitch = (w * 3 + 3) // 4 * 4
+        buf = np.zeros((h, pitch), np.uint8)
+        px = buf[:, :w * 3].reshape(h, w, 3); px[..., 0] = B; px[..., 1] = G; px[..., 2] = R
+    elif name in ("RGB32", "ARGB32"):
+        pitch = w * 4
+        buf = np.zeros((h, pitch), np.uint8)
+        px = buf.reshape(h, w, 4); px[..., 0] = B; px[..., 1] = G; px[..., 2] = R; px[..., 3] = A8 if name == "RGB32" else 0x80
+    elif name == "r210":
+        pitch = w * 4
+        word = (R.astype(np.uint32) << 20) | (G.astype(np.uint32) << 10) | B.astype(np.uint32)
+        buf = np.ascontiguousarray(word.astype(">u4")).view(np.uint8).reshape(h, pitch).copy()
+    elif name in ("RGB48", "BGR48"):
+        pitch = (w * 6 + 3) // 4 * 4 if name == "BGR48" else w * 6
+        buf = np.zeros((h, pitch), np.uint8)
+        px = buf[:, :w * 6].view("<u2").reshape(h, w, 3)
+        first, last = (R, B) if name == "RGB48" else (B, R)
+        px[..., 0] = first; px[..., 1] = G; px[..., 2] = last
+    elif name == "BGRA64":
+        pitch = w * 8
+        buf = np.zeros((h, pitch), np.uint8)
+        px = buf.view("<u2").reshape(h, w, 4); px[..., 0] = B; px[..., 1] = G; px[..., 2] = R; px[..., 3] = A16
+    elif name == "b64a":
+        pitch = w * 8
+        buf = np.zeros((h, pitch), np.uint8)
+        px = buf.view(">u2").reshape(h, w, 4); px[..., 0] = A16; px[..., 1] = R; px[..., 2] = G; px[..., 3] = B
+    else:
+        raise ValueError(name)
+    if bottom_up:
+        buf = buf[::-1].copy()
+    return buf.reshape(-1), pitch
+
+
+def _pack_v210(w, h, Y, U, V):
+    """SMPTE v210: 6 pixels in 4 little-endian words, 3 x 10 bit each; rows padded to 128 bytes"""
+    pitch = ((w + 5) // 6 * 16 + 127) // 128 * 128
+    groups = (w + 5) // 6
+    Yp = np.zeros((h, groups * 6), np.uint32); Yp[:, :w] = Y
+    Up = np.zeros((h, groups * 3), np.uint32); Up[:, :w // 2] = U
+    Vp = np.zeros((h, groups * 3), np.uint32); Vp[:, :w // 2] = V
+    words = np.zeros((h, groups, 4), np.uint32)
+    y = Yp.reshape(h, groups, 6); u = Up.reshape(h, groups, 3); v = Vp.reshape(h, groups, 3)
+    words[..., 0] = u[..., 0] | (y[..., 0] << 10) | (v[..., 0] << 20)
+    words[..., 1] = y[..., 1] | (u[..., 1] << 10) | (y[..., 2] << 20)
+    words[..., 2] = v[..., 1] | (y[..., 3] << 10) | (u[..., 2] << 20)
+    words[..., 3] = y[..., 4] | (v[..., 2] << 10) | (y[..., 5] << 20)
+    buf = np.zeros((h, pitch), np.uint8)
+    buf[:, :groups * 16] = words.astype("<u4").view(np.uint8).reshape(h, groups * 16)
+    return buf.reshape(-1), pitch
+
+
+def pack(cf, w, h, codes, pitch=None, bottom_up=False):
     """Pack code planes into the caller's frame buffer exactly as the reference expects it
     (layout walked by MemCopyToTexSrcVideo, Source/DX11VideoProcessor.cpp:1213-1252).
     Returns (buffer uint8[...], pitch, planes[list of np views], pitches)."""
@@ -66,6 +123,21 @@ def pack(cf, w, h, codes, pitch=None):
     Y, U, V, bits = codes["Y"], codes["U"], codes["V"], codes["bits"]
     layout = f.layout
     cw, ch = w // f.div_w, h // f.div_h
+    if layout == 5:      # RGB sample: the oracle sees the texture the reference's CPU repack produces (orc_repack)
+        buf, spitch = _pack_rgb_sample(name, w, h, Y, U, V, bottom_up)      # code planes "Y,U,V" carry R,G,B here
+        tex_pitch = w * (8 if f.packed_kind == 2 else 4)
+        tex = O.repack(cf, w, h, buf, -spitch if bottom_up else spitch, tex_pitch)
+        return buf, (-spitch if bottom_up else spitch), [tex.reshape(-1)], [tex_pitch]
+    if name == "v210":
+        buf, spitch = _pack_v210(w, h, Y, U, V)
+        tex = O.repack(cf, w, h, buf, spitch, w * 4)
+        return buf, spitch, [tex.reshape(-1)], [w * 4]
+    if layout == 6:      # gray plane
+        dtg = np.uint8 if f.bytes == 1 else np.uint16
+        pitch = pitch or ((w + 3) // 4 * 4 if name == "Y8" else w * f.packsize)
+        buf = np.zeros((h, pitch), np.uint8)
+        buf[:, :w * f.bytes].view(dtg)[:] = Y.astype(dtg)
+        return buf.reshape(-1), pitch, [buf.reshape(-1)], [pitch]
     if f.bytes == 1:
         dt = np.uint8; up = 0
     else:
@@ -127,7 +199,7 @@ class Case:
     def __init__(self, cf, w, h, dst_w, dst_h, ex, backbuffer=O.SURF_BGRA8, tex=O.TEXFMT_AUTOINT, chroma=O.CHROMA_Bilinear,
                  up=O.UPSCALE["CatmullRom"], down=O.DOWNSCALE["Hamming"], interp50=1, dither=1, to_sdr=1, nits=125,
                  src_rect=None, dst_rect=None, win=None, variant=O.VARIANT_D3D11, procamp=None, interlaced=0, deint_blend=0,
-                 name=None):
+                 name=None, bottom_up=0):
         self.__dict__.update(locals()); del self.__dict__["self"]
         self.name = name or "case"
 
@@ -152,7 +224,8 @@ class Case:
     def make_processor(self, device=0, path=None):
         import videorenderer_b200 as V
         vp = V.VideoProcessor(self.settings(), device=device)
-        mt = V.VideoProcessor.media_type(self.cf, self.w, self.h, self.ex, src_rect=self.src_rect, interlaced=self.interlaced)
+        mt = V.VideoProcessor.media_type(self.cf, self.w, self.h, self.ex, src_rect=self.src_rect, interlaced=self.interlaced,
+                                         bottom_up=self.bottom_up)
         assert vp.InitMediaType(mt), "InitMediaType failed: " + vp.last_error()
         if self.procamp:
             vp.SetProcAmpValues(**self.procamp)

@@ -11,7 +11,9 @@ ORC_DIR = os.path.join(ROOT, "oracle")
 # enums (oracle/orc_types.h == reference numeric values)
 CF = dict(NONE=0, NV12=1, P010=2, P016=3, YUY2=4, UYVY=5, P210=6, P216=7, Y210=8, Y216=9, V210=10, AYUV=11,
           Y410=12, Y416=13, YV12=14, YV16=15, YV24=16, YUV420P8=17, YUV422P8=18, YUV444P8=19, YUV420P10=20,
-          YUV420P16=21, YUV422P10=22, YUV422P16=23, YUV444P10=24, YUV444P16=25)
+          YUV420P16=21, YUV422P10=22, YUV422P16=23, YUV444P10=24, YUV444P16=25,
+          GBRP8=26, GBRP10=27, GBRP16=28, RGB24=29, XRGB32=30, ARGB32=31, r210=32, RGB48=33, BGR48=34, BGRA64=35,
+          B64A=36, Y8=37, Y10=38, Y16=39)
 SURF_BGRA8, SURF_RGB10A2, SURF_RGBA16F = 0, 1, 2
 MODE_SPEC, MODE_LITERAL, MODE_F64 = 0, 1, 2
 VARIANT_D3D11, VARIANT_D3D9 = 0, 1
@@ -85,6 +87,8 @@ def lib():
         L.orc_set_colorspace.argtypes = [C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_specify_extended_format.restype = C.c_uint32
         L.orc_specify_extended_format.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_repack.restype = C.c_int
+        L.orc_repack.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.orc_get_fmt.restype = C.POINTER(OrcFmt)
         L.orc_get_fmt.argtypes = [C.c_int]
         L.orc_dither_thresholds.restype = C.POINTER(C.c_uint16)
@@ -113,6 +117,31 @@ def ref():
         R.ref_gamut_matrix.argtypes = [C.c_int, C.c_int, C.c_void_p]
         _ref = R
     return _ref
+
+
+_refcopy = None
+
+
+def ref_copy():
+    """the reference's own CopyFrame* functions compiled in place (None when not built / not shipped)"""
+    global _refcopy
+    if _refcopy is None:
+        path = os.path.join(ORC_DIR, "_ref", "libref_copy.so")
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.ref_copy_frame.restype = C.c_int
+        R.ref_copy_frame.argtypes = [C.c_int, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_int]
+        _refcopy = R
+    return _refcopy
+
+
+def repack(cformat, width, lines, src, src_pitch, dst_pitch):
+    """orc_repack: sample buffer -> source texture memory; src_pitch < 0 = bottom-up DIB (src = start of the buffer)"""
+    dst = np.zeros((lines, dst_pitch), np.uint8)
+    rc = lib().orc_repack(cformat, width, lines, src.ctypes.data, src_pitch, dst.ctypes.data, dst_pitch)
+    assert rc == 0, rc
+    return dst
 
 
 def csp_matrix(ex, cdepth, gray=0, brightness=0.0, contrast=1.0, hue=0.0, saturation=1.0):

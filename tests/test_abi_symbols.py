@@ -30,7 +30,7 @@ def test_struct_layouts_match_header():
     # sizes the C side was compiled with (any drift between include/mpcvr_b200.h and _abi.py shows up here)
     assert ctypes.sizeof(_abi.Settings) == 33 * 4
     assert ctypes.sizeof(_abi.Rect) == 16
-    assert ctypes.sizeof(_abi.MediaType) == 5 * 4 + 16 + 4 * 4 + 4 + 8
+    assert ctypes.sizeof(_abi.MediaType) == 5 * 4 + 16 + 4 * 4 + 4 + 8 + 2 * 4
     assert ctypes.sizeof(_abi.SideDataHDR) == 80 and ctypes.sizeof(_abi.SideDataHDRCLL) == 8   # Include/IMediaSideData.h:35-60, pack(1)
     assert ctypes.sizeof(_abi.PlanInfo) == 14 * 4
     s = _abi.Sample()

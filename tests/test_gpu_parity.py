@@ -25,7 +25,7 @@ def _run_gpu(case, buf, pitch, path=PATH_MULTIPASS, capture=False):
 def _check(case, kind="noise", seed=0, path=None):
     """path None: both kernel families (multipass, and whatever the planner picks = fused when the plan has a fused form)"""
     codes = H.make_codes(case.cf, case.w, case.h, kind, seed)
-    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes, bottom_up=bool(case.bottom_up))
     ref = H.run_oracle(case, planes, pitches)
     vp = None
     for p in ((PATH_MULTIPASS, PATH_AUTO, PATH_FUSED) if path is None else (path,)):
@@ -77,7 +77,7 @@ def test_integer_stages_from_oracle_intermediate():
     assert H.compare(out, ref, case.backbuffer) == (0, 0)
 
 
-FORMATS = ["NV12", "P010", "P016", "YUY2", "UYVY", "P210", "P216", "Y210", "Y216", "AYUV", "Y410", "Y416", "YV12", "YV16",
+FORMATS = ["NV12", "P010", "P016", "YUY2", "UYVY", "P210", "P216", "Y210", "Y216", "V210", "AYUV", "Y410", "Y416", "YV12", "YV16",
            "YV24", "YUV420P8", "YUV422P8", "YUV444P8", "YUV420P10", "YUV420P16", "YUV422P10", "YUV422P16", "YUV444P10",
            "YUV444P16"]
 
@@ -361,3 +361,50 @@ def test_fused_c1_full_size():
     case = H.baseline_cases(1.0)[0]
     vp = _check_fused(case, "natural", 43)
     assert vp.LastFrameKernels() == 1
+
+
+# ---- RGB / planar RGB / gray samples (read in their own byte layout; the oracle goes through the reference's
+#      CPU repack into a DXGI texture first) ----
+RGB_SAMPLES = ["RGB24", "XRGB32", "ARGB32", "r210", "RGB48", "BGR48", "BGRA64", "B64A"]
+PLANAR_GRAY = ["GBRP8", "GBRP10", "GBRP16", "Y8", "Y10", "Y16"]
+PROCAMP = dict(brightness=12.0, contrast=1.25)
+
+
+@pytest.mark.parametrize("name", RGB_SAMPLES + PLANAR_GRAY)
+@pytest.mark.parametrize("procamp", [None, PROCAMP], ids=["default", "procamp"])
+def test_rgb_and_gray_inputs_upscale(name, procamp):
+    """default ProcAmp + RGB sample = no convert pass (the chain samples the source itself, DX11VideoProcessor.cpp:3320-3322)"""
+    _check(H.Case(O.CF[name], 64, 36, 96, 54, 0, up=O.UPSCALE["Lanczos3"], procamp=procamp, name=name), "fullnoise", seed=11)
+
+
+@pytest.mark.parametrize("name", ["RGB24", "r210", "RGB48", "GBRP10", "Y16"])
+@pytest.mark.parametrize("backbuffer", [O.SURF_BGRA8, O.SURF_RGB10A2])
+def test_rgb_inputs_one_to_one_and_final_pass(name, backbuffer):
+    """no scaling: plain copy, or the final pass dithering straight from the source ("pTex = pInputTexture", :3350-3352)"""
+    _check(H.Case(O.CF[name], 80, 45, 80, 45, 0, backbuffer=backbuffer, up=O.UPSCALE["Nearest"], name=name), "fullnoise", seed=12)
+
+
+@pytest.mark.parametrize("name", ["XRGB32", "BGRA64", "GBRP8"])
+def test_rgb_inputs_downscale_and_crop(name):
+    """convolution downscale of a cropped source rect: without a convert pass the taps outside the rect are real texels"""
+    _check(H.Case(O.CF[name], 160, 90, 50, 31, 0, down=O.DOWNSCALE["Lanczos"], src_rect=(16, 8, 144, 80), name=name), "natural", seed=13)
+    _check(H.Case(O.CF[name], 160, 90, 200, 120, 0, up=O.UPSCALE["CatmullRom"], src_rect=(16, 8, 144, 80), dst_rect=(10, 6, 190, 110),
+                  win=(200, 120), name=name), "fullnoise", seed=14)
+
+
+@pytest.mark.parametrize("name", ["RGB24", "XRGB32"])
+@pytest.mark.parametrize("procamp", [None, PROCAMP], ids=["default", "procamp"])
+def test_bottom_up_dib(name, procamp):
+    """BI_RGB with positive biHeight: rows stored last to first, negative pitch (:1801-1803, :1246)"""
+    _check(H.Case(O.CF[name], 62, 33, 93, 50, 0, up=O.UPSCALE["Mitchell"], procamp=procamp, bottom_up=1, name=name + "_bu"), "fullnoise", seed=15)
+
+
+def test_v210_equals_y210():
+    """the same codes delivered as v210 words and as Y210 give the same picture"""
+    outs = []
+    for name in ("V210", "Y210"):
+        case = H.Case(O.CF[name], 66, 30, 99, 45, H.EX_709, chroma=O.CHROMA_CatmullRom, up=O.UPSCALE["Lanczos2"], name=name)
+        codes = H.make_codes(O.CF["Y210"], 66, 30, "fullnoise", 16)
+        buf, pitch, _, _ = H.pack(case.cf, 66, 30, codes)
+        outs.append(_run_gpu(case, buf, pitch)[1])
+    assert np.array_equal(outs[0], outs[1])

@@ -141,8 +141,12 @@ def test_media_type_rules():
     assert vp.InitMediaType(mt)
     assert vp.GetSourceRect() == (0, 0, 1920, 1080) and vp.debug_plan().src_pitch == 2048
     # rejects
-    assert not vp.VerifyMediaType(V.VideoProcessor.media_type(V.CF.RGB24, 64, 64))      # RGB inputs: next row
-    assert not vp.VerifyMediaType(V.VideoProcessor.media_type(V.CF.V210, 64, 64))
+    # RGB / v210 samples: pitch rules of InitMediaType (:1789-1803): RGB24 rows align to 4, v210 to 128, BI_RGB bottom-up negates
+    assert vp.InitMediaType(V.VideoProcessor.media_type(V.CF.RGB24, 62, 64, bottom_up=1))
+    assert vp.debug_plan().src_pitch == -188 and vp.debug_plan().src_lines == 64
+    assert vp.InitMediaType(V.VideoProcessor.media_type(V.CF.V210, 1280, 64))
+    assert vp.debug_plan().src_pitch == (1280 + 5) // 6 * 16 // 128 * 128 + 128
+    assert vp.InitMediaType(V.VideoProcessor.media_type(V.CF.BGR48, 63, 64)) and vp.debug_plan().src_pitch == 380
     assert not vp.VerifyMediaType(V.VideoProcessor.media_type(V.CF.NONE, 64, 64))
     assert not vp.VerifyMediaType(V.VideoProcessor.media_type(V.CF.NV12, 0, 64))
     assert not vp.InitMediaType(V.VideoProcessor.media_type(V.CF.NV12, 64, 64, src_rect=(0, 0, 100, 64)))

@@ -226,3 +226,59 @@ def test_edge_cases_oracle():
     buf, pitch, planes, pitches = H.pack(case.cf, 32, 32, codes)
     out = H.rgb_view(H.run_oracle(case, planes, pitches), O.SURF_BGRA8)
     assert out.min() == out.max() == 128
+
+
+@pytest.mark.skipif(O.ref() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_rgb_and_gray_matrices_match_reference_library():
+    """extfmt.value == 0 -> MP_CSP_RGB / PC levels (Source/Helper.cpp:953-957); RGB and gray sources incl. ProcAmp"""
+    R = O.ref()
+    rng = np.random.Generator(np.random.PCG64(1))
+    for gray in (0, 1):
+        for depth in (8, 10, 16):
+            for k in range(5):
+                b, ct = (0.0, 1.0) if k == 0 else (rng.uniform(-100, 100), rng.uniform(0, 2))
+                m, c = O.csp_matrix(0, depth, gray=gray, brightness=b, contrast=ct)
+                rm = np.zeros(9, np.float32); rc = np.zeros(3, np.float32)
+                R.ref_csp_matrix(6, 2, float(np.float32(b) / np.float32(255)), float(np.float32(ct)), 0.0, 1.0, gray, depth, rm.ctypes.data, rc.ctypes.data)
+                assert _bits(m) == _bits(rm) and _bits(c) == _bits(rc), (gray, depth, b, ct)
+
+
+@pytest.mark.skipif(O.ref_copy() is None, reason="oracle/_ref/libref_copy.so not built (reference tree absent)")
+@pytest.mark.parametrize("name,which,bpp_src,bpp_dst,ncmp", [
+    ("RGB24", 1, 3, 4, 3), ("RGB48", 2, 6, 8, 6), ("BGR48", 3, 6, 8, 6), ("BGRA64", 4, 8, 8, 8), ("B64A", 5, 8, 8, 8),
+    ("r210", 7, 4, 4, 4)])
+def test_repack_matches_reference_copy_functions(name, which, bpp_src, bpp_dst, ncmp):
+    """orc_repack vs the reference's CopyFrame* compiled where they lie (Source/Helper.cpp:446-787), incl. a bottom-up DIB"""
+    R = O.ref_copy()
+    rng = np.random.Generator(np.random.PCG64(which))
+    for w, h in ((16, 5), (37, 4), (64, 3)):
+        src_pitch = (w * bpp_src + 3) // 4 * 4 if name in ("RGB24", "BGR48") else w * bpp_src
+        src = rng.integers(0, 256, (h + 1) * src_pitch + 64, dtype=np.uint8)        # slack: the reference reads whole words
+        for bottom_up in ((0, 1) if name == "RGB24" else (0,)):
+            dst_pitch = w * bpp_dst
+            mine = O.repack(O.CF[name], w, h, src, -src_pitch if bottom_up else src_pitch, dst_pitch)
+            ref = np.zeros((h, dst_pitch + 64), np.uint8)
+            start = src.ctypes.data + (src_pitch * (h - 1) if bottom_up else 0)     # MemCopyToTexSrcVideo :1246
+            R.ref_copy_frame(which, h, ref.ctypes.data, dst_pitch + 64, start, -src_pitch if bottom_up else src_pitch)
+            a = mine.reshape(h, w, bpp_dst)[..., :ncmp]; b = ref[:, :dst_pitch].reshape(h, w, bpp_dst)[..., :ncmp]
+            if name == "RGB48":     # CopyFrameRGB48 (:541-565) has no remainder loop: the last w % 4 texels of a row stay unwritten
+                a = a[:, :w & ~3]; b = b[:, :w & ~3]
+            if name == "r210":                                                       # alpha bits are zero in both
+                assert np.array_equal(mine.reshape(h, w, 4), ref[:, :dst_pitch].reshape(h, w, 4))
+            assert np.array_equal(a, b), (name, w, h, bottom_up)
+
+
+@pytest.mark.skipif(O.ref_copy() is None, reason="oracle/_ref/libref_copy.so not built (reference tree absent)")
+def test_v210_repack_matches_reference_copy_function():
+    R = O.ref_copy()
+    rng = np.random.Generator(np.random.PCG64(9))
+    for w in (48, 96, 1280 // 4):
+        h = 3
+        src_pitch = ((w + 5) // 6 * 16 + 127) // 128 * 128
+        src = rng.integers(0, 256, h * src_pitch, dtype=np.uint8)
+        dst_pitch = w * 4                                                            # Y210 texture row: 8 bytes per 2 pixels
+        mine = O.repack(O.CF["V210"], w, h, src, src_pitch, dst_pitch)
+        ref = np.zeros((h, dst_pitch), np.uint8)
+        R.ref_copy_frame(6, h, ref.ctypes.data, dst_pitch, src.ctypes.data, src_pitch)
+        n = (w // 6) * 6 * 4                                                         # whole 6-pixel groups
+        assert np.array_equal(mine[:, :n], ref[:, :n]), w

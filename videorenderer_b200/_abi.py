@@ -88,7 +88,8 @@ class Rect(C.Structure):
 class MediaType(C.Structure):
     _fields_ = [("cformat", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("frame_width", C.c_int32),
                 ("frame_height", C.c_int32), ("src_rect", Rect), ("aspect_x", C.c_uint32), ("aspect_y", C.c_uint32),
-                ("ext_format", C.c_uint32), ("interlaced", C.c_int32), ("avg_time_per_frame", C.c_int64)]
+                ("ext_format", C.c_uint32), ("interlaced", C.c_int32), ("avg_time_per_frame", C.c_int64),
+                ("bottom_up", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SideDataHDR(C.Structure):

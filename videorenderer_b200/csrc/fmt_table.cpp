@@ -16,7 +16,7 @@ static const FmtConvParams s_table[MPCVR_CF_COUNT] = {
     {MPCVR_CF_P216,      "P216",      LAYOUT_BIPLANAR,  2,   2, 4, CS_YUV,  422, 16, 2, 1, 0, false, 0},
     {MPCVR_CF_Y210,      "Y210",      LAYOUT_PACKED422, 2,   4, 2, CS_YUV,  422, 10, 2, 1, 0, false, 0},
     {MPCVR_CF_Y216,      "Y216",      LAYOUT_PACKED422, 2,   4, 2, CS_YUV,  422, 16, 2, 1, 0, false, 0},
-    {MPCVR_CF_V210,      "v210",      U,                0,   2, 2, CS_YUV,  422, 10, 2, 1, 0, false, 0},   // repack to Y210: SURVEY 8(f)-4
+    {MPCVR_CF_V210,      "v210",      LAYOUT_PACKED422, 2,   2, 2, CS_YUV,  422, 10, 2, 1, 0, false, 2},   // read in place (no CopyFrameV210 repack pass)
     {MPCVR_CF_AYUV,      "AYUV",      LAYOUT_PACKED444, 1,   4, 2, CS_YUV,  444,  8, 1, 1, 0, false, 0},
     {MPCVR_CF_Y410,      "Y410",      LAYOUT_PACKED444, 4,   4, 2, CS_YUV,  444, 10, 1, 1, 0, false, 1},
     {MPCVR_CF_Y416,      "Y416",      LAYOUT_PACKED444, 2,   8, 2, CS_YUV,  444, 16, 1, 1, 0, false, 2},
@@ -32,21 +32,22 @@ static const FmtConvParams s_table[MPCVR_CF_COUNT] = {
     {MPCVR_CF_YUV422P16, "YUV422P16", LAYOUT_PLANAR3,   2,   2, 4, CS_YUV,  422, 16, 2, 1, 0, false, 0},
     {MPCVR_CF_YUV444P10, "YUV444P10", LAYOUT_PLANAR3,   2,   2, 6, CS_YUV,  444, 10, 1, 1, 6, false, 0},
     {MPCVR_CF_YUV444P16, "YUV444P16", LAYOUT_PLANAR3,   2,   2, 6, CS_YUV,  444, 16, 1, 1, 0, false, 0},
-    // RGB / gray inputs: SURVEY 8(f)-4 ("next" row) -- table rows kept so VerifyMediaType can answer
-    {MPCVR_CF_GBRP8,     "GBRP8",     U,                1,   1, 6, CS_RGB,  444,  8, 1, 1, 0, false, 0},
-    {MPCVR_CF_GBRP10,    "GBRP10",    U,                2,   2, 6, CS_RGB,  444, 10, 1, 1, 6, false, 0},
-    {MPCVR_CF_GBRP16,    "GBRP16",    U,                2,   2, 6, CS_RGB,  444, 16, 1, 1, 0, false, 0},
-    {MPCVR_CF_RGB24,     "RGB24",     U,                1,   3, 2, CS_RGB,  444,  8, 1, 1, 0, false, 0},
-    {MPCVR_CF_XRGB32,    "RGB32",     U,                1,   4, 2, CS_RGB,  444,  8, 1, 1, 0, false, 0},
-    {MPCVR_CF_ARGB32,    "ARGB32",    U,                1,   4, 2, CS_RGB,  444,  8, 1, 1, 0, false, 0},
-    {MPCVR_CF_r210,      "r210",      U,                4,   4, 2, CS_RGB,  444, 10, 1, 1, 0, false, 0},
-    {MPCVR_CF_RGB48,     "RGB48",     U,                2,   6, 2, CS_RGB,  444, 16, 1, 1, 0, false, 0},
-    {MPCVR_CF_BGR48,     "BGR48",     U,                2,   6, 2, CS_RGB,  444, 16, 1, 1, 0, false, 0},
-    {MPCVR_CF_BGRA64,    "BGRA64",    U,                2,   8, 2, CS_RGB,  444, 16, 1, 1, 0, false, 0},
-    {MPCVR_CF_B64A,      "b64a",      U,                2,   8, 2, CS_RGB,  444, 16, 1, 1, 0, false, 0},
-    {MPCVR_CF_Y8,        "Y8",        U,                1,   1, 2, CS_GRAY, 400,  8, 1, 1, 0, false, 0},
-    {MPCVR_CF_Y10,       "Y10",       U,                2,   2, 2, CS_GRAY, 400, 10, 1, 1, 6, false, 0},
-    {MPCVR_CF_Y16,       "Y16",       U,                2,   2, 2, CS_GRAY, 400, 16, 1, 1, 0, false, 0},
+    // RGB / gray inputs (Source/Helper.cpp:341-358).  The reference repacks these samples on the CPU into a DXGI texture
+    // (CopyFrame*, Source/Helper.cpp:446-803); here the kernels read the sample layout directly -- packed_kind selects it.
+    {MPCVR_CF_GBRP8,     "GBRP8",     LAYOUT_PLANAR3,   1,   1, 6, CS_RGB,  444,  8, 1, 1, 0, false, 0},
+    {MPCVR_CF_GBRP10,    "GBRP10",    LAYOUT_PLANAR3,   2,   2, 6, CS_RGB,  444, 10, 1, 1, 6, false, 0},
+    {MPCVR_CF_GBRP16,    "GBRP16",    LAYOUT_PLANAR3,   2,   2, 6, CS_RGB,  444, 16, 1, 1, 0, false, 0},
+    {MPCVR_CF_RGB24,     "RGB24",     LAYOUT_RGB,       1,   3, 2, CS_RGB,  444,  8, 1, 1, 0, false, RGBK_BGR24},
+    {MPCVR_CF_XRGB32,    "RGB32",     LAYOUT_RGB,       1,   4, 2, CS_RGB,  444,  8, 1, 1, 0, false, RGBK_BGRX32},
+    {MPCVR_CF_ARGB32,    "ARGB32",    LAYOUT_RGB,       1,   4, 2, CS_RGB,  444,  8, 1, 1, 0, false, RGBK_BGRX32},
+    {MPCVR_CF_r210,      "r210",      LAYOUT_RGB,       4,   4, 2, CS_RGB,  444, 10, 1, 1, 0, false, RGBK_R210},
+    {MPCVR_CF_RGB48,     "RGB48",     LAYOUT_RGB,       2,   6, 2, CS_RGB,  444, 16, 1, 1, 0, false, RGBK_RGB48},
+    {MPCVR_CF_BGR48,     "BGR48",     LAYOUT_RGB,       2,   6, 2, CS_RGB,  444, 16, 1, 1, 0, false, RGBK_BGR48},
+    {MPCVR_CF_BGRA64,    "BGRA64",    LAYOUT_RGB,       2,   8, 2, CS_RGB,  444, 16, 1, 1, 0, false, RGBK_BGRA64},
+    {MPCVR_CF_B64A,      "b64a",      LAYOUT_RGB,       2,   8, 2, CS_RGB,  444, 16, 1, 1, 0, false, RGBK_B64A},
+    {MPCVR_CF_Y8,        "Y8",        LAYOUT_GRAY,      1,   1, 2, CS_GRAY, 400,  8, 1, 1, 0, false, 0},
+    {MPCVR_CF_Y10,       "Y10",       LAYOUT_GRAY,      2,   2, 2, CS_GRAY, 400, 10, 1, 1, 6, false, 0},
+    {MPCVR_CF_Y16,       "Y16",       LAYOUT_GRAY,      2,   2, 2, CS_GRAY, 400, 16, 1, 1, 0, false, 0},
 };
 #undef U
 

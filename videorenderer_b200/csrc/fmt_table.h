@@ -17,6 +17,20 @@ enum SrcLayout {
     LAYOUT_PLANAR3,      // three R8|R16 planes                            (YV12.., YUV4xxP*)
     LAYOUT_PACKED422,    // R8G8B8A8|R16G16B16A16 macro-pixel              (YUY2, UYVY, Y210, Y216)
     LAYOUT_PACKED444,    // one texel per pixel                            (AYUV, Y410, Y416)
+    LAYOUT_RGB,          // one RGB(A) pixel per packsize bytes, sample layout (RGB24 ... b64a)
+    LAYOUT_GRAY,         // one R8|R16 plane                               (Y8, Y10, Y16)
+};
+
+// packed_kind of LAYOUT_RGB: the SAMPLE byte layout.  What the reference's texture would hold after its CPU repack
+// (Source/Helper.cpp:446-787) is noted on the right; fetch_rgb() returns exactly those texel values.
+enum RgbKind {
+    RGBK_BGRX32 = 0,     // B G R X bytes                      -> B8G8R8X8 / B8G8R8A8          (CopyPlaneAsIs)
+    RGBK_BGR24,          // B G R bytes                        -> B8G8R8X8                     (CopyFrameRGB24 :446-482)
+    RGBK_R210,           // big-endian x2 R10 G10 B10          -> R10G10B10A2                  (CopyFrameR210 :769-787)
+    RGBK_RGB48,          // R G B little-endian words          -> R16G16B16A16                 (CopyFrameRGB48 :541-565)
+    RGBK_BGR48,          // B G R words                        -> R16G16B16A16                 (CopyFrameBGR48 :600-640)
+    RGBK_BGRA64,         // B G R A words                      -> R16G16B16A16                 (CopyFrameBGRA64 :642-658)
+    RGBK_B64A,           // big-endian A R G B words           -> R16G16B16A16                 (CopyFrameB64A :660-677)
 };
 
 struct FmtConvParams {
@@ -32,7 +46,7 @@ struct FmtConvParams {
     int           div_chroma_w, div_chroma_h;
     int           lsb_shift;      // CopyPlane10to16 (Source/Helper.cpp:789-803): stored code << 6
     bool          v_before_u;     // YV12/YV16/YV24 plane order (Source/Shaders.cpp:159-165)
-    int           packed_kind;    // packed422: 0 Y0 U Y1 V, 1 U Y0 V Y1; packed444: 0 AYUV, 1 Y410, 2 Y416
+    int           packed_kind;    // packed422: 0 Y0 U Y1 V, 1 U Y0 V Y1, 2 v210 words; packed444: 0 AYUV, 1 Y410, 2 Y416; rgb: RgbKind
 };
 
 const FmtConvParams& GetFmtConvParams(int cformat);                  // Source/Helper.cpp:365-369

@@ -33,6 +33,9 @@ __device__ __forceinline__ f3 surf_load(const SurfDesc& s, int x, int y)
     } else if (s.fmt == MPCVR_SURF_BGRA8) {
         const uint32_t v = __ldg((const uint32_t*)row + x);
         r.z = unorm8(v & 255u); r.y = unorm8((v >> 8) & 255u); r.x = unorm8((v >> 16) & 255u);
+    } else if (s.fmt == MPCVR_SURF_RGBA16) {
+        const uint2 v = __ldg((const uint2*)row + x);
+        r.x = unorm16(v.x & 0xFFFFu); r.y = unorm16(v.x >> 16); r.z = unorm16(v.y & 0xFFFFu);
     } else {
         const uint2 v = __ldg((const uint2*)row + x);
         const __half2 a = *reinterpret_cast<const __half2*>(&v.x), b = *reinterpret_cast<const __half2*>(&v.y);
@@ -48,6 +51,9 @@ __device__ __forceinline__ void surf_store(const SurfDesc& s, int x, int y, f3 v
         ((uint32_t*)row)[x] = qunorm(v.x, 1023.0f) | (qunorm(v.y, 1023.0f) << 10) | (qunorm(v.z, 1023.0f) << 20) | (3u << 30);
     } else if (s.fmt == MPCVR_SURF_BGRA8) {
         ((uint32_t*)row)[x] = qunorm(v.z, 255.0f) | (qunorm(v.y, 255.0f) << 8) | (qunorm(v.x, 255.0f) << 16) | (255u << 24);
+    } else if (s.fmt == MPCVR_SURF_RGBA16) {
+        uint2 o; o.x = qunorm(v.x, 65535.0f) | (qunorm(v.y, 65535.0f) << 16); o.y = qunorm(v.z, 65535.0f) | (65535u << 16);
+        ((uint2*)row)[x] = o;
     } else {
         const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, 1.0f);
         uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
@@ -60,6 +66,7 @@ __device__ __forceinline__ float rt_roundtrip(int fmt, float v)
 {
     if (fmt == MPCVR_SURF_RGB10A2) return unorm10(qunorm(v, 1023.0f));
     if (fmt == MPCVR_SURF_BGRA8)   return unorm8(qunorm(v, 255.0f));
+    if (fmt == MPCVR_SURF_RGBA16)  return unorm16(qunorm(v, 65535.0f));
     return f16_roundtrip(v);
 }
 
@@ -68,7 +75,7 @@ __device__ __forceinline__ float rt_roundtrip(int fmt, float v)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float src_comp(const SrcDesc& S, int plane, int x, int y, int comp, int ncomp)
 {
-    const uint8_t* p = S.pl[plane] + (size_t)y * S.pitch[plane];
+    const uint8_t* p = S.pl[plane] + (ptrdiff_t)y * S.pitch[plane];      // pitch < 0: bottom-up DIB (RGB samples)
     if (S.bytes == 1) return unorm8(__ldg(p + x * ncomp + comp));
     const uint32_t v = __ldg((const uint16_t*)p + x * ncomp + comp);
     return unorm16((v << S.lsb_shift) & 0xFFFFu);
@@ -162,9 +169,54 @@ __device__ __forceinline__ f3 fetch_planar(const SrcDesc& S, int sx, int sy)
     return r;
 }
 
+// v210 sample read in place.  Four little-endian words carry six pixels (Cb0 Y0 Cr0 | Y1 Cb1 Y2 | Cr1 Y3 Cb2 | Y4 Cr2 Y5,
+// three 10-bit fields per word); the reference rewrites them on the CPU as Y210 macro-pixels with the codes in the top ten
+// bits (CopyFrameV210, Source/Helper.cpp:709-748), so a component reads back as unorm16(code << 6).
+__device__ __forceinline__ float v210_field(const uint8_t* row, int word, int field)
+{
+    const uint32_t w = __ldg((const uint32_t*)row + word);
+    return unorm16(((w >> (10 * field)) & 1023u) << 6);
+}
+__device__ __forceinline__ float v210_luma(const uint8_t* row, int x)
+{
+    const int g = x / 6, k = x - 6 * g;                    // Y0:w0.1 Y1:w1.0 Y2:w1.2 Y3:w2.1 Y4:w3.0 Y5:w3.2
+    const int word = (k == 0) ? 0 : ((k <= 2) ? 1 : ((k == 3) ? 2 : 3));
+    const int field = (k == 0 || k == 3) ? 1 : ((k == 1 || k == 4) ? 0 : 2);
+    return v210_field(row, 4 * g + word, field);
+}
+__device__ __forceinline__ f2 v210_chroma(const uint8_t* row, int m)      // m = macro-pixel (chroma sample) index
+{
+    const int g = m / 3, j = m - 3 * g;                    // Cb0:w0.0 Cr0:w0.2 | Cb1:w1.1 Cr1:w2.0 | Cb2:w2.2 Cr2:w3.1
+    f2 c;
+    if (j == 0)      { c.u = v210_field(row, 4 * g,     0); c.v = v210_field(row, 4 * g,     2); }
+    else if (j == 1) { c.u = v210_field(row, 4 * g + 1, 1); c.v = v210_field(row, 4 * g + 2, 0); }
+    else             { c.u = v210_field(row, 4 * g + 2, 2); c.v = v210_field(row, 4 * g + 3, 1); }
+    return c;
+}
+__device__ __forceinline__ f3 fetch_v210(const SrcDesc& S, int sx, int sy)   // shader side: Source/Shaders.cpp:209-228 (packed422)
+{
+    const uint8_t* row = S.pl[0] + (ptrdiff_t)sy * S.pitch[0];
+    const int mw = S.W >> 1, mx = sx >> 1;
+    f3 r;
+    r.x = v210_luma(row, sx);
+    if ((sx & 1) == 0) { const f2 c = v210_chroma(row, mx); r.y = c.u; r.z = c.v; }
+    else {
+        const int m0 = max(mx - 1, 0), m2 = min(mx + 1, mw - 1), m3 = min(mx + 2, mw - 1);
+        const f2 c1 = v210_chroma(row, mx), c2 = v210_chroma(row, m2);
+        if (S.chroma_mode == MPCVR_CHROMA_CatmullRom) {
+            const f2 c0 = v210_chroma(row, m0), c3 = v210_chroma(row, m3);
+            r.y = catmull05(c0.u, c1.u, c2.u, c3.u); r.z = catmull05(c0.v, c1.v, c2.v, c3.v);
+        } else {
+            r.y = __fmul_rn(__fadd_rn(c1.u, c2.u), 0.5f); r.z = __fmul_rn(__fadd_rn(c1.v, c2.v), 0.5f);
+        }
+    }
+    return r;
+}
+
 // packed 4:2:2 (Source/Shaders.cpp:195-228): one RGBA texel holds two pixels
 __device__ __forceinline__ f3 fetch_packed422(const SrcDesc& S, int sx, int sy)
 {
+    if (S.packed_kind == 2) return fetch_v210(S, sx, sy);
     const int mw = S.W >> 1, mx = sx >> 1;
     const bool uyvy = S.packed_kind == 1;
     const int iy0 = uyvy ? 1 : 0, iu = uyvy ? 0 : 1, iy1 = uyvy ? 3 : 2, iv = uyvy ? 2 : 3;
@@ -188,7 +240,7 @@ __device__ __forceinline__ f3 fetch_packed422(const SrcDesc& S, int sx, int sy)
 // packed 4:4:4 (Source/Shaders.cpp:183-194)
 __device__ __forceinline__ f3 fetch_packed444(const SrcDesc& S, int sx, int sy)
 {
-    const uint8_t* row = S.pl[0] + (size_t)sy * S.pitch[0];
+    const uint8_t* row = S.pl[0] + (ptrdiff_t)sy * S.pitch[0];
     f3 r;
     if (S.packed_kind == 0) {          // AYUV: V U Y A
         const uint32_t v = __ldg((const uint32_t*)row + sx);
@@ -203,10 +255,43 @@ __device__ __forceinline__ f3 fetch_packed444(const SrcDesc& S, int sx, int sy)
     return r;
 }
 
+// RGB samples: "float4 color = tex.Sample(samp, input.Tex)" (Source/Shaders.cpp:183-185) of the texture the reference's
+// CPU repack would have produced (fmt_table.h RgbKind); alpha is not carried (opaque swap chain).
+__device__ __forceinline__ f3 fetch_rgb(const SrcDesc& S, int sx, int sy)
+{
+    const uint8_t* row = S.pl[0] + (ptrdiff_t)sy * S.pitch[0];
+    f3 r;
+    switch (S.packed_kind) {
+    case RGBK_BGRX32: {
+        const uint32_t v = __ldg((const uint32_t*)row + sx);
+        r.z = unorm8(v & 255u); r.y = unorm8((v >> 8) & 255u); r.x = unorm8((v >> 16) & 255u); break; }
+    case RGBK_BGR24: {
+        const uint8_t* p = row + 3 * sx;
+        r.z = unorm8(__ldg(p)); r.y = unorm8(__ldg(p + 1)); r.x = unorm8(__ldg(p + 2)); break; }
+    case RGBK_R210: {
+        const uint32_t be = __byte_perm(__ldg((const uint32_t*)row + sx), 0, 0x0123);
+        r.x = unorm10((be >> 20) & 1023u); r.y = unorm10((be >> 10) & 1023u); r.z = unorm10(be & 1023u); break; }
+    case RGBK_RGB48: case RGBK_BGR48: {
+        const uint16_t* p = (const uint16_t*)row + 3 * sx;
+        const float a = unorm16(__ldg(p)), b = unorm16(__ldg(p + 1)), c = unorm16(__ldg(p + 2));
+        if (S.packed_kind == RGBK_RGB48) { r.x = a; r.y = b; r.z = c; } else { r.x = c; r.y = b; r.z = a; }
+        break; }
+    case RGBK_BGRA64: {
+        const uint2 v = __ldg((const uint2*)row + sx);
+        r.z = unorm16(v.x & 0xFFFFu); r.y = unorm16(v.x >> 16); r.x = unorm16(v.y & 0xFFFFu); break; }
+    default: {  // RGBK_B64A: bytes Ahi Alo Rhi Rlo Ghi Glo Bhi Blo
+        const uint2 v = __ldg((const uint2*)row + sx);
+        r.x = unorm16(__byte_perm(v.x, 0, 0x4423)); r.y = unorm16(__byte_perm(v.y, 0, 0x4401)); r.z = unorm16(__byte_perm(v.y, 0, 0x4423)); break; }
+    }
+    return r;
+}
+
 __device__ __forceinline__ f3 fetch_yuv(const SrcDesc& S, int sx, int sy)
 {
     if (S.layout == LAYOUT_PACKED422) return fetch_packed422(S, sx, sy);
     if (S.layout == LAYOUT_PACKED444) return fetch_packed444(S, sx, sy);
+    if (S.layout == LAYOUT_RGB)       return fetch_rgb(S, sx, sy);
+    if (S.layout == LAYOUT_GRAY)      { f3 r; r.x = src_comp(S, 0, sx, sy, 0, 1); r.y = 0.0f; r.z = 0.0f; return r; }   // R8/R16 view: .gb = 0
     return fetch_planar(S, sx, sy);
 }
 

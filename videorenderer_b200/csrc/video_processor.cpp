@@ -9,7 +9,7 @@
 namespace b200vr {
 
 static inline int AlignUp(int v, int a) { return (v + a - 1) / a * a; }
-static inline int SurfBpp(int fmt) { return fmt == MPCVR_SURF_RGBA16F ? 8 : 4; }
+static inline int SurfBpp(int fmt) { return (fmt == MPCVR_SURF_RGBA16F || fmt == MPCVR_SURF_RGBA16) ? 8 : 4; }
 
 // ------------------------------------------------------------------------------------------------
 // Tex2D / DeviceAxis
@@ -58,7 +58,7 @@ CB200VideoProcessor::~CB200VideoProcessor()
         cudaSetDevice(m_device);
         if (m_stream) cudaStreamSynchronize(m_stream);
         for (auto& t : m_TexSrcVideo) t.Release();
-        m_TexConvertOutput.Release(); m_TexResize.Release(); m_TexsPostScale.Release(); m_BackBuffer.Release(); m_TexImage.Release();
+        m_TexConvertOutput.Release(); m_TexSrcUnpacked.Release(); m_TexResize.Release(); m_TexsPostScale.Release(); m_BackBuffer.Release(); m_TexImage.Release();
         m_dbgConvertF32.Release();
         m_axisX.Release(); m_axisY.Release(); m_pointX.Release(); m_pointY.Release(); m_pointRX.Release(); m_pointRY.Release();
         if (m_ownStream && m_stream) cudaStreamDestroy(m_stream);
@@ -155,6 +155,7 @@ int32_t CB200VideoProcessor::InitMediaType(const mpcvr_media_type* mt)
         m_srcPitch = AlignUp((biWidth + 5) / 6 * 16, 128); break;
     default: break;
     }
+    if (mt->bottom_up) m_srcPitch = -m_srcPitch;                            // BI_RGB && biHeight > 0, :1801-1803
     unsigned origW = biWidth, origH = biHeight;                             // VR_Extradata, :1805-1813
     if (mt->frame_width > 0 && mt->frame_height != 0) { origW = (unsigned)mt->frame_width; origH = (unsigned)std::abs(mt->frame_height); }
 
@@ -192,7 +193,8 @@ int32_t CB200VideoProcessor::InitMediaType(const mpcvr_media_type* mt)
         case LAYOUT_PLANAR3:
             nplanes = 3; pw[0] = origW * bpc; ph[0] = origH;
             pw[1] = pw[2] = (origW / FmtParams.div_chroma_w) * bpc; ph[1] = ph[2] = origH / FmtParams.div_chroma_h; break;
-        case LAYOUT_PACKED422: pw[0] = (origW / 2) * 4 * bpc; ph[0] = origH; break;
+        case LAYOUT_PACKED422:
+            pw[0] = (FmtParams.packed_kind == 2) ? std::abs(m_srcPitch) : (int)(origW / 2) * 4 * bpc; ph[0] = origH; break;   // v210: whole 16-byte groups
         default:               pw[0] = origW * FmtParams.Packsize; ph[0] = origH; break;
         }
         for (int i = 0; i < nplanes; i++) {
@@ -258,6 +260,16 @@ int CB200VideoProcessor::Transfer() const
 void CB200VideoProcessor::SetShaderConvertColorParams()
 {
     BuildColorTransform(m_srcExFmt, m_srcParams, m_ProcAmp, m_PSConvColorData);
+    {
+        float (&m)[3][3] = m_PSConvColorData.m;
+        if (m_srcParams.CSType == CS_RGB && m_srcParams.layout == LAYOUT_PLANAR3) {          // GBRP: planes are G, B, R (:863-867)
+            for (int i = 0; i < 3; i++) { std::swap(m[i][0], m[i][1]); std::swap(m[i][1], m[i][2]); }
+            m_PSConvColorData.enable = true;                                                  // :848
+        } else if (m_srcParams.CSType == CS_GRAY) {                                          // :868-873
+            m[1][0] = m[1][1]; m[1][1] = 0;
+            m[2][0] = m[2][2]; m[2][2] = 0;
+        }
+    }
     for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) m_color.cm[i][j] = m_PSConvColorData.m[i][j]; m_color.cc[i] = m_PSConvColorData.c[i]; }
     BuildGamutMatrix(CHR_BT2020, CHR_BT709, m_color.gamut);               // Source/Shaders.cpp:634-645
     m_color.transfer = Transfer();
@@ -440,7 +452,7 @@ int32_t CB200VideoProcessor::MemCopyToTexSrcVideo(const uint8_t* data, int pitch
     const FmtConvParams& f = m_srcParams;
     const int H = (int)m_srcHeight;
     auto copy = [&](Tex2D& t, const uint8_t* src, int spitch, int lines) {
-        return cudaMemcpy2DAsync(t.ptr, t.pitch, src, spitch, (size_t)t.w, lines, cudaMemcpyHostToDevice, m_stream);
+        return cudaMemcpy2DAsync(t.ptr, t.pitch, src, spitch, (size_t)std::min(t.w, spitch), lines, cudaMemcpyHostToDevice, m_stream);
     };
     if (f.layout == LAYOUT_BIPLANAR || f.layout == LAYOUT_PLANAR3) {
         if (!Cuda(copy(m_TexSrcVideo[0], data, pitch, H), "H2D luma")) return MPCVR_E_FAIL;
@@ -474,18 +486,22 @@ int32_t CB200VideoProcessor::CopySample(const mpcvr_sample* s)
         // IMediaSampleD3D11 path (:2528-2570): the decoder's planes are read in place
         const int np = f.layout == LAYOUT_BIPLANAR ? 2 : (f.layout == LAYOUT_PLANAR3 ? 3 : 1);
         for (int i = 0; i < np; i++) {
-            if (!s->planes[i] || s->pitches[i] <= 0) return Fail(MPCVR_E_POINTER, "device sample: missing plane");
+            if (!s->planes[i] || s->pitches[i] == 0 || (s->pitches[i] < 0 && np > 1)) return Fail(MPCVR_E_POINTER, "device sample: missing plane");
             S.pl[i] = (const uint8_t*)s->planes[i]; S.pitch[i] = s->pitches[i];
         }
         if (s->ready_event && !Cuda(cudaStreamWaitEvent(m_stream, (cudaEvent_t)s->ready_event, 0), "cudaStreamWaitEvent")) return MPCVR_E_FAIL;
     } else {
         if (!s->data) return Fail(MPCVR_E_POINTER, "host sample: null data");
         const int pitch = s->pitch ? s->pitch : m_srcPitch;
-        if (pitch <= 0) return Fail(MPCVR_E_NOTIMPL, "bottom-up (negative pitch) samples are RGB only");
-        if (s->size > 0 && s->size < (int64_t)pitch * (int64_t)m_srcLines) return Fail(MPCVR_E_FAIL, "host sample smaller than pitch*lines (:2579)");
-        const int32_t hr = MemCopyToTexSrcVideo((const uint8_t*)s->data, pitch);
+        if (pitch == 0) return Fail(MPCVR_E_INVALIDARG, "host sample: zero pitch");
+        if (pitch < 0 && (f.layout == LAYOUT_BIPLANAR || f.layout == LAYOUT_PLANAR3)) return Fail(MPCVR_E_NOTIMPL, "bottom-up (negative pitch) samples are single-plane only (:1243-1249)");
+        if (s->size > 0 && s->size < (int64_t)std::abs(pitch) * (int64_t)m_srcLines) return Fail(MPCVR_E_FAIL, "host sample smaller than pitch*lines (:2579)");
+        // a bottom-up DIB is uploaded as it lies in memory; the kernels walk it from its last row with a negative pitch,
+        // which is what "src = srcData + srcPitch * (1 - lines)" (:1246) does on the CPU
+        const int32_t hr = MemCopyToTexSrcVideo((const uint8_t*)s->data, std::abs(pitch));
         if (hr != MPCVR_S_OK) return hr;
         for (int i = 0; i < 3; i++) { S.pl[i] = (const uint8_t*)m_TexSrcVideo[i].ptr; S.pitch[i] = (int32_t)m_TexSrcVideo[i].pitch; }
+        if (pitch < 0) { S.pl[0] += (size_t)S.pitch[0] * (m_srcHeight - 1); S.pitch[0] = -S.pitch[0]; }
     }
     if (f.layout == LAYOUT_PLANAR3 && f.v_before_u) { std::swap(S.pl[1], S.pl[2]); std::swap(S.pitch[1], S.pitch[2]); }   // texV:t1, texU:t2
     m_rtStart = s->rt_start; m_rtEnd = s->rt_end;
@@ -550,7 +566,9 @@ int32_t CB200VideoProcessor::Reset(bool) { m_planDirty = true; return MPCVR_S_OK
 int32_t CB200VideoProcessor::UpdatePlan()
 {
     if (!m_planDirty) return MPCVR_S_OK;
-    const CRect rSrc(0, 0, (int)m_srcRectWidth, (int)m_srcRectHeight);       // after ConvertColorPass, :3319
+    // after ConvertColorPass rSrc is the whole convert output (:3319); without one the chain samples the source
+    // texture itself and rSrc stays m_srcRect (:3320-3322)
+    const CRect rSrc = m_PSConvColorData.enable ? CRect(0, 0, (int)m_srcRectWidth, (int)m_srcRectHeight) : m_srcRect;
     const CRect& dst = m_videoRect;
     const int w1 = rSrc.Width(), h1 = rSrc.Height(), w2 = dst.Width(), h2 = dst.Height();
     int kx = ChooseScaler(w1, w2, m_bInterpolateAt50pct), ky = ChooseScaler(h1, h2, m_bInterpolateAt50pct);
@@ -560,7 +578,9 @@ int32_t CB200VideoProcessor::UpdatePlan()
     const int fx = kx == SCALER_CONV ? m_iDownscaling : m_iUpscaling, fy = ky == SCALER_CONV ? m_iDownscaling : m_iUpscaling;
     const bool d3d9 = !m_bUseD3D11;
     if (!BuildAxisTable(kx, fx, d3d9, rSrc.left, w1, dst.left, w2, m_axisX.host)) return Fail(MPCVR_E_NOTIMPL, "X scaler not available (Jinc2 is a 'next' row)");
-    if (!BuildAxisTable(ky, fy, d3d9, rSrc.top, h1, dst.top, h2, m_axisY.host)) return Fail(MPCVR_E_NOTIMPL, "Y scaler not available (Jinc2 is a 'next' row)");
+    // two shader passes: the Y pass reads m_TexResize, whose rows start at 0 (resize rect (dst.left, 0, dst.right, h1), :3150-3160)
+    const bool twoPass = (kx == SCALER_INTERP || kx == SCALER_CONV) && (ky == SCALER_INTERP || ky == SCALER_CONV);
+    if (!BuildAxisTable(ky, fy, d3d9, twoPass ? 0 : rSrc.top, h1, dst.top, h2, m_axisY.host)) return Fail(MPCVR_E_NOTIMPL, "Y scaler not available (Jinc2 is a 'next' row)");
     // point-sampled maps: other axis of a single-axis resize, and plain copies
     BuildAxisTable(SCALER_NEAREST, 0, d3d9, rSrc.left, w1, dst.left, w2, m_pointX.host);
     BuildAxisTable(SCALER_NEAREST, 0, d3d9, rSrc.top, h1, dst.top, h2, m_pointY.host);
@@ -649,9 +669,22 @@ int32_t CB200VideoProcessor::Process(const Tex2D& target, const CRect& srcRect, 
 
     // ---- multipass family: the reference's passes, one kernel each
     if (!covers) { m_lastLaunches++; if (!Cuda(LaunchClear(target.desc(), m_stream), "clear")) return MPCVR_E_FAIL; }   // ClearRenderTargetView, :2617
-    if (!skipConvert) { hr = ConvertColorPass(m_TexConvertOutput); if (hr != MPCVR_S_OK) return hr; }
     const Tex2D* pInputTexture = &m_TexConvertOutput;
-    const CRect rSrc(0, 0, m_TexConvertOutput.w, m_TexConvertOutput.h);
+    CRect rSrc(0, 0, m_TexConvertOutput.w, m_TexConvertOutput.h);
+    if (!m_PSConvColorData.enable && !skipConvert) {
+        // "pInputTexture = &m_TexSrcVideo" (:3320-3322): RGB source, default ProcAmp -> no ConvertColorPass.  The sample stays in
+        // its own byte layout here, so one unpack kernel writes the texture the reference's CPU repack would have produced
+        // (B8G8R8X8 / R10G10B10A2 / R16G16B16A16, Source/Helper.cpp:345-354) -- an exact, code-preserving copy -- and the
+        // later passes sample that with rSrc = m_srcRect.
+        const int fmt = m_srcParams.bytes == 1 ? MPCVR_SURF_BGRA8 : (m_srcParams.packed_kind == RGBK_R210 ? MPCVR_SURF_RGB10A2 : MPCVR_SURF_RGBA16);
+        if (!Cuda(m_TexSrcUnpacked.CheckCreate(fmt, (int)m_srcWidth, (int)m_srcHeight), "m_TexSrcUnpacked")) return MPCVR_E_FAIL;
+        SrcDesc whole = m_src; whole.rect_l = 0; whole.rect_t = 0; whole.rect_w = (int32_t)m_srcWidth; whole.rect_h = (int32_t)m_srcHeight;
+        ColorParams ident = m_color; ident.transfer = TRANSFER_NONE;
+        for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) ident.cm[i][j] = (i == j) ? 1.0f : 0.0f; ident.cc[i] = 0.0f; }
+        m_lastLaunches++;
+        if (!Cuda(LaunchConvertPass(whole, ident, m_TexSrcUnpacked.desc(), nullptr, m_stream), "source unpack")) return MPCVR_E_FAIL;
+        pInputTexture = &m_TexSrcUnpacked; rSrc = m_srcRect;
+    } else if (!skipConvert) { hr = ConvertColorPass(m_TexConvertOutput); if (hr != MPCVR_S_OK) return hr; }
 
     if (m_bFinalPass) {                                                       // numSteps == 1, :3325-3416
         if (!m_TexsPostScale.ptr || m_TexsPostScale.w != target.w || m_TexsPostScale.h != target.h || m_TexsPostScale.fmt != m_InternalTexFmt) {
@@ -674,6 +707,7 @@ int32_t CB200VideoProcessor::Process(const Tex2D& target, const CRect& srcRect, 
 bool CB200VideoProcessor::PlanFused(const Tex2D& target, const CRect& dstRect, FusedPlan& fp, const char** why)
 {
     memset(&fp, 0, sizeof(fp));
+    if (!m_PSConvColorData.enable) { if (why) *why = "no convert pass on this plan (RGB source, default ProcAmp): multipass only"; return false; }
     fp.src = m_src; fp.color = m_color;
     fp.ax = m_axisX.table(); fp.ay = m_axisY.table();
     fp.out = target.desc();

@@ -173,6 +173,7 @@ private:
 
     Tex2D m_TexSrcVideo[3];                      // plane buffers of the source "texture"
     SrcDesc m_src = {};                          // what the kernels read (own planes or the sample's device planes)
+    Tex2D m_TexSrcUnpacked;      // RGB source as the texture the reference's CPU repack produces (only when no convert pass runs)
     Tex2D m_TexConvertOutput, m_TexResize, m_TexsPostScale, m_BackBuffer, m_TexImage;
     Tex2D m_UserBackBuffer;                      // caller-bound target (not owned)
     DevArray<float4> m_dbgConvertF32; bool m_captureF32 = false;

@@ -44,8 +44,9 @@ class VideoProcessor:
     # -- media type
     @staticmethod
     def media_type(cformat, width, height, ext_format=0, src_rect=None, frame_size=None, aspect=(0, 0), interlaced=0,
-                   avg_time_per_frame=400000):
+                   avg_time_per_frame=400000, bottom_up=0):
         mt = A.MediaType()
+        mt.bottom_up = bottom_up
         mt.cformat = cformat; mt.width = width; mt.height = height
         if frame_size:
             mt.frame_width, mt.frame_height = frame_size
