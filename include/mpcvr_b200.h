@@ -87,7 +87,7 @@ typedef struct mpcvr_settings {
     int32_t bAdjustPresentTime;
     int32_t bReinitByDisplay;
     int32_t bHdrPreferDoVi;
-    int32_t bHdrPassthrough;         /* no HDR display on this target: treated as unsupported */
+    int32_t bHdrPassthrough;         /* effective only after mpcvr_set_display_hdr(vp, 1) */
     int32_t iHdrToggleDisplay;
     int32_t iHdrOsdBrightness;
     int32_t bConvertToSdr;           /* acts */
@@ -201,6 +201,11 @@ void    mpcvr_set_video_rect(mpcvr* vp, const mpcvr_rect* r);
 int32_t mpcvr_set_window_rect(mpcvr* vp, const mpcvr_rect* r);
 int32_t mpcvr_set_rotation(mpcvr* vp, int32_t degrees);       /* 0 accepted; 90/180/270 -> E_NOTIMPL */
 int32_t mpcvr_set_flip(mpcvr* vp, int32_t flip);              /* 0 accepted; 1 -> E_NOTIMPL */
+/* m_bHdrPassthroughSupport (Source/DX11VideoProcessor.cpp:1476): the reference reads it from the DXGI output; here the
+ * caller states whether the presentation target is an HDR10 (PQ / BT.2020) display.  With it set, bHdrPassthrough /
+ * bHdrLocalToneMapping pick SHADER_CONVERT_NONE / _TO_PQ (:2948-2950) and the ps_hdr10_tonemap post-scale step
+ * (:3359-3367) fed from mpcvr_sample.hdr / .hdr_cll (:2233-2268, :2715-2725). */
+int32_t mpcvr_set_display_hdr(mpcvr* vp, int32_t hdr10_supported);
 void    mpcvr_get_video_size(mpcvr* vp, int32_t* w, int32_t* h);                      /* GetVideoSize */
 void    mpcvr_get_aspect_ratio(mpcvr* vp, int32_t* ax, int32_t* ay);                  /* GetAspectRatio */
 

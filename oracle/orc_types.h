@@ -89,6 +89,12 @@ typedef struct orc_config {
     /* DXVA2 ProcAmp values already in float (DXVA2FixedToFloat) */
     float    brightness, contrast, hue, saturation;
     int32_t  variant;            /* ORC_VARIANT_*                                    */
+    /* HDR output.  hdr_out = m_bHdrPassthroughSupport && (m_bHdrPassthrough || m_bHdrLocalToneMapping):
+     * picks the convert type (UpdateConvertColorShader, DX11VideoProcessor.cpp:2948-2950).  tonemap = the
+     * ps_hdr10_tonemap post-scale step runs (:3359-3367) with the raw arguments of SetHDR10ShaderParams (:907-921). */
+    int32_t  hdr_out, tonemap;
+    float    tm_min_nits, tm_max_nits, tm_max_cll, tm_max_fall, tm_display_nits;
+    int32_t  tm_type;
 } orc_config;
 
 /* optional taps into the pass chain for stage-wise parity tests */

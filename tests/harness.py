@@ -199,7 +199,7 @@ class Case:
     def __init__(self, cf, w, h, dst_w, dst_h, ex, backbuffer=O.SURF_BGRA8, tex=O.TEXFMT_AUTOINT, chroma=O.CHROMA_Bilinear,
                  up=O.UPSCALE["CatmullRom"], down=O.DOWNSCALE["Hamming"], interp50=1, dither=1, to_sdr=1, nits=125,
                  src_rect=None, dst_rect=None, win=None, variant=O.VARIANT_D3D11, procamp=None, interlaced=0, deint_blend=0,
-                 name=None, bottom_up=0):
+                 name=None, bottom_up=0, hdr=None):
         self.__dict__.update(locals()); del self.__dict__["self"]
         self.name = name or "case"
 
@@ -210,7 +210,7 @@ class Case:
                              up=self.up, down=self.down, interp50=self.interp50, dither=self.dither, to_sdr=self.to_sdr,
                              nits=self.nits, deint_blend=int(bool(self.deint_blend and self.interlaced)),
                              brightness=pa.get("brightness", 0.0), contrast=pa.get("contrast", 1.0), hue=pa.get("hue", 0.0),
-                             saturation=pa.get("saturation", 1.0), variant=self.variant)
+                             saturation=pa.get("saturation", 1.0), variant=self.variant, hdr=self.hdr)
 
     def settings(self):
         import videorenderer_b200 as V
@@ -219,11 +219,15 @@ class Case:
         s.iTexFormat = self.tex; s.iChromaScaling = self.chroma; s.iUpscaling = self.up; s.iDownscaling = self.down
         s.bInterpolateAt50pct = self.interp50; s.bUseDither = self.dither; s.bConvertToSdr = self.to_sdr
         s.iSDRDisplayNits = self.nits; s.bDeintBlend = self.deint_blend
+        if self.hdr:
+            self.hdr_settings(s)
         return s
 
     def make_processor(self, device=0, path=None):
         import videorenderer_b200 as V
         vp = V.VideoProcessor(self.settings(), device=device)
+        if self.hdr:
+            vp.SetDisplayHdr(True)
         mt = V.VideoProcessor.media_type(self.cf, self.w, self.h, self.ex, src_rect=self.src_rect, interlaced=self.interlaced,
                                          bottom_up=self.bottom_up)
         assert vp.InitMediaType(mt), "InitMediaType failed: " + vp.last_error()
@@ -236,6 +240,14 @@ class Case:
         if path is not None:
             vp.debug_set_path(path)
         return vp
+
+    def hdr_settings(self, s):
+        """HDR output cases: Settings_t fields + the display capability (mpcvr_set_display_hdr)"""
+        h = self.hdr or {}
+        s.bHdrPassthrough = 1 if h.get("out", 0) else 0
+        s.bHdrLocalToneMapping = 1 if h.get("tonemap", 0) else 0
+        s.iHdrLocalToneMappingType = int(h.get("type", 1)); s.iHdrDisplayMaxNits = int(h.get("display", 1000))
+        return s
 
 
 def run_oracle(case, planes, pitches, mode=O.MODE_SPEC, want_debug=False, threads=0):

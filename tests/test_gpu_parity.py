@@ -17,7 +17,8 @@ def _run_gpu(case, buf, pitch, path=PATH_MULTIPASS, capture=False):
     vp = case.make_processor(device=0, path=path)
     if capture:
         vp.debug_capture_f32(True)
-    vp.ProcessSample(data=buf, pitch=pitch)
+    side = getattr(case, "side_data", None) or {}
+    vp.ProcessSample(data=buf, pitch=pitch, hdr=side.get("hdr"), hdr_cll=side.get("cll"))
     out = vp.ReadBackbuffer()
     return vp, out
 
@@ -408,3 +409,44 @@ def test_v210_equals_y210():
         buf, pitch, _, _ = H.pack(case.cf, 66, 30, codes)
         outs.append(_run_gpu(case, buf, pitch)[1])
     assert np.array_equal(outs[0], outs[1])
+
+
+# ---- HDR output -- passthrough convert types and the HDR10 local tone-map post-scale step ----
+def _hdr_case(cf, ex, tm_type, tonemap=1, side=None, tex=O.TEXFMT_AUTOINT, backbuffer=O.SURF_RGB10A2, display=600, **kw):
+    """side: dict(hdr=dict(max_lum, min_lum), cll=(MaxCLL, MaxFALL)) as IMediaSideData delivers it; the oracle gets the raw
+    SetHDR10ShaderParams arguments the reference derives from it (DX11VideoProcessor.cpp:2255-2267, :2673-2684, :2721-2724)"""
+    if side and "hdr" in side:
+        mx, mn = round(side["hdr"]["max_lum"]), round(side["hdr"]["min_lum"] * 10000.0)
+        cll, fall = side.get("cll", (0, 0))
+    else:                                                      # no (valid) mastering-display blob: Display-P3 defaults, and the
+        mx, mn, cll, fall = 1000, 50, 0, 0                     # light-level blob alone is never applied (:2673-2684)
+    hdr = dict(out=1, tonemap=tonemap, min=float(mn), max=float(mx), cll=float(cll), fall=float(fall), display=float(display), type=tm_type)
+    case = H.Case(cf, 64, 36, 96, 54, ex, backbuffer=backbuffer, tex=tex, up=O.UPSCALE["Lanczos3"], hdr=hdr, name="hdr_tm%d" % tm_type, **kw)
+    case.side_data = side
+    return case
+
+
+@pytest.mark.parametrize("tm_type", [1, 2, 3, 4, 5, 6])
+def test_hdr10_local_tonemap_types(tm_type):
+    side = dict(hdr=dict(max_lum=4000.0, min_lum=0.005), cll=(1200, 300))
+    _check(_hdr_case(O.CF["P010"], H.EX_2020_PQ, tm_type, side=side), "natural", seed=21)
+
+
+@pytest.mark.parametrize("tm_type", [1, 5, 6])
+def test_hdr10_tonemap_without_metadata_and_with_final_pass(tm_type):
+    """no side data -> Display-P3 defaults; 16F intermediates -> tone-map step writes the ring's second texture, final pass dithers"""
+    _check(_hdr_case(O.CF["P010"], H.EX_2020_PQ, tm_type, tex=O.TEXFMT_16FLOAT), "natural", seed=22)
+    _check(_hdr_case(O.CF["P016"], H.EX_2020_PQ, tm_type, side=dict(cll=(800, 120)), display=400), "noise", seed=23)
+
+
+def test_hdr_passthrough_pq_and_hlg():
+    """HDR output without tone mapping: PQ is passed through (matrix only), HLG is converted to PQ (Source/Shaders.cpp:886-891)"""
+    _check(_hdr_case(O.CF["P010"], H.EX_2020_PQ, 1, tonemap=0), "natural", seed=24)
+    _check(_hdr_case(O.CF["P010"], H.EX_2020_HLG, 1, tonemap=0), "natural", seed=25)
+    _check(_hdr_case(O.CF["YUY2"], H.EX_2020_HLG, 3, tonemap=1, side=dict(cll=(1000, 200))), "natural", seed=26)
+
+
+def test_hdr_settings_without_hdr_display_change_nothing():
+    """bHdrPassthrough defaults to true, but without an HDR display the SDR conversion stays (m_bHdrPassthroughSupport false)"""
+    case = H.baseline_cases(scale=0.05)[1]
+    _check(case, "natural", seed=27)

@@ -184,3 +184,20 @@ def test_unorm_read_sequence_is_exact():
         assert np.all(e.astype(np.float64) == c.astype(np.float64) - q.astype(np.float64) * np.float64(N)), "residual must be exact"
         q2 = (q.astype(np.float64) + e.astype(np.float64) * np.float64(r)).astype(np.float32)
         assert np.array_equal(q2, c / N)
+
+
+def test_hdr_output_picks_the_convert_type():
+    """UpdateConvertColorShader's convertType (Source/DX11VideoProcessor.cpp:2948-2950) with and without an HDR display"""
+    vp = V.VideoProcessor(device=-1)                       # defaults: bHdrPassthrough = 1, bConvertToSdr = 1
+    pq = V.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=15); hlg = V.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=16)
+    assert vp.InitMediaType(V.VideoProcessor.media_type(V.CF.P010, 64, 64, pq)) and vp.debug_plan().transfer == 1      # PQ -> SDR
+    assert vp.InitMediaType(V.VideoProcessor.media_type(V.CF.P010, 64, 64, hlg)) and vp.debug_plan().transfer == 2     # HLG -> SDR
+    vp.SetDisplayHdr(True)
+    assert vp.debug_plan().transfer == 4                                                                               # HLG -> PQ
+    assert vp.InitMediaType(V.VideoProcessor.media_type(V.CF.P010, 64, 64, pq)) and vp.debug_plan().transfer == 0      # PQ untouched
+    s = vp.GetSettings(); s.bHdrPassthrough = 0; vp.Configure(s)
+    assert vp.debug_plan().transfer == 1                   # HDR display, but neither passthrough nor local tone mapping
+    s.bHdrLocalToneMapping = 1; vp.Configure(s)
+    assert vp.debug_plan().transfer == 0
+    vp.SetDisplayHdr(False)
+    assert vp.debug_plan().transfer == 1

@@ -153,6 +153,7 @@ SIGNATURES = {
     "mpcvr_set_window_rect": (C.c_int32, [vp, P(Rect)]),
     "mpcvr_set_rotation": (C.c_int32, [vp, C.c_int32]),
     "mpcvr_set_flip": (C.c_int32, [vp, C.c_int32]),
+    "mpcvr_set_display_hdr": (C.c_int32, [vp, C.c_int32]),
     "mpcvr_get_video_size": (None, [vp, P(C.c_int32), P(C.c_int32)]),
     "mpcvr_get_aspect_ratio": (None, [vp, P(C.c_int32), P(C.c_int32)]),
     "mpcvr_get_settings": (None, [vp, P(Settings)]),

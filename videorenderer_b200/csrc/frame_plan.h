@@ -11,6 +11,12 @@ enum Transfer : int32_t {           // which body GetShaderConvertColor emits, S
     TRANSFER_PQ_TO_SDR = 1,         // :870-884
     TRANSFER_HLG_TO_SDR = 2,        // :862-868 then :870-884
     TRANSFER_SDR_2020 = 3,          // :892-915
+    TRANSFER_HLG_TO_PQ = 4,         // :886-891 (SHADER_CONVERT_TO_PQ, HDR output)
+};
+
+struct TonemapParams {              // HDRParamsConstantBuffer, Shaders/d3d11/ps_hdr10_tonemap.hlsl:12-21 (after SetHDR10ShaderParams' clamps)
+    float min_nits, max_nits, max_cll, max_fall, display;
+    int32_t sel;                    // 1 ACES, 2 Reinhard, 3 Habel, 4 Moebius, 5 BT.2390, 6 ST 2094-10
 };
 
 struct SrcDesc {                    // the source "texture views" (Source/DX11Helper.h:87-170)

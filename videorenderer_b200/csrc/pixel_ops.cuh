@@ -358,13 +358,14 @@ __device__ __forceinline__ f3 convert_color(const ColorParams& P, f3 yuv)
         f3 l; l.x = powr(sat(c.x), P.sdr_gamma); l.y = powr(sat(c.y), P.sdr_gamma); l.z = powr(sat(c.z), P.sdr_gamma);
         c = mat3_apply(P.gamut, l);
     } else {
-        if (tr == TRANSFER_HLG_TO_SDR) {                                            // :862-868
+        if (tr == TRANSFER_HLG_TO_SDR || tr == TRANSFER_HLG_TO_PQ) {                // :862-868 and :886-891: the same three lines
             f3 l; l.x = inverse_hlg(P, sat(c.x)); l.y = inverse_hlg(P, sat(c.y)); l.z = inverse_hlg(P, sat(c.z));
             const float dt = fma_rn(0.0593f, l.z, fma_rn(0.6780f, l.y, __fmul_rn(0.2627f, l.x)));   // hlg.hlsl:16-17
             const float g  = powr(__fmul_rn(2000.0f, dt), 0.2f);
             c.x = linear_to_st2084(__fmul_rn(l.x, g), P.r1000);
             c.y = linear_to_st2084(__fmul_rn(l.y, g), P.r1000);
             c.z = linear_to_st2084(__fmul_rn(l.z, g), P.r1000);
+            if (tr == TRANSFER_HLG_TO_PQ) return c;
         }
         f3 h;                                                                       // :870-880; x / HABLE_DIV -> x * (1/HABLE_DIV)
         h.x = __fmul_rn(hable(P, st2084_to_linear(P, sat(c.x), P.lum_scale)), P.hable_rdiv);

@@ -58,7 +58,7 @@ CB200VideoProcessor::~CB200VideoProcessor()
         cudaSetDevice(m_device);
         if (m_stream) cudaStreamSynchronize(m_stream);
         for (auto& t : m_TexSrcVideo) t.Release();
-        m_TexConvertOutput.Release(); m_TexSrcUnpacked.Release(); m_TexResize.Release(); m_TexsPostScale.Release(); m_BackBuffer.Release(); m_TexImage.Release();
+        m_TexConvertOutput.Release(); m_TexSrcUnpacked.Release(); m_TexResize.Release(); m_TexsPostScale.Release(); m_TexsPostScale2.Release(); m_BackBuffer.Release(); m_TexImage.Release();
         m_dbgConvertF32.Release();
         m_axisX.Release(); m_axisY.Release(); m_pointX.Release(); m_pointY.Release(); m_pointRX.Release(); m_pointRY.Release();
         if (m_ownStream && m_stream) cudaStreamDestroy(m_stream);
@@ -95,6 +95,10 @@ void CB200VideoProcessor::ApplySettings(const mpcvr_settings& s)
     m_bConvertToSdr = s.bConvertToSdr != 0;
     m_iSDRDisplayNits = s.iSDRDisplayNits;
     if (m_iSDRDisplayNits < MPCVR_SDR_NITS_MIN || m_iSDRDisplayNits > MPCVR_SDR_NITS_MAX) m_iSDRDisplayNits = MPCVR_SDR_NITS_DEF;
+    m_bHdrPassthrough = s.bHdrPassthrough != 0;
+    m_bHdrLocalToneMapping = s.bHdrLocalToneMapping != 0;
+    m_iHdrLocalToneMappingType = s.iHdrLocalToneMappingType;
+    m_iHdrDisplayMaxNits = s.iHdrDisplayMaxNits;
 }
 
 int32_t CB200VideoProcessor::Init(const mpcvr_settings* s, int device, void* stream)
@@ -244,9 +248,12 @@ int CB200VideoProcessor::Transfer() const
 {
     // GetShaderConvertColor, Source/Shaders.cpp:613-616, :861-915; convertType per UpdateConvertColorShader (:2948-2950)
     // with no HDR display: SHADER_CONVERT_TO_SDR iff m_bConvertToSdr.
+    // HDR output: SHADER_CONVERT_TO_PQ for HLG, SHADER_CONVERT_NONE otherwise (:2948-2950)
     const uint32_t trc = m_srcExFmt.TransferFunction();
-    if (m_bConvertToSdr && trc == Trc_2084) return TRANSFER_PQ_TO_SDR;
-    if (m_bConvertToSdr && trc == Trc_HLG)  return TRANSFER_HLG_TO_SDR;
+    const bool toSdr = m_bConvertToSdr && !HdrOut();
+    if (toSdr && trc == Trc_2084) return TRANSFER_PQ_TO_SDR;
+    if (toSdr && trc == Trc_HLG)  return TRANSFER_HLG_TO_SDR;
+    if (HdrOut() && trc == Trc_HLG) return TRANSFER_HLG_TO_PQ;
     if (m_srcExFmt.Primaries() == Prim_BT2020) {
         switch (trc) {
         case Trc_18: case Trc_20: case Trc_HLG: case Trc_22: case Trc_709: case Trc_240M: case Trc_sRGB: case Trc_28: case Trc_26:
@@ -350,6 +357,51 @@ int32_t CB200VideoProcessor::SetFlip(bool v)
     return Fail(MPCVR_E_NOTIMPL, "flip is not implemented on this path (SURVEY 8f-4)");
 }
 
+int32_t CB200VideoProcessor::SetDisplayHdr(bool supported)
+{
+    // m_bHdrPassthroughSupport: in the reference it is read from the DXGI output (HDR-capable display + OS HDR mode)
+    if (supported == m_bHdrPassthroughSupport) return MPCVR_S_OK;
+    m_bHdrPassthroughSupport = supported;
+    m_hdrColorSpaceActive = false; m_bTonemap = false; m_lastHdr10 = Hdr10();
+    if (m_bInit) SetShaderConvertColorParams();
+    m_planDirty = true;
+    return MPCVR_S_OK;
+}
+
+void CB200VideoProcessor::SetHDR10ShaderParams(float mn, float mx, float cll, float fall, float disp, int type)
+{
+    if (mn <= 0.f) mn = 0.f;                                                  // :911-916
+    if (mx <= 10.f) mx = 1000.f;
+    if (cll <= 10.f) cll = mx;
+    if (fall <= 1.f) fall = cll;
+    if (disp < 100.f || disp > 10000.f) disp = 1000.f;
+    if (type < 1 || type > 6) type = 1;
+    m_tm.min_nits = mn; m_tm.max_nits = mx; m_tm.max_cll = cll; m_tm.max_fall = fall; m_tm.display = disp; m_tm.sel = type;
+    m_bTonemap = true;                                                        // m_pPSHDR10ToneMapping created, :924-929
+}
+
+void CB200VideoProcessor::UpdateHdrState()
+{
+    // The part of Render() under "if (m_pDXGISwapChain4)" (:2626-2727); that swap chain exists when
+    // bHdrOutput = m_bHdrPassthroughSupport && (m_bHdrPassthrough || m_bHdrLocalToneMapping) && SourceIsHDR() (:1476).
+    if (!(HdrOut() && SourceIsHDR10orHLG())) { m_hdrColorSpaceActive = false; m_bTonemap = false; return; }
+    if (!m_hdrColorSpaceActive) {                                             // SetColorSpace1(G2084/P2020) succeeded, :2651-2690
+        m_hdrColorSpaceActive = true;
+        if (m_hdr10.bValid) m_lastHdr10 = m_hdr10;
+        else if (!m_lastHdr10.bValid) {                                       // Display-P3 defaults, :2673-2684
+            m_lastHdr10 = Hdr10(); m_lastHdr10.bValid = true;
+            m_lastHdr10.MaxMasteringLuminance = 1000; m_lastHdr10.MinMasteringLuminance = 50;
+        }
+    } else if (m_hdr10.bValid) {                                              // :2703-2712
+        if (m_hdr10.MaxMasteringLuminance != m_lastHdr10.MaxMasteringLuminance || m_hdr10.MinMasteringLuminance != m_lastHdr10.MinMasteringLuminance ||
+            m_hdr10.MaxCLL != m_lastHdr10.MaxCLL || m_hdr10.MaxFALL != m_lastHdr10.MaxFALL || !m_lastHdr10.bValid) m_lastHdr10 = m_hdr10;
+    }
+    if (m_bHdrLocalToneMapping && m_lastHdr10.bValid)                         // :2715-2725 (no Dolby Vision L1 on this path)
+        SetHDR10ShaderParams((float)m_lastHdr10.MinMasteringLuminance, (float)m_lastHdr10.MaxMasteringLuminance, (float)m_lastHdr10.MaxCLL,
+                             (float)m_lastHdr10.MaxFALL, (float)m_iHdrDisplayMaxNits, m_iHdrLocalToneMappingType);
+    else m_bTonemap = false;
+}
+
 void CB200VideoProcessor::GetVideoSize(int32_t& w, int32_t& h) const
 {
     w = m_srcRectWidth; h = m_srcRectHeight;                                // CVideoProcessor::GetVideoSize, Source/VideoProcessor.cpp
@@ -363,10 +415,12 @@ void CB200VideoProcessor::Configure(const mpcvr_settings& s)
 {
     // diff and rebuild the minimum, like Source/DX11VideoProcessor.cpp:3800-4050
     const int oldTex = m_iTexFormat; const bool oldSdr = m_bConvertToSdr; const int oldNits = m_iSDRDisplayNits;
+    const bool oldHdrOut = HdrOut();
     ApplySettings(s);
     if (!m_bInit) return;
     if (oldTex != m_iTexFormat) { UpdateTexParams(m_srcParams.CDepth); UpdateTexures(); }
-    if (oldSdr != m_bConvertToSdr) SetShaderConvertColorParams();
+    if (oldSdr != m_bConvertToSdr || oldHdrOut != HdrOut()) SetShaderConvertColorParams();
+    if (!HdrOut()) { m_hdrColorSpaceActive = false; m_bTonemap = false; }
     if (oldNits != m_iSDRDisplayNits) SetShaderLuminanceParams();
     UpdatePostScaleTexures();
     m_planDirty = true;
@@ -482,6 +536,20 @@ int32_t CB200VideoProcessor::CopySample(const mpcvr_sample* s)
     S.deint_blend = (m_bDeintBlend && m_bInterlaced && f.Subsampling == 420) ? 1 : 0;   // :2965, :3075
     S.rect_l = m_srcRect.left; S.rect_t = m_srcRect.top; S.rect_w = m_srcRectWidth; S.rect_h = m_srcRectHeight;
 
+    m_hdr10 = Hdr10();                                                        // :2231
+    if (SourceIsHDR10orHLG() && (m_bHdrPassthrough || m_bHdrLocalToneMapping)) {   // IMediaSideData HDR blobs, :2233-2268
+        if (const mpcvr_side_data_hdr* hdr = s->hdr) {
+            const double* px = hdr->display_primaries_x; const double* py = hdr->display_primaries_y;
+            if (px[0] > 0. && px[1] > 0. && px[2] > 0. && py[0] > 0. && py[1] > 0. && py[2] > 0. && hdr->white_point_x > 0. && hdr->white_point_y > 0.
+                && hdr->max_display_mastering_luminance > 0. && hdr->min_display_mastering_luminance > 0.) {
+                m_hdr10.bValid = true;
+                m_hdr10.MaxMasteringLuminance = (uint32_t)std::lround(hdr->max_display_mastering_luminance);
+                m_hdr10.MinMasteringLuminance = (uint32_t)std::lround(hdr->min_display_mastering_luminance * 10000.0);
+            }
+        }
+        if (const mpcvr_side_data_hdr_cll* cll = s->hdr_cll) { m_hdr10.MaxCLL = (uint16_t)cll->MaxCLL; m_hdr10.MaxFALL = (uint16_t)cll->MaxFALL; }
+    }
+
     if (s->flags & MPCVR_SAMPLE_DEVICE_MEMORY) {
         // IMediaSampleD3D11 path (:2528-2570): the decoder's planes are read in place
         const int np = f.layout == LAYOUT_BIPLANAR ? 2 : (f.layout == LAYOUT_PLANAR3 ? 3 : 1);
@@ -530,6 +598,7 @@ int32_t CB200VideoProcessor::Render(int field, int64_t frameStartTime)
     m_lastLaunches = 0;
     Tex2D& target = CurrentTarget();
     if (!target.ptr) { int32_t hr = UpdatePostScaleTexures(); if (hr != MPCVR_S_OK) return hr; }
+    UpdateHdrState();
     int32_t hr = Process(CurrentTarget(), m_srcRect, m_videoRect, false);
     if (hr != MPCVR_S_OK) return hr;
     return DrawSubtitles(CurrentTarget());
@@ -641,6 +710,12 @@ int32_t CB200VideoProcessor::FinalPass(const Tex2D& tex, const Tex2D& rt, const 
     return Cuda(LaunchFinalPass(tex.desc(), rt.desc(), rect.left, rect.top, rect.right, rect.bottom, Q, m_stream), "FinalPass") ? MPCVR_S_OK : MPCVR_E_FAIL;
 }
 
+int32_t CB200VideoProcessor::TonemapPass(const Tex2D& tex, const Tex2D& rt, const CRect& rect)
+{
+    m_lastLaunches++;
+    return Cuda(LaunchTonemapPass(tex.desc(), rt.desc(), m_color, m_tm, rect.left, rect.top, rect.right, rect.bottom, m_stream), "HDR10 tone-map") ? MPCVR_S_OK : MPCVR_E_FAIL;
+}
+
 int32_t CB200VideoProcessor::Process(const Tex2D& target, const CRect& srcRect, const CRect& dstRect, bool skipConvert)
 {
     (void)srcRect;
@@ -686,16 +761,20 @@ int32_t CB200VideoProcessor::Process(const Tex2D& target, const CRect& srcRect, 
         pInputTexture = &m_TexSrcUnpacked; rSrc = m_srcRect;
     } else if (!skipConvert) { hr = ConvertColorPass(m_TexConvertOutput); if (hr != MPCVR_S_OK) return hr; }
 
-    if (m_bFinalPass) {                                                       // numSteps == 1, :3325-3416
-        if (!m_TexsPostScale.ptr || m_TexsPostScale.w != target.w || m_TexsPostScale.h != target.h || m_TexsPostScale.fmt != m_InternalTexFmt) {
-            if (!Cuda(m_TexsPostScale.CheckCreate(m_InternalTexFmt, target.w, target.h), "m_TexsPostScale")) return MPCVR_E_FAIL;
-        }
+    const int numSteps = (m_bTonemap ? 1 : 0) + (m_bFinalPass ? 1 : 0);       // GetPostScaleSteps, :779-795
+    if (numSteps) {                                                           // :3325-3416
+        if (!Cuda(m_TexsPostScale.CheckCreate(m_InternalTexFmt, target.w, target.h), "m_TexsPostScale")) return MPCVR_E_FAIL;
+        if (numSteps > 1 && !Cuda(m_TexsPostScale2.CheckCreate(m_InternalTexFmt, target.w, target.h), "m_TexsPostScale[1]")) return MPCVR_E_FAIL;
         const Tex2D* pTex = &m_TexsPostScale;
         CRect rect; rect.IntersectRect(dstRect, CRect(0, 0, pTex->w, pTex->h));
         if (rSrc != dstRect) { hr = ResizeShaderPass(*pInputTexture, *pTex, rSrc, dstRect); if (hr != MPCVR_S_OK) return hr; }
         else pTex = pInputTexture;                                            // "Hmm", :3351
-        hr = FinalPass(*pTex, target, rect);
-        m_bDitherUsed = true;
+        if (m_bTonemap) {                                                     // StepSetting(); :3359-3367
+            const Tex2D& rt = m_bFinalPass ? m_TexsPostScale2 : target;
+            hr = TonemapPass(*pTex, rt, rect); if (hr != MPCVR_S_OK) return hr;
+            pTex = &rt;
+        }
+        if (m_bFinalPass) { hr = FinalPass(*pTex, target, rect); m_bDitherUsed = true; }
         return hr;
     }
     return ResizeShaderPass(*pInputTexture, target, rSrc, dstRect);           // :3418
@@ -708,6 +787,7 @@ bool CB200VideoProcessor::PlanFused(const Tex2D& target, const CRect& dstRect, F
 {
     memset(&fp, 0, sizeof(fp));
     if (!m_PSConvColorData.enable) { if (why) *why = "no convert pass on this plan (RGB source, default ProcAmp): multipass only"; return false; }
+    if (m_bTonemap) { if (why) *why = "HDR10 tone-map post-scale step: multipass only"; return false; }
     fp.src = m_src; fp.color = m_color;
     fp.ax = m_axisX.table(); fp.ay = m_axisY.table();
     fp.out = target.desc();

@@ -92,6 +92,7 @@ public:
     int32_t SetWindowRect(const CRect& r);
     int32_t SetRotation(int v);
     int32_t SetFlip(bool v);
+    int32_t SetDisplayHdr(bool supported);
     void    GetVideoSize(int32_t& w, int32_t& h) const;
     void    GetAspectRatio(int32_t& ax, int32_t& ay) const;
 
@@ -139,6 +140,9 @@ private:
     bool m_bConvertToSdr = true;
     int  m_iSDRDisplayNits = MPCVR_SDR_NITS_DEF;
     bool m_bUseD3D11 = true;                 // which shader set is restated (D3D11 / D3D9 twins)
+    // HDR output (Source/VideoProcessor.h:66-71): the display capability comes from the caller (mpcvr_set_display_hdr)
+    bool m_bHdrPassthroughSupport = false, m_bHdrPassthrough = true, m_bHdrLocalToneMapping = false;
+    int  m_iHdrLocalToneMappingType = 1, m_iHdrDisplayMaxNits = 1000;
     void ApplySettings(const mpcvr_settings& s);
 
     // ---- input parameters (Source/VideoProcessor.h:80-95)
@@ -177,6 +181,20 @@ private:
     Tex2D m_TexConvertOutput, m_TexResize, m_TexsPostScale, m_BackBuffer, m_TexImage;
     Tex2D m_UserBackBuffer;                      // caller-bound target (not owned)
     DevArray<float4> m_dbgConvertF32; bool m_captureF32 = false;
+
+    // DXGI_HDR_METADATA_HDR10 subset kept per sample / last applied (HDRMetadata, Source/DX11VideoProcessor.h)
+    struct Hdr10 { bool bValid = false; uint32_t MaxMasteringLuminance = 0, MinMasteringLuminance = 0; uint16_t MaxCLL = 0, MaxFALL = 0; };
+    Hdr10 m_hdr10, m_lastHdr10;
+    bool  m_hdrColorSpaceActive = false;         // m_currentSwapChainColorSpace == RGB_FULL_G2084_NONE_P2020
+    bool  m_bTonemap = false;                    // m_pPSHDR10ToneMapping exists
+    TonemapParams m_tm = {};
+    Tex2D m_TexsPostScale2;                      // second texture of the m_TexsPostScale ring (two post-scale steps)
+    bool  HdrOut() const { return m_bHdrPassthroughSupport && (m_bHdrPassthrough || m_bHdrLocalToneMapping); }
+    bool  SourceIsHDR10orHLG() const {           // Source/VideoProcessor.h:239-242
+        return (m_decExFmt.TransferFunction() == Trc_2084 && m_decExFmt.TransferMatrix() != Matrix_Unknown) || m_decExFmt.TransferFunction() == Trc_HLG; }
+    void  UpdateHdrState();                      // the HDR part of Render(), :2626-2727
+    void  SetHDR10ShaderParams(float minNits, float maxNits, float maxCLL, float maxFALL, float displayMaxNits, int type);   // :907-951
+    int32_t TonemapPass(const Tex2D& tex, const Tex2D& rt, const CRect& rect);
 
     ColorTransform m_PSConvColorData = {};
     ColorParams    m_color = {};

@@ -92,6 +92,9 @@ class VideoProcessor:
     def SetFlip(self, flip):
         return self._L.mpcvr_set_flip(self._h, int(flip))
 
+    def SetDisplayHdr(self, supported):
+        return self._L.mpcvr_set_display_hdr(self._h, int(bool(supported)))
+
     def GetSettings(self):
         s = A.Settings(); self._L.mpcvr_get_settings(self._h, C.byref(s)); return s
 
@@ -115,9 +118,24 @@ class VideoProcessor:
         return self._check(self._L.mpcvr_bind_backbuffer(self._h, dev_ptr, pitch), "BindBackbuffer")
 
     # -- frames
-    def ProcessSample(self, data=None, pitch=0, device_planes=None, device_pitches=None, rt_start=0, rt_end=0, check=True):
+    def ProcessSample(self, data=None, pitch=0, device_planes=None, device_pitches=None, rt_start=0, rt_end=0, check=True,
+                      hdr=None, hdr_cll=None):
+        """hdr: dict(max_lum, min_lum[, primaries_x, primaries_y, white]) -> MediaSideDataHDR; hdr_cll: (MaxCLL, MaxFALL)"""
         s = A.Sample()
         s.rt_start, s.rt_end = rt_start, rt_end
+        if hdr is not None:
+            h = A.SideDataHDR()
+            px = hdr.get("primaries_x", (0.265, 0.150, 0.680)); py = hdr.get("primaries_y", (0.690, 0.060, 0.320))
+            for i in range(3):
+                h.display_primaries_x[i] = px[i]; h.display_primaries_y[i] = py[i]
+            h.white_point_x, h.white_point_y = hdr.get("white", (0.3127, 0.3290))
+            h.max_display_mastering_luminance = hdr["max_lum"]; h.min_display_mastering_luminance = hdr["min_lum"]
+            self._keep_hdr = h
+            s.hdr = C.pointer(h)
+        if hdr_cll is not None:
+            c = A.SideDataHDRCLL(); c.MaxCLL, c.MaxFALL = hdr_cll
+            self._keep_cll = c
+            s.hdr_cll = C.pointer(c)
         if device_planes is not None:
             s.flags = A.SAMPLE_DEVICE_MEMORY
             for i, p in enumerate(device_planes):
