@@ -450,3 +450,29 @@ def test_hdr_settings_without_hdr_display_change_nothing():
     """bHdrPassthrough defaults to true, but without an HDR display the SDR conversion stays (m_bHdrPassthroughSupport false)"""
     case = H.baseline_cases(scale=0.05)[1]
     _check(case, "natural", seed=27)
+
+
+# ---- gamma + UNORM10 quantiser through the threshold table (fused 2x PQ kernel) ----
+def test_gamma_threshold_table_is_exhaustively_exact():
+    """every float of [0,1]: table path == direct Q10(pow(x, 1/2.2)) read back, bit for bit (1.07e9 values, on the device)"""
+    case = H.baseline_cases(scale=0.05)[1]
+    vp = case.make_processor(device=0)
+    assert vp.debug_verify_gamma_table() == 0
+
+
+def test_gamma_threshold_table_on_off_same_frame():
+    case = H.baseline_cases(scale=0.25)[1]
+    codes = H.make_codes(case.cf, case.w, case.h, "fullnoise", 31)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    outs = []
+    try:
+        for on in (1, 0):
+            vp = case.make_processor(device=0, path=PATH_FUSED)
+            vp.debug_set_gamma_table(on)
+            vp.ProcessSample(data=buf, pitch=pitch)
+            outs.append(vp.ReadBackbuffer())
+    finally:
+        vp.debug_set_gamma_table(1)
+    assert np.array_equal(outs[0], outs[1])
+    ref = H.run_oracle(case, planes, pitches)
+    assert H.compare(outs[0], ref, case.backbuffer) == (0, 0)

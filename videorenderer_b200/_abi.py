@@ -176,6 +176,8 @@ SIGNATURES = {
     "mpcvr_get_last_frame_kernels": (C.c_int32, [vp, P(C.c_int32)]),
     # debug header
     "mpcvr_debug_set_path": (C.c_int32, [vp, C.c_int32]),
+    "mpcvr_debug_set_gamma_table": (C.c_int32, [C.c_int32]),
+    "mpcvr_debug_verify_gamma_table": (C.c_int64, [vp]),
     "mpcvr_debug_get_plan": (C.c_int32, [vp, P(PlanInfo)]),
     "mpcvr_debug_get_color_params": (C.c_int32, [vp, vp, vp, vp, P(C.c_float)]),
     "mpcvr_debug_axis_taps": (C.c_int32, [vp, C.c_int32, C.c_int32, P(C.c_int32), vp, C.c_int32, P(C.c_float)]),

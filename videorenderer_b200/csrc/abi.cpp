@@ -96,6 +96,8 @@ int32_t mpcvr_get_stream(mpcvr* h, void** st) { VP_OR(MPCVR_E_POINTER); if (!st)
 int32_t mpcvr_get_last_frame_kernels(mpcvr* h, int32_t* n) { VP_OR(MPCVR_E_POINTER); if (!n) return MPCVR_E_POINTER; *n = vp.LastFrameKernels(); return MPCVR_S_OK; }
 
 // ---- debug surface
+int64_t mpcvr_debug_verify_gamma_table(mpcvr* h) { VP_OR(-2); return vp.DebugVerifyGammaTable(); }
+int32_t mpcvr_debug_set_gamma_table(int32_t enable) { b200vr::SetGammaTableEnabled(enable != 0); return MPCVR_S_OK; }
 int32_t mpcvr_debug_set_path(mpcvr* h, int32_t path) { VP_OR(MPCVR_E_POINTER); return vp.DebugSetPath(path); }
 int32_t mpcvr_debug_get_plan(mpcvr* h, mpcvr_plan_info* info) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugGetPlan(info)); }
 int32_t mpcvr_debug_get_color_params(mpcvr* h, float m9[9], float c3[3], float g9[9], float* lum) { VP_OR(MPCVR_E_POINTER); return vp.DebugGetColorParams(m9, c3, g9, lum); }

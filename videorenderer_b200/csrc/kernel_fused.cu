@@ -17,6 +17,8 @@
 // With a 2x ratio every output pair (2j, 2j+1) uses the source window [j+b0, j+b0+NT]; there are exactly two
 // weight vectors (phase t=3/4 and t=1/4), passed as kernel parameters.
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <mutex>
 #include <cuda_fp16.h>
 #include "kernels.h"
 #include "pixel_ops.cuh"
@@ -29,6 +31,42 @@ namespace b200vr {
 #define MPCVR_DITHER_F(k) ((float)(k) * 0.0009765625f)
 __device__ const uint16_t g_dither32_fused[1024] = { MPCVR_DITHER32_VALUES };
 __device__ float g_dither32_f[1024];
+// ---- gamma + UNORM10 quantiser as a threshold table ---------------------------------------------------------------
+// The last two steps of the convert shader on the 10-bit path are  c = Q10(pow(sat(x), 1/2.2))  and the read-back c/1023.
+// As a function of the float x in [0,1] the code c is a step function, so it is stored as its 1023 step positions
+// T[c] = smallest x whose code is >= c, found once per process by scanning EVERY float of [0,1] with the contract's own
+// pow (k_gamma_scan, ~1.07e9 evaluations).  Where the contract's pow is not monotone across a step (one float on this
+// exponent: 0x3f0f90d2 reads 786 between two 787s) the scan records the float as an exception.  In the kernel a MUFU
+// estimate biased a quarter code low gives c0 with c in {c0, c0+1}; one compare against T[c0+1] decides -- bit-exact by
+// construction, ~25 % fewer FMA-pipe cycles in stage A.  More than kGammaMaxExc exceptions -> the table is not used.
+constexpr int kGammaN = 1023;
+constexpr int kGammaMaxExc = 2;
+constexpr int kGammaMaxTrans = 4096;
+__device__ float    g_gammaT[kGammaN + 2];       // T[0] = 0, T[1..N], T[N+1] = +inf
+__device__ float    g_gammaD[kGammaN + 1];       // c / 1023, correctly rounded
+__device__ uint32_t g_gammaExc[kGammaMaxExc];    // float bit patterns whose code is one below the table's
+__device__ uint32_t g_gammaTransCount;
+__device__ uint2    g_gammaTrans[kGammaMaxTrans];   // (u, from << 16 | to): code(u - 1 ulp) = from, code(u) = to
+
+__device__ __forceinline__ uint32_t gamma_code(float x) { return qunorm(powr(x, 1.0f / 2.2f), (float)kGammaN); }
+
+__global__ void __launch_bounds__(256) k_gamma_scan(uint32_t run)
+{
+    const uint64_t first = 1ull + (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * run;
+    if (first > 0x3f800000ull) return;
+    const uint32_t last = (uint32_t)min(first + run - 1, (uint64_t)0x3f800000u);
+    uint32_t prev = gamma_code(__uint_as_float((uint32_t)first - 1u));
+    for (uint32_t u = (uint32_t)first; u <= last; u++) {
+        const uint32_t c = gamma_code(__uint_as_float(u));
+        if (c != prev) {
+            const uint32_t i = atomicAdd(&g_gammaTransCount, 1u);
+            if (i < kGammaMaxTrans) g_gammaTrans[i] = make_uint2(u, (prev << 16) | c);
+        }
+        prev = c;
+        if (u == 0x3f800000u) break;
+    }
+}
+
 __global__ void k_init_dither() { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < 1024) g_dither32_f[i] = MPCVR_DITHER_F(g_dither32_fused[i]); }
 
 constexpr int kCore = 64;            // convert-surface pixels per tile side
@@ -147,6 +185,18 @@ __device__ __forceinline__ float2 pq_channel_to_hable2(const ColorParams& P, flo
     return mul2(add2(div_rn_safe_2(hn, hd), -P.hable_ef), P.hable_rdiv);
 }
 
+// everything before the final pow: saturate(mul(matrix_conv_prim, ToneMappingHable(ST2084ToLinear(saturate(rgb)))))
+__device__ __forceinline__ f3x2 convert_color_pq2_pre(const ColorParams& P, const f3x2& yuv)
+{
+    f3x2 c;
+    c.x = add2(dp3_2(P.cm[0], yuv), P.cc[0]); c.y = add2(dp3_2(P.cm[1], yuv), P.cc[1]); c.z = add2(dp3_2(P.cm[2], yuv), P.cc[2]);
+    f3x2 h;
+    h.x = pq_channel_to_hable2(P, c.x); h.y = pq_channel_to_hable2(P, c.y); h.z = pq_channel_to_hable2(P, c.z);
+    f3x2 g;
+    g.x = sat2(dp3_2(P.gamut[0], h)); g.y = sat2(dp3_2(P.gamut[1], h)); g.z = sat2(dp3_2(P.gamut[2], h));
+    return g;
+}
+
 __device__ __forceinline__ f3x2 convert_color_pq2(const ColorParams& P, const f3x2& yuv)
 {
     f3x2 c;
@@ -167,11 +217,32 @@ __device__ __forceinline__ float2 rt_roundtrip2(int fmt, float2 v)
     return make_float2(f16_roundtrip(v.x), f16_roundtrip(v.y));
 }
 
-// bi-planar 16-bit source, bilinear chroma, PQ->SDR, two pixels per work item
+// gamma + UNORM10 write + read-back through the threshold table (see g_gammaT): x is already saturated
+__device__ __forceinline__ float gamma_q10_thr(float x, const float* __restrict__ sT, const float* __restrict__ sD, uint32_t exc0, uint32_t exc1)
+{
+    float l, e;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l * (1.0f / 2.2f)));
+    const int c0 = (int)fmaf(e, (float)kGammaN, 0.25f);                    // true code is c0 or c0 + 1
+    const uint32_t xb = __float_as_uint(x);
+    int c = c0 + (x >= sT[c0 + 1] ? 1 : 0);
+    c -= (xb == exc0 || xb == exc1) ? 1 : 0;
+    return sD[c];
+}
+
+// bi-planar 16-bit source, bilinear chroma, PQ->SDR, two pixels per work item.  THR: 10-bit internal format through the
+// threshold table (sT/sD live behind the chroma texels in the not-yet-used X buffer).
+template <bool THR>
 __device__ __forceinline__ void convert_tile_biplanar16_pq2(const FusedParams& prm, const int ifmt, float* __restrict__ sConv,
                                                             float2* __restrict__ sUV, const int TW, const int TH, const int TWP,
-                                                            const int cx0, const int cy0)
+                                                            const int cx0, const int cy0, float* __restrict__ sT = nullptr,
+                                                            float* __restrict__ sD = nullptr)
 {
+    if (THR) {
+        for (int i = threadIdx.x; i < kGammaN + 2; i += kThreads) sT[i] = g_gammaT[i];
+        for (int i = threadIdx.x; i < kGammaN + 1; i += kThreads) sD[i] = g_gammaD[i];
+    }
+    const uint32_t exc0 = THR ? g_gammaExc[0] : 0u, exc1 = THR ? g_gammaExc[1] : 0u;
     const SrcDesc& S = prm.src;
     int ox, oy, my;
     if (S.subsampling == 420) {
@@ -214,11 +285,18 @@ __device__ __forceinline__ void convert_tile_biplanar16_pq2(const FusedParams& p
             uv[s] = fma2(fy, sub2(bot, top), top);
         }
         yuv.y = make_float2(uv[0].x, uv[1].x); yuv.z = make_float2(uv[0].y, uv[1].y);
-        const f3x2 rgb = convert_color_pq2(prm.color, yuv);
         float* d = sConv + ty * TWP + tx;
-        *reinterpret_cast<float2*>(d)                = rt_roundtrip2(ifmt, rgb.x);
-        *reinterpret_cast<float2*>(d + TH * TWP)     = rt_roundtrip2(ifmt, rgb.y);
-        *reinterpret_cast<float2*>(d + 2 * TH * TWP) = rt_roundtrip2(ifmt, rgb.z);
+        if (THR) {
+            const f3x2 g = convert_color_pq2_pre(prm.color, yuv);            // saturated gamut-mapped linear light
+            *reinterpret_cast<float2*>(d)                = make_float2(gamma_q10_thr(g.x.x, sT, sD, exc0, exc1), gamma_q10_thr(g.x.y, sT, sD, exc0, exc1));
+            *reinterpret_cast<float2*>(d + TH * TWP)     = make_float2(gamma_q10_thr(g.y.x, sT, sD, exc0, exc1), gamma_q10_thr(g.y.y, sT, sD, exc0, exc1));
+            *reinterpret_cast<float2*>(d + 2 * TH * TWP) = make_float2(gamma_q10_thr(g.z.x, sT, sD, exc0, exc1), gamma_q10_thr(g.z.y, sT, sD, exc0, exc1));
+        } else {
+            const f3x2 rgb = convert_color_pq2(prm.color, yuv);
+            *reinterpret_cast<float2*>(d)                = rt_roundtrip2(ifmt, rgb.x);
+            *reinterpret_cast<float2*>(d + TH * TWP)     = rt_roundtrip2(ifmt, rgb.y);
+            *reinterpret_cast<float2*>(d + 2 * TH * TWP) = rt_roundtrip2(ifmt, rgb.z);
+        }
     }
 }
 
@@ -280,7 +358,8 @@ cudaError_t LaunchProbePQ(const float* y, const float* u, const float* v, float*
 }
 
 // which stage A a kernel instantiation carries
-enum { CONV_GENERIC = 0, CONV_BIPLANAR16_PQ = 1, CONV_BIPLANAR8_NONE = 2, CONV_BIPLANAR16_ANY = 3, CONV_BIPLANAR8_ANY = 4 };
+enum { CONV_GENERIC = 0, CONV_BIPLANAR16_PQ = 1, CONV_BIPLANAR8_NONE = 2, CONV_BIPLANAR16_ANY = 3, CONV_BIPLANAR8_ANY = 4,
+       CONV_BIPLANAR16_PQ_THR = 5 /* 10-bit internal format only: gamma + quantiser through the threshold table */ };
 // which (internal, target, final) combination is fixed at compile time
 enum { SPEC_RUNTIME = 0, SPEC_10_BGRA8_DITHER = 1, SPEC_8_BGRA8 = 2 };
 
@@ -309,7 +388,11 @@ k_fused2x(const __grid_constant__ FusedParams prm)
     {
         float2* sUV = reinterpret_cast<float2*>(sX);                 // aliases the (still unused) X-pass buffer
         const int cx0 = jx0 + prm.b0, cy0 = jy0 + prm.b0;
-        if (CONV == CONV_BIPLANAR16_PQ)        convert_tile_biplanar16_pq2(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
+        if (CONV == CONV_BIPLANAR16_PQ)        convert_tile_biplanar16_pq2<false>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
+        else if (CONV == CONV_BIPLANAR16_PQ_THR) {
+            float* sT = reinterpret_cast<float*>(smem_raw + G::conv_bytes + G::x_bytes) - (2 * kGammaN + 4);   // tail of the X buffer
+            convert_tile_biplanar16_pq2<true>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0, sT, sT + kGammaN + 2);
+        }
         else if (CONV == CONV_BIPLANAR8_NONE)  convert_tile_biplanar<1, TRANSFER_NONE>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
         else if (CONV == CONV_BIPLANAR16_ANY)  convert_tile_biplanar<2, -1>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
         else if (CONV == CONV_BIPLANAR8_ANY)   convert_tile_biplanar<1, -1>(prm, IFMT, sConv, sUV, G::TW, G::TH, G::TWP, cx0, cy0);
@@ -652,6 +735,9 @@ static cudaError_t LaunchC(const FusedParams& prm, int conv, cudaStream_t st)
 {
     switch (conv) {
     case CONV_BIPLANAR16_PQ:   return LaunchT<NT, SPEC, CONV_BIPLANAR16_PQ>(prm, st);
+    case CONV_BIPLANAR16_PQ_THR:
+        if (SPEC == SPEC_10_BGRA8_DITHER) return LaunchT<NT, SPEC_10_BGRA8_DITHER, CONV_BIPLANAR16_PQ_THR>(prm, st);
+        return LaunchT<NT, SPEC, CONV_BIPLANAR16_PQ>(prm, st);
     case CONV_BIPLANAR8_NONE:  return LaunchT<NT, SPEC, CONV_BIPLANAR8_NONE>(prm, st);
     case CONV_BIPLANAR16_ANY:  return LaunchT<NT, SPEC, CONV_BIPLANAR16_ANY>(prm, st);
     case CONV_BIPLANAR8_ANY:   return LaunchT<NT, SPEC, CONV_BIPLANAR8_ANY>(prm, st);
@@ -675,6 +761,90 @@ static cudaError_t EnsureDither(cudaStream_t st)
     k_init_dither<<<4, 256, 0, st>>>();
     if (dev >= 0 && dev < 64) done[dev] = true;
     return cudaGetLastError();
+}
+
+// builds g_gammaT / g_gammaD / g_gammaExc once per device; returns false (and leaves the plain kernel in charge) when the
+// scan finds the step function unusable
+static int g_useGammaTable = 1;                       // debug switch (mpcvr_debug_set_gamma_table)
+void SetGammaTableEnabled(int on) { g_useGammaTable = on; }
+
+static bool EnsureGammaTable(cudaStream_t st)
+{
+    static int state[64] = {};                        // 0 unknown, 1 ready, 2 unusable
+    static std::mutex mtx;
+    std::lock_guard<std::mutex> lock(mtx);
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return false;
+    if (state[dev]) return state[dev] == 1;
+    state[dev] = 2;
+    const uint32_t zero = 0;
+    if (cudaMemcpyToSymbolAsync(g_gammaTransCount, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+    const uint32_t run = 2048, threads = (0x3f800000u + run - 1) / run;
+    k_gamma_scan<<<(threads + 255) / 256, 256, 0, st>>>(run);
+    uint32_t count = 0;
+    static uint2 trans[kGammaMaxTrans];
+    if (cudaMemcpyFromSymbolAsync(&count, g_gammaTransCount, sizeof(count), 0, cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
+    if (cudaStreamSynchronize(st) != cudaSuccess || count == 0 || count > kGammaMaxTrans) return false;
+    if (cudaMemcpyFromSymbol(trans, g_gammaTrans, sizeof(uint2) * count, 0, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    std::sort(trans, trans + count, [](const uint2& a, const uint2& b) { return a.x < b.x; });
+    static float T[kGammaN + 2], D[kGammaN + 1];
+    uint32_t exc[kGammaMaxExc]; int nexc = 0;
+    for (int i = 0; i < kGammaMaxExc; i++) exc[i] = 0xFFFFFFFFu;
+    for (int c = 0; c <= kGammaN + 1; c++) T[c] = 0.0f;
+    uint32_t top = 0;                                 // highest code reached so far; code(0.0f) = 0
+    for (uint32_t i = 0; i < count; i++) {
+        const uint32_t u = trans[i].x, from = trans[i].y >> 16, to = trans[i].y & 0xFFFFu;
+        if (to > from) {
+            if (from == top) { for (uint32_t c = top + 1; c <= to && c <= (uint32_t)kGammaN; c++) memcpy(&T[c], &u, 4); top = to; }
+            else if (to != top) return false;         // climbing back after a dip must land on the plateau
+        } else {
+            // a dip: only single-float dips of one code are representable (next transition restores the plateau one ulp later)
+            if (from != top || to + 1 != from || i + 1 >= count || trans[i + 1].x != u + 1 || (trans[i + 1].y & 0xFFFFu) != top) return false;
+            if (nexc >= kGammaMaxExc) return false;
+            exc[nexc++] = u;
+        }
+    }
+    if (top != (uint32_t)kGammaN) return false;
+    { const uint32_t inf = 0x7f800000u; memcpy(&T[kGammaN + 1], &inf, 4); }
+    for (int c = 0; c <= kGammaN; c++) D[c] = (float)((double)c / (double)kGammaN);
+    if (cudaMemcpyToSymbolAsync(g_gammaT, T, sizeof(T), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+    if (cudaMemcpyToSymbolAsync(g_gammaD, D, sizeof(D), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+    if (cudaMemcpyToSymbolAsync(g_gammaExc, exc, sizeof(exc), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return false;    // T, D are function statics reused across devices
+    state[dev] = 1;
+    return true;
+}
+
+// exhaustive self-check used by the tests: the table path against the direct evaluation on every float of [0,1]
+__device__ unsigned long long g_gammaMismatch;
+__global__ void __launch_bounds__(256) k_gamma_verify(uint32_t run)
+{
+    const uint64_t first = (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * run;
+    if (first > 0x3f800000ull) return;
+    const uint32_t last = (uint32_t)min(first + run - 1, (uint64_t)0x3f800000u);
+    const uint32_t exc0 = g_gammaExc[0], exc1 = g_gammaExc[1];
+    unsigned bad = 0;
+    for (uint32_t u = (uint32_t)first; ; u++) {
+        const float x = __uint_as_float(u);
+        const float direct = unorm10(gamma_code(x));
+        const float table = gamma_q10_thr(x, g_gammaT, g_gammaD, exc0, exc1);
+        bad += (__float_as_uint(direct) != __float_as_uint(table)) ? 1u : 0u;
+        if (u == last) break;
+    }
+    if (bad) atomicAdd(&g_gammaMismatch, (unsigned long long)bad);
+}
+
+long long VerifyGammaTable(cudaStream_t st)
+{
+    if (!EnsureGammaTable(st)) return -1;
+    const unsigned long long zero = 0;
+    if (cudaMemcpyToSymbolAsync(g_gammaMismatch, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return -2;
+    const uint32_t run = 2048, threads = (0x3f800000u + run) / run + 1;
+    k_gamma_verify<<<(threads + 255) / 256, 256, 0, st>>>(run);
+    unsigned long long bad = 0;
+    if (cudaMemcpyFromSymbolAsync(&bad, g_gammaMismatch, sizeof(bad), 0, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
+    return (long long)bad;
 }
 
 cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
@@ -733,6 +903,7 @@ cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
         (S.subsampling == 420 || S.subsampling == 422)) {
         if (S.bytes == 2) conv = (p.color.transfer == TRANSFER_PQ_TO_SDR) ? CONV_BIPLANAR16_PQ : CONV_BIPLANAR16_ANY;
         else              conv = (p.color.transfer == TRANSFER_NONE) ? CONV_BIPLANAR8_NONE : CONV_BIPLANAR8_ANY;
+        if (conv == CONV_BIPLANAR16_PQ && spec == SPEC_10_BGRA8_DITHER && g_useGammaTable && EnsureGammaTable(st)) conv = CONV_BIPLANAR16_PQ_THR;
     }
     if (nt == 6) return LaunchS<6>(prm, spec, conv, st);
     return LaunchS<4>(prm, spec, conv, st);

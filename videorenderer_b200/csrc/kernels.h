@@ -16,6 +16,8 @@ cudaError_t LaunchCopyPass(const SurfDesc& in, const SurfDesc& out, const int32_
                            int dst_x0, int dst_y0, int dst_w, int dst_h, cudaStream_t st);
 // FinalPass (:3189-3233): ordered dither + quantise inside rect.
 cudaError_t LaunchFinalPass(const SurfDesc& in, const SurfDesc& out, int x0, int y0, int x1, int y1, float Q, cudaStream_t st);
+long long VerifyGammaTable(cudaStream_t st);   // mismatches of table vs direct over every float of [0,1]; -1 = table unusable
+void SetGammaTableEnabled(int on);   // debug: 0 = the 2x PQ kernel evaluates the final pow directly instead of the threshold table
 cudaError_t LaunchTonemapPass(const SurfDesc& in, const SurfDesc& out, const ColorParams& P, const TonemapParams& T,
                               int x0, int y0, int x1, int y1, cudaStream_t st);      // ps_hdr10_tonemap post-scale step
 cudaError_t LaunchClear(const SurfDesc& s, cudaStream_t st);

@@ -119,6 +119,7 @@ public:
 
     // debug hooks (include/mpcvr_b200_debug.h)
     int32_t DebugSetPath(int path);
+    int64_t DebugVerifyGammaTable() { if (m_device < 0) return -2; cudaSetDevice(m_device); return VerifyGammaTable(m_stream); }
     int32_t DebugGetPlan(mpcvr_plan_info* info);
     int32_t DebugGetColorParams(float m9[9], float c3[3], float g9[9], float* lum);
     int32_t DebugAxisTaps(int axis, int i, int32_t* base, float* w, int maxw, float* wsum);

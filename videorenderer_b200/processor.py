@@ -212,6 +212,12 @@ class VideoProcessor:
         n = C.c_int32(); self._L.mpcvr_get_last_frame_kernels(self._h, C.byref(n)); return n.value
 
     # -- debug hooks
+    def debug_verify_gamma_table(self):
+        return int(self._L.mpcvr_debug_verify_gamma_table(self._h))
+
+    def debug_set_gamma_table(self, enable):
+        return self._L.mpcvr_debug_set_gamma_table(int(bool(enable)))
+
     def debug_set_path(self, path):
         return self._check(self._L.mpcvr_debug_set_path(self._h, path), "debug_set_path")
 
