@@ -311,6 +311,17 @@ def main():
             roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         except Exception:
             pass
+    # The kernel keeps the reference's fp32 arithmetic exact, which makes it instruction-issue bound rather than HBM bound.
+    # That ceiling is reported next to the contract's HBM roofline: warp instructions per launch from the committed ncu
+    # capture (smsp__inst_executed.sum) against 4 warp instructions / clk / SM at the SM clock sampled during this run.
+    if plan.path == V.PATH.FUSED:
+        WARP_INSTR = 152_621_688                         # profiles/r01f_fused_c2_gamma_table.md
+        sm_hz = float(clocks.get("sm_mhz") or 1965.0) * 1e6
+        issue_peak = 148 * 4 * sm_hz                    # warp instructions / s
+        roof["issue"] = {"bound": "instruction issue", "warp_instr_per_launch": WARP_INSTR, "achieved": WARP_INSTR / (kernel_ms * 1e-3) / 1e9,
+                         "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": WARP_INSTR / (kernel_ms * 1e-3) / issue_peak,
+                         "source": "profiles/r01f_fused_c2_gamma_table.md"}
+    e2e_d2h_gbs = OUT_BYTES * e2e_fps / world / 1e9     # per GPU; the D2H of the 8K frame is the e2e bottleneck (PCIe)
 
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -321,7 +332,9 @@ def main():
                        "parity": "bit-exact vs oracle SPEC mode (tests -m gpu)"},
             "clocks": clocks,
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": IN_BYTES, "d2h_bytes_per_step": OUT_BYTES,
-                    "note": "pinned host frame -> mpcvr_process_sample (H2D inside) -> mpcvr_read_backbuffer_async (D2H of the full 7680x4320 BGRA8 frame into pinned memory); two instances/streams alternate so copies overlap kernels"},
+                    "note": "pinned host frame -> mpcvr_process_sample (H2D inside) -> mpcvr_read_backbuffer_async (D2H of the full 7680x4320 BGRA8 frame into pinned memory); two instances/streams alternate so copies overlap kernels",
+                    "d2h_gbs_per_gpu": e2e_d2h_gbs, "h2d_gbs_per_gpu": IN_BYTES * e2e_fps / world / 1e9,
+                    "bound": "PCIe device-to-host copy of the 133 MB output frame"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof}
 
