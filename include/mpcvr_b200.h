@@ -199,8 +199,8 @@ void    mpcvr_get_source_rect(mpcvr* vp, mpcvr_rect* r);
 void    mpcvr_get_video_rect(mpcvr* vp, mpcvr_rect* r);
 void    mpcvr_set_video_rect(mpcvr* vp, const mpcvr_rect* r);
 int32_t mpcvr_set_window_rect(mpcvr* vp, const mpcvr_rect* r);
-int32_t mpcvr_set_rotation(mpcvr* vp, int32_t degrees);       /* 0 accepted; 90/180/270 -> E_NOTIMPL */
-int32_t mpcvr_set_flip(mpcvr* vp, int32_t flip);              /* 0 accepted; 1 -> E_NOTIMPL */
+int32_t mpcvr_set_rotation(mpcvr* vp, int32_t degrees);       /* 0 / 90 / 180 / 270 clockwise (Source/DX11VideoProcessor.cpp:4052-4058); else E_INVALIDARG */
+int32_t mpcvr_set_flip(mpcvr* vp, int32_t flip);              /* horizontal flip of the source (Source/VideoProcessor.h:210) */
 /* m_bHdrPassthroughSupport (Source/DX11VideoProcessor.cpp:1476): the reference reads it from the DXGI output; here the
  * caller states whether the presentation target is an HDR10 (PQ / BT.2020) display.  With it set, bHdrPassthrough /
  * bHdrLocalToneMapping pick SHADER_CONVERT_NONE / _TO_PQ (:2948-2950) and the ps_hdr10_tonemap post-scale step

@@ -95,6 +95,8 @@ typedef struct orc_config {
     int32_t  hdr_out, tonemap;
     float    tm_min_nits, tm_max_nits, tm_max_cll, tm_max_fall, tm_display_nits;
     int32_t  tm_type;
+    /* SetRotation / SetFlip (Source/VideoProcessor.h:205-210): 0/90/180/270 clockwise, horizontal flip of the source */
+    int32_t  rotation, flip;
 } orc_config;
 
 /* optional taps into the pass chain for stage-wise parity tests */

@@ -199,7 +199,7 @@ class Case:
     def __init__(self, cf, w, h, dst_w, dst_h, ex, backbuffer=O.SURF_BGRA8, tex=O.TEXFMT_AUTOINT, chroma=O.CHROMA_Bilinear,
                  up=O.UPSCALE["CatmullRom"], down=O.DOWNSCALE["Hamming"], interp50=1, dither=1, to_sdr=1, nits=125,
                  src_rect=None, dst_rect=None, win=None, variant=O.VARIANT_D3D11, procamp=None, interlaced=0, deint_blend=0,
-                 name=None, bottom_up=0, hdr=None):
+                 name=None, bottom_up=0, hdr=None, rotation=0, flip=0):
         self.__dict__.update(locals()); del self.__dict__["self"]
         self.name = name or "case"
 
@@ -210,7 +210,7 @@ class Case:
                              up=self.up, down=self.down, interp50=self.interp50, dither=self.dither, to_sdr=self.to_sdr,
                              nits=self.nits, deint_blend=int(bool(self.deint_blend and self.interlaced)),
                              brightness=pa.get("brightness", 0.0), contrast=pa.get("contrast", 1.0), hue=pa.get("hue", 0.0),
-                             saturation=pa.get("saturation", 1.0), variant=self.variant, hdr=self.hdr)
+                             saturation=pa.get("saturation", 1.0), variant=self.variant, hdr=self.hdr, rotation=self.rotation, flip=self.flip)
 
     def settings(self):
         import videorenderer_b200 as V
@@ -237,6 +237,8 @@ class Case:
         vp.SetBackbufferFormat(self.backbuffer)
         vp.SetWindowRect((0, 0, win[0], win[1]))
         vp.SetVideoRect(self.dst_rect or (0, 0, self.dst_w, self.dst_h))
+        if self.rotation or self.flip:
+            assert vp.SetRotation(self.rotation) == 0 and vp.SetFlip(self.flip) == 0
         if path is not None:
             vp.debug_set_path(path)
         return vp

@@ -476,3 +476,43 @@ def test_gamma_threshold_table_on_off_same_frame():
     assert np.array_equal(outs[0], outs[1])
     ref = H.run_oracle(case, planes, pitches)
     assert H.compare(outs[0], ref, case.backbuffer) == (0, 0)
+
+
+# ---- SetRotation / SetFlip (FillVertices, Source/DX11VideoProcessor.cpp:130-179; ResizeShaderPass :3106-3186) ----
+def _rot_case(rot, flip, sw, sh, dw, dh, **kw):
+    """dw x dh is the upright target size; a quarter turn presents it as dh x dw"""
+    if rot in (90, 270):
+        dw, dh = dh, dw
+    return H.Case(O.CF["NV12"], sw, sh, dw, dh, H.EX_709, rotation=rot, flip=flip, name="rot%d_f%d" % (rot, flip), **kw)
+
+
+@pytest.mark.parametrize("rot", [0, 90, 180, 270])
+@pytest.mark.parametrize("flip", [0, 1])
+def test_rotation_flip_copy_and_upscale(rot, flip):
+    if rot == 0 and not flip:
+        pytest.skip("covered everywhere else")
+    _check(_rot_case(rot, flip, 64, 36, 64, 36, up=O.UPSCALE["Nearest"]), "fullnoise", 41)                     # ps_simple copy
+    _check(_rot_case(rot, flip, 64, 36, 96, 54, up=O.UPSCALE["Lanczos3"]), "natural", 42)                       # both up: quarter turns filter one direction only
+    _check(_rot_case(rot, flip, 64, 36, 96, 36, up=O.UPSCALE["CatmullRom"]), "natural", 43)                     # one direction scaled
+    _check(_rot_case(rot, flip, 64, 36, 64, 54, up=O.UPSCALE["Mitchell"]), "natural", 44)
+
+
+@pytest.mark.parametrize("rot", [90, 180, 270])
+def test_rotation_downscale_mixed_and_final_pass(rot):
+    _check(_rot_case(rot, 0, 160, 90, 50, 31, down=O.DOWNSCALE["Hamming"]), "natural", 45)                       # both down (conv scale-constant quirk on quarter turns)
+    _check(_rot_case(rot, 1, 160, 90, 200, 31, down=O.DOWNSCALE["Bicubic"], up=O.UPSCALE["Lanczos2"]), "natural", 46)   # up one way, down the other: two passes
+    c = _rot_case(rot, 0, 64, 36, 96, 54, up=O.UPSCALE["Lanczos3"], tex=O.TEXFMT_16FLOAT)                     # final pass after the turned draw
+    _check(c, "natural", 47)
+    _check(_rot_case(rot, 1, 64, 36, 80, 60, up=O.UPSCALE["CatmullRom"], dst_rect=None, src_rect=(8, 4, 56, 32)), "fullnoise", 48)
+
+
+def test_flip_alone_is_lost_when_final_pass_reads_the_convert_output():
+    """rSrc == dstRect, a final pass and no rotation: 'pTex = pInputTexture' (:3350-3352) skips the only draw that would flip"""
+    a = H.Case(O.CF["P010"], 64, 36, 64, 36, H.EX_709, up=O.UPSCALE["Nearest"], flip=1, name="flip_lost")
+    _check(a, "fullnoise", 49)
+    assert a.orc_config().flip == 1
+
+
+def test_rotation_reports_turned_video_size():
+    vp = _rot_case(90, 0, 64, 36, 36, 64).make_processor(device=0)
+    assert vp.GetVideoSize() == (36, 64)

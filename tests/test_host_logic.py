@@ -161,8 +161,8 @@ def test_no_cpu_fallback_and_error_convention():
     hr = vp.ProcessSample(data=np.zeros(64 * 96, np.uint8), check=False)
     assert hr == V.HRESULT.E_UNEXPECTED and "no CPU path" in vp.last_error()
     assert vp._L.mpcvr_render(vp._h, 1, 0) == V.HRESULT.E_UNEXPECTED
-    assert vp.SetRotation(0) == 0 and vp.SetRotation(90) == V.HRESULT.E_NOTIMPL
-    assert vp.SetFlip(False) == 0 and vp.SetFlip(True) == V.HRESULT.E_NOTIMPL
+    assert vp.SetRotation(90) == 0 and vp.GetVideoSize() == (64, 64) and vp.SetRotation(45) == V.HRESULT.E_INVALIDARG
+    assert vp.SetRotation(0) == 0 and vp.SetFlip(True) == 0 and vp.SetFlip(False) == 0
     assert vp._L.mpcvr_process_sample(None, None) == V.HRESULT.E_POINTER
     with pytest.raises(V.MpcvrError):
         V.VideoProcessor(device=12345)

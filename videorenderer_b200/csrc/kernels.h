@@ -8,12 +8,13 @@ namespace b200vr {
 // ---- multipass family: one kernel per reference pass (Process, Source/DX11VideoProcessor.cpp:3285-3424)
 // ConvertColorPass (:3048-3101). dbg_f32 (optional): float4 per pixel, shader output before the RT write.
 cudaError_t LaunchConvertPass(const SrcDesc& src, const ColorParams& color, const SurfDesc& out, float4* dbg_f32, cudaStream_t st);
-// TextureResizeShader (:332-377) along `axis` (0 = X, 1 = Y); `other` maps the other axis (point sample).
+// TextureResizeShader (:332-377): output axis `axis` (0 = X, 1 = Y) is filtered along texture axis `in_axis` (default: the same;
+// differs on quads turned by 90/270 degrees); `other` maps the other output axis to the other texture axis (point sample).
 cudaError_t LaunchResizePass(const SurfDesc& in, const SurfDesc& out, const AxisTable& table, int axis,
-                             const int32_t* other_idx, int other_dst0, int other_dst_len, cudaStream_t st);
+                             const int32_t* other_idx, int other_dst0, int other_dst_len, cudaStream_t st, int in_axis = -1);
 // TextureCopyRect with ps_simple (:300-330, :3178-3181): point-sampled copy / stretch.
 cudaError_t LaunchCopyPass(const SurfDesc& in, const SurfDesc& out, const int32_t* idx_x, const int32_t* idx_y,
-                           int dst_x0, int dst_y0, int dst_w, int dst_h, cudaStream_t st);
+                           int dst_x0, int dst_y0, int dst_w, int dst_h, cudaStream_t st, int transpose = 0);
 // FinalPass (:3189-3233): ordered dither + quantise inside rect.
 cudaError_t LaunchFinalPass(const SurfDesc& in, const SurfDesc& out, int x0, int y0, int x1, int y1, float Q, cudaStream_t st);
 long long VerifyGammaTable(cudaStream_t st);   // mismatches of table vs direct over every float of [0,1]; -1 = table unusable

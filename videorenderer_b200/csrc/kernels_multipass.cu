@@ -32,7 +32,7 @@ k_convert(const __grid_constant__ SrcDesc S, const __grid_constant__ ColorParams
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_resize(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc out, const __grid_constant__ AxisTable T,
-         const int axis, const int32_t* __restrict__ other_idx, const int other_dst0, const int other_dst_len)
+         const int axis, const int32_t* __restrict__ other_idx, const int other_dst0, const int other_dst_len, const int in_axis)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y * blockDim.y + threadIdx.y;
     // (a, b) index the output rectangle: a along X, b along Y
@@ -42,8 +42,9 @@ k_resize(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc o
     const int ox = axis == 0 ? T.dst0 + i : other_dst0 + j;
     const int oy = axis == 0 ? other_dst0 + j : T.dst0 + i;
     if (ox < 0 || oy < 0 || ox >= out.w || oy >= out.h) return;
-    const int lim   = axis == 0 ? in.w : in.h;
-    const int fixed = clampi(__ldg(other_idx + j), 0, (axis == 0 ? in.h : in.w) - 1);
+    // in_axis: the texture axis the taps run along; differs from the output axis on a quad turned by 90/270 degrees
+    const int lim   = in_axis == 0 ? in.w : in.h;
+    const int fixed = clampi(__ldg(other_idx + j), 0, (in_axis == 0 ? in.h : in.w) - 1);
     const int base  = __ldg(T.base + i);
     const float* w  = T.w + (size_t)i * T.ntaps;
     f3 acc = {0.f, 0.f, 0.f};
@@ -51,7 +52,7 @@ k_resize(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc o
         int idx = base + k;
         if (T.dup_q1 && k == 1) idx = base;                 // ps_interpolation_lanczos3.hlsl:33-34
         idx = clampi(idx, 0, lim - 1);
-        const f3 p = axis == 0 ? surf_load(in, idx, fixed) : surf_load(in, fixed, idx);
+        const f3 p = in_axis == 0 ? surf_load(in, idx, fixed) : surf_load(in, fixed, idx);
         const float wk = __ldg(w + k);
         if (k == 0 && T.kind != SCALER_CONV) { acc.x = __fmul_rn(wk, p.x); acc.y = __fmul_rn(wk, p.y); acc.z = __fmul_rn(wk, p.z); }
         else { acc.x = fma_rn(wk, p.x, acc.x); acc.y = fma_rn(wk, p.y, acc.y); acc.z = fma_rn(wk, p.z, acc.z); }
@@ -68,13 +69,14 @@ k_resize(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc o
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_copy(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc out,
-       const int32_t* __restrict__ idx_x, const int32_t* __restrict__ idx_y, int dx0, int dy0, int dw, int dh)
+       const int32_t* __restrict__ idx_x, const int32_t* __restrict__ idx_y, int dx0, int dy0, int dw, int dh, int transpose)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dw || y >= dh) return;
     const int ox = dx0 + x, oy = dy0 + y;
     if (ox < 0 || oy < 0 || ox >= out.w || oy >= out.h) return;
-    const int ix = clampi(__ldg(idx_x + x), 0, in.w - 1), iy = clampi(__ldg(idx_y + y), 0, in.h - 1);
+    // transpose (quarter turns): the source column follows the output row and vice versa
+    const int ix = clampi(__ldg(idx_x + (transpose ? y : x)), 0, in.w - 1), iy = clampi(__ldg(idx_y + (transpose ? x : y)), 0, in.h - 1);
     surf_store(out, ox, oy, surf_load(in, ix, iy));
 }
 
@@ -261,19 +263,19 @@ cudaError_t LaunchConvertPass(const SrcDesc& src, const ColorParams& color, cons
 }
 
 cudaError_t LaunchResizePass(const SurfDesc& in, const SurfDesc& out, const AxisTable& table, int axis,
-                             const int32_t* other_idx, int other_dst0, int other_dst_len, cudaStream_t st)
+                             const int32_t* other_idx, int other_dst0, int other_dst_len, cudaStream_t st, int in_axis)
 {
     const dim3 b(32, 8);
     const int w = axis == 0 ? table.dst_len : other_dst_len, h = axis == 0 ? other_dst_len : table.dst_len;
-    k_resize<<<Grid2D(w, h, b), b, 0, st>>>(in, out, table, axis, other_idx, other_dst0, other_dst_len);
+    k_resize<<<Grid2D(w, h, b), b, 0, st>>>(in, out, table, axis, other_idx, other_dst0, other_dst_len, in_axis < 0 ? axis : in_axis);
     return cudaGetLastError();
 }
 
 cudaError_t LaunchCopyPass(const SurfDesc& in, const SurfDesc& out, const int32_t* idx_x, const int32_t* idx_y,
-                           int dst_x0, int dst_y0, int dst_w, int dst_h, cudaStream_t st)
+                           int dst_x0, int dst_y0, int dst_w, int dst_h, cudaStream_t st, int transpose)
 {
     const dim3 b(32, 8);
-    k_copy<<<Grid2D(dst_w, dst_h, b), b, 0, st>>>(in, out, idx_x, idx_y, dst_x0, dst_y0, dst_w, dst_h);
+    k_copy<<<Grid2D(dst_w, dst_h, b), b, 0, st>>>(in, out, idx_x, idx_y, dst_x0, dst_y0, dst_w, dst_h, transpose);
     return cudaGetLastError();
 }
 

@@ -105,7 +105,8 @@ float ConvSupport(int filter)
 
 }  // namespace
 
-bool BuildAxisTable(int kind, int filter, bool d3d9_variant, int src0, int src_len, int dst0, int dst_len, HostAxisTable& T)
+bool BuildAxisTable(int kind, int filter, bool d3d9_variant, int src0, int src_len, int dst0, int dst_len, HostAxisTable& T,
+                    bool reverse, float qscale)
 {
     T = HostAxisTable();
     T.kind = kind; T.filter = filter; T.src0 = src0; T.src_len = src_len; T.dst0 = dst0; T.dst_len = dst_len;
@@ -113,11 +114,13 @@ bool BuildAxisTable(int kind, int filter, bool d3d9_variant, int src0, int src_l
     // constants of TextureResizeShader, Source/DX11VideoProcessor.cpp:351-354: scale = (float)src/dst
     const float scale = (float)src_len / (float)dst_len;
     T.base.resize(dst_len);
+    const float far_edge = (float)(src0 + src_len);
+    auto coord = [&](int i) { return reverse ? far_edge - ((float)i + 0.5f) * scale : ((float)i + 0.5f) * scale + (float)src0; };
 
     if (kind == SCALER_NONE || kind == SCALER_NEAREST) {
         // point sample of the interpolated coordinate: texel floor(src0 + (i+.5)*scale)
         T.ntaps = 1; T.w.assign(dst_len, 1.f);
-        for (int i = 0; i < dst_len; i++) T.base[i] = (int)floorf(((float)i + 0.5f) * scale + (float)src0);
+        for (int i = 0; i < dst_len; i++) T.base[i] = (int)floorf(coord(i));
         return true;
     }
     if (kind == SCALER_INTERP) {
@@ -130,7 +133,7 @@ bool BuildAxisTable(int kind, int filter, bool d3d9_variant, int src0, int src_l
         T.ntaps = nt; T.w.resize((size_t)dst_len * nt);
         T.dup_q1 = (filter == MPCVR_UPSCALE_Lanczos3) && !d3d9_variant;
         for (int i = 0; i < dst_len; i++) {
-            const float c = ((float)i + 0.5f) * scale + (float)src0;   // interpolated Tex*wh
+            const float c = coord(i);                                  // interpolated Tex*wh
             const float pos = c - 0.5f;
             const float fl = floorf(pos);
             const float t = pos - fl;
@@ -144,12 +147,13 @@ bool BuildAxisTable(int kind, int filter, bool d3d9_variant, int src0, int src_l
         return true;
     }
     // convolution: Shaders/d3d11/ps_convolution.hlsl:23-49 (pos = Tex*wh + 0.5), D3D9 twin convolution.hlsl:17 (pos = c)
-    const float support = ConvSupport(filter) * scale;
-    const float ss = 1.0f / scale;
+    const float cscale = qscale > 0.0f ? qscale : scale;            // the shader's `scale` constant
+    const float support = ConvSupport(filter) * cscale;
+    const float ss = 1.0f / cscale;
     std::vector<int> lows(dst_len), counts(dst_len);
     int nt = 1;
     for (int i = 0; i < dst_len; i++) {
-        const float c = ((float)i + 0.5f) * scale + (float)src0;
+        const float c = coord(i);
         const float pos = d3d9_variant ? c : c + 0.5f;
         lows[i] = (int)floorf(pos - support);
         counts[i] = (int)ceilf(pos + support) - lows[i];
@@ -158,7 +162,7 @@ bool BuildAxisTable(int kind, int filter, bool d3d9_variant, int src0, int src_l
     if (nt > 256) return false;
     T.ntaps = nt; T.w.assign((size_t)dst_len * nt, 0.f); T.wsum.resize(dst_len);
     for (int i = 0; i < dst_len; i++) {
-        const float c = ((float)i + 0.5f) * scale + (float)src0;
+        const float c = coord(i);
         const float pos = d3d9_variant ? c : c + 0.5f;
         float ww = 0.f;
         for (int k = 0; k < counts[i]; k++) {

@@ -26,6 +26,11 @@ struct HostAxisTable {
 int ChooseScaler(int src_len, int dst_len, bool interpolateAt50pct);
 
 // d3d9_variant: restate the Shaders/d3d9 twins instead
-bool BuildAxisTable(int kind, int filter, bool d3d9_variant, int src0, int src_len, int dst0, int dst_len, HostAxisTable& out);
+// reverse: the interpolated coordinate runs from the far edge down (rotated / flipped quads, FillVertices :130-179):
+//          c = (src0 + src_len) - (i + .5) * scale.
+// qscale : the `scale` constant the convolution shader is handed (TextureResizeShader :351-354 divides same-named axes of
+//          srcRect and dstRect, which is not the geometric ratio once the quad is turned by 90 degrees); <= 0: geometric.
+bool BuildAxisTable(int kind, int filter, bool d3d9_variant, int src0, int src_len, int dst0, int dst_len, HostAxisTable& out,
+                    bool reverse = false, float qscale = 0.0f);
 
 }  // namespace b200vr

@@ -60,7 +60,7 @@ CB200VideoProcessor::~CB200VideoProcessor()
         for (auto& t : m_TexSrcVideo) t.Release();
         m_TexConvertOutput.Release(); m_TexSrcUnpacked.Release(); m_TexResize.Release(); m_TexsPostScale.Release(); m_TexsPostScale2.Release(); m_BackBuffer.Release(); m_TexImage.Release();
         m_dbgConvertF32.Release();
-        m_axisX.Release(); m_axisY.Release(); m_pointX.Release(); m_pointY.Release(); m_pointRX.Release(); m_pointRY.Release();
+        m_axisX.Release(); m_axisY.Release(); m_pointX.Release(); m_pointY.Release(); m_pointRX.Release(); m_pointRY.Release(); m_oFilt.Release(); m_oU.Release(); m_oV.Release();
         if (m_ownStream && m_stream) cudaStreamDestroy(m_stream);
     }
 }
@@ -348,13 +348,14 @@ int32_t CB200VideoProcessor::SetWindowRect(const CRect& r)
 
 int32_t CB200VideoProcessor::SetRotation(int v)
 {
-    if (v == 0) { m_iRotation = 0; return MPCVR_S_OK; }
-    return Fail(MPCVR_E_NOTIMPL, "rotation is not implemented on this path (SURVEY 8f-4)");
+    if (v != 0 && v != 90 && v != 180 && v != 270) return Fail(MPCVR_E_INVALIDARG, "rotation must be 0, 90, 180 or 270");
+    m_iRotation = v; m_planDirty = true;                                    // Source/DX11VideoProcessor.cpp:4052-4058
+    return MPCVR_S_OK;
 }
 int32_t CB200VideoProcessor::SetFlip(bool v)
 {
-    if (!v) { m_bFlip = false; return MPCVR_S_OK; }
-    return Fail(MPCVR_E_NOTIMPL, "flip is not implemented on this path (SURVEY 8f-4)");
+    m_bFlip = v; m_planDirty = true;                                        // Source/VideoProcessor.h:210
+    return MPCVR_S_OK;
 }
 
 int32_t CB200VideoProcessor::SetDisplayHdr(bool supported)
@@ -404,11 +405,13 @@ void CB200VideoProcessor::UpdateHdrState()
 
 void CB200VideoProcessor::GetVideoSize(int32_t& w, int32_t& h) const
 {
-    w = m_srcRectWidth; h = m_srcRectHeight;                                // CVideoProcessor::GetVideoSize, Source/VideoProcessor.cpp
+    const bool q = (m_iRotation == 90 || m_iRotation == 270);               // CVideoProcessor::GetVideoSize, Source/VideoProcessor.cpp:30-39
+    w = q ? m_srcRectHeight : m_srcRectWidth; h = q ? m_srcRectWidth : m_srcRectHeight;
 }
 void CB200VideoProcessor::GetAspectRatio(int32_t& ax, int32_t& ay) const
 {
-    ax = m_srcAspectRatioX; ay = m_srcAspectRatioY;
+    const bool q = (m_iRotation == 90 || m_iRotation == 270);               // Source/VideoProcessor.cpp:41-50
+    ax = q ? m_srcAspectRatioY : m_srcAspectRatioX; ay = q ? m_srcAspectRatioX : m_srcAspectRatioY;
 }
 
 void CB200VideoProcessor::Configure(const mpcvr_settings& s)
@@ -639,7 +642,10 @@ int32_t CB200VideoProcessor::UpdatePlan()
     // texture itself and rSrc stays m_srcRect (:3320-3322)
     const CRect rSrc = m_PSConvColorData.enable ? CRect(0, 0, (int)m_srcRectWidth, (int)m_srcRectHeight) : m_srcRect;
     const CRect& dst = m_videoRect;
-    const int w1 = rSrc.Width(), h1 = rSrc.Height(), w2 = dst.Width(), h2 = dst.Height();
+    const int rot = m_iRotation; const bool rotated = (rot == 90 || rot == 270);
+    m_oriented = (rot != 0 || m_bFlip);
+    // ResizeShaderPass, :3106-3127: a quarter turn swaps the source dimensions the scaler choice looks at
+    const int w1 = rotated ? rSrc.Height() : rSrc.Width(), h1 = rotated ? rSrc.Width() : rSrc.Height(), w2 = dst.Width(), h2 = dst.Height();
     int kx = ChooseScaler(w1, w2, m_bInterpolateAt50pct), ky = ChooseScaler(h1, h2, m_bInterpolateAt50pct);
     // UPSCALE_Nearest has no shader (m_pShaderUpscaleX == nullptr, :94-95, :2919): that axis is point sampled
     if (kx == SCALER_INTERP && m_iUpscaling == MPCVR_UPSCALE_Nearest) kx = SCALER_NEAREST;
@@ -656,6 +662,40 @@ int32_t CB200VideoProcessor::UpdatePlan()
     // two-pass: X pass keeps rows (h1 -> h1), Y pass keeps columns (w2 -> w2)
     BuildAxisTable(SCALER_NEAREST, 0, d3d9, rSrc.top, h1, 0, h1, m_pointRY.host);
     BuildAxisTable(SCALER_NEAREST, 0, d3d9, dst.left, w2, dst.left, w2, m_pointRX.host);
+    m_oInAxis = -1; m_oOutAxis = 0; m_oTwoPass = false;
+    if (m_oriented) {
+        // The first draw of the source carries the orientation (:3137-3181).  Output pixel (x, y) samples the texture at
+        //   rot 0: u<-x, v<-y   rot 90: u<-y, v<-x reversed   rot 180: both reversed   rot 270: u<-y reversed, v<-x;  flip inverts u.
+        // For a quarter turn the X-direction resizer is the Y shader (:3111-3119); when both directions pick the same shader
+        // object (both up or both down) the reference takes its "one pass resize" branch (:3135-3141): one direction is
+        // filtered, the other merely point sampled.  Kept as is.
+        const bool shaderX = (kx == SCALER_INTERP || kx == SCALER_CONV), shaderY = (ky == SCALER_INTERP || ky == SCALER_CONV);
+        const bool sameShader = rotated && shaderX && shaderY && kx == ky;
+        m_oTwoPass = shaderX && shaderY && !sameShader;
+        const int ow = w2, oh = m_oTwoPass ? h1 : h2;                      // first-draw target: m_TexResize rows when two passes follow
+        const int oy0 = m_oTwoPass ? 0 : dst.top;
+        const bool uFromX = !rotated;
+        const int uLen = uFromX ? ow : oh, vLen = uFromX ? oh : ow;
+        const bool uRev = ((rot == 180 || rot == 270) != m_bFlip), vRev = (rot == 90 || rot == 180);
+        BuildAxisTable(SCALER_NEAREST, 0, d3d9, rSrc.left, rSrc.Width(), uFromX ? dst.left : oy0, uLen, m_oU.host, uRev);
+        BuildAxisTable(SCALER_NEAREST, 0, d3d9, rSrc.top, rSrc.Height(), uFromX ? oy0 : dst.left, vLen, m_oV.host, vRev);
+        int kind = SCALER_NONE, filt = 0;
+        if (shaderX)      { m_oInAxis = rotated ? 1 : 0; m_oOutAxis = 0; kind = kx; filt = fx; }
+        else if (shaderY) { m_oInAxis = rotated ? 0 : 1; m_oOutAxis = 1; kind = ky; filt = fy; }
+        if (m_oInAxis >= 0) {
+            // shader constant: scale.x = srcRect.W / dstRect.W, scale.y = srcRect.H / dstRect.H (:351-354), turned or not
+            const float qscale = m_oInAxis == 0 ? (float)rSrc.Width() / (float)ow : (float)rSrc.Height() / (float)oh;
+            const bool ok = m_oInAxis == 0
+                ? BuildAxisTable(kind, filt, d3d9, rSrc.left, rSrc.Width(), m_oOutAxis == 0 ? dst.left : oy0, uLen, m_oFilt.host, uRev, qscale)
+                : BuildAxisTable(kind, filt, d3d9, rSrc.top, rSrc.Height(), m_oOutAxis == 0 ? dst.left : oy0, vLen, m_oFilt.host, vRev, qscale);
+            if (!ok) return Fail(MPCVR_E_NOTIMPL, "scaler not available for the rotated draw (Jinc2 is a 'next' row)");
+        }
+        if (m_device >= 0) {
+            cudaSetDevice(m_device);
+            if (!Cuda(m_oU.Upload(m_stream), "upload") || !Cuda(m_oV.Upload(m_stream), "upload") ||
+                (m_oInAxis >= 0 && !Cuda(m_oFilt.Upload(m_stream), "upload"))) return MPCVR_E_FAIL;
+        }
+    }
     if (m_device >= 0) {
         cudaSetDevice(m_device);
         if (!Cuda(m_axisX.Upload(m_stream), "upload X table") || !Cuda(m_axisY.Upload(m_stream), "upload Y table") ||
@@ -684,6 +724,29 @@ int32_t CB200VideoProcessor::ResizeShaderPass(const Tex2D& tex, const Tex2D& rt,
     const int kx = m_axisX.host.kind, ky = m_axisY.host.kind;
     const bool shaderX = (kx == SCALER_INTERP || kx == SCALER_CONV), shaderY = (ky == SCALER_INTERP || ky == SCALER_CONV);
     const int h1 = m_axisY.host.src_len;
+    if (m_oriented) {
+        const bool rotated = (m_iRotation == 90 || m_iRotation == 270);
+        const Tex2D* first = &rt;
+        int oy0 = dstRect.top, oh = dstRect.Height();
+        if (m_oTwoPass) {
+            if (!Cuda(m_TexResize.CheckCreate(MPCVR_SURF_RGBA16F, rt.w, h1), "m_TexResize")) return MPCVR_E_FAIL;
+            first = &m_TexResize; oy0 = 0; oh = h1;
+        }
+        m_lastLaunches++;
+        if (m_oInAxis < 0) {
+            if (!Cuda(LaunchCopyPass(tex.desc(), first->desc(), m_oU.base.ptr, m_oV.base.ptr, dstRect.left, oy0, dstRect.Width(), oh, m_stream, rotated ? 1 : 0), "oriented copy")) return MPCVR_E_FAIL;
+        } else {
+            // the other output axis is point sampled along the other texture axis
+            const int32_t* other = (m_oInAxis == 0) ? m_oV.base.ptr : m_oU.base.ptr;
+            const int other0 = m_oOutAxis == 0 ? oy0 : dstRect.left, otherLen = m_oOutAxis == 0 ? oh : dstRect.Width();
+            if (!Cuda(LaunchResizePass(tex.desc(), first->desc(), m_oFilt.table(), m_oOutAxis, other, other0, otherLen, m_stream, m_oInAxis), "oriented resize")) return MPCVR_E_FAIL;
+        }
+        if (m_oTwoPass) {
+            m_lastLaunches++;
+            if (!Cuda(LaunchResizePass(m_TexResize.desc(), rt.desc(), m_axisY.table(), 1, m_pointRX.base.ptr, dstRect.left, dstRect.Width(), m_stream), "resize Y")) return MPCVR_E_FAIL;
+        }
+        return MPCVR_S_OK;
+    }
     if (shaderX && shaderY) {
         // two passes through m_TexResize: RGBA16F, width = render-target width, height = h1 (:3143-3167)
         if (!Cuda(m_TexResize.CheckCreate(MPCVR_SURF_RGBA16F, rt.w, h1), "m_TexResize")) return MPCVR_E_FAIL;
@@ -767,8 +830,8 @@ int32_t CB200VideoProcessor::Process(const Tex2D& target, const CRect& srcRect, 
         if (numSteps > 1 && !Cuda(m_TexsPostScale2.CheckCreate(m_InternalTexFmt, target.w, target.h), "m_TexsPostScale[1]")) return MPCVR_E_FAIL;
         const Tex2D* pTex = &m_TexsPostScale;
         CRect rect; rect.IntersectRect(dstRect, CRect(0, 0, pTex->w, pTex->h));
-        if (rSrc != dstRect) { hr = ResizeShaderPass(*pInputTexture, *pTex, rSrc, dstRect); if (hr != MPCVR_S_OK) return hr; }
-        else pTex = pInputTexture;                                            // "Hmm", :3351
+        if (rSrc != dstRect || m_iRotation != 0) { hr = ResizeShaderPass(*pInputTexture, *pTex, rSrc, dstRect); if (hr != MPCVR_S_OK) return hr; }
+        else pTex = pInputTexture;                                            // "Hmm", :3351 (a flip alone is lost here, as in the reference)
         if (m_bTonemap) {                                                     // StepSetting(); :3359-3367
             const Tex2D& rt = m_bFinalPass ? m_TexsPostScale2 : target;
             hr = TonemapPass(*pTex, rt, rect); if (hr != MPCVR_S_OK) return hr;
@@ -788,6 +851,7 @@ bool CB200VideoProcessor::PlanFused(const Tex2D& target, const CRect& dstRect, F
     memset(&fp, 0, sizeof(fp));
     if (!m_PSConvColorData.enable) { if (why) *why = "no convert pass on this plan (RGB source, default ProcAmp): multipass only"; return false; }
     if (m_bTonemap) { if (why) *why = "HDR10 tone-map post-scale step: multipass only"; return false; }
+    if (m_oriented) { if (why) *why = "rotation / flip: multipass only"; return false; }
     fp.src = m_src; fp.color = m_color;
     fp.ax = m_axisX.table(); fp.ay = m_axisY.table();
     fp.out = target.desc();

@@ -202,6 +202,11 @@ private:
     DeviceAxis m_axisX, m_axisY;                 // filtered axes
     DeviceAxis m_pointX, m_pointY;               // point-sampled index maps (other axis / copies)
     DeviceAxis m_pointRX, m_pointRY;             // second pass maps of the two-pass resize
+    // rotated / flipped first draw (TextureResizeShader / TextureCopyRect with iRotation, bFlip; FillVertices :130-179)
+    bool m_oriented = false;                     // m_iRotation != 0 || m_bFlip
+    DeviceAxis m_oFilt, m_oU, m_oV;              // filtered table of the first draw; point maps output index -> texture x / y
+    int  m_oInAxis = -1, m_oOutAxis = 0;         // texture axis the first draw filters (-1: ps_simple) and the output axis it feeds
+    bool m_oTwoPass = false;
     bool m_planDirty = true;
     int  m_forcePath = MPCVR_PATH_AUTO, m_path = MPCVR_PATH_MULTIPASS;
 
