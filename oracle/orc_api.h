@@ -42,6 +42,7 @@ const uint16_t* orc_dither_thresholds(void);   /* 1024 entries, row-major 32x32 
 
 /* ---- scalar math for tests ---- */
 float  orc_test_lg2(float x);
+float  orc_test_sin(float x);
 float  orc_test_ex2(float x);
 float  orc_test_pow(float x, float y, int mode);
 

@@ -89,6 +89,7 @@ int orc_axis_taps(int kind, int filter, int variant, int src_origin, int src_len
 }
 
 float orc_test_lg2(float x) { return orc_lg2_spec(x); }
+float orc_test_sin(float x) { return orc_sin_spec(x); }
 float orc_test_ex2(float x) { return orc_ex2_spec(x); }
 float orc_test_pow(float x, float y, int mode)
 {

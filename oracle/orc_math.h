@@ -68,6 +68,29 @@ static inline float orc_ex2p_spec(float a, float b)
 
 static inline float orc_ex2_spec(float t) { return orc_ex2p_spec(t, 1.0f); }
 
+/* SIN (contract for the per-pixel sines of the Jinc2 shader; arguments are in [0, 16)):
+ * k = nearest integer to x/pi via the 1.5*2^23 trick, three-term Cody-Waite reduction r = x - k*pi (k*PI_A is exact),
+ * odd Taylor polynomial of degree 11 on [-pi/2, pi/2] evaluated with fused steps, sign from the parity of k.
+ * |error| < 1.5e-7 absolute on the range used. */
+static inline float orc_sin_spec(float x)
+{
+    const float magic = 12582912.0f;
+    const float z = fmaf(x, 0.318309886f, magic);
+    const float kf = z - magic;
+    float r = fmaf(-kf, 3.140625f, x);
+    r = fmaf(-kf, 9.67502593994140625e-4f, r);
+    r = fmaf(-kf, 1.509957990978376e-7f, r);
+    const float r2 = r * r;
+    float p = -2.50521084e-8f;                 /* -1/11! */
+    p = fmaf(p, r2, 2.75573192e-6f);           /*  1/9!  */
+    p = fmaf(p, r2, -1.98412698e-4f);          /* -1/7!  */
+    p = fmaf(p, r2, 8.33333333e-3f);           /*  1/5!  */
+    p = fmaf(p, r2, -1.66666667e-1f);          /* -1/3!  */
+    const float s = fmaf(r * r2, p, r);
+    uint32_t zb; memcpy(&zb, &z, 4);
+    return (zb & 1u) ? -s : s;
+}
+
 /* HLSL pow(x,y) for x >= 0:  exp2(y*log2(x)); pow(0,y>0) = 0 (log2(0) = -inf). */
 static inline float orc_pow_spec(float x, float y)
 {

@@ -96,6 +96,7 @@ def lib():
         L.orc_get_fmt.argtypes = [C.c_int]
         L.orc_dither_thresholds.restype = C.POINTER(C.c_uint16)
         L.orc_test_lg2.restype = C.c_float; L.orc_test_lg2.argtypes = [C.c_float]
+        L.orc_test_sin.restype = C.c_float; L.orc_test_sin.argtypes = [C.c_float]
         L.orc_test_ex2.restype = C.c_float; L.orc_test_ex2.argtypes = [C.c_float]
         L.orc_test_pow.restype = C.c_float; L.orc_test_pow.argtypes = [C.c_float, C.c_float, C.c_int]
         L.orc_axis_taps.restype = C.c_int

@@ -516,3 +516,31 @@ def test_flip_alone_is_lost_when_final_pass_reads_the_convert_output():
 def test_rotation_reports_turned_video_size():
     vp = _rot_case(90, 0, 64, 36, 36, 64).make_processor(device=0)
     assert vp.GetVideoSize() == (36, 64)
+
+
+# ---- UPSCALE_Jinc2, the one-pass 2-D resizer (Shaders/examples/ps_resize_onepass_jinc2.hlsl) ----
+def test_sin_contract_on_device():
+    import videorenderer_b200 as V
+    L = V.lib(); OL = O.lib()
+    rng = np.random.Generator(np.random.PCG64(5))
+    x = np.concatenate([rng.uniform(0, 16, 60000), np.arange(0, 6) * np.pi, [0.0, 1e-6, np.pi / 2, 15.99]]).astype(np.float32)
+    out = np.empty_like(x)
+    assert L.mpcvr_debug_math(0, 6, x.ctypes.data, None, out.ctypes.data, x.size) == 0
+    exp = np.array([OL.orc_test_sin(float(v)) for v in x], np.float32)
+    np.testing.assert_array_equal(out.view(np.uint32), exp.view(np.uint32))
+    assert np.abs(exp.astype(np.float64) - np.sin(x.astype(np.float64))).max() < 2e-7
+
+
+@pytest.mark.parametrize("dst", [(128, 72), (96, 54), (128, 36), (64, 72), (128, 20), (40, 72), (91, 67)])
+@pytest.mark.parametrize("variant", [O.VARIANT_D3D11, O.VARIANT_D3D9])
+def test_jinc2(dst, variant):
+    """both directions up (one draw), one direction only, and up one way / down the other (Jinc2 + convolution through m_TexResize)"""
+    _check(H.Case(O.CF["P010"], 64, 36, dst[0], dst[1], H.EX_709, up=O.UPSCALE["Jinc2"], down=O.DOWNSCALE["Hamming"], variant=variant,
+                  name="jinc2_%dx%d" % dst), "natural", 51)
+
+
+def test_jinc2_rects_and_final_pass():
+    _check(H.Case(O.CF["NV12"], 96, 64, 160, 104, H.EX_709, src_rect=(8, 6, 88, 58), up=O.UPSCALE["Jinc2"], name="jinc2_crop"), "fullnoise", 52)
+    _check(H.Case(O.CF["P010"], 64, 36, 128, 72, H.EX_2020_PQ, dst_rect=(16, 11, 144, 83), win=(160, 100), up=O.UPSCALE["Jinc2"], name="jinc2_letterbox"), "noise", 53)
+    _check(H.Case(O.CF["XRGB32"], 64, 36, 100, 60, 0, src_rect=(4, 2, 60, 34), up=O.UPSCALE["Jinc2"], name="jinc2_rgb_direct"), "natural", 54)
+    _check(H.Case(O.CF["P010"], 64, 36, 96, 54, H.EX_709, tex=O.TEXFMT_16FLOAT, backbuffer=O.SURF_RGB10A2, up=O.UPSCALE["Jinc2"], name="jinc2_16f"), "natural", 55)

@@ -95,6 +95,62 @@ k_final(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc ou
 }
 
 // ---------------------------------------------------------------------------------------------
+// Jinc2 one-pass resizer (UPSCALE_Jinc2), Shaders/examples/ps_resize_onepass_jinc2.hlsl:44-101: a 2-D shader, 4x4 texels
+// around floor(pc - .5) weighted by sin(d wa) sin(d wb) / d^2 of their distance d, normalised, anti-ringing clamp.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_jinc2(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc out,
+        int in_l, int in_t, int in_w, int in_h, int out_l, int out_t, int out_w, int out_h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out_w || y >= out_h) return;
+    const int ox = out_l + x, oy = out_t + y;
+    if (ox < 0 || oy < 0 || ox >= out.w || oy >= out.h) return;
+    const float sx = __fdiv_rn((float)in_w, (float)out_w), sy = __fdiv_rn((float)in_h, (float)out_h);   // :351-354
+    const float pcx = __fadd_rn(__fmul_rn(__fadd_rn((float)x, 0.5f), sx), (float)in_l);
+    const float pcy = __fadd_rn(__fmul_rn(__fadd_rn((float)y, 0.5f), sy), (float)in_t);
+    const float pi = 3.14159265358979323846f;
+    const float wa = __fmul_rn(0.416f, pi), wb = __fmul_rn(0.985f, pi), wab = __fmul_rn(wa, wb);
+    const float tcx = __fadd_rn(floorf(__fsub_rn(pcx, 0.5f)), 0.5f), tcy = __fadd_rn(floorf(__fsub_rn(pcy, 0.5f)), 0.5f);
+    const int ix = (int)floorf(tcx), iy = (int)floorf(tcy);
+    float tot = 0.0f;
+    f3 col = {0.f, 0.f, 0.f};
+    f3 mn = {0.f, 0.f, 0.f}, mx = {0.f, 0.f, 0.f};
+    #pragma unroll
+    for (int n = 0; n < 4; n++) {
+        const float vy = __fsub_rn(__fadd_rn(tcy, (float)(n - 1)), pcy);
+        const int ty = clampi(iy + n - 1, 0, in.h - 1);
+        float w[4]; f3 c[4];
+        #pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const float vx = __fsub_rn(__fadd_rn(tcx, (float)(m - 1)), pcx);
+            const float d = __fsqrt_rn(fma_rn(vy, vy, __fmul_rn(vx, vx)));
+            w[m] = (d == 0.0f) ? wab : __fdiv_rn(__fmul_rn(sin_spec(__fmul_rn(d, wa)), sin_spec(__fmul_rn(d, wb))), __fmul_rn(d, d));
+            c[m] = surf_load(in, clampi(ix + m - 1, 0, in.w - 1), ty);
+        }
+        const float rs = __fadd_rn(__fadd_rn(__fadd_rn(w[0], w[1]), w[2]), w[3]);
+        f3 r;
+        r.x = fma_rn(w[3], c[3].x, fma_rn(w[2], c[2].x, fma_rn(w[1], c[1].x, __fmul_rn(w[0], c[0].x))));
+        r.y = fma_rn(w[3], c[3].y, fma_rn(w[2], c[2].y, fma_rn(w[1], c[1].y, __fmul_rn(w[0], c[0].y))));
+        r.z = fma_rn(w[3], c[3].z, fma_rn(w[2], c[2].z, fma_rn(w[1], c[1].z, __fmul_rn(w[0], c[0].z))));
+        if (n == 0) { tot = rs; col = r; }
+        else { tot = __fadd_rn(tot, rs); col.x = __fadd_rn(col.x, r.x); col.y = __fadd_rn(col.y, r.y); col.z = __fadd_rn(col.z, r.z); }
+        if (n == 1) {                                          // c11, c21
+            mn.x = fminf(c[1].x, c[2].x); mn.y = fminf(c[1].y, c[2].y); mn.z = fminf(c[1].z, c[2].z);
+            mx.x = fmaxf(c[1].x, c[2].x); mx.y = fmaxf(c[1].y, c[2].y); mx.z = fmaxf(c[1].z, c[2].z);
+        } else if (n == 2) {                                   // c12, c22
+            mn.x = fminf(fminf(mn.x, c[1].x), c[2].x); mn.y = fminf(fminf(mn.y, c[1].y), c[2].y); mn.z = fminf(fminf(mn.z, c[1].z), c[2].z);
+            mx.x = fmaxf(fmaxf(mx.x, c[1].x), c[2].x); mx.y = fmaxf(fmaxf(mx.y, c[1].y), c[2].y); mx.z = fmaxf(fmaxf(mx.z, c[1].z), c[2].z);
+        }
+    }
+    f3 o;
+    { const float v = __fdiv_rn(col.x, tot); o.x = fma_rn(0.8f, __fsub_rn(fminf(fmaxf(v, mn.x), mx.x), v), v); }
+    { const float v = __fdiv_rn(col.y, tot); o.y = fma_rn(0.8f, __fsub_rn(fminf(fmaxf(v, mn.y), mx.y), v), v); }
+    { const float v = __fdiv_rn(col.z, tot); o.z = fma_rn(0.8f, __fsub_rn(fminf(fmaxf(v, mn.z), mx.z), v), v); }
+    surf_store(out, ox, oy, o);
+}
+
+// ---------------------------------------------------------------------------------------------
 // HDR10 local tone-map post-scale step: Shaders/d3d11/ps_hdr10_tonemap.hlsl:34-336 without the Dolby Vision trims
 // (L2Enabled = 0), drawn by TextureCopyRect over rect (Source/DX11VideoProcessor.cpp:3359-3367).
 // Same contract as the other passes: written-order fp32, a*b+c fused, runtime quotients IEEE, pow = 2^(y log2 x).
@@ -234,6 +290,7 @@ __global__ void k_math_probe(int op, const float* __restrict__ x, const float* _
     case 3: r = unorm16((uint32_t)a); break;
     case 4: r = unorm10((uint32_t)a); break;
     case 5: r = unorm8((uint32_t)a); break;
+    case 6: r = sin_spec(a); break;
     // two-lane forms (mpcvr_math2.cuh): lane x = this element, lane y = its successor; lane x is returned
     case 10: r = lg2_2(make_float2(a, x[(i + 1) % n])).x; break;
     case 11: r = ex2_2(make_float2(a, x[(i + 1) % n])).x; break;
@@ -284,6 +341,15 @@ cudaError_t LaunchFinalPass(const SurfDesc& in, const SurfDesc& out, int x0, int
     if (x1 <= x0 || y1 <= y0) return cudaSuccess;
     const dim3 b(32, 8);
     k_final<<<Grid2D(x1 - x0, y1 - y0, b), b, 0, st>>>(in, out, x0, y0, x1, y1, Q);
+    return cudaGetLastError();
+}
+
+cudaError_t LaunchJinc2Pass(const SurfDesc& in, const SurfDesc& out, int in_l, int in_t, int in_w, int in_h,
+                            int out_l, int out_t, int out_w, int out_h, cudaStream_t st)
+{
+    if (out_w <= 0 || out_h <= 0) return cudaSuccess;
+    const dim3 b(32, 8);
+    k_jinc2<<<Grid2D(out_w, out_h, b), b, 0, st>>>(in, out, in_l, in_t, in_w, in_h, out_l, out_t, out_w, out_h);
     return cudaGetLastError();
 }
 

@@ -652,10 +652,15 @@ int32_t CB200VideoProcessor::UpdatePlan()
     if (ky == SCALER_INTERP && m_iUpscaling == MPCVR_UPSCALE_Nearest) ky = SCALER_NEAREST;
     const int fx = kx == SCALER_CONV ? m_iDownscaling : m_iUpscaling, fy = ky == SCALER_CONV ? m_iDownscaling : m_iUpscaling;
     const bool d3d9 = !m_bUseD3D11;
-    if (!BuildAxisTable(kx, fx, d3d9, rSrc.left, w1, dst.left, w2, m_axisX.host)) return Fail(MPCVR_E_NOTIMPL, "X scaler not available (Jinc2 is a 'next' row)");
+    // Jinc2 has no per-axis table: it is one 2-D draw (LaunchJinc2Pass); the slot keeps a point map so the bookkeeping stays uniform
+    m_kx = kx; m_ky = ky;
+    m_jincX = (kx == SCALER_INTERP && m_iUpscaling == MPCVR_UPSCALE_Jinc2);
+    m_jincY = (ky == SCALER_INTERP && m_iUpscaling == MPCVR_UPSCALE_Jinc2);
+    if ((m_jincX || m_jincY) && m_oriented) return Fail(MPCVR_E_NOTIMPL, "Jinc2 on a rotated / flipped draw is not implemented");
+    if (!BuildAxisTable(m_jincX ? SCALER_NEAREST : kx, fx, d3d9, rSrc.left, w1, dst.left, w2, m_axisX.host)) return Fail(MPCVR_E_NOTIMPL, "X scaler not available");
     // two shader passes: the Y pass reads m_TexResize, whose rows start at 0 (resize rect (dst.left, 0, dst.right, h1), :3150-3160)
     const bool twoPass = (kx == SCALER_INTERP || kx == SCALER_CONV) && (ky == SCALER_INTERP || ky == SCALER_CONV);
-    if (!BuildAxisTable(ky, fy, d3d9, twoPass ? 0 : rSrc.top, h1, dst.top, h2, m_axisY.host)) return Fail(MPCVR_E_NOTIMPL, "Y scaler not available (Jinc2 is a 'next' row)");
+    if (!BuildAxisTable(m_jincY ? SCALER_NEAREST : ky, fy, d3d9, twoPass ? 0 : rSrc.top, h1, dst.top, h2, m_axisY.host)) return Fail(MPCVR_E_NOTIMPL, "Y scaler not available");
     // point-sampled maps: other axis of a single-axis resize, and plain copies
     BuildAxisTable(SCALER_NEAREST, 0, d3d9, rSrc.left, w1, dst.left, w2, m_pointX.host);
     BuildAxisTable(SCALER_NEAREST, 0, d3d9, rSrc.top, h1, dst.top, h2, m_pointY.host);
@@ -720,10 +725,30 @@ int32_t CB200VideoProcessor::ConvertColorPass(const Tex2D& rt)
 
 int32_t CB200VideoProcessor::ResizeShaderPass(const Tex2D& tex, const Tex2D& rt, const CRect& srcRect, const CRect& dstRect)
 {
-    (void)srcRect;
-    const int kx = m_axisX.host.kind, ky = m_axisY.host.kind;
+    const int kx = m_kx, ky = m_ky;
     const bool shaderX = (kx == SCALER_INTERP || kx == SCALER_CONV), shaderY = (ky == SCALER_INTERP || ky == SCALER_CONV);
     const int h1 = m_axisY.host.src_len;
+    if (m_jincX || m_jincY) {
+        // resizerX == resizerY (or only one of them): one 2-D draw (:3135-3141, :3169-3177); if the other direction shrinks, the
+        // convolution shader takes that pass and m_TexResize sits in between (:3143-3167)
+        if (kx == SCALER_CONV || ky == SCALER_CONV) {
+            if (!Cuda(m_TexResize.CheckCreate(MPCVR_SURF_RGBA16F, rt.w, h1), "m_TexResize")) return MPCVR_E_FAIL;
+            m_lastLaunches += 2;
+            const cudaError_t e1 = m_jincX
+                ? LaunchJinc2Pass(tex.desc(), m_TexResize.desc(), srcRect.left, srcRect.top, srcRect.Width(), srcRect.Height(), dstRect.left, 0, dstRect.Width(), h1, m_stream)
+                : LaunchResizePass(tex.desc(), m_TexResize.desc(), m_axisX.table(), 0, m_pointRY.base.ptr, 0, h1, m_stream);
+            if (!Cuda(e1, "resize X")) return MPCVR_E_FAIL;
+            const cudaError_t e2 = m_jincY
+                ? LaunchJinc2Pass(m_TexResize.desc(), rt.desc(), dstRect.left, 0, dstRect.Width(), h1, dstRect.left, dstRect.top, dstRect.Width(), dstRect.Height(), m_stream)
+                : LaunchResizePass(m_TexResize.desc(), rt.desc(), m_axisY.table(), 1, m_pointRX.base.ptr, dstRect.left, dstRect.Width(), m_stream);
+            if (!Cuda(e2, "resize Y")) return MPCVR_E_FAIL;
+        } else {
+            m_lastLaunches++;
+            if (!Cuda(LaunchJinc2Pass(tex.desc(), rt.desc(), srcRect.left, srcRect.top, srcRect.Width(), srcRect.Height(),
+                                      dstRect.left, dstRect.top, dstRect.Width(), dstRect.Height(), m_stream), "Jinc2")) return MPCVR_E_FAIL;
+        }
+        return MPCVR_S_OK;
+    }
     if (m_oriented) {
         const bool rotated = (m_iRotation == 90 || m_iRotation == 270);
         const Tex2D* first = &rt;
@@ -852,6 +877,7 @@ bool CB200VideoProcessor::PlanFused(const Tex2D& target, const CRect& dstRect, F
     if (!m_PSConvColorData.enable) { if (why) *why = "no convert pass on this plan (RGB source, default ProcAmp): multipass only"; return false; }
     if (m_bTonemap) { if (why) *why = "HDR10 tone-map post-scale step: multipass only"; return false; }
     if (m_oriented) { if (why) *why = "rotation / flip: multipass only"; return false; }
+    if (m_jincX || m_jincY) { if (why) *why = "Jinc2: multipass only"; return false; }
     fp.src = m_src; fp.color = m_color;
     fp.ax = m_axisX.table(); fp.ay = m_axisY.table();
     fp.out = target.desc();
@@ -978,7 +1004,7 @@ int32_t CB200VideoProcessor::DebugGetPlan(mpcvr_plan_info* info)
     if (hr != MPCVR_S_OK) return hr;
     memset(info, 0, sizeof(*info));
     info->internal_fmt = m_InternalTexFmt; info->final_pass = m_bFinalPass;
-    info->scaler_x = m_axisX.host.kind; info->scaler_y = m_axisY.host.kind;
+    info->scaler_x = m_kx; info->scaler_y = m_ky;
     info->filter_x = m_axisX.host.filter; info->filter_y = m_axisY.host.filter;
     info->taps_x = m_axisX.host.ntaps; info->taps_y = m_axisY.host.ntaps;
     info->path = m_path; info->transfer = m_color.transfer; info->src_exfmt = m_srcExFmt.value;

@@ -207,6 +207,9 @@ private:
     DeviceAxis m_oFilt, m_oU, m_oV;              // filtered table of the first draw; point maps output index -> texture x / y
     int  m_oInAxis = -1, m_oOutAxis = 0;         // texture axis the first draw filters (-1: ps_simple) and the output axis it feeds
     bool m_oTwoPass = false;
+    // UPSCALE_Jinc2: m_pShaderUpscaleX/Y are the same one-pass 2-D shader (Source/DX11VideoProcessor.cpp:94-101)
+    bool m_jincX = false, m_jincY = false;
+    int  m_kx = 0, m_ky = 0;                     // scaler kind per direction as ResizeShaderPass picks it (:3106-3127)
     bool m_planDirty = true;
     int  m_forcePath = MPCVR_PATH_AUTO, m_path = MPCVR_PATH_MULTIPASS;
 
