@@ -143,6 +143,27 @@ typedef struct mpcvr_side_data_hdr_cll {      /* MediaSideDataHDRContentLightLev
 } mpcvr_side_data_hdr_cll;
 #pragma pack(pop)
 
+/* Dolby Vision reshaping data of one frame: the fields of MediaSideDataDOVIMetadata (IID_MediaSideDataDOVIMetadataV2,
+ * Include/IMediaSideData.h:166-243) that the convert shader consumes -- Header.coef_log2_denom / bl_bit_depth,
+ * Mapping.curves[3], ColorMetadata.ycc_to_rgb_matrix / ycc_to_rgb_offset / rgb_to_lms_matrix -- in natural (unpacked)
+ * C layout.  The adapter copies them field by field.  Accepted as CheckDoviMetadata does
+ * (Source/VideoProcessor.cpp:273-297): num_pivots in [2, 9], mapping_idc 0 (polynomial) or 1 (MMR). */
+typedef struct mpcvr_dovi_curve {
+    uint8_t  num_pivots;
+    uint16_t pivots[9];
+    uint8_t  mapping_idc[8];
+    uint8_t  poly_order[8];
+    int64_t  poly_coef[8][3];
+    uint8_t  mmr_order[8];
+    int64_t  mmr_constant[8];
+    int64_t  mmr_coef[8][3][7];
+} mpcvr_dovi_curve;
+typedef struct mpcvr_dovi_metadata {
+    uint8_t  coef_log2_denom, bl_bit_depth;
+    mpcvr_dovi_curve curves[3];
+    double   ycc_to_rgb_matrix[9], ycc_to_rgb_offset[3], rgb_to_lms_matrix[9];
+} mpcvr_dovi_metadata;
+
 #define MPCVR_SAMPLE_DEVICE_MEMORY 0x1u  /* planes are CUDA device pointers (IMediaSampleD3D11 analogue)   */
 
 /* What IMediaSample hands to ProcessSample/CopySample (Source/DX11VideoProcessor.cpp:2143-2597).
@@ -160,6 +181,8 @@ typedef struct mpcvr_sample {
     int64_t     rt_start, rt_end; /* REFERENCE_TIME                                                   */
     const mpcvr_side_data_hdr*     hdr;      /* optional IID_MediaSideDataHDR                         */
     const mpcvr_side_data_hdr_cll* hdr_cll;  /* optional IID_MediaSideDataHDRContentLightLevel        */
+    const mpcvr_dovi_metadata*     dovi;     /* optional Dolby Vision reshaping data (YUV types only; used when
+                                                bHdrPreferDoVi or the stream is not tagged PQ/HLG, :2271)        */
 } mpcvr_sample;
 
 /* DXVA2_ProcAmpValues in float (DXVA2FixedToFloat), SetProcAmpValues Source/DX11VideoProcessor.cpp:4506-4537 */

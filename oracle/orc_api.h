@@ -65,6 +65,10 @@ int orc_axis_taps(int kind, int filter, int variant, int src_origin, int src_len
 int orc_process(const orc_config* cfg, const void* const planes[3], const int32_t pitches[3],
                 void* out, int32_t out_pitch, orc_debug* dbg, int mode, int threads);
 
+/* same with the Dolby Vision reshaping data of the frame (NULL = none) */
+int orc_process_dovi(const orc_config* cfg, const void* const planes[3], const int32_t pitches[3],
+                     void* out, int32_t out_pitch, orc_debug* dbg, int mode, int threads, const orc_dovi* dovi);
+
 /* run only the post-convert passes on a given m_TexConvertOutput surface (packed, internal fmt) */
 int orc_process_from_convert(const orc_config* cfg, const void* convert_surf, int32_t pitch,
                              void* out, int32_t out_pitch, orc_debug* dbg, int mode, int threads);

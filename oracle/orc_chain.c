@@ -58,16 +58,22 @@ int orc_scaler_kind(int src, int dst, int bInterpolateAt50pct)
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
 
-int orc_process(const orc_config* cfg, const void* const planes[3], const int32_t pitches[3],
-                void* out, int32_t out_pitch, orc_debug* dbg, int mode, int threads)
+int orc_process_dovi(const orc_config* cfg, const void* const planes[3], const int32_t pitches[3],
+                     void* out, int32_t out_pitch, orc_debug* dbg, int mode, int threads, const orc_dovi* dovi)
 {
     if (threads <= 0) threads = omp_get_max_threads();
     switch (mode) {
-    case ORC_MODE_SPEC:    return process_spec(cfg, planes, pitches, out, out_pitch, dbg, threads);
-    case ORC_MODE_LITERAL: return process_lit(cfg, planes, pitches, out, out_pitch, dbg, threads);
-    case ORC_MODE_F64:     return process_f64(cfg, planes, pitches, out, out_pitch, dbg, threads);
+    case ORC_MODE_SPEC:    return process_spec(cfg, planes, pitches, out, out_pitch, dbg, threads, dovi);
+    case ORC_MODE_LITERAL: return process_lit(cfg, planes, pitches, out, out_pitch, dbg, threads, dovi);
+    case ORC_MODE_F64:     return process_f64(cfg, planes, pitches, out, out_pitch, dbg, threads, dovi);
     }
     return -100;
+}
+
+int orc_process(const orc_config* cfg, const void* const planes[3], const int32_t pitches[3],
+                void* out, int32_t out_pitch, orc_debug* dbg, int mode, int threads)
+{
+    return orc_process_dovi(cfg, planes, pitches, out, out_pitch, dbg, mode, threads, NULL);
 }
 
 int orc_process_from_convert(const orc_config* cfg, const void* convert_surf, int32_t pitch,

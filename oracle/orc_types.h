@@ -99,6 +99,24 @@ typedef struct orc_config {
     int32_t  rotation, flip;
 } orc_config;
 
+/* Dolby Vision reshaping data of one frame: the fields of MediaSideDataDOVIMetadata (Include/IMediaSideData.h:166-243)
+ * that the convert shader consumes (Source/Shaders.cpp:531-589, :703-859; Source/DX11VideoProcessor.cpp:817-834, :990-1141). */
+typedef struct orc_dovi_curve {
+    uint8_t  num_pivots;                 /* [2, 9] */
+    uint16_t pivots[9];
+    uint8_t  mapping_idc[8];             /* 0 polynomial, 1 mmr */
+    uint8_t  poly_order[8];
+    int64_t  poly_coef[8][3];
+    uint8_t  mmr_order[8];               /* [1, 3] */
+    int64_t  mmr_constant[8];
+    int64_t  mmr_coef[8][3][7];
+} orc_dovi_curve;
+typedef struct orc_dovi {
+    uint8_t  coef_log2_denom, bl_bit_depth;
+    orc_dovi_curve curves[3];
+    double   ycc_to_rgb_matrix[9], ycc_to_rgb_offset[3], rgb_to_lms_matrix[9];
+} orc_dovi;
+
 /* optional taps into the pass chain for stage-wise parity tests */
 typedef struct orc_debug {
     float*    convert_f32;   /* [srcRectH][srcRectW][3]  convert pass output before the RT write    */

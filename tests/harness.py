@@ -199,7 +199,7 @@ class Case:
     def __init__(self, cf, w, h, dst_w, dst_h, ex, backbuffer=O.SURF_BGRA8, tex=O.TEXFMT_AUTOINT, chroma=O.CHROMA_Bilinear,
                  up=O.UPSCALE["CatmullRom"], down=O.DOWNSCALE["Hamming"], interp50=1, dither=1, to_sdr=1, nits=125,
                  src_rect=None, dst_rect=None, win=None, variant=O.VARIANT_D3D11, procamp=None, interlaced=0, deint_blend=0,
-                 name=None, bottom_up=0, hdr=None, rotation=0, flip=0):
+                 name=None, bottom_up=0, hdr=None, rotation=0, flip=0, dovi=None):
         self.__dict__.update(locals()); del self.__dict__["self"]
         self.name = name or "case"
 
@@ -253,7 +253,62 @@ class Case:
 
 
 def run_oracle(case, planes, pitches, mode=O.MODE_SPEC, want_debug=False, threads=0):
-    return O.process(case.orc_config(), planes, pitches, mode=mode, want_debug=want_debug, threads=threads)
+    return O.process(case.orc_config(), planes, pitches, mode=mode, want_debug=want_debug, threads=threads, dovi=case.dovi)
+
+
+def make_dovi(seed=0, mmr=0, bits=10, denom=23):
+    """Synthetic Dolby Vision reshaping data (OrcDovi; the product's mpcvr_dovi_metadata has the same layout): per component a
+    few polynomial pieces close to identity, optionally MMR pieces of order 1..3 for the chroma components (as profile 5 streams
+    have), the BT.2020-like YCC->RGB matrix with full-range offsets and an RGB->LMS matrix near the ICtCp one.
+    mmr: 0 none, 1 one MMR piece per chroma curve, 2 several MMR pieces of different orders."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    d = O.OrcDovi()
+    d.coef_log2_denom = denom; d.bl_bit_depth = bits
+    one = 1 << denom
+    top = (1 << bits) - 1
+    for c in range(3):
+        cv = d.curves[c]
+        if c == 0 or not mmr:
+            npiv = int(rng.integers(2, 10))
+            piv = np.sort(rng.choice(np.arange(1, top), npiv - 2, replace=False)) if npiv > 2 else np.array([], int)
+            piv = np.concatenate([[0], piv, [top]])
+            cv.num_pivots = npiv
+            for i in range(npiv):
+                cv.pivots[i] = int(piv[i])
+            for i in range(npiv - 1):
+                cv.mapping_idc[i] = 0
+                cv.poly_order[i] = int(rng.integers(1, 3))
+                cv.poly_coef[i][0] = int(rng.uniform(-0.02, 0.02) * one)
+                cv.poly_coef[i][1] = int(rng.uniform(0.9, 1.1) * one)
+                cv.poly_coef[i][2] = int(rng.uniform(-0.08, 0.08) * one)
+        else:
+            npiv = 2 if mmr == 1 else 4
+            piv = [0, top] if mmr == 1 else [0, top // 3, 2 * top // 3, top]
+            cv.num_pivots = npiv
+            for i in range(npiv):
+                cv.pivots[i] = piv[i]
+            for i in range(npiv - 1):
+                if mmr == 2 and i == 1 and c == 2:      # a polynomial piece between MMR pieces: methods == POLY + MMR
+                    cv.mapping_idc[i] = 0; cv.poly_order[i] = 2
+                    cv.poly_coef[i][0] = int(0.01 * one); cv.poly_coef[i][1] = int(0.97 * one); cv.poly_coef[i][2] = int(0.02 * one)
+                    continue
+                cv.mapping_idc[i] = 1
+                order = 3 if mmr == 1 else int(1 + (i + c) % 3)
+                cv.mmr_order[i] = order
+                cv.mmr_constant[i] = int(rng.uniform(-0.02, 0.02) * one)
+                for j in range(order):
+                    for k in range(7):
+                        base = 1.0 if (j == 0 and k == c) else 0.0       # first-order term of the own component ~ identity
+                        cv.mmr_coef[i][j][k] = int((base + rng.uniform(-0.05, 0.05)) * one)
+    ycc = np.array([[1.0, 0.0, 1.4746], [1.0, -0.16455, -0.57135], [1.0, 1.8814, 0.0]]) * rng.uniform(0.98, 1.02)
+    for i in range(9):
+        d.ycc_to_rgb_matrix[i] = float(ycc.ravel()[i])
+    for i, v in enumerate((0.0, 0.5, 0.5)):
+        d.ycc_to_rgb_offset[i] = v
+    lms = np.array([[0.4121, 0.5239, 0.0640], [0.1667, 0.7204, 0.1129], [0.0242, 0.0755, 0.9004]]) + rng.uniform(-0.01, 0.01, (3, 3))
+    for i in range(9):
+        d.rgb_to_lms_matrix[i] = float(lms.ravel()[i])
+    return d
 
 
 def rgb_view(buf, fmt_):

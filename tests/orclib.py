@@ -54,6 +54,17 @@ class OrcDebug(C.Structure):
                 ("out_resize_x", C.c_int32), ("out_resize_y", C.c_int32)]
 
 
+class OrcDoviCurve(C.Structure):      # orc_dovi_curve
+    _fields_ = [("num_pivots", C.c_uint8), ("pivots", C.c_uint16 * 9), ("mapping_idc", C.c_uint8 * 8), ("poly_order", C.c_uint8 * 8),
+                ("poly_coef", (C.c_int64 * 3) * 8), ("mmr_order", C.c_uint8 * 8), ("mmr_constant", C.c_int64 * 8),
+                ("mmr_coef", ((C.c_int64 * 7) * 3) * 8)]
+
+
+class OrcDovi(C.Structure):           # orc_dovi
+    _fields_ = [("coef_log2_denom", C.c_uint8), ("bl_bit_depth", C.c_uint8), ("curves", OrcDoviCurve * 3),
+                ("ycc_to_rgb_matrix", C.c_double * 9), ("ycc_to_rgb_offset", C.c_double * 3), ("rgb_to_lms_matrix", C.c_double * 9)]
+
+
 class OrcFmt(C.Structure):
     _fields_ = [("cformat", C.c_int32), ("layout", C.c_int32), ("bytes", C.c_int32), ("cdepth", C.c_int32),
                 ("cstype", C.c_int32), ("subsampling", C.c_int32), ("div_w", C.c_int32), ("div_h", C.c_int32),
@@ -79,6 +90,9 @@ def lib():
         L.orc_process.restype = C.c_int
         L.orc_process.argtypes = [C.POINTER(OrcConfig), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_void_p,
                                   C.c_int32, C.POINTER(OrcDebug), C.c_int, C.c_int]
+        L.orc_process_dovi.restype = C.c_int
+        L.orc_process_dovi.argtypes = [C.POINTER(OrcConfig), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_void_p,
+                                       C.c_int32, C.POINTER(OrcDebug), C.c_int, C.c_int, C.c_void_p]
         L.orc_process_from_convert.restype = C.c_int
         L.orc_process_from_convert.argtypes = [C.POINTER(OrcConfig), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                                C.POINTER(OrcDebug), C.c_int, C.c_int]
@@ -186,7 +200,7 @@ def make_config(cformat, width, height, dst_w, dst_h, ex, backbuffer=SURF_BGRA8,
     return cfg
 
 
-def process(cfg, planes, pitches, mode=MODE_SPEC, threads=0, want_debug=False, from_convert=None):
+def process(cfg, planes, pitches, mode=MODE_SPEC, threads=0, want_debug=False, from_convert=None, dovi=None):
     """planes: list of numpy arrays (kept alive by caller). Returns out bytes array [win_h, win_w*bpp] (+debug dict)"""
     L = lib()
     bpp = surf_bpp(cfg.backbuffer_fmt)
@@ -209,7 +223,8 @@ def process(cfg, planes, pitches, mode=MODE_SPEC, threads=0, want_debug=False, f
     else:
         pl = (C.c_void_p * 3)(*[p.ctypes.data if p is not None else None for p in (list(planes) + [None] * 3)[:3]])
         pi = (C.c_int32 * 3)(*((list(pitches) + [0] * 3)[:3]))
-        rc = L.orc_process(C.byref(cfg), pl, pi, out.ctypes.data, out.strides[0], C.byref(dbg), mode, threads)
+        rc = L.orc_process_dovi(C.byref(cfg), pl, pi, out.ctypes.data, out.strides[0], C.byref(dbg), mode, threads,
+                                C.addressof(dovi) if dovi is not None else None)
     if rc != 0:
         raise RuntimeError("orc_process failed rc=%d" % rc)
     if want_debug:

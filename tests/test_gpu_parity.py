@@ -18,7 +18,7 @@ def _run_gpu(case, buf, pitch, path=PATH_MULTIPASS, capture=False):
     if capture:
         vp.debug_capture_f32(True)
     side = getattr(case, "side_data", None) or {}
-    vp.ProcessSample(data=buf, pitch=pitch, hdr=side.get("hdr"), hdr_cll=side.get("cll"))
+    vp.ProcessSample(data=buf, pitch=pitch, hdr=side.get("hdr"), hdr_cll=side.get("cll"), dovi=getattr(case, "dovi", None))
     out = vp.ReadBackbuffer()
     return vp, out
 
@@ -544,3 +544,33 @@ def test_jinc2_rects_and_final_pass():
     _check(H.Case(O.CF["P010"], 64, 36, 128, 72, H.EX_2020_PQ, dst_rect=(16, 11, 144, 83), win=(160, 100), up=O.UPSCALE["Jinc2"], name="jinc2_letterbox"), "noise", 53)
     _check(H.Case(O.CF["XRGB32"], 64, 36, 100, 60, 0, src_rect=(4, 2, 60, 34), up=O.UPSCALE["Jinc2"], name="jinc2_rgb_direct"), "natural", 54)
     _check(H.Case(O.CF["P010"], 64, 36, 96, 54, H.EX_709, tex=O.TEXFMT_16FLOAT, backbuffer=O.SURF_RGB10A2, up=O.UPSCALE["Jinc2"], name="jinc2_16f"), "natural", 55)
+
+
+# ---- Dolby Vision reshaping inside the convert stage (Source/Shaders.cpp:531-589, :703-859) ----
+@pytest.mark.parametrize("mmr", [0, 1, 2])
+@pytest.mark.parametrize("to_sdr", [1, 0])
+def test_dolby_vision_reshape(mmr, to_sdr):
+    """polynomial-only and MMR (single / several pieces of orders 1..3, mixed with a polynomial piece) curves; reshaped signal
+    through the custom YCC->RGB matrix, PQ->linear->LMS->PQ, then tone-mapped to SDR or left as PQ"""
+    ex = O.exfmt(chroma=5, range_=1, matrix=0, prim=0, trc=0)            # profile-5 style stream: no PQ/HLG tag
+    for seed in (61, 62):
+        case = H.Case(O.CF["P010"], 64, 36, 96, 54, ex, up=O.UPSCALE["Lanczos2"], to_sdr=to_sdr, dovi=H.make_dovi(seed, mmr=mmr),
+                      backbuffer=O.SURF_BGRA8 if to_sdr else O.SURF_RGB10A2, name="dovi_mmr%d" % mmr)
+        _check(case, "fullnoise", seed)
+
+
+def test_dolby_vision_procamp_and_12bit_base():
+    case = H.Case(O.CF["P016"], 48, 28, 48, 28, O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=0), up=O.UPSCALE["Nearest"],
+                  dovi=H.make_dovi(63, mmr=1, bits=12, denom=20), procamp=dict(brightness=6.0, contrast=1.1), name="dovi_procamp")
+    _check(case, "natural", 63)
+
+
+def test_dolby_vision_is_ignored_for_tagged_hdr10_unless_preferred():
+    """m_bHdrPreferDoVi false and the stream tagged PQ: the side data is not taken (Source/DX11VideoProcessor.cpp:2271)"""
+    plain = H.Case(O.CF["P010"], 48, 28, 72, 42, H.EX_2020_PQ, up=O.UPSCALE["CatmullRom"], name="dovi_ignored")
+    codes = H.make_codes(plain.cf, plain.w, plain.h, "natural", 64)
+    buf, pitch, planes, pitches = H.pack(plain.cf, plain.w, plain.h, codes)
+    ref = H.run_oracle(plain, planes, pitches)                            # oracle without Dolby Vision data
+    plain.dovi = H.make_dovi(64, mmr=1)                                   # the product is handed the side data anyway
+    _, out = _run_gpu(plain, buf, pitch)
+    assert H.compare(out, ref, plain.backbuffer) == (0, 0)

@@ -104,6 +104,17 @@ class SideDataHDRCLL(C.Structure):
     _fields_ = [("MaxCLL", C.c_uint32), ("MaxFALL", C.c_uint32)]
 
 
+class DoviCurve(C.Structure):         # mpcvr_dovi_curve (natural C layout)
+    _fields_ = [("num_pivots", C.c_uint8), ("pivots", C.c_uint16 * 9), ("mapping_idc", C.c_uint8 * 8), ("poly_order", C.c_uint8 * 8),
+                ("poly_coef", (C.c_int64 * 3) * 8), ("mmr_order", C.c_uint8 * 8), ("mmr_constant", C.c_int64 * 8),
+                ("mmr_coef", ((C.c_int64 * 7) * 3) * 8)]
+
+
+class DoviMetadata(C.Structure):      # mpcvr_dovi_metadata
+    _fields_ = [("coef_log2_denom", C.c_uint8), ("bl_bit_depth", C.c_uint8), ("curves", DoviCurve * 3),
+                ("ycc_to_rgb_matrix", C.c_double * 9), ("ycc_to_rgb_offset", C.c_double * 3), ("rgb_to_lms_matrix", C.c_double * 9)]
+
+
 SAMPLE_DEVICE_MEMORY = 0x1
 
 
@@ -111,7 +122,7 @@ class Sample(C.Structure):
     _fields_ = [("flags", C.c_uint32), ("data", C.c_void_p), ("size", C.c_int64), ("pitch", C.c_int32),
                 ("planes", C.c_void_p * 3), ("pitches", C.c_int32 * 3), ("ready_event", C.c_void_p),
                 ("rt_start", C.c_int64), ("rt_end", C.c_int64), ("hdr", C.POINTER(SideDataHDR)),
-                ("hdr_cll", C.POINTER(SideDataHDRCLL))]
+                ("hdr_cll", C.POINTER(SideDataHDRCLL)), ("dovi", C.POINTER(DoviMetadata))]
 
 
 class ProcAmp(C.Structure):

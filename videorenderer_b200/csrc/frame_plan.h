@@ -50,6 +50,15 @@ struct ColorParams {
     float r1000;                    // 1/1000 (LinearToST2084 divider)                   (Source/Shaders.cpp:866)
 };
 
+struct DoviParams {                 // PS_DOVI_CURVE x3 (Source/Shaders.cpp:715-733) + the LMS matrix literal (:823-840)
+    float   pivots[3][7];
+    float   coeffs[3][8][4];
+    float   mmr[3][48][4];
+    int32_t methods[3], mmr_single[3], min_order[3], max_order[3];
+    float   mat[3][3];
+    int32_t has_mmr;
+};
+
 struct SurfDesc {                   // a render target / shader resource of the pass chain
     void*   ptr;
     int32_t pitch;                  // bytes

@@ -7,7 +7,9 @@ namespace b200vr {
 
 // ---- multipass family: one kernel per reference pass (Process, Source/DX11VideoProcessor.cpp:3285-3424)
 // ConvertColorPass (:3048-3101). dbg_f32 (optional): float4 per pixel, shader output before the RT write.
-cudaError_t LaunchConvertPass(const SrcDesc& src, const ColorParams& color, const SurfDesc& out, float4* dbg_f32, cudaStream_t st);
+// dovi_dev (optional, device memory): Dolby Vision reshaping data of the frame
+cudaError_t LaunchConvertPass(const SrcDesc& src, const ColorParams& color, const SurfDesc& out, float4* dbg_f32, cudaStream_t st,
+                              const DoviParams* dovi_dev = nullptr);
 // TextureResizeShader (:332-377): output axis `axis` (0 = X, 1 = Y) is filtered along texture axis `in_axis` (default: the same;
 // differs on quads turned by 90/270 degrees); `other` maps the other output axis to the other texture axis (point sample).
 cudaError_t LaunchResizePass(const SurfDesc& in, const SurfDesc& out, const AxisTable& table, int axis,

@@ -17,12 +17,12 @@ __device__ const uint16_t g_dither32[1024] = { MPCVR_DITHER32_VALUES };
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_convert(const __grid_constant__ SrcDesc S, const __grid_constant__ ColorParams P, const __grid_constant__ SurfDesc out,
-          float4* __restrict__ dbg)
+          float4* __restrict__ dbg, const DoviParams* __restrict__ dovi)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= out.w || y >= out.h) return;
     const f3 yuv = fetch_yuv(S, S.rect_l + x, S.rect_t + y);
-    const f3 rgb = convert_color<-1>(P, yuv);
+    const f3 rgb = convert_color<-1>(P, yuv, dovi);
     if (dbg) dbg[(size_t)y * out.w + x] = make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
     surf_store(out, x, y, rgb);
 }
@@ -312,10 +312,11 @@ __global__ void k_math_probe(int op, const float* __restrict__ x, const float* _
 // ---------------------------------------------------------------------------------------------
 static inline dim3 Grid2D(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
 
-cudaError_t LaunchConvertPass(const SrcDesc& src, const ColorParams& color, const SurfDesc& out, float4* dbg_f32, cudaStream_t st)
+cudaError_t LaunchConvertPass(const SrcDesc& src, const ColorParams& color, const SurfDesc& out, float4* dbg_f32, cudaStream_t st,
+                              const DoviParams* dovi_dev)
 {
     const dim3 b(32, 8);
-    k_convert<<<Grid2D(out.w, out.h, b), b, 0, st>>>(src, color, out, dbg_f32);
+    k_convert<<<Grid2D(out.w, out.h, b), b, 0, st>>>(src, color, out, dbg_f32, dovi_dev);
     return cudaGetLastError();
 }
 

@@ -346,13 +346,68 @@ __device__ __forceinline__ f3 mat3_apply(const float m[3][3], f3 v)             
     return r;
 }
 
+// ---- Dolby Vision reshaping (ShaderDoviReshape / ShaderDoviReshapePoly, Source/Shaders.cpp:531-589; reshape_mmr :734-765)
+__device__ __forceinline__ float dv_dot3(const float m[4], float x, float y, float z) { return fma_rn(m[2], z, fma_rn(m[1], y, __fmul_rn(m[0], x))); }
+__device__ __forceinline__ float dv_dot4(const float m[4], float x, float y, float z, float w) { return fma_rn(m[3], w, fma_rn(m[2], z, fma_rn(m[1], y, __fmul_rn(m[0], x)))); }
+
+__device__ __forceinline__ float dovi_mmr(const DoviParams& D, int c, const float co[4], f3 sig)
+{
+    const int idx = D.mmr_single[c] ? 0 : (int)co[1];
+    const float (*M)[4] = D.mmr[c];
+    float s = co[0];
+    const float x0 = __fmul_rn(sig.x, sig.y), x1 = __fmul_rn(sig.x, sig.z), x2 = __fmul_rn(sig.y, sig.z), x3 = __fmul_rn(x0, sig.z);
+    s = __fadd_rn(s, dv_dot3(M[idx + 0], sig.x, sig.y, sig.z));
+    s = __fadd_rn(s, dv_dot4(M[idx + 1], x0, x1, x2, x3));
+    if (D.max_order[c] >= 2) {
+        const int order = (int)co[3];
+        if (D.min_order[c] < 2 && order < 2) return s;
+        const float sx = __fmul_rn(sig.x, sig.x), sy = __fmul_rn(sig.y, sig.y), sz = __fmul_rn(sig.z, sig.z);
+        const float y0 = __fmul_rn(x0, x0), y1 = __fmul_rn(x1, x1), y2 = __fmul_rn(x2, x2), y3 = __fmul_rn(x3, x3);
+        s = __fadd_rn(s, dv_dot3(M[idx + 2], sx, sy, sz));
+        s = __fadd_rn(s, dv_dot4(M[idx + 3], y0, y1, y2, y3));
+        if (D.max_order[c] == 3) {
+            if (D.min_order[c] < 3 && order < 3) return s;
+            s = __fadd_rn(s, dv_dot3(M[idx + 4], __fmul_rn(sx, sig.x), __fmul_rn(sy, sig.y), __fmul_rn(sz, sig.z)));
+            s = __fadd_rn(s, dv_dot4(M[idx + 5], __fmul_rn(y0, x0), __fmul_rn(y1, x1), __fmul_rn(y2, x2), __fmul_rn(y3, x3)));
+        }
+    }
+    return s;
+}
+
+__device__ __forceinline__ f3 dovi_reshape(const DoviParams& D, f3 yuv)
+{
+    f3 sig; sig.x = sat(yuv.x); sig.y = sat(yuv.y); sig.z = sat(yuv.z);
+    float r[3];
+    #pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float s = c == 0 ? sig.x : (c == 1 ? sig.y : sig.z);
+        const float* pv = D.pivots[c];
+        const int k = (s < pv[3]) ? ((s < pv[1]) ? ((s < pv[0]) ? 0 : 1) : ((s < pv[2]) ? 2 : 3))
+                                  : ((s < pv[5]) ? ((s < pv[4]) ? 4 : 5) : ((s < pv[6]) ? 6 : 7));
+        const float* co = D.coeffs[c][k];
+        bool poly = true;
+        if (D.has_mmr) poly = (D.methods[c] == 3) ? (co[3] == 0.0f) : (D.methods[c] == 1);
+        r[c] = sat(poly ? fma_rn(fma_rn(co[2], s, co[1]), s, co[0]) : dovi_mmr(D, c, co, sig));
+    }
+    f3 o; o.x = r[0]; o.y = r[1]; o.z = r[2];
+    return o;
+}
+
 // convert shader body; returns the value before the render-target write.  TR >= 0 fixes the transfer at compile time.
+// D (optional): Dolby Vision -- reshape before the matrix, PQ -> linear -> LMS matrix -> PQ after it (Source/Shaders.cpp:842-858).
 template <int TR = -1>
-__device__ __forceinline__ f3 convert_color(const ColorParams& P, f3 yuv)
+__device__ __forceinline__ f3 convert_color(const ColorParams& P, f3 yuv, const DoviParams* D = nullptr)
 {
     const int tr = (TR >= 0) ? TR : P.transfer;
+    if (D) yuv = dovi_reshape(*D, yuv);
     f3 c = mat3_apply(P.cm, yuv);                                                   // Source/Shaders.cpp:820
     c.x = __fadd_rn(c.x, P.cc[0]); c.y = __fadd_rn(c.y, P.cc[1]); c.z = __fadd_rn(c.z, P.cc[2]);
+    if (D) {
+        f3 l;                                                                       // ST2084ToLinear(max(color, 0), 1.0)
+        l.x = st2084_to_linear(P, fmaxf(c.x, 0.0f), 1.0f); l.y = st2084_to_linear(P, fmaxf(c.y, 0.0f), 1.0f); l.z = st2084_to_linear(P, fmaxf(c.z, 0.0f), 1.0f);
+        const f3 m = mat3_apply(D->mat, l);
+        c.x = linear_to_st2084(fmaxf(m.x, 0.0f), 1.0f); c.y = linear_to_st2084(fmaxf(m.y, 0.0f), 1.0f); c.z = linear_to_st2084(fmaxf(m.z, 0.0f), 1.0f);
+    }
     if (tr == TRANSFER_NONE) return c;
     if (tr == TRANSFER_SDR_2020) {                                                  // :892-915
         f3 l; l.x = powr(sat(c.x), P.sdr_gamma); l.y = powr(sat(c.y), P.sdr_gamma); l.z = powr(sat(c.z), P.sdr_gamma);

@@ -59,7 +59,7 @@ CB200VideoProcessor::~CB200VideoProcessor()
         if (m_stream) cudaStreamSynchronize(m_stream);
         for (auto& t : m_TexSrcVideo) t.Release();
         m_TexConvertOutput.Release(); m_TexSrcUnpacked.Release(); m_TexResize.Release(); m_TexsPostScale.Release(); m_TexsPostScale2.Release(); m_BackBuffer.Release(); m_TexImage.Release();
-        m_dbgConvertF32.Release();
+        m_dbgConvertF32.Release(); m_doviDev.Release();
         m_axisX.Release(); m_axisY.Release(); m_pointX.Release(); m_pointY.Release(); m_pointRX.Release(); m_pointRY.Release(); m_oFilt.Release(); m_oU.Release(); m_oV.Release();
         if (m_ownStream && m_stream) cudaStreamDestroy(m_stream);
     }
@@ -95,6 +95,7 @@ void CB200VideoProcessor::ApplySettings(const mpcvr_settings& s)
     m_bConvertToSdr = s.bConvertToSdr != 0;
     m_iSDRDisplayNits = s.iSDRDisplayNits;
     if (m_iSDRDisplayNits < MPCVR_SDR_NITS_MIN || m_iSDRDisplayNits > MPCVR_SDR_NITS_MAX) m_iSDRDisplayNits = MPCVR_SDR_NITS_DEF;
+    m_bHdrPreferDoVi = s.bHdrPreferDoVi != 0;
     m_bHdrPassthrough = s.bHdrPassthrough != 0;
     m_bHdrLocalToneMapping = s.bHdrLocalToneMapping != 0;
     m_iHdrLocalToneMappingType = s.iHdrLocalToneMappingType;
@@ -140,6 +141,7 @@ int32_t CB200VideoProcessor::InitMediaType(const mpcvr_media_type* mt)
     const FmtConvParams FmtParams = GetFmtConvParams(mt->cformat);
 
     m_decExFmt.value = 0;
+    m_Dovi.bValid = false; m_Dovi.bHasMMR = false;                          // m_Dovi = {} on a new media type
     m_srcRect = CRect(mt->src_rect.left, mt->src_rect.top, mt->src_rect.right, mt->src_rect.bottom);
     m_srcAspectRatioX = mt->aspect_x; m_srcAspectRatioY = mt->aspect_y;
     if (FmtParams.CSType == CS_YUV && mt->ext_format) {
@@ -251,9 +253,10 @@ int CB200VideoProcessor::Transfer() const
     // HDR output: SHADER_CONVERT_TO_PQ for HLG, SHADER_CONVERT_NONE otherwise (:2948-2950)
     const uint32_t trc = m_srcExFmt.TransferFunction();
     const bool toSdr = m_bConvertToSdr && !HdrOut();
-    if (toSdr && trc == Trc_2084) return TRANSFER_PQ_TO_SDR;
+    // bConvertHDRtoSDR also holds for Dolby Vision (the reshaped signal is PQ); bApplyHLG excludes it (Shaders.cpp:614-615)
+    if (toSdr && (trc == Trc_2084 || m_Dovi.bValid)) return TRANSFER_PQ_TO_SDR;
     if (toSdr && trc == Trc_HLG)  return TRANSFER_HLG_TO_SDR;
-    if (HdrOut() && trc == Trc_HLG) return TRANSFER_HLG_TO_PQ;
+    if (HdrOut() && trc == Trc_HLG && !m_Dovi.bValid) return TRANSFER_HLG_TO_PQ;
     if (m_srcExFmt.Primaries() == Prim_BT2020) {
         switch (trc) {
         case Trc_18: case Trc_20: case Trc_HLG: case Trc_22: case Trc_709: case Trc_240M: case Trc_sRGB: case Trc_28: case Trc_26:
@@ -267,6 +270,16 @@ int CB200VideoProcessor::Transfer() const
 void CB200VideoProcessor::SetShaderConvertColorParams()
 {
     BuildColorTransform(m_srcExFmt, m_srcParams, m_ProcAmp, m_PSConvColorData);
+    if (m_Dovi.bValid) {                                                    // :817-834
+        const float brightness = m_ProcAmp.brightness / 255, contrast = m_ProcAmp.contrast;
+        float (&m)[3][3] = m_PSConvColorData.m; float (&c)[3] = m_PSConvColorData.c;
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m[i][j] = (float)m_Dovi.msd.ycc_to_rgb_matrix[i * 3 + j] * contrast;
+        for (int i = 0; i < 3; i++) {
+            c[i] = brightness;
+            for (int j = 0; j < 3; j++) c[i] = (float)((double)c[i] - (double)m[i][j] * m_Dovi.msd.ycc_to_rgb_offset[j]);
+        }
+        m_PSConvColorData.enable = true;
+    }
     {
         float (&m)[3][3] = m_PSConvColorData.m;
         if (m_srcParams.CSType == CS_RGB && m_srcParams.layout == LAYOUT_PLANAR3) {          // GBRP: planes are G, B, R (:863-867)
@@ -355,6 +368,78 @@ int32_t CB200VideoProcessor::SetRotation(int v)
 int32_t CB200VideoProcessor::SetFlip(bool v)
 {
     m_bFlip = v; m_planDirty = true;                                        // Source/VideoProcessor.h:210
+    return MPCVR_S_OK;
+}
+
+bool CB200VideoProcessor::CheckDoviMetadata(const mpcvr_dovi_metadata* p) const
+{
+    if (p->bl_bit_depth < 8 || p->bl_bit_depth > 16 || p->coef_log2_denom > 31) return false;
+    for (const auto& curve : p->curves) {
+        if (curve.num_pivots < 2 || curve.num_pivots > 9) return false;
+        for (int i = 0; i < (int)curve.num_pivots - 1; i++) {
+            if (curve.mapping_idc[i] > 1) return false;                     // 0 polynomial, 1 mmr
+            if (curve.mapping_idc[i] == 1 && (curve.mmr_order[i] < 1 || curve.mmr_order[i] > 3)) return false;
+        }
+    }
+    return true;
+}
+
+int32_t CB200VideoProcessor::SetShaderDoviCurves()
+{
+    // SetShaderDoviCurves / SetShaderDoviCurvesPoly (:990-1141) and the matrix literal of GetShaderConvertColor
+    // (Source/Shaders.cpp:823-840: dovi_lms2rgb x rgb_to_lms through mul_matrix3x3, Source/csputils.cpp:531-538)
+    const mpcvr_dovi_metadata& dv = m_Dovi.msd;
+    DoviParams& P = m_doviHost;
+    memset(&P, 0, sizeof(P));
+    bool any_mmr = false;
+    for (const auto& cv : dv.curves) for (int i = 0; i < cv.num_pivots - 1; i++) if (cv.mapping_idc[i] == 1) any_mmr = true;
+    m_Dovi.bHasMMR = any_mmr; P.has_mmr = any_mmr ? 1 : 0;
+    const float scale = 1.0f / (float)((1 << dv.bl_bit_depth) - 1);
+    const float scale_coef = 1.0f / (float)(1u << dv.coef_log2_denom);
+    for (int c = 0; c < 3; c++) {
+        const mpcvr_dovi_curve& cv = dv.curves[c];
+        bool has_poly = false, has_mmr = false, mmr_single = true;
+        int mmr_idx = 0, min_order = 3, max_order = 1;
+        for (int i = 0; i < cv.num_pivots - 1; i++) {
+            float* co = P.coeffs[c][i];
+            if (cv.mapping_idc[i] == 0) {
+                has_poly = true;
+                co[0] = scale_coef * (float)cv.poly_coef[i][0];
+                co[1] = cv.poly_order[i] >= 1 ? scale_coef * (float)cv.poly_coef[i][1] : 0.0f;
+                co[2] = cv.poly_order[i] >= 2 ? scale_coef * (float)cv.poly_coef[i][2] : 0.0f;
+                co[3] = 0.0f;                                                // order 0 signals polynomial
+            } else {
+                min_order = std::min<int>(min_order, cv.mmr_order[i]); max_order = std::max<int>(max_order, cv.mmr_order[i]);
+                mmr_single = !has_mmr; has_mmr = true;
+                co[0] = scale_coef * (float)cv.mmr_constant[i]; co[1] = (float)mmr_idx; co[3] = (float)cv.mmr_order[i];
+                for (int j = 0; j < cv.mmr_order[i]; j++) {                  // weights per order as two packed float4s
+                    for (int k = 0; k < 3; k++) P.mmr[c][mmr_idx][k] = scale_coef * (float)cv.mmr_coef[i][j][k];
+                    mmr_idx++;
+                    for (int k = 0; k < 4; k++) P.mmr[c][mmr_idx][k] = scale_coef * (float)cv.mmr_coef[i][j][3 + k];
+                    mmr_idx++;
+                }
+            }
+        }
+        const int n = cv.num_pivots - 2;
+        for (int i = 0; i < 7; i++) P.pivots[c][i] = i < n ? scale * (float)cv.pivots[i + 1] : 1e9f;
+        P.methods[c] = (has_poly ? 1 : 0) | (has_mmr ? 2 : 0);
+        if (has_mmr) { P.mmr_single[c] = mmr_single; P.min_order[c] = min_order; P.max_order[c] = max_order; }
+    }
+    static const float lms2rgb[3][3] = { { 3.06441879f, -2.16597676f,  0.10155818f}, {-0.65612108f,  1.78554118f, -0.12943749f},
+                                         { 0.01736321f, -0.04725154f,  1.03004253f} };
+    float lin[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) lin[i][j] = (float)dv.rgb_to_lms_matrix[i * 3 + j];
+    for (int r = 0; r < 3; r++)
+        for (int i = 0; i < 3; i++) {
+            float v = lms2rgb[r][0] * lin[0][i]; v = v + lms2rgb[r][1] * lin[1][i]; v = v + lms2rgb[r][2] * lin[2][i];
+            P.mat[r][i] = v;
+        }
+    if (m_device >= 0) {
+        cudaSetDevice(m_device);
+        if (!m_doviDev.ptr) { if (!Cuda(cudaMalloc(&m_doviDev.ptr, sizeof(DoviParams)), "cudaMalloc(dovi)")) return MPCVR_E_FAIL; m_doviDev.n = 1; }
+        if (!Cuda(cudaMemcpyAsync(m_doviDev.ptr, &P, sizeof(P), cudaMemcpyHostToDevice, m_stream), "H2D dovi")) return MPCVR_E_FAIL;
+    }
+    m_planDirty = true;
     return MPCVR_S_OK;
 }
 
@@ -553,6 +638,22 @@ int32_t CB200VideoProcessor::CopySample(const mpcvr_sample* s)
         if (const mpcvr_side_data_hdr_cll* cll = s->hdr_cll) { m_hdr10.MaxCLL = (uint16_t)cll->MaxCLL; m_hdr10.MaxFALL = (uint16_t)cll->MaxFALL; }
     }
 
+    // Dolby Vision side data (:2271-2330): taken for YUV types when preferred or when the stream is not tagged PQ/HLG
+    {
+        const bool take = s->dovi && f.CSType == CS_YUV && (m_bHdrPreferDoVi || !SourceIsHDR10orHLG()) && CheckDoviMetadata(s->dovi);
+        if (take) {
+            const bool changed = !m_Dovi.bValid || memcmp(&m_Dovi.msd, s->dovi, sizeof(m_Dovi.msd)) != 0;
+            if (changed) {
+                m_Dovi.msd = *s->dovi; m_Dovi.bValid = true;
+                const int32_t hr = SetShaderDoviCurves();
+                if (hr != MPCVR_S_OK) return hr;
+                SetShaderConvertColorParams();
+            }
+        } else if (m_Dovi.bValid && !s->dovi) {
+            // the reference keeps the last metadata until the media type changes; a sample without it keeps using it (:2271-2330)
+        }
+    }
+
     if (s->flags & MPCVR_SAMPLE_DEVICE_MEMORY) {
         // IMediaSampleD3D11 path (:2528-2570): the decoder's planes are read in place
         const int np = f.layout == LAYOUT_BIPLANAR ? 2 : (f.layout == LAYOUT_PLANAR3 ? 3 : 1);
@@ -720,7 +821,7 @@ int32_t CB200VideoProcessor::ConvertColorPass(const Tex2D& rt)
         dbg = m_dbgConvertF32.ptr;
     }
     m_lastLaunches++;
-    return Cuda(LaunchConvertPass(m_src, m_color, rt.desc(), dbg, m_stream), "ConvertColorPass") ? MPCVR_S_OK : MPCVR_E_FAIL;
+    return Cuda(LaunchConvertPass(m_src, m_color, rt.desc(), dbg, m_stream, m_Dovi.bValid ? m_doviDev.ptr : nullptr), "ConvertColorPass") ? MPCVR_S_OK : MPCVR_E_FAIL;
 }
 
 int32_t CB200VideoProcessor::ResizeShaderPass(const Tex2D& tex, const Tex2D& rt, const CRect& srcRect, const CRect& dstRect)
@@ -877,6 +978,7 @@ bool CB200VideoProcessor::PlanFused(const Tex2D& target, const CRect& dstRect, F
     if (!m_PSConvColorData.enable) { if (why) *why = "no convert pass on this plan (RGB source, default ProcAmp): multipass only"; return false; }
     if (m_bTonemap) { if (why) *why = "HDR10 tone-map post-scale step: multipass only"; return false; }
     if (m_oriented) { if (why) *why = "rotation / flip: multipass only"; return false; }
+    if (m_Dovi.bValid) { if (why) *why = "Dolby Vision reshaping: multipass only"; return false; }
     if (m_jincX || m_jincY) { if (why) *why = "Jinc2: multipass only"; return false; }
     fp.src = m_src; fp.color = m_color;
     fp.ax = m_axisX.table(); fp.ay = m_axisY.table();

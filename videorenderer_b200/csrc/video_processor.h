@@ -197,6 +197,14 @@ private:
     void  SetHDR10ShaderParams(float minNits, float maxNits, float maxCLL, float maxFALL, float displayMaxNits, int type);   // :907-951
     int32_t TonemapPass(const Tex2D& tex, const Tex2D& rt, const CRect& rect);
 
+    // Dolby Vision (m_Dovi, Source/VideoProcessor.h:110-114): reshaping data of the current frame and its device copy
+    struct { mpcvr_dovi_metadata msd = {}; bool bValid = false; bool bHasMMR = false; } m_Dovi;
+    bool m_bHdrPreferDoVi = false;
+    DoviParams m_doviHost = {};
+    DevArray<DoviParams> m_doviDev;
+    bool    CheckDoviMetadata(const mpcvr_dovi_metadata* p) const;          // Source/VideoProcessor.cpp:273-297 (curve part)
+    int32_t SetShaderDoviCurves();                                          // :990-1141
+
     ColorTransform m_PSConvColorData = {};
     ColorParams    m_color = {};
     DeviceAxis m_axisX, m_axisY;                 // filtered axes

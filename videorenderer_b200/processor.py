@@ -119,7 +119,7 @@ class VideoProcessor:
 
     # -- frames
     def ProcessSample(self, data=None, pitch=0, device_planes=None, device_pitches=None, rt_start=0, rt_end=0, check=True,
-                      hdr=None, hdr_cll=None):
+                      hdr=None, hdr_cll=None, dovi=None):
         """hdr: dict(max_lum, min_lum[, primaries_x, primaries_y, white]) -> MediaSideDataHDR; hdr_cll: (MaxCLL, MaxFALL)"""
         s = A.Sample()
         s.rt_start, s.rt_end = rt_start, rt_end
@@ -132,6 +132,9 @@ class VideoProcessor:
             h.max_display_mastering_luminance = hdr["max_lum"]; h.min_display_mastering_luminance = hdr["min_lum"]
             self._keep_hdr = h
             s.hdr = C.pointer(h)
+        if dovi is not None:                       # an _abi.DoviMetadata (or any ctypes struct with that layout)
+            self._keep_dovi = dovi
+            s.dovi = C.cast(C.pointer(dovi), C.POINTER(A.DoviMetadata))
         if hdr_cll is not None:
             c = A.SideDataHDRCLL(); c.MaxCLL, c.MaxFALL = hdr_cll
             self._keep_cll = c
