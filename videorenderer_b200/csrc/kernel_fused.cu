@@ -306,48 +306,14 @@ __global__ void k_probe_pq(const float* __restrict__ y, const float* __restrict_
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int j = (i + 1) % n;
-    if (mode == 0) {
+    if (mode == 0) {                       // scalar chain (what k_convert runs) ...
         f3 a; a.x = y[i]; a.y = u[i]; a.z = v[i];
         const f3 r = convert_color<TRANSFER_PQ_TO_SDR>(P, a);
         out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
-    } else if (mode == 1) {
+    } else {                               // ... against the two-lane chain of the fused kernel (tests compare them bit for bit)
         f3x2 a; a.x = make_float2(y[i], y[j]); a.y = make_float2(u[i], u[j]); a.z = make_float2(v[i], v[j]);
         const f3x2 r = convert_color_pq2(P, a);
         out[3 * i] = r.x.x; out[3 * i + 1] = r.y.x; out[3 * i + 2] = r.z.x;
-    } else if (mode >= 8) {
-        const float2 c = make_float2(y[i], y[j]);
-        const float2 a   = powr01_ylt1_2(sat2(c), P.inv_m2);
-        const float2 num = max2(add2(a, -ST2084_C1), 0.0f);
-        const float2 den = fma2(-ST2084_C3, a, ST2084_C2);
-        const float2 lin = mul2(powr01_ygt1_2(div_rn_safe_2(num, den), P.inv_m1), P.lum_scale);
-        const float2 hn  = fma2(lin, fma2(0.15f, lin, P.hable_cb), P.hable_de);
-        const float2 hd  = fma2(lin, fma2(0.15f, lin, 0.50f), P.hable_df);
-        const float2 q = div_rn_safe_2(hn, hd);
-        const float2 h = mul2(add2(q, -P.hable_ef), P.hable_rdiv);
-        if (mode == 8) { out[3 * i] = hn.x; out[3 * i + 1] = hd.x; out[3 * i + 2] = q.x; }
-        else if (mode == 9) { out[3 * i] = add2(q, -P.hable_ef).x; out[3 * i + 1] = h.x; out[3 * i + 2] = h.y; }
-        else { out[3 * i] = lin.x; out[3 * i + 1] = lin.y; out[3 * i + 2] = pq_channel_to_hable2(P, c).x; }
-    } else if (mode >= 5) {
-        f3x2 a; a.x = make_float2(y[i], y[j]); a.y = make_float2(u[i], u[j]); a.z = make_float2(v[i], v[j]);
-        f3x2 c;
-        c.x = add2(dp3_2(P.cm[0], a), P.cc[0]); c.y = add2(dp3_2(P.cm[1], a), P.cc[1]); c.z = add2(dp3_2(P.cm[2], a), P.cc[2]);
-        if (mode == 5) { out[3 * i] = c.x.x; out[3 * i + 1] = c.y.x; out[3 * i + 2] = c.z.x; }
-        else {
-            f3x2 h; h.x = pq_channel_to_hable2(P, c.x); h.y = pq_channel_to_hable2(P, c.y); h.z = pq_channel_to_hable2(P, c.z);
-            if (mode == 6) { out[3 * i] = h.x.x; out[3 * i + 1] = h.y.x; out[3 * i + 2] = h.z.x; }
-            else { const float2 g = dp3_2(P.gamut[0], h); out[3 * i] = g.x; out[3 * i + 1] = sat2(g).x; out[3 * i + 2] = powr01_ylt1_2(sat2(g), P.inv_gamma22).x; }
-        }
-    } else {
-        // stage dump of the two-lane chain on channel value c = y[i]
-        const float2 c = make_float2(y[i], y[j]);
-        const float2 a   = powr01_ylt1_2(sat2(c), P.inv_m2);
-        const float2 num = max2(add2(a, -ST2084_C1), 0.0f);
-        const float2 den = fma2(-ST2084_C3, a, ST2084_C2);
-        const float2 b = div_rn_safe_2(num, den);
-        const float2 lin = mul2(powr01_ygt1_2(b, P.inv_m1), P.lum_scale);
-        out[3 * i] = mode == 2 ? a.x : (mode == 3 ? num.x : lin.x);
-        out[3 * i + 1] = mode == 2 ? den.x : (mode == 3 ? b.x : P.inv_m1);
-        out[3 * i + 2] = mode == 2 ? P.inv_m2 : (mode == 3 ? P.lum_scale : powr01_ygt1_2(b, P.inv_m1).x);
     }
 }
 
