@@ -158,10 +158,18 @@ typedef struct mpcvr_dovi_curve {
     int64_t  mmr_constant[8];
     int64_t  mmr_coef[8][3][7];
 } mpcvr_dovi_curve;
+typedef struct mpcvr_dovi_ext {      /* one slot of MediaSideDataDOVIMetadata::Extensions (Include/IMediaSideData.h:245-300) */
+    uint8_t  level;                   /* 0 = unused; 2 = Level2: v = {target_max_pq, trim_slope, trim_offset, trim_power,
+                                         trim_chroma_weight, trim_saturation_gain, ms_weight} -> the L2 trims of the to-SDR chain
+                                         (Source/DX11VideoProcessor.cpp:2383-2466, Source/Shaders.cpp:787-795); other levels are ignored */
+    uint16_t v[7];
+} mpcvr_dovi_ext;
 typedef struct mpcvr_dovi_metadata {
     uint8_t  coef_log2_denom, bl_bit_depth;
     mpcvr_dovi_curve curves[3];
     double   ycc_to_rgb_matrix[9], ycc_to_rgb_offset[3], rgb_to_lms_matrix[9];
+    uint16_t source_min_pq, source_max_pq;     /* ColorMetadata */
+    mpcvr_dovi_ext ext[32];
 } mpcvr_dovi_metadata;
 
 #define MPCVR_SAMPLE_DEVICE_MEMORY 0x1u  /* planes are CUDA device pointers (IMediaSampleD3D11 analogue)   */

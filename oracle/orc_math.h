@@ -98,6 +98,15 @@ static inline float orc_pow_spec(float x, float y)
     return orc_ex2p_spec(orc_lg2_spec(x), y);
 }
 
+/* std::lerp(float, float, float) as libstdc++ evaluates it (exactness / monotonicity guards of C++20 [c.math.lerp]) */
+static inline float orc_lerpf(float a, float b, float t)
+{
+    if ((a <= 0 && b >= 0) || (a >= 0 && b <= 0)) return t * b + (1 - t) * a;
+    if (t == 1) return b;
+    const float x = a + t * (b - a);
+    return ((t > 1) == (b > a)) ? (b < x ? x : b) : (b > x ? x : b);
+}
+
 static inline float orc_pow_literal(float x, float y)
 {
     if (!(x > 0.0f)) return 0.0f;

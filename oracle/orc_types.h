@@ -111,10 +111,17 @@ typedef struct orc_dovi_curve {
     int64_t  mmr_constant[8];
     int64_t  mmr_coef[8][3][7];
 } orc_dovi_curve;
+typedef struct orc_dovi_ext {           /* one slot of MediaSideDataDOVIMetadata::Extensions (Include/IMediaSideData.h:245-300) */
+    uint8_t  level;                      /* 0 = unused slot; 2 = Level2 {target_max_pq, trim_slope, trim_offset, trim_power,
+                                            trim_chroma_weight, trim_saturation_gain, ms_weight}; other levels are carried, not used */
+    uint16_t v[7];
+} orc_dovi_ext;
 typedef struct orc_dovi {
     uint8_t  coef_log2_denom, bl_bit_depth;
     orc_dovi_curve curves[3];
     double   ycc_to_rgb_matrix[9], ycc_to_rgb_offset[3], rgb_to_lms_matrix[9];
+    uint16_t source_min_pq, source_max_pq;
+    orc_dovi_ext ext[32];
 } orc_dovi;
 
 /* optional taps into the pass chain for stage-wise parity tests */

@@ -256,7 +256,18 @@ def run_oracle(case, planes, pitches, mode=O.MODE_SPEC, want_debug=False, thread
     return O.process(case.orc_config(), planes, pitches, mode=mode, want_debug=want_debug, threads=threads, dovi=case.dovi)
 
 
-def make_dovi(seed=0, mmr=0, bits=10, denom=23):
+def make_dovi(seed=0, mmr=0, bits=10, denom=23, l2=None, source_max_pq=3079):
+    d = _make_dovi(seed, mmr, bits, denom)
+    d.source_min_pq = 62; d.source_max_pq = source_max_pq
+    for i, blk in enumerate(l2 or []):              # (target_max_pq, slope, offset, power, chroma_weight, saturation_gain)
+        e = d.ext[2 * i + 1]                         # leave gaps: the reference scans all 32 slots by level
+        e.level = 2
+        for k, v in enumerate(blk):
+            e.v[k] = int(v)
+    return d
+
+
+def _make_dovi(seed=0, mmr=0, bits=10, denom=23):
     """Synthetic Dolby Vision reshaping data (OrcDovi; the product's mpcvr_dovi_metadata has the same layout): per component a
     few polynomial pieces close to identity, optionally MMR pieces of order 1..3 for the chroma components (as profile 5 streams
     have), the BT.2020-like YCC->RGB matrix with full-range offsets and an RGB->LMS matrix near the ICtCp one.

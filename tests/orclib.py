@@ -60,9 +60,14 @@ class OrcDoviCurve(C.Structure):      # orc_dovi_curve
                 ("mmr_coef", ((C.c_int64 * 7) * 3) * 8)]
 
 
+class OrcDoviExt(C.Structure):
+    _fields_ = [("level", C.c_uint8), ("v", C.c_uint16 * 7)]
+
+
 class OrcDovi(C.Structure):           # orc_dovi
     _fields_ = [("coef_log2_denom", C.c_uint8), ("bl_bit_depth", C.c_uint8), ("curves", OrcDoviCurve * 3),
-                ("ycc_to_rgb_matrix", C.c_double * 9), ("ycc_to_rgb_offset", C.c_double * 3), ("rgb_to_lms_matrix", C.c_double * 9)]
+                ("ycc_to_rgb_matrix", C.c_double * 9), ("ycc_to_rgb_offset", C.c_double * 3), ("rgb_to_lms_matrix", C.c_double * 9),
+                ("source_min_pq", C.c_uint16), ("source_max_pq", C.c_uint16), ("ext", OrcDoviExt * 32)]
 
 
 class OrcFmt(C.Structure):

@@ -574,3 +574,17 @@ def test_dolby_vision_is_ignored_for_tagged_hdr10_unless_preferred():
     plain.dovi = H.make_dovi(64, mmr=1)                                   # the product is handed the side data anyway
     _, out = _run_gpu(plain, buf, pitch)
     assert H.compare(out, ref, plain.backbuffer) == (0, 0)
+
+
+@pytest.mark.parametrize("scenario", ["between", "brighter", "dimmer", "equal_targets"])
+def test_dolby_vision_l2_trims(scenario):
+    """Level 2 trims picked / interpolated for the display (Source/DX11VideoProcessor.cpp:2383-2466) and applied in the to-SDR chain
+    (DolbyVisionTrims, Source/Shaders.cpp:787-795).  display = iHdrDisplayMaxNits = 1000 nits -> PQ code ~3079"""
+    lo = (2081, 2100, 2030, 2120, 2010, 2075)       # 100-nit target
+    mid = (2851, 1990, 2060, 2000, 2080, 2020)      # 600-nit target
+    hi = (3388, 2070, 2040, 2090, 2060, 2000)       # 2000-nit target
+    l2 = dict(between=[lo, hi, mid], brighter=[lo, mid], dimmer=[hi], equal_targets=[mid, mid])[scenario]
+    ex = O.exfmt(chroma=5, range_=1, matrix=0, prim=0, trc=0)
+    case = H.Case(O.CF["P010"], 64, 36, 96, 54, ex, up=O.UPSCALE["CatmullRom"], dovi=H.make_dovi(71, mmr=1, l2=l2, source_max_pq=3696),
+                  hdr=dict(out=0, display=1000), name="dovi_l2_" + scenario)
+    _check(case, "natural", 71)

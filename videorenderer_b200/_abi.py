@@ -110,9 +110,14 @@ class DoviCurve(C.Structure):         # mpcvr_dovi_curve (natural C layout)
                 ("mmr_coef", ((C.c_int64 * 7) * 3) * 8)]
 
 
+class DoviExt(C.Structure):
+    _fields_ = [("level", C.c_uint8), ("v", C.c_uint16 * 7)]
+
+
 class DoviMetadata(C.Structure):      # mpcvr_dovi_metadata
     _fields_ = [("coef_log2_denom", C.c_uint8), ("bl_bit_depth", C.c_uint8), ("curves", DoviCurve * 3),
-                ("ycc_to_rgb_matrix", C.c_double * 9), ("ycc_to_rgb_offset", C.c_double * 3), ("rgb_to_lms_matrix", C.c_double * 9)]
+                ("ycc_to_rgb_matrix", C.c_double * 9), ("ycc_to_rgb_offset", C.c_double * 3), ("rgb_to_lms_matrix", C.c_double * 9),
+                ("source_min_pq", C.c_uint16), ("source_max_pq", C.c_uint16), ("ext", DoviExt * 32)]
 
 
 SAMPLE_DEVICE_MEMORY = 0x1

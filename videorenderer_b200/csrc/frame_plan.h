@@ -57,6 +57,9 @@ struct DoviParams {                 // PS_DOVI_CURVE x3 (Source/Shaders.cpp:715-
     int32_t methods[3], mmr_single[3], min_order[3], max_order[3];
     float   mat[3][3];
     int32_t has_mmr;
+    // DolbyConstants (Source/Shaders.cpp:775-786; SetDolbyVisionDynamicParams Source/DX11VideoProcessor.cpp:953-960)
+    int32_t l2_enabled;
+    float   l2_chroma_weight, l2_saturation_gain, l2_slope, l2_offset, l2_power;
 };
 
 struct SurfDesc {                   // a render target / shader resource of the pass chain

@@ -422,10 +422,21 @@ __device__ __forceinline__ f3 convert_color(const ColorParams& P, f3 yuv, const 
             c.z = linear_to_st2084(__fmul_rn(l.z, g), P.r1000);
             if (tr == TRANSFER_HLG_TO_PQ) return c;
         }
-        f3 h;                                                                       // :870-880; x / HABLE_DIV -> x * (1/HABLE_DIV)
-        h.x = __fmul_rn(hable(P, st2084_to_linear(P, sat(c.x), P.lum_scale)), P.hable_rdiv);
-        h.y = __fmul_rn(hable(P, st2084_to_linear(P, sat(c.y), P.lum_scale)), P.hable_rdiv);
-        h.z = __fmul_rn(hable(P, st2084_to_linear(P, sat(c.z), P.lum_scale)), P.hable_rdiv);
+        c.x = sat(c.x); c.y = sat(c.y); c.z = sat(c.z);                              // :870-872
+        if (D && D->l2_enabled) {                                                   // DolbyVisionTrims, :787-795, :873-877
+            c.x = powr(fma_rn(c.x, D->l2_slope, D->l2_offset), D->l2_power);
+            c.y = powr(fma_rn(c.y, D->l2_slope, D->l2_offset), D->l2_power);
+            c.z = powr(fma_rn(c.z, D->l2_slope, D->l2_offset), D->l2_power);
+            const float Y = fma_rn(0.0593f, c.z, fma_rn(0.6780f, c.y, __fmul_rn(0.2627f, c.x)));
+            const float g = __fadd_rn(1.0f, D->l2_chroma_weight);
+            c.x = __fmul_rn(c.x, powr(__fdiv_rn(__fmul_rn(g, c.x), Y), D->l2_saturation_gain));
+            c.y = __fmul_rn(c.y, powr(__fdiv_rn(__fmul_rn(g, c.y), Y), D->l2_saturation_gain));
+            c.z = __fmul_rn(c.z, powr(__fdiv_rn(__fmul_rn(g, c.z), Y), D->l2_saturation_gain));
+        }
+        f3 h;                                                                       // :878-880; x / HABLE_DIV -> x * (1/HABLE_DIV)
+        h.x = __fmul_rn(hable(P, st2084_to_linear(P, c.x, P.lum_scale)), P.hable_rdiv);
+        h.y = __fmul_rn(hable(P, st2084_to_linear(P, c.y, P.lum_scale)), P.hable_rdiv);
+        h.z = __fmul_rn(hable(P, st2084_to_linear(P, c.z, P.lum_scale)), P.hable_rdiv);
         c = mat3_apply(P.gamut, h);                                                 // :881
     }
     c.x = powr(sat(c.x), P.inv_gamma22); c.y = powr(sat(c.y), P.inv_gamma22); c.z = powr(sat(c.z), P.inv_gamma22);   // :917-923

@@ -434,6 +434,47 @@ int32_t CB200VideoProcessor::SetShaderDoviCurves()
             float v = lms2rgb[r][0] * lin[0][i]; v = v + lms2rgb[r][1] * lin[1][i]; v = v + lms2rgb[r][2] * lin[2][i];
             P.mat[r][i] = v;
         }
+    // Level 2 trims for this display (:2383-2466) -> DolbyConstants (:953-960).  Host arithmetic as written there (libm powf);
+    // std::lerp spelled out so that the value does not depend on the C++ library at hand.
+    {
+        auto lerpf = [](float a, float b, float t) {
+            if ((a <= 0 && b >= 0) || (a >= 0 && b <= 0)) return t * b + (1 - t) * a;
+            if (t == 1) return b;
+            const float x = a + t * (b - a);
+            return ((t > 1) == (b > a)) ? (b < x ? x : b) : (b > x ? x : b);
+        };
+        const float PQ_M1 = 2610.f / (4096.f * 4.f), PQ_M2 = 2523.f / 4096.f * 128.f, PQ_C1 = 3424.f / 4096.f,
+                    PQ_C2 = 2413.f / 4096.f * 32.f, PQ_C3 = 2392.f / 4096.f * 32.f;
+        float y = (float)m_iHdrDisplayMaxNits; y /= 10000.0f; y = fmaxf(y, 0.0f); y = powf(y, PQ_M1);
+        y = (PQ_C1 + PQ_C2 * y) / (1.0f + PQ_C3 * y);
+        const float display_pq = powf(y, PQ_M2);
+        int lower = -1, upper = -1; bool present = false; float dl = 1.0f, du = 1.0f;
+        for (int i = 0; i < 32; i++) {
+            if (dv.ext[i].level != 2) continue;
+            present = true;
+            const float t = dv.ext[i].v[0] / 4095.0f;
+            if (t <= display_pq) { const float d = display_pq - t; if (d < dl) { dl = d; lower = i; } }
+            else                 { const float d = t - display_pq; if (d < du) { du = d; upper = i; } }
+        }
+        if (present) {
+            float tv[5] = { 1.0f, 0.0f, 1.0f, 0.0f, 0.0f };                 // slope, offset, power, chroma weight, saturation gain
+            auto clamp01 = [](float w) { return w < 0.0f ? 0.0f : (w > 1.0f ? 1.0f : w); };
+            if (lower != -1 && upper != -1) {
+                const float lp = dv.ext[lower].v[0] / 4095.0f, up = dv.ext[upper].v[0] / 4095.0f;
+                const float w = clamp01((up != lp) ? (display_pq - lp) / (up - lp) : 0.0f);
+                for (int k = 0; k < 5; k++) tv[k] = lerpf((float)dv.ext[lower].v[1 + k], (float)dv.ext[upper].v[1 + k], w);
+            } else if (lower != -1) {
+                const float mp = dv.source_max_pq / 4095.0f, lp = dv.ext[lower].v[0] / 4095.0f;
+                const float w = clamp01((mp > lp) ? (display_pq - lp) / (mp - lp) : 0.0f);
+                for (int k = 0; k < 5; k++) tv[k] = lerpf((float)dv.ext[lower].v[1 + k], 2048.0f, w);
+            } else if (upper != -1) {
+                for (int k = 0; k < 5; k++) tv[k] = (float)dv.ext[upper].v[1 + k];
+            }
+            P.l2_enabled = 1;
+            P.l2_slope = tv[0] / 4096.0f + 0.5f; P.l2_offset = tv[1] / 4096.0f - 0.5f; P.l2_power = tv[2] / 4096.0f + 0.5f;
+            P.l2_chroma_weight = tv[3] / 4096.0f - 0.5f; P.l2_saturation_gain = tv[4] / 4096.0f - 0.5f;
+        }
+    }
     if (m_device >= 0) {
         cudaSetDevice(m_device);
         if (!m_doviDev.ptr) { if (!Cuda(cudaMalloc(&m_doviDev.ptr, sizeof(DoviParams)), "cudaMalloc(dovi)")) return MPCVR_E_FAIL; m_doviDev.n = 1; }
