@@ -1059,6 +1059,7 @@ int32_t CB200VideoProcessor::GetCurentImage(void* host, size_t pitch, int32_t* p
     if (!m_bInit || !m_haveFrame) return Fail(MPCVR_E_UNEXPECTED, "no frame");
     unsigned w = m_srcRectWidth, h = m_srcRectHeight;                          // :3495-3503
     if (m_srcAnamorphic) w = (unsigned)(((int64_t)h * m_srcAspectRatioX + m_srcAspectRatioY / 2) / m_srcAspectRatioY);   // MulDiv rounds to nearest
+    if (m_iRotation == 90 || m_iRotation == 270) std::swap(w, h);               // :3500-3502
     if (pw) *pw = (int32_t)w; if (ph) *ph = (int32_t)h;
     if (!host) return MPCVR_S_OK;                                              // size query
     if (pitch < (size_t)w * 4) return MPCVR_E_INVALIDARG;
