@@ -54,24 +54,75 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks line of B200_PROFILING.md, sampled during the timed region"""
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region (the clocks line of B200_PROFILING.md).
+    NVML is polled from a thread every ~2 ms (a frame kernel lasts 0.2 ms, so a short timed region still gets samples);
+    `nvidia-smi -lms` is the fallback when the NVML binding is missing.  Samples carry host timestamps; only those taken
+    between mark_begin() and mark_end() -- which bracket the synchronised timed loop -- are reported."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         super().__init__(daemon=True)
-        self.gpu = gpu_index; self.samples = []; self.stop_flag = False; self.proc = None
+        self.gpu = gpu_index; self.uuid = uuid; self.samples = []; self.stop_flag = False; self.proc = None
+        self.t_begin = None; self.t_end = None; self.source = None; self.ready = threading.Event()
+
+    def _run_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        h = None
+        if self.uuid:                                   # CUDA_VISIBLE_DEVICES may renumber: address the GPU by UUID
+            try:
+                h = N.nvmlDeviceGetHandleByUUID(self.uuid.encode() if isinstance(self.uuid, str) else self.uuid)
+            except Exception:
+                h = None
+        if h is None:
+            h = N.nvmlDeviceGetHandleByIndex(self.gpu)
+        mx = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(N, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        self.source = "nvml"
+        self.ready.set()
+        while not self.stop_flag:
+            t = time.perf_counter()
+            sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+            r = int(get_reasons(h))
+            self.samples.append((t, sm, mx, {k for k, b in bits.items() if r & b}))
+            time.sleep(0.002)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) >= 9:
+                try:
+                    reasons = {n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]) if v.lower().startswith("active")}
+                    self.samples.append((time.perf_counter(), float(f[1]), float(f[2]), reasons))
+                    self.ready.set()
+                except ValueError:
+                    pass
+            if self.stop_flag:
+                break
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.samples.append(line.strip())
-                if self.stop_flag:
-                    break
+            self._run_nvml()
         except Exception:
-            pass
+            try:
+                self._run_smi()
+            except Exception:
+                pass
+        self.ready.set()
+
+    def wait_ready(self, timeout=5.0):
+        self.ready.wait(timeout)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def finish(self):
         self.stop_flag = True
@@ -80,22 +131,22 @@ class ClockSampler(threading.Thread):
                 self.proc.terminate()
             except Exception:
                 pass
-        sm, mx, reasons = [], [], set()
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        self.join(timeout=1.0)
+        alls = list(self.samples)
+        if not alls:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable (no NVML binding, no nvidia-smi)"], "samples": 0}
+        inside = [s for s in alls if self.t_begin is not None and self.t_end is not None and self.t_begin <= s[0] <= self.t_end]
+        note = None
+        if not inside:      # region shorter than one sampling period: the samples adjacent to it (GPU still warm from the warm-up steps)
+            near = sorted(alls, key=lambda s: abs(s[0] - (self.t_begin or s[0])))[:3]
+            inside = near; note = "timed region shorter than the sampling period: nearest samples"
+        sm = [s[1] for s in inside]; mx = [s[2] for s in inside]
+        reasons = set().union(*[s[3] for s in inside])
         busy = [v for v in sm if v > 0.5 * max(mx)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
+        if note:
+            out["note"] = note
+        return out
 
 
 def host_threads():
@@ -191,7 +242,7 @@ def impl_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="auto", choices=["auto", "multipass", "fused"])
@@ -283,8 +334,16 @@ def main():
         step_device(i)
     launches_per_step = vp.LastFrameKernels()
     plan = vp.debug_plan()
-    sampler = ClockSampler(local); sampler.start(); time.sleep(0.15)
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local, gpu_uuid); sampler.start(); sampler.wait_ready()
+    for i in range(min(args.warmup, 3)):            # keep the GPU busy right up to the timed region (the sampler start may have idled it)
+        step_device(i)
+    sampler.mark_begin()
     ms = timed(step_device, args.steps)
+    sampler.mark_end()
     clocks = sampler.finish()
     fps = streams.aggregate_fps(args.steps, world, ms)
 
