@@ -58,6 +58,29 @@ int orc_scaler_kind(int src, int dst, int bInterpolateAt50pct)
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
 
+/* Level 1 (+ Level 3 offsets) of the Dolby Vision extension blocks -> nits, as CopySample does before feeding
+ * SetHDR10ShaderParams (DX11VideoProcessor.cpp:2347-2381, :2717-2720).  Returns 1 when a Level 1 block exists. */
+int orc_dovi_l1_nits(const orc_dovi* dv, float out_min_max_avg[3])
+{
+    const float PQ_M1 = 2610.f / (4096.f * 4.f), PQ_M2 = 2523.f / 4096.f * 128.f, PQ_C1 = 3424.f / 4096.f,
+                PQ_C2 = 2413.f / 4096.f * 32.f, PQ_C3 = 2392.f / 4096.f * 32.f;
+    for (int i = 0; i < 32; i++) {
+        if (dv->ext[i].level != 1) continue;
+        uint16_t v[3] = { dv->ext[i].v[0], dv->ext[i].v[1], dv->ext[i].v[2] };
+        for (int k = 0; k < 32; k++)
+            if (dv->ext[k].level == 3) { for (int j = 0; j < 3; j++) v[j] = (uint16_t)(v[j] + dv->ext[k].v[j] - 2048); break; }
+        for (int j = 0; j < 3; j++) {
+            float x = v[j] / 4095.f;
+            x = powf(x, 1.0f / PQ_M2);
+            x = fmaxf(x - PQ_C1, 0.0f) / (PQ_C2 - PQ_C3 * x);
+            x = powf(x, 1.0f / PQ_M1);
+            out_min_max_avg[j] = (float)(uint16_t)(unsigned int)(x * 10000.0f);
+        }
+        return 1;
+    }
+    return 0;
+}
+
 int orc_process_dovi(const orc_config* cfg, const void* const planes[3], const int32_t pitches[3],
                      void* out, int32_t out_pitch, orc_debug* dbg, int mode, int threads, const orc_dovi* dovi)
 {

@@ -248,7 +248,8 @@ class Case:
         h = self.hdr or {}
         s.bHdrPassthrough = 1 if h.get("out", 0) else 0
         s.bHdrLocalToneMapping = 1 if h.get("tonemap", 0) else 0
-        s.iHdrLocalToneMappingType = int(h.get("type", 1)); s.iHdrDisplayMaxNits = int(h.get("display", 1000))
+        # "type" is what SetHDR10ShaderParams receives (oracle side); "settings_type" what the user selected, when they differ
+        s.iHdrLocalToneMappingType = int(h.get("settings_type", h.get("type", 1))); s.iHdrDisplayMaxNits = int(h.get("display", 1000))
         return s
 
 
@@ -256,8 +257,16 @@ def run_oracle(case, planes, pitches, mode=O.MODE_SPEC, want_debug=False, thread
     return O.process(case.orc_config(), planes, pitches, mode=mode, want_debug=want_debug, threads=threads, dovi=case.dovi)
 
 
-def make_dovi(seed=0, mmr=0, bits=10, denom=23, l2=None, source_max_pq=3079):
+def make_dovi(seed=0, mmr=0, bits=10, denom=23, l2=None, source_max_pq=3079, l1=None, l3=None):
     d = _make_dovi(seed, mmr, bits, denom)
+    if l1:                                          # (min_pq, max_pq, avg_pq); l3: offsets around 2048
+        d.ext[20].level = 1
+        for k, v in enumerate(l1):
+            d.ext[20].v[k] = int(v)
+    if l3:
+        d.ext[4].level = 3
+        for k, v in enumerate(l3):
+            d.ext[4].v[k] = int(v)
     d.source_min_pq = 62; d.source_max_pq = source_max_pq
     for i, blk in enumerate(l2 or []):              # (target_max_pq, slope, offset, power, chroma_weight, saturation_gain)
         e = d.ext[2 * i + 1]                         # leave gaps: the reference scans all 32 slots by level

@@ -98,6 +98,8 @@ def lib():
         L.orc_process_dovi.restype = C.c_int
         L.orc_process_dovi.argtypes = [C.POINTER(OrcConfig), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_void_p,
                                        C.c_int32, C.POINTER(OrcDebug), C.c_int, C.c_int, C.c_void_p]
+        L.orc_dovi_l1_nits.restype = C.c_int
+        L.orc_dovi_l1_nits.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_process_from_convert.restype = C.c_int
         L.orc_process_from_convert.argtypes = [C.POINTER(OrcConfig), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                                C.POINTER(OrcDebug), C.c_int, C.c_int]

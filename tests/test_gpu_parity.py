@@ -588,3 +588,22 @@ def test_dolby_vision_l2_trims(scenario):
     case = H.Case(O.CF["P010"], 64, 36, 96, 54, ex, up=O.UPSCALE["CatmullRom"], dovi=H.make_dovi(71, mmr=1, l2=l2, source_max_pq=3696),
                   hdr=dict(out=0, display=1000), name="dovi_l2_" + scenario)
     _check(case, "natural", 71)
+
+
+@pytest.mark.parametrize("tm_type,l1", [(1, True), (5, True), (3, False), (6, True)])
+def test_dolby_vision_on_an_hdr_display_with_local_tone_mapping(tm_type, l1):
+    """Dolby Vision -> PQ (no SDR conversion), then ps_hdr10_tonemap fed from Level 1 (+ Level 3) brightness in nits, BT.2390
+    replaced by ST 2094-10 (Source/DX11VideoProcessor.cpp:2716-2720), with the L2 trims bound as cbuffer b1 (:3362-3364)"""
+    import ctypes as C
+    lo = (2081, 2100, 2030, 2120, 2010, 2075); hi = (3388, 2070, 2040, 2090, 2060, 2000)
+    dv = H.make_dovi(81, mmr=2, l2=[lo, hi], source_max_pq=3696, l1=(40, 3300, 1500) if l1 else None, l3=(2040, 2100, 2000) if l1 else None)
+    if l1:
+        nits = (C.c_float * 3)()
+        assert O.lib().orc_dovi_l1_nits(C.addressof(dv), nits) == 1
+        hdr = dict(out=1, tonemap=1, min=nits[0], max=nits[1], cll=nits[1], fall=nits[2], display=600.0, type=6 if tm_type == 5 else tm_type)
+    else:
+        hdr = dict(out=1, tonemap=1, min=50.0, max=1000.0, cll=0.0, fall=0.0, display=600.0, type=tm_type)     # Display-P3 defaults
+    ex = O.exfmt(chroma=5, range_=1, matrix=0, prim=0, trc=0)
+    hdr["settings_type"] = tm_type                            # the user's curve choice; the oracle gets what SetHDR10ShaderParams receives
+    case = H.Case(O.CF["P010"], 64, 36, 96, 54, ex, backbuffer=O.SURF_RGB10A2, up=O.UPSCALE["Lanczos2"], dovi=dv, hdr=hdr, name="dovi_hdr_tm%d" % tm_type)
+    _check(case, "natural", 81)

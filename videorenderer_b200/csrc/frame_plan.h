@@ -17,6 +17,9 @@ enum Transfer : int32_t {           // which body GetShaderConvertColor emits, S
 struct TonemapParams {              // HDRParamsConstantBuffer, Shaders/d3d11/ps_hdr10_tonemap.hlsl:12-21 (after SetHDR10ShaderParams' clamps)
     float min_nits, max_nits, max_cll, max_fall, display;
     int32_t sel;                    // 1 ACES, 2 Reinhard, 3 Habel, 4 Moebius, 5 BT.2390, 6 ST 2094-10
+    // DolbyConstants (cbuffer b1 of ps_hdr10_tonemap.hlsl:23-32), bound when the frame carries Dolby Vision L2 trims
+    int32_t l2_enabled;
+    float   l2_chroma_weight, l2_saturation_gain, l2_slope, l2_offset, l2_power;
 };
 
 struct SrcDesc {                    // the source "texture views" (Source/DX11Helper.h:87-170)

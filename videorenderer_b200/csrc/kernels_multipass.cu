@@ -252,6 +252,16 @@ k_tonemap(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc 
     if (x >= x1 || y >= y1) return;
     const f3 p = surf_load(in, x, y);
     f3 c; c.x = tm::pq2l(P, sat(p.x)); c.y = tm::pq2l(P, sat(p.y)); c.z = tm::pq2l(P, sat(p.z));     // main, :265-336
+    if (T.l2_enabled) {                                                                                // DolbyVisionTrims, :245-263
+        c.x = powr(fma_rn(tm::l2pq(c.x), T.l2_slope, T.l2_offset), T.l2_power);
+        c.y = powr(fma_rn(tm::l2pq(c.y), T.l2_slope, T.l2_offset), T.l2_power);
+        c.z = powr(fma_rn(tm::l2pq(c.z), T.l2_slope, T.l2_offset), T.l2_power);
+        const float Y = tm::dot2020(c);
+        const float g = __fadd_rn(1.0f, T.l2_chroma_weight);
+        c.x = tm::pq2l(P, __fmul_rn(c.x, powr(__fdiv_rn(__fmul_rn(g, c.x), Y), T.l2_saturation_gain)));
+        c.y = tm::pq2l(P, __fmul_rn(c.y, powr(__fdiv_rn(__fmul_rn(g, c.y), Y), T.l2_saturation_gain)));
+        c.z = tm::pq2l(P, __fmul_rn(c.z, powr(__fdiv_rn(__fmul_rn(g, c.z), Y), T.l2_saturation_gain)));
+    }
     f3 o;
     if (T.sel == 5 || T.sel == 6) {
         c = (T.sel == 5) ? tm::bt2390(P, T, c) : tm::st2094(P, T, c);

@@ -475,6 +475,24 @@ int32_t CB200VideoProcessor::SetShaderDoviCurves()
             P.l2_chroma_weight = tv[3] / 4096.0f - 0.5f; P.l2_saturation_gain = tv[4] / 4096.0f - 0.5f;
         }
     }
+    // Level 1 (+ Level 3 offsets) -> nits (:2347-2381): feeds SetHDR10ShaderParams when local tone mapping is on
+    m_doviL1Present = false;
+    for (int i = 0; i < 32 && !m_doviL1Present; i++) {
+        if (dv.ext[i].level != 1) continue;
+        uint16_t v[3] = { dv.ext[i].v[0], dv.ext[i].v[1], dv.ext[i].v[2] };
+        for (int k = 0; k < 32; k++)
+            if (dv.ext[k].level == 3) { for (int j = 0; j < 3; j++) v[j] = (uint16_t)(v[j] + dv.ext[k].v[j] - 2048); break; }
+        const float PQ_M1 = 2610.f / (4096.f * 4.f), PQ_M2 = 2523.f / 4096.f * 128.f, PQ_C1 = 3424.f / 4096.f,
+                    PQ_C2 = 2413.f / 4096.f * 32.f, PQ_C3 = 2392.f / 4096.f * 32.f;
+        for (int j = 0; j < 3; j++) {
+            float x = v[j] / 4095.f;
+            x = powf(x, 1.0f / PQ_M2);
+            x = fmaxf(x - PQ_C1, 0.0f) / (PQ_C2 - PQ_C3 * x);
+            x = powf(x, 1.0f / PQ_M1);
+            m_doviL1Nits[j] = (float)(uint16_t)(unsigned int)(x * 10000.0f);
+        }
+        m_doviL1Present = true;
+    }
     if (m_device >= 0) {
         cudaSetDevice(m_device);
         if (!m_doviDev.ptr) { if (!Cuda(cudaMalloc(&m_doviDev.ptr, sizeof(DoviParams)), "cudaMalloc(dovi)")) return MPCVR_E_FAIL; m_doviDev.n = 1; }
@@ -511,7 +529,7 @@ void CB200VideoProcessor::UpdateHdrState()
 {
     // The part of Render() under "if (m_pDXGISwapChain4)" (:2626-2727); that swap chain exists when
     // bHdrOutput = m_bHdrPassthroughSupport && (m_bHdrPassthrough || m_bHdrLocalToneMapping) && SourceIsHDR() (:1476).
-    if (!(HdrOut() && SourceIsHDR10orHLG())) { m_hdrColorSpaceActive = false; m_bTonemap = false; return; }
+    if (!(HdrOut() && (SourceIsHDR10orHLG() || m_Dovi.bValid))) { m_hdrColorSpaceActive = false; m_bTonemap = false; return; }   // SourceIsHDR(), :1476
     if (!m_hdrColorSpaceActive) {                                             // SetColorSpace1(G2084/P2020) succeeded, :2651-2690
         m_hdrColorSpaceActive = true;
         if (m_hdr10.bValid) m_lastHdr10 = m_hdr10;
@@ -523,10 +541,18 @@ void CB200VideoProcessor::UpdateHdrState()
         if (m_hdr10.MaxMasteringLuminance != m_lastHdr10.MaxMasteringLuminance || m_hdr10.MinMasteringLuminance != m_lastHdr10.MinMasteringLuminance ||
             m_hdr10.MaxCLL != m_lastHdr10.MaxCLL || m_hdr10.MaxFALL != m_lastHdr10.MaxFALL || !m_lastHdr10.bValid) m_lastHdr10 = m_hdr10;
     }
-    if (m_bHdrLocalToneMapping && m_lastHdr10.bValid)                         // :2715-2725 (no Dolby Vision L1 on this path)
+    m_tm.l2_enabled = 0;
+    if (m_bHdrLocalToneMapping && m_Dovi.bValid && m_doviL1Present) {         // :2716-2720: Dolby Vision L1 drives the curve, BT.2390 becomes ST 2094-10
+        SetHDR10ShaderParams(m_doviL1Nits[0], m_doviL1Nits[1], m_doviL1Nits[1], m_doviL1Nits[2], (float)m_iHdrDisplayMaxNits,
+                             m_iHdrLocalToneMappingType == 5 ? 6 : m_iHdrLocalToneMappingType);
+    } else if (m_bHdrLocalToneMapping && m_lastHdr10.bValid) {                // :2721-2725
         SetHDR10ShaderParams((float)m_lastHdr10.MinMasteringLuminance, (float)m_lastHdr10.MaxMasteringLuminance, (float)m_lastHdr10.MaxCLL,
                              (float)m_lastHdr10.MaxFALL, (float)m_iHdrDisplayMaxNits, m_iHdrLocalToneMappingType);
-    else m_bTonemap = false;
+    } else m_bTonemap = false;
+    if (m_bTonemap && m_Dovi.bValid && m_doviHost.l2_enabled) {               // cbuffer b1 = m_pDoViDynamicConstants, :3362-3364
+        m_tm.l2_enabled = 1; m_tm.l2_chroma_weight = m_doviHost.l2_chroma_weight; m_tm.l2_saturation_gain = m_doviHost.l2_saturation_gain;
+        m_tm.l2_slope = m_doviHost.l2_slope; m_tm.l2_offset = m_doviHost.l2_offset; m_tm.l2_power = m_doviHost.l2_power;
+    }
 }
 
 void CB200VideoProcessor::GetVideoSize(int32_t& w, int32_t& h) const

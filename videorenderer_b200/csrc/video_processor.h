@@ -201,6 +201,7 @@ private:
     struct { mpcvr_dovi_metadata msd = {}; bool bValid = false; bool bHasMMR = false; } m_Dovi;
     bool m_bHdrPreferDoVi = false;
     DoviParams m_doviHost = {};
+    bool  m_doviL1Present = false; float m_doviL1Nits[3] = {0, 0, 0};       // m_DoviExtensionMetadata.L1 (min, max, avg) in nits
     DevArray<DoviParams> m_doviDev;
     bool    CheckDoviMetadata(const mpcvr_dovi_metadata* p) const;          // Source/VideoProcessor.cpp:273-297 (curve part)
     int32_t SetShaderDoviCurves();                                          // :990-1141
