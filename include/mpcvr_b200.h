@@ -237,6 +237,14 @@ int32_t mpcvr_set_flip(mpcvr* vp, int32_t flip);              /* horizontal flip
  * bHdrLocalToneMapping pick SHADER_CONVERT_NONE / _TO_PQ (:2948-2950) and the ps_hdr10_tonemap post-scale step
  * (:3359-3367) fed from mpcvr_sample.hdr / .hdr_cll (:2233-2268, :2715-2725). */
 int32_t mpcvr_set_display_hdr(mpcvr* vp, int32_t hdr10_supported);
+/* Path-B correction shaders for RGB-input callers.  In the reference these post-process what the vendor's
+ * D3D11 VideoProcessor blit produced (a YCbCr->RGB conversion that knows neither BT.2020 nor PQ/HLG): m_pPSCorrection is
+ * picked from the stream's colour tags (Source/DX11VideoProcessor.cpp:1893-1931) and drawn after the resize (:3354-3357).
+ * Here the caller states that its RGB samples (RGB32 / r210 / RGB48 ...) come from such a fixed-function converter; the
+ * ext_format of the media type then describes the ORIGINAL stream and selects ps_convert_pq_to_sdr (pq_supported = the
+ * converter handled PQ, ID3D11VideoProcessor IsPqSupported) / ps_fixconvert_pq_to_sdr / ps_fixconvert_hlg_to_sdr /
+ * ps_convert_hlg_to_pq / ps_fix_bt2020 as the reference does.  present = 0 restores the plain RGB path. */
+int32_t mpcvr_set_upstream_converter(mpcvr* vp, int32_t present, int32_t pq_supported);
 void    mpcvr_get_video_size(mpcvr* vp, int32_t* w, int32_t* h);                      /* GetVideoSize */
 void    mpcvr_get_aspect_ratio(mpcvr* vp, int32_t* ax, int32_t* ay);                  /* GetAspectRatio */
 

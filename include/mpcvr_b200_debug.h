@@ -26,6 +26,8 @@ typedef struct mpcvr_plan_info {
     uint32_t src_exfmt;          /* m_srcExFmt.value after SpecifyExtendedFormat                         */
     int32_t src_pitch, src_lines;/* m_srcPitch, m_srcLines                                               */
     int32_t variant;             /* 0 D3D11 shader set, 1 D3D9 shader set (Settings_t::bUseD3D11)        */
+    int32_t correction;          /* m_pPSCorrection: 0 none, 1 convert_pq_to_sdr, 2 fixconvert_pq_to_sdr, 3 fixconvert_hlg_to_sdr,
+                                    4 fix_bt2020, 5 convert_hlg_to_pq                                        */
 } mpcvr_plan_info;
 
 int32_t mpcvr_debug_set_path(mpcvr* vp, int32_t path);

@@ -97,7 +97,13 @@ typedef struct orc_config {
     int32_t  tm_type;
     /* SetRotation / SetFlip (Source/VideoProcessor.h:205-210): 0/90/180/270 clockwise, horizontal flip of the source */
     int32_t  rotation, flip;
+    /* path-B correction shader drawn as a post-scale step on RGB that an upstream fixed-function converter produced
+     * (m_pPSCorrection, DX11VideoProcessor.cpp:1893-1931, :3354-3357): ORC_CORR_* */
+    int32_t  correction;
 } orc_config;
+
+enum { ORC_CORR_NONE = 0, ORC_CORR_CONVERT_PQ_TO_SDR = 1, ORC_CORR_FIXCONVERT_PQ_TO_SDR = 2, ORC_CORR_FIXCONVERT_HLG_TO_SDR = 3,
+       ORC_CORR_FIX_BT2020 = 4, ORC_CORR_CONVERT_HLG_TO_PQ = 5, ORC_CORR_FIX_YCGCO = 6 };
 
 /* Dolby Vision reshaping data of one frame: the fields of MediaSideDataDOVIMetadata (Include/IMediaSideData.h:166-243)
  * that the convert shader consumes (Source/Shaders.cpp:531-589, :703-859; Source/DX11VideoProcessor.cpp:817-834, :990-1141). */

@@ -199,7 +199,7 @@ class Case:
     def __init__(self, cf, w, h, dst_w, dst_h, ex, backbuffer=O.SURF_BGRA8, tex=O.TEXFMT_AUTOINT, chroma=O.CHROMA_Bilinear,
                  up=O.UPSCALE["CatmullRom"], down=O.DOWNSCALE["Hamming"], interp50=1, dither=1, to_sdr=1, nits=125,
                  src_rect=None, dst_rect=None, win=None, variant=O.VARIANT_D3D11, procamp=None, interlaced=0, deint_blend=0,
-                 name=None, bottom_up=0, hdr=None, rotation=0, flip=0, dovi=None):
+                 name=None, bottom_up=0, hdr=None, rotation=0, flip=0, dovi=None, correction=0, upstream_vp=None):
         self.__dict__.update(locals()); del self.__dict__["self"]
         self.name = name or "case"
 
@@ -210,7 +210,7 @@ class Case:
                              up=self.up, down=self.down, interp50=self.interp50, dither=self.dither, to_sdr=self.to_sdr,
                              nits=self.nits, deint_blend=int(bool(self.deint_blend and self.interlaced)),
                              brightness=pa.get("brightness", 0.0), contrast=pa.get("contrast", 1.0), hue=pa.get("hue", 0.0),
-                             saturation=pa.get("saturation", 1.0), variant=self.variant, hdr=self.hdr, rotation=self.rotation, flip=self.flip)
+                             saturation=pa.get("saturation", 1.0), variant=self.variant, hdr=self.hdr, rotation=self.rotation, flip=self.flip, correction=self.correction)
 
     def settings(self):
         import videorenderer_b200 as V
@@ -228,6 +228,8 @@ class Case:
         vp = V.VideoProcessor(self.settings(), device=device)
         if self.hdr:
             vp.SetDisplayHdr(True)
+        if self.upstream_vp:                                   # (present, pq_supported): RGB samples from a fixed-function converter
+            vp.SetUpstreamConverter(*self.upstream_vp)
         mt = V.VideoProcessor.media_type(self.cf, self.w, self.h, self.ex, src_rect=self.src_rect, interlaced=self.interlaced,
                                          bottom_up=self.bottom_up)
         assert vp.InitMediaType(mt), "InitMediaType failed: " + vp.last_error()

@@ -44,7 +44,8 @@ class OrcConfig(C.Structure):
                 ("variant", C.c_int32),
                 ("hdr_out", C.c_int32), ("tonemap", C.c_int32),
                 ("tm_min_nits", C.c_float), ("tm_max_nits", C.c_float), ("tm_max_cll", C.c_float), ("tm_max_fall", C.c_float),
-                ("tm_display_nits", C.c_float), ("tm_type", C.c_int32), ("rotation", C.c_int32), ("flip", C.c_int32)]
+                ("tm_display_nits", C.c_float), ("tm_type", C.c_int32), ("rotation", C.c_int32), ("flip", C.c_int32),
+                ("correction", C.c_int32)]
 
 
 class OrcDebug(C.Structure):
@@ -184,8 +185,9 @@ def make_config(cformat, width, height, dst_w, dst_h, ex, backbuffer=SURF_BGRA8,
                 win=None, tex=TEXFMT_AUTOINT, chroma=CHROMA_Bilinear, up=UPSCALE["CatmullRom"],
                 down=DOWNSCALE["Hamming"], interp50=1, dither=1, to_sdr=1, nits=125, deint_blend=0,
                 brightness=0.0, contrast=1.0, hue=0.0, saturation=1.0, variant=VARIANT_D3D11, hdr=None,
-                rotation=0, flip=0):
+                rotation=0, flip=0, correction=0):
     cfg = OrcConfig()
+    cfg.correction = correction
     cfg.rotation = rotation; cfg.flip = flip
     if hdr:   # dict(out=1, tonemap=0/1, min, max, cll, fall, display, type): SetHDR10ShaderParams' raw arguments
         cfg.hdr_out = int(hdr.get("out", 1)); cfg.tonemap = int(hdr.get("tonemap", 0))

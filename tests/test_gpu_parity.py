@@ -607,3 +607,34 @@ def test_dolby_vision_on_an_hdr_display_with_local_tone_mapping(tm_type, l1):
     hdr["settings_type"] = tm_type                            # the user's curve choice; the oracle gets what SetHDR10ShaderParams receives
     case = H.Case(O.CF["P010"], 64, 36, 96, 54, ex, backbuffer=O.SURF_RGB10A2, up=O.UPSCALE["Lanczos2"], dovi=dv, hdr=hdr, name="dovi_hdr_tm%d" % tm_type)
     _check(case, "natural", 81)
+
+
+# ---- path-B correction shaders as a post-scale step on RGB from an upstream fixed-function converter ----
+EX_PQ_TAGS = O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=15)
+EX_HLG_TAGS = O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=16)
+EX_2020_SDR_TAGS = O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=5)
+
+
+@pytest.mark.parametrize("name,ex,pq,to_sdr,hdr,mode", [
+    ("r210",   EX_PQ_TAGS,       True,  1, None,          1),     # ps_convert_pq_to_sdr
+    ("RGB48",  EX_PQ_TAGS,       False, 1, None,          2),     # ps_fixconvert_pq_to_sdr
+    ("XRGB32", EX_HLG_TAGS,      False, 1, None,          3),     # ps_fixconvert_hlg_to_sdr
+    ("r210",   EX_2020_SDR_TAGS, False, 1, None,          4),     # ps_fix_bt2020
+    ("RGB48",  EX_HLG_TAGS,      False, 0, None,          4),     # HLG shown as SDR: ps_fix_bt2020
+    ("r210",   EX_HLG_TAGS,      False, 1, dict(out=1),   5),     # HDR display: ps_convert_hlg_to_pq
+    ("r210",   EX_PQ_TAGS,       False, 1, dict(out=1),   0),     # HDR display, PQ: passed through
+    ("XRGB32", H.EX_709,         False, 1, None,          0),     # nothing to correct
+])
+def test_correction_shader_selection_and_pixels(name, ex, pq, to_sdr, hdr, mode):
+    """m_pPSCorrection choice (Source/DX11VideoProcessor.cpp:1893-1931) and the shader itself, drawn after the resize (:3354-3357)"""
+    for (dw, dh, tex) in ((96, 54, O.TEXFMT_AUTOINT), (64, 36, O.TEXFMT_16FLOAT)):        # resized / 1:1 with a final pass behind
+        case = H.Case(O.CF[name], 64, 36, dw, dh, ex, up=O.UPSCALE["CatmullRom"], to_sdr=to_sdr, hdr=hdr, tex=tex, correction=mode,
+                      upstream_vp=(True, pq), backbuffer=O.SURF_RGB10A2 if hdr else O.SURF_BGRA8, name="corr%d_%s" % (mode, name))
+        vp = _check(case, "natural", 90 + mode)
+        assert vp.debug_plan().correction == mode
+
+
+def test_correction_needs_the_upstream_converter_flag():
+    plain = H.Case(O.CF["r210"], 64, 36, 96, 54, EX_PQ_TAGS, up=O.UPSCALE["CatmullRom"], name="corr_off")       # tags alone change nothing
+    vp = _check(plain, "natural", 99)
+    assert vp.debug_plan().correction == 0

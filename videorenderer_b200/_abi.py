@@ -138,7 +138,7 @@ class PlanInfo(C.Structure):
     _fields_ = [("internal_fmt", C.c_int32), ("final_pass", C.c_int32), ("scaler_x", C.c_int32), ("scaler_y", C.c_int32),
                 ("filter_x", C.c_int32), ("filter_y", C.c_int32), ("taps_x", C.c_int32), ("taps_y", C.c_int32),
                 ("path", C.c_int32), ("transfer", C.c_int32), ("src_exfmt", C.c_uint32), ("src_pitch", C.c_int32),
-                ("src_lines", C.c_int32), ("variant", C.c_int32)]
+                ("src_lines", C.c_int32), ("variant", C.c_int32), ("correction", C.c_int32)]
 
 
 SUB_RENDER_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, Rect, Rect, Rect, C.c_double,
@@ -170,6 +170,7 @@ SIGNATURES = {
     "mpcvr_set_rotation": (C.c_int32, [vp, C.c_int32]),
     "mpcvr_set_flip": (C.c_int32, [vp, C.c_int32]),
     "mpcvr_set_display_hdr": (C.c_int32, [vp, C.c_int32]),
+    "mpcvr_set_upstream_converter": (C.c_int32, [vp, C.c_int32, C.c_int32]),
     "mpcvr_get_video_size": (None, [vp, P(C.c_int32), P(C.c_int32)]),
     "mpcvr_get_aspect_ratio": (None, [vp, P(C.c_int32), P(C.c_int32)]),
     "mpcvr_get_settings": (None, [vp, P(Settings)]),

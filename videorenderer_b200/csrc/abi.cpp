@@ -70,6 +70,7 @@ void mpcvr_set_video_rect(mpcvr* h, const mpcvr_rect* r) { if (h && r) h->vp.Set
 int32_t mpcvr_set_window_rect(mpcvr* h, const mpcvr_rect* r) { VP_OR(MPCVR_E_POINTER); if (!r) return MPCVR_E_POINTER; GUARD(vp.SetWindowRect(CRect(r->left, r->top, r->right, r->bottom))); }
 int32_t mpcvr_set_rotation(mpcvr* h, int32_t d) { VP_OR(MPCVR_E_POINTER); return vp.SetRotation(d); }
 int32_t mpcvr_set_flip(mpcvr* h, int32_t f)     { VP_OR(MPCVR_E_POINTER); return vp.SetFlip(f != 0); }
+int32_t mpcvr_set_upstream_converter(mpcvr* h, int32_t present, int32_t pq) { VP_OR(MPCVR_E_POINTER); return vp.SetUpstreamConverter(present != 0, pq != 0); }
 int32_t mpcvr_set_display_hdr(mpcvr* h, int32_t s) { VP_OR(MPCVR_E_POINTER); return vp.SetDisplayHdr(s != 0); }
 void mpcvr_get_video_size(mpcvr* h, int32_t* w, int32_t* hh) { if (!h || !w || !hh) return; h->vp.GetVideoSize(*w, *hh); }
 void mpcvr_get_aspect_ratio(mpcvr* h, int32_t* ax, int32_t* ay) { if (!h || !ax || !ay) return; h->vp.GetAspectRatio(*ax, *ay); }

@@ -65,6 +65,17 @@ struct DoviParams {                 // PS_DOVI_CURVE x3 (Source/Shaders.cpp:715-
     float   l2_chroma_weight, l2_saturation_gain, l2_slope, l2_offset, l2_power;
 };
 
+enum Correction : int32_t {         // m_pPSCorrection (Source/DX11VideoProcessor.cpp:1893-1931); the files under Shaders/d3d11/
+    CORR_NONE = 0, CORR_CONVERT_PQ_TO_SDR = 1, CORR_FIXCONVERT_PQ_TO_SDR = 2, CORR_FIXCONVERT_HLG_TO_SDR = 3,
+    CORR_FIX_BT2020 = 4, CORR_CONVERT_HLG_TO_PQ = 5, CORR_FIX_YCGCO = 6,
+};
+struct CorrectionParams {           // compile-time matrices of the correction shaders, folded on the host
+    float fix2020[3][3];            // mul(ycbcr2020nc_rgb, rgb_ycbcr709)           (conv_matrix.hlsl, ps_fix_bt2020.hlsl:10)
+    float fixycgco[3][3];           // mul(ycgco_rgb, rgb_ycbcr709)                 (ps_fix_ycgco.hlsl:6)
+    float gamut[3][3];              // convert_matrix_2020_to_709                   (colorspace_gamut_conversion.hlsl:86-88)
+    int32_t mode;
+};
+
 struct SurfDesc {                   // a render target / shader resource of the pass chain
     void*   ptr;
     int32_t pitch;                  // bytes

@@ -21,6 +21,9 @@ cudaError_t LaunchCopyPass(const SurfDesc& in, const SurfDesc& out, const int32_
 cudaError_t LaunchFinalPass(const SurfDesc& in, const SurfDesc& out, int x0, int y0, int x1, int y1, float Q, cudaStream_t st);
 long long VerifyGammaTable(cudaStream_t st);   // mismatches of table vs direct over every float of [0,1]; -1 = table unusable
 void SetGammaTableEnabled(int on);   // debug: 0 = the 2x PQ kernel evaluates the final pow directly instead of the threshold table
+// path-B correction shader (m_pPSCorrection) over rect, Source/DX11VideoProcessor.cpp:3354-3357
+cudaError_t LaunchCorrectionPass(const SurfDesc& in, const SurfDesc& out, const ColorParams& P, const CorrectionParams& K,
+                                 int x0, int y0, int x1, int y1, cudaStream_t st);
 // UPSCALE_Jinc2: the one-pass 2-D resizer (Shaders/examples/ps_resize_onepass_jinc2.hlsl) from in rect to out rect
 cudaError_t LaunchJinc2Pass(const SurfDesc& in, const SurfDesc& out, int in_l, int in_t, int in_w, int in_h,
                             int out_l, int out_t, int out_w, int out_h, cudaStream_t st);

@@ -244,6 +244,39 @@ __device__ __forceinline__ float curve(const ColorParams& P, const TonemapParams
 }
 }  // namespace tm
 
+// ---------------------------------------------------------------------------------------------
+// Path-B correction shaders as a post-scale step (m_pPSCorrection, Source/DX11VideoProcessor.cpp:3354-3357):
+// ps_convert_pq_to_sdr / ps_fixconvert_pq_to_sdr / ps_fixconvert_hlg_to_sdr / ps_fix_bt2020 / ps_convert_hlg_to_pq / ps_fix_ycgco
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_correction(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc out, const __grid_constant__ ColorParams P,
+             const __grid_constant__ CorrectionParams K, int x0, int y0, int x1, int y1)
+{
+    const int x = x0 + blockIdx.x * blockDim.x + threadIdx.x, y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= x1 || y >= y1) return;
+    f3 c = surf_load(in, x, y);
+    const int mode = K.mode;
+    if (mode == CORR_FIX_YCGCO) { surf_store(out, x, y, mat3_apply(K.fixycgco, c)); return; }
+    if (mode == CORR_FIXCONVERT_PQ_TO_SDR || mode == CORR_FIXCONVERT_HLG_TO_SDR || mode == CORR_FIX_BT2020) c = mat3_apply(K.fix2020, c);
+    if (mode == CORR_FIXCONVERT_HLG_TO_SDR || mode == CORR_CONVERT_HLG_TO_PQ) {                  // HLG to PQ
+        f3 l; l.x = inverse_hlg(P, sat(c.x)); l.y = inverse_hlg(P, sat(c.y)); l.z = inverse_hlg(P, sat(c.z));
+        const float dt = fma_rn(0.0593f, l.z, fma_rn(0.6780f, l.y, __fmul_rn(0.2627f, l.x)));
+        const float g  = powr(__fmul_rn(2000.0f, dt), 0.2f);
+        c.x = linear_to_st2084(__fmul_rn(l.x, g), P.r1000); c.y = linear_to_st2084(__fmul_rn(l.y, g), P.r1000); c.z = linear_to_st2084(__fmul_rn(l.z, g), P.r1000);
+        if (mode == CORR_CONVERT_HLG_TO_PQ) { surf_store(out, x, y, c); return; }
+    }
+    if (mode == CORR_FIX_BT2020) {
+        c.x = powr(sat(c.x), 2.2f); c.y = powr(sat(c.y), 2.2f); c.z = powr(sat(c.z), 2.2f);
+    } else {                                                                                      // PQ to linear, Hable
+        c.x = __fmul_rn(hable(P, st2084_to_linear(P, sat(c.x), P.lum_scale)), P.hable_rdiv);
+        c.y = __fmul_rn(hable(P, st2084_to_linear(P, sat(c.y), P.lum_scale)), P.hable_rdiv);
+        c.z = __fmul_rn(hable(P, st2084_to_linear(P, sat(c.z), P.lum_scale)), P.hable_rdiv);
+    }
+    c = mat3_apply(K.gamut, c);
+    c.x = powr(sat(c.x), P.inv_gamma22); c.y = powr(sat(c.y), P.inv_gamma22); c.z = powr(sat(c.z), P.inv_gamma22);
+    surf_store(out, x, y, c);
+}
+
 __global__ void __launch_bounds__(256)
 k_tonemap(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc out, const __grid_constant__ ColorParams P,
           const __grid_constant__ TonemapParams T, int x0, int y0, int x1, int y1)
@@ -352,6 +385,15 @@ cudaError_t LaunchFinalPass(const SurfDesc& in, const SurfDesc& out, int x0, int
     if (x1 <= x0 || y1 <= y0) return cudaSuccess;
     const dim3 b(32, 8);
     k_final<<<Grid2D(x1 - x0, y1 - y0, b), b, 0, st>>>(in, out, x0, y0, x1, y1, Q);
+    return cudaGetLastError();
+}
+
+cudaError_t LaunchCorrectionPass(const SurfDesc& in, const SurfDesc& out, const ColorParams& P, const CorrectionParams& K,
+                                 int x0, int y0, int x1, int y1, cudaStream_t st)
+{
+    if (x1 <= x0 || y1 <= y0) return cudaSuccess;
+    const dim3 b(32, 8);
+    k_correction<<<Grid2D(x1 - x0, y1 - y0, b), b, 0, st>>>(in, out, P, K, x0, y0, x1, y1);
     return cudaGetLastError();
 }
 

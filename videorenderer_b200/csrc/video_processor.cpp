@@ -144,6 +144,7 @@ int32_t CB200VideoProcessor::InitMediaType(const mpcvr_media_type* mt)
     m_Dovi.bValid = false; m_Dovi.bHasMMR = false;                          // m_Dovi = {} on a new media type
     m_srcRect = CRect(mt->src_rect.left, mt->src_rect.top, mt->src_rect.right, mt->src_rect.bottom);
     m_srcAspectRatioX = mt->aspect_x; m_srcAspectRatioY = mt->aspect_y;
+    m_upstreamExFmt.value = (FmtParams.CSType == CS_RGB) ? mt->ext_format : 0u;   // used only with mpcvr_set_upstream_converter
     if (FmtParams.CSType == CS_YUV && mt->ext_format) {
         // m_decExFmt.value = dwControlFlags; SampleFormat = AMCONTROL_USED | AMCONTROL_COLORINFO_PRESENT  (:1765-1768)
         m_decExFmt.value = (mt->ext_format & ~0xFFu) | 0x3u;
@@ -213,6 +214,7 @@ int32_t CB200VideoProcessor::InitMediaType(const mpcvr_media_type* mt)
     }
     SetShaderConvertColorParams();
     SetShaderLuminanceParams();
+    UpdateCorrection();
     m_bInit = true;
     m_planDirty = true;
     if (m_videoRect.IsRectEmpty()) m_videoRect = CRect(0, 0, (int)m_srcRectWidth, (int)m_srcRectHeight);
@@ -502,13 +504,86 @@ int32_t CB200VideoProcessor::SetShaderDoviCurves()
     return MPCVR_S_OK;
 }
 
+int32_t CB200VideoProcessor::SetUpstreamConverter(bool present, bool pqSupported)
+{
+    m_upstreamVP = present; m_upstreamPq = pqSupported;
+    UpdateCorrection();
+    m_planDirty = true;
+    return MPCVR_S_OK;
+}
+
+void CB200VideoProcessor::UpdateCorrection()
+{
+    // shader choice of InitMediaType, :1893-1931, on the tags of the original stream
+    int mode = CORR_NONE;
+    if (m_upstreamVP && m_srcParams.CSType == CS_RGB && m_upstreamExFmt.value) {
+        const uint32_t trc = m_upstreamExFmt.TransferFunction(), prim = m_upstreamExFmt.Primaries();
+        const bool bTransFunc22 = (trc == Trc_22 || trc == Trc_709 || trc == Trc_240M);
+        if (trc == Trc_2084 && !HdrOut() && m_bConvertToSdr) mode = m_upstreamPq ? CORR_CONVERT_PQ_TO_SDR : CORR_FIXCONVERT_PQ_TO_SDR;
+        else if (trc == Trc_HLG) {
+            if (HdrOut()) mode = CORR_CONVERT_HLG_TO_PQ;
+            else if (m_bConvertToSdr) mode = CORR_FIXCONVERT_HLG_TO_SDR;
+            else if (prim == Prim_BT2020) mode = CORR_FIX_BT2020;                 // HLG compatible with SDR
+        }
+        else if ((bTransFunc22 || !m_bHdrPassthroughSupport) && prim == Prim_BT2020) mode = CORR_FIX_BT2020;
+    }
+    if (mode != CORR_NONE && m_corr.gamut[0][0] == 0.0f) {
+        // `static const` matrices of the shaders: fxc folds them at compile time in double precision (warning X4122 in
+        // colorspace_gamut_conversion.hlsl); evaluated in double in the written order, rounded once to fp32
+        static const double rgb_ycbcr709[3][3] = { { 0.2126, 0.7152, 0.0722 }, { -0.114572, -0.385428, 0.5 }, { 0.5, -0.454153, -0.045847 } };
+        static const double ycbcr2020nc_rgb[3][3] = { { 1.0, 0.0, 1.4746 }, { 1.0, -0.164553, -0.571353 }, { 1.0, 1.8814, 0.0 } };
+        static const double ycgco_rgb[3][3] = { { 1.0, -1.0, 1.0 }, { 1.0, 1.0, 0.0 }, { 1.0, -1.0, -1.0 } };
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                double a = 0, b = 0;
+                for (int k = 0; k < 3; k++) { a += ycbcr2020nc_rgb[i][k] * rgb_ycbcr709[k][j]; b += ycgco_rgb[i][k] * rgb_ycbcr709[k][j]; }
+                m_corr.fix2020[i][j] = (float)a; m_corr.fixycgco[i][j] = (float)b;
+            }
+        // Colorspace_Gamut_Conversion_2020_to_709 (colorspace_gamut_conversion.hlsl:1-93, from zimg)
+        auto det2 = [](double a00, double a01, double a10, double a11) { return a00 * a11 - a01 * a10; };
+        auto inverse = [&](const double X[3][3], double I[3][3]) {
+            double det = 0;
+            det += X[0][0] * det2(X[1][1], X[1][2], X[2][1], X[2][2]);
+            det -= X[0][1] * det2(X[1][0], X[1][2], X[2][0], X[2][2]);
+            det += X[0][2] * det2(X[1][0], X[1][1], X[2][0], X[2][1]);
+            I[0][0] = det2(X[1][1], X[1][2], X[2][1], X[2][2]) / det; I[0][1] = det2(X[0][2], X[0][1], X[2][2], X[2][1]) / det; I[0][2] = det2(X[0][1], X[0][2], X[1][1], X[1][2]) / det;
+            I[1][0] = det2(X[1][2], X[1][0], X[2][2], X[2][0]) / det; I[1][1] = det2(X[0][0], X[0][2], X[2][0], X[2][2]) / det; I[1][2] = det2(X[0][2], X[0][0], X[1][2], X[1][0]) / det;
+            I[2][0] = det2(X[1][0], X[1][1], X[2][0], X[2][1]) / det; I[2][1] = det2(X[0][1], X[0][0], X[2][1], X[2][0]) / det; I[2][2] = det2(X[0][0], X[0][1], X[1][0], X[1][1]) / det;
+        };
+        static const double P709[3][2] = { { 0.640, 0.330 }, { 0.300, 0.600 }, { 0.150, 0.060 } };
+        static const double P2020[3][2] = { { 0.708, 0.292 }, { 0.170, 0.797 }, { 0.131, 0.046 } };
+        const double wx = 0.3127, wy = 0.3290;
+        double M[2][3][3];
+        for (int s2 = 0; s2 < 2; s2++) {
+            const double (*P)[2] = s2 ? P2020 : P709;
+            double X[3][3], I[3][3], S[3];
+            for (int c = 0; c < 3; c++) { X[0][c] = P[c][0] / P[c][1]; X[1][c] = 1.0; X[2][c] = (1.0 - P[c][0] - P[c][1]) / P[c][1]; }
+            const double W[3] = { wx / wy, 1.0, (1.0 - wx - wy) / wy };
+            inverse(X, I);
+            for (int r = 0; r < 3; r++) S[r] = I[r][0] * W[0] + I[r][1] * W[1] + I[r][2] * W[2];
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) M[s2][r][c] = X[r][c] * S[c];
+        }
+        double I709[3][3];
+        inverse(M[0], I709);
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) { double a = 0; for (int k = 0; k < 3; k++) a += I709[r][k] * M[1][k][c]; m_corr.gamut[r][c] = (float)a; }
+    }
+    if (mode != m_corr.mode) { m_corr.mode = mode; m_planDirty = true; }
+}
+
+int32_t CB200VideoProcessor::CorrectionPass(const Tex2D& tex, const Tex2D& rt, const CRect& rect)
+{
+    m_lastLaunches++;
+    return Cuda(LaunchCorrectionPass(tex.desc(), rt.desc(), m_color, m_corr, rect.left, rect.top, rect.right, rect.bottom, m_stream), "correction shader") ? MPCVR_S_OK : MPCVR_E_FAIL;
+}
+
 int32_t CB200VideoProcessor::SetDisplayHdr(bool supported)
 {
     // m_bHdrPassthroughSupport: in the reference it is read from the DXGI output (HDR-capable display + OS HDR mode)
     if (supported == m_bHdrPassthroughSupport) return MPCVR_S_OK;
     m_bHdrPassthroughSupport = supported;
     m_hdrColorSpaceActive = false; m_bTonemap = false; m_lastHdr10 = Hdr10();
-    if (m_bInit) SetShaderConvertColorParams();
+    if (m_bInit) { SetShaderConvertColorParams(); UpdateCorrection(); }
     m_planDirty = true;
     return MPCVR_S_OK;
 }
@@ -576,6 +651,7 @@ void CB200VideoProcessor::Configure(const mpcvr_settings& s)
     if (oldTex != m_iTexFormat) { UpdateTexParams(m_srcParams.CDepth); UpdateTexures(); }
     if (oldSdr != m_bConvertToSdr || oldHdrOut != HdrOut()) SetShaderConvertColorParams();
     if (!HdrOut()) { m_hdrColorSpaceActive = false; m_bTonemap = false; }
+    UpdateCorrection();
     if (oldNits != m_iSDRDisplayNits) SetShaderLuminanceParams();
     UpdatePostScaleTexures();
     m_planDirty = true;
@@ -1017,7 +1093,8 @@ int32_t CB200VideoProcessor::Process(const Tex2D& target, const CRect& srcRect, 
         pInputTexture = &m_TexSrcUnpacked; rSrc = m_srcRect;
     } else if (!skipConvert) { hr = ConvertColorPass(m_TexConvertOutput); if (hr != MPCVR_S_OK) return hr; }
 
-    const int numSteps = (m_bTonemap ? 1 : 0) + (m_bFinalPass ? 1 : 0);       // GetPostScaleSteps, :779-795
+    const bool correction = m_corr.mode != CORR_NONE;
+    const int numSteps = (correction ? 1 : 0) + (m_bTonemap ? 1 : 0) + (m_bFinalPass ? 1 : 0);   // GetPostScaleSteps, :779-795
     if (numSteps) {                                                           // :3325-3416
         if (!Cuda(m_TexsPostScale.CheckCreate(m_InternalTexFmt, target.w, target.h), "m_TexsPostScale")) return MPCVR_E_FAIL;
         if (numSteps > 1 && !Cuda(m_TexsPostScale2.CheckCreate(m_InternalTexFmt, target.w, target.h), "m_TexsPostScale[1]")) return MPCVR_E_FAIL;
@@ -1025,8 +1102,18 @@ int32_t CB200VideoProcessor::Process(const Tex2D& target, const CRect& srcRect, 
         CRect rect; rect.IntersectRect(dstRect, CRect(0, 0, pTex->w, pTex->h));
         if (rSrc != dstRect || m_iRotation != 0) { hr = ResizeShaderPass(*pInputTexture, *pTex, rSrc, dstRect); if (hr != MPCVR_S_OK) return hr; }
         else pTex = pInputTexture;                                            // "Hmm", :3351 (a flip alone is lost here, as in the reference)
-        if (m_bTonemap) {                                                     // StepSetting(); :3359-3367
-            const Tex2D& rt = m_bFinalPass ? m_TexsPostScale2 : target;
+        // StepSetting(), :3330-3339: ping-pong through the two-texture ring, the last step writes the back buffer
+        int stepsLeft = numSteps;
+        const Tex2D* ring[2] = { &m_TexsPostScale, &m_TexsPostScale2 };
+        int next = (pTex == &m_TexsPostScale) ? 1 : 0;
+        auto stepTarget = [&]() -> const Tex2D& { const Tex2D& rt = (--stepsLeft == 0) ? target : *ring[next]; next ^= 1; return rt; };
+        if (correction) {                                                     // :3354-3357
+            const Tex2D& rt = stepTarget();
+            hr = CorrectionPass(*pTex, rt, rect); if (hr != MPCVR_S_OK) return hr;
+            pTex = &rt;
+        }
+        if (m_bTonemap) {                                                     // :3359-3367
+            const Tex2D& rt = stepTarget();
             hr = TonemapPass(*pTex, rt, rect); if (hr != MPCVR_S_OK) return hr;
             pTex = &rt;
         }
@@ -1045,6 +1132,7 @@ bool CB200VideoProcessor::PlanFused(const Tex2D& target, const CRect& dstRect, F
     if (!m_PSConvColorData.enable) { if (why) *why = "no convert pass on this plan (RGB source, default ProcAmp): multipass only"; return false; }
     if (m_bTonemap) { if (why) *why = "HDR10 tone-map post-scale step: multipass only"; return false; }
     if (m_oriented) { if (why) *why = "rotation / flip: multipass only"; return false; }
+    if (m_corr.mode != CORR_NONE) { if (why) *why = "correction shader step: multipass only"; return false; }
     if (m_Dovi.bValid) { if (why) *why = "Dolby Vision reshaping: multipass only"; return false; }
     if (m_jincX || m_jincY) { if (why) *why = "Jinc2: multipass only"; return false; }
     fp.src = m_src; fp.color = m_color;
@@ -1174,7 +1262,7 @@ int32_t CB200VideoProcessor::DebugGetPlan(mpcvr_plan_info* info)
     if (hr != MPCVR_S_OK) return hr;
     memset(info, 0, sizeof(*info));
     info->internal_fmt = m_InternalTexFmt; info->final_pass = m_bFinalPass;
-    info->scaler_x = m_kx; info->scaler_y = m_ky;
+    info->scaler_x = m_kx; info->scaler_y = m_ky; info->correction = m_corr.mode;
     info->filter_x = m_axisX.host.filter; info->filter_y = m_axisY.host.filter;
     info->taps_x = m_axisX.host.ntaps; info->taps_y = m_axisY.host.ntaps;
     info->path = m_path; info->transfer = m_color.transfer; info->src_exfmt = m_srcExFmt.value;

@@ -93,6 +93,7 @@ public:
     int32_t SetRotation(int v);
     int32_t SetFlip(bool v);
     int32_t SetDisplayHdr(bool supported);
+    int32_t SetUpstreamConverter(bool present, bool pqSupported);
     void    GetVideoSize(int32_t& w, int32_t& h) const;
     void    GetAspectRatio(int32_t& ax, int32_t& ay) const;
 
@@ -205,6 +206,13 @@ private:
     DevArray<DoviParams> m_doviDev;
     bool    CheckDoviMetadata(const mpcvr_dovi_metadata* p) const;          // Source/VideoProcessor.cpp:273-297 (curve part)
     int32_t SetShaderDoviCurves();                                          // :990-1141
+
+    // path-B correction step (m_pPSCorrection): the caller's RGB samples come from a fixed-function YCbCr->RGB converter
+    bool m_upstreamVP = false, m_upstreamPq = false;
+    ExtendedFormat m_upstreamExFmt;              // colour tags of the ORIGINAL stream (the RGB media type itself is untagged)
+    CorrectionParams m_corr = {};                // .mode = the shader picked by UpdateCorrection (:1893-1931)
+    void    UpdateCorrection();
+    int32_t CorrectionPass(const Tex2D& tex, const Tex2D& rt, const CRect& rect);
 
     ColorTransform m_PSConvColorData = {};
     ColorParams    m_color = {};

@@ -92,6 +92,9 @@ class VideoProcessor:
     def SetFlip(self, flip):
         return self._L.mpcvr_set_flip(self._h, int(flip))
 
+    def SetUpstreamConverter(self, present, pq_supported=False):
+        return self._L.mpcvr_set_upstream_converter(self._h, int(bool(present)), int(bool(pq_supported)))
+
     def SetDisplayHdr(self, supported):
         return self._L.mpcvr_set_display_hdr(self._h, int(bool(supported)))
 
