@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "4K frames/s (P010->RGB8, Lanczos3 2x, PQ->SDR)"
+METRIC = "4K frames/s (P010\u2192RGB8, Lanczos3 2\u00d7, PQ\u2192SDR)"    # BASELINE.json "metric", first clause (the second, HBM GB/s vs roofline, is the roofline object)
 UNIT = "frames/s"
 WORKLOAD = "C2: 3840x2160 P010 BT.2020 PQ -> 7680x4320 BGRA8, Lanczos3 2x, PQ->SDR 125nit, bilinear chroma, ordered dither"
 SRC_W, SRC_H, DST_W, DST_H = 3840, 2160, 7680, 4320
