@@ -389,7 +389,10 @@ def main():
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams": "one independent stream per GPU, no collective",
+            "config": {"workload": WORKLOAD,
+                       "baseline_config": ("configs[1]: 4K P010\u2192RGB8 BT.2020 PQ\u2192SDR, Lanczos3 2\u00d7 upscale, ordered dither, 1 GPU" if world == 1 else
+                                           "configs[4] at N=%d: independent 4K P010 streams, Lanczos3 2\u00d7 + PQ\u2192SDR, one per GPU" % world),
+                       "streams": "one independent stream per GPU, no collective",
                        "path": {V.PATH.FUSED: "fused", V.PATH.MULTIPASS: "multipass"}.get(plan.path, "?"),
                        "l2": "8 distinct input frames cycled (199 MB) and a 133 MB output per frame: working set exceeds the 126 MB L2, no explicit flush",
                        "parity": "bit-exact vs oracle SPEC mode (tests -m gpu)"},
