@@ -111,3 +111,44 @@ def test_subtitle_callback_sees_the_frame_on_its_stream():
     ptr, bpitch, w, h, f = vp.GetBackbuffer()
     assert target == ptr and tpitch == bpitch and fmt == f and stream == vp.GetStream()
     assert devs == [0]
+
+
+def test_midstream_changes_rebuild_the_plan():
+    """one instance, one frame, a sequence of Configure / rect / ProcAmp / rotation / format changes (Source/DX11VideoProcessor.cpp:3800-4050,
+    SetVideoRect, SetProcAmpValues, SetRotation): after each change Render() must equal the oracle configured from scratch"""
+    base = dict(cf=O.CF["P010"], w=64, h=36, ex=H.EX_2020_PQ)
+    frame_case = H.Case(base["cf"], 64, 36, 128, 72, base["ex"], up=O.UPSCALE["Lanczos3"])
+    buf, pitch, planes, pitches = _frame(frame_case, "natural", 7)
+    vp = frame_case.make_processor(device=0)
+    vp.ProcessSample(data=buf, pitch=pitch)
+
+    def expect(**kw):
+        c = H.Case(base["cf"], 64, 36, kw.pop("dw", 128), kw.pop("dh", 72), base["ex"], **kw)
+        return H.run_oracle(c, planes, pitches), c.backbuffer
+
+    def check(tag, **kw):
+        vp.Render(1, 0)
+        ref, fmt = expect(**kw)
+        assert H.compare(vp.ReadBackbuffer(), ref, fmt) == (0, 0), tag
+
+    check("initial", up=O.UPSCALE["Lanczos3"])
+    s = vp.GetSettings(); s.iUpscaling = O.UPSCALE["CatmullRom"]; vp.Configure(s)
+    check("upscaler", up=O.UPSCALE["CatmullRom"])
+    s.iSDRDisplayNits = 200; s.bUseDither = 0; vp.Configure(s)
+    check("nits+dither", up=O.UPSCALE["CatmullRom"], nits=200, dither=0)
+    s.iTexFormat = O.TEXFMT_16FLOAT; s.bUseDither = 1; vp.Configure(s)
+    check("texfmt", up=O.UPSCALE["CatmullRom"], nits=200, tex=O.TEXFMT_16FLOAT)
+    vp.SetProcAmpValues(brightness=8.0, contrast=1.15, hue=10.0, saturation=0.9)
+    pa = dict(brightness=8.0, contrast=1.15, hue=10.0, saturation=0.9)
+    check("procamp", up=O.UPSCALE["CatmullRom"], nits=200, tex=O.TEXFMT_16FLOAT, procamp=pa)
+    vp.SetWindowRect((0, 0, 100, 80)); vp.SetVideoRect((5, 10, 95, 61))
+    check("rects", dw=100, dh=80, win=(100, 80), dst_rect=(5, 10, 95, 61), up=O.UPSCALE["CatmullRom"], nits=200, tex=O.TEXFMT_16FLOAT, procamp=pa)
+    s.bConvertToSdr = 0; vp.Configure(s)
+    check("no sdr", dw=100, dh=80, win=(100, 80), dst_rect=(5, 10, 95, 61), up=O.UPSCALE["CatmullRom"], nits=200, tex=O.TEXFMT_16FLOAT, procamp=pa, to_sdr=0)
+    vp.SetRotation(180); vp.SetFlip(True)
+    check("turned", dw=100, dh=80, win=(100, 80), dst_rect=(5, 10, 95, 61), up=O.UPSCALE["CatmullRom"], nits=200, tex=O.TEXFMT_16FLOAT, procamp=pa, to_sdr=0,
+          rotation=180, flip=1)
+    vp.SetRotation(0); vp.SetFlip(False); vp.SetBackbufferFormat(O.SURF_RGB10A2)
+    s.iDownscaling = O.DOWNSCALE["Lanczos"]; vp.Configure(s); vp.SetWindowRect((0, 0, 40, 20)); vp.SetVideoRect((0, 0, 40, 20))
+    check("downscale to 10 bit", dw=40, dh=20, backbuffer=O.SURF_RGB10A2, down=O.DOWNSCALE["Lanczos"], up=O.UPSCALE["CatmullRom"], nits=200,
+          tex=O.TEXFMT_16FLOAT, procamp=pa, to_sdr=0)
