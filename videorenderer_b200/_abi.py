@@ -6,7 +6,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path():
-    return os.path.join(_HERE, "libmpcvr_b200.so")
+    # MPCVR_B200_LIB: developer override used by tools/sweep_threads.sh to compare kernel variants; unset in normal use
+    return os.environ.get("MPCVR_B200_LIB") or os.path.join(_HERE, "libmpcvr_b200.so")
 
 
 class MpcvrError(RuntimeError):
