@@ -214,7 +214,7 @@ def impl_reference(args, rank, world):
     t0 = time.time(); H.run_oracle(case, planes, pitches, threads=cores); t_full = time.time() - t0          # warm-up + cost probe
     # each step is a bounded sample sized so that the K timed steps end within ~2 minutes: whole frames when they fit, otherwise a
     # band of source rows (never fewer than 135 rows = 270 output rows, so the OpenMP row loop still feeds every host thread)
-    budget_per_step = 120.0 / max(1, args.steps)
+    budget_per_step = args.ref_seconds / max(1, args.steps)
     if t_full <= budget_per_step:
         run, frac = (lambda: H.run_oracle(case, planes, pitches, threads=cores)), 1.0
         sample = "each step = one full C2 frame; CPU port of the reference shaders (oracle, SPEC arithmetic), %d OpenMP threads" % cores
@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-seconds", type=float, default=120.0, help="--impl reference: wall-clock target of the K timed steps")
     ap.add_argument("--path", default="auto", choices=["auto", "multipass", "fused"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
