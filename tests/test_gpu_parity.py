@@ -638,3 +638,58 @@ def test_correction_needs_the_upstream_converter_flag():
     plain = H.Case(O.CF["r210"], 64, 36, 96, 54, EX_PQ_TAGS, up=O.UPSCALE["CatmullRom"], name="corr_off")       # tags alone change nothing
     vp = _check(plain, "natural", 99)
     assert vp.debug_plan().correction == 0
+
+
+# ---- seeded fuzz over whole plans: formats x sizes x rects x settings x orientation, every kernel family vs the oracle ----
+def _random_case(rng, i):
+    yuv = ["NV12", "P010", "P016", "YUY2", "UYVY", "P210", "Y210", "V210", "AYUV", "Y410", "Y416", "YV12", "YV16", "YV24", "YUV420P10", "YUV422P16", "YUV444P10"]
+    rgb = ["RGB24", "XRGB32", "r210", "RGB48", "BGR48", "BGRA64", "B64A", "GBRP8", "GBRP10", "GBRP16", "Y8", "Y10", "Y16"]
+    name = str(rng.choice(yuv if rng.random() < 0.7 else rgb))
+    is_yuv = name in yuv
+    w = int(rng.integers(4, 80)) * 2; h = int(rng.integers(4, 60)) * 2
+    exs = [H.EX_709, H.EX_2020_PQ, H.EX_2020_HLG, H.EX_2020_SDR, O.exfmt(chroma=1, range_=1, matrix=2, prim=5, trc=4), O.exfmt(chroma=7, range_=2, matrix=7, prim=2, trc=5)]
+    ex = exs[int(rng.integers(0, len(exs)))] if is_yuv else 0
+    # source rect: whole frame or an even-aligned crop
+    src_rect = None
+    if rng.random() < 0.4:
+        l = int(rng.integers(0, w // 4)) * 2; t = int(rng.integers(0, h // 4)) * 2
+        r = w - int(rng.integers(0, w // 4)) * 2; b = h - int(rng.integers(0, h // 4)) * 2
+        if r - l >= 4 and b - t >= 4:
+            src_rect = (l, t, r, b)
+    sw, sh = (src_rect[2] - src_rect[0], src_rect[3] - src_rect[1]) if src_rect else (w, h)
+    rot = int(rng.choice([0, 0, 0, 90, 180, 270])); flip = int(rng.random() < 0.15)
+    up = str(rng.choice(["Nearest", "Mitchell", "CatmullRom", "Lanczos2", "Lanczos3", "Jinc2"]))
+    if (rot or flip) and up == "Jinc2":
+        up = "Lanczos2"
+    mode = rng.random()
+    tw, th = (sh, sw) if rot in (90, 270) else (sw, sh)
+    if mode < 0.2:
+        dw, dh = tw, th
+    elif mode < 0.4:
+        dw, dh = 2 * tw, 2 * th
+    else:
+        dw = max(2, int(tw * rng.uniform(0.3, 2.6))); dh = max(2, int(th * rng.uniform(0.3, 2.6)))
+    win = (dw + int(rng.integers(0, 20)), dh + int(rng.integers(0, 20)))
+    ox, oy = int(rng.integers(-6, win[0] - dw + 7)), int(rng.integers(-6, win[1] - dh + 7))
+    dst_rect = (ox, oy, ox + dw, oy + dh) if rng.random() < 0.5 else (0, 0, dw, dh)
+    if dst_rect == (0, 0, dw, dh):
+        win = (dw, dh)
+    tex = int(rng.choice([O.TEXFMT_AUTOINT, O.TEXFMT_8INT, O.TEXFMT_10INT, O.TEXFMT_16FLOAT]))
+    bb = int(rng.choice([O.SURF_BGRA8, O.SURF_BGRA8, O.SURF_RGB10A2, O.SURF_RGBA16F]))
+    procamp = dict(brightness=float(rng.uniform(-20, 20)), contrast=float(rng.uniform(0.7, 1.3)), hue=float(rng.uniform(-30, 30)),
+                   saturation=float(rng.uniform(0.6, 1.4))) if rng.random() < 0.3 else None
+    return H.Case(O.CF[name], w, h, dw, dh, ex, backbuffer=bb, tex=tex, chroma=int(rng.integers(0, 3)), up=O.UPSCALE[up],
+                  down=int(rng.integers(0, 6)), interp50=int(rng.random() < 0.7), dither=int(rng.random() < 0.7), to_sdr=int(rng.random() < 0.8),
+                  nits=int(rng.integers(5, 80)) * 5, src_rect=src_rect, dst_rect=dst_rect, win=win, variant=int(rng.random() < 0.2), procamp=procamp,
+                  rotation=rot, flip=flip, name="fuzz%d_%s" % (i, name))
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_fuzzed_plans(block):
+    rng = np.random.Generator(np.random.PCG64(1000 + block))
+    for i in range(20):
+        case = _random_case(rng, 20 * block + i)
+        try:
+            _check(case, str(rng.choice(["fullnoise", "natural", "ramp"])), seed=3000 + 20 * block + i)
+        except AssertionError as e:
+            raise AssertionError("%s  [%s]" % (e, {k: v for k, v in case.__dict__.items() if k not in ("dovi", "hdr")}))
