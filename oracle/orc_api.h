@@ -55,7 +55,7 @@ int orc_scaler_kind(int src, int dst, int bInterpolateAt50pct);
 /* per-axis resize weights for one output index, returns tap count; base = first source texel index.
  * kind/filter as above; origin = srcRect.left/top; used by tests to pin KATs. */
 int orc_axis_taps(int kind, int filter, int variant, int src_origin, int src_len, int dst_len,
-                  int i, int* base, float* weights /* >= 256 */, float* wsum);
+                  int i, int* base, float* weights /* >= 1024 */, float* wsum);
 
 /* ---- the pass chain ---- */
 /* planes[]/pitches[] as the DX11 texture views see them:

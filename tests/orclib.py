@@ -244,6 +244,6 @@ def process(cfg, planes, pitches, mode=MODE_SPEC, threads=0, want_debug=False, f
 
 
 def axis_taps(kind, filt, variant, origin, src_len, dst_len, i):
-    base = C.c_int(); wsum = C.c_float(); w = np.zeros(256, np.float32)
+    base = C.c_int(); wsum = C.c_float(); w = np.zeros(1024, np.float32)
     n = lib().orc_axis_taps(kind, filt, variant, origin, src_len, dst_len, i, C.byref(base), w.ctypes.data, C.byref(wsum))
     return base.value, w[:max(n, 0)].copy(), wsum.value, n

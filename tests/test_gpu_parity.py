@@ -693,3 +693,9 @@ def test_fuzzed_plans(block):
             _check(case, str(rng.choice(["fullnoise", "natural", "ramp"])), seed=3000 + 20 * block + i)
         except AssertionError as e:
             raise AssertionError("%s  [%s]" % (e, {k: v for k, v in case.__dict__.items() if k not in ("dovi", "hdr")}))
+
+
+def test_extreme_downscale_long_convolutions():
+    """hundreds of taps per output (the convolution support grows with the ratio): table-driven passes, no tap limit in practice"""
+    _check(H.Case(O.CF["NV12"], 2048, 64, 16, 8, H.EX_709, down=O.DOWNSCALE["Lanczos"], name="down128x"), "natural", 101)
+    _check(H.Case(O.CF["NV12"], 64, 1024, 40, 6, H.EX_709, down=O.DOWNSCALE["Bicubic"], name="down170y"), "fullnoise", 102)

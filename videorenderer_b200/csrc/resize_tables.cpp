@@ -159,7 +159,7 @@ bool BuildAxisTable(int kind, int filter, bool d3d9_variant, int src0, int src_l
         counts[i] = (int)ceilf(pos + support) - lows[i];
         if (counts[i] > nt) nt = counts[i];
     }
-    if (nt > 256) return false;
+    if (nt > 1024) return false;                                 // 340x reduction with the widest filter; beyond that E_NOTIMPL
     T.ntaps = nt; T.w.assign((size_t)dst_len * nt, 0.f); T.wsum.resize(dst_len);
     for (int i = 0; i < dst_len; i++) {
         const float c = coord(i);

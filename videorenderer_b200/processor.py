@@ -236,8 +236,8 @@ class VideoProcessor:
         return m, c, g, lum.value
 
     def debug_axis_taps(self, axis, i):
-        base = C.c_int32(); wsum = C.c_float(); w = np.zeros(256, np.float32)
-        n = self._check(self._L.mpcvr_debug_axis_taps(self._h, axis, i, C.byref(base), w.ctypes.data, 256, C.byref(wsum)), "debug_axis_taps")
+        base = C.c_int32(); wsum = C.c_float(); w = np.zeros(1024, np.float32)
+        n = self._check(self._L.mpcvr_debug_axis_taps(self._h, axis, i, C.byref(base), w.ctypes.data, 1024, C.byref(wsum)), "debug_axis_taps")
         return base.value, w[:n].copy(), wsum.value
 
     def debug_capture_f32(self, enable=True):
