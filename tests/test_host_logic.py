@@ -201,3 +201,26 @@ def test_hdr_output_picks_the_convert_type():
     assert vp.debug_plan().transfer == 0
     vp.SetDisplayHdr(False)
     assert vp.debug_plan().transfer == 1
+
+
+def test_correction_shader_choice_follows_the_reference_rules():
+    """m_pPSCorrection: D3D11 rule (Source/DX11VideoProcessor.cpp:1893-1931) and its D3D9 twin (Source/DX9VideoProcessor.cpp:1225-1238)"""
+    pq = V.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=15); hlg = V.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=16)
+    sdr2020 = V.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=5); sdr709 = V.exfmt(chroma=5, range_=2, matrix=1, prim=2, trc=5)
+
+    def mode(ex, upstream=(True, False), d3d11=1, to_sdr=1, hdr_display=False, passthrough=1):
+        vp = V.VideoProcessor(device=-1)
+        s = vp.GetSettings(); s.bUseD3D11 = d3d11; s.bConvertToSdr = to_sdr; s.bHdrPassthrough = passthrough; vp.Configure(s)
+        vp.SetDisplayHdr(hdr_display)
+        if upstream:
+            vp.SetUpstreamConverter(*upstream)
+        assert vp.InitMediaType(V.VideoProcessor.media_type(V.CF.r210, 64, 64, ex))
+        return vp.debug_plan().correction
+
+    assert mode(pq, upstream=None) == 0 and mode(sdr709) == 0
+    assert mode(pq, upstream=(True, True)) == 1 and mode(pq) == 2 and mode(hlg) == 3 and mode(sdr2020) == 4
+    assert mode(hlg, to_sdr=0) == 4 and mode(pq, to_sdr=0) == 4          # !bTransFunc22, no HDR display, BT.2020 primaries
+    assert mode(hlg, hdr_display=True) == 5 and mode(pq, hdr_display=True) == 0
+    assert mode(pq, hdr_display=True, passthrough=0) == 2                  # HDR display but neither passthrough nor local tone mapping
+    assert mode(pq, d3d11=0, upstream=(True, True)) == 2 and mode(hlg, d3d11=0) == 3 and mode(sdr2020, d3d11=0) == 4
+    assert mode(pq, d3d11=0, to_sdr=0) == 4 and mode(sdr709, d3d11=0) == 0

@@ -519,7 +519,12 @@ void CB200VideoProcessor::UpdateCorrection()
     if (m_upstreamVP && m_srcParams.CSType == CS_RGB && m_upstreamExFmt.value) {
         const uint32_t trc = m_upstreamExFmt.TransferFunction(), prim = m_upstreamExFmt.Primaries();
         const bool bTransFunc22 = (trc == Trc_22 || trc == Trc_709 || trc == Trc_240M);
-        if (trc == Trc_2084 && !HdrOut() && m_bConvertToSdr) mode = m_upstreamPq ? CORR_CONVERT_PQ_TO_SDR : CORR_FIXCONVERT_PQ_TO_SDR;
+        if (!m_bUseD3D11) {                                   // the D3D9 twin's rule, Source/DX9VideoProcessor.cpp:1225-1238
+            if (trc == Trc_2084 && m_bConvertToSdr) mode = CORR_FIXCONVERT_PQ_TO_SDR;
+            else if (trc == Trc_HLG && m_bConvertToSdr) mode = CORR_FIXCONVERT_HLG_TO_SDR;
+            else if (prim == Prim_BT2020) mode = CORR_FIX_BT2020;
+        }
+        else if (trc == Trc_2084 && !HdrOut() && m_bConvertToSdr) mode = m_upstreamPq ? CORR_CONVERT_PQ_TO_SDR : CORR_FIXCONVERT_PQ_TO_SDR;
         else if (trc == Trc_HLG) {
             if (HdrOut()) mode = CORR_CONVERT_HLG_TO_PQ;
             else if (m_bConvertToSdr) mode = CORR_FIXCONVERT_HLG_TO_SDR;
