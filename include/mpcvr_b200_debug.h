@@ -35,6 +35,8 @@ int32_t mpcvr_debug_get_plan(mpcvr* vp, mpcvr_plan_info* info);
 /* PS_COLOR_TRANSFORM cm_r,cm_g,cm_b (row-major 3x3) + cm_c, and matrix_conv_prim */
 /* process-wide: 1 (default) lets the fused 2x PQ kernel use the gamma+UNORM10 threshold table, 0 forces the direct pow */
 int32_t mpcvr_debug_set_gamma_table(int32_t enable);
+/* process-wide: 1 (default) runs the multipass ConvertColorPass two pixels per thread in the packed-fp32 lanes, 0 one pixel per thread */
+int32_t mpcvr_debug_set_convert_two_lane(int32_t enable);
 /* exhaustive check of that table against the direct evaluation over every float in [0,1] on the instance's device:
  * returns the number of mismatching floats (0 expected), -1 if the table was found unusable, -2 on a CUDA error */
 int64_t mpcvr_debug_verify_gamma_table(mpcvr* vp);

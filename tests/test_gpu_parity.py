@@ -699,3 +699,26 @@ def test_extreme_downscale_long_convolutions():
     """hundreds of taps per output (the convolution support grows with the ratio): table-driven passes, no tap limit in practice"""
     _check(H.Case(O.CF["NV12"], 2048, 64, 16, 8, H.EX_709, down=O.DOWNSCALE["Lanczos"], name="down128x"), "natural", 101)
     _check(H.Case(O.CF["NV12"], 64, 1024, 40, 6, H.EX_709, down=O.DOWNSCALE["Bicubic"], name="down170y"), "fullnoise", 102)
+
+
+def test_convert_pass_two_lane_equals_scalar():
+    """k_convert2 (two pixels per thread in the packed-fp32 lanes) against k_convert, every transfer chain, odd widths"""
+    import videorenderer_b200 as V
+    exs = [H.EX_709, H.EX_2020_PQ, H.EX_2020_HLG, H.EX_2020_SDR, O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=14)]
+    try:
+        for i, ex in enumerate(exs):
+            for hdr in (None, dict(out=1)):
+                case = H.Case(O.CF["P010"], 66, 34, 66, 34, ex, up=O.UPSCALE["Nearest"], src_rect=(2, 0, 65, 33), dst_rect=(0, 0, 63, 33), win=(63, 33),
+                              hdr=hdr, backbuffer=O.SURF_RGBA16F, tex=O.TEXFMT_16FLOAT, dither=0, name="twolane%d" % i)
+                codes = H.make_codes(case.cf, case.w, case.h, "fullnoise", 200 + i)
+                buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+                outs = []
+                for on in (1, 0):
+                    vp = case.make_processor(device=0, path=PATH_MULTIPASS)
+                    vp.debug_set_convert_two_lane(on)
+                    vp.ProcessSample(data=buf, pitch=pitch)
+                    outs.append(vp.ReadBackbuffer())
+                assert np.array_equal(outs[0], outs[1]), (i, hdr)
+                assert H.compare(outs[0], H.run_oracle(case, planes, pitches), case.backbuffer) == (0, 0)
+    finally:
+        vp.debug_set_convert_two_lane(1)

@@ -23,6 +23,7 @@
 #include "kernels.h"
 #include "pixel_ops.cuh"
 #include "mpcvr_math2.cuh"
+#include "pixel_ops2.cuh"
 #include "dither32.h"
 
 namespace b200vr {
@@ -169,22 +170,7 @@ __device__ __forceinline__ void convert_tile_biplanar(const FusedParams& prm, co
     }
 }
 
-// ---- two-lane (FFMA2) PQ->SDR convert: lanes = two horizontally adjacent pixels, same operations as convert_color<PQ>
-struct f3x2 { float2 x, y, z; };
-
-__device__ __forceinline__ float2 dp3_2(const float m[3], const f3x2& v) { return fma2(m[2], v.z, fma2(m[1], v.y, mul2(v.x, m[0]))); }
-
-__device__ __forceinline__ float2 pq_channel_to_hable2(const ColorParams& P, float2 c)
-{
-    const float2 a   = powr01_ylt1_2(sat2(c), P.inv_m2);                         // ST2084ToLinear, st2084.hlsl:9-16
-    const float2 num = max2(add2(a, -ST2084_C1), 0.0f);
-    const float2 den = fma2(-ST2084_C3, a, ST2084_C2);
-    const float2 lin = mul2(powr01_ygt1_2(div_rn_safe_2(num, den), P.inv_m1), P.lum_scale);
-    const float2 hn  = fma2(lin, fma2(0.15f, lin, P.hable_cb), P.hable_de);       // hable(), hdr_tone_mapping.hlsl:1-6
-    const float2 hd  = fma2(lin, fma2(0.15f, lin, 0.50f), P.hable_df);
-    return mul2(add2(div_rn_safe_2(hn, hd), -P.hable_ef), P.hable_rdiv);
-}
-
+// ---- two-lane (FFMA2) PQ->SDR convert: f3x2, dp3_2 and pq_channel_to_hable2 live in pixel_ops2.cuh (shared with k_convert2)
 // everything before the final pow: saturate(mul(matrix_conv_prim, ToneMappingHable(ST2084ToLinear(saturate(rgb)))))
 __device__ __forceinline__ f3x2 convert_color_pq2_pre(const ColorParams& P, const f3x2& yuv)
 {

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include "kernels.h"
 #include "pixel_ops.cuh"
+#include "pixel_ops2.cuh"
 #include "mpcvr_math2.cuh"
 #include "dither32.h"
 
@@ -25,6 +26,29 @@ k_convert(const __grid_constant__ SrcDesc S, const __grid_constant__ ColorParams
     const f3 rgb = convert_color<-1>(P, yuv, dovi);
     if (dbg) dbg[(size_t)y * out.w + x] = make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
     surf_store(out, x, y, rgb);
+}
+
+// ConvertColorPass, two horizontally adjacent pixels per thread: the shader body runs in the two lanes of FFMA2 / FADD2 /
+// FMUL2 (pixel_ops2.cuh), bit-identical to k_convert; fetches stay scalar.  Frames with Dolby Vision data use k_convert.
+__global__ void __launch_bounds__(256)
+k_convert2(const __grid_constant__ SrcDesc S, const __grid_constant__ ColorParams P, const __grid_constant__ SurfDesc out,
+           float4* __restrict__ dbg)
+{
+    const int x = 2 * (blockIdx.x * blockDim.x + threadIdx.x), y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out.w || y >= out.h) return;
+    const bool two = x + 1 < out.w;
+    const f3 a = fetch_yuv(S, S.rect_l + x, S.rect_t + y);
+    const f3 b = two ? fetch_yuv(S, S.rect_l + x + 1, S.rect_t + y) : a;
+    f3x2 yuv; yuv.x = make_float2(a.x, b.x); yuv.y = make_float2(a.y, b.y); yuv.z = make_float2(a.z, b.z);
+    const f3x2 rgb = convert_color2(P, yuv);
+    f3 r0; r0.x = rgb.x.x; r0.y = rgb.y.x; r0.z = rgb.z.x;
+    if (dbg) dbg[(size_t)y * out.w + x] = make_float4(r0.x, r0.y, r0.z, 1.0f);
+    surf_store(out, x, y, r0);
+    if (two) {
+        f3 r1; r1.x = rgb.x.y; r1.y = rgb.y.y; r1.z = rgb.z.y;
+        if (dbg) dbg[(size_t)y * out.w + x + 1] = make_float4(r1.x, r1.y, r1.z, 1.0f);
+        surf_store(out, x + 1, y, r1);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -355,10 +379,17 @@ __global__ void k_math_probe(int op, const float* __restrict__ x, const float* _
 // ---------------------------------------------------------------------------------------------
 static inline dim3 Grid2D(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
 
+static int g_convertTwoLane = 1;          // debug switch: 0 = one pixel per thread (scalar shader body)
+void SetConvertTwoLane(int on) { g_convertTwoLane = on; }
+
 cudaError_t LaunchConvertPass(const SrcDesc& src, const ColorParams& color, const SurfDesc& out, float4* dbg_f32, cudaStream_t st,
                               const DoviParams* dovi_dev)
 {
     const dim3 b(32, 8);
+    if (!dovi_dev && g_convertTwoLane) {
+        k_convert2<<<Grid2D((out.w + 1) / 2, out.h, b), b, 0, st>>>(src, color, out, dbg_f32);
+        return cudaGetLastError();
+    }
     k_convert<<<Grid2D(out.w, out.h, b), b, 0, st>>>(src, color, out, dbg_f32, dovi_dev);
     return cudaGetLastError();
 }

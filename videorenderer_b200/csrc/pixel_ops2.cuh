@@ -1,0 +1,74 @@
+// pixel_ops2.cuh -- two-lane (FFMA2 / FADD2 / FMUL2) forms of the convert shader body: the two lanes are two horizontally
+// adjacent pixels, every lane performs exactly the operations of convert_color<TR> in pixel_ops.cuh (same order, same
+// roundings), so the results are bit-identical to the scalar form.  Used by stage A of the fused 2x kernel (PQ) and by
+// k_convert2, the two-pixels-per-thread ConvertColorPass of the multipass family.
+//
+// ptxas 12.9 note ("Toolchain findings"): a packed multiply immediately followed by a packed add is contracted
+// into FFMA2 even under -fmad=false.  Every product below therefore feeds a multiplicand, the addend of an explicit fma2, or
+// a non-arithmetic consumer -- never an add2.
+#pragma once
+#include "pixel_ops.cuh"
+#include "mpcvr_math2.cuh"
+
+namespace b200vr {
+
+struct f3x2 { float2 x, y, z; };
+
+__device__ __forceinline__ float2 dp3_2(const float m[3], const f3x2& v) { return fma2(m[2], v.z, fma2(m[1], v.y, mul2(v.x, m[0]))); }
+__device__ __forceinline__ f3x2 mat3_apply2(const float m[3][3], const f3x2& v) { f3x2 r; r.x = dp3_2(m[0], v); r.y = dp3_2(m[1], v); r.z = dp3_2(m[2], v); return r; }
+
+__device__ __forceinline__ float2 pq_channel_to_hable2(const ColorParams& P, float2 c)
+{
+    const float2 a   = powr01_ylt1_2(sat2(c), P.inv_m2);                         // ST2084ToLinear, st2084.hlsl:9-16
+    const float2 num = max2(add2(a, -ST2084_C1), 0.0f);
+    const float2 den = fma2(-ST2084_C3, a, ST2084_C2);
+    const float2 lin = mul2(powr01_ygt1_2(div_rn_safe_2(num, den), P.inv_m1), P.lum_scale);
+    const float2 hn  = fma2(lin, fma2(0.15f, lin, P.hable_cb), P.hable_de);       // hable(), hdr_tone_mapping.hlsl:1-6
+    const float2 hd  = fma2(lin, fma2(0.15f, lin, 0.50f), P.hable_df);
+    return mul2(add2(div_rn_safe_2(hn, hd), -P.hable_ef), P.hable_rdiv);
+}
+
+__device__ __forceinline__ float2 sel2(bool cx, bool cy, float2 a, float2 b) { return make_float2(cx ? a.x : b.x, cy ? a.y : b.y); }
+
+__device__ __forceinline__ float2 inverse_hlg2(const ColorParams& P, float2 x)                            // hlg.hlsl:1-11
+{
+    const float b = 0.28466892f, c = 0.55991073f;
+    const float2 lo = mul2(mul2(x, x), 4.0f);
+    const float2 hi = add2(ex2p_2(mul2(add2(x, -c), P.hlg_ra), 1.44269504f), b);
+    return sel2(x.x <= 0.5f, x.y <= 0.5f, lo, hi);
+}
+
+__device__ __forceinline__ float2 linear_to_st2084_2(float2 v, float rdivider)                           // st2084.hlsl:18-25
+{
+    v = mul2(v, rdivider);
+    const float2 p = powr_2(v, ST2084_M1);
+    const float2 q = div_rn_safe_2(fma2(ST2084_C2, p, ST2084_C1), fma2(ST2084_C3, p, 1.0f));
+    return powr_2(q, ST2084_M2);
+}
+
+// convert_color<-1> for two pixels (no Dolby Vision: those frames take the scalar kernel)
+__device__ __forceinline__ f3x2 convert_color2(const ColorParams& P, const f3x2& yuv)
+{
+    const int tr = P.transfer;
+    f3x2 c;
+    c.x = add2(dp3_2(P.cm[0], yuv), P.cc[0]); c.y = add2(dp3_2(P.cm[1], yuv), P.cc[1]); c.z = add2(dp3_2(P.cm[2], yuv), P.cc[2]);
+    if (tr == TRANSFER_NONE) return c;
+    if (tr == TRANSFER_SDR_2020) {
+        f3x2 l; l.x = powr_2(sat2(c.x), P.sdr_gamma); l.y = powr_2(sat2(c.y), P.sdr_gamma); l.z = powr_2(sat2(c.z), P.sdr_gamma);
+        c = mat3_apply2(P.gamut, l);
+    } else {
+        if (tr == TRANSFER_HLG_TO_SDR || tr == TRANSFER_HLG_TO_PQ) {
+            f3x2 l; l.x = inverse_hlg2(P, sat2(c.x)); l.y = inverse_hlg2(P, sat2(c.y)); l.z = inverse_hlg2(P, sat2(c.z));
+            const float2 dt = fma2(0.0593f, l.z, fma2(0.6780f, l.y, mul2(l.x, 0.2627f)));
+            const float2 g  = powr_2(mul2(dt, 2000.0f), 0.2f);
+            c.x = linear_to_st2084_2(mul2(l.x, g), P.r1000); c.y = linear_to_st2084_2(mul2(l.y, g), P.r1000); c.z = linear_to_st2084_2(mul2(l.z, g), P.r1000);
+            if (tr == TRANSFER_HLG_TO_PQ) return c;
+        }
+        f3x2 h; h.x = pq_channel_to_hable2(P, c.x); h.y = pq_channel_to_hable2(P, c.y); h.z = pq_channel_to_hable2(P, c.z);
+        c = mat3_apply2(P.gamut, h);
+    }
+    c.x = powr_2(sat2(c.x), P.inv_gamma22); c.y = powr_2(sat2(c.y), P.inv_gamma22); c.z = powr_2(sat2(c.z), P.inv_gamma22);
+    return c;
+}
+
+}  // namespace b200vr
