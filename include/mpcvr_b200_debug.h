@@ -37,6 +37,8 @@ int32_t mpcvr_debug_get_plan(mpcvr* vp, mpcvr_plan_info* info);
 int32_t mpcvr_debug_set_gamma_table(int32_t enable);
 /* process-wide: 1 (default) runs the multipass ConvertColorPass two pixels per thread in the packed-fp32 lanes, 0 one pixel per thread */
 int32_t mpcvr_debug_set_convert_two_lane(int32_t enable);
+/* process-wide: 1 (default) runs upright resize passes four outputs per thread, 0 one output per thread */
+int32_t mpcvr_debug_set_resize_four(int32_t enable);
 /* exhaustive check of that table against the direct evaluation over every float in [0,1] on the instance's device:
  * returns the number of mismatching floats (0 expected), -1 if the table was found unusable, -2 on a CUDA error */
 int64_t mpcvr_debug_verify_gamma_table(mpcvr* vp);

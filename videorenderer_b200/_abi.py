@@ -196,6 +196,7 @@ SIGNATURES = {
     "mpcvr_debug_set_path": (C.c_int32, [vp, C.c_int32]),
     "mpcvr_debug_set_gamma_table": (C.c_int32, [C.c_int32]),
     "mpcvr_debug_set_convert_two_lane": (C.c_int32, [C.c_int32]),
+    "mpcvr_debug_set_resize_four": (C.c_int32, [C.c_int32]),
     "mpcvr_debug_verify_gamma_table": (C.c_int64, [vp]),
     "mpcvr_debug_get_plan": (C.c_int32, [vp, P(PlanInfo)]),
     "mpcvr_debug_get_color_params": (C.c_int32, [vp, vp, vp, vp, P(C.c_float)]),

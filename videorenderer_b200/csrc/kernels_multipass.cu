@@ -88,6 +88,63 @@ k_resize(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc o
     surf_store(out, ox, oy, acc);
 }
 
+// Same pass, four consecutive outputs of the filtered axis per thread: neighbouring outputs share most of their taps, so the
+// union window is loaded and decoded once and every texel feeds the (up to four) accumulators it belongs to.  Each output
+// still receives its taps in ascending k with the same first-product / fma chain, so results are bit-identical to k_resize.
+__global__ void __launch_bounds__(256)
+k_resize4(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc out, const __grid_constant__ AxisTable T,
+          const int axis, const int32_t* __restrict__ other_idx, const int other_dst0, const int other_dst_len)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i0 = 4 * (axis == 0 ? a : b);        // first output index along the filtered axis
+    const int j  = axis == 0 ? b : a;              // index along the other axis
+    if (i0 >= T.dst_len || j >= other_dst_len) return;
+    const int n = min(4, T.dst_len - i0);
+    const int oj = other_dst0 + j;
+    if (oj < 0 || oj >= (axis == 0 ? out.h : out.w)) return;
+    const int lim   = axis == 0 ? in.w : in.h;
+    const int fixed = clampi(__ldg(other_idx + j), 0, (axis == 0 ? in.h : in.w) - 1);
+    const int nt = T.ntaps;
+    int base[4]; const float* w[4];
+    int lo = 0x7fffffff, hi = -0x7fffffff;
+    #pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int i = i0 + min(q, n - 1);
+        base[q] = __ldg(T.base + i); w[q] = T.w + (size_t)i * nt;
+        lo = min(lo, base[q]); hi = max(hi, base[q] + nt);
+    }
+    f3 acc[4];
+    #pragma unroll
+    for (int q = 0; q < 4; q++) { acc[q].x = 0.f; acc[q].y = 0.f; acc[q].z = 0.f; }
+    const bool conv = T.kind == SCALER_CONV, dup = T.dup_q1 != 0;
+    f3 prev = {0.f, 0.f, 0.f};
+    for (int t = lo; t < hi; t++) {
+        const int idx = clampi(t, 0, lim - 1);
+        const f3 p = axis == 0 ? surf_load(in, idx, fixed) : surf_load(in, fixed, idx);
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = t - base[q];
+            if (q < n && k >= 0 && k < nt) {
+                const f3 v = (dup && k == 1) ? prev : p;                 // ps_interpolation_lanczos3.hlsl:33-34: tap 1 re-reads tap 0's texel
+                const float wk = __ldg(w[q] + k);
+                if (k == 0 && !conv) { acc[q].x = __fmul_rn(wk, v.x); acc[q].y = __fmul_rn(wk, v.y); acc[q].z = __fmul_rn(wk, v.z); }
+                else { acc[q].x = fma_rn(wk, v.x, acc[q].x); acc[q].y = fma_rn(wk, v.y, acc[q].y); acc[q].z = fma_rn(wk, v.z, acc[q].z); }
+            }
+        }
+        prev = p;
+    }
+    #pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (q >= n) break;
+        const int i = i0 + q;
+        f3 r = acc[q];
+        if (conv) { const float ww = __ldg(T.wsum + i); r.x = __fdiv_rn(r.x, ww); r.y = __fdiv_rn(r.y, ww); r.z = __fdiv_rn(r.z, ww); }
+        const int ox = axis == 0 ? T.dst0 + i : oj, oy = axis == 0 ? oj : T.dst0 + i;
+        if (ox < 0 || oy < 0 || ox >= out.w || oy >= out.h) continue;
+        surf_store(out, ox, oy, r);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // TextureCopyRect + ps_simple: point-sampled copy / nearest-neighbour stretch
 // ---------------------------------------------------------------------------------------------
@@ -379,6 +436,8 @@ __global__ void k_math_probe(int op, const float* __restrict__ x, const float* _
 // ---------------------------------------------------------------------------------------------
 static inline dim3 Grid2D(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
 
+static int g_resizeFour = 1;              // debug switch: 0 = one output per thread (k_resize)
+void SetResizeFour(int on) { g_resizeFour = on; }
 static int g_convertTwoLane = 1;          // debug switch: 0 = one pixel per thread (scalar shader body)
 void SetConvertTwoLane(int on) { g_convertTwoLane = on; }
 
@@ -399,6 +458,11 @@ cudaError_t LaunchResizePass(const SurfDesc& in, const SurfDesc& out, const Axis
 {
     const dim3 b(32, 8);
     const int w = axis == 0 ? table.dst_len : other_dst_len, h = axis == 0 ? other_dst_len : table.dst_len;
+    if ((in_axis < 0 || in_axis == axis) && g_resizeFour) {               // upright draws: four outputs per thread
+        const int w4 = axis == 0 ? (w + 3) / 4 : w, h4 = axis == 0 ? h : (h + 3) / 4;
+        k_resize4<<<Grid2D(w4, h4, b), b, 0, st>>>(in, out, table, axis, other_idx, other_dst0, other_dst_len);
+        return cudaGetLastError();
+    }
     k_resize<<<Grid2D(w, h, b), b, 0, st>>>(in, out, table, axis, other_idx, other_dst0, other_dst_len, in_axis < 0 ? axis : in_axis);
     return cudaGetLastError();
 }
