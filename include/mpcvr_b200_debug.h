@@ -35,6 +35,12 @@ int32_t mpcvr_debug_get_plan(mpcvr* vp, mpcvr_plan_info* info);
 /* PS_COLOR_TRANSFORM cm_r,cm_g,cm_b (row-major 3x3) + cm_c, and matrix_conv_prim */
 /* process-wide: 1 (default) lets the fused 2x PQ kernel use the gamma+UNORM10 threshold table, 0 forces the direct pow */
 int32_t mpcvr_debug_set_gamma_table(int32_t enable);
+/* process-wide: enable = 1 (default) lets exact-2x plans of bi-planar sources run the persistent warp-specialised kernel (TMA-staged
+ * source rows), 0 keeps them on the tile kernel; cfg picks the warp-role split of the headline variant (0 = default) */
+int32_t mpcvr_debug_set_strip_kernel(int32_t enable, int32_t cfg);
+/* watchdog record of that kernel on the current CUDA device: out8[0] = number of bounded mbarrier waits that timed out (0 expected),
+ * [1] barrier slot, [2] parity, [3] row-group iteration, [4] block, [5] warp of the first one; clear != 0 resets the record */
+int32_t mpcvr_debug_strip_status(uint32_t out8[8], int32_t clear);
 /* process-wide: 1 (default) runs the multipass ConvertColorPass two pixels per thread in the packed-fp32 lanes, 0 one pixel per thread */
 int32_t mpcvr_debug_set_convert_two_lane(int32_t enable);
 /* process-wide: 1 (default) runs upright resize passes four outputs per thread, 0 one output per thread */

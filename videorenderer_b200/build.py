@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmpcvr_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CU = ["kernels_multipass.cu", "kernel_fused.cu"]
+CU = ["kernels_multipass.cu", "kernel_fused.cu", "kernel_strip.cu"]
 CPP = ["abi.cpp", "video_processor.cpp", "fmt_table.cpp", "cspmath.cpp", "resize_tables.cpp"]
 
 # -fmad=false: multiply-adds are fused only where the source says __fmaf_rn (arithmetic contract).

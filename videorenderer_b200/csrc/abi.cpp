@@ -3,6 +3,7 @@
 #include <cstring>
 #include <new>
 #include "video_processor.h"
+#include "kernel_strip.h"
 
 using b200vr::CB200VideoProcessor;
 using b200vr::CRect;
@@ -101,6 +102,8 @@ int64_t mpcvr_debug_verify_gamma_table(mpcvr* h) { VP_OR(-2); return vp.DebugVer
 int32_t mpcvr_debug_set_resize_four(int32_t enable) { b200vr::SetResizeFour(enable != 0); return MPCVR_S_OK; }
 int32_t mpcvr_debug_set_convert_two_lane(int32_t enable) { b200vr::SetConvertTwoLane(enable != 0); return MPCVR_S_OK; }
 int32_t mpcvr_debug_set_gamma_table(int32_t enable) { b200vr::SetGammaTableEnabled(enable != 0); return MPCVR_S_OK; }
+int32_t mpcvr_debug_set_strip_kernel(int32_t enable, int32_t cfg) { b200vr::SetStripKernel(enable != 0, cfg); return MPCVR_S_OK; }
+int32_t mpcvr_debug_strip_status(uint32_t out8[8], int32_t clear) { return b200vr::StripStatus(out8, clear) == 0 ? MPCVR_S_OK : MPCVR_E_FAIL; }
 int32_t mpcvr_debug_set_path(mpcvr* h, int32_t path) { VP_OR(MPCVR_E_POINTER); return vp.DebugSetPath(path); }
 int32_t mpcvr_debug_get_plan(mpcvr* h, mpcvr_plan_info* info) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugGetPlan(info)); }
 int32_t mpcvr_debug_get_color_params(mpcvr* h, float m9[9], float c3[3], float g9[9], float* lum) { VP_OR(MPCVR_E_POINTER); return vp.DebugGetColorParams(m9, c3, g9, lum); }

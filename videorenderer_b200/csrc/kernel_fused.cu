@@ -24,14 +24,15 @@
 #include "pixel_ops.cuh"
 #include "mpcvr_math2.cuh"
 #include "pixel_ops2.cuh"
-#include "dither32.h"
+#include "dither32f.cuh"
+#include "kernel_strip.h"
 
 namespace b200vr {
 
-// dither values d = k/1024 (exact in fp32), read through L1 in stage C
-#define MPCVR_DITHER_F(k) ((float)(k) * 0.0009765625f)
-__device__ const uint16_t g_dither32_fused[1024] = { MPCVR_DITHER32_VALUES };
-__device__ float g_dither32_f[1024];
+// dither values d = k/1024 (exact in fp32), read through L1 in stage C.  A compile-time constant: nothing to initialise, so
+// instances on different streams of one device cannot race on it (round-1 advisor finding on EnsureDither).
+__device__ const DitherTableF g_dither32_tab = MakeDitherTableF(0.0009765625f);
+#define g_dither32_f (g_dither32_tab.v)
 // ---- gamma + UNORM10 quantiser as a threshold table ---------------------------------------------------------------
 // The last two steps of the convert shader on the 10-bit path are  c = Q10(pow(sat(x), 1/2.2))  and the read-back c/1023.
 // As a function of the float x in [0,1] the code c is a step function, so it is stored as its 1023 step positions
@@ -40,7 +41,6 @@ __device__ float g_dither32_f[1024];
 // exponent: 0x3f0f90d2 reads 786 between two 787s) the scan records the float as an exception.  In the kernel a MUFU
 // estimate biased a quarter code low gives c0 with c in {c0, c0+1}; one compare against T[c0+1] decides -- bit-exact by
 // construction, ~25 % fewer FMA-pipe cycles in stage A.  More than kGammaMaxExc exceptions -> the table is not used.
-constexpr int kGammaN = 1023;
 constexpr int kGammaMaxExc = 2;
 constexpr int kGammaMaxTrans = 4096;
 __device__ float    g_gammaT[kGammaN + 2];       // T[0] = 0, T[1..N], T[N+1] = +inf
@@ -67,8 +67,6 @@ __global__ void __launch_bounds__(256) k_gamma_scan(uint32_t run)
         if (u == 0x3f800000u) break;
     }
 }
-
-__global__ void k_init_dither() { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < 1024) g_dither32_f[i] = MPCVR_DITHER_F(g_dither32_fused[i]); }
 
 constexpr int kCore = 64;            // convert-surface pixels per tile side
 constexpr int kOut = 2 * kCore;      // output pixels per tile side
@@ -168,52 +166,6 @@ __device__ __forceinline__ void convert_tile_biplanar(const FusedParams& prm, co
         d[TH * TWP]     = rt_roundtrip(ifmt, rgb.y);
         d[2 * TH * TWP] = rt_roundtrip(ifmt, rgb.z);
     }
-}
-
-// ---- two-lane (FFMA2) PQ->SDR convert: f3x2, dp3_2 and pq_channel_to_hable2 live in pixel_ops2.cuh (shared with k_convert2)
-// everything before the final pow: saturate(mul(matrix_conv_prim, ToneMappingHable(ST2084ToLinear(saturate(rgb)))))
-__device__ __forceinline__ f3x2 convert_color_pq2_pre(const ColorParams& P, const f3x2& yuv)
-{
-    f3x2 c;
-    c.x = add2(dp3_2(P.cm[0], yuv), P.cc[0]); c.y = add2(dp3_2(P.cm[1], yuv), P.cc[1]); c.z = add2(dp3_2(P.cm[2], yuv), P.cc[2]);
-    f3x2 h;
-    h.x = pq_channel_to_hable2(P, c.x); h.y = pq_channel_to_hable2(P, c.y); h.z = pq_channel_to_hable2(P, c.z);
-    f3x2 g;
-    g.x = sat2(dp3_2(P.gamut[0], h)); g.y = sat2(dp3_2(P.gamut[1], h)); g.z = sat2(dp3_2(P.gamut[2], h));
-    return g;
-}
-
-__device__ __forceinline__ f3x2 convert_color_pq2(const ColorParams& P, const f3x2& yuv)
-{
-    f3x2 c;
-    c.x = add2(dp3_2(P.cm[0], yuv), P.cc[0]); c.y = add2(dp3_2(P.cm[1], yuv), P.cc[1]); c.z = add2(dp3_2(P.cm[2], yuv), P.cc[2]);
-    f3x2 h;
-    h.x = pq_channel_to_hable2(P, c.x); h.y = pq_channel_to_hable2(P, c.y); h.z = pq_channel_to_hable2(P, c.z);
-    f3x2 o;
-    o.x = powr01_ylt1_2(sat2(dp3_2(P.gamut[0], h)), P.inv_gamma22);
-    o.y = powr01_ylt1_2(sat2(dp3_2(P.gamut[1], h)), P.inv_gamma22);
-    o.z = powr01_ylt1_2(sat2(dp3_2(P.gamut[2], h)), P.inv_gamma22);
-    return o;
-}
-
-__device__ __forceinline__ float2 rt_roundtrip2(int fmt, float2 v)
-{
-    if (fmt == MPCVR_SURF_RGB10A2) return unorm_roundtrip2(v, 1023.0f, 1.0f / 1023.0f);
-    if (fmt == MPCVR_SURF_BGRA8)   return unorm_roundtrip2(v, 255.0f, 1.0f / 255.0f);
-    return make_float2(f16_roundtrip(v.x), f16_roundtrip(v.y));
-}
-
-// gamma + UNORM10 write + read-back through the threshold table (see g_gammaT): x is already saturated
-__device__ __forceinline__ float gamma_q10_thr(float x, const float* __restrict__ sT, const float* __restrict__ sD, uint32_t exc0, uint32_t exc1)
-{
-    float l, e;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l * (1.0f / 2.2f)));
-    const int c0 = (int)fmaf(e, (float)kGammaN, 0.25f);                    // true code is c0 or c0 + 1
-    const uint32_t xb = __float_as_uint(x);
-    int c = c0 + (x >= sT[c0 + 1] ? 1 : 0);
-    c -= (xb == exc0 || xb == exc1) ? 1 : 0;
-    return sD[c];
 }
 
 // bi-planar 16-bit source, bilinear chroma, PQ->SDR, two pixels per work item.  THR: 10-bit internal format through the
@@ -664,6 +616,8 @@ bool FusedSupported(const FusedPlan& p, const char** why)
     return no("the per-tile source window of this plan does not fit in shared memory: multipass");
 }
 
+static std::mutex g_cfgMutex;           // guards the per-device "attributes set" flags below (instances may live on several host threads)
+
 template <int NT, int SPEC, int CONV>
 static cudaError_t LaunchT(const FusedParams& prm, cudaStream_t st)
 {
@@ -671,6 +625,7 @@ static cudaError_t LaunchT(const FusedParams& prm, cudaStream_t st)
     auto kern = k_fused2x<NT, SPEC, CONV>;
     static bool configured[64] = {};     // per instantiation and device
     int dev = 0; cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_cfgMutex);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
         if (e != cudaSuccess) return e;
@@ -705,20 +660,12 @@ static cudaError_t LaunchS(const FusedParams& prm, int spec, int conv, cudaStrea
     return LaunchC<NT, SPEC_RUNTIME>(prm, conv, st);
 }
 
-static cudaError_t EnsureDither(cudaStream_t st)
-{
-    static bool done[64] = {};
-    int dev = 0; cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-    k_init_dither<<<4, 256, 0, st>>>();
-    if (dev >= 0 && dev < 64) done[dev] = true;
-    return cudaGetLastError();
-}
-
 // builds g_gammaT / g_gammaD / g_gammaExc once per device; returns false (and leaves the plain kernel in charge) when the
 // scan finds the step function unusable
 static int g_useGammaTable = 1;                       // debug switch (mpcvr_debug_set_gamma_table)
 void SetGammaTableEnabled(int on) { g_useGammaTable = on; }
+
+static const float* g_gammaTdev[64]; static const float* g_gammaDdev[64]; static uint32_t g_gammaExcHost[64][2];   // per device, valid once ready
 
 static bool EnsureGammaTable(cudaStream_t st)
 {
@@ -763,6 +710,10 @@ static bool EnsureGammaTable(cudaStream_t st)
     if (cudaMemcpyToSymbolAsync(g_gammaD, D, sizeof(D), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
     if (cudaMemcpyToSymbolAsync(g_gammaExc, exc, sizeof(exc), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
     if (cudaStreamSynchronize(st) != cudaSuccess) return false;    // T, D are function statics reused across devices
+    void* pt = nullptr; void* pd = nullptr;
+    if (cudaGetSymbolAddress(&pt, g_gammaT) != cudaSuccess || cudaGetSymbolAddress(&pd, g_gammaD) != cudaSuccess) return false;
+    g_gammaTdev[dev] = (const float*)pt; g_gammaDdev[dev] = (const float*)pd;
+    g_gammaExcHost[dev][0] = exc[0]; g_gammaExcHost[dev][1] = exc[1];
     state[dev] = 1;
     return true;
 }
@@ -801,8 +752,6 @@ long long VerifyGammaTable(cudaStream_t st)
 
 cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
 {
-    cudaError_t de = EnsureDither(st);
-    if (de != cudaSuccess) return de;
     if (Is1x(p)) {
         Fused1xParams q;
         memset(&q, 0, sizeof(q));
@@ -823,6 +772,7 @@ cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
         g.internal_fmt = p.internal_fmt; g.final_pass = p.final_pass; g.two_pass = p.two_pass; g.Q = p.Q;
         static bool configured[64] = {};
         int dev = 0; cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(g_cfgMutex);
         if (dev < 0 || dev >= 64 || !configured[dev]) {
             cudaError_t e = cudaFuncSetAttribute(k_fused_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
             if (e != cudaSuccess) return e;
@@ -831,6 +781,16 @@ cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
         if (launches) *launches = 1;
         k_fused_generic<<<g.tiles_x * g.tiles_y, 256, smem, st>>>(g);
         return cudaGetLastError();
+    }
+    if (StripEligible(p)) {
+        // persistent warp-specialised kernel (kernel_strip.cuh): bi-planar sources with bilinear chroma, planes TMA-addressable
+        const bool thr = p.color.transfer == TRANSFER_PQ_TO_SDR && p.src.bytes == 2 && p.internal_fmt == MPCVR_SURF_RGB10A2 &&
+                         p.out.fmt == MPCVR_SURF_BGRA8 && p.final_pass && g_useGammaTable && EnsureGammaTable(st);
+        int dev = 0; cudaGetDevice(&dev);
+        const bool ok = thr && dev >= 0 && dev < 64;
+        if (launches) *launches = 1;
+        const cudaError_t e = LaunchStrip2x(p, ok ? g_gammaTdev[dev] : nullptr, ok ? g_gammaDdev[dev] : nullptr, ok ? g_gammaExcHost[dev] : nullptr, st);
+        if (e != cudaErrorNotSupported) return e;
     }
     FusedParams prm;
     memset(&prm, 0, sizeof(prm));

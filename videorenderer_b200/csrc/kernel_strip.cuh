@@ -1,0 +1,532 @@
+// kernel_strip.cuh -- the per-frame chain of exact 2x interpolation upscales as ONE persistent, warp-specialised kernel
+// (sm_100a): the Blackwell-native form of CDX11VideoProcessor::Process (Source/DX11VideoProcessor.cpp:3285-3424) for bi-planar
+// sources (NV12 / P010 / P016 / P210 / P216) with bilinear chroma -- BASELINE configs 2 and 5.
+//
+//   one CTA per SM walks column strips of SW convert-surface pixels from top to bottom (a contiguous range of the frame's
+//   (strip, 4-row quad) list, so every CTA gets the same amount of work and the vertical halo is converted once, not per tile);
+//   inside the CTA the frame flows through four warp roles coupled by mbarriers, with no CTA-wide barrier in steady state:
+//
+//   TMA      one elected thread: cp.async.bulk.tensor.2d of the luma and chroma rows of the next row group into shared memory
+//            (raw codes; out-of-frame texels arrive as zeros and are never used: CLAMP addressing is applied downstream)
+//   role P   raw codes -> floats: UNORM read of luma, chroma texels (sampler CLAMP), horizontal then vertical bilinear
+//            reconstruction at the luma positions   (ShaderGetPixels, Source/Shaders.cpp:230-272)
+//   role A   the convert shader body on two pixels per thread in the packed-fp32 lanes, render-target rounding
+//            (Source/Shaders.cpp:819-923; m_TexConvertOutput) -> fp32 rows in shared memory.  Pure arithmetic: three 64-bit
+//            shared loads, three 64-bit shared stores, addresses linear in the item index.
+//   role C   X pass (8 outputs per item, fp16 rounding = m_TexResize) into a ring of rows, then Y pass + post-scale rounding +
+//            final pass (ordered dither) + packing, 64-bit coalesced stores to the back buffer
+//            (ResizeShaderPass :3103-3187, ps_interpolation_*.hlsl, FinalPass :3189-3233, ps_final_pass.hlsl)
+//
+// Arithmetic is the same device code as the tile kernel / multipass kernels (pixel_ops2.cuh), so the output is bit-identical.
+// CLAMP addressing of the resize taps: columns are clamped when the X pass reads the converted rows (edge strips only), rows
+// when the Y pass picks ring rows (first / last quads only); rows and columns outside the convert surface are never computed.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include "kernels.h"
+#include "pixel_ops.cuh"
+#include "mpcvr_math2.cuh"
+#include "pixel_ops2.cuh"
+#include "dither32f.cuh"
+
+namespace b200vr {
+
+static __device__ const DitherTableF g_dither32_strip = MakeDitherTableF(0.0009765625f);    // d = k/1024, compile-time constant
+
+enum { SCONV_PQ_THR = 0,      // PQ -> SDR, 10-bit internal format: gamma + UNORM10 write/read through the threshold table
+       SCONV_PQ = 1,          // PQ -> SDR, any internal format
+       SCONV_ANY = 2 };       // any transfer (runtime switch), any internal format
+enum { SSPEC_RUNTIME = 0, SSPEC_10_BGRA8_DITHER = 1, SSPEC_8_BGRA8 = 2 };
+
+struct StripParams {
+    alignas(64) CUtensorMap tmY;          // luma plane: W x H elements of 1 or 2 bytes, box LUMA_BOX x R
+    alignas(64) CUtensorMap tmC;          // interleaved chroma plane: cw x ch texels of 2 or 4 bytes, box CP x rc_rows
+    ColorParams color;
+    SurfDesc    out;
+    float       wE[6], wO[6];             // weights of even / odd outputs (the 2x ratio has exactly two phases)
+    const float* gT; const float* gD;     // threshold table (SCONV_PQ_THR)
+    uint32_t    exc0, exc1;
+    int32_t     b0;                       // window start relative to j (even output); odd = b0 + 1
+    int32_t     w1, h1;                   // convert surface size (= m_srcRect size)
+    int32_t     rect_l, rect_t;
+    int32_t     cw, ch;                   // chroma plane size in texels
+    int32_t     bytes;                    // per component: 1 or 2
+    int32_t     ox, oy, my;               // chroma sample position of luma (sx, sy) in quarter texels: (2 sx + ox, my sy + oy)
+    int32_t     rc_rows;                  // chroma rows per row group (tmC box height)
+    int32_t     luma_pitch, chroma_pitch; // shared-memory row pitches of the raw boxes, bytes
+    int32_t     luma_bytes, chroma_bytes; // bytes per TMA box
+    int32_t     dst_x0, dst_y0;
+    int32_t     internal_fmt, final_pass;
+    float       Q;
+    int32_t     strips, nq;               // column strips, quads (4 convert rows) per strip
+};
+
+// ---- PTX helpers -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug makes the role give up (the frame is then wrong and g_stripStatus says where it stopped; the
+// launcher's debug query reports it) instead of hanging the device
+static __device__ unsigned int g_stripStatus[8];       // [0] = failures, [1] = barrier slot, [2] = parity, [3] = iteration, [4] = block, [5] = warp
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int it = -1)
+{
+    if (mbar_try(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 400000000ll) {
+            if (atomicAdd(&g_stripStatus[0], 1u) == 0) {
+                g_stripStatus[1] = (bar & 127u) >> 3; g_stripStatus[2] = parity; g_stripStatus[3] = (unsigned)it;
+                g_stripStatus[4] = blockIdx.x; g_stripStatus[5] = threadIdx.x >> 5;
+            }
+            return false;
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ float fma_sat(float a, float b, float c) { float d; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+// prmt.b32 in its default mode: selector nibbles 0-7 pick a byte of {a, b}; bit 3 of a nibble replicates that byte's sign bit
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; }
+
+// ---- geometry ---------------------------------------------------------------------------------------------------------
+template <int SW_, int R_, int NP_, int NA_, int W_>
+struct StripCfg {
+    static constexpr int SW = SW_;                 // convert-surface pixels per strip
+    static constexpr int R = R_;                   // convert rows per row group
+    static constexpr int NP = NP_, NA = NA_, W = W_;
+    static constexpr int CB = SW / 32;             // column blocks of 32 core pixels (= 64 outputs, one warp wide)
+    static constexpr int NC = CB * W;              // consumer warps
+    static constexpr int THREADS = 32 * (NP + NA + NC);
+    static constexpr int WP = SW + 8;              // window pitch in pixels (window = SW + NT <= WP)
+    static constexpr int PAIRS = WP / 2;
+    static constexpr int CP = SW / 2 + 8;          // chroma texels per box row
+    static constexpr int RCMAX = R + 1;            // chroma rows per group: R/2 + 2 (4:2:0) or R + 1 (4:2:2)
+    static constexpr int RING = 32;                // rows of the X-pass ring (>= 2R + NT + 6)
+    static constexpr int NRAW = 3;                 // TMA stages
+    static_assert(RING >= 2 * R + 6 + 6, "ring too small");
+    static_assert((R % 4) == 0 && (R * 8) % (W * 32) == 0, "X-pass items must tile the column block's threads");
+    static constexpr int align128(int x) { return (x + 127) / 128 * 128; }
+    // shared memory layout (byte offsets)
+    static constexpr int oBars = 0;                                   // 16 mbarriers
+    static constexpr int oT = 128;
+    static constexpr int oD = oT + align128((kGammaN + 2) * 4);
+    static constexpr int oDith = oD + align128((kGammaN + 1) * 4);
+    static constexpr int oRawY = oDith + 4096;
+    // TMA boxes start on 16-byte boundaries of the plane rows (the hardware rejects other inner coordinates), so the boxes are
+    // wider than the window by the worst-case misalignment
+    static constexpr int LBOX16 = WP + 8, LBOX8 = WP + 24;            // luma box width in texels (16-bit / 8-bit components)
+    static constexpr int CBOX32 = CP + 4, CBOX16 = CP + 8;            // chroma box width in texels (4-byte / 2-byte texels)
+    static constexpr int szRawY = align128(R * LBOX16 * 2);
+    static constexpr int oRawC = oRawY + NRAW * szRawY;
+    static constexpr int szRawC = align128(RCMAX * CBOX32 * 4);
+    static constexpr int oCu = oRawC + NRAW * szRawC;
+    static constexpr int szC = align128(RCMAX * CP * 4);
+    static constexpr int oCv = oCu + szC;
+    static constexpr int oHU = oCv + szC;
+    static constexpr int szH = align128(RCMAX * WP * 4);
+    static constexpr int oHV = oHU + szH;
+    static constexpr int oPrep = oHV + szH;
+    static constexpr int szPlane = R * WP * 4;                        // one fp32 plane of a row group
+    static constexpr int oConv = oPrep + 2 * 3 * szPlane;
+    static constexpr int oX = oConv + 2 * 3 * szPlane;
+    static constexpr int szX = 3 * RING * 2 * SW * 2;                 // [3][RING][2 SW] halfs
+    static constexpr int smem_bytes = oX + szX;
+};
+
+// barrier slots
+enum { B_RAWFULL = 0, B_RAWEMPTY = 3, B_PREPFULL = 6, B_PREPEMPTY = 8, B_CONVFULL = 10, B_CONVEMPTY = 12, B_COUNT = 14 };
+
+// the (strip, quad range) segments a CTA owns and their row groups; every role walks the same sequence
+template <class C, int NT>
+struct GroupIter {
+    int Qc, Q1, nq, b0, h1;
+    int s, qa, qb, wyA, wyB, ngroups, g;
+    bool valid;
+    __device__ __forceinline__ bool next_seg()
+    {
+        if (Qc >= Q1) return false;
+        s = Qc / nq; qa = Qc - s * nq;
+        const int n = min(nq - qa, Q1 - Qc);
+        qb = qa + n; Qc += n;
+        wyA = max(4 * qa + b0, 0);                              // first / last convert row the segment's outputs read (CLAMP applied)
+        wyB = min(4 * qb - 1 + b0 + NT, h1 - 1);
+        ngroups = (wyB - wyA + C::R) / C::R;
+        g = 0;
+        return true;
+    }
+    __device__ __forceinline__ void init(int q0, int q1, int nq_, int b0_, int h1_) { Qc = q0; Q1 = q1; nq = nq_; b0 = b0_; h1 = h1_; valid = next_seg(); }
+    __device__ __forceinline__ void advance() { if (++g >= ngroups) valid = next_seg(); }
+    __device__ __forceinline__ int cy0() const { return wyA + g * C::R; }
+    __device__ __forceinline__ int rows() const { return min(C::R, wyB - cy0() + 1); }
+};
+
+template <class C, int NT, bool DUP, int SPEC, int CONV>
+__global__ void __launch_bounds__(C::THREADS, 1)
+k_strip2x(const __grid_constant__ StripParams prm)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sT = reinterpret_cast<float*>(smem + C::oT);
+    float* sD = reinterpret_cast<float*>(smem + C::oD);
+    float* sDith = reinterpret_cast<float*>(smem + C::oDith);      // NEGATED dither values when SPEC == SSPEC_10_BGRA8_DITHER
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::NRAW; i++) { mbar_init(sbase + 8 * (B_RAWFULL + i), 1); mbar_init(sbase + 8 * (B_RAWEMPTY + i), C::NP); }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(sbase + 8 * (B_PREPFULL + i), C::NP);  mbar_init(sbase + 8 * (B_PREPEMPTY + i), C::NA);
+            mbar_init(sbase + 8 * (B_CONVFULL + i), C::NA);  mbar_init(sbase + 8 * (B_CONVEMPTY + i), C::NC);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (CONV == SCONV_PQ_THR) {
+        for (int i = threadIdx.x; i < kGammaN + 2; i += C::THREADS) sT[i] = prm.gT[i];
+        for (int i = threadIdx.x; i < kGammaN + 1; i += C::THREADS) sD[i] = prm.gD[i];
+    }
+    for (int i = threadIdx.x; i < 1024; i += C::THREADS) sDith[i] = (SPEC == SSPEC_10_BGRA8_DITHER) ? -g_dither32_strip.v[i] : g_dither32_strip.v[i];
+    __syncthreads();
+
+    const long long total = (long long)prm.strips * prm.nq;
+    const int Q0 = (int)(total * blockIdx.x / gridDim.x), Q1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
+    const int IFMT = SPEC == SSPEC_10_BGRA8_DITHER ? (int)MPCVR_SURF_RGB10A2 : (SPEC == SSPEC_8_BGRA8 ? (int)MPCVR_SURF_BGRA8 : prm.internal_fmt);
+
+    if (warp < C::NP) {
+        // ================================================================================================ TMA + role P
+        constexpr int TP = C::NP * 32;
+        const int tP = threadIdx.x;
+        GroupIter<C, NT> gi; gi.init(Q0, Q1, prm.nq, prm.b0, prm.h1);
+        GroupIter<C, NT> iss = gi; int it_iss = 0;                       // issue cursor (thread 0 only)
+        float* sCu = reinterpret_cast<float*>(smem + C::oCu); float* sCv = reinterpret_cast<float*>(smem + C::oCv);
+        float* sHU = reinterpret_cast<float*>(smem + C::oHU); float* sHV = reinterpret_cast<float*>(smem + C::oHV);
+        const int bytes = prm.bytes, ox = prm.ox, oy = prm.oy, my = prm.my, RC = prm.rc_rows;
+        const int lmask = 16 / bytes - 1, cmask = 8 / bytes - 1;          // box origins are multiples of 16 bytes
+        const int cbox = bytes == 2 ? C::CBOX32 : C::CBOX16;
+        for (int it = 0; gi.valid; it++, gi.advance()) {
+            if (tP == 0) {
+                while (iss.valid && it_iss < it + C::NRAW) {
+                    const int slot = it_iss % C::NRAW;
+                    if (!mbar_wait(sbase + 8 * (B_RAWEMPTY + slot), ((it_iss / C::NRAW) & 1) ^ 1, it_iss)) break;
+                    const uint32_t full = sbase + 8 * (B_RAWFULL + slot);
+                    mbar_expect_tx(full, (uint32_t)(prm.luma_bytes + prm.chroma_bytes));
+                    const int X0 = prm.rect_l + iss.s * C::SW + prm.b0, sy0 = prm.rect_t + iss.cy0();
+                    tma_load_2d(sbase + C::oRawY + slot * C::szRawY, &prm.tmY, X0 & ~lmask, sy0, full);
+                    tma_load_2d(sbase + C::oRawC + slot * C::szRawC, &prm.tmC, ((2 * X0 + ox) >> 2) & ~cmask, (my * sy0 + oy) >> 2, full);
+                    it_iss++; iss.advance();
+                }
+            }
+            __syncwarp();
+            const int slot = it % C::NRAW, pslot = it & 1;
+            const int rows = gi.rows();
+            const int X0 = prm.rect_l + gi.s * C::SW + prm.b0, sy0 = prm.rect_t + gi.cy0();
+            const int ux0 = (2 * X0 + ox) >> 2, uy0 = (my * sy0 + oy) >> 2;
+            const int xoff = X0 & lmask, uoff = ux0 & cmask;              // window origin inside the aligned boxes
+            const unsigned char* rawY = smem + C::oRawY + slot * C::szRawY;
+            const unsigned char* rawC = smem + C::oRawC + slot * C::szRawC;
+            float2* pY = reinterpret_cast<float2*>(smem + C::oPrep + (pslot * 3 + 0) * C::szPlane);
+            float2* pU = reinterpret_cast<float2*>(smem + C::oPrep + (pslot * 3 + 1) * C::szPlane);
+            float2* pV = reinterpret_cast<float2*>(smem + C::oPrep + (pslot * 3 + 2) * C::szPlane);
+            if (!mbar_wait(sbase + 8 * (B_RAWFULL + slot), (it / C::NRAW) & 1, it)) return;
+            if (!mbar_wait(sbase + 8 * (B_PREPEMPTY + pslot), ((it >> 1) & 1) ^ 1, it)) return;
+            // P0: luma codes -> floats (UNORM read)
+            for (int k = tP; k < rows * C::PAIRS; k += TP) {
+                const int r = k / C::PAIRS, p = k - r * C::PAIRS;
+                float2 y;
+                if (bytes == 2) { const uint16_t* q = reinterpret_cast<const uint16_t*>(rawY + r * prm.luma_pitch) + xoff + 2 * p; y = make_float2(unorm16(q[0]), unorm16(q[1])); }
+                else            { const uint8_t* q = rawY + r * prm.luma_pitch + xoff + 2 * p; y = make_float2(unorm8(q[0]), unorm8(q[1])); }
+                pY[k] = y;
+            }
+            // P1: chroma texels -> floats, sampler CLAMP at the plane borders
+            for (int k = tP; k < RC * C::CP; k += TP) {
+                const int rr = k / C::CP, c = k - rr * C::CP;
+                const int cl = min(max(min(max(ux0 + c, 0), prm.cw - 1) - ux0 + uoff, 0), cbox - 1);
+                const int rl = min(max(min(max(uy0 + rr, 0), prm.ch - 1) - uy0, 0), RC - 1);
+                float u, v;
+                if (bytes == 2) { const uint32_t w = *reinterpret_cast<const uint32_t*>(rawC + rl * prm.chroma_pitch + 4 * cl); u = unorm16(w & 0xFFFFu); v = unorm16(w >> 16); }
+                else            { const uint32_t w = *reinterpret_cast<const uint16_t*>(rawC + rl * prm.chroma_pitch + 2 * cl); u = unorm8(w & 255u); v = unorm8(w >> 8); }
+                sCu[k] = u; sCv[k] = v;
+            }
+            named_bar(1, TP);
+            // P2: horizontal bilinear reconstruction at the luma columns (top / bot of the bilinear sample)
+            for (int k = tP; k < RC * C::PAIRS; k += TP) {
+                const int rr = k / C::PAIRS, p = k - rr * C::PAIRS;
+                const int qx0 = 2 * (X0 + 2 * p) + ox, qx1 = qx0 + 2;
+                const int t0 = rr * C::CP + (qx0 >> 2) - ux0, t1 = rr * C::CP + (qx1 >> 2) - ux0;
+                const float2 fx = make_float2((float)(qx0 & 3) * 0.25f, (float)(qx1 & 3) * 0.25f);
+                const float2 ua = make_float2(sCu[t0], sCu[t1]), ub = make_float2(sCu[t0 + 1], sCu[t1 + 1]);
+                const float2 va = make_float2(sCv[t0], sCv[t1]), vb = make_float2(sCv[t0 + 1], sCv[t1 + 1]);
+                reinterpret_cast<float2*>(sHU)[k] = fma2(fx, sub2(ub, ua), ua);
+                reinterpret_cast<float2*>(sHV)[k] = fma2(fx, sub2(vb, va), va);
+            }
+            named_bar(1, TP);
+            // P3: vertical interpolation at the luma rows
+            for (int k = tP; k < rows * C::PAIRS; k += TP) {
+                const int r = k / C::PAIRS, p = k - r * C::PAIRS;
+                const int qy = my * (sy0 + r) + oy;
+                const int h0 = ((qy >> 2) - uy0) * C::PAIRS + p;
+                const float fy = (float)(qy & 3) * 0.25f;
+                const float2 ut = reinterpret_cast<const float2*>(sHU)[h0], ub = reinterpret_cast<const float2*>(sHU)[h0 + C::PAIRS];
+                const float2 vt = reinterpret_cast<const float2*>(sHV)[h0], vb = reinterpret_cast<const float2*>(sHV)[h0 + C::PAIRS];
+                pU[k] = fma2(fy, sub2(ub, ut), ut);
+                pV[k] = fma2(fy, sub2(vb, vt), vt);
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(sbase + 8 * (B_RAWEMPTY + slot)); mbar_arrive(sbase + 8 * (B_PREPFULL + pslot)); }
+        }
+    } else if (warp < C::NP + C::NA) {
+        // ================================================================================================ role A
+        constexpr int TA = C::NA * 32;
+        const int tA = threadIdx.x - C::NP * 32;
+        GroupIter<C, NT> gi; gi.init(Q0, Q1, prm.nq, prm.b0, prm.h1);
+        int stream = 0;                                                 // items handed out so far, modulo TA
+        const uint32_t exc0 = prm.exc0, exc1 = prm.exc1;
+        for (int it = 0; gi.valid; it++, gi.advance()) {
+            const int slot = it & 1;
+            const int items = gi.rows() * C::PAIRS;
+            const float2* pY = reinterpret_cast<const float2*>(smem + C::oPrep + (slot * 3 + 0) * C::szPlane);
+            const float2* pU = reinterpret_cast<const float2*>(smem + C::oPrep + (slot * 3 + 1) * C::szPlane);
+            const float2* pV = reinterpret_cast<const float2*>(smem + C::oPrep + (slot * 3 + 2) * C::szPlane);
+            float2* c0 = reinterpret_cast<float2*>(smem + C::oConv + (slot * 3 + 0) * C::szPlane);
+            float2* c1 = reinterpret_cast<float2*>(smem + C::oConv + (slot * 3 + 1) * C::szPlane);
+            float2* c2 = reinterpret_cast<float2*>(smem + C::oConv + (slot * 3 + 2) * C::szPlane);
+            if (!mbar_wait(sbase + 8 * (B_PREPFULL + slot), (it >> 1) & 1, it)) return;
+            if (!mbar_wait(sbase + 8 * (B_CONVEMPTY + slot), ((it >> 1) & 1) ^ 1, it)) return;
+            int k = tA - stream; if (k < 0) k += TA;
+            for (; k < items; k += TA) {
+                f3x2 yuv; yuv.x = pY[k]; yuv.y = pU[k]; yuv.z = pV[k];
+                if (CONV == SCONV_PQ_THR) {
+                    const f3x2 g = convert_color_pq2_pre(prm.color, yuv);            // saturated gamut-mapped linear light
+                    c0[k] = make_float2(gamma_q10_thr(g.x.x, sT, sD, exc0, exc1), gamma_q10_thr(g.x.y, sT, sD, exc0, exc1));
+                    c1[k] = make_float2(gamma_q10_thr(g.y.x, sT, sD, exc0, exc1), gamma_q10_thr(g.y.y, sT, sD, exc0, exc1));
+                    c2[k] = make_float2(gamma_q10_thr(g.z.x, sT, sD, exc0, exc1), gamma_q10_thr(g.z.y, sT, sD, exc0, exc1));
+                } else {
+                    const f3x2 rgb = (CONV == SCONV_PQ) ? convert_color_pq2(prm.color, yuv) : convert_color2(prm.color, yuv);
+                    c0[k] = rt_roundtrip2(IFMT, rgb.x); c1[k] = rt_roundtrip2(IFMT, rgb.y); c2[k] = rt_roundtrip2(IFMT, rgb.z);
+                }
+            }
+            stream = (stream + items) % TA;
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(sbase + 8 * (B_CONVFULL + slot)); mbar_arrive(sbase + 8 * (B_PREPEMPTY + slot)); }
+        }
+    } else {
+        // ================================================================================================ role C
+        const int wc = warp - C::NP - C::NA, cb = wc / C::W, sw = wc - cb * C::W;
+        const int tCB = sw * 32 + lane;                                  // thread index inside the column block's warps
+        constexpr int TCB = C::W * 32;
+        const int  OFMT  = SPEC != SSPEC_RUNTIME ? (int)MPCVR_SURF_BGRA8 : prm.out.fmt;
+        const bool FINAL = SPEC == SSPEC_10_BGRA8_DITHER ? true : (SPEC == SSPEC_8_BGRA8 ? false : prm.final_pass != 0);
+        __half* sX = reinterpret_cast<__half*>(smem + C::oX);
+        float wE[NT], wO[NT];
+        #pragma unroll
+        for (int k = 0; k < NT; k++) { wE[k] = prm.wE[k]; wO[k] = prm.wO[k]; }
+        GroupIter<C, NT> gi; gi.init(Q0, Q1, prm.nq, prm.b0, prm.h1);
+        int qnext = 0;
+        for (int it = 0; gi.valid; it++, gi.advance()) {
+            const int slot = it & 1;
+            const int cx0 = gi.s * C::SW + prm.b0;                       // convert-surface column of window column 0
+            const int colbase = gi.s * C::SW + 32 * cb;                  // first core column of this block
+            const bool active = colbase < prm.w1;
+            if (gi.g == 0) { named_bar(2 + cb, TCB); qnext = gi.qa; }    // new segment: the ring restarts
+            if (!mbar_wait(sbase + 8 * (B_CONVFULL + slot), (it >> 1) & 1, it)) return;
+            const int rows = gi.rows(), cy0 = gi.cy0();
+            // ---- X pass of the group's rows: item = (channel, row, block of 8 outputs)
+            if (active) {
+                const bool xedge = (cx0 + 32 * cb < 0) || (cx0 + 32 * cb + 32 + NT > prm.w1);
+                #pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float* plane = reinterpret_cast<const float*>(smem + C::oConv + (slot * 3 + c) * C::szPlane);
+                    for (int idx = tCB; idx < rows * 8; idx += TCB) {
+                        const int row = idx >> 3, b = idx & 7;
+                        const float* src = plane + row * C::WP + 32 * cb + 4 * b;
+                        float v[NT + 4];
+                        if (!xedge) {
+                            const float4 a = *reinterpret_cast<const float4*>(src), d = *reinterpret_cast<const float4*>(src + 4);
+                            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
+                            if (NT == 6) { const float2 e = *reinterpret_cast<const float2*>(src + 8); v[8] = e.x; v[9] = e.y; }
+                        } else {
+                            #pragma unroll
+                            for (int i = 0; i < NT + 4; i++) {                    // CLAMP addressing of the X taps
+                                const int wx = min(max(cx0 + 32 * cb + 4 * b + i, 0), prm.w1 - 1) - cx0;
+                                v[i] = plane[row * C::WP + wx];
+                            }
+                        }
+                        __half2 o[4];
+                        #pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            float e = __fmul_rn(wE[0], v[q]), d = __fmul_rn(wO[0], v[q + 1]);
+                            #pragma unroll
+                            for (int k = 1; k < NT; k++) {
+                                // D3D11 lanczos3 re-reads tap 0's texel for tap 1 (ps_interpolation_lanczos3.hlsl:33-34)
+                                const float te = (NT == 6 && k == 1 && DUP) ? v[q] : v[q + k];
+                                const float to = (NT == 6 && k == 1 && DUP) ? v[q + 1] : v[q + 1 + k];
+                                e = fma_rn(wE[k], te, e);
+                                d = fma_rn(wO[k], to, d);
+                            }
+                            o[q] = __floats2half2_rn(e, d);                       // m_TexResize is RGBA16F
+                        }
+                        uint4 pk;
+                        pk.x = *reinterpret_cast<uint32_t*>(&o[0]); pk.y = *reinterpret_cast<uint32_t*>(&o[1]);
+                        pk.z = *reinterpret_cast<uint32_t*>(&o[2]); pk.w = *reinterpret_cast<uint32_t*>(&o[3]);
+                        const int ring = (cy0 + row - gi.wyA) & (C::RING - 1);
+                        *reinterpret_cast<uint4*>(sX + ((size_t)(c * C::RING + ring) * 2 * C::SW) + 64 * cb + 8 * b) = pk;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sbase + 8 * (B_CONVEMPTY + slot));
+            named_bar(2 + cb, TCB);
+            // ---- Y pass + rounding + final pass for the quads whose rows are now complete
+            const int cyLast = cy0 + rows - 1;
+            for (; qnext < gi.qb && min(4 * qnext + 3 + prm.b0 + NT, prm.h1 - 1) <= cyLast; qnext++) {
+                if (!active || ((qnext - gi.qa) % C::W) != sw) continue;
+                const int q = qnext;
+                const int col = colbase + lane;                                    // convert-surface column of this lane's output pair
+                if (col >= prm.w1) continue;
+                const int jy = 4 * q;                                              // first convert row of the quad
+                const int gx = prm.dst_x0 + 2 * col, gy = prm.dst_y0 + 2 * jy;
+                const bool yedge = (jy + prm.b0 < 0) || (jy + 3 + prm.b0 + NT > prm.h1 - 1);
+                int ringrow[NT + 4];
+                #pragma unroll
+                for (int r = 0; r < NT + 4; r++) {
+                    int cy = jy + prm.b0 + r;
+                    if (yedge) cy = min(max(cy, 0), prm.h1 - 1);                   // CLAMP addressing of the Y taps
+                    ringrow[r] = (cy - gi.wyA) & (C::RING - 1);
+                }
+                const int nrows = min(8, 2 * (prm.h1 - jy));                       // output rows of this quad that exist
+                const __half* colp = sX + 64 * cb + 2 * lane;
+                if (SPEC == SSPEC_10_BGRA8_DITHER) {
+                    // channel-sequential: B, G, R; codes are packed as they appear (two PRMTs per pixel)
+                    float2 nd[8];
+                    #pragma unroll
+                    for (int r = 0; r < 8; r++) nd[r] = *reinterpret_cast<const float2*>(sDith + (((gy + r) & 31) << 5) + (gx & 31));
+                    uint32_t w0[8], w1[8];
+                    #pragma unroll
+                    for (int cc = 0; cc < 3; cc++) {
+                        const int c = 2 - cc;
+                        float2 v[NT + 4];
+                        #pragma unroll
+                        for (int r = 0; r < NT + 4; r++)
+                            v[r] = __half22float2(*reinterpret_cast<const __half2*>(colp + (size_t)(c * C::RING + ringrow[r]) * 2 * C::SW));
+                        #pragma unroll
+                        for (int qq = 0; qq < 4; qq++) {
+                            float2 e = mul2(v[qq], wE[0]), d = mul2(v[qq + 1], wO[0]);
+                            #pragma unroll
+                            for (int k = 1; k < NT - 1; k++) {
+                                const float2 te = (NT == 6 && k == 1 && DUP) ? v[qq] : v[qq + k];
+                                const float2 to = (NT == 6 && k == 1 && DUP) ? v[qq + 1] : v[qq + 1 + k];
+                                e = fma2(wE[k], te, e);
+                                d = fma2(wO[k], to, d);
+                            }
+                            // last tap with the saturate of the UNORM write folded in (fma.rn.sat: same value as sat(fma))
+                            const float2 le = v[qq + NT - 1], lo = v[qq + NT];
+                            e = make_float2(fma_sat(wE[NT - 1], le.x, e.x), fma_sat(wE[NT - 1], le.y, e.y));
+                            d = make_float2(fma_sat(wO[NT - 1], lo.x, d.x), fma_sat(wO[NT - 1], lo.y, d.y));
+                            #pragma unroll
+                            for (int h = 0; h < 2; h++) {
+                                const int r = 2 * qq + h;
+                                const float2 val = h ? d : e;
+                                // m_TexsPostScale (RGB10A2) write + read, then ps_final_pass: floor(p*255 + dither), negated so that the
+                                // sign byte doubles as the alpha byte: fl = -(2^23 + floor(t))
+                                const float2 p = div_by_const_exact2(floor_pos2(fma2(val, 1023.0f, 0.5f)), 1023.0f, 1.0f / 1023.0f);
+                                const float2 fl = __fadd2_ru(fma2(p, -255.0f, nd[r]), bc2(-8388608.0f));
+                                const uint32_t f0 = __float_as_uint(fl.x), f1 = __float_as_uint(fl.y);
+                                if (cc == 0)      { w0[r] = f0; w1[r] = f1; }                                        // B
+                                else if (cc == 1) { w0[r] = prmt(w0[r], f0, 0x0040); w1[r] = prmt(w1[r], f1, 0x0040); }   // B, G
+                                else              { w0[r] = prmt(w0[r], f0, 0xF410); w1[r] = prmt(w1[r], f1, 0xF410); }   // B, G, R, 0xFF
+                            }
+                        }
+                    }
+                    uint8_t* orow = (uint8_t*)prm.out.ptr + (size_t)gy * prm.out.pitch + (size_t)gx * 4;
+                    #pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        if (r < nrows) *reinterpret_cast<uint2*>(orow) = make_uint2(w0[r], w1[r]);
+                        orow += prm.out.pitch;
+                    }
+                } else {
+                    float2 res[3][8];
+                    #pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        float2 v[NT + 4];
+                        #pragma unroll
+                        for (int r = 0; r < NT + 4; r++)
+                            v[r] = __half22float2(*reinterpret_cast<const __half2*>(colp + (size_t)(c * C::RING + ringrow[r]) * 2 * C::SW));
+                        #pragma unroll
+                        for (int qq = 0; qq < 4; qq++) {
+                            float2 e = mul2(v[qq], wE[0]), d = mul2(v[qq + 1], wO[0]);
+                            #pragma unroll
+                            for (int k = 1; k < NT; k++) {
+                                const float2 te = (NT == 6 && k == 1 && DUP) ? v[qq] : v[qq + k];
+                                const float2 to = (NT == 6 && k == 1 && DUP) ? v[qq + 1] : v[qq + 1 + k];
+                                e = fma2(wE[k], te, e);
+                                d = fma2(wO[k], to, d);
+                            }
+                            res[c][2 * qq] = e; res[c][2 * qq + 1] = d;
+                        }
+                    }
+                    #pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        if (r >= nrows) break;
+                        const int y = gy + r;
+                        uint32_t code[2][3];
+                        __half hv[2][3];
+                        float2 dth = make_float2(0.f, 0.f);
+                        if (FINAL) dth = *reinterpret_cast<const float2*>(sDith + ((y & 31) << 5) + (gx & 31));
+                        #pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const float2 val = res[c][r];
+                            if (FINAL) {
+                                const float2 p = rt_roundtrip2(IFMT, val);
+                                const float2 t = fma2(p, prm.Q, dth);
+                                if (IFMT == MPCVR_SURF_RGBA16F) {
+                                    code[0][c] = (uint32_t)min(max((int)floorf(t.x), 0), (int)prm.Q);
+                                    code[1][c] = (uint32_t)min(max((int)floorf(t.y), 0), (int)prm.Q);
+                                } else {
+                                    const float2 fl = __fadd2_rd(t, bc2(8388608.0f));
+                                    code[0][c] = __float_as_uint(fl.x) & 0x3FFFFFu; code[1][c] = __float_as_uint(fl.y) & 0x3FFFFFu;
+                                }
+                            } else if (OFMT == MPCVR_SURF_RGBA16F) {
+                                hv[0][c] = __float2half_rn(val.x); hv[1][c] = __float2half_rn(val.y);
+                            } else {
+                                const float2 fl = __fadd2_rd(fma2(sat2(val), OFMT == MPCVR_SURF_RGB10A2 ? 1023.0f : 255.0f, 0.5f), bc2(8388608.0f));
+                                code[0][c] = __float_as_uint(fl.x) & 0x3FFFFFu; code[1][c] = __float_as_uint(fl.y) & 0x3FFFFFu;
+                            }
+                        }
+                        uint8_t* orow = (uint8_t*)prm.out.ptr + (size_t)y * prm.out.pitch;
+                        if (OFMT == MPCVR_SURF_RGBA16F) {
+                            uint4 o;
+                            const __half2 a0 = __halves2half2(hv[0][0], hv[0][1]), a1 = __halves2half2(hv[0][2], __float2half_rn(1.0f));
+                            const __half2 b0 = __halves2half2(hv[1][0], hv[1][1]), b1 = __halves2half2(hv[1][2], __float2half_rn(1.0f));
+                            o.x = *reinterpret_cast<const uint32_t*>(&a0); o.y = *reinterpret_cast<const uint32_t*>(&a1);
+                            o.z = *reinterpret_cast<const uint32_t*>(&b0); o.w = *reinterpret_cast<const uint32_t*>(&b1);
+                            *reinterpret_cast<uint4*>(orow + (size_t)gx * 8) = o;
+                        } else {
+                            uint2 o;
+                            if (OFMT == MPCVR_SURF_RGB10A2) {
+                                o.x = code[0][0] | (code[0][1] << 10) | (code[0][2] << 20) | (3u << 30);
+                                o.y = code[1][0] | (code[1][1] << 10) | (code[1][2] << 20) | (3u << 30);
+                            } else {
+                                o.x = code[0][2] | (code[0][1] << 8) | (code[0][0] << 16) | (255u << 24);
+                                o.y = code[1][2] | (code[1][1] << 8) | (code[1][0] << 16) | (255u << 24);
+                            }
+                            *reinterpret_cast<uint2*>(orow + (size_t)gx * 4) = o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace b200vr

@@ -71,4 +71,52 @@ __device__ __forceinline__ f3x2 convert_color2(const ColorParams& P, const f3x2&
     return c;
 }
 
+constexpr int kGammaN = 1023;      // codes of the UNORM10 threshold table (kernel_fused.cu: EnsureGammaTable)
+
+// ---- two-lane (FFMA2) PQ->SDR convert: f3x2, dp3_2 and pq_channel_to_hable2 live in pixel_ops2.cuh (shared with k_convert2)
+// everything before the final pow: saturate(mul(matrix_conv_prim, ToneMappingHable(ST2084ToLinear(saturate(rgb)))))
+__device__ __forceinline__ f3x2 convert_color_pq2_pre(const ColorParams& P, const f3x2& yuv)
+{
+    f3x2 c;
+    c.x = add2(dp3_2(P.cm[0], yuv), P.cc[0]); c.y = add2(dp3_2(P.cm[1], yuv), P.cc[1]); c.z = add2(dp3_2(P.cm[2], yuv), P.cc[2]);
+    f3x2 h;
+    h.x = pq_channel_to_hable2(P, c.x); h.y = pq_channel_to_hable2(P, c.y); h.z = pq_channel_to_hable2(P, c.z);
+    f3x2 g;
+    g.x = sat2(dp3_2(P.gamut[0], h)); g.y = sat2(dp3_2(P.gamut[1], h)); g.z = sat2(dp3_2(P.gamut[2], h));
+    return g;
+}
+
+__device__ __forceinline__ f3x2 convert_color_pq2(const ColorParams& P, const f3x2& yuv)
+{
+    f3x2 c;
+    c.x = add2(dp3_2(P.cm[0], yuv), P.cc[0]); c.y = add2(dp3_2(P.cm[1], yuv), P.cc[1]); c.z = add2(dp3_2(P.cm[2], yuv), P.cc[2]);
+    f3x2 h;
+    h.x = pq_channel_to_hable2(P, c.x); h.y = pq_channel_to_hable2(P, c.y); h.z = pq_channel_to_hable2(P, c.z);
+    f3x2 o;
+    o.x = powr01_ylt1_2(sat2(dp3_2(P.gamut[0], h)), P.inv_gamma22);
+    o.y = powr01_ylt1_2(sat2(dp3_2(P.gamut[1], h)), P.inv_gamma22);
+    o.z = powr01_ylt1_2(sat2(dp3_2(P.gamut[2], h)), P.inv_gamma22);
+    return o;
+}
+
+__device__ __forceinline__ float2 rt_roundtrip2(int fmt, float2 v)
+{
+    if (fmt == MPCVR_SURF_RGB10A2) return unorm_roundtrip2(v, 1023.0f, 1.0f / 1023.0f);
+    if (fmt == MPCVR_SURF_BGRA8)   return unorm_roundtrip2(v, 255.0f, 1.0f / 255.0f);
+    return make_float2(f16_roundtrip(v.x), f16_roundtrip(v.y));
+}
+
+// gamma + UNORM10 write + read-back through the threshold table (see g_gammaT): x is already saturated
+__device__ __forceinline__ float gamma_q10_thr(float x, const float* __restrict__ sT, const float* __restrict__ sD, uint32_t exc0, uint32_t exc1)
+{
+    float l, e;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l * (1.0f / 2.2f)));
+    const int c0 = (int)fmaf(e, (float)kGammaN, 0.25f);                    // true code is c0 or c0 + 1
+    const uint32_t xb = __float_as_uint(x);
+    int c = c0 + (x >= sT[c0 + 1] ? 1 : 0);
+    c -= (xb == exc0 || xb == exc1) ? 1 : 0;
+    return sD[c];
+}
+
 }  // namespace b200vr

@@ -230,6 +230,18 @@ class VideoProcessor:
     def debug_set_gamma_table(self, enable):
         return self._L.mpcvr_debug_set_gamma_table(int(bool(enable)))
 
+    def debug_set_strip_kernel(self, enable, cfg=0):
+        return self._L.mpcvr_debug_set_strip_kernel(int(bool(enable)), int(cfg))
+
+    def debug_strip_status(self, clear=True):
+        """watchdog record of the persistent 2x kernel: list of 8 ints, [0] = timed-out waits (0 expected)"""
+        import ctypes as C
+        out = (C.c_uint32 * 8)()
+        hr = self._L.mpcvr_debug_strip_status(out, 1 if clear else 0)
+        if hr != 0:
+            raise RuntimeError("mpcvr_debug_strip_status failed")
+        return list(out)
+
     def debug_set_path(self, path):
         return self._check(self._L.mpcvr_debug_set_path(self._h, path), "debug_set_path")
 
