@@ -744,3 +744,110 @@ def test_resize_four_outputs_per_thread_equals_one(cfg):
             vp.debug_set_resize_four(1)
         assert np.array_equal(outs[0], outs[1])
         assert H.compare(outs[0], H.run_oracle(case, planes, pitches), case.backbuffer) == (0, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# persistent warp-specialised 2x kernel (kernel_strip.cuh): TMA-staged source rows, role pipeline P -> A -> B -> C
+# ------------------------------------------------------------------------------------------------
+def _strip_cases():
+    P = O.CF
+    cs = []
+    # strip geometry: widths around the 128-pixel strip, heights around the 4-row quad / 8-row group, tiny frames (fewer quads than SMs)
+    for (w, h) in ((150, 70), (128, 64), (126, 62), (130, 66), (258, 38), (2, 2), (10, 130), (386, 30), (512, 300), (640, 42)):
+        cs.append(H.Case(P["P010"], w, h, 2 * w, 2 * h, H.EX_2020_PQ, up=O.UPSCALE["Lanczos3"], name="strip_p010_%dx%d" % (w, h)))
+    cs.append(H.Case(P["NV12"], 96, 64, 160, 104, H.EX_709, src_rect=(8, 6, 88, 58), up=O.UPSCALE["Lanczos3"], name="strip_nv12_crop"))
+    cs.append(H.Case(P["NV12"], 96, 64, 2 * 77, 2 * 51, H.EX_709, src_rect=(3, 5, 80, 56), up=O.UPSCALE["CatmullRom"], name="strip_nv12_oddcrop"))
+    cs.append(H.Case(P["P010"], 64, 36, 128, 72, H.EX_2020_PQ, dst_rect=(16, 11, 144, 83), win=(160, 100), up=O.UPSCALE["Lanczos3"], name="strip_letterbox"))
+    cs.append(H.Case(P["P210"], 200, 50, 400, 100, H.EX_2020_PQ, up=O.UPSCALE["Lanczos2"], name="strip_p210"))
+    cs.append(H.Case(P["P216"], 136, 40, 272, 80, H.EX_2020_SDR, up=O.UPSCALE["Mitchell"], name="strip_p216_sdr2020"))
+    cs.append(H.Case(P["P016"], 140, 44, 280, 88, H.EX_2020_HLG, up=O.UPSCALE["Mitchell"], name="strip_p016_hlg"))
+    for siting in (1, 5, 7):
+        ex = O.exfmt(chroma=siting, range_=2, matrix=1, prim=2, trc=5)
+        cs.append(H.Case(P["NV12"], 140, 52, 280, 104, ex, up=O.UPSCALE["Lanczos3"], variant=O.VARIANT_D3D9, name="strip_nv12_siting%d" % siting))
+    cs.append(H.Case(P["P010"], 132, 34, 264, 68, H.EX_2020_PQ, backbuffer=O.SURF_RGB10A2, tex=O.TEXFMT_16FLOAT, up=O.UPSCALE["Lanczos3"], name="strip_16f_rgb10"))
+    cs.append(H.Case(P["P010"], 132, 34, 264, 68, H.EX_2020_PQ, backbuffer=O.SURF_RGBA16F, tex=O.TEXFMT_16FLOAT, dither=0, up=O.UPSCALE["Lanczos3"], name="strip_16f_16f"))
+    cs.append(H.Case(P["P010"], 132, 34, 264, 68, H.EX_2020_PQ, tex=O.TEXFMT_8INT, dither=0, up=O.UPSCALE["Lanczos3"], name="strip_8int"))
+    cs.append(H.Case(P["P010"], 132, 34, 264, 68, H.EX_2020_PQ, nits=400, procamp=dict(brightness=12.0, contrast=1.1, hue=10.0, saturation=0.9), up=O.UPSCALE["Lanczos3"], name="strip_procamp"))
+    return cs
+
+
+def _run_strip(case, buf, pitch, enable, cfg=0):
+    vp = case.make_processor(device=0, path=PATH_FUSED)
+    vp.debug_strip_status(clear=True)
+    vp.debug_set_strip_kernel(enable, cfg)
+    try:
+        vp.ProcessSample(data=buf, pitch=pitch)
+        out = vp.ReadBackbuffer()
+    finally:
+        vp.debug_set_strip_kernel(1, 0)
+    st = vp.debug_strip_status(clear=True)
+    assert st[0] == 0, "strip kernel watchdog: %d mbarrier waits timed out (slot %d parity %d iteration %d block %d warp %d)" % tuple(st[:6])
+    return vp, out
+
+
+@pytest.mark.parametrize("case", _strip_cases(), ids=lambda c: c.name)
+def test_strip_kernel_equals_tile_kernel_and_oracle(case):
+    codes = H.make_codes(case.cf, case.w, case.h, "fullnoise", 5)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    ref = H.run_oracle(case, planes, pitches)
+    _, a = _run_strip(case, buf, pitch, 1)
+    _, b = _run_strip(case, buf, pitch, 0)
+    assert H.compare(a, ref, case.backbuffer) == (0, 0)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3])
+def test_strip_kernel_role_splits_give_the_same_frame(cfg):
+    case = H.baseline_cases(scale=0.25)[1]
+    codes = H.make_codes(case.cf, case.w, case.h, "natural", 77)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    ref = H.run_oracle(case, planes, pitches)
+    _, out = _run_strip(case, buf, pitch, 1, cfg)
+    assert H.compare(out, ref, case.backbuffer) == (0, 0)
+
+
+def test_strip_kernel_falls_back_for_unaligned_device_planes():
+    """device samples whose planes / pitches are not 16-byte aligned cannot be addressed by a TMA tensor map: the tile kernel takes them"""
+    import torch
+    case = H.Case(O.CF["P010"], 150, 70, 300, 140, H.EX_2020_PQ, up=O.UPSCALE["Lanczos3"], name="unaligned")
+    codes = H.make_codes(case.cf, case.w, case.h, "noise", 9)
+    pitch = 150 * 2 + 6                                        # 306 bytes: multiple of 2, not of 16
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes, pitch=pitch)
+    ref = H.run_oracle(case, planes, pitches)
+    t = torch.from_numpy(buf).cuda()
+    vp = case.make_processor(device=0, path=PATH_FUSED)
+    vp.ProcessSample(device_planes=[t.data_ptr(), t.data_ptr() + pitch * case.h], device_pitches=[pitch, pitch])
+    torch.cuda.synchronize()
+    assert H.compare(vp.ReadBackbuffer(), ref, case.backbuffer) == (0, 0)
+
+
+def test_two_instances_on_two_streams_render_their_first_frames_concurrently():
+    """round-1 advisor finding: per-device tables must be ready for an instance that never rendered before, whatever another
+    instance on another stream is doing (the dither table is a compile-time constant now; the gamma table build is serialised)"""
+    import threading
+    import torch
+    case = H.baseline_cases(scale=0.25)[1]
+    codes = H.make_codes(case.cf, case.w, case.h, "natural", 78)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    ref = H.run_oracle(case, planes, pitches)
+    outs = [None, None]
+
+    def work(i):
+        torch.cuda.set_device(0)
+        s = torch.cuda.Stream()
+        import videorenderer_b200 as V
+        vp = V.VideoProcessor(case.settings(), device=0, stream=s.cuda_stream)
+        mt = V.VideoProcessor.media_type(case.cf, case.w, case.h, case.ex)
+        assert vp.InitMediaType(mt)
+        vp.SetWindowRect((0, 0, case.dst_w, case.dst_h)); vp.SetVideoRect((0, 0, case.dst_w, case.dst_h))
+        vp.debug_set_path(PATH_FUSED if i == 0 else PATH_AUTO)
+        vp.ProcessSample(data=buf, pitch=pitch)
+        outs[i] = vp.ReadBackbuffer()
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for o in outs:
+        assert o is not None and H.compare(o, ref, case.backbuffer) == (0, 0)

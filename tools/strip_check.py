@@ -109,7 +109,7 @@ def timing(cfgs, steps=300):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-time", action="store_true"); ap.add_argument("--no-check", action="store_true")
-    ap.add_argument("--cfgs", default="0,1,2,3,4,5")
+    ap.add_argument("--cfgs", default="0,1,2,3")
     ap.add_argument("--one", action="store_true", help="run one small case on the strip kernel and print the watchdog record")
     a = ap.parse_args()
     if a.one:

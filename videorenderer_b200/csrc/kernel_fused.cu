@@ -787,7 +787,7 @@ cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
         const bool thr = p.color.transfer == TRANSFER_PQ_TO_SDR && p.src.bytes == 2 && p.internal_fmt == MPCVR_SURF_RGB10A2 &&
                          p.out.fmt == MPCVR_SURF_BGRA8 && p.final_pass && g_useGammaTable && EnsureGammaTable(st);
         int dev = 0; cudaGetDevice(&dev);
-        const bool ok = thr && dev >= 0 && dev < 64;
+        const bool ok = thr && dev >= 0 && dev < 64 && g_gammaExcHost[dev][1] == 0xFFFFFFFFu;   // the strip kernel checks one exception float
         if (launches) *launches = 1;
         const cudaError_t e = LaunchStrip2x(p, ok ? g_gammaTdev[dev] : nullptr, ok ? g_gammaDdev[dev] : nullptr, ok ? g_gammaExcHost[dev] : nullptr, st);
         if (e != cudaErrorNotSupported) return e;

@@ -78,12 +78,12 @@ static cudaError_t LaunchK(const StripParams& prm, int grid, cudaStream_t st)
     return cudaGetLastError();
 }
 
-typedef StripCfg<128, 8, 2, 14, 2> Cfg0;      // 24 warps: 2 P + 14 A + 8 C
-typedef StripCfg<128, 8, 2, 18, 2> Cfg1;      // 28 warps
-typedef StripCfg<128, 8, 2, 22, 2> Cfg2;      // 32 warps
-typedef StripCfg<128, 8, 2, 10, 2> Cfg3;      // 20 warps
-typedef StripCfg<128, 8, 1, 11, 1> Cfg4;      // 16 warps, one consumer warp per column block
-typedef StripCfg<128, 8, 2, 16, 1> Cfg5;      // 22 warps, one consumer warp per column block
+// warp-role splits measured on B200 (C2 frame, us): see DESIGN.md 4.1.  Cfg0 is the default; the others stay selectable through
+// mpcvr_debug_set_strip_kernel for the role-balance experiments.
+typedef StripCfg<128, 8, 4, 12, 4, 8> Cfg0;       // 28 warps: 4 P (two teams of 2) + 12 A + 4 B + 8 C
+typedef StripCfg<128, 8, 4, 10, 4, 8> Cfg1;       // 26 warps
+typedef StripCfg<128, 8, 6, 10, 4, 8> Cfg2;       // 28 warps (P teams of 3)
+typedef StripCfg<128, 8, 8, 10, 2, 8> Cfg3;       // 28 warps (P teams of 4)
 
 template <int NT, bool DUP>
 static cudaError_t LaunchV(const StripParams& prm, int spec, int conv, int grid, cudaStream_t st)
@@ -94,8 +94,6 @@ static cudaError_t LaunchV(const StripParams& prm, int spec, int conv, int grid,
             case 1:  return LaunchK<Cfg1, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             case 2:  return LaunchK<Cfg2, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             case 3:  return LaunchK<Cfg3, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
-            case 4:  return LaunchK<Cfg4, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
-            case 5:  return LaunchK<Cfg5, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             default: break;
             }
         }

@@ -74,22 +74,27 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
     return ok != 0;
 }
 // bounded wait: a protocol bug makes the role give up (the frame is then wrong and g_stripStatus says where it stopped; the
-// launcher's debug query reports it) instead of hanging the device
+// launcher's debug query reports it) instead of hanging the device.  try_wait suspends the thread in hardware for up to the
+// hinted time, so a waiting warp costs a few instructions per microsecond, not per cycle.
 static __device__ unsigned int g_stripStatus[8];       // [0] = failures, [1] = barrier slot, [2] = parity, [3] = iteration, [4] = block, [5] = warp
+__device__ __forceinline__ bool mbar_try_hint(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int it = -1)
 {
     if (mbar_try(bar, parity)) return true;
-    const long long t0 = clock64();
-    while (!mbar_try(bar, parity)) {
-        if (clock64() - t0 > 400000000ll) {
-            if (atomicAdd(&g_stripStatus[0], 1u) == 0) {
-                g_stripStatus[1] = (bar & 127u) >> 3; g_stripStatus[2] = parity; g_stripStatus[3] = (unsigned)it;
-                g_stripStatus[4] = blockIdx.x; g_stripStatus[5] = threadIdx.x >> 5;
-            }
-            return false;
-        }
+    #pragma unroll 1
+    for (int n = 0; n < (1 << 17); n++)
+        if (mbar_try_hint(bar, parity)) return true;
+    if (atomicAdd(&g_stripStatus[0], 1u) == 0) {
+        g_stripStatus[1] = (bar & 255u) >> 3; g_stripStatus[2] = parity; g_stripStatus[3] = (unsigned)it;
+        g_stripStatus[4] = blockIdx.x; g_stripStatus[5] = threadIdx.x >> 5;
     }
-    return true;
+    return false;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar)
 {
@@ -102,29 +107,31 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) { float d; a
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; }
 
 // ---- geometry ---------------------------------------------------------------------------------------------------------
-template <int SW_, int R_, int NP_, int NA_, int W_>
+template <int SW_, int R_, int NP_, int NA_, int NB_, int NC_>
 struct StripCfg {
     static constexpr int SW = SW_;                 // convert-surface pixels per strip
     static constexpr int R = R_;                   // convert rows per row group
-    static constexpr int NP = NP_, NA = NA_, W = W_;
+    static constexpr int NP = NP_, NA = NA_, NB = NB_, NC = NC_;      // warps per role
     static constexpr int CB = SW / 32;             // column blocks of 32 core pixels (= 64 outputs, one warp wide)
-    static constexpr int NC = CB * W;              // consumer warps
-    static constexpr int THREADS = 32 * (NP + NA + NC);
+    static constexpr int THREADS = 32 * (NP + NA + NB + NC);
     static constexpr int WP = SW + 8;              // window pitch in pixels (window = SW + NT <= WP)
     static constexpr int PAIRS = WP / 2;
     static constexpr int CP = SW / 2 + 8;          // chroma texels per box row
     static constexpr int RCMAX = R + 1;            // chroma rows per group: R/2 + 2 (4:2:0) or R + 1 (4:2:2)
     static constexpr int RING = 32;                // rows of the X-pass ring (>= 2R + NT + 6)
-    static constexpr int NRAW = 3;                 // TMA stages
+    static constexpr int NRAW = 4;                 // TMA stages (two per P team)
+    static constexpr int PT = NP / 2;              // role P works as two teams of PT warps on alternate row groups
+    static constexpr int NS = 3;                   // stages of the P -> A (prep) and A -> C (conv) rings
     static_assert(RING >= 2 * R + 6 + 6, "ring too small");
-    static_assert((R % 4) == 0 && (R * 8) % (W * 32) == 0, "X-pass items must tile the column block's threads");
+    static_assert(R == 8 && RING == 4 * R && (NB % 2) == 0, "the X-pass ring is four row groups; X-pass warps work in pairs");
+    static_assert((NP % 2) == 0, "two P teams");
     static constexpr int align128(int x) { return (x + 127) / 128 * 128; }
     // shared memory layout (byte offsets)
-    static constexpr int oBars = 0;                                   // 16 mbarriers
-    static constexpr int oT = 128;
+    static constexpr int oBars = 0;                                   // 28 mbarriers
+    static constexpr int oT = 256;
     static constexpr int oD = oT + align128((kGammaN + 2) * 4);
     static constexpr int oDith = oD + align128((kGammaN + 1) * 4);
-    static constexpr int oRawY = oDith + 4096;
+    static constexpr int oRawY = oDith + 8192;                         // dither table stored twice (64 rows): 8 consecutive rows never wrap
     // TMA boxes start on 16-byte boundaries of the plane rows (the hardware rejects other inner coordinates), so the boxes are
     // wider than the window by the worst-case misalignment
     static constexpr int LBOX16 = WP + 8, LBOX8 = WP + 24;            // luma box width in texels (16-bit / 8-bit components)
@@ -138,16 +145,17 @@ struct StripCfg {
     static constexpr int oHU = oCv + szC;
     static constexpr int szH = align128(RCMAX * WP * 4);
     static constexpr int oHV = oHU + szH;
-    static constexpr int oPrep = oHV + szH;
+    static constexpr int szScratch = 2 * szC + 2 * szH;              // per P team: chroma texels (u, v) + horizontally reconstructed rows (u, v)
+    static constexpr int oPrep = oCu + 2 * szScratch;
     static constexpr int szPlane = R * WP * 4;                        // one fp32 plane of a row group
-    static constexpr int oConv = oPrep + 2 * 3 * szPlane;
-    static constexpr int oX = oConv + 2 * 3 * szPlane;
+    static constexpr int oConv = oPrep + NS * 3 * szPlane;
+    static constexpr int oX = oConv + NS * 3 * szPlane;
     static constexpr int szX = 3 * RING * 2 * SW * 2;                 // [3][RING][2 SW] halfs
     static constexpr int smem_bytes = oX + szX;
 };
 
 // barrier slots
-enum { B_RAWFULL = 0, B_RAWEMPTY = 3, B_PREPFULL = 6, B_PREPEMPTY = 8, B_CONVFULL = 10, B_CONVEMPTY = 12, B_COUNT = 14 };
+enum { B_RAWFULL = 0, B_RAWEMPTY = 4, B_PREPFULL = 8, B_PREPEMPTY = 11, B_CONVFULL = 14, B_CONVEMPTY = 17, B_XFULL = 20, B_XDONE = 24, B_COUNT = 28 };
 
 // the (strip, quad range) segments a CTA owns and their row groups; every role walks the same sequence
 template <class C, int NT>
@@ -173,6 +181,54 @@ struct GroupIter {
     __device__ __forceinline__ int rows() const { return min(C::R, wyB - cy0() + 1); }
 };
 
+// X pass (TextureResizeShader AXIS 0, 2x interpolation) of one row group for one column block: item = (channel, row, 8 outputs).
+// XEDGE: the block's window crosses the left / right border of the convert surface -> CLAMP addressing of the taps.
+template <class C, int NT, bool DUP, bool XEDGE>
+__device__ __forceinline__ void xpass_rows(const float* __restrict__ conv, __half* __restrict__ sX, const float (&wE)[NT], const float (&wO)[NT],
+                                           int rows, int ring0, int cb, int tCB, int cx0, int w1)
+{
+    constexpr int TCB = 64;                                          // a pair of warps per column block
+    #pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float* plane = conv + c * (C::szPlane / 4);
+        for (int idx = tCB; idx < rows * 8; idx += TCB) {
+            const int row = idx >> 3, b = idx & 7;
+            const float* src = plane + row * C::WP + 32 * cb + 4 * b;
+            float v[NT + 4];
+            if (!XEDGE) {
+                const float4 a = *reinterpret_cast<const float4*>(src), d = *reinterpret_cast<const float4*>(src + 4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
+                if (NT == 6) { const float2 e = *reinterpret_cast<const float2*>(src + 8); v[8] = e.x; v[9] = e.y; }
+            } else {
+                #pragma unroll
+                for (int i = 0; i < NT + 4; i++) {
+                    const int wx = min(max(cx0 + 32 * cb + 4 * b + i, 0), w1 - 1) - cx0;
+                    v[i] = plane[row * C::WP + wx];
+                }
+            }
+            __half2 o[4];
+            #pragma unroll
+            for (int q = 0; q < 4; q++) {
+                float e = __fmul_rn(wE[0], v[q]), d = __fmul_rn(wO[0], v[q + 1]);
+                #pragma unroll
+                for (int k = 1; k < NT; k++) {
+                    // D3D11 lanczos3 re-reads tap 0's texel for tap 1 (ps_interpolation_lanczos3.hlsl:33-34)
+                    const float te = (NT == 6 && k == 1 && DUP) ? v[q] : v[q + k];
+                    const float to = (NT == 6 && k == 1 && DUP) ? v[q + 1] : v[q + 1 + k];
+                    e = fma_rn(wE[k], te, e);
+                    d = fma_rn(wO[k], to, d);
+                }
+                o[q] = __floats2half2_rn(e, d);                       // m_TexResize is RGBA16F
+            }
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&o[0]); pk.y = *reinterpret_cast<uint32_t*>(&o[1]);
+            pk.z = *reinterpret_cast<uint32_t*>(&o[2]); pk.w = *reinterpret_cast<uint32_t*>(&o[3]);
+            const int ring = (ring0 + row) & (C::RING - 1);
+            *reinterpret_cast<uint4*>(sX + ((size_t)(c * C::RING + ring) * 2 * C::SW) + 64 * cb + 8 * b) = pk;
+        }
+    }
+}
+
 template <class C, int NT, bool DUP, int SPEC, int CONV>
 __global__ void __launch_bounds__(C::THREADS, 1)
 k_strip2x(const __grid_constant__ StripParams prm)
@@ -185,18 +241,19 @@ k_strip2x(const __grid_constant__ StripParams prm)
     float* sDith = reinterpret_cast<float*>(smem + C::oDith);      // NEGATED dither values when SPEC == SSPEC_10_BGRA8_DITHER
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < C::NRAW; i++) { mbar_init(sbase + 8 * (B_RAWFULL + i), 1); mbar_init(sbase + 8 * (B_RAWEMPTY + i), C::NP); }
-        for (int i = 0; i < 2; i++) {
-            mbar_init(sbase + 8 * (B_PREPFULL + i), C::NP);  mbar_init(sbase + 8 * (B_PREPEMPTY + i), C::NA);
-            mbar_init(sbase + 8 * (B_CONVFULL + i), C::NA);  mbar_init(sbase + 8 * (B_CONVEMPTY + i), C::NC);
+        for (int i = 0; i < C::NRAW; i++) { mbar_init(sbase + 8 * (B_RAWFULL + i), 1); mbar_init(sbase + 8 * (B_RAWEMPTY + i), C::PT); }
+        for (int i = 0; i < C::NS; i++) {
+            mbar_init(sbase + 8 * (B_PREPFULL + i), C::PT);  mbar_init(sbase + 8 * (B_PREPEMPTY + i), C::NA);
+            mbar_init(sbase + 8 * (B_CONVFULL + i), C::NA);  mbar_init(sbase + 8 * (B_CONVEMPTY + i), C::NB);
         }
+        for (int i = 0; i < 4; i++) { mbar_init(sbase + 8 * (B_XFULL + i), C::NB); mbar_init(sbase + 8 * (B_XDONE + i), C::NC); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (CONV == SCONV_PQ_THR) {
         for (int i = threadIdx.x; i < kGammaN + 2; i += C::THREADS) sT[i] = prm.gT[i];
         for (int i = threadIdx.x; i < kGammaN + 1; i += C::THREADS) sD[i] = prm.gD[i];
     }
-    for (int i = threadIdx.x; i < 1024; i += C::THREADS) sDith[i] = (SPEC == SSPEC_10_BGRA8_DITHER) ? -g_dither32_strip.v[i] : g_dither32_strip.v[i];
+    for (int i = threadIdx.x; i < 2048; i += C::THREADS) sDith[i] = (SPEC == SSPEC_10_BGRA8_DITHER) ? -g_dither32_strip.v[i & 1023] : g_dither32_strip.v[i & 1023];
     __syncthreads();
 
     const long long total = (long long)prm.strips * prm.nq;
@@ -205,30 +262,34 @@ k_strip2x(const __grid_constant__ StripParams prm)
 
     if (warp < C::NP) {
         // ================================================================================================ TMA + role P
-        constexpr int TP = C::NP * 32;
-        const int tP = threadIdx.x;
+        asm volatile("pmevent 1;");                                      // marks the role in SASS listings / ncu source pages (PMTRIG)
+        constexpr int TP = C::PT * 32;                                    // threads of one team
+        const int team = warp / C::PT, tP = threadIdx.x - team * TP;
         GroupIter<C, NT> gi; gi.init(Q0, Q1, prm.nq, prm.b0, prm.h1);
-        GroupIter<C, NT> iss = gi; int it_iss = 0;                       // issue cursor (thread 0 only)
-        float* sCu = reinterpret_cast<float*>(smem + C::oCu); float* sCv = reinterpret_cast<float*>(smem + C::oCv);
-        float* sHU = reinterpret_cast<float*>(smem + C::oHU); float* sHV = reinterpret_cast<float*>(smem + C::oHV);
+        GroupIter<C, NT> iss = gi; int it_iss = 0;                       // issue cursor (thread 0 of each team, for the team's own groups)
+        float* sCu = reinterpret_cast<float*>(smem + C::oCu + team * C::szScratch); float* sCv = sCu + C::szC / 4;
+        float* sHU = sCv + C::szC / 4; float* sHV = sHU + C::szH / 4;
         const int bytes = prm.bytes, ox = prm.ox, oy = prm.oy, my = prm.my, RC = prm.rc_rows;
         const int lmask = 16 / bytes - 1, cmask = 8 / bytes - 1;          // box origins are multiples of 16 bytes
         const int cbox = bytes == 2 ? C::CBOX32 : C::CBOX16;
         for (int it = 0; gi.valid; it++, gi.advance()) {
+            if ((it & 1) != team) continue;
             if (tP == 0) {
                 while (iss.valid && it_iss < it + C::NRAW) {
-                    const int slot = it_iss % C::NRAW;
-                    if (!mbar_wait(sbase + 8 * (B_RAWEMPTY + slot), ((it_iss / C::NRAW) & 1) ^ 1, it_iss)) break;
-                    const uint32_t full = sbase + 8 * (B_RAWFULL + slot);
-                    mbar_expect_tx(full, (uint32_t)(prm.luma_bytes + prm.chroma_bytes));
-                    const int X0 = prm.rect_l + iss.s * C::SW + prm.b0, sy0 = prm.rect_t + iss.cy0();
-                    tma_load_2d(sbase + C::oRawY + slot * C::szRawY, &prm.tmY, X0 & ~lmask, sy0, full);
-                    tma_load_2d(sbase + C::oRawC + slot * C::szRawC, &prm.tmC, ((2 * X0 + ox) >> 2) & ~cmask, (my * sy0 + oy) >> 2, full);
+                    if ((it_iss & 1) == team) {
+                        const int slot = it_iss % C::NRAW;
+                        if (!mbar_wait(sbase + 8 * (B_RAWEMPTY + slot), ((it_iss / C::NRAW) & 1) ^ 1, it_iss)) break;
+                        const uint32_t full = sbase + 8 * (B_RAWFULL + slot);
+                        mbar_expect_tx(full, (uint32_t)(prm.luma_bytes + prm.chroma_bytes));
+                        const int X0 = prm.rect_l + iss.s * C::SW + prm.b0, sy0 = prm.rect_t + iss.cy0();
+                        tma_load_2d(sbase + C::oRawY + slot * C::szRawY, &prm.tmY, X0 & ~lmask, sy0, full);
+                        tma_load_2d(sbase + C::oRawC + slot * C::szRawC, &prm.tmC, ((2 * X0 + ox) >> 2) & ~cmask, (my * sy0 + oy) >> 2, full);
+                    }
                     it_iss++; iss.advance();
                 }
             }
             __syncwarp();
-            const int slot = it % C::NRAW, pslot = it & 1;
+            const int slot = it % C::NRAW, pslot = it % C::NS;
             const int rows = gi.rows();
             const int X0 = prm.rect_l + gi.s * C::SW + prm.b0, sy0 = prm.rect_t + gi.cy0();
             const int ux0 = (2 * X0 + ox) >> 2, uy0 = (my * sy0 + oy) >> 2;
@@ -239,7 +300,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
             float2* pU = reinterpret_cast<float2*>(smem + C::oPrep + (pslot * 3 + 1) * C::szPlane);
             float2* pV = reinterpret_cast<float2*>(smem + C::oPrep + (pslot * 3 + 2) * C::szPlane);
             if (!mbar_wait(sbase + 8 * (B_RAWFULL + slot), (it / C::NRAW) & 1, it)) return;
-            if (!mbar_wait(sbase + 8 * (B_PREPEMPTY + pslot), ((it >> 1) & 1) ^ 1, it)) return;
+            if (!mbar_wait(sbase + 8 * (B_PREPEMPTY + pslot), ((it / C::NS) & 1) ^ 1, it)) return;
             // P0: luma codes -> floats (UNORM read)
             for (int k = tP; k < rows * C::PAIRS; k += TP) {
                 const int r = k / C::PAIRS, p = k - r * C::PAIRS;
@@ -248,17 +309,28 @@ k_strip2x(const __grid_constant__ StripParams prm)
                 else            { const uint8_t* q = rawY + r * prm.luma_pitch + xoff + 2 * p; y = make_float2(unorm8(q[0]), unorm8(q[1])); }
                 pY[k] = y;
             }
-            // P1: chroma texels -> floats, sampler CLAMP at the plane borders
-            for (int k = tP; k < RC * C::CP; k += TP) {
-                const int rr = k / C::CP, c = k - rr * C::CP;
-                const int cl = min(max(min(max(ux0 + c, 0), prm.cw - 1) - ux0 + uoff, 0), cbox - 1);
-                const int rl = min(max(min(max(uy0 + rr, 0), prm.ch - 1) - uy0, 0), RC - 1);
-                float u, v;
-                if (bytes == 2) { const uint32_t w = *reinterpret_cast<const uint32_t*>(rawC + rl * prm.chroma_pitch + 4 * cl); u = unorm16(w & 0xFFFFu); v = unorm16(w >> 16); }
-                else            { const uint32_t w = *reinterpret_cast<const uint16_t*>(rawC + rl * prm.chroma_pitch + 2 * cl); u = unorm8(w & 255u); v = unorm8(w >> 8); }
-                sCu[k] = u; sCv[k] = v;
+            // P1: chroma texels -> floats, sampler CLAMP at the plane borders (interior boxes skip the clamps)
+            const bool cedge = ux0 < 0 || uy0 < 0 || ux0 + C::CP > prm.cw || uy0 + RC > prm.ch;
+            if (!cedge) {
+                for (int k = tP; k < RC * C::CP; k += TP) {
+                    const int rr = k / C::CP, c = k - rr * C::CP;
+                    float u, v;
+                    if (bytes == 2) { const uint32_t w = *reinterpret_cast<const uint32_t*>(rawC + rr * prm.chroma_pitch + 4 * (c + uoff)); u = unorm16(w & 0xFFFFu); v = unorm16(w >> 16); }
+                    else            { const uint32_t w = *reinterpret_cast<const uint16_t*>(rawC + rr * prm.chroma_pitch + 2 * (c + uoff)); u = unorm8(w & 255u); v = unorm8(w >> 8); }
+                    sCu[k] = u; sCv[k] = v;
+                }
+            } else {
+                for (int k = tP; k < RC * C::CP; k += TP) {
+                    const int rr = k / C::CP, c = k - rr * C::CP;
+                    const int cl = min(max(min(max(ux0 + c, 0), prm.cw - 1) - ux0 + uoff, 0), cbox - 1);
+                    const int rl = min(max(min(max(uy0 + rr, 0), prm.ch - 1) - uy0, 0), RC - 1);
+                    float u, v;
+                    if (bytes == 2) { const uint32_t w = *reinterpret_cast<const uint32_t*>(rawC + rl * prm.chroma_pitch + 4 * cl); u = unorm16(w & 0xFFFFu); v = unorm16(w >> 16); }
+                    else            { const uint32_t w = *reinterpret_cast<const uint16_t*>(rawC + rl * prm.chroma_pitch + 2 * cl); u = unorm8(w & 255u); v = unorm8(w >> 8); }
+                    sCu[k] = u; sCv[k] = v;
+                }
             }
-            named_bar(1, TP);
+            named_bar(1 + team, TP);
             // P2: horizontal bilinear reconstruction at the luma columns (top / bot of the bilinear sample)
             for (int k = tP; k < RC * C::PAIRS; k += TP) {
                 const int rr = k / C::PAIRS, p = k - rr * C::PAIRS;
@@ -270,7 +342,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
                 reinterpret_cast<float2*>(sHU)[k] = fma2(fx, sub2(ub, ua), ua);
                 reinterpret_cast<float2*>(sHV)[k] = fma2(fx, sub2(vb, va), va);
             }
-            named_bar(1, TP);
+            named_bar(1 + team, TP);
             // P3: vertical interpolation at the luma rows
             for (int k = tP; k < rows * C::PAIRS; k += TP) {
                 const int r = k / C::PAIRS, p = k - r * C::PAIRS;
@@ -287,13 +359,15 @@ k_strip2x(const __grid_constant__ StripParams prm)
         }
     } else if (warp < C::NP + C::NA) {
         // ================================================================================================ role A
+        asm volatile("pmevent 2;");
         constexpr int TA = C::NA * 32;
         const int tA = threadIdx.x - C::NP * 32;
         GroupIter<C, NT> gi; gi.init(Q0, Q1, prm.nq, prm.b0, prm.h1);
         int stream = 0;                                                 // items handed out so far, modulo TA
-        const uint32_t exc0 = prm.exc0, exc1 = prm.exc1;
+        const uint32_t exc0 = prm.exc0;
+        const float ym2s = prm.color.inv_m2 * 1.1920928955078125e-07f, ym1s = prm.color.inv_m1 * 1.1920928955078125e-07f;   // exponents * 2^-23 (exact)
         for (int it = 0; gi.valid; it++, gi.advance()) {
-            const int slot = it & 1;
+            const int slot = it % C::NS; const uint32_t ph = (it / C::NS) & 1;
             const int items = gi.rows() * C::PAIRS;
             const float2* pY = reinterpret_cast<const float2*>(smem + C::oPrep + (slot * 3 + 0) * C::szPlane);
             const float2* pU = reinterpret_cast<const float2*>(smem + C::oPrep + (slot * 3 + 1) * C::szPlane);
@@ -301,16 +375,16 @@ k_strip2x(const __grid_constant__ StripParams prm)
             float2* c0 = reinterpret_cast<float2*>(smem + C::oConv + (slot * 3 + 0) * C::szPlane);
             float2* c1 = reinterpret_cast<float2*>(smem + C::oConv + (slot * 3 + 1) * C::szPlane);
             float2* c2 = reinterpret_cast<float2*>(smem + C::oConv + (slot * 3 + 2) * C::szPlane);
-            if (!mbar_wait(sbase + 8 * (B_PREPFULL + slot), (it >> 1) & 1, it)) return;
-            if (!mbar_wait(sbase + 8 * (B_CONVEMPTY + slot), ((it >> 1) & 1) ^ 1, it)) return;
+            if (!mbar_wait(sbase + 8 * (B_PREPFULL + slot), ph, it)) return;
+            if (!mbar_wait(sbase + 8 * (B_CONVEMPTY + slot), ph ^ 1, it)) return;
             int k = tA - stream; if (k < 0) k += TA;
             for (; k < items; k += TA) {
                 f3x2 yuv; yuv.x = pY[k]; yuv.y = pU[k]; yuv.z = pV[k];
                 if (CONV == SCONV_PQ_THR) {
-                    const f3x2 g = convert_color_pq2_pre(prm.color, yuv);            // saturated gamut-mapped linear light
-                    c0[k] = make_float2(gamma_q10_thr(g.x.x, sT, sD, exc0, exc1), gamma_q10_thr(g.x.y, sT, sD, exc0, exc1));
-                    c1[k] = make_float2(gamma_q10_thr(g.y.x, sT, sD, exc0, exc1), gamma_q10_thr(g.y.y, sT, sD, exc0, exc1));
-                    c2[k] = make_float2(gamma_q10_thr(g.z.x, sT, sD, exc0, exc1), gamma_q10_thr(g.z.y, sT, sD, exc0, exc1));
+                    const f3x2 g = convert_color_pq2_pre_s(prm.color, ym2s, ym1s, yuv);      // saturated gamut-mapped linear light
+                    c0[k] = make_float2(gamma_q10_thr1(g.x.x, sT, sD, exc0), gamma_q10_thr1(g.x.y, sT, sD, exc0));
+                    c1[k] = make_float2(gamma_q10_thr1(g.y.x, sT, sD, exc0), gamma_q10_thr1(g.y.y, sT, sD, exc0));
+                    c2[k] = make_float2(gamma_q10_thr1(g.z.x, sT, sD, exc0), gamma_q10_thr1(g.z.y, sT, sD, exc0));
                 } else {
                     const f3x2 rgb = (CONV == SCONV_PQ) ? convert_color_pq2(prm.color, yuv) : convert_color2(prm.color, yuv);
                     c0[k] = rt_roundtrip2(IFMT, rgb.x); c1[k] = rt_roundtrip2(IFMT, rgb.y); c2[k] = rt_roundtrip2(IFMT, rgb.z);
@@ -320,11 +394,38 @@ k_strip2x(const __grid_constant__ StripParams prm)
             __syncwarp();
             if (lane == 0) { mbar_arrive(sbase + 8 * (B_CONVFULL + slot)); mbar_arrive(sbase + 8 * (B_PREPEMPTY + slot)); }
         }
+    } else if (warp < C::NP + C::NA + C::NB) {
+        // ================================================================================================ role B: X pass
+        asm volatile("pmevent 3;");
+        const int wb = warp - C::NP - C::NA, pair = wb >> 1, tB = (wb & 1) * 32 + lane;
+        __half* sX = reinterpret_cast<__half*>(smem + C::oX);
+        float wE[NT], wO[NT];
+        #pragma unroll
+        for (int k = 0; k < NT; k++) { wE[k] = prm.wE[k]; wO[k] = prm.wO[k]; }
+        GroupIter<C, NT> gi; gi.init(Q0, Q1, prm.nq, prm.b0, prm.h1);
+        int it0 = 0;
+        for (int it = 0; gi.valid; it++, gi.advance()) {
+            if (gi.g == 0) it0 = it;
+            const int slot = it % C::NS; const uint32_t ph = (it / C::NS) & 1;
+            const int cx0 = gi.s * C::SW + prm.b0;                       // convert-surface column of window column 0
+            if (!mbar_wait(sbase + 8 * (B_CONVFULL + slot), ph, it)) return;
+            // ring slot it % 4 held the rows of group it - 4; their last readers are the quads completed by group it - 3
+            if (it >= 3 && !mbar_wait(sbase + 8 * (B_XDONE + ((it - 3) & 3)), ((it - 3) >> 2) & 1, it)) return;
+            const int rows = gi.rows(), ring0 = gi.cy0() - gi.wyA + C::R * it0;
+            const float* conv = reinterpret_cast<const float*>(smem + C::oConv + slot * 3 * C::szPlane);
+            for (int cb = pair; cb < C::CB; cb += C::NB / 2) {
+                if (gi.s * C::SW + 32 * cb >= prm.w1) continue;
+                const bool xedge = (cx0 + 32 * cb < 0) || (cx0 + 32 * cb + 32 + NT > prm.w1);
+                if (!xedge) xpass_rows<C, NT, DUP, false>(conv, sX, wE, wO, rows, ring0, cb, tB, 0, 0);
+                else        xpass_rows<C, NT, DUP, true>(conv, sX, wE, wO, rows, ring0, cb, tB, cx0, prm.w1);
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(sbase + 8 * (B_CONVEMPTY + slot)); mbar_arrive(sbase + 8 * (B_XFULL + (it & 3))); }
+        }
     } else {
-        // ================================================================================================ role C
-        const int wc = warp - C::NP - C::NA, cb = wc / C::W, sw = wc - cb * C::W;
-        const int tCB = sw * 32 + lane;                                  // thread index inside the column block's warps
-        constexpr int TCB = C::W * 32;
+        // ================================================================================================ role C: Y pass + final pass
+        asm volatile("pmevent 4;");
+        const int wc = warp - C::NP - C::NA - C::NB;
         const int  OFMT  = SPEC != SSPEC_RUNTIME ? (int)MPCVR_SURF_BGRA8 : prm.out.fmt;
         const bool FINAL = SPEC == SSPEC_10_BGRA8_DITHER ? true : (SPEC == SSPEC_8_BGRA8 ? false : prm.final_pass != 0);
         __half* sX = reinterpret_cast<__half*>(smem + C::oX);
@@ -332,85 +433,46 @@ k_strip2x(const __grid_constant__ StripParams prm)
         #pragma unroll
         for (int k = 0; k < NT; k++) { wE[k] = prm.wE[k]; wO[k] = prm.wO[k]; }
         GroupIter<C, NT> gi; gi.init(Q0, Q1, prm.nq, prm.b0, prm.h1);
-        int qnext = 0;
+        int qnext = 0, it0 = 0, turn = 0;                                // turn: items handed out so far, modulo NC
         for (int it = 0; gi.valid; it++, gi.advance()) {
-            const int slot = it & 1;
-            const int cx0 = gi.s * C::SW + prm.b0;                       // convert-surface column of window column 0
-            const int colbase = gi.s * C::SW + 32 * cb;                  // first core column of this block
-            const bool active = colbase < prm.w1;
-            if (gi.g == 0) { named_bar(2 + cb, TCB); qnext = gi.qa; }    // new segment: the ring restarts
-            if (!mbar_wait(sbase + 8 * (B_CONVFULL + slot), (it >> 1) & 1, it)) return;
-            const int rows = gi.rows(), cy0 = gi.cy0();
-            // ---- X pass of the group's rows: item = (channel, row, block of 8 outputs)
-            if (active) {
-                const bool xedge = (cx0 + 32 * cb < 0) || (cx0 + 32 * cb + 32 + NT > prm.w1);
-                #pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const float* plane = reinterpret_cast<const float*>(smem + C::oConv + (slot * 3 + c) * C::szPlane);
-                    for (int idx = tCB; idx < rows * 8; idx += TCB) {
-                        const int row = idx >> 3, b = idx & 7;
-                        const float* src = plane + row * C::WP + 32 * cb + 4 * b;
-                        float v[NT + 4];
-                        if (!xedge) {
-                            const float4 a = *reinterpret_cast<const float4*>(src), d = *reinterpret_cast<const float4*>(src + 4);
-                            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
-                            if (NT == 6) { const float2 e = *reinterpret_cast<const float2*>(src + 8); v[8] = e.x; v[9] = e.y; }
-                        } else {
-                            #pragma unroll
-                            for (int i = 0; i < NT + 4; i++) {                    // CLAMP addressing of the X taps
-                                const int wx = min(max(cx0 + 32 * cb + 4 * b + i, 0), prm.w1 - 1) - cx0;
-                                v[i] = plane[row * C::WP + wx];
-                            }
-                        }
-                        __half2 o[4];
-                        #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            float e = __fmul_rn(wE[0], v[q]), d = __fmul_rn(wO[0], v[q + 1]);
-                            #pragma unroll
-                            for (int k = 1; k < NT; k++) {
-                                // D3D11 lanczos3 re-reads tap 0's texel for tap 1 (ps_interpolation_lanczos3.hlsl:33-34)
-                                const float te = (NT == 6 && k == 1 && DUP) ? v[q] : v[q + k];
-                                const float to = (NT == 6 && k == 1 && DUP) ? v[q + 1] : v[q + 1 + k];
-                                e = fma_rn(wE[k], te, e);
-                                d = fma_rn(wO[k], to, d);
-                            }
-                            o[q] = __floats2half2_rn(e, d);                       // m_TexResize is RGBA16F
-                        }
-                        uint4 pk;
-                        pk.x = *reinterpret_cast<uint32_t*>(&o[0]); pk.y = *reinterpret_cast<uint32_t*>(&o[1]);
-                        pk.z = *reinterpret_cast<uint32_t*>(&o[2]); pk.w = *reinterpret_cast<uint32_t*>(&o[3]);
-                        const int ring = (cy0 + row - gi.wyA) & (C::RING - 1);
-                        *reinterpret_cast<uint4*>(sX + ((size_t)(c * C::RING + ring) * 2 * C::SW) + 64 * cb + 8 * b) = pk;
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sbase + 8 * (B_CONVEMPTY + slot));
-            named_bar(2 + cb, TCB);
-            // ---- Y pass + rounding + final pass for the quads whose rows are now complete
-            const int cyLast = cy0 + rows - 1;
+            if (gi.g == 0) { it0 = it; qnext = gi.qa; }
+            if (!mbar_wait(sbase + 8 * (B_XFULL + (it & 3)), (it >> 2) & 1, it)) return;
+            // ---- Y pass + rounding + final pass for the quads whose rows are now complete; item = (quad, column block)
+            const int cyLast = gi.cy0() + gi.rows() - 1;
             for (; qnext < gi.qb && min(4 * qnext + 3 + prm.b0 + NT, prm.h1 - 1) <= cyLast; qnext++) {
-                if (!active || ((qnext - gi.qa) % C::W) != sw) continue;
+              for (int cb = 0; cb < C::CB; cb++) {
+                const bool mine = turn == wc;
+                turn = (turn + 1 == C::NC) ? 0 : turn + 1;
+                if (!mine) continue;
                 const int q = qnext;
-                const int col = colbase + lane;                                    // convert-surface column of this lane's output pair
+                const int col = gi.s * C::SW + 32 * cb + lane;                     // convert-surface column of this lane's output pair
                 if (col >= prm.w1) continue;
                 const int jy = 4 * q;                                              // first convert row of the quad
                 const int gx = prm.dst_x0 + 2 * col, gy = prm.dst_y0 + 2 * jy;
                 const bool yedge = (jy + prm.b0 < 0) || (jy + 3 + prm.b0 + NT > prm.h1 - 1);
-                int ringrow[NT + 4];
-                #pragma unroll
-                for (int r = 0; r < NT + 4; r++) {
-                    int cy = jy + prm.b0 + r;
-                    if (yedge) cy = min(max(cy, 0), prm.h1 - 1);                   // CLAMP addressing of the Y taps
-                    ringrow[r] = (cy - gi.wyA) & (C::RING - 1);
+                // byte offsets of the ring rows the quad reads (row pitch 4*SW bytes; RING = 32 rows wrap through the top 5 bits)
+                constexpr int ROWB = 2 * C::SW * 2;
+                static_assert(C::RING == 32, "ring arithmetic below assumes 32 rows");
+                const int rbase = C::R * it0 - gi.wyA;                             // ring row of convert row cy: (cy + rbase) mod 32
+                uint32_t roff[NT + 4];
+                if (!yedge) {
+                    const uint32_t t = (uint32_t)(jy + prm.b0 + rbase) << 27;
+                    #pragma unroll
+                    for (int r = 0; r < NT + 4; r++) roff[r] = ((t + ((uint32_t)r << 27)) >> 27) * ROWB;
+                } else {
+                    #pragma unroll
+                    for (int r = 0; r < NT + 4; r++) {
+                        const int cy = min(max(jy + prm.b0 + r, 0), prm.h1 - 1);         // CLAMP addressing of the Y taps
+                        roff[r] = (uint32_t)((cy + rbase) & (C::RING - 1)) * ROWB;
+                    }
                 }
                 const int nrows = min(8, 2 * (prm.h1 - jy));                       // output rows of this quad that exist
-                const __half* colp = sX + 64 * cb + 2 * lane;
+                const char* colp = reinterpret_cast<const char*>(sX + 64 * cb + 2 * lane);
                 if (SPEC == SSPEC_10_BGRA8_DITHER) {
                     // channel-sequential: B, G, R; codes are packed as they appear (two PRMTs per pixel)
                     float2 nd[8];
                     #pragma unroll
-                    for (int r = 0; r < 8; r++) nd[r] = *reinterpret_cast<const float2*>(sDith + (((gy + r) & 31) << 5) + (gx & 31));
+                    for (int r = 0; r < 8; r++) nd[r] = *reinterpret_cast<const float2*>(sDith + ((gy & 31) << 5) + (gx & 31) + 32 * r);
                     uint32_t w0[8], w1[8];
                     #pragma unroll
                     for (int cc = 0; cc < 3; cc++) {
@@ -418,7 +480,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
                         float2 v[NT + 4];
                         #pragma unroll
                         for (int r = 0; r < NT + 4; r++)
-                            v[r] = __half22float2(*reinterpret_cast<const __half2*>(colp + (size_t)(c * C::RING + ringrow[r]) * 2 * C::SW));
+                            v[r] = __half22float2(*reinterpret_cast<const __half2*>(colp + roff[r] + c * C::RING * ROWB));
                         #pragma unroll
                         for (int qq = 0; qq < 4; qq++) {
                             float2 e = mul2(v[qq], wE[0]), d = mul2(v[qq + 1], wO[0]);
@@ -449,11 +511,10 @@ k_strip2x(const __grid_constant__ StripParams prm)
                         }
                     }
                     uint8_t* orow = (uint8_t*)prm.out.ptr + (size_t)gy * prm.out.pitch + (size_t)gx * 4;
+                    const uint32_t opitch = (uint32_t)prm.out.pitch;
                     #pragma unroll
-                    for (int r = 0; r < 8; r++) {
-                        if (r < nrows) *reinterpret_cast<uint2*>(orow) = make_uint2(w0[r], w1[r]);
-                        orow += prm.out.pitch;
-                    }
+                    for (int r = 0; r < 8; r++)
+                        if (r < nrows) *reinterpret_cast<uint2*>(orow + (size_t)((uint32_t)r * opitch)) = make_uint2(w0[r], w1[r]);
                 } else {
                     float2 res[3][8];
                     #pragma unroll
@@ -461,7 +522,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
                         float2 v[NT + 4];
                         #pragma unroll
                         for (int r = 0; r < NT + 4; r++)
-                            v[r] = __half22float2(*reinterpret_cast<const __half2*>(colp + (size_t)(c * C::RING + ringrow[r]) * 2 * C::SW));
+                            v[r] = __half22float2(*reinterpret_cast<const __half2*>(colp + roff[r] + c * C::RING * ROWB));
                         #pragma unroll
                         for (int qq = 0; qq < 4; qq++) {
                             float2 e = mul2(v[qq], wE[0]), d = mul2(v[qq + 1], wO[0]);
@@ -524,7 +585,10 @@ k_strip2x(const __grid_constant__ StripParams prm)
                         }
                     }
                 }
+              }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sbase + 8 * (B_XDONE + (it & 3)));
         }
     }
 }

@@ -47,6 +47,29 @@ __device__ __forceinline__ float2 lg2_2(float2 x)
     return fma2(f, p, e);
 }
 
+// 2^23 * log2(x) per lane: lg2_2() with the coefficients and the exponent term scaled by 2^23 (every Horner step and the final
+// fma scale exactly, so the result is exactly 2^23 * lg2_2(x)); saves the 2^-23 multiply of the exponent.  Callers pair it
+// with an exponent y * 2^-23: ex2p's products a*b are then the same real numbers and every rounding is the same.
+__device__ __forceinline__ float2 lg2s_2(float2 x)
+{
+    constexpr float S = 8388608.0f;
+    const uint32_t u0 = __float_as_uint(x.x), u1 = __float_as_uint(x.y);
+    const uint32_t k0 = (u0 - 0x3f3504f3u) & 0xff800000u, k1 = (u1 - 0x3f3504f3u) & 0xff800000u;
+    const float2   m  = make_float2(__uint_as_float(u0 - k0), __uint_as_float(u1 - k1));
+    const float2   e  = make_float2((float)(int32_t)k0, (float)(int32_t)k1);
+    const float2   f  = add2(m, -1.0f);
+    float2 p = bc2(MPCVR_LG2_C8 * S);
+    p = fma2(p, f, MPCVR_LG2_C7 * S);
+    p = fma2(p, f, MPCVR_LG2_C6 * S);
+    p = fma2(p, f, MPCVR_LG2_C5 * S);
+    p = fma2(p, f, MPCVR_LG2_C4 * S);
+    p = fma2(p, f, MPCVR_LG2_C3 * S);
+    p = fma2(p, f, MPCVR_LG2_C2 * S);
+    p = fma2(p, f, MPCVR_LG2_C1 * S);
+    p = fma2(p, f, MPCVR_LG2_C0 * S);
+    return fma2(f, p, e);
+}
+
 // 2^(a*b) per lane, without the range selects (caller guarantees -125.5 < a*b < 127.5)
 __device__ __forceinline__ float2 ex2p_core2(float2 a, float b, float2& z)
 {

@@ -99,6 +99,62 @@ __device__ __forceinline__ f3x2 convert_color_pq2(const ColorParams& P, const f3
     return o;
 }
 
+// ---- the same PQ -> SDR chain with the bookkeeping trimmed (persistent strip kernel); bit-identical results:
+//  * log2 through lg2s_2 with exponents pre-scaled by 2^-23 (ys = y * 2^-23, exact);
+//  * the first pow drops pow(0,y) = 0's guard: for x < FLT_MIN the unguarded 2^(y lg2 x) is <= 2^-1.59 < ST2084_C1, so
+//    max(a - c1, 0) -- the only consumer besides a positive denominator -- is the same +0, and 0 / den = +0 either way;
+//  * saturates ride on the producing add / fma (add.sat, fma.sat: NaN -> 0 like sat()).
+__device__ __forceinline__ float add_sat(float a, float b) { float d; asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ float fma_sat1(float a, float b, float c) { float d; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+
+__device__ __forceinline__ float2 pq_channel_to_hable2s(const ColorParams& P, float ym2s, float ym1s, float2 csat)
+{
+    float2 z;
+    const float2 a   = ex2p_core2(lg2s_2(csat), ym2s, z);
+    const float2 num = max2(add2(a, -ST2084_C1), 0.0f);
+    const float2 den = fma2(-ST2084_C3, a, ST2084_C2);
+    const float2 q   = div_rn_safe_2(num, den);
+    const float2 v   = ex2p_core2(lg2s_2(q), ym1s, z);
+    const float lo = 12582912.0f - 125.0f;
+    const float2 lin = mul2(make_float2(z.x < lo ? 0.0f : v.x, z.y < lo ? 0.0f : v.y), P.lum_scale);
+    const float2 hn  = fma2(lin, fma2(0.15f, lin, P.hable_cb), P.hable_de);
+    const float2 hd  = fma2(lin, fma2(0.15f, lin, 0.50f), P.hable_df);
+    return mul2(add2(div_rn_safe_2(hn, hd), -P.hable_ef), P.hable_rdiv);
+}
+
+// saturate(mul(matrix_conv_prim, ToneMappingHable(ST2084ToLinear(saturate(rgb))))) == convert_color_pq2_pre
+__device__ __forceinline__ f3x2 convert_color_pq2_pre_s(const ColorParams& P, float ym2s, float ym1s, const f3x2& yuv)
+{
+    f3x2 h;
+    #pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float2 t = dp3_2(P.cm[i], yuv);
+        const float2 c = make_float2(add_sat(t.x, P.cc[i]), add_sat(t.y, P.cc[i]));
+        const float2 r = pq_channel_to_hable2s(P, ym2s, ym1s, c);
+        if (i == 0) h.x = r; else if (i == 1) h.y = r; else h.z = r;
+    }
+    f3x2 g;
+    #pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float2 t = fma2(P.gamut[i][1], h.y, mul2(h.x, P.gamut[i][0]));
+        const float2 r = make_float2(fma_sat1(P.gamut[i][2], h.z.x, t.x), fma_sat1(P.gamut[i][2], h.z.y, t.y));
+        if (i == 0) g.x = r; else if (i == 1) g.y = r; else g.z = r;
+    }
+    return g;
+}
+
+// gamma_q10_thr with a single exception float
+__device__ __forceinline__ float gamma_q10_thr1(float x, const float* __restrict__ sT, const float* __restrict__ sD, uint32_t exc0)
+{
+    float l, e;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(l * (1.0f / 2.2f)));
+    const int c0 = (int)fmaf(e, (float)kGammaN, 0.25f);                    // true code is c0 or c0 + 1
+    int c = c0 + (x >= sT[c0 + 1] ? 1 : 0);
+    c -= (__float_as_uint(x) == exc0) ? 1 : 0;
+    return sD[c];
+}
+
 __device__ __forceinline__ float2 rt_roundtrip2(int fmt, float2 v)
 {
     if (fmt == MPCVR_SURF_RGB10A2) return unorm_roundtrip2(v, 1023.0f, 1.0f / 1023.0f);
