@@ -31,6 +31,11 @@ typedef struct mpcvr_plan_info {
 } mpcvr_plan_info;
 
 int32_t mpcvr_debug_set_path(mpcvr* vp, int32_t path);
+/* the row of the input format table (Source/Helper.cpp:311-359 columns the chain uses): cformat, Packsize, PitchCoeff, CSType, Subsampling,
+ * CDepth, layout (SrcLayout), bytes per component, div_chroma_w, div_chroma_h, lsb_shift, v_before_u.  No device needed. */
+int32_t mpcvr_debug_fmt_params(int32_t cformat, int32_t out[12]);
+/* SpecifyExtendedFormat (Source/Helper.cpp:1169-1211) as the product applies it.  No device needed. */
+uint32_t mpcvr_debug_specify_extended_format(uint32_t exfmt, int32_t cformat, uint32_t width, uint32_t height);
 int32_t mpcvr_debug_get_plan(mpcvr* vp, mpcvr_plan_info* info);
 /* PS_COLOR_TRANSFORM cm_r,cm_g,cm_b (row-major 3x3) + cm_c, and matrix_conv_prim */
 /* process-wide: 1 (default) lets the fused 2x PQ kernel use the gamma+UNORM10 threshold table, 0 forces the direct pow */

@@ -69,6 +69,8 @@ int orc_process(const orc_config* cfg, const void* const planes[3], const int32_
 int orc_process_dovi(const orc_config* cfg, const void* const planes[3], const int32_t pitches[3],
                      void* out, int32_t out_pitch, orc_debug* dbg, int mode, int threads, const orc_dovi* dovi);
 
+/* the fetch branch and the convert-shader steps the oracle takes for cfg, as text (see orc_core.inc FN(describe)) */
+int orc_describe_convert(const orc_config* cfg, const orc_dovi* dovi, char* out, int cap);
 int orc_dovi_l1_nits(const orc_dovi* dv, float out_min_max_avg[3]);
 
 /* run only the post-convert passes on a given m_TexConvertOutput surface (packed, internal fmt) */

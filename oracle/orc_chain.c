@@ -6,6 +6,7 @@
  *   UpdatePostScaleTexures    Source/DX11VideoProcessor.cpp:2894-2907
  *   ResizeShaderPass scaler   Source/DX11VideoProcessor.cpp:3106-3127
  */
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -92,6 +93,8 @@ int orc_process_dovi(const orc_config* cfg, const void* const planes[3], const i
     }
     return -100;
 }
+
+int orc_describe_convert(const orc_config* cfg, const orc_dovi* dovi, char* out, int cap) { return describe_spec(cfg, dovi, out, cap); }
 
 int orc_process(const orc_config* cfg, const void* const planes[3], const int32_t pitches[3],
                 void* out, int32_t out_pitch, orc_debug* dbg, int mode, int threads)

@@ -811,7 +811,7 @@ def test_strip_kernel_falls_back_for_unaligned_device_planes():
     import torch
     case = H.Case(O.CF["P010"], 150, 70, 300, 140, H.EX_2020_PQ, up=O.UPSCALE["Lanczos3"], name="unaligned")
     codes = H.make_codes(case.cf, case.w, case.h, "noise", 9)
-    pitch = 150 * 2 + 6                                        # 306 bytes: multiple of 2, not of 16
+    pitch = 150 * 2 + 8                                        # 308 bytes: a multiple of the 4-byte UV texel, not of 16
     buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes, pitch=pitch)
     ref = H.run_oracle(case, planes, pitches)
     t = torch.from_numpy(buf).cuda()
@@ -819,6 +819,10 @@ def test_strip_kernel_falls_back_for_unaligned_device_planes():
     vp.ProcessSample(device_planes=[t.data_ptr(), t.data_ptr() + pitch * case.h], device_pitches=[pitch, pitch])
     torch.cuda.synchronize()
     assert H.compare(vp.ReadBackbuffer(), ref, case.backbuffer) == (0, 0)
+    # a pitch that is not a multiple of the chroma texel cannot be read with typed loads at all: refused, not a device fault
+    import videorenderer_b200 as V
+    hr = vp.ProcessSample(device_planes=[t.data_ptr(), t.data_ptr() + 306 * case.h], device_pitches=[306, 306], check=False)
+    assert hr == V.HRESULT.E_INVALIDARG
 
 
 def test_two_instances_on_two_streams_render_their_first_frames_concurrently():

@@ -195,6 +195,8 @@ SIGNATURES = {
     # debug header
     "mpcvr_debug_set_path": (C.c_int32, [vp, C.c_int32]),
     "mpcvr_debug_set_gamma_table": (C.c_int32, [C.c_int32]),
+    "mpcvr_debug_fmt_params": (C.c_int32, [C.c_int32, C.POINTER(C.c_int32)]),
+    "mpcvr_debug_specify_extended_format": (C.c_uint32, [C.c_uint32, C.c_int32, C.c_uint32, C.c_uint32]),
     "mpcvr_debug_set_strip_kernel": (C.c_int32, [C.c_int32, C.c_int32]),
     "mpcvr_debug_strip_status": (C.c_int32, [C.POINTER(C.c_uint32), C.c_int32]),
     "mpcvr_debug_set_convert_two_lane": (C.c_int32, [C.c_int32]),

@@ -104,6 +104,20 @@ int32_t mpcvr_debug_set_convert_two_lane(int32_t enable) { b200vr::SetConvertTwo
 int32_t mpcvr_debug_set_gamma_table(int32_t enable) { b200vr::SetGammaTableEnabled(enable != 0); return MPCVR_S_OK; }
 int32_t mpcvr_debug_set_strip_kernel(int32_t enable, int32_t cfg) { b200vr::SetStripKernel(enable != 0, cfg); return MPCVR_S_OK; }
 int32_t mpcvr_debug_strip_status(uint32_t out8[8], int32_t clear) { return b200vr::StripStatus(out8, clear) == 0 ? MPCVR_S_OK : MPCVR_E_FAIL; }
+int32_t mpcvr_debug_fmt_params(int32_t cformat, int32_t out[12])
+{
+    if (!out || cformat <= 0 || cformat >= MPCVR_CF_COUNT) return MPCVR_E_INVALIDARG;
+    const b200vr::FmtConvParams& p = b200vr::GetFmtConvParams(cformat);
+    out[0] = p.cformat; out[1] = p.Packsize; out[2] = p.PitchCoeff; out[3] = p.CSType; out[4] = p.Subsampling; out[5] = p.CDepth;
+    out[6] = p.layout; out[7] = p.bytes; out[8] = p.div_chroma_w; out[9] = p.div_chroma_h; out[10] = p.lsb_shift; out[11] = p.v_before_u ? 1 : 0;
+    return MPCVR_S_OK;
+}
+uint32_t mpcvr_debug_specify_extended_format(uint32_t exfmt, int32_t cformat, uint32_t width, uint32_t height)
+{
+    if (cformat <= 0 || cformat >= MPCVR_CF_COUNT) return 0;
+    b200vr::ExtendedFormat e; e.value = exfmt;
+    return b200vr::SpecifyExtendedFormat(e, b200vr::GetFmtConvParams(cformat), width, height).value;
+}
 int32_t mpcvr_debug_set_path(mpcvr* h, int32_t path) { VP_OR(MPCVR_E_POINTER); return vp.DebugSetPath(path); }
 int32_t mpcvr_debug_get_plan(mpcvr* h, mpcvr_plan_info* info) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugGetPlan(info)); }
 int32_t mpcvr_debug_get_color_params(mpcvr* h, float m9[9], float c3[3], float g9[9], float* lum) { VP_OR(MPCVR_E_POINTER); return vp.DebugGetColorParams(m9, c3, g9, lum); }

@@ -8,6 +8,8 @@
 
 namespace b200vr {
 
+int PlaneLoadBytes(const FmtConvParams& f, int plane);
+
 static inline int AlignUp(int v, int a) { return (v + a - 1) / a * a; }
 static inline int SurfBpp(int fmt) { return (fmt == MPCVR_SURF_RGBA16F || fmt == MPCVR_SURF_RGBA16) ? 8 : 4; }
 
@@ -165,6 +167,7 @@ int32_t CB200VideoProcessor::InitMediaType(const mpcvr_media_type* mt)
     if (mt->bottom_up) m_srcPitch = -m_srcPitch;                            // BI_RGB && biHeight > 0, :1801-1803
     unsigned origW = biWidth, origH = biHeight;                             // VR_Extradata, :1805-1813
     if (mt->frame_width > 0 && mt->frame_height != 0) { origW = (unsigned)mt->frame_width; origH = (unsigned)std::abs(mt->frame_height); }
+    if (origW > biWidth || origH > biHeight) return 0;                      // VR_Extradata names the frame INSIDE the (pitch-aligned) buffer
 
     if (m_srcRect.IsRectNull()) m_srcRect = CRect(0, 0, (int)origW, (int)origH);
     if (m_srcRect.left < 0 || m_srcRect.top < 0 || m_srcRect.right > (int)origW || m_srcRect.bottom > (int)origH || m_srcRect.IsRectEmpty())
@@ -650,9 +653,14 @@ void CB200VideoProcessor::Configure(const mpcvr_settings& s)
 {
     // diff and rebuild the minimum, like Source/DX11VideoProcessor.cpp:3800-4050
     const int oldTex = m_iTexFormat; const bool oldSdr = m_bConvertToSdr; const int oldNits = m_iSDRDisplayNits;
-    const bool oldHdrOut = HdrOut();
+    const bool oldHdrOut = HdrOut(); const int oldHdrNits = m_iHdrDisplayMaxNits;
     ApplySettings(s);
     if (!m_bInit) return;
+    // the convert shader is rebuilt on a chroma-scaling / blend change (:3985-3999): the current frame re-renders with the new fetch
+    m_src.chroma_mode = m_iChromaScaling;
+    m_src.deint_blend = (m_bDeintBlend && m_bInterlaced && m_srcParams.Subsampling == 420) ? 1 : 0;
+    // the Dolby Vision Level-2 trims are picked for iHdrDisplayMaxNits (:2383-2466): recompute them when the display changes
+    if (m_Dovi.bValid && oldHdrNits != m_iHdrDisplayMaxNits) SetShaderDoviCurves();
     if (oldTex != m_iTexFormat) { UpdateTexParams(m_srcParams.CDepth); UpdateTexures(); }
     if (oldSdr != m_bConvertToSdr || oldHdrOut != HdrOut()) SetShaderConvertColorParams();
     if (!HdrOut()) { m_hdrColorSpaceActive = false; m_bTonemap = false; }
@@ -807,6 +815,9 @@ int32_t CB200VideoProcessor::CopySample(const mpcvr_sample* s)
         const int np = f.layout == LAYOUT_BIPLANAR ? 2 : (f.layout == LAYOUT_PLANAR3 ? 3 : 1);
         for (int i = 0; i < np; i++) {
             if (!s->planes[i] || s->pitches[i] == 0 || (s->pitches[i] < 0 && np > 1)) return Fail(MPCVR_E_POINTER, "device sample: missing plane");
+            // the kernels read a plane with typed loads of its texel (a D3D11 texture is always that aligned; a raw pointer need not be)
+            const int a = PlaneLoadBytes(f, i);
+            if (((uintptr_t)s->planes[i] % a) || (s->pitches[i] % a)) return Fail(MPCVR_E_INVALIDARG, "device sample: plane address / pitch not aligned to the texel size");
             S.pl[i] = (const uint8_t*)s->planes[i]; S.pitch[i] = s->pitches[i];
         }
         if (s->ready_event && !Cuda(cudaStreamWaitEvent(m_stream, (cudaEvent_t)s->ready_event, 0), "cudaStreamWaitEvent")) return MPCVR_E_FAIL;
@@ -818,7 +829,10 @@ int32_t CB200VideoProcessor::CopySample(const mpcvr_sample* s)
         if (s->size > 0 && s->size < (int64_t)std::abs(pitch) * (int64_t)m_srcLines) return Fail(MPCVR_E_FAIL, "host sample smaller than pitch*lines (:2579)");
         // a bottom-up DIB is uploaded as it lies in memory; the kernels walk it from its last row with a negative pitch,
         // which is what "src = srcData + srcPitch * (1 - lines)" (:1246) does on the CPU
-        const int32_t hr = MemCopyToTexSrcVideo((const uint8_t*)s->data, std::abs(pitch));
+        // bottom-up DIB inside a taller buffer (VR_Extradata): the frame's rows are the LAST ones in memory, "src = srcData + srcPitch * (1 - lines)"
+        // with lines = m_srcLines (:1246)
+        const uint8_t* first = (const uint8_t*)s->data + (pitch < 0 ? (size_t)std::abs(pitch) * (m_srcLines > m_srcHeight ? m_srcLines - m_srcHeight : 0) : 0);
+        const int32_t hr = MemCopyToTexSrcVideo(first, std::abs(pitch));
         if (hr != MPCVR_S_OK) return hr;
         for (int i = 0; i < 3; i++) { S.pl[i] = (const uint8_t*)m_TexSrcVideo[i].ptr; S.pitch[i] = (int32_t)m_TexSrcVideo[i].pitch; }
         if (pitch < 0) { S.pl[0] += (size_t)S.pitch[0] * (m_srcHeight - 1); S.pitch[0] = -S.pitch[0]; }
@@ -827,6 +841,21 @@ int32_t CB200VideoProcessor::CopySample(const mpcvr_sample* s)
     m_rtStart = s->rt_start; m_rtEnd = s->rt_end;
     m_haveFrame = true;
     return MPCVR_S_OK;
+}
+
+// width in bytes of the loads the kernels issue on plane `plane` of a sample (pixel_ops.cuh fetch_*)
+int PlaneLoadBytes(const FmtConvParams& f, int plane)
+{
+    switch (f.layout) {
+    case LAYOUT_BIPLANAR:  return plane == 0 ? f.bytes : 2 * f.bytes;                         // R8|R16 ; R8G8|R16G16 texels
+    case LAYOUT_PLANAR3:   return f.bytes;
+    case LAYOUT_PACKED422: return f.packed_kind == 2 ? 4 : f.bytes;                           // v210 words ; byte / 16-bit components
+    case LAYOUT_PACKED444: return f.packed_kind == 2 ? 8 : 4;                                 // Y416 ; AYUV, Y410
+    case LAYOUT_RGB:
+        switch (f.packed_kind) { case RGBK_BGR24: return 1; case RGBK_RGB48: case RGBK_BGR48: return 2;
+                                 case RGBK_BGRA64: case RGBK_B64A: return 8; default: return 4; }
+    default:               return f.bytes;
+    }
 }
 
 int32_t CB200VideoProcessor::ProcessSample(const mpcvr_sample* s)
