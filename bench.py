@@ -7,7 +7,9 @@ bilinear chroma, ordered dither.  One "step" = one frame through CVideoProcessor
 
   value      frames/s with the input planes already resident in HBM (device sample), whole job (all ranks)
   e2e        frames/s through the C ABI with HOST buffers: pinned host frame -> H2D -> kernels -> D2H of the
-             rendered frame into pinned host memory, every step
+             rendered frame into pinned host memory, every step (B8G8R8A8 back buffer, the reference's swap-chain format)
+  e2e_rgb8   the same loop with the packed R8G8B8 back buffer (MPCVR_SURF_RGB8, an extension: 25 % fewer bytes over PCIe);
+             a separate row, never the headline
   roofline   algorithmic bytes of one frame (input read once + output written once) / the frame
              kernel's average duration from CUDA events on the launching stream, vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the CPU oracle (restatement of the reference's shaders; the reference has no CPU path) on the
@@ -87,7 +89,7 @@ class ClockSampler(threading.Thread):
             sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
             r = int(get_reasons(h))
             self.samples.append((t, sm, mx, {k for k, b in bits.items() if r & b}))
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def _run_smi(self):
         self.source = "nvidia-smi"
@@ -266,6 +268,8 @@ def main():
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device: the frame path has no CPU fallback"})); return 2
     torch.cuda.set_device(local)
+    # host side of a stream: bind this rank and its pinned buffers to the GPU's NUMA node BEFORE anything is allocated
+    numa = streams.bind_to_gpu_numa(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -287,7 +291,6 @@ def main():
         t = torch.from_numpy(buf).cuda()
         dev_frames.append((t, pitch))
     pinned_in = [torch.from_numpy(f[0]).pin_memory() for f in frames]
-    pinned_out = torch.empty((DST_H, DST_W * 4), dtype=torch.uint8).pin_memory()
     L = V.lib()
 
     def step_device(i):
@@ -298,22 +301,34 @@ def main():
     # e2e: host frames in, host frames out.  Two instances (two CUDA streams) alternate so that the H2D of frame i+1 and the
     # D2H of frame i-1 overlap the kernels of frame i (what a player's upload/present queue does); device-timed on stream s0.
     e2e_streams = [stream, torch.cuda.Stream(device=local)]
-    e2e_vps = [vp]
-    vp2 = V.VideoProcessor(s, device=local, stream=e2e_streams[1].cuda_stream)
-    assert vp2.InitMediaType(mt), vp2.last_error()
-    vp2.SetWindowRect((0, 0, DST_W, DST_H)); vp2.SetVideoRect((0, 0, DST_W, DST_H))
-    vp2.debug_set_path({"auto": V.PATH.AUTO, "multipass": V.PATH.MULTIPASS, "fused": V.PATH.FUSED}[args.path])
-    e2e_vps.append(vp2)
-    pinned_outs = [pinned_out, torch.empty((DST_H, DST_W * 4), dtype=torch.uint8).pin_memory()]
 
-    def step_e2e(i):
-        k = i & 1
-        v = e2e_vps[k]
-        v.WaitIdle()                                   # the previous frame of this instance has been read back
-        h = pinned_in[i % N_FRAMES]
-        v.ProcessSample(data=(h.data_ptr(), h.numel()), pitch=frames[0][1])
-        hr = L.mpcvr_read_backbuffer_async(v._h, pinned_outs[k].data_ptr(), DST_W * 4)     # D2H of the rendered frame
-        assert hr == 0
+    def make_e2e(backbuffer, first=None):
+        bpp = 3 if backbuffer == V.SURF.RGB8 else 4
+        vps = []
+        for k in range(2):
+            if k == 0 and first is not None:
+                v = first
+            else:
+                v = V.VideoProcessor(s, device=local, stream=e2e_streams[k].cuda_stream)
+                assert v.InitMediaType(mt), v.last_error()
+                v.SetBackbufferFormat(backbuffer)
+                v.SetWindowRect((0, 0, DST_W, DST_H)); v.SetVideoRect((0, 0, DST_W, DST_H))
+                v.debug_set_path({"auto": V.PATH.AUTO, "multipass": V.PATH.MULTIPASS, "fused": V.PATH.FUSED}[args.path])
+            vps.append(v)
+        outs = [torch.empty((DST_H, DST_W * bpp), dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+        def step(i):
+            k = i & 1
+            v = vps[k]
+            v.WaitIdle()                                   # the previous frame of this instance has been read back
+            h = pinned_in[i % N_FRAMES]
+            v.ProcessSample(data=(h.data_ptr(), h.numel()), pitch=frames[0][1])
+            hr = L.mpcvr_read_backbuffer_async(v._h, outs[k].data_ptr(), DST_W * bpp)     # D2H of the rendered frame
+            assert hr == 0
+        return step, DST_W * DST_H * bpp
+
+    step_e2e, e2e_out_bytes = make_e2e(V.SURF.BGRA8, first=vp)
+    step_e2e_rgb8, rgb8_out_bytes = make_e2e(V.SURF.RGB8)
 
     def e2e_join():
         e2e_streams[0].wait_stream(e2e_streams[1])
@@ -327,7 +342,7 @@ def main():
         e0.record(stream)
         for i in range(steps):
             fn(i)
-        if fn is step_e2e:
+        if fn is step_e2e or fn is step_e2e_rgb8:
             e2e_join()
         e1.record(stream)
         torch.cuda.synchronize()
@@ -361,6 +376,10 @@ def main():
     ms_e2e = max(ms_e2e, 0.0)
     # the e2e loop synchronises every step (read back), so host wall clock and device events agree; use the events
     e2e_fps = streams.aggregate_fps(e2e_steps, world, ms_e2e)
+    for i in range(3):
+        step_e2e_rgb8(i)
+    ms_rgb8 = max(timed(step_e2e_rgb8, e2e_steps), 0.0)
+    rgb8_fps = streams.aggregate_fps(e2e_steps, world, ms_rgb8)
 
     pk, pk_src = peaks()
     kernel_ms = ms / args.steps                       # one frame kernel per step on the fused path
@@ -369,22 +388,31 @@ def main():
             "peak_source": pk_src, "algorithmic_bytes_per_launch": ALGO_BYTES,
             "kernel": "fused frame kernel" if plan.path == V.PATH.FUSED else "multipass chain (%d kernels/frame; bytes are per frame)" % launches_per_step,
             "secondary_ceiling": "instruction issue (exact fp32 tone-map + 6-tap resize), see DESIGN.md"}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_c2.json")
-    if os.path.exists(traffic_file):
+    # Numbers that cannot be measured inside this process (DRAM bytes, warp instructions of the frame kernel) come from the committed
+    # ncu capture profiles/capture_c2.json, which also records the sha256 of videorenderer_b200/csrc at capture time.  If the kernel
+    # sources changed since, the figures belong to another binary: say so and do not quote the issue ceiling.
+    cap_file = os.path.join(ROOT, "profiles", "capture_c2.json")
+    if os.path.exists(cap_file) and plan.path == V.PATH.FUSED:
         try:
-            roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-    # The kernel keeps the reference's fp32 arithmetic exact, which makes it instruction-issue bound rather than HBM bound.
-    # That ceiling is reported next to the contract's HBM roofline: warp instructions per launch from the committed ncu
-    # capture (smsp__inst_executed.sum) against 4 warp instructions / clk / SM at the SM clock sampled during this run.
-    if plan.path == V.PATH.FUSED:
-        WARP_INSTR = 152_621_688                         # profiles/r01f_fused_c2_gamma_table.md
-        sm_hz = float(clocks.get("sm_mhz") or 1965.0) * 1e6
-        issue_peak = 148 * 4 * sm_hz                    # warp instructions / s
-        roof["issue"] = {"bound": "instruction issue", "warp_instr_per_launch": WARP_INSTR, "achieved": WARP_INSTR / (kernel_ms * 1e-3) / 1e9,
-                         "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": WARP_INSTR / (kernel_ms * 1e-3) / issue_peak,
-                         "source": "profiles/r01f_fused_c2_gamma_table.md"}
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from make_capture_json import csrc_sha256
+            cap = json.load(open(cap_file))
+            stale = cap.get("csrc_sha256") != csrc_sha256()
+            roof["traffic"] = cap.get("dram_bytes_per_launch")
+            roof["traffic_source"] = "profiles/capture_c2.json (%s, %s)" % (cap.get("report"), cap.get("kernel", "")[:60])
+            roof["traffic_stale"] = bool(stale)
+            if not stale:
+                # the kernel keeps the reference's fp32 arithmetic exact, which makes it instruction-issue / FMA-pipe bound rather than HBM
+                # bound; that ceiling is reported next to the contract's HBM roofline: warp instructions per launch of the capture against
+                # 4 warp instructions / clk / SM at the SM clock sampled during THIS run
+                wi = int(cap["warp_instr_per_launch"])
+                sm_hz = float(clocks.get("sm_mhz") or 1965.0) * 1e6
+                issue_peak = 148 * 4 * sm_hz
+                roof["issue"] = {"bound": "instruction issue", "warp_instr_per_launch": wi, "achieved": wi / (kernel_ms * 1e-3) / 1e9,
+                                 "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": wi / (kernel_ms * 1e-3) / issue_peak,
+                                 "source": "profiles/capture_c2.json"}
+        except Exception as e:
+            roof["traffic_source"] = "capture unreadable: %r" % (e,)
     e2e_d2h_gbs = OUT_BYTES * e2e_fps / world / 1e9     # per GPU; the D2H of the 8K frame is the e2e bottleneck (PCIe)
 
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -402,6 +430,10 @@ def main():
                     "note": "pinned host frame -> mpcvr_process_sample (H2D inside) -> mpcvr_read_backbuffer_async (D2H of the full 7680x4320 BGRA8 frame into pinned memory); two instances/streams alternate so copies overlap kernels",
                     "d2h_gbs_per_gpu": e2e_d2h_gbs, "h2d_gbs_per_gpu": IN_BYTES * e2e_fps / world / 1e9,
                     "bound": "PCIe device-to-host copy of the 133 MB output frame"},
+            "e2e_rgb8": {"value": rgb8_fps, "unit": UNIT, "h2d_bytes_per_step": IN_BYTES, "d2h_bytes_per_step": rgb8_out_bytes,
+                         "d2h_gbs_per_gpu": rgb8_out_bytes * rgb8_fps / world / 1e9,
+                         "note": "same loop, back buffer MPCVR_SURF_RGB8 (packed R,G,B: the B8G8R8A8 codes without the alpha byte; extension, not the reference's swap-chain format); algorithmic bytes 124 416 000 per frame"},
+            "host": {"numa": numa},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof}
 

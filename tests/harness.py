@@ -339,6 +339,8 @@ def rgb_view(buf, fmt_):
     if fmt_ == O.SURF_BGRA8:
         a = buf.reshape(h, -1, 4)
         return a[..., [2, 1, 0]].astype(np.int32)
+    if fmt_ == O.SURF_RGB8:
+        return buf.reshape(h, -1, 3).astype(np.int32)
     if fmt_ == O.SURF_RGB10A2:
         v = buf.view(np.uint32)
         return np.stack([v & 1023, (v >> 10) & 1023, (v >> 20) & 1023], -1).astype(np.int32)

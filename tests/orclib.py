@@ -15,6 +15,7 @@ CF = dict(NONE=0, NV12=1, P010=2, P016=3, YUY2=4, UYVY=5, P210=6, P216=7, Y210=8
           GBRP8=26, GBRP10=27, GBRP16=28, RGB24=29, XRGB32=30, ARGB32=31, r210=32, RGB48=33, BGR48=34, BGRA64=35,
           B64A=36, Y8=37, Y10=38, Y16=39)
 SURF_BGRA8, SURF_RGB10A2, SURF_RGBA16F = 0, 1, 2
+SURF_RGB8 = 4        # product extension (packed R,G,B bytes of the B8G8R8A8 codes); the oracle renders B8G8R8A8 for it
 MODE_SPEC, MODE_LITERAL, MODE_F64 = 0, 1, 2
 VARIANT_D3D11, VARIANT_D3D9 = 0, 1
 TEXFMT_AUTOINT, TEXFMT_8INT, TEXFMT_10INT, TEXFMT_16FLOAT = 0, 8, 10, 16

@@ -855,3 +855,80 @@ def test_two_instances_on_two_streams_render_their_first_frames_concurrently():
         t.join()
     for o in outs:
         assert o is not None and H.compare(o, ref, case.backbuffer) == (0, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# the four single-GPU BASELINE configs at the sizes BASELINE.json names, every pixel of the frame (all four frame edges included)
+# ------------------------------------------------------------------------------------------------
+def _frame_hash(out, fmt_):
+    import hashlib
+    rgb = np.ascontiguousarray(H.rgb_view(out, fmt_))
+    if rgb.dtype == np.float16:
+        rgb = rgb.view(np.uint16)
+    return hashlib.sha256(rgb.tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_full_size_baseline_configs_equal_the_oracle_on_every_pixel(idx):
+    """C1 1920x1080 NV12; C2 3840x2160 P010 -> 7680x4320; C3 1920x1080 YUY2 -> 2880x1620 RGB10A2; C4 7680x4320 P016 -> 3840x2160 RGBA16F:
+    the oracle renders the whole frame on the host cores and every kernel family must equal it on every pixel; the oracle's own output
+    is pinned by the committed hash (tests/golden/frames_full.json, minted by tests/golden/make_golden_fullsize.py)."""
+    import hashlib
+    import json
+    import os
+    case = H.baseline_cases(1.0)[idx]
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "frames_full.json")))[case.name]
+    codes = H.make_codes(case.cf, case.w, case.h, golden["kind"], golden["seed"])
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    assert hashlib.sha256(buf.tobytes()).hexdigest() == golden["in_sha256"]
+    ref = H.run_oracle(case, planes, pitches)
+    assert _frame_hash(ref, case.backbuffer) == golden["out_rgb_sha256"], "the oracle's full-size frame drifted from the committed hash"
+    for p in (PATH_MULTIPASS, PATH_AUTO, PATH_FUSED):
+        vp, out = _run_gpu(case, buf, pitch, p)
+        n, d = H.compare(out, ref, case.backbuffer)
+        assert n == 0, "%s path %d(%d): %d channel values differ (max delta %d)" % (case.name, p, vp.debug_plan().path, n, d)
+        assert _frame_hash(out, case.backbuffer) == golden["out_rgb_sha256"]
+    if idx == 1:                                   # C2 also through the tile kernel (the strip kernel's fallback)
+        _, out = _run_strip(case, buf, pitch, 0)
+        assert H.compare(out, ref, case.backbuffer) == (0, 0)
+
+
+# ---- MPCVR_SURF_RGB8 (extension): the B8G8R8A8 codes as packed R,G,B bytes -----------------------------------------------------
+def _rgb8_pair(case_kw, cf, w, h, dw, dh, ex, **kw):
+    a = H.Case(O.CF[cf], w, h, dw, dh, ex, backbuffer=O.SURF_BGRA8, name="bgra", **kw)
+    b = H.Case(O.CF[cf], w, h, dw, dh, ex, backbuffer=O.SURF_RGB8, name="rgb8", **kw)
+    return a, b
+
+
+@pytest.mark.parametrize("geom", [("P010", 150, 70, 300, 140, "pq", {}), ("P010", 131, 35, 262, 70, "pq", {}), ("P010", 64, 36, 128, 72, "pq", dict(dst_rect=(16, 11, 144, 83), win=(160, 100))),
+                                  ("P010", 64, 36, 128, 72, "pq", dict(dst_rect=(18, 11, 146, 83), win=(164, 100))), ("NV12", 96, 64, 192, 128, "709", {}),
+                                  ("NV12", 100, 60, 100, 60, "709", {}), ("YUY2", 96, 54, 144, 81, "hlg", dict(tex=O.TEXFMT_16FLOAT)), ("P016", 120, 68, 60, 34, "sdr2020", dict(tex=O.TEXFMT_10INT))],
+                         ids=lambda g: "%s_%dx%d_%dx%d" % g[:5])
+def test_rgb8_backbuffer_holds_the_bgra8_codes(geom):
+    cf, w, h, dw, dh, exn, kw = geom
+    ex = {"pq": H.EX_2020_PQ, "709": H.EX_709, "hlg": H.EX_2020_HLG, "sdr2020": H.EX_2020_SDR}[exn]
+    kw = dict(kw); kw.setdefault("up", O.UPSCALE["Lanczos3"])
+    win = kw.get("win", (dw, dh))
+    a = H.Case(O.CF[cf], w, h, dw, dh, ex, backbuffer=O.SURF_BGRA8, name="bgra", **kw)
+    b = H.Case(O.CF[cf], w, h, dw, dh, ex, backbuffer=O.SURF_RGB8, name="rgb8", **kw)
+    codes = H.make_codes(a.cf, w, h, "fullnoise", 11)
+    buf, pitch, planes, pitches = H.pack(a.cf, w, h, codes)
+    ref = H.rgb_view(H.run_oracle(a, planes, pitches), O.SURF_BGRA8)           # the oracle's B8G8R8A8 frame
+    for p in (PATH_MULTIPASS, PATH_AUTO):
+        vp, out = _run_gpu(b, buf, pitch, p)
+        assert out.shape == (win[1], win[0] * 3)
+        got = H.rgb_view(out, O.SURF_RGB8)
+        assert np.array_equal(got, ref), "path %d(%d): %d values differ" % (p, vp.debug_plan().path, int((got != ref).sum()))
+        st = vp.debug_strip_status(clear=True)
+        assert st[0] == 0
+
+
+def test_rgb8_full_size_c2_equals_the_bgra8_frame():
+    case = H.baseline_cases(1.0)[1]
+    codes = H.make_codes(case.cf, case.w, case.h, "natural", 21)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    _, bgra = _run_gpu(case, buf, pitch, PATH_AUTO)
+    c8 = H.Case(case.cf, case.w, case.h, case.dst_w, case.dst_h, case.ex, backbuffer=O.SURF_RGB8, up=case.up, name="c2_rgb8")
+    vp, rgb = _run_gpu(c8, buf, pitch, PATH_AUTO)
+    assert vp.debug_plan().path == PATH_FUSED and vp.LastFrameKernels() == 1
+    assert np.array_equal(H.rgb_view(rgb, O.SURF_RGB8), H.rgb_view(bgra, O.SURF_BGRA8))

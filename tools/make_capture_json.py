@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""tools/make_capture_json.py <report.ncu-rep> [kernel-regex] -> profiles/capture_c2.json
+Records, from one `ncu --set full` capture of the C2 frame kernel, the numbers bench.py quotes next to its live timing
+(DRAM bytes per launch, warp instructions per launch) TOGETHER WITH the sha256 of videorenderer_b200/csrc at capture time.
+bench.py recomputes that hash: if the kernel sources changed since the capture it says so ("traffic_stale": true) and drops
+the instruction-issue figure instead of quoting numbers of another binary."""
+import csv, hashlib, io, json, os, re, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def csrc_sha256():
+    d = os.path.join(ROOT, "videorenderer_b200", "csrc")
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".cpp", ".h")):
+            h.update(name.encode()); h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()
+
+
+def main():
+    rep = sys.argv[1]; pat = re.compile(sys.argv[2] if len(sys.argv) > 2 else "k_strip2x|k_fused2x")
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    for row in rows[2:]:
+        d = dict(zip(hdr, row)); u = dict(zip(hdr, units))
+        if not pat.search(d.get("Kernel Name", "")):
+            continue
+        def b(k):
+            v = float(d[k]); unit = u.get(k, "")
+            return int(round(v * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}.get(unit, 1)))
+        cap = {"kernel": d["Kernel Name"], "report": os.path.basename(rep), "dram_bytes_read": b("dram__bytes_read.sum"), "dram_bytes_write": b("dram__bytes_write.sum"),
+               "warp_instr_per_launch": int(float(d["smsp__inst_executed.sum"])), "gpu_time_us": float(d["gpu__time_duration.sum"]),
+               "issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]), "registers_per_thread": int(float(d["launch__registers_per_thread"])),
+               "csrc_sha256": csrc_sha256()}
+        cap["dram_bytes_per_launch"] = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+        json.dump(cap, open(os.path.join(ROOT, "profiles", "capture_c2.json"), "w"), indent=1)
+        print(json.dumps(cap, indent=1)); return 0
+    print("no kernel matching", pat.pattern); return 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -36,6 +36,7 @@ class CF:  # ColorFormat_t, Source/Helper.h:86-127
 
 class SURF:
     BGRA8, RGB10A2, RGBA16F = 0, 1, 2
+    RGB8 = 4              # extension: packed R,G,B bytes
 
 
 class TEXFMT:

@@ -588,6 +588,7 @@ static bool Is2x(const FusedPlan& p)
     if (p.ax.src0 != 0 || p.ay.src0 != 0) return false;
     if (p.ax.dst0 < 0 || p.ay.dst0 < 0 || p.ax.dst0 + p.ax.dst_len > p.out.w || p.ay.dst0 + p.ay.dst_len > p.out.h) return false;
     if ((p.ax.dst0 & 1) || (p.out.pitch & 15) || ((uintptr_t)p.out.ptr & 15)) return false;
+    if (p.out.fmt == MPCVR_SURF_RGB8 && !StripEligible(p)) return false;       // packed RGB8 targets: only the strip kernel writes them
     return true;
 }
 
@@ -785,13 +786,14 @@ cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
     if (StripEligible(p)) {
         // persistent warp-specialised kernel (kernel_strip.cuh): bi-planar sources with bilinear chroma, planes TMA-addressable
         const bool thr = p.color.transfer == TRANSFER_PQ_TO_SDR && p.src.bytes == 2 && p.internal_fmt == MPCVR_SURF_RGB10A2 &&
-                         p.out.fmt == MPCVR_SURF_BGRA8 && p.final_pass && g_useGammaTable && EnsureGammaTable(st);
+                         (p.out.fmt == MPCVR_SURF_BGRA8 || p.out.fmt == MPCVR_SURF_RGB8) && p.final_pass && g_useGammaTable && EnsureGammaTable(st);
         int dev = 0; cudaGetDevice(&dev);
         const bool ok = thr && dev >= 0 && dev < 64 && g_gammaExcHost[dev][1] == 0xFFFFFFFFu;   // the strip kernel checks one exception float
         if (launches) *launches = 1;
         const cudaError_t e = LaunchStrip2x(p, ok ? g_gammaTdev[dev] : nullptr, ok ? g_gammaDdev[dev] : nullptr, ok ? g_gammaExcHost[dev] : nullptr, st);
         if (e != cudaErrorNotSupported) return e;
     }
+    if (p.out.fmt == MPCVR_SURF_RGB8) return cudaErrorNotSupported;              // the tile kernel does not write packed RGB8
     FusedParams prm;
     memset(&prm, 0, sizeof(prm));
     prm.src = p.src; prm.color = p.color; prm.out = p.out;

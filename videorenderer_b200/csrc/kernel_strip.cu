@@ -99,6 +99,7 @@ static cudaError_t LaunchV(const StripParams& prm, int spec, int conv, int grid,
         }
         return LaunchK<Cfg0, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
     }
+    if (spec == SSPEC_10_RGB8_DITHER && conv == SCONV_PQ_THR) return LaunchK<Cfg0, NT, DUP, SSPEC_10_RGB8_DITHER, SCONV_PQ_THR>(prm, grid, st);
     if (spec == SSPEC_10_BGRA8_DITHER) return LaunchK<Cfg0, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_ANY>(prm, grid, st);
     if (spec == SSPEC_8_BGRA8)         return LaunchK<Cfg0, NT, DUP, SSPEC_8_BGRA8, SCONV_ANY>(prm, grid, st);
     if (conv == SCONV_PQ)              return LaunchK<Cfg0, NT, DUP, SSPEC_RUNTIME, SCONV_PQ>(prm, grid, st);
@@ -139,9 +140,11 @@ cudaError_t LaunchStrip2x(const FusedPlan& p, const float* gT, const float* gD, 
 
     int spec = SSPEC_RUNTIME;
     if (p.internal_fmt == MPCVR_SURF_RGB10A2 && p.out.fmt == MPCVR_SURF_BGRA8 && p.final_pass && p.Q == 255.0f) spec = SSPEC_10_BGRA8_DITHER;
+    else if (p.internal_fmt == MPCVR_SURF_RGB10A2 && p.out.fmt == MPCVR_SURF_RGB8 && p.final_pass && p.Q == 255.0f && (p.ax.dst0 & 3) == 0 &&
+             p.color.transfer == TRANSFER_PQ_TO_SDR && S.bytes == 2 && gT && gD) spec = SSPEC_10_RGB8_DITHER;
     else if (p.internal_fmt == MPCVR_SURF_BGRA8 && p.out.fmt == MPCVR_SURF_BGRA8 && !p.final_pass) spec = SSPEC_8_BGRA8;
     int conv = SCONV_ANY;
-    if (p.color.transfer == TRANSFER_PQ_TO_SDR && S.bytes == 2) conv = (spec == SSPEC_10_BGRA8_DITHER && gT && gD) ? SCONV_PQ_THR : SCONV_PQ;
+    if (p.color.transfer == TRANSFER_PQ_TO_SDR && S.bytes == 2) conv = ((spec == SSPEC_10_BGRA8_DITHER || spec == SSPEC_10_RGB8_DITHER) && gT && gD) ? SCONV_PQ_THR : SCONV_PQ;
 
     static int sms[64] = {};
     int dev = 0; cudaGetDevice(&dev);

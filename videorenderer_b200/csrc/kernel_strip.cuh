@@ -37,7 +37,8 @@ static __device__ const DitherTableF g_dither32_strip = MakeDitherTableF(0.00097
 enum { SCONV_PQ_THR = 0,      // PQ -> SDR, 10-bit internal format: gamma + UNORM10 write/read through the threshold table
        SCONV_PQ = 1,          // PQ -> SDR, any internal format
        SCONV_ANY = 2 };       // any transfer (runtime switch), any internal format
-enum { SSPEC_RUNTIME = 0, SSPEC_10_BGRA8_DITHER = 1, SSPEC_8_BGRA8 = 2 };
+enum { SSPEC_RUNTIME = 0, SSPEC_10_BGRA8_DITHER = 1, SSPEC_8_BGRA8 = 2,
+       SSPEC_10_RGB8_DITHER = 3 };   // as 1, written as packed R,G,B bytes (MPCVR_SURF_RGB8); lane pairs exchange two bytes by warp shuffle
 
 struct StripParams {
     alignas(64) CUtensorMap tmY;          // luma plane: W x H elements of 1 or 2 bytes, box LUMA_BOX x R
@@ -233,6 +234,7 @@ template <class C, int NT, bool DUP, int SPEC, int CONV>
 __global__ void __launch_bounds__(C::THREADS, 1)
 k_strip2x(const __grid_constant__ StripParams prm)
 {
+    constexpr bool HOT = SPEC == SSPEC_10_BGRA8_DITHER || SPEC == SSPEC_10_RGB8_DITHER;   // 10-bit internal format, final pass to 8 bits
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -253,12 +255,12 @@ k_strip2x(const __grid_constant__ StripParams prm)
         for (int i = threadIdx.x; i < kGammaN + 2; i += C::THREADS) sT[i] = prm.gT[i];
         for (int i = threadIdx.x; i < kGammaN + 1; i += C::THREADS) sD[i] = prm.gD[i];
     }
-    for (int i = threadIdx.x; i < 2048; i += C::THREADS) sDith[i] = (SPEC == SSPEC_10_BGRA8_DITHER) ? -g_dither32_strip.v[i & 1023] : g_dither32_strip.v[i & 1023];
+    for (int i = threadIdx.x; i < 2048; i += C::THREADS) sDith[i] = HOT ? -g_dither32_strip.v[i & 1023] : g_dither32_strip.v[i & 1023];
     __syncthreads();
 
     const long long total = (long long)prm.strips * prm.nq;
     const int Q0 = (int)(total * blockIdx.x / gridDim.x), Q1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
-    const int IFMT = SPEC == SSPEC_10_BGRA8_DITHER ? (int)MPCVR_SURF_RGB10A2 : (SPEC == SSPEC_8_BGRA8 ? (int)MPCVR_SURF_BGRA8 : prm.internal_fmt);
+    const int IFMT = HOT ? (int)MPCVR_SURF_RGB10A2 : (SPEC == SSPEC_8_BGRA8 ? (int)MPCVR_SURF_BGRA8 : prm.internal_fmt);
 
     if (warp < C::NP) {
         // ================================================================================================ TMA + role P
@@ -427,7 +429,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
         asm volatile("pmevent 4;");
         const int wc = warp - C::NP - C::NA - C::NB;
         const int  OFMT  = SPEC != SSPEC_RUNTIME ? (int)MPCVR_SURF_BGRA8 : prm.out.fmt;
-        const bool FINAL = SPEC == SSPEC_10_BGRA8_DITHER ? true : (SPEC == SSPEC_8_BGRA8 ? false : prm.final_pass != 0);
+        const bool FINAL = HOT ? true : (SPEC == SSPEC_8_BGRA8 ? false : prm.final_pass != 0);
         __half* sX = reinterpret_cast<__half*>(smem + C::oX);
         float wE[NT], wO[NT];
         #pragma unroll
@@ -446,7 +448,8 @@ k_strip2x(const __grid_constant__ StripParams prm)
                 if (!mine) continue;
                 const int q = qnext;
                 const int col = gi.s * C::SW + 32 * cb + lane;                     // convert-surface column of this lane's output pair
-                if (col >= prm.w1) continue;
+                const bool valid = col < prm.w1;                                   // lanes past the right edge compute (on in-bounds garbage) but never store
+                if (SPEC != SSPEC_10_RGB8_DITHER && !valid) continue;
                 const int jy = 4 * q;                                              // first convert row of the quad
                 const int gx = prm.dst_x0 + 2 * col, gy = prm.dst_y0 + 2 * jy;
                 const bool yedge = (jy + prm.b0 < 0) || (jy + 3 + prm.b0 + NT > prm.h1 - 1);
@@ -468,15 +471,15 @@ k_strip2x(const __grid_constant__ StripParams prm)
                 }
                 const int nrows = min(8, 2 * (prm.h1 - jy));                       // output rows of this quad that exist
                 const char* colp = reinterpret_cast<const char*>(sX + 64 * cb + 2 * lane);
-                if (SPEC == SSPEC_10_BGRA8_DITHER) {
-                    // channel-sequential: B, G, R; codes are packed as they appear (two PRMTs per pixel)
+                if (HOT) {
+                    // channel-sequential: B, G, R (R, G, B for the packed RGB8 target); codes are packed as they appear (two PRMTs per pixel)
                     float2 nd[8];
                     #pragma unroll
                     for (int r = 0; r < 8; r++) nd[r] = *reinterpret_cast<const float2*>(sDith + ((gy & 31) << 5) + (gx & 31) + 32 * r);
                     uint32_t w0[8], w1[8];
                     #pragma unroll
                     for (int cc = 0; cc < 3; cc++) {
-                        const int c = 2 - cc;
+                        const int c = SPEC == SSPEC_10_RGB8_DITHER ? cc : 2 - cc;
                         float2 v[NT + 4];
                         #pragma unroll
                         for (int r = 0; r < NT + 4; r++)
@@ -504,17 +507,41 @@ k_strip2x(const __grid_constant__ StripParams prm)
                                 const float2 p = div_by_const_exact2(floor_pos2(fma2(val, 1023.0f, 0.5f)), 1023.0f, 1.0f / 1023.0f);
                                 const float2 fl = __fadd2_ru(fma2(p, -255.0f, nd[r]), bc2(-8388608.0f));
                                 const uint32_t f0 = __float_as_uint(fl.x), f1 = __float_as_uint(fl.y);
-                                if (cc == 0)      { w0[r] = f0; w1[r] = f1; }                                        // B
-                                else if (cc == 1) { w0[r] = prmt(w0[r], f0, 0x0040); w1[r] = prmt(w1[r], f1, 0x0040); }   // B, G
-                                else              { w0[r] = prmt(w0[r], f0, 0xF410); w1[r] = prmt(w1[r], f1, 0xF410); }   // B, G, R, 0xFF
+                                if (cc == 0)      { w0[r] = f0; w1[r] = f1; }                                        // B       (R)
+                                else if (cc == 1) { w0[r] = prmt(w0[r], f0, 0x0040); w1[r] = prmt(w1[r], f1, 0x0040); }   // B, G    (R, G)
+                                else              { w0[r] = prmt(w0[r], f0, 0xF410); w1[r] = prmt(w1[r], f1, 0xF410); }   // B, G, R, 0xFF  (R, G, B, x)
                             }
                         }
                     }
-                    uint8_t* orow = (uint8_t*)prm.out.ptr + (size_t)gy * prm.out.pitch + (size_t)gx * 4;
                     const uint32_t opitch = (uint32_t)prm.out.pitch;
-                    #pragma unroll
-                    for (int r = 0; r < 8; r++)
-                        if (r < nrows) *reinterpret_cast<uint2*>(orow + (size_t)((uint32_t)r * opitch)) = make_uint2(w0[r], w1[r]);
+                    if (SPEC == SSPEC_10_RGB8_DITHER) {
+                        // 6 bytes per lane, 12 contiguous bytes per lane pair = three aligned 32-bit words: the even lane writes words 0 and 1
+                        // (its pixels + the partner's first two bytes, fetched by shuffle), the odd lane word 2.  dst_x0 % 4 == 0 (launcher).
+                        uint8_t* orow = (uint8_t*)prm.out.ptr + (size_t)gy * prm.out.pitch + (size_t)gx * 3;
+                        const bool odd = lane & 1;
+                        const bool pvalid = __shfl_xor_sync(0xFFFFFFFFu, (int)valid, 1) != 0;
+                        #pragma unroll
+                        for (int r = 0; r < 8; r++) {
+                            const uint32_t lo = prmt(w0[r], w1[r], 0x4210);              // R0 G0 B0 R1
+                            const uint32_t hi = prmt(w1[r], w1[r], 0x0021);              // G1 B1 . .
+                            const uint32_t plo = __shfl_xor_sync(0xFFFFFFFFu, lo, 1);
+                            if (r < nrows && valid) {
+                                uint8_t* q = orow + (size_t)((uint32_t)r * opitch);
+                                if (!odd) {
+                                    *reinterpret_cast<uint32_t*>(q) = lo;
+                                    if (pvalid) *reinterpret_cast<uint32_t*>(q + 4) = prmt(hi, plo, 0x5410);      // G1 B1 | partner R0 G0
+                                    else        *reinterpret_cast<uint16_t*>(q + 4) = (uint16_t)hi;
+                                } else {
+                                    *reinterpret_cast<uint32_t*>(q + 2) = prmt(lo, hi, 0x5432);                  // B0 R1 G1 B1
+                                }
+                            }
+                        }
+                    } else {
+                        uint8_t* orow = (uint8_t*)prm.out.ptr + (size_t)gy * prm.out.pitch + (size_t)gx * 4;
+                        #pragma unroll
+                        for (int r = 0; r < 8; r++)
+                            if (r < nrows) *reinterpret_cast<uint2*>(orow + (size_t)((uint32_t)r * opitch)) = make_uint2(w0[r], w1[r]);
+                    }
                 } else {
                     float2 res[3][8];
                     #pragma unroll
@@ -565,6 +592,11 @@ k_strip2x(const __grid_constant__ StripParams prm)
                             }
                         }
                         uint8_t* orow = (uint8_t*)prm.out.ptr + (size_t)y * prm.out.pitch;
+                        if (OFMT == MPCVR_SURF_RGB8) {                              // packed R,G,B: three 16-bit stores (gx is even)
+                            uint16_t* q = reinterpret_cast<uint16_t*>(orow + (size_t)gx * 3);
+                            q[0] = (uint16_t)(code[0][0] | (code[0][1] << 8)); q[1] = (uint16_t)(code[0][2] | (code[1][0] << 8));
+                            q[2] = (uint16_t)(code[1][1] | (code[1][2] << 8));
+                        } else
                         if (OFMT == MPCVR_SURF_RGBA16F) {
                             uint4 o;
                             const __half2 a0 = __halves2half2(hv[0][0], hv[0][1]), a1 = __halves2half2(hv[0][2], __float2half_rn(1.0f));

@@ -512,7 +512,7 @@ cudaError_t LaunchTonemapPass(const SurfDesc& in, const SurfDesc& out, const Col
 
 cudaError_t LaunchClear(const SurfDesc& s, cudaStream_t st)
 {
-    return cudaMemset2DAsync(s.ptr, s.pitch, 0, (size_t)s.w * ((s.fmt == MPCVR_SURF_RGBA16F || s.fmt == MPCVR_SURF_RGBA16) ? 8 : 4), s.h, st);
+    return cudaMemset2DAsync(s.ptr, s.pitch, 0, (size_t)s.w * ((s.fmt == MPCVR_SURF_RGBA16F || s.fmt == MPCVR_SURF_RGBA16) ? 8 : (s.fmt == MPCVR_SURF_RGB8 ? 3 : 4)), s.h, st);
 }
 
 cudaError_t LaunchToBGRX(const SurfDesc& in, const SurfDesc& out, cudaStream_t st)

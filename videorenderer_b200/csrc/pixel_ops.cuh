@@ -36,6 +36,8 @@ __device__ __forceinline__ f3 surf_load(const SurfDesc& s, int x, int y)
     } else if (s.fmt == MPCVR_SURF_RGBA16) {
         const uint2 v = __ldg((const uint2*)row + x);
         r.x = unorm16(v.x & 0xFFFFu); r.y = unorm16(v.x >> 16); r.z = unorm16(v.y & 0xFFFFu);
+    } else if (s.fmt == MPCVR_SURF_RGB8) {
+        r.x = unorm8(__ldg(row + 3 * x)); r.y = unorm8(__ldg(row + 3 * x + 1)); r.z = unorm8(__ldg(row + 3 * x + 2));
     } else {
         const uint2 v = __ldg((const uint2*)row + x);
         const __half2 a = *reinterpret_cast<const __half2*>(&v.x), b = *reinterpret_cast<const __half2*>(&v.y);
@@ -54,6 +56,8 @@ __device__ __forceinline__ void surf_store(const SurfDesc& s, int x, int y, f3 v
     } else if (s.fmt == MPCVR_SURF_RGBA16) {
         uint2 o; o.x = qunorm(v.x, 65535.0f) | (qunorm(v.y, 65535.0f) << 16); o.y = qunorm(v.z, 65535.0f) | (65535u << 16);
         ((uint2*)row)[x] = o;
+    } else if (s.fmt == MPCVR_SURF_RGB8) {                  // extension: the B8G8R8A8 codes, packed R,G,B
+        row[3 * x] = (uint8_t)qunorm(v.x, 255.0f); row[3 * x + 1] = (uint8_t)qunorm(v.y, 255.0f); row[3 * x + 2] = (uint8_t)qunorm(v.z, 255.0f);
     } else {
         const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, 1.0f);
         uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);

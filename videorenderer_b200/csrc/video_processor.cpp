@@ -11,7 +11,7 @@ namespace b200vr {
 int PlaneLoadBytes(const FmtConvParams& f, int plane);
 
 static inline int AlignUp(int v, int a) { return (v + a - 1) / a * a; }
-static inline int SurfBpp(int fmt) { return (fmt == MPCVR_SURF_RGBA16F || fmt == MPCVR_SURF_RGBA16) ? 8 : 4; }
+static inline int SurfBpp(int fmt) { return (fmt == MPCVR_SURF_RGBA16F || fmt == MPCVR_SURF_RGBA16) ? 8 : (fmt == MPCVR_SURF_RGB8 ? 3 : 4); }
 
 // ------------------------------------------------------------------------------------------------
 // Tex2D / DeviceAxis
@@ -337,7 +337,7 @@ int32_t CB200VideoProcessor::UpdateTexures()
 int32_t CB200VideoProcessor::UpdatePostScaleTexures()
 {
     const bool needDither =
-        (m_SwapChainFmt == MPCVR_SURF_BGRA8 && m_InternalTexFmt != MPCVR_SURF_BGRA8)
+        ((m_SwapChainFmt == MPCVR_SURF_BGRA8 || m_SwapChainFmt == MPCVR_SURF_RGB8) && m_InternalTexFmt != MPCVR_SURF_BGRA8)
         || (m_SwapChainFmt == MPCVR_SURF_RGB10A2 && m_InternalTexFmt == MPCVR_SURF_RGBA16F);
     m_bFinalPass = m_bUseDither && needDither;
     m_planDirty = true;
@@ -696,7 +696,7 @@ int32_t CB200VideoProcessor::GetProcAmpValues(uint32_t flags, mpcvr_procamp* v) 
 // ------------------------------------------------------------------------------------------------
 int32_t CB200VideoProcessor::SetBackbufferFormat(int fmt)
 {
-    if (fmt != MPCVR_SURF_BGRA8 && fmt != MPCVR_SURF_RGB10A2 && fmt != MPCVR_SURF_RGBA16F) return MPCVR_E_INVALIDARG;
+    if (fmt != MPCVR_SURF_BGRA8 && fmt != MPCVR_SURF_RGB10A2 && fmt != MPCVR_SURF_RGBA16F && fmt != MPCVR_SURF_RGB8) return MPCVR_E_INVALIDARG;
     m_SwapChainFmt = fmt;
     m_UserBackBuffer = Tex2D();
     return UpdatePostScaleTexures();
@@ -1099,10 +1099,14 @@ int32_t CB200VideoProcessor::Process(const Tex2D& target, const CRect& srcRect, 
         if (PlanFused(target, dstRect, fp, &why) && (m_forcePath == MPCVR_PATH_FUSED || FusedKind(fp) != 3)) {
             if (!covers) { m_lastLaunches++; if (!Cuda(LaunchClear(target.desc(), m_stream), "clear")) return MPCVR_E_FAIL; }
             int launches = 0;
-            if (!Cuda(LaunchFused(fp, m_stream, &launches), "fused frame kernel")) return MPCVR_E_FAIL;
-            m_lastLaunches += launches;
-            m_path = MPCVR_PATH_FUSED; m_bDitherUsed = fp.final_pass != 0;
-            return MPCVR_S_OK;
+            const cudaError_t fe = LaunchFused(fp, m_stream, &launches);
+            if (fe != cudaErrorNotSupported || m_forcePath == MPCVR_PATH_FUSED) {      // "not supported" at launch time: the multipass chain renders the frame
+                if (!Cuda(fe, "fused frame kernel")) return MPCVR_E_FAIL;
+                m_lastLaunches += launches;
+                m_path = MPCVR_PATH_FUSED; m_bDitherUsed = fp.final_pass != 0;
+                return MPCVR_S_OK;
+            }
+            cudaGetLastError();
         }
         if (m_forcePath == MPCVR_PATH_FUSED) return Fail(MPCVR_E_NOTIMPL, why ? why : "plan has no fused form");
     }

@@ -8,7 +8,7 @@ from . import _abi as A
 
 
 def _surf_bpp(fmt):
-    return 8 if fmt == A.SURF.RGBA16F else 4
+    return 8 if fmt in (A.SURF.RGBA16F, 3) else (3 if fmt == A.SURF.RGB8 else 4)
 
 
 class VideoProcessor:
