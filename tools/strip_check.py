@@ -11,6 +11,7 @@ import orclib as O
 import videorenderer_b200 as V
 
 PATH_FUSED = 2
+MASKS = []
 
 
 def run(case, buf, pitch, strip, cfg=0):
@@ -81,7 +82,9 @@ def timing(cfgs, steps=300):
     vp.debug_set_path(PATH_FUSED)
     ref_out = None
     res = {}
-    for name, strip, cfg in [("tile", 0, 0)] + [("strip%d" % c, 1, c) for c in cfgs]:
+    runs = [("tile", 0, 0)] + [("strip%d" % c, 1, c) for c in cfgs]
+    runs += [("skip%x" % m, 1, (m << 8)) for m in MASKS if m < 16]      # role-balance experiment: bit set = that role (P, A, B, C) only handshakes
+    for name, strip, cfg in runs:
         vp.debug_set_strip_kernel(strip, cfg)
         def step(i):
             t, pitch, _ = frames[i % 4]
@@ -95,7 +98,8 @@ def timing(cfgs, steps=300):
             e1.record(stream); torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / steps * 1e3
             step(0); out = vp.ReadBackbuffer()
-            if ref_out is None: ref_out = out; same = "ref"
+            if name.startswith("skip"): same = "(partial work)"
+            elif ref_out is None: ref_out = out; same = "ref"
             else: same = "equal" if np.array_equal(out, ref_out) else "DIFFERENT (%d bytes)" % int((out != ref_out).sum())
             res[name] = us
             print("TIME %-8s %8.1f us/frame  %8.1f fps   output %s" % (name, us, 1e6 / us, same), flush=True)
@@ -110,8 +114,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-time", action="store_true"); ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--cfgs", default="0,1,2,3")
+    ap.add_argument("--masks", default="", help="comma separated hex role-skip masks to time (bit0 P, bit1 A, bit2 B, bit3 C)")
     ap.add_argument("--one", action="store_true", help="run one small case on the strip kernel and print the watchdog record")
     a = ap.parse_args()
+    MASKS[:] = [int(x, 16) for x in a.masks.split(",") if x]
     if a.one:
         c = H.Case(O.CF["P010"], 150, 70, 300, 140, H.EX_2020_PQ, up=O.UPSCALE["Lanczos3"], name="one")
         codes = H.make_codes(c.cf, c.w, c.h, "fullnoise", 5)

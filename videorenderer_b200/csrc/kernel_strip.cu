@@ -43,8 +43,8 @@ int StripStatus(unsigned int out[8], int clear)
     return 0;
 }
 
-static int g_stripEnabled = 1, g_stripCfg = 0;
-void SetStripKernel(int enabled, int cfg) { g_stripEnabled = enabled; g_stripCfg = cfg; }
+static int g_stripEnabled = 1, g_stripCfg = 0, g_stripSkip = 0;
+void SetStripKernel(int enabled, int cfg) { g_stripEnabled = enabled; g_stripCfg = cfg & 0xFF; g_stripSkip = (cfg >> 8) & 0xF; }   // cfg bits 8..11: role-skip mask (debug)
 
 bool StripEligible(const FusedPlan& p)
 {
@@ -137,6 +137,7 @@ cudaError_t LaunchStrip2x(const FusedPlan& p, const float* gT, const float* gD, 
     prm.dst_x0 = p.ax.dst0; prm.dst_y0 = p.ay.dst0;
     prm.internal_fmt = p.internal_fmt; prm.final_pass = p.final_pass; prm.Q = p.Q;
     prm.strips = (prm.w1 + SW - 1) / SW; prm.nq = (prm.h1 + 3) / 4;
+    prm.dbg_skip = g_stripSkip;
 
     int spec = SSPEC_RUNTIME;
     if (p.internal_fmt == MPCVR_SURF_RGB10A2 && p.out.fmt == MPCVR_SURF_BGRA8 && p.final_pass && p.Q == 255.0f) spec = SSPEC_10_BGRA8_DITHER;

@@ -61,6 +61,7 @@ struct StripParams {
     int32_t     internal_fmt, final_pass;
     float       Q;
     int32_t     strips, nq;               // column strips, quads (4 convert rows) per strip
+    int32_t     dbg_skip;                 // debug (role-balance experiments): bit 0/1/2/3 = role P/A/B/C keeps its handshakes but skips its work
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------------
@@ -77,12 +78,15 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
 // bounded wait: a protocol bug makes the role give up (the frame is then wrong and g_stripStatus says where it stopped; the
 // launcher's debug query reports it) instead of hanging the device.  try_wait suspends the thread in hardware for up to the
 // hinted time, so a waiting warp costs a few instructions per microsecond, not per cycle.
+#ifndef MPCVR_STRIP_WAIT_HINT_NS
+#define MPCVR_STRIP_WAIT_HINT_NS 2000     /* suspend-time hint of mbarrier.try_wait; 20 .. 20000 ns measure the same frame time */
+#endif
 static __device__ unsigned int g_stripStatus[8];       // [0] = failures, [1] = barrier slot, [2] = parity, [3] = iteration, [4] = block, [5] = warp
 __device__ __forceinline__ bool mbar_try_hint(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"((unsigned)MPCVR_STRIP_WAIT_HINT_NS) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int it = -1)
@@ -303,6 +307,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
             float2* pV = reinterpret_cast<float2*>(smem + C::oPrep + (pslot * 3 + 2) * C::szPlane);
             if (!mbar_wait(sbase + 8 * (B_RAWFULL + slot), (it / C::NRAW) & 1, it)) return;
             if (!mbar_wait(sbase + 8 * (B_PREPEMPTY + pslot), ((it / C::NS) & 1) ^ 1, it)) return;
+            if (!(prm.dbg_skip & 1)) {
             // P0: luma codes -> floats (UNORM read)
             for (int k = tP; k < rows * C::PAIRS; k += TP) {
                 const int r = k / C::PAIRS, p = k - r * C::PAIRS;
@@ -356,6 +361,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
                 pU[k] = fma2(fy, sub2(ub, ut), ut);
                 pV[k] = fma2(fy, sub2(vb, vt), vt);
             }
+            }
             __syncwarp();
             if (lane == 0) { mbar_arrive(sbase + 8 * (B_RAWEMPTY + slot)); mbar_arrive(sbase + 8 * (B_PREPFULL + pslot)); }
         }
@@ -368,6 +374,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
         int stream = 0;                                                 // items handed out so far, modulo TA
         const uint32_t exc0 = prm.exc0;
         const float ym2s = prm.color.inv_m2 * 1.1920928955078125e-07f, ym1s = prm.color.inv_m1 * 1.1920928955078125e-07f;   // exponents * 2^-23 (exact)
+
         for (int it = 0; gi.valid; it++, gi.advance()) {
             const int slot = it % C::NS; const uint32_t ph = (it / C::NS) & 1;
             const int items = gi.rows() * C::PAIRS;
@@ -380,6 +387,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
             if (!mbar_wait(sbase + 8 * (B_PREPFULL + slot), ph, it)) return;
             if (!mbar_wait(sbase + 8 * (B_CONVEMPTY + slot), ph ^ 1, it)) return;
             int k = tA - stream; if (k < 0) k += TA;
+            if (prm.dbg_skip & 2) k = items;
             for (; k < items; k += TA) {
                 f3x2 yuv; yuv.x = pY[k]; yuv.y = pU[k]; yuv.z = pV[k];
                 if (CONV == SCONV_PQ_THR) {
@@ -416,7 +424,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
             const int rows = gi.rows(), ring0 = gi.cy0() - gi.wyA + C::R * it0;
             const float* conv = reinterpret_cast<const float*>(smem + C::oConv + slot * 3 * C::szPlane);
             for (int cb = pair; cb < C::CB; cb += C::NB / 2) {
-                if (gi.s * C::SW + 32 * cb >= prm.w1) continue;
+                if (gi.s * C::SW + 32 * cb >= prm.w1 || (prm.dbg_skip & 4)) continue;
                 const bool xedge = (cx0 + 32 * cb < 0) || (cx0 + 32 * cb + 32 + NT > prm.w1);
                 if (!xedge) xpass_rows<C, NT, DUP, false>(conv, sX, wE, wO, rows, ring0, cb, tB, 0, 0);
                 else        xpass_rows<C, NT, DUP, true>(conv, sX, wE, wO, rows, ring0, cb, tB, cx0, prm.w1);
@@ -436,6 +444,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
         for (int k = 0; k < NT; k++) { wE[k] = prm.wE[k]; wO[k] = prm.wO[k]; }
         GroupIter<C, NT> gi; gi.init(Q0, Q1, prm.nq, prm.b0, prm.h1);
         int qnext = 0, it0 = 0, turn = 0;                                // turn: items handed out so far, modulo NC
+
         for (int it = 0; gi.valid; it++, gi.advance()) {
             if (gi.g == 0) { it0 = it; qnext = gi.qa; }
             if (!mbar_wait(sbase + 8 * (B_XFULL + (it & 3)), (it >> 2) & 1, it)) return;
@@ -445,7 +454,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
               for (int cb = 0; cb < C::CB; cb++) {
                 const bool mine = turn == wc;
                 turn = (turn + 1 == C::NC) ? 0 : turn + 1;
-                if (!mine) continue;
+                if (!mine || (prm.dbg_skip & 8)) continue;
                 const int q = qnext;
                 const int col = gi.s * C::SW + 32 * cb + lane;                     // convert-surface column of this lane's output pair
                 const bool valid = col < prm.w1;                                   // lanes past the right edge compute (on in-bounds garbage) but never store
