@@ -269,6 +269,7 @@ def main():
         print(json.dumps({"error": "no CUDA device: the frame path has no CPU fallback"})); return 2
     torch.cuda.set_device(local)
     # host side of a stream: bind this rank and its pinned buffers to the GPU's NUMA node BEFORE anything is allocated
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     numa = streams.bind_to_gpu_numa(local)
     dist = None
     if world > 1:
@@ -439,6 +440,8 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
+            if all_cpus:                                   # the CPU leg gets every host core back (the GPU legs ran bound to one NUMA node)
+                os.sched_setaffinity(0, all_cpus)
             line["cpu_baseline"] = run_cpu_sample(case, frames[0], budget_s=args.cpu_seconds)
         except Exception as e:   # the checker is not the product: report, do not fail the bench
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}

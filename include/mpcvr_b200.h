@@ -162,9 +162,12 @@ typedef struct mpcvr_dovi_curve {
     int64_t  mmr_coef[8][3][7];
 } mpcvr_dovi_curve;
 typedef struct mpcvr_dovi_ext {      /* one slot of MediaSideDataDOVIMetadata::Extensions (Include/IMediaSideData.h:245-300) */
-    uint8_t  level;                   /* 0 = unused; 2 = Level2: v = {target_max_pq, trim_slope, trim_offset, trim_power,
+    uint8_t  level;                   /* 0 = unused; 1 = Level1 {min_pq, max_pq, avg_pq}; 3 = Level3 {min, max, avg pq offsets};
+                                         2 = Level2: v = {target_max_pq, trim_slope, trim_offset, trim_power,
                                          trim_chroma_weight, trim_saturation_gain, ms_weight} -> the L2 trims of the to-SDR chain
-                                         (Source/DX11VideoProcessor.cpp:2383-2466, Source/Shaders.cpp:787-795); other levels are ignored */
+                                         (Source/DX11VideoProcessor.cpp:2383-2466, Source/Shaders.cpp:787-795);
+                                         6 = Level6 {max_luminance, min_luminance, max_cll, max_fall}: static HDR10 metadata (:2477-2490);
+                                         other levels are carried, not used */
     uint16_t v[7];
 } mpcvr_dovi_ext;
 typedef struct mpcvr_dovi_metadata {
@@ -173,6 +176,10 @@ typedef struct mpcvr_dovi_metadata {
     double   ycc_to_rgb_matrix[9], ycc_to_rgb_offset[3], rgb_to_lms_matrix[9];
     uint16_t source_min_pq, source_max_pq;     /* ColorMetadata */
     mpcvr_dovi_ext ext[32];
+    /* the header / NLQ fields CheckDoviMetadata reads to turn away profile 4 and profile 7 FEL streams (Source/VideoProcessor.cpp:273-284,
+     * Source/VideoProcessor.h:249-263); a base-layer-only stream (profiles 5, 8) has disable_residual_flag = 1 */
+    uint8_t  el_spatial_resampling_filter_flag, disable_residual_flag, vdr_bit_depth, nlq_method_idc;
+    struct { uint16_t nlq_offset; uint64_t vdr_in_max, linear_deadzone_slope, linear_deadzone_threshold; } nlq[3];
 } mpcvr_dovi_metadata;
 
 #define MPCVR_SAMPLE_DEVICE_MEMORY 0x1u  /* planes are CUDA device pointers (IMediaSampleD3D11 analogue)   */

@@ -71,6 +71,7 @@ int orc_process_dovi(const orc_config* cfg, const void* const planes[3], const i
 
 /* the fetch branch and the convert-shader steps the oracle takes for cfg, as text (see orc_core.inc FN(describe)) */
 int orc_describe_convert(const orc_config* cfg, const orc_dovi* dovi, char* out, int cap);
+float orc_pq_to_linear_nits(float x);   /* PqToLinearNits, DX11VideoProcessor.cpp:2329-2334 */
 int orc_dovi_l1_nits(const orc_dovi* dv, float out_min_max_avg[3]);
 
 /* run only the post-convert passes on a given m_TexConvertOutput surface (packed, internal fmt) */

@@ -82,6 +82,17 @@ int orc_dovi_l1_nits(const orc_dovi* dv, float out_min_max_avg[3])
     return 0;
 }
 
+/* PqToLinearNits of CopySample (DX11VideoProcessor.cpp:2329-2334): host arithmetic as written there (fp32, libm powf) */
+float orc_pq_to_linear_nits(float x)
+{
+    const float PQ_M1 = 2610.f / (4096.f * 4.f), PQ_M2 = 2523.f / 4096.f * 128.f, PQ_C1 = 3424.f / 4096.f,
+                PQ_C2 = 2413.f / 4096.f * 32.f, PQ_C3 = 2392.f / 4096.f * 32.f;
+    x = powf(x, 1.0f / PQ_M2);
+    x = fmaxf(x - PQ_C1, 0.0f) / (PQ_C2 - PQ_C3 * x);
+    x = powf(x, 1.0f / PQ_M1);
+    return x * 10000.0f;
+}
+
 int orc_process_dovi(const orc_config* cfg, const void* const planes[3], const int32_t pitches[3],
                      void* out, int32_t out_pitch, orc_debug* dbg, int mode, int threads, const orc_dovi* dovi)
 {

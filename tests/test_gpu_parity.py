@@ -546,6 +546,22 @@ def test_jinc2_rects_and_final_pass():
     _check(H.Case(O.CF["P010"], 64, 36, 96, 54, H.EX_709, tex=O.TEXFMT_16FLOAT, backbuffer=O.SURF_RGB10A2, up=O.UPSCALE["Jinc2"], name="jinc2_16f"), "natural", 55)
 
 
+@pytest.mark.parametrize("rot", [0, 90, 180, 270])
+@pytest.mark.parametrize("flip", [0, 1])
+def test_jinc2_on_rotated_and_flipped_draws(rot, flip):
+    """the 2-D Jinc2 shader on a turned quad (Source/DX11VideoProcessor.cpp:3113-3141, FillVertices :130-179): both directions up (one
+    draw), one direction only, up one way / down the other (the first of the two passes carries the orientation), crop + final pass"""
+    if rot == 0 and not flip:
+        pytest.skip("covered by test_jinc2")
+    J = O.UPSCALE["Jinc2"]
+    _check(_rot_case(rot, flip, 64, 36, 96, 54, up=J), "natural", 61)
+    _check(_rot_case(rot, flip, 64, 36, 96, 36, up=J), "natural", 62)
+    _check(_rot_case(rot, flip, 64, 36, 64, 54, up=J), "natural", 63)
+    _check(_rot_case(rot, flip, 160, 40, 200, 31, up=J, down=O.DOWNSCALE["Bicubic"]), "natural", 64)        # X up (Jinc2, turned), Y down
+    _check(_rot_case(rot, flip, 40, 160, 31, 200, up=J, down=O.DOWNSCALE["Hamming"]), "natural", 65)        # X down (turned convolution), Y up (Jinc2)
+    _check(_rot_case(rot, flip, 64, 36, 80, 60, up=J, tex=O.TEXFMT_16FLOAT, src_rect=(8, 4, 56, 32)), "fullnoise", 66)
+
+
 # ---- SURVEY 8(f)-3: Dolby Vision reshaping inside the convert stage (Source/Shaders.cpp:531-589, :703-859) ----
 @pytest.mark.parametrize("mmr", [0, 1, 2])
 @pytest.mark.parametrize("to_sdr", [1, 0])
@@ -590,6 +606,20 @@ def test_dolby_vision_l2_trims(scenario):
     _check(case, "natural", 71)
 
 
+def _rpu_mastering(dv):
+    """m_DoviMaxMasteringLuminance / m_DoviMinMasteringLuminance as CopySample derives them from the RPU (:2472-2490)"""
+    import ctypes as C
+    f = O.lib().orc_pq_to_linear_nits
+    f.restype = C.c_float; f.argtypes = [C.c_float]
+    mx = int(f(np.float32(dv.source_max_pq) / np.float32(4095.0)))
+    mn = int(np.float32(f(np.float32(dv.source_min_pq) / np.float32(4095.0))) * np.float32(10000.0))
+    for i in range(32):
+        if dv.ext[i].level == 6:
+            mx, mn = int(dv.ext[i].v[0]), int(dv.ext[i].v[1])
+            break
+    return mx, mn
+
+
 @pytest.mark.parametrize("tm_type,l1", [(1, True), (5, True), (3, False), (6, True)])
 def test_dolby_vision_on_an_hdr_display_with_local_tone_mapping(tm_type, l1):
     """Dolby Vision -> PQ (no SDR conversion), then ps_hdr10_tonemap fed from Level 1 (+ Level 3) brightness in nits, BT.2390
@@ -602,11 +632,71 @@ def test_dolby_vision_on_an_hdr_display_with_local_tone_mapping(tm_type, l1):
         assert O.lib().orc_dovi_l1_nits(C.addressof(dv), nits) == 1
         hdr = dict(out=1, tonemap=1, min=nits[0], max=nits[1], cll=nits[1], fall=nits[2], display=600.0, type=6 if tm_type == 5 else tm_type)
     else:
-        hdr = dict(out=1, tonemap=1, min=50.0, max=1000.0, cll=0.0, fall=0.0, display=600.0, type=tm_type)     # Display-P3 defaults
+        # no Level 1: the static HDR10 metadata drives the curve; the stream carries none, so the Display-P3 defaults apply with the
+        # mastering luminance the RPU states (source_max_pq / source_min_pq, :2472-2475, :2685-2686)
+        mx, mn = _rpu_mastering(dv)
+        hdr = dict(out=1, tonemap=1, min=float(mn or 50), max=float(mx or 1000), cll=0.0, fall=0.0, display=600.0, type=tm_type)
     ex = O.exfmt(chroma=5, range_=1, matrix=0, prim=0, trc=0)
     hdr["settings_type"] = tm_type                            # the user's curve choice; the oracle gets what SetHDR10ShaderParams receives
     case = H.Case(O.CF["P010"], 64, 36, 96, 54, ex, backbuffer=O.SURF_RGB10A2, up=O.UPSCALE["Lanczos2"], dovi=dv, hdr=hdr, name="dovi_hdr_tm%d" % tm_type)
     _check(case, "natural", 81)
+
+
+def test_dolby_vision_level6_and_sticky_extension_blocks():
+    """(a) a Level 6 block overrides the mastering luminance derived from source_max_pq (:2477-2490); (b) the L2 trims of an earlier
+    frame stay in force for frames that carry no Level 2 block until Flush() (m_DoviExtensionMetadata is only cleared there, :4082)"""
+    import copy
+    ex = O.exfmt(chroma=5, range_=1, matrix=0, prim=0, trc=0)
+    # (a)
+    dv = H.make_dovi(83, mmr=0, source_max_pq=3696)
+    dv.ext[9].level = 6
+    for k, v in enumerate((1200, 40, 900, 300)):
+        dv.ext[9].v[k] = v
+    hdr = dict(out=1, tonemap=1, min=40.0, max=1200.0, cll=0.0, fall=0.0, display=600.0, type=2, settings_type=2)
+    _check(H.Case(O.CF["P010"], 64, 36, 96, 54, ex, backbuffer=O.SURF_RGB10A2, up=O.UPSCALE["Lanczos2"], dovi=dv, hdr=hdr, name="dovi_l6"), "natural", 83)
+    # (b) to-SDR chain: frame A carries Level 2, frame B (other curves) does not
+    l2 = [(2081, 2100, 2030, 2120, 2010, 2075), (3388, 2070, 2040, 2090, 2060, 2000)]
+    dvA = H.make_dovi(84, mmr=1, l2=l2)
+    dvB = H.make_dovi(85, mmr=1)
+    dvB_with_A = H.make_dovi(85, mmr=1, l2=l2)                     # what the reference renders B with: B's curves, A's trims
+    caseB = H.Case(O.CF["P010"], 64, 36, 96, 54, ex, up=O.UPSCALE["Lanczos2"], dovi=dvB, name="dovi_sticky")
+    codes = H.make_codes(caseB.cf, caseB.w, caseB.h, "natural", 84)
+    buf, pitch, planes, pitches = H.pack(caseB.cf, caseB.w, caseB.h, codes)
+    ref_sticky = H.run_oracle(H.Case(O.CF["P010"], 64, 36, 96, 54, ex, up=O.UPSCALE["Lanczos2"], dovi=dvB_with_A, name="x"), planes, pitches)
+    ref_plain = H.run_oracle(caseB, planes, pitches)
+    assert H.compare(ref_sticky, ref_plain, caseB.backbuffer)[0] > 0             # the trims matter on this frame
+    vp = caseB.make_processor(device=0, path=PATH_MULTIPASS)
+    vp.ProcessSample(data=buf, pitch=pitch, dovi=dvA)
+    vp.ProcessSample(data=buf, pitch=pitch, dovi=dvB)
+    assert H.compare(vp.ReadBackbuffer(), ref_sticky, caseB.backbuffer) == (0, 0)
+    vp.Flush()
+    vp.ProcessSample(data=buf, pitch=pitch, dovi=H.make_dovi(86, mmr=1))         # a different RPU, so that the curves are rebuilt
+    vp.ProcessSample(data=buf, pitch=pitch, dovi=dvB)
+    assert H.compare(vp.ReadBackbuffer(), ref_plain, caseB.backbuffer) == (0, 0)
+
+
+def test_dolby_vision_profile4_and_fel_streams_are_ignored():
+    """CheckDoviMetadata (Source/VideoProcessor.cpp:273-284): profile 4 (EL spatial resampling, residual enabled, vdr_bit_depth != 12) and
+    profile 7 FEL (non-trivial NLQ with the residual enabled) metadata is not taken: the frame renders as if there were none"""
+    ex = O.exfmt(chroma=5, range_=1, matrix=0, prim=0, trc=0)
+    case = H.Case(O.CF["P010"], 64, 36, 96, 54, ex, up=O.UPSCALE["Lanczos2"], name="dovi_rejected")
+    codes = H.make_codes(case.cf, case.w, case.h, "natural", 87)
+    buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+    ref_none = H.run_oracle(case, planes, pitches)
+    for header in (dict(el_spatial_resampling_filter_flag=1, disable_residual_flag=0, vdr_bit_depth=14, nlq=[dict(vdr_in_max=1 << 23)] * 3),
+                   dict(disable_residual_flag=0, nlq_method_idc=0, nlq=[dict(nlq_offset=5, vdr_in_max=1 << 23)] * 3)):
+        dv = H.make_dovi(87, mmr=0)
+        dv.header = header
+        vp = case.make_processor(device=0, path=PATH_MULTIPASS)
+        vp.ProcessSample(data=buf, pitch=pitch, dovi=dv)
+        assert H.compare(vp.ReadBackbuffer(), ref_none, case.backbuffer) == (0, 0), header
+    # the same metadata with the residual disabled (profile 5 / 8) IS taken
+    dv = H.make_dovi(87, mmr=0)
+    vp = case.make_processor(device=0, path=PATH_MULTIPASS)
+    vp.ProcessSample(data=buf, pitch=pitch, dovi=dv)
+    ref_dv = H.run_oracle(H.Case(O.CF["P010"], 64, 36, 96, 54, ex, up=O.UPSCALE["Lanczos2"], dovi=dv, name="x"), planes, pitches)
+    assert H.compare(vp.ReadBackbuffer(), ref_dv, case.backbuffer) == (0, 0)
+    assert H.compare(ref_dv, ref_none, case.backbuffer)[0] > 0
 
 
 # ---- SURVEY 8(f)-1: path-B correction shaders as a post-scale step on RGB from an upstream fixed-function converter ----
@@ -932,3 +1022,37 @@ def test_rgb8_full_size_c2_equals_the_bgra8_frame():
     vp, rgb = _run_gpu(c8, buf, pitch, PATH_AUTO)
     assert vp.debug_plan().path == PATH_FUSED and vp.LastFrameKernels() == 1
     assert np.array_equal(H.rgb_view(rgb, O.SURF_RGB8), H.rgb_view(bgra, O.SURF_BGRA8))
+
+
+# ---- 1:1 plans of bi-planar sources: the 128-bit span kernel (k_fused1x_bp) against the one-pixel-per-thread kernel and the oracle ----
+@pytest.mark.parametrize("name,ex", [("NV12", "709"), ("P010", "pq"), ("P016", "hlg"), ("P210", "sdr2020"), ("P216", "709")])
+@pytest.mark.parametrize("siting", [1, 5, 7])
+def test_fused_1x_span_kernel_equals_the_pixel_kernel(name, ex, siting):
+    base = {"709": dict(range_=2, matrix=1, prim=2, trc=5), "pq": dict(range_=2, matrix=4, prim=9, trc=15),
+            "hlg": dict(range_=2, matrix=4, prim=9, trc=16), "sdr2020": dict(range_=2, matrix=4, prim=9, trc=5)}[ex]
+    exf = O.exfmt(chroma=siting, **base)
+    geoms = [dict(w=160, h=46, src_rect=None, dst_rect=None, win=None),                    # aligned spans only
+             dict(w=150, h=38, src_rect=None, dst_rect=None, win=None),                    # ragged last span
+             dict(w=192, h=40, src_rect=(32, 4, 176, 38), dst_rect=None, win=None),        # crop on a span boundary (16 | 32)
+             dict(w=192, h=40, src_rect=(6, 3, 150, 37), dst_rect=None, win=None),         # crop off the boundary: pixel kernel
+             dict(w=160, h=46, src_rect=None, dst_rect=(8, 5, 168, 51), win=(180, 60))]    # offset inside a larger window
+    for g in geoms:
+        sr = g["src_rect"] or (0, 0, g["w"], g["h"])
+        dw, dh = sr[2] - sr[0], sr[3] - sr[1]
+        for tex, bb, dither in ((O.TEXFMT_AUTOINT, O.SURF_BGRA8, 1), (O.TEXFMT_16FLOAT, O.SURF_RGB10A2, 1), (O.TEXFMT_16FLOAT, O.SURF_RGBA16F, 0)):
+            case = H.Case(O.CF[name], g["w"], g["h"], dw, dh, exf, backbuffer=bb, tex=tex, dither=dither, src_rect=g["src_rect"],
+                          dst_rect=g["dst_rect"], win=g["win"], name="span1x")
+            codes = H.make_codes(case.cf, case.w, case.h, "fullnoise", 13)
+            buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+            ref = H.run_oracle(case, planes, pitches)
+            outs = []
+            try:
+                for on in (1, 0):
+                    vp = case.make_processor(device=0, path=PATH_FUSED)
+                    vp.debug_set_fused1x_vector(on)
+                    vp.ProcessSample(data=buf, pitch=pitch)
+                    outs.append(vp.ReadBackbuffer())
+            finally:
+                vp.debug_set_fused1x_vector(1)
+            assert np.array_equal(outs[0], outs[1]), (name, siting, g, tex, bb)
+            assert H.compare(outs[0], ref, bb) == (0, 0), (name, siting, g, tex, bb)

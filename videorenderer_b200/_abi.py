@@ -116,10 +116,16 @@ class DoviExt(C.Structure):
     _fields_ = [("level", C.c_uint8), ("v", C.c_uint16 * 7)]
 
 
+class DoviNlq(C.Structure):
+    _fields_ = [("nlq_offset", C.c_uint16), ("vdr_in_max", C.c_uint64), ("linear_deadzone_slope", C.c_uint64), ("linear_deadzone_threshold", C.c_uint64)]
+
+
 class DoviMetadata(C.Structure):      # mpcvr_dovi_metadata
     _fields_ = [("coef_log2_denom", C.c_uint8), ("bl_bit_depth", C.c_uint8), ("curves", DoviCurve * 3),
                 ("ycc_to_rgb_matrix", C.c_double * 9), ("ycc_to_rgb_offset", C.c_double * 3), ("rgb_to_lms_matrix", C.c_double * 9),
-                ("source_min_pq", C.c_uint16), ("source_max_pq", C.c_uint16), ("ext", DoviExt * 32)]
+                ("source_min_pq", C.c_uint16), ("source_max_pq", C.c_uint16), ("ext", DoviExt * 32),
+                ("el_spatial_resampling_filter_flag", C.c_uint8), ("disable_residual_flag", C.c_uint8), ("vdr_bit_depth", C.c_uint8),
+                ("nlq_method_idc", C.c_uint8), ("nlq", DoviNlq * 3)]
 
 
 SAMPLE_DEVICE_MEMORY = 0x1
@@ -196,6 +202,7 @@ SIGNATURES = {
     # debug header
     "mpcvr_debug_set_path": (C.c_int32, [vp, C.c_int32]),
     "mpcvr_debug_set_gamma_table": (C.c_int32, [C.c_int32]),
+    "mpcvr_debug_set_fused1x_vector": (C.c_int32, [C.c_int32]),
     "mpcvr_debug_fmt_params": (C.c_int32, [C.c_int32, C.POINTER(C.c_int32)]),
     "mpcvr_debug_specify_extended_format": (C.c_uint32, [C.c_uint32, C.c_int32, C.c_uint32, C.c_uint32]),
     "mpcvr_debug_set_strip_kernel": (C.c_int32, [C.c_int32, C.c_int32]),

@@ -456,6 +456,149 @@ k_fused1x(const __grid_constant__ Fused1xParams prm)
     surf_store(prm.out, gx, gy, p);
 }
 
+
+// the pixels of one span: OX (the horizontal quarter-texel offset of the siting) is a compile-time constant so that every index into the
+// texel window is static
+template <int PX, int OX>
+__device__ __forceinline__ void fused1x_span(const Fused1xParams& prm, const float (&Y)[PX], const float2 (&T)[2][PX / 2 + 2], float fy,
+                                             int x0, int gy, bool f16out, uint32_t (&outw)[PX], __half2 (&outh)[PX][2])
+{
+    #pragma unroll
+    for (int i = 0; i < PX; i += 2) {
+        f3x2 yuv; yuv.x = make_float2(Y[i], Y[i + 1]);
+        float2 uu, vv;
+        #pragma unroll
+        for (int k = 0; k < 2; k++) {
+            // qx = 2 (sx0 + i + k) + OX with 2 sx0 = 4 t0: texel (qx >> 2) sits at T[.][((2 (i + k) + OX) >> 2) + 1]
+            const int q = 2 * (i + k) + OX;
+            const int j = (q >> 2) + 1;
+            const float fx = (float)(q & 3) * 0.25f;
+            const float2 c00 = T[0][j], c10 = T[0][j + 1], c01 = T[1][j], c11 = T[1][j + 1];
+            const float u = lerp_mad(lerp_mad(c00.x, c10.x, fx), lerp_mad(c01.x, c11.x, fx), fy);
+            const float v = lerp_mad(lerp_mad(c00.y, c10.y, fx), lerp_mad(c01.y, c11.y, fx), fy);
+            if (k == 0) { uu.x = u; vv.x = v; } else { uu.y = u; vv.y = v; }
+        }
+        yuv.y = uu; yuv.z = vv;
+        const f3x2 rgb = convert_color2(prm.color, yuv);
+        #pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int gx = prm.dst_x0 + x0 + i + k;
+            f3 p;
+            p.x = rt_roundtrip(prm.internal_fmt, k ? rgb.x.y : rgb.x.x); p.y = rt_roundtrip(prm.internal_fmt, k ? rgb.y.y : rgb.y.x); p.z = rt_roundtrip(prm.internal_fmt, k ? rgb.z.y : rgb.z.x);
+            if (prm.final_pass) {
+                const float d = g_dither32_f[((gy & 31) << 5) + (gx & 31)];
+                p.x = final_quant(p.x, prm.Q, d); p.y = final_quant(p.y, prm.Q, d); p.z = final_quant(p.z, prm.Q, d);
+            }
+            if (f16out) { outh[i + k][0] = __floats2half2_rn(p.x, p.y); outh[i + k][1] = __floats2half2_rn(p.z, 1.0f); }
+            else if (prm.out.fmt == MPCVR_SURF_RGB10A2) outw[i + k] = qunorm(p.x, 1023.0f) | (qunorm(p.y, 1023.0f) << 10) | (qunorm(p.z, 1023.0f) << 20) | (3u << 30);
+            else outw[i + k] = qunorm(p.z, 255.0f) | (qunorm(p.y, 255.0f) << 8) | (qunorm(p.x, 255.0f) << 16) | (255u << 24);
+        }
+    }
+}
+
+// 1:1 plans of bi-planar sources (NV12 / P010 / P016 / P210 / P216) with bilinear chroma: one thread renders PX pixels of a row from ONE
+// 128-bit luma load and one 128-bit load per chroma row (+ the two neighbour texels), and writes 128-bit words.  Same arithmetic as
+// k_fused1x (fetch_planar's bilinear branch, convert_color, rt_roundtrip, final_quant, surf_store's quantiser), so the frame is bit-identical;
+// what changes is the number of memory instructions and of texel conversions per pixel.  Threads whose span touches the right edge of the
+// rect, and plans that are not 16-byte aligned, use k_fused1x's per-pixel path.
+template <int BYTES>
+__global__ void __launch_bounds__(128)
+k_fused1x_bp(const __grid_constant__ Fused1xParams prm)
+{
+    constexpr int PX = 16 / BYTES;                               // pixels per thread: 16 (8-bit) or 8 (16-bit)
+    const SrcDesc& S = prm.src;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y;
+    if (x0 >= prm.w1) return;
+    const int gy = prm.dst_y0 + y;
+    const int sy = S.rect_t + y, sx0 = S.rect_l + x0;
+    int ox, oy, my;
+    if (S.subsampling == 420) {
+        my = 2;
+        if (S.siting == ChromaSub_Cosited)    { ox = 0;  oy = 0;  }
+        else if (S.siting == ChromaSub_MPEG1) { ox = -1; oy = -1; }
+        else                                  { ox = 0;  oy = -1; }
+    } else { my = 4; ox = 0; oy = 0; }
+    if (x0 + PX > prm.w1) {                                      // ragged last span: per-pixel path
+        for (int x = x0; x < prm.w1; x++) {
+            const int gx = prm.dst_x0 + x;
+            const f3 rgb = convert_color<-1>(prm.color, fetch_yuv(S, S.rect_l + x, sy));
+            f3 p; p.x = rt_roundtrip(prm.internal_fmt, rgb.x); p.y = rt_roundtrip(prm.internal_fmt, rgb.y); p.z = rt_roundtrip(prm.internal_fmt, rgb.z);
+            if (prm.final_pass) { const float d = g_dither32_f[((gy & 31) << 5) + (gx & 31)]; p.x = final_quant(p.x, prm.Q, d); p.y = final_quant(p.y, prm.Q, d); p.z = final_quant(p.z, prm.Q, d); }
+            surf_store(prm.out, gx, gy, p);
+        }
+        return;
+    }
+    // ---- luma: one 128-bit load
+    float Y[PX];
+    {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(S.pl[0] + (ptrdiff_t)sy * S.pitch[0] + (size_t)sx0 * BYTES));
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        #pragma unroll
+        for (int i = 0; i < PX; i++)
+            Y[i] = BYTES == 1 ? unorm8((w[i >> 2] >> (8 * (i & 3))) & 255u) : unorm16((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+    }
+    // ---- chroma: texel columns [t0 - 1, t0 + PX/2 + 1] of the two rows the bilinear sample spans (sampler CLAMP on indices)
+    constexpr int NTX = PX / 2 + 2;
+    const int t0 = sx0 >> 1;                                     // texel holding luma column sx0 (sx0 is even: multiple of PX)
+    const int qy = my * sy + oy;
+    const float fy = (float)(qy & 3) * 0.25f;
+    const int r0 = clampi(qy >> 2, 0, S.ch - 1), r1 = clampi((qy >> 2) + 1, 0, S.ch - 1);
+    float2 T[2][NTX];                                            // [row][texel - (t0 - 1)] = (u, v)
+    #pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const uint8_t* row = S.pl[1] + (ptrdiff_t)(rr ? r1 : r0) * S.pitch[1];
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + (size_t)t0 * 2 * BYTES));          // texels t0 .. t0 + PX/2 - 1
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        #pragma unroll
+        for (int i = 0; i < PX / 2; i++) {
+            if (BYTES == 1) { const uint32_t c = (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu; T[rr][1 + i] = make_float2(unorm8(c & 255u), unorm8(c >> 8)); }
+            else            { const uint32_t c = w[i]; T[rr][1 + i] = make_float2(unorm16(c & 0xFFFFu), unorm16(c >> 16)); }
+        }
+        const int tl = clampi(t0 - 1, 0, S.cw - 1), tr = clampi(t0 + PX / 2, 0, S.cw - 1);
+        if (BYTES == 1) {
+            const uint32_t a = __ldg(reinterpret_cast<const uint16_t*>(row) + tl), b = __ldg(reinterpret_cast<const uint16_t*>(row) + tr);
+            T[rr][0] = make_float2(unorm8(a & 255u), unorm8(a >> 8)); T[rr][NTX - 1] = make_float2(unorm8(b & 255u), unorm8(b >> 8));
+        } else {
+            const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(row) + tl), b = __ldg(reinterpret_cast<const uint32_t*>(row) + tr);
+            T[rr][0] = make_float2(unorm16(a & 0xFFFFu), unorm16(a >> 16)); T[rr][NTX - 1] = make_float2(unorm16(b & 0xFFFFu), unorm16(b >> 16));
+        }
+    }
+    // ---- two pixels at a time through the packed-fp32 convert body, then the output stage of k_fused1x
+    uint32_t outw[PX];
+    __half2 outh[PX][2];
+    const bool f16out = prm.out.fmt == MPCVR_SURF_RGBA16F;
+    if (ox == 0) fused1x_span<PX, 0>(prm, Y, T, fy, x0, gy, f16out, outw, outh);
+    else         fused1x_span<PX, -1>(prm, Y, T, fy, x0, gy, f16out, outw, outh);
+    uint8_t* orow = (uint8_t*)prm.out.ptr + (size_t)gy * prm.out.pitch;
+    if (f16out) {
+        uint4* q = reinterpret_cast<uint4*>(orow + (size_t)(prm.dst_x0 + x0) * 8);
+        #pragma unroll
+        for (int i = 0; i < PX; i += 2)
+            q[i >> 1] = make_uint4(*reinterpret_cast<uint32_t*>(&outh[i][0]), *reinterpret_cast<uint32_t*>(&outh[i][1]),
+                                   *reinterpret_cast<uint32_t*>(&outh[i + 1][0]), *reinterpret_cast<uint32_t*>(&outh[i + 1][1]));
+    } else {
+        uint4* q = reinterpret_cast<uint4*>(orow + (size_t)(prm.dst_x0 + x0) * 4);
+        #pragma unroll
+        for (int i = 0; i < PX; i += 4) q[i >> 2] = make_uint4(outw[i], outw[i + 1], outw[i + 2], outw[i + 3]);
+    }
+}
+
+// 128-bit path of the 1:1 kernel: bi-planar, bilinear chroma, planes / pitches / rect origin / target all 16-byte aligned, target inside the window
+static bool Fused1xVectorOk(const FusedPlan& p)
+{
+    const SrcDesc& S = p.src;
+    if (S.layout != LAYOUT_BIPLANAR || S.chroma_mode != MPCVR_CHROMA_Bilinear || S.deint_blend || S.lsb_shift != 0) return false;
+    if ((S.subsampling != 420 && S.subsampling != 422) || (S.bytes != 1 && S.bytes != 2)) return false;
+    const int px = 16 / S.bytes;
+    if (((uintptr_t)S.pl[0] & 15) || ((uintptr_t)S.pl[1] & 15) || S.pitch[0] <= 0 || S.pitch[1] <= 0 || (S.pitch[0] & 15) || (S.pitch[1] & 15)) return false;
+    if ((S.rect_l % px) != 0) return false;
+    if (p.out.fmt != MPCVR_SURF_BGRA8 && p.out.fmt != MPCVR_SURF_RGB10A2 && p.out.fmt != MPCVR_SURF_RGBA16F) return false;
+    if (((uintptr_t)p.out.ptr & 15) || (p.out.pitch & 15) || (p.ax.dst0 % 4) != 0) return false;
+    if (p.ax.dst0 < 0 || p.ay.dst0 < 0 || p.ax.dst0 + p.ax.src_len > p.out.w || p.ay.dst0 + p.ay.src_len > p.out.h) return false;
+    // the 128-bit chroma load of the last full span must stay inside the plane row: texels t0 .. t0 + px/2 - 1 with t0 = sx0/2 <= (W - px)/2
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // generic fused kernel: ANY plan (arbitrary ratios, interpolation / convolution / point-sampled axes, any tap count)
 // whose per-tile source window fits in shared memory.  Same three stages, table driven; no register blocking.
@@ -664,6 +807,8 @@ static cudaError_t LaunchS(const FusedParams& prm, int spec, int conv, cudaStrea
 // builds g_gammaT / g_gammaD / g_gammaExc once per device; returns false (and leaves the plain kernel in charge) when the
 // scan finds the step function unusable
 static int g_useGammaTable = 1;                       // debug switch (mpcvr_debug_set_gamma_table)
+static int g_fused1xVector = 1;                       // debug switch: 0 keeps 1:1 plans on the one-pixel-per-thread kernel
+void SetFused1xVector(int on) { g_fused1xVector = on; }
 void SetGammaTableEnabled(int on) { g_useGammaTable = on; }
 
 static const float* g_gammaTdev[64]; static const float* g_gammaDdev[64]; static uint32_t g_gammaExcHost[64][2];   // per device, valid once ready
@@ -760,6 +905,12 @@ cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
         q.w1 = p.ax.src_len; q.h1 = p.ay.src_len; q.dst_x0 = p.ax.dst0; q.dst_y0 = p.ay.dst0;
         q.internal_fmt = p.internal_fmt; q.final_pass = p.final_pass; q.Q = p.Q;
         if (launches) *launches = 1;
+        if (g_fused1xVector && Fused1xVectorOk(p)) {
+            const int px = 16 / p.src.bytes, spans = (q.w1 + px - 1) / px;
+            const dim3 b(128, 1), g((spans + 127) / 128, q.h1);
+            if (p.src.bytes == 1) k_fused1x_bp<1><<<g, b, 0, st>>>(q); else k_fused1x_bp<2><<<g, b, 0, st>>>(q);
+            return cudaGetLastError();
+        }
         const dim3 b(32, 8), g((q.w1 + 31) / 32, (q.h1 + 7) / 8);
         k_fused1x<<<g, b, 0, st>>>(q);
         return cudaGetLastError();

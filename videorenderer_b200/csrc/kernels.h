@@ -22,13 +22,15 @@ cudaError_t LaunchFinalPass(const SurfDesc& in, const SurfDesc& out, int x0, int
 long long VerifyGammaTable(cudaStream_t st);   // mismatches of table vs direct over every float of [0,1]; -1 = table unusable
 void SetResizeFour(int on);          // debug: 0 = resize passes one output per thread (k_resize) instead of four (k_resize4)
 void SetConvertTwoLane(int on);      // debug: 0 = multipass ConvertColorPass with the scalar shader body (k_convert) instead of k_convert2
-void SetGammaTableEnabled(int on);   // debug: 0 = the 2x PQ kernel evaluates the final pow directly instead of the threshold table
+void SetGammaTableEnabled(int on);
+void SetFused1xVector(int on);      // debug: 0 = 1:1 plans one pixel per thread (k_fused1x) instead of the 128-bit span kernel (k_fused1x_bp)   // debug: 0 = the 2x PQ kernel evaluates the final pow directly instead of the threshold table
 // path-B correction shader (m_pPSCorrection) over rect, Source/DX11VideoProcessor.cpp:3354-3357
 cudaError_t LaunchCorrectionPass(const SurfDesc& in, const SurfDesc& out, const ColorParams& P, const CorrectionParams& K,
                                  int x0, int y0, int x1, int y1, cudaStream_t st);
-// UPSCALE_Jinc2: the one-pass 2-D resizer (Shaders/examples/ps_resize_onepass_jinc2.hlsl) from in rect to out rect
+// UPSCALE_Jinc2: the one-pass 2-D resizer (Shaders/examples/ps_resize_onepass_jinc2.hlsl) from in rect to out rect.
+// orient: the quad's orientation (FillVertices): bit 0 quarter turn (u follows y), bit 1 u reversed, bit 2 v reversed
 cudaError_t LaunchJinc2Pass(const SurfDesc& in, const SurfDesc& out, int in_l, int in_t, int in_w, int in_h,
-                            int out_l, int out_t, int out_w, int out_h, cudaStream_t st);
+                            int out_l, int out_t, int out_w, int out_h, cudaStream_t st, int orient = 0);
 cudaError_t LaunchTonemapPass(const SurfDesc& in, const SurfDesc& out, const ColorParams& P, const TonemapParams& T,
                               int x0, int y0, int x1, int y1, cudaStream_t st);      // ps_hdr10_tonemap post-scale step
 cudaError_t LaunchClear(const SurfDesc& s, cudaStream_t st);

@@ -181,15 +181,19 @@ k_final(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc ou
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_jinc2(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc out,
-        int in_l, int in_t, int in_w, int in_h, int out_l, int out_t, int out_w, int out_h)
+        int in_l, int in_t, int in_w, int in_h, int out_l, int out_t, int out_w, int out_h, int orient)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= out_w || y >= out_h) return;
     const int ox = out_l + x, oy = out_t + y;
     if (ox < 0 || oy < 0 || ox >= out.w || oy >= out.h) return;
-    const float sx = __fdiv_rn((float)in_w, (float)out_w), sy = __fdiv_rn((float)in_h, (float)out_h);   // :351-354
-    const float pcx = __fadd_rn(__fmul_rn(__fadd_rn((float)x, 0.5f), sx), (float)in_l);
-    const float pcy = __fadd_rn(__fmul_rn(__fadd_rn((float)y, 0.5f), sy), (float)in_t);
+    // orient (FillVertices, Source/DX11VideoProcessor.cpp:130-179): bit 0 = quarter turn (u follows y), bit 1 = u reversed, bit 2 = v reversed
+    const bool turned = orient & 1, u_rev = orient & 2, v_rev = orient & 4;
+    const int ui = turned ? y : x, vi = turned ? x : y;
+    const float su = __fdiv_rn((float)in_w, (float)(turned ? out_h : out_w)), sv = __fdiv_rn((float)in_h, (float)(turned ? out_w : out_h));   // :351-354
+    const float du = __fmul_rn(__fadd_rn((float)ui, 0.5f), su), dv = __fmul_rn(__fadd_rn((float)vi, 0.5f), sv);
+    const float pcx = u_rev ? __fsub_rn((float)(in_l + in_w), du) : __fadd_rn(du, (float)in_l);
+    const float pcy = v_rev ? __fsub_rn((float)(in_t + in_h), dv) : __fadd_rn(dv, (float)in_t);
     const float pi = 3.14159265358979323846f;
     const float wa = __fmul_rn(0.416f, pi), wb = __fmul_rn(0.985f, pi), wab = __fmul_rn(wa, wb);
     const float tcx = __fadd_rn(floorf(__fsub_rn(pcx, 0.5f)), 0.5f), tcy = __fadd_rn(floorf(__fsub_rn(pcy, 0.5f)), 0.5f);
@@ -493,11 +497,11 @@ cudaError_t LaunchCorrectionPass(const SurfDesc& in, const SurfDesc& out, const 
 }
 
 cudaError_t LaunchJinc2Pass(const SurfDesc& in, const SurfDesc& out, int in_l, int in_t, int in_w, int in_h,
-                            int out_l, int out_t, int out_w, int out_h, cudaStream_t st)
+                            int out_l, int out_t, int out_w, int out_h, cudaStream_t st, int orient)
 {
     if (out_w <= 0 || out_h <= 0) return cudaSuccess;
     const dim3 b(32, 8);
-    k_jinc2<<<Grid2D(out_w, out_h, b), b, 0, st>>>(in, out, in_l, in_t, in_w, in_h, out_l, out_t, out_w, out_h);
+    k_jinc2<<<Grid2D(out_w, out_h, b), b, 0, st>>>(in, out, in_l, in_t, in_w, in_h, out_l, out_t, out_w, out_h, orient);
     return cudaGetLastError();
 }
 

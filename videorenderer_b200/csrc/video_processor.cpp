@@ -379,6 +379,14 @@ int32_t CB200VideoProcessor::SetFlip(bool v)
 bool CB200VideoProcessor::CheckDoviMetadata(const mpcvr_dovi_metadata* p) const
 {
     if (p->bl_bit_depth < 8 || p->bl_bit_depth > 16 || p->coef_log2_denom > 31) return false;
+    // "ignore Profile 4" (Source/VideoProcessor.cpp:275-279)
+    if (p->el_spatial_resampling_filter_flag && !p->disable_residual_flag && p->vdr_bit_depth != 12) return false;
+    // "Ignore Profile 7 Full Enhancement Layer" (SourceIsDoviFel, Source/VideoProcessor.h:249-263)
+    if (!p->disable_residual_flag && p->nlq_method_idc == 0) {
+        for (int i = 0; i < 3; i++)
+            if (p->nlq[i].nlq_offset != 0 || p->nlq[i].vdr_in_max != (1ULL << p->coef_log2_denom) ||
+                p->nlq[i].linear_deadzone_slope != 0 || p->nlq[i].linear_deadzone_threshold != 0) return false;
+    }
     for (const auto& curve : p->curves) {
         if (curve.num_pivots < 2 || curve.num_pivots > 9) return false;
         for (int i = 0; i < (int)curve.num_pivots - 1; i++) {
@@ -475,14 +483,18 @@ int32_t CB200VideoProcessor::SetShaderDoviCurves()
             } else if (upper != -1) {
                 for (int k = 0; k < 5; k++) tv[k] = (float)dv.ext[upper].v[1 + k];
             }
+            m_doviL2Present = true;                                       // m_DoviExtensionMetadata.L2.present = true, :2463 -- never cleared per frame
+            m_doviL2[0] = tv[0] / 4096.0f + 0.5f; m_doviL2[1] = tv[1] / 4096.0f - 0.5f; m_doviL2[2] = tv[2] / 4096.0f + 0.5f;
+            m_doviL2[3] = tv[3] / 4096.0f - 0.5f; m_doviL2[4] = tv[4] / 4096.0f - 0.5f;
+        }
+        if (m_doviL2Present) {                                           // SetDolbyVisionDynamicParams, :953-960: the last trims seen
             P.l2_enabled = 1;
-            P.l2_slope = tv[0] / 4096.0f + 0.5f; P.l2_offset = tv[1] / 4096.0f - 0.5f; P.l2_power = tv[2] / 4096.0f + 0.5f;
-            P.l2_chroma_weight = tv[3] / 4096.0f - 0.5f; P.l2_saturation_gain = tv[4] / 4096.0f - 0.5f;
+            P.l2_slope = m_doviL2[0]; P.l2_offset = m_doviL2[1]; P.l2_power = m_doviL2[2];
+            P.l2_chroma_weight = m_doviL2[3]; P.l2_saturation_gain = m_doviL2[4];
         }
     }
     // Level 1 (+ Level 3 offsets) -> nits (:2347-2381): feeds SetHDR10ShaderParams when local tone mapping is on
-    m_doviL1Present = false;
-    for (int i = 0; i < 32 && !m_doviL1Present; i++) {
+    for (int i = 0; i < 32; i++) {                                           // the first Level 1 block; none: the previous values stay (sticky)
         if (dv.ext[i].level != 1) continue;
         uint16_t v[3] = { dv.ext[i].v[0], dv.ext[i].v[1], dv.ext[i].v[2] };
         for (int k = 0; k < 32; k++)
@@ -497,6 +509,7 @@ int32_t CB200VideoProcessor::SetShaderDoviCurves()
             m_doviL1Nits[j] = (float)(uint16_t)(unsigned int)(x * 10000.0f);
         }
         m_doviL1Present = true;
+        break;
     }
     if (m_device >= 0) {
         cudaSetDevice(m_device);
@@ -613,12 +626,25 @@ void CB200VideoProcessor::UpdateHdrState()
     // The part of Render() under "if (m_pDXGISwapChain4)" (:2626-2727); that swap chain exists when
     // bHdrOutput = m_bHdrPassthroughSupport && (m_bHdrPassthrough || m_bHdrLocalToneMapping) && SourceIsHDR() (:1476).
     if (!(HdrOut() && (SourceIsHDR10orHLG() || m_Dovi.bValid))) { m_hdrColorSpaceActive = false; m_bTonemap = false; return; }   // SourceIsHDR(), :1476
+    if (m_Dovi.bValid) {                                                      // :2627-2648: the RPU's static metadata tops up the stream's
+        if (!m_hdr10.bValid && m_lastHdr10.bValid) { m_hdr10 = m_lastHdr10; m_hdr10.bValid = true; }
+        if (m_hdr10.bValid) {
+            if (m_DoviMaxMasteringLuminance > m_hdr10.MaxMasteringLuminance) m_hdr10.MaxMasteringLuminance = m_DoviMaxMasteringLuminance;
+            if (m_DoviMinMasteringLuminance && m_DoviMinMasteringLuminance != m_hdr10.MinMasteringLuminance) m_hdr10.MinMasteringLuminance = m_DoviMinMasteringLuminance;
+            if (m_DoviMaxContentLightLevel && m_DoviMaxContentLightLevel != m_hdr10.MaxCLL) m_hdr10.MaxCLL = (uint16_t)m_DoviMaxContentLightLevel;
+            if (m_DoviMaxFrameAverageLightLevel && m_DoviMaxFrameAverageLightLevel != m_hdr10.MaxFALL) m_hdr10.MaxFALL = (uint16_t)m_DoviMaxFrameAverageLightLevel;
+        }
+    }
     if (!m_hdrColorSpaceActive) {                                             // SetColorSpace1(G2084/P2020) succeeded, :2651-2690
         m_hdrColorSpaceActive = true;
         if (m_hdr10.bValid) m_lastHdr10 = m_hdr10;
-        else if (!m_lastHdr10.bValid) {                                       // Display-P3 defaults, :2673-2684
+        else if (!m_lastHdr10.bValid) {                                       // Display-P3 defaults, :2673-2692
             m_lastHdr10 = Hdr10(); m_lastHdr10.bValid = true;
-            m_lastHdr10.MaxMasteringLuminance = 1000; m_lastHdr10.MinMasteringLuminance = 50;
+            m_lastHdr10.MaxMasteringLuminance = m_DoviMaxMasteringLuminance ? m_DoviMaxMasteringLuminance : 1000;
+            m_lastHdr10.MinMasteringLuminance = m_DoviMinMasteringLuminance ? m_DoviMinMasteringLuminance : 50;
+            // the reference writes the RPU's MaxCLL / MaxFALL into m_hdr10 here, which is not valid at this point (:2687-2692): kept
+            if (m_DoviMaxContentLightLevel) m_hdr10.MaxCLL = (uint16_t)m_DoviMaxContentLightLevel;
+            if (m_DoviMaxFrameAverageLightLevel) m_hdr10.MaxFALL = (uint16_t)m_DoviMaxFrameAverageLightLevel;
         }
     } else if (m_hdr10.bValid) {                                              // :2703-2712
         if (m_hdr10.MaxMasteringLuminance != m_lastHdr10.MaxMasteringLuminance || m_hdr10.MinMasteringLuminance != m_lastHdr10.MinMasteringLuminance ||
@@ -653,9 +679,14 @@ void CB200VideoProcessor::Configure(const mpcvr_settings& s)
 {
     // diff and rebuild the minimum, like Source/DX11VideoProcessor.cpp:3800-4050
     const int oldTex = m_iTexFormat; const bool oldSdr = m_bConvertToSdr; const int oldNits = m_iSDRDisplayNits;
-    const bool oldHdrOut = HdrOut(); const int oldHdrNits = m_iHdrDisplayMaxNits;
+    const bool oldHdrOut = HdrOut(); const int oldHdrNits = m_iHdrDisplayMaxNits; const bool oldPreferDoVi = m_bHdrPreferDoVi;
     ApplySettings(s);
     if (!m_bInit) return;
+    if (oldPreferDoVi != m_bHdrPreferDoVi && m_Dovi.bValid && !m_bHdrPreferDoVi && SourceIsHDR10orHLG()) {   // :3891-3898
+        m_Dovi.bValid = false; m_Dovi.bHasMMR = false; m_Dovi.msd = mpcvr_dovi_metadata();
+        m_doviL1Present = false; m_doviL2Present = false;
+        SetShaderConvertColorParams();
+    }
     // the convert shader is rebuilt on a chroma-scaling / blend change (:3985-3999): the current frame re-renders with the new fetch
     m_src.chroma_mode = m_iChromaScaling;
     m_src.deint_blend = (m_bDeintBlend && m_bInterlaced && m_srcParams.Subsampling == 420) ? 1 : 0;
@@ -799,6 +830,26 @@ int32_t CB200VideoProcessor::CopySample(const mpcvr_sample* s)
         const bool take = s->dovi && f.CSType == CS_YUV && (m_bHdrPreferDoVi || !SourceIsHDR10orHLG()) && CheckDoviMetadata(s->dovi);
         if (take) {
             const bool changed = !m_Dovi.bValid || memcmp(&m_Dovi.msd, s->dovi, sizeof(m_Dovi.msd)) != 0;
+            // bMasteringLuminanceChanged compares with whatever m_Dovi.msd held before (zeros at first), :2300-2301
+            const bool masteringChanged = m_Dovi.msd.source_max_pq != s->dovi->source_max_pq || m_Dovi.msd.source_min_pq != s->dovi->source_min_pq;
+            if (masteringChanged) {                                       // :2472-2490
+                auto PqToLinearNits = [](float x) {
+                    const float PQ_M1 = 2610.f / (4096.f * 4.f), PQ_M2 = 2523.f / 4096.f * 128.f, PQ_C1 = 3424.f / 4096.f,
+                                PQ_C2 = 2413.f / 4096.f * 32.f, PQ_C3 = 2392.f / 4096.f * 32.f;
+                    x = powf(x, 1.0f / PQ_M2);
+                    x = fmaxf(x - PQ_C1, 0.0f) / (PQ_C2 - PQ_C3 * x);
+                    x = powf(x, 1.0f / PQ_M1);
+                    return x * 10000.0f;
+                };
+                m_DoviMaxMasteringLuminance = (uint32_t)PqToLinearNits(s->dovi->source_max_pq / 4095.f);
+                m_DoviMinMasteringLuminance = (uint32_t)(PqToLinearNits(s->dovi->source_min_pq / 4095.f) * 10000.0f);
+                for (int i = 0; i < 32; i++) {
+                    if (s->dovi->ext[i].level != 6) continue;
+                    m_DoviMaxMasteringLuminance = s->dovi->ext[i].v[0]; m_DoviMinMasteringLuminance = s->dovi->ext[i].v[1];
+                    m_DoviMaxContentLightLevel = s->dovi->ext[i].v[2]; m_DoviMaxFrameAverageLightLevel = s->dovi->ext[i].v[3];
+                    break;
+                }
+            }
             if (changed) {
                 m_Dovi.msd = *s->dovi; m_Dovi.bValid = true;
                 const int32_t hr = SetShaderDoviCurves();
@@ -906,7 +957,11 @@ int32_t CB200VideoProcessor::FillBlack()
     return Cuda(LaunchClear(t.desc(), m_stream), "clear") ? MPCVR_S_OK : MPCVR_E_FAIL;
 }
 
-void CB200VideoProcessor::Flush() { m_haveFrame = false; m_rtStart = 0; }
+void CB200VideoProcessor::Flush()
+{
+    m_haveFrame = false; m_rtStart = 0;
+    m_doviL1Present = false; m_doviL2Present = false;                       // m_DoviExtensionMetadata = {}, Source/DX11VideoProcessor.cpp:4082
+}
 
 int32_t CB200VideoProcessor::Reset(bool) { m_planDirty = true; return MPCVR_S_OK; }
 
@@ -934,7 +989,6 @@ int32_t CB200VideoProcessor::UpdatePlan()
     m_kx = kx; m_ky = ky;
     m_jincX = (kx == SCALER_INTERP && m_iUpscaling == MPCVR_UPSCALE_Jinc2);
     m_jincY = (ky == SCALER_INTERP && m_iUpscaling == MPCVR_UPSCALE_Jinc2);
-    if ((m_jincX || m_jincY) && m_oriented) return Fail(MPCVR_E_NOTIMPL, "Jinc2 on a rotated / flipped draw is not implemented");
     if (!BuildAxisTable(m_jincX ? SCALER_NEAREST : kx, fx, d3d9, rSrc.left, w1, dst.left, w2, m_axisX.host)) return Fail(MPCVR_E_NOTIMPL, "X scaler not available");
     // two shader passes: the Y pass reads m_TexResize, whose rows start at 0 (resize rect (dst.left, 0, dst.right, h1), :3150-3160)
     const bool twoPass = (kx == SCALER_INTERP || kx == SCALER_CONV) && (ky == SCALER_INTERP || ky == SCALER_CONV);
@@ -963,8 +1017,10 @@ int32_t CB200VideoProcessor::UpdatePlan()
         BuildAxisTable(SCALER_NEAREST, 0, d3d9, rSrc.left, rSrc.Width(), uFromX ? dst.left : oy0, uLen, m_oU.host, uRev);
         BuildAxisTable(SCALER_NEAREST, 0, d3d9, rSrc.top, rSrc.Height(), uFromX ? oy0 : dst.left, vLen, m_oV.host, vRev);
         int kind = SCALER_NONE, filt = 0;
-        if (shaderX)      { m_oInAxis = rotated ? 1 : 0; m_oOutAxis = 0; kind = kx; filt = fx; }
-        else if (shaderY) { m_oInAxis = rotated ? 0 : 1; m_oOutAxis = 1; kind = ky; filt = fy; }
+        // a Jinc2 direction needs no table (the 2-D shader takes the turned quad as it is, LaunchJinc2Pass' orient); the only table an
+        // oriented Jinc2 plan may need is the convolution of a shrinking X direction, whose draw then carries the orientation
+        if (shaderX && !m_jincX)                   { m_oInAxis = rotated ? 1 : 0; m_oOutAxis = 0; kind = kx; filt = fx; }
+        else if (!shaderX && shaderY && !m_jincY)  { m_oInAxis = rotated ? 0 : 1; m_oOutAxis = 1; kind = ky; filt = fy; }
         if (m_oInAxis >= 0) {
             // shader constant: scale.x = srcRect.W / dstRect.W, scale.y = srcRect.H / dstRect.H (:351-354), turned or not
             const float qscale = m_oInAxis == 0 ? (float)rSrc.Width() / (float)ow : (float)rSrc.Height() / (float)oh;
@@ -1008,13 +1064,18 @@ int32_t CB200VideoProcessor::ResizeShaderPass(const Tex2D& tex, const Tex2D& rt,
     const int h1 = m_axisY.host.src_len;
     if (m_jincX || m_jincY) {
         // resizerX == resizerY (or only one of them): one 2-D draw (:3135-3141, :3169-3177); if the other direction shrinks, the
-        // convolution shader takes that pass and m_TexResize sits in between (:3143-3167)
+        // convolution shader takes that pass and m_TexResize sits in between (:3143-3167).  The FIRST draw carries rotation / flip.
+        const int rot = m_iRotation;
+        const int orient = m_oriented ? (((rot == 90 || rot == 270) ? 1 : 0) | ((((rot == 180 || rot == 270) != m_bFlip)) ? 2 : 0) | ((rot == 90 || rot == 180) ? 4 : 0)) : 0;
         if (kx == SCALER_CONV || ky == SCALER_CONV) {
             if (!Cuda(m_TexResize.CheckCreate(MPCVR_SURF_RGBA16F, rt.w, h1), "m_TexResize")) return MPCVR_E_FAIL;
             m_lastLaunches += 2;
-            const cudaError_t e1 = m_jincX
-                ? LaunchJinc2Pass(tex.desc(), m_TexResize.desc(), srcRect.left, srcRect.top, srcRect.Width(), srcRect.Height(), dstRect.left, 0, dstRect.Width(), h1, m_stream)
-                : LaunchResizePass(tex.desc(), m_TexResize.desc(), m_axisX.table(), 0, m_pointRY.base.ptr, 0, h1, m_stream);
+            cudaError_t e1;
+            if (m_jincX) e1 = LaunchJinc2Pass(tex.desc(), m_TexResize.desc(), srcRect.left, srcRect.top, srcRect.Width(), srcRect.Height(), dstRect.left, 0, dstRect.Width(), h1, m_stream, orient);
+            else if (m_oriented) {                 // turned convolution of the X direction (see the oriented branch below)
+                const int32_t* other = (m_oInAxis == 0) ? m_oV.base.ptr : m_oU.base.ptr;
+                e1 = LaunchResizePass(tex.desc(), m_TexResize.desc(), m_oFilt.table(), 0, other, 0, h1, m_stream, m_oInAxis);
+            } else e1 = LaunchResizePass(tex.desc(), m_TexResize.desc(), m_axisX.table(), 0, m_pointRY.base.ptr, 0, h1, m_stream);
             if (!Cuda(e1, "resize X")) return MPCVR_E_FAIL;
             const cudaError_t e2 = m_jincY
                 ? LaunchJinc2Pass(m_TexResize.desc(), rt.desc(), dstRect.left, 0, dstRect.Width(), h1, dstRect.left, dstRect.top, dstRect.Width(), dstRect.Height(), m_stream)
@@ -1023,7 +1084,7 @@ int32_t CB200VideoProcessor::ResizeShaderPass(const Tex2D& tex, const Tex2D& rt,
         } else {
             m_lastLaunches++;
             if (!Cuda(LaunchJinc2Pass(tex.desc(), rt.desc(), srcRect.left, srcRect.top, srcRect.Width(), srcRect.Height(),
-                                      dstRect.left, dstRect.top, dstRect.Width(), dstRect.Height(), m_stream), "Jinc2")) return MPCVR_E_FAIL;
+                                      dstRect.left, dstRect.top, dstRect.Width(), dstRect.Height(), m_stream, orient), "Jinc2")) return MPCVR_E_FAIL;
         }
         return MPCVR_S_OK;
     }

@@ -202,7 +202,12 @@ private:
     struct { mpcvr_dovi_metadata msd = {}; bool bValid = false; bool bHasMMR = false; } m_Dovi;
     bool m_bHdrPreferDoVi = false;
     DoviParams m_doviHost = {};
-    bool  m_doviL1Present = false; float m_doviL1Nits[3] = {0, 0, 0};       // m_DoviExtensionMetadata.L1 (min, max, avg) in nits
+    // m_DoviExtensionMetadata (Source/DX11VideoProcessor.h:211-237): L1 (min, max, avg in nits) and the L2 trims stay set once a frame
+    // carried them -- later frames without those blocks keep the last values -- until Flush() or a bHdrPreferDoVi change clears them
+    bool  m_doviL1Present = false; float m_doviL1Nits[3] = {0, 0, 0};
+    bool  m_doviL2Present = false; float m_doviL2[5] = {0, 0, 0, 0, 0};     // slope, offset, power, chroma weight, saturation gain (as DolbyConstants take them)
+    // static HDR10 metadata derived from the RPU (:2472-2490): source_max_pq / source_min_pq, overridden by a Level 6 block
+    uint32_t m_DoviMaxMasteringLuminance = 0, m_DoviMinMasteringLuminance = 0, m_DoviMaxContentLightLevel = 0, m_DoviMaxFrameAverageLightLevel = 0;
     DevArray<DoviParams> m_doviDev;
     bool    CheckDoviMetadata(const mpcvr_dovi_metadata* p) const;          // Source/VideoProcessor.cpp:273-297 (curve part)
     int32_t SetShaderDoviCurves();                                          // :990-1141

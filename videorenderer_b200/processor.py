@@ -135,7 +135,21 @@ class VideoProcessor:
             h.max_display_mastering_luminance = hdr["max_lum"]; h.min_display_mastering_luminance = hdr["min_lum"]
             self._keep_hdr = h
             s.hdr = C.pointer(h)
-        if dovi is not None:                       # an _abi.DoviMetadata (or any ctypes struct with that layout)
+        if dovi is not None:                       # an _abi.DoviMetadata, or a ctypes struct with the layout of its leading part
+            if not isinstance(dovi, A.DoviMetadata):
+                # e.g. the oracle's OrcDovi (curves, matrices, extension blocks): completed as a base-layer-only stream (profile 5 / 8);
+                # a `header` attribute (dict) on the object overrides the acceptance fields
+                d = A.DoviMetadata()
+                C.memmove(C.byref(d), C.byref(dovi), min(C.sizeof(dovi), C.sizeof(d)))
+                d.disable_residual_flag = 1
+                for k, v in (getattr(dovi, "header", None) or {}).items():
+                    if k == "nlq":
+                        for i, q in enumerate(v):
+                            for kk, vv in q.items():
+                                setattr(d.nlq[i], kk, vv)
+                    else:
+                        setattr(d, k, v)
+                dovi = d
             self._keep_dovi = dovi
             s.dovi = C.cast(C.pointer(dovi), C.POINTER(A.DoviMetadata))
         if hdr_cll is not None:
@@ -229,6 +243,9 @@ class VideoProcessor:
 
     def debug_set_gamma_table(self, enable):
         return self._L.mpcvr_debug_set_gamma_table(int(bool(enable)))
+
+    def debug_set_fused1x_vector(self, enable):
+        return self._L.mpcvr_debug_set_fused1x_vector(int(bool(enable)))
 
     def debug_set_strip_kernel(self, enable, cfg=0):
         return self._L.mpcvr_debug_set_strip_kernel(int(bool(enable)), int(cfg))
