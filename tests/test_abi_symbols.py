@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_abi.MediaType) == 5 * 4 + 16 + 4 * 4 + 4 + 8 + 2 * 4
     assert ctypes.sizeof(_abi.SideDataHDR) == 80 and ctypes.sizeof(_abi.SideDataHDRCLL) == 8   # Include/IMediaSideData.h:35-60, pack(1)
     assert ctypes.sizeof(_abi.PlanInfo) == 15 * 4
-    assert ctypes.sizeof(_abi.DoviMetadata) == 5640 and ctypes.sizeof(_abi.Sample) == 120
+    assert ctypes.sizeof(_abi.DoviMetadata) == 5736 and ctypes.sizeof(_abi.Sample) == 120
     s = _abi.Sample()
     assert ctypes.sizeof(s) % 8 == 0
 
