@@ -31,6 +31,8 @@ typedef struct mpcvr_plan_info {
 } mpcvr_plan_info;
 
 int32_t mpcvr_debug_set_path(mpcvr* vp, int32_t path);
+/* Render() the current frame n times back to back from C (measurement aid: the per-frame cost without the caller's language overhead) */
+int32_t mpcvr_debug_render_n(mpcvr* vp, int32_t n);
 /* the row of the input format table (Source/Helper.cpp:311-359 columns the chain uses): cformat, Packsize, PitchCoeff, CSType, Subsampling,
  * CDepth, layout (SrcLayout), bytes per component, div_chroma_w, div_chroma_h, lsb_shift, v_before_u.  No device needed. */
 int32_t mpcvr_debug_fmt_params(int32_t cformat, int32_t out[12]);

@@ -224,3 +224,14 @@ def test_correction_shader_choice_follows_the_reference_rules():
     assert mode(pq, hdr_display=True, passthrough=0) == 2                  # HDR display but neither passthrough nor local tone mapping
     assert mode(pq, d3d11=0, upstream=(True, True)) == 2 and mode(hlg, d3d11=0) == 3 and mode(sdr2020, d3d11=0) == 4
     assert mode(pq, d3d11=0, to_sdr=0) == 4 and mode(sdr709, d3d11=0) == 0
+
+
+def test_unorm8_readback_then_requantise_is_identity():
+    """The 1:1 span kernel writes Q8(v) directly when an 8-bit convert surface is copied to an 8-bit back buffer
+    (kernel_fused.cu fused1x_span, same8): UNORM8 read-back (c/255, correctly rounded) followed by the UNORM8 write
+    (floor(fma(p, 255, 0.5))) must return c for every code."""
+    import numpy as np
+    c = np.arange(256, dtype=np.float32)
+    p = (c / np.float32(255.0)).astype(np.float32)
+    q = np.floor((p.astype(np.float64) * 255.0 + 0.5).astype(np.float32))
+    assert np.array_equal(q, c)

@@ -33,6 +33,10 @@ for idx, case in enumerate(H.baseline_cases(1.0)):
         for i in range(n): step(i)
         e1.record(stream); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
+        # the same frame re-rendered from C (no Python between launches): the kernels' own rate
+        vp.debug_render_n(20); torch.cuda.synchronize()
+        e0.record(stream); vp.debug_render_n(200); e1.record(stream); torch.cuda.synchronize()
+        ms_c = e0.elapsed_time(e1) / 200
         gbs = ALGO[idx] / (ms * 1e-3) / 1e9
         print(json.dumps({"config": case.name, "path": {1: "multipass", 2: "fused"}[vp.debug_plan().path], "kernels_per_frame": vp.LastFrameKernels(),
-                          "ms_per_frame": round(ms, 4), "frames_per_s": round(1e3 / ms, 1), "algorithmic_GBps": round(gbs, 1), "frac_of_measured_hbm": round(gbs / peak, 4)}))
+                          "ms_per_frame": round(ms, 4), "frames_per_s": round(1e3 / ms, 1), "ms_per_frame_c_loop": round(ms_c, 4), "frames_per_s_c_loop": round(1e3 / ms_c, 1), "algorithmic_GBps": round(gbs, 1), "frac_of_measured_hbm": round(gbs / peak, 4)}))

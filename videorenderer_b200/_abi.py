@@ -202,6 +202,7 @@ SIGNATURES = {
     # debug header
     "mpcvr_debug_set_path": (C.c_int32, [vp, C.c_int32]),
     "mpcvr_debug_set_gamma_table": (C.c_int32, [C.c_int32]),
+    "mpcvr_debug_render_n": (C.c_int32, [C.c_void_p, C.c_int32]),
     "mpcvr_debug_set_fused1x_vector": (C.c_int32, [C.c_int32]),
     "mpcvr_debug_fmt_params": (C.c_int32, [C.c_int32, C.POINTER(C.c_int32)]),
     "mpcvr_debug_specify_extended_format": (C.c_uint32, [C.c_uint32, C.c_int32, C.c_uint32, C.c_uint32]),

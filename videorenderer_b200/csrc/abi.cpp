@@ -119,6 +119,12 @@ uint32_t mpcvr_debug_specify_extended_format(uint32_t exfmt, int32_t cformat, ui
     b200vr::ExtendedFormat e; e.value = exfmt;
     return b200vr::SpecifyExtendedFormat(e, b200vr::GetFmtConvParams(cformat), width, height).value;
 }
+int32_t mpcvr_debug_render_n(mpcvr* h, int32_t n)
+{
+    VP_OR(MPCVR_E_POINTER);
+    for (int32_t i = 0; i < n; i++) { const int32_t hr = vp.Render(1, 0); if (hr != MPCVR_S_OK) return hr; }
+    return MPCVR_S_OK;
+}
 int32_t mpcvr_debug_set_path(mpcvr* h, int32_t path) { VP_OR(MPCVR_E_POINTER); return vp.DebugSetPath(path); }
 int32_t mpcvr_debug_get_plan(mpcvr* h, mpcvr_plan_info* info) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugGetPlan(info)); }
 int32_t mpcvr_debug_get_color_params(mpcvr* h, float m9[9], float c3[3], float g9[9], float* lum) { VP_OR(MPCVR_E_POINTER); return vp.DebugGetColorParams(m9, c3, g9, lum); }

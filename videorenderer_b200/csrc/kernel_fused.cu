@@ -463,6 +463,7 @@ template <int PX, int OX>
 __device__ __forceinline__ void fused1x_span(const Fused1xParams& prm, const float (&Y)[PX], const float2 (&T)[2][PX / 2 + 2], float fy,
                                              int x0, int gy, bool f16out, uint32_t (&outw)[PX], __half2 (&outh)[PX][2])
 {
+    const bool same8 = prm.internal_fmt == MPCVR_SURF_BGRA8 && prm.out.fmt == MPCVR_SURF_BGRA8 && !prm.final_pass;
     #pragma unroll
     for (int i = 0; i < PX; i += 2) {
         f3x2 yuv; yuv.x = make_float2(Y[i], Y[i + 1]);
@@ -479,7 +480,17 @@ __device__ __forceinline__ void fused1x_span(const Fused1xParams& prm, const flo
             if (k == 0) { uu.x = u; vv.x = v; } else { uu.y = u; vv.y = v; }
         }
         yuv.y = uu; yuv.z = vv;
-        const f3x2 rgb = convert_color2(prm.color, yuv);
+        // matrix-only convert body (TRANSFER_NONE, the launcher's condition): the first statement of convert_color2.  The span is fully
+        // unrolled, so a transfer chain inlined here would be replicated PX/2 times and the kernel would run out of the instruction cache
+        f3x2 rgb;
+        rgb.x = add2(dp3_2(prm.color.cm[0], yuv), prm.color.cc[0]); rgb.y = add2(dp3_2(prm.color.cm[1], yuv), prm.color.cc[1]); rgb.z = add2(dp3_2(prm.color.cm[2], yuv), prm.color.cc[2]);
+        if (same8) {
+            // B8G8R8A8 convert surface copied to a B8G8R8A8 back buffer: UNORM8 read-back then UNORM8 write returns the code itself
+            // (c/255 rounded, times 255, is within 2^-16 of c; tests/test_host_tables.py checks all 256 codes), so one quantiser suffices
+            outw[i]     = qunorm(rgb.z.x, 255.0f) | (qunorm(rgb.y.x, 255.0f) << 8) | (qunorm(rgb.x.x, 255.0f) << 16) | (255u << 24);
+            outw[i + 1] = qunorm(rgb.z.y, 255.0f) | (qunorm(rgb.y.y, 255.0f) << 8) | (qunorm(rgb.x.y, 255.0f) << 16) | (255u << 24);
+            continue;
+        }
         #pragma unroll
         for (int k = 0; k < 2; k++) {
             const int gx = prm.dst_x0 + x0 + i + k;
@@ -589,6 +600,7 @@ static bool Fused1xVectorOk(const FusedPlan& p)
     const SrcDesc& S = p.src;
     if (S.layout != LAYOUT_BIPLANAR || S.chroma_mode != MPCVR_CHROMA_Bilinear || S.deint_blend || S.lsb_shift != 0) return false;
     if ((S.subsampling != 420 && S.subsampling != 422) || (S.bytes != 1 && S.bytes != 2)) return false;
+    if (p.color.transfer != TRANSFER_NONE) return false;          // matrix-only convert bodies (see fused1x_span)
     const int px = 16 / S.bytes;
     if (((uintptr_t)S.pl[0] & 15) || ((uintptr_t)S.pl[1] & 15) || S.pitch[0] <= 0 || S.pitch[1] <= 0 || (S.pitch[0] & 15) || (S.pitch[1] & 15)) return false;
     if ((S.rect_l % px) != 0) return false;

@@ -244,6 +244,9 @@ class VideoProcessor:
     def debug_set_gamma_table(self, enable):
         return self._L.mpcvr_debug_set_gamma_table(int(bool(enable)))
 
+    def debug_render_n(self, n):
+        self._check(self._L.mpcvr_debug_render_n(self._h, int(n)), "debug_render_n")
+
     def debug_set_fused1x_vector(self, enable):
         return self._L.mpcvr_debug_set_fused1x_vector(int(bool(enable)))
 
