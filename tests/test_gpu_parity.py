@@ -814,9 +814,9 @@ def test_convert_pass_two_lane_equals_scalar():
         vp.debug_set_convert_two_lane(1)
 
 
-@pytest.mark.parametrize("cfg", [("Lanczos3", 0, 133, 77), ("CatmullRom", 0, 96, 54), ("Lanczos3", 1, 133, 77), (None, 0, 50, 31), (None, 1, 23, 90)])
+@pytest.mark.parametrize("cfg", [("Lanczos3", 0, 133, 77), ("CatmullRom", 0, 96, 54), ("Lanczos3", 1, 133, 77), (None, 0, 50, 31), (None, 1, 23, 90), (None, 0, 31, 17)])
 def test_resize_four_outputs_per_thread_equals_one(cfg):
-    """k_resize4 against k_resize: interpolation (incl. the D3D11 duplicate tap), convolution, mixed axes, clipped rects, every surface format"""
+    """k_resize_p and k_resize4 against k_resize: interpolation (incl. the D3D11 duplicate tap), convolution, mixed axes, clipped rects, every surface format"""
     up, variant, dw, dh = cfg
     for tex, bb in ((O.TEXFMT_10INT, O.SURF_BGRA8), (O.TEXFMT_16FLOAT, O.SURF_RGBA16F), (O.TEXFMT_8INT, O.SURF_RGB10A2)):
         case = H.Case(O.CF["NV12"], 62, 34, dw, dh, H.EX_709, up=O.UPSCALE[up or "Mitchell"], down=O.DOWNSCALE["Lanczos"], variant=variant, tex=tex, backbuffer=bb,
@@ -825,14 +825,14 @@ def test_resize_four_outputs_per_thread_equals_one(cfg):
         buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
         outs = []
         try:
-            for on in (1, 0):
+            for mode in (1, 2, 0):                 # k_resize_p (compile-time taps / formats, two lines per thread), k_resize4, k_resize
                 vp = case.make_processor(device=0, path=PATH_MULTIPASS)
-                vp.debug_set_resize_four(on)
+                vp.debug_set_resize_four(mode)
                 vp.ProcessSample(data=buf, pitch=pitch)
                 outs.append(vp.ReadBackbuffer())
         finally:
             vp.debug_set_resize_four(1)
-        assert np.array_equal(outs[0], outs[1])
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
         assert H.compare(outs[0], H.run_oracle(case, planes, pitches), case.backbuffer) == (0, 0)
 
 

@@ -12,6 +12,7 @@ import videorenderer_b200 as V
 
 PATH_FUSED = 2
 MASKS = []
+WAITS = []
 
 
 def run(case, buf, pitch, strip, cfg=0):
@@ -83,6 +84,7 @@ def timing(cfgs, steps=300):
     ref_out = None
     res = {}
     runs = [("tile", 0, 0)] + [("strip%d" % c, 1, c) for c in cfgs]
+    runs += [("wait%d" % (16 << w), 1, (w << 12)) for w in WAITS]          # sleep-between-polls wait mode, ns
     runs += [("skip%x" % m, 1, (m << 8)) for m in MASKS if m < 16]      # role-balance experiment: bit set = that role (P, A, B, C) only handshakes
     for name, strip, cfg in runs:
         vp.debug_set_strip_kernel(strip, cfg)
@@ -100,7 +102,11 @@ def timing(cfgs, steps=300):
             step(0); out = vp.ReadBackbuffer()
             if name.startswith("skip"): same = "(partial work)"
             elif ref_out is None: ref_out = out; same = "ref"
-            else: same = "equal" if np.array_equal(out, ref_out) else "DIFFERENT (%d bytes)" % int((out != ref_out).sum())
+            elif np.array_equal(out, ref_out): same = "equal"
+            else:
+                d = np.abs(out.astype(np.int16) - ref_out.astype(np.int16))
+                same = "DIFFERENT: %d of %d bytes (%.4f %%), |diff| 1: %d, 2: %d, >2: %d, max %d" % (int((d != 0).sum()), d.size, 100.0 * float((d != 0).mean()),
+                                                                                             int((d == 1).sum()), int((d == 2).sum()), int((d > 2).sum()), int(d.max()))
             res[name] = us
             print("TIME %-8s %8.1f us/frame  %8.1f fps   output %s" % (name, us, 1e6 / us, same), flush=True)
         except Exception as e:
@@ -114,9 +120,11 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-time", action="store_true"); ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--cfgs", default="0,1,2,3")
+    ap.add_argument("--waits", default="", help="comma separated wait codes w (sleep 16<<w ns between polls)")
     ap.add_argument("--masks", default="", help="comma separated hex role-skip masks to time (bit0 P, bit1 A, bit2 B, bit3 C)")
     ap.add_argument("--one", action="store_true", help="run one small case on the strip kernel and print the watchdog record")
     a = ap.parse_args()
+    WAITS[:] = [int(x) for x in a.waits.split(",") if x]
     MASKS[:] = [int(x, 16) for x in a.masks.split(",") if x]
     if a.one:
         c = H.Case(O.CF["P010"], 150, 70, 300, 140, H.EX_2020_PQ, up=O.UPSCALE["Lanczos3"], name="one")

@@ -17,6 +17,7 @@
 // With a 2x ratio every output pair (2j, 2j+1) uses the source window [j+b0, j+b0+NT]; there are exactly two
 // weight vectors (phase t=3/4 and t=1/4), passed as kernel parameters.
 #include <cuda_runtime.h>
+#include <atomic>
 #include <algorithm>
 #include <mutex>
 #include <cuda_fp16.h>
@@ -818,8 +819,8 @@ static cudaError_t LaunchS(const FusedParams& prm, int spec, int conv, cudaStrea
 
 // builds g_gammaT / g_gammaD / g_gammaExc once per device; returns false (and leaves the plain kernel in charge) when the
 // scan finds the step function unusable
-static int g_useGammaTable = 1;                       // debug switch (mpcvr_debug_set_gamma_table)
-static int g_fused1xVector = 1;                       // debug switch: 0 keeps 1:1 plans on the one-pixel-per-thread kernel
+static std::atomic<int> g_useGammaTable{1};                       // debug switch (mpcvr_debug_set_gamma_table)
+static std::atomic<int> g_fused1xVector{1};                       // debug switch: 0 keeps 1:1 plans on the one-pixel-per-thread kernel
 void SetFused1xVector(int on) { g_fused1xVector = on; }
 void SetGammaTableEnabled(int on) { g_useGammaTable = on; }
 

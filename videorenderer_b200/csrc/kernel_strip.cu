@@ -1,5 +1,6 @@
 // kernel_strip.cu -- host side of the persistent strip kernel (kernel_strip.cuh): eligibility, TMA tensor maps, launch.
 #include <mutex>
+#include <atomic>
 #include <cstring>
 #include "kernel_strip.cuh"
 #include "kernel_strip.h"
@@ -43,8 +44,9 @@ int StripStatus(unsigned int out[8], int clear)
     return 0;
 }
 
-static int g_stripEnabled = 1, g_stripCfg = 0, g_stripSkip = 0;
-void SetStripKernel(int enabled, int cfg) { g_stripEnabled = enabled; g_stripCfg = cfg & 0xFF; g_stripSkip = (cfg >> 8) & 0xF; }   // cfg bits 8..11: role-skip mask (debug)
+// process-wide debug switches (tests flip them between frames; atomics so a concurrent instance reads a whole value)
+static std::atomic<int> g_stripEnabled{1}, g_stripCfg{0}, g_stripSkip{0}, g_stripWaitNs{0};
+void SetStripKernel(int enabled, int cfg) { g_stripEnabled = enabled; g_stripCfg = cfg & 0xFF; g_stripSkip = (cfg >> 8) & 0xF; g_stripWaitNs = ((cfg >> 12) & 0xF) ? (16 << ((cfg >> 12) & 0xF)) : 0; }   // cfg bits 8..11: role-skip mask (debug)
 
 bool StripEligible(const FusedPlan& p)
 {
@@ -90,10 +92,12 @@ static cudaError_t LaunchV(const StripParams& prm, int spec, int conv, int grid,
 {
     if (spec == SSPEC_10_BGRA8_DITHER && conv == SCONV_PQ_THR) {
         if constexpr (NT == 6 && DUP) {           // the headline variant carries the alternative warp-role splits (debug switch)
-            switch (g_stripCfg) {
+            switch (g_stripCfg.load()) {
             case 1:  return LaunchK<Cfg1, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             case 2:  return LaunchK<Cfg2, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             case 3:  return LaunchK<Cfg3, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
+            case 4:  return LaunchK<Cfg0, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR_RELAX1>(prm, grid, st);   // measurement only
+            case 5:  return LaunchK<Cfg0, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR_RELAX2>(prm, grid, st);   // measurement only
             default: break;
             }
         }
@@ -137,7 +141,7 @@ cudaError_t LaunchStrip2x(const FusedPlan& p, const float* gT, const float* gD, 
     prm.dst_x0 = p.ax.dst0; prm.dst_y0 = p.ay.dst0;
     prm.internal_fmt = p.internal_fmt; prm.final_pass = p.final_pass; prm.Q = p.Q;
     prm.strips = (prm.w1 + SW - 1) / SW; prm.nq = (prm.h1 + 3) / 4;
-    prm.dbg_skip = g_stripSkip;
+    prm.dbg_skip = g_stripSkip; prm.wait_ns = g_stripWaitNs;
 
     int spec = SSPEC_RUNTIME;
     if (p.internal_fmt == MPCVR_SURF_RGB10A2 && p.out.fmt == MPCVR_SURF_BGRA8 && p.final_pass && p.Q == 255.0f) spec = SSPEC_10_BGRA8_DITHER;

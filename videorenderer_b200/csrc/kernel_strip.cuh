@@ -13,9 +13,10 @@
 //   role A   the convert shader body on two pixels per thread in the packed-fp32 lanes, render-target rounding
 //            (Source/Shaders.cpp:819-923; m_TexConvertOutput) -> fp32 rows in shared memory.  Pure arithmetic: three 64-bit
 //            shared loads, three 64-bit shared stores, addresses linear in the item index.
-//   role C   X pass (8 outputs per item, fp16 rounding = m_TexResize) into a ring of rows, then Y pass + post-scale rounding +
-//            final pass (ordered dither) + packing, 64-bit coalesced stores to the back buffer
-//            (ResizeShaderPass :3103-3187, ps_interpolation_*.hlsl, FinalPass :3189-3233, ps_final_pass.hlsl)
+//   role B   X pass: 8 outputs per item from 10 converted values, two weight phases, fp16 rounding (= m_TexResize) into a
+//            32-row ring in shared memory   (ResizeShaderPass :3103-3187, ps_interpolation_*.hlsl)
+//   role C   Y pass from the ring + post-scale rounding + final pass (ordered dither) + packing, coalesced 64-bit stores to
+//            the back buffer   (FinalPass :3189-3233, ps_final_pass.hlsl)
 //
 // Arithmetic is the same device code as the tile kernel / multipass kernels (pixel_ops2.cuh), so the output is bit-identical.
 // CLAMP addressing of the resize taps: columns are clamped when the X pass reads the converted rows (edge strips only), rows
@@ -36,7 +37,8 @@ static __device__ const DitherTableF g_dither32_strip = MakeDitherTableF(0.00097
 
 enum { SCONV_PQ_THR = 0,      // PQ -> SDR, 10-bit internal format: gamma + UNORM10 write/read through the threshold table
        SCONV_PQ = 1,          // PQ -> SDR, any internal format
-       SCONV_ANY = 2 };       // any transfer (runtime switch), any internal format
+       SCONV_ANY = 2,         // any transfer (runtime switch), any internal format
+       SCONV_PQ_THR_RELAX1 = 3, SCONV_PQ_THR_RELAX2 = 4 };   // measurement only: SCONV_PQ_THR with a loosened float stage (pixel_ops2.cuh)
 enum { SSPEC_RUNTIME = 0, SSPEC_10_BGRA8_DITHER = 1, SSPEC_8_BGRA8 = 2,
        SSPEC_10_RGB8_DITHER = 3 };   // as 1, written as packed R,G,B bytes (MPCVR_SURF_RGB8); lane pairs exchange two bytes by warp shuffle
 
@@ -61,6 +63,7 @@ struct StripParams {
     int32_t     internal_fmt, final_pass;
     float       Q;
     int32_t     strips, nq;               // column strips, quads (4 convert rows) per strip
+    int32_t     wait_ns;                  // 0: mbarrier.try_wait with a suspend hint; else nanosleep this long between polls
     int32_t     dbg_skip;                 // debug (role-balance experiments): bit 0/1/2/3 = role P/A/B/C keeps its handshakes but skips its work
 };
 
@@ -89,12 +92,21 @@ __device__ __forceinline__ bool mbar_try_hint(uint32_t bar, uint32_t parity)
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"((unsigned)MPCVR_STRIP_WAIT_HINT_NS) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int it = -1)
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int it, uint32_t wns)
 {
     if (mbar_try(bar, parity)) return true;
-    #pragma unroll 1
-    for (int n = 0; n < (1 << 17); n++)
-        if (mbar_try_hint(bar, parity)) return true;
+    if (wns) {
+        // poll with a real sleep in between: a waiting warp then issues a handful of instructions per wns nanoseconds
+        #pragma unroll 1
+        for (int n = 0; n < (1 << 22); n++) {
+            asm volatile("nanosleep.u32 %0;" :: "r"(wns));
+            if (mbar_try(bar, parity)) return true;
+        }
+    } else {
+        #pragma unroll 1
+        for (int n = 0; n < (1 << 17); n++)
+            if (mbar_try_hint(bar, parity)) return true;
+    }
     if (atomicAdd(&g_stripStatus[0], 1u) == 0) {
         g_stripStatus[1] = (bar & 255u) >> 3; g_stripStatus[2] = parity; g_stripStatus[3] = (unsigned)it;
         g_stripStatus[4] = blockIdx.x; g_stripStatus[5] = threadIdx.x >> 5;
@@ -242,6 +254,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t wns = (uint32_t)prm.wait_ns;
     float* sT = reinterpret_cast<float*>(smem + C::oT);
     float* sD = reinterpret_cast<float*>(smem + C::oD);
     float* sDith = reinterpret_cast<float*>(smem + C::oDith);      // NEGATED dither values when SPEC == SSPEC_10_BGRA8_DITHER
@@ -255,7 +268,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
         for (int i = 0; i < 4; i++) { mbar_init(sbase + 8 * (B_XFULL + i), C::NB); mbar_init(sbase + 8 * (B_XDONE + i), C::NC); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (CONV == SCONV_PQ_THR) {
+    if (CONV == SCONV_PQ_THR || CONV >= SCONV_PQ_THR_RELAX1) {
         for (int i = threadIdx.x; i < kGammaN + 2; i += C::THREADS) sT[i] = prm.gT[i];
         for (int i = threadIdx.x; i < kGammaN + 1; i += C::THREADS) sD[i] = prm.gD[i];
     }
@@ -284,7 +297,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
                 while (iss.valid && it_iss < it + C::NRAW) {
                     if ((it_iss & 1) == team) {
                         const int slot = it_iss % C::NRAW;
-                        if (!mbar_wait(sbase + 8 * (B_RAWEMPTY + slot), ((it_iss / C::NRAW) & 1) ^ 1, it_iss)) break;
+                        if (!mbar_wait(sbase + 8 * (B_RAWEMPTY + slot), ((it_iss / C::NRAW) & 1) ^ 1, it_iss, wns)) break;
                         const uint32_t full = sbase + 8 * (B_RAWFULL + slot);
                         mbar_expect_tx(full, (uint32_t)(prm.luma_bytes + prm.chroma_bytes));
                         const int X0 = prm.rect_l + iss.s * C::SW + prm.b0, sy0 = prm.rect_t + iss.cy0();
@@ -305,8 +318,8 @@ k_strip2x(const __grid_constant__ StripParams prm)
             float2* pY = reinterpret_cast<float2*>(smem + C::oPrep + (pslot * 3 + 0) * C::szPlane);
             float2* pU = reinterpret_cast<float2*>(smem + C::oPrep + (pslot * 3 + 1) * C::szPlane);
             float2* pV = reinterpret_cast<float2*>(smem + C::oPrep + (pslot * 3 + 2) * C::szPlane);
-            if (!mbar_wait(sbase + 8 * (B_RAWFULL + slot), (it / C::NRAW) & 1, it)) return;
-            if (!mbar_wait(sbase + 8 * (B_PREPEMPTY + pslot), ((it / C::NS) & 1) ^ 1, it)) return;
+            if (!mbar_wait(sbase + 8 * (B_RAWFULL + slot), (it / C::NRAW) & 1, it, wns)) return;
+            if (!mbar_wait(sbase + 8 * (B_PREPEMPTY + pslot), ((it / C::NS) & 1) ^ 1, it, wns)) return;
             if (!(prm.dbg_skip & 1)) {
             // P0: luma codes -> floats (UNORM read)
             for (int k = tP; k < rows * C::PAIRS; k += TP) {
@@ -384,14 +397,16 @@ k_strip2x(const __grid_constant__ StripParams prm)
             float2* c0 = reinterpret_cast<float2*>(smem + C::oConv + (slot * 3 + 0) * C::szPlane);
             float2* c1 = reinterpret_cast<float2*>(smem + C::oConv + (slot * 3 + 1) * C::szPlane);
             float2* c2 = reinterpret_cast<float2*>(smem + C::oConv + (slot * 3 + 2) * C::szPlane);
-            if (!mbar_wait(sbase + 8 * (B_PREPFULL + slot), ph, it)) return;
-            if (!mbar_wait(sbase + 8 * (B_CONVEMPTY + slot), ph ^ 1, it)) return;
+            if (!mbar_wait(sbase + 8 * (B_PREPFULL + slot), ph, it, wns)) return;
+            if (!mbar_wait(sbase + 8 * (B_CONVEMPTY + slot), ph ^ 1, it, wns)) return;
             int k = tA - stream; if (k < 0) k += TA;
             if (prm.dbg_skip & 2) k = items;
             for (; k < items; k += TA) {
                 f3x2 yuv; yuv.x = pY[k]; yuv.y = pU[k]; yuv.z = pV[k];
-                if (CONV == SCONV_PQ_THR) {
-                    const f3x2 g = convert_color_pq2_pre_s(prm.color, ym2s, ym1s, yuv);      // saturated gamut-mapped linear light
+                if (CONV == SCONV_PQ_THR || CONV >= SCONV_PQ_THR_RELAX1) {
+                    const f3x2 g = CONV == SCONV_PQ_THR_RELAX1 ? convert_color_pq2_pre_relaxed<1>(prm.color, ym2s, ym1s, yuv)
+                                 : CONV == SCONV_PQ_THR_RELAX2 ? convert_color_pq2_pre_relaxed<2>(prm.color, ym2s, ym1s, yuv)
+                                 : convert_color_pq2_pre_s(prm.color, ym2s, ym1s, yuv);       // saturated gamut-mapped linear light
                     c0[k] = make_float2(gamma_q10_thr1(g.x.x, sT, sD, exc0), gamma_q10_thr1(g.x.y, sT, sD, exc0));
                     c1[k] = make_float2(gamma_q10_thr1(g.y.x, sT, sD, exc0), gamma_q10_thr1(g.y.y, sT, sD, exc0));
                     c2[k] = make_float2(gamma_q10_thr1(g.z.x, sT, sD, exc0), gamma_q10_thr1(g.z.y, sT, sD, exc0));
@@ -418,9 +433,9 @@ k_strip2x(const __grid_constant__ StripParams prm)
             if (gi.g == 0) it0 = it;
             const int slot = it % C::NS; const uint32_t ph = (it / C::NS) & 1;
             const int cx0 = gi.s * C::SW + prm.b0;                       // convert-surface column of window column 0
-            if (!mbar_wait(sbase + 8 * (B_CONVFULL + slot), ph, it)) return;
+            if (!mbar_wait(sbase + 8 * (B_CONVFULL + slot), ph, it, wns)) return;
             // ring slot it % 4 held the rows of group it - 4; their last readers are the quads completed by group it - 3
-            if (it >= 3 && !mbar_wait(sbase + 8 * (B_XDONE + ((it - 3) & 3)), ((it - 3) >> 2) & 1, it)) return;
+            if (it >= 3 && !mbar_wait(sbase + 8 * (B_XDONE + ((it - 3) & 3)), ((it - 3) >> 2) & 1, it, wns)) return;
             const int rows = gi.rows(), ring0 = gi.cy0() - gi.wyA + C::R * it0;
             const float* conv = reinterpret_cast<const float*>(smem + C::oConv + slot * 3 * C::szPlane);
             for (int cb = pair; cb < C::CB; cb += C::NB / 2) {
@@ -447,7 +462,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
 
         for (int it = 0; gi.valid; it++, gi.advance()) {
             if (gi.g == 0) { it0 = it; qnext = gi.qa; }
-            if (!mbar_wait(sbase + 8 * (B_XFULL + (it & 3)), (it >> 2) & 1, it)) return;
+            if (!mbar_wait(sbase + 8 * (B_XFULL + (it & 3)), (it >> 2) & 1, it, wns)) return;
             // ---- Y pass + rounding + final pass for the quads whose rows are now complete; item = (quad, column block)
             const int cyLast = gi.cy0() + gi.rows() - 1;
             for (; qnext < gi.qb && min(4 * qnext + 3 + prm.b0 + NT, prm.h1 - 1) <= cyLast; qnext++) {

@@ -3,6 +3,7 @@
 // reference's own surface formats.  This family handles every plan; the fused kernel
 // (kernel_fused.cu) covers the plans that matter for throughput.  sm_100a, -fmad=false.
 #include <cuda_runtime.h>
+#include <atomic>
 #include "kernels.h"
 #include "pixel_ops.cuh"
 #include "pixel_ops2.cuh"
@@ -142,6 +143,80 @@ k_resize4(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc 
         const int ox = axis == 0 ? T.dst0 + i : oj, oy = axis == 0 ? oj : T.dst0 + i;
         if (ox < 0 || oy < 0 || ox >= out.w || oy >= out.h) continue;
         surf_store(out, ox, oy, r);
+    }
+}
+
+// Same pass for upright draws with the tap count, both surface formats, the axis and the shader kind fixed at compile time:
+// one thread = one index of the filtered axis x TWO neighbouring lines of the other axis.  The two outputs share the tap
+// window, the clamps and the weights and ride in the two lanes of FFMA2; each still sees its taps in ascending k with the same
+// first-product / fma chain as k_resize, so the pass is bit-identical.  Y passes fetch the texel pair with one 64/128-bit load.
+template <int FMT> __device__ __forceinline__ f3 surf_load_f(const SurfDesc& s, int x, int y) { SurfDesc t = s; t.fmt = FMT; return surf_load(t, x, y); }
+template <int FMT> __device__ __forceinline__ void surf_store_f(const SurfDesc& s, int x, int y, f3 v) { SurfDesc t = s; t.fmt = FMT; surf_store(t, x, y, v); }
+template <int FMT> __device__ __forceinline__ f3 texel_decode(uint32_t lo, uint32_t hi)
+{
+    f3 r;
+    if (FMT == MPCVR_SURF_RGB10A2)    { r.x = unorm10(lo & 1023u); r.y = unorm10((lo >> 10) & 1023u); r.z = unorm10((lo >> 20) & 1023u); }
+    else if (FMT == MPCVR_SURF_BGRA8) { r.z = unorm8(lo & 255u); r.y = unorm8((lo >> 8) & 255u); r.x = unorm8((lo >> 16) & 255u); }
+    else { const __half2 a = *reinterpret_cast<const __half2*>(&lo), b = *reinterpret_cast<const __half2*>(&hi); r.x = __low2float(a); r.y = __high2float(a); r.z = __low2float(b); }
+    return r;
+}
+
+template <int NT, int INF, int OUTF, int AXIS, bool CONV>
+__global__ void __launch_bounds__(256)
+k_resize_p(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc out, const __grid_constant__ AxisTable T,
+           const int32_t* __restrict__ other_idx, const int other_dst0, const int other_dst_len)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i  = AXIS == 0 ? a : b;                  // index along the filtered axis
+    const int j0 = 2 * (AXIS == 0 ? b : a);            // first of the two lines of the other axis
+    if (i >= T.dst_len || j0 >= other_dst_len) return;
+    const bool two = j0 + 1 < other_dst_len;
+    const int lim = AXIS == 0 ? in.w : in.h, olim = AXIS == 0 ? in.h : in.w;
+    const int fA = clampi(__ldg(other_idx + j0), 0, olim - 1);
+    const int fB = two ? clampi(__ldg(other_idx + j0 + 1), 0, olim - 1) : fA;
+    constexpr int TEXEL = INF == MPCVR_SURF_RGBA16F ? 8 : 4;
+    const bool vec = AXIS == 1 && fB == fA + 1 && (fA & 1) == 0;          // the pair is one aligned 2-texel word of the row
+    const int base = __ldg(T.base + i);
+    const int nt = NT > 0 ? NT : T.ntaps;
+    const float* w = T.w + (size_t)i * nt;
+    const bool dup = T.dup_q1 != 0;
+    float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
+    #pragma unroll
+    for (int k = 0; k < (NT > 0 ? NT : nt); k++) {
+        int idx = base + k;
+        if (!CONV && dup && k == 1) idx = base;                          // ps_interpolation_lanczos3.hlsl:33-34
+        idx = clampi(idx, 0, lim - 1);
+        f3 pa, pb;
+        if (AXIS == 1) {
+            const uint8_t* row = (const uint8_t*)in.ptr + (size_t)idx * in.pitch;
+            if (vec) {
+                if (TEXEL == 8) { const uint4 v = __ldg((const uint4*)(row + (size_t)fA * 8)); pa = texel_decode<INF>(v.x, v.y); pb = texel_decode<INF>(v.z, v.w); }
+                else            { const uint2 v = __ldg((const uint2*)(row + (size_t)fA * 4)); pa = texel_decode<INF>(v.x, 0u); pb = texel_decode<INF>(v.y, 0u); }
+            } else { pa = surf_load_f<INF>(in, fA, idx); pb = surf_load_f<INF>(in, fB, idx); }
+        } else { pa = surf_load_f<INF>(in, idx, fA); pb = surf_load_f<INF>(in, idx, fB); }
+        const float wk = __ldg(w + k);
+        const float2 vx = make_float2(pa.x, pb.x), vy = make_float2(pa.y, pb.y), vz = make_float2(pa.z, pb.z);
+        if (k == 0 && !CONV) { ax = mul2(vx, wk); ay = mul2(vy, wk); az = mul2(vz, wk); }
+        else { ax = fma2(wk, vx, ax); ay = fma2(wk, vy, ay); az = fma2(wk, vz, az); }
+    }
+    f3 rA = {ax.x, ay.x, az.x}, rB = {ax.y, ay.y, az.y};
+    if (CONV) {                                                          // avg /= ww, ps_convolution.hlsl:47
+        const float ww = __ldg(T.wsum + i);
+        const bool wok = ww > 1e-10f && ww < 1e10f;
+        // correctly rounded either way: the residual-corrected reciprocal sequence when every intermediate stays a normal
+        // number (always, for pixel data), div.rn otherwise
+        auto dv = [&](float x) { const float ax = fabsf(x); return (wok && ax < 1e30f && (ax > 1e-30f || ax == 0.0f)) ? div_rn_safe(x, ww) : __fdiv_rn(x, ww); };
+        rA.x = dv(rA.x); rA.y = dv(rA.y); rA.z = dv(rA.z);
+        rB.x = dv(rB.x); rB.y = dv(rB.y); rB.z = dv(rB.z);
+    }
+    const int oi = T.dst0 + i, oj = other_dst0 + j0;
+    {
+        const int ox = AXIS == 0 ? oi : oj, oy = AXIS == 0 ? oj : oi;
+        if (ox >= 0 && oy >= 0 && ox < out.w && oy < out.h) surf_store_f<OUTF>(out, ox, oy, rA);
+    }
+    if (two) {
+        const int ox = AXIS == 0 ? oi : oj + 1, oy = AXIS == 0 ? oj + 1 : oi;
+        if (ox >= 0 && oy >= 0 && ox < out.w && oy < out.h) surf_store_f<OUTF>(out, ox, oy, rB);
     }
 }
 
@@ -440,9 +515,9 @@ __global__ void k_math_probe(int op, const float* __restrict__ x, const float* _
 // ---------------------------------------------------------------------------------------------
 static inline dim3 Grid2D(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
 
-static int g_resizeFour = 1;              // debug switch: 0 = one output per thread (k_resize)
+static std::atomic<int> g_resizeFour{1};             // debug switch: 0 = k_resize (one output per thread), 2 = k_resize4, 1 = k_resize_p where it applies
 void SetResizeFour(int on) { g_resizeFour = on; }
-static int g_convertTwoLane = 1;          // debug switch: 0 = one pixel per thread (scalar shader body)
+static std::atomic<int> g_convertTwoLane{1};         // debug switch: 0 = one pixel per thread (scalar shader body)
 void SetConvertTwoLane(int on) { g_convertTwoLane = on; }
 
 cudaError_t LaunchConvertPass(const SrcDesc& src, const ColorParams& color, const SurfDesc& out, float4* dbg_f32, cudaStream_t st,
@@ -457,12 +532,46 @@ cudaError_t LaunchConvertPass(const SrcDesc& src, const ColorParams& color, cons
     return cudaGetLastError();
 }
 
+// picks the compile-time variant of k_resize_p for the common (taps, formats) combinations; false = not covered
+template <int NT, bool CONV>
+static bool LaunchResizeP(const SurfDesc& in, const SurfDesc& out, const AxisTable& T, int axis, const int32_t* other_idx, int other_dst0, int other_dst_len, cudaStream_t st)
+{
+    const dim3 b(32, 8);
+    const int w = axis == 0 ? T.dst_len : (other_dst_len + 1) / 2, h = axis == 0 ? (other_dst_len + 1) / 2 : T.dst_len;
+    const dim3 g = Grid2D(w, h, b);
+#define MPCVR_RP(INF, OUTF) \
+    if (in.fmt == INF && out.fmt == OUTF) { \
+        if (axis == 0) k_resize_p<NT, INF, OUTF, 0, CONV><<<g, b, 0, st>>>(in, out, T, other_idx, other_dst0, other_dst_len); \
+        else           k_resize_p<NT, INF, OUTF, 1, CONV><<<g, b, 0, st>>>(in, out, T, other_idx, other_dst0, other_dst_len); \
+        return true; }
+    // first pass: internal format -> m_TexResize (RGBA16F); second pass: m_TexResize -> internal format / back buffer
+    MPCVR_RP(MPCVR_SURF_RGBA16F, MPCVR_SURF_RGBA16F)
+    MPCVR_RP(MPCVR_SURF_RGB10A2, MPCVR_SURF_RGBA16F)
+    MPCVR_RP(MPCVR_SURF_BGRA8,   MPCVR_SURF_RGBA16F)
+    MPCVR_RP(MPCVR_SURF_RGBA16F, MPCVR_SURF_RGB10A2)
+    MPCVR_RP(MPCVR_SURF_RGBA16F, MPCVR_SURF_BGRA8)
+#undef MPCVR_RP
+    return false;
+}
+
 cudaError_t LaunchResizePass(const SurfDesc& in, const SurfDesc& out, const AxisTable& table, int axis,
                              const int32_t* other_idx, int other_dst0, int other_dst_len, cudaStream_t st, int in_axis)
 {
     const dim3 b(32, 8);
     const int w = axis == 0 ? table.dst_len : other_dst_len, h = axis == 0 ? other_dst_len : table.dst_len;
-    if ((in_axis < 0 || in_axis == axis) && g_resizeFour) {               // upright draws: four outputs per thread
+    const int mode = g_resizeFour;                                         // 1: default, 2: k_resize4 everywhere, 0: k_resize everywhere
+    if ((in_axis < 0 || in_axis == axis) && mode == 1 && (table.kind == SCALER_INTERP || table.kind == SCALER_CONV)) {
+        bool done = false;
+        if (table.kind == SCALER_INTERP) {
+            if (table.ntaps == 4)      done = LaunchResizeP<4, false>(in, out, table, axis, other_idx, other_dst0, other_dst_len, st);
+            else if (table.ntaps == 6) done = LaunchResizeP<6, false>(in, out, table, axis, other_idx, other_dst0, other_dst_len, st);
+        } else {
+            if (table.ntaps == 9)      done = LaunchResizeP<9, true>(in, out, table, axis, other_idx, other_dst0, other_dst_len, st);   // 2:1 reductions with the 2-lobe filters
+            else if (table.ntaps <= 32) done = LaunchResizeP<0, true>(in, out, table, axis, other_idx, other_dst0, other_dst_len, st);
+        }
+        if (done) return cudaGetLastError();
+    }
+    if ((in_axis < 0 || in_axis == axis) && mode) {                       // upright draws: four outputs per thread
         const int w4 = axis == 0 ? (w + 3) / 4 : w, h4 = axis == 0 ? h : (h + 3) / 4;
         k_resize4<<<Grid2D(w4, h4, b), b, 0, st>>>(in, out, table, axis, other_idx, other_dst0, other_dst_len);
         return cudaGetLastError();

@@ -143,6 +143,48 @@ __device__ __forceinline__ f3x2 convert_color_pq2_pre_s(const ColorParams& P, fl
     return g;
 }
 
+// ---- measurement only (tools/strip_check.py --relaxed): the same stage with the float contract loosened -----------------------
+// RELAX 1: both divisions as x * rcp.approx(y) (about 1.5 ULP), polynomials kept.  RELAX 2: also both pows on the MUFU unit
+// (lg2.approx / ex2.approx, tens of ULP after the 78.8 exponent).  Never dispatched by the product; see DESIGN.md "relaxed float stage".
+template <int RELAX>
+__device__ __forceinline__ float2 pq_channel_to_hable2_relaxed(const ColorParams& P, float ym2s, float ym1s, float2 csat)
+{
+    auto fdiv = [](float2 x, float2 y) { float2 r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(y.x)); asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(y.y)); return mul2(x, r); };
+    auto fpow = [](float2 x, float y) { float2 l, e; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l.x) : "f"(x.x)); asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l.y) : "f"(x.y));
+                                        l = mul2(l, y); asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(l.x)); asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(l.y)); return e; };
+    float2 z, v;
+    const float2 a   = RELAX >= 2 ? fpow(csat, P.inv_m2) : ex2p_core2(lg2s_2(csat), ym2s, z);
+    const float2 num = max2(add2(a, -ST2084_C1), 0.0f);
+    const float2 den = fma2(-ST2084_C3, a, ST2084_C2);
+    const float2 q   = fdiv(num, den);
+    if (RELAX >= 2) v = fpow(q, P.inv_m1);
+    else { const float2 t = ex2p_core2(lg2s_2(q), ym1s, z); const float lo = 12582912.0f - 125.0f; v = make_float2(z.x < lo ? 0.0f : t.x, z.y < lo ? 0.0f : t.y); }
+    const float2 lin = mul2(v, P.lum_scale);
+    const float2 hn  = fma2(lin, fma2(0.15f, lin, P.hable_cb), P.hable_de);
+    const float2 hd  = fma2(lin, fma2(0.15f, lin, 0.50f), P.hable_df);
+    return mul2(add2(fdiv(hn, hd), -P.hable_ef), P.hable_rdiv);
+}
+template <int RELAX>
+__device__ __forceinline__ f3x2 convert_color_pq2_pre_relaxed(const ColorParams& P, float ym2s, float ym1s, const f3x2& yuv)
+{
+    f3x2 h;
+    #pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float2 t = dp3_2(P.cm[i], yuv);
+        const float2 c = make_float2(add_sat(t.x, P.cc[i]), add_sat(t.y, P.cc[i]));
+        const float2 r = pq_channel_to_hable2_relaxed<RELAX>(P, ym2s, ym1s, c);
+        if (i == 0) h.x = r; else if (i == 1) h.y = r; else h.z = r;
+    }
+    f3x2 g;
+    #pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float2 t = fma2(P.gamut[i][1], h.y, mul2(h.x, P.gamut[i][0]));
+        const float2 r = make_float2(fma_sat1(P.gamut[i][2], h.z.x, t.x), fma_sat1(P.gamut[i][2], h.z.y, t.y));
+        if (i == 0) g.x = r; else if (i == 1) g.y = r; else g.z = r;
+    }
+    return g;
+}
+
 // gamma_q10_thr with a single exception float
 __device__ __forceinline__ float gamma_q10_thr1(float x, const float* __restrict__ sT, const float* __restrict__ sD, uint32_t exc0)
 {

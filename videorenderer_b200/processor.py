@@ -236,7 +236,7 @@ class VideoProcessor:
         return int(self._L.mpcvr_debug_verify_gamma_table(self._h))
 
     def debug_set_resize_four(self, enable):
-        return self._L.mpcvr_debug_set_resize_four(int(bool(enable)))
+        return self._L.mpcvr_debug_set_resize_four(int(enable))
 
     def debug_set_convert_two_lane(self, enable):
         return self._L.mpcvr_debug_set_convert_two_lane(int(bool(enable)))
