@@ -814,6 +814,30 @@ def test_convert_pass_two_lane_equals_scalar():
         vp.debug_set_convert_two_lane(1)
 
 
+@pytest.mark.parametrize("cfname,w,h,rect", [("NV12", 150, 38, None), ("P010", 150, 38, None), ("P016", 136, 22, (16, 2, 129, 21)), ("P210", 72, 20, None), ("NV12", 96, 18, (32, 0, 96, 18))])
+def test_convert_pass_span_kernel_equals_two_lane_and_scalar(cfname, w, h, rect):
+    """k_convert_bp (128-bit source spans staged through shared memory, then the two-lane body) against k_convert2 and k_convert:
+    ragged last spans, cropped rects on span boundaries, every chroma siting, the three internal formats, transfer chains"""
+    exs = [H.EX_709, H.EX_2020_PQ, H.EX_2020_SDR, O.exfmt(chroma=1, range_=2, matrix=1, prim=2, trc=5), O.exfmt(chroma=3, range_=1, matrix=2, prim=2, trc=5)]
+    try:
+        for i, ex in enumerate(exs):
+            for tex, bb in ((O.TEXFMT_10INT, O.SURF_BGRA8), (O.TEXFMT_16FLOAT, O.SURF_RGBA16F), (O.TEXFMT_8INT, O.SURF_RGB10A2)):
+                dw, dh = (rect[2] - rect[0], rect[3] - rect[1]) if rect else (w, h)
+                case = H.Case(O.CF[cfname], w, h, dw * 3 // 2, dh * 3 // 2, ex, up=O.UPSCALE["CatmullRom"], src_rect=rect, tex=tex, backbuffer=bb, name="span%d" % i)
+                codes = H.make_codes(case.cf, case.w, case.h, "fullnoise", 400 + i)
+                buf, pitch, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+                outs = []
+                for mode in (1, 2, 0):
+                    vp = case.make_processor(device=0, path=PATH_MULTIPASS)
+                    vp.debug_set_convert_two_lane(mode)
+                    vp.ProcessSample(data=buf, pitch=pitch)
+                    outs.append(vp.ReadBackbuffer())
+                assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]), (i, tex)
+                assert H.compare(outs[0], H.run_oracle(case, planes, pitches), case.backbuffer) == (0, 0)
+    finally:
+        vp.debug_set_convert_two_lane(1)
+
+
 @pytest.mark.parametrize("cfg", [("Lanczos3", 0, 133, 77), ("CatmullRom", 0, 96, 54), ("Lanczos3", 1, 133, 77), (None, 0, 50, 31), (None, 1, 23, 90), (None, 0, 31, 17)])
 def test_resize_four_outputs_per_thread_equals_one(cfg):
     """k_resize_p and k_resize4 against k_resize: interpolation (incl. the D3D11 duplicate tap), convolution, mixed axes, clipped rects, every surface format"""

@@ -100,7 +100,7 @@ int32_t mpcvr_get_last_frame_kernels(mpcvr* h, int32_t* n) { VP_OR(MPCVR_E_POINT
 // ---- debug surface
 int64_t mpcvr_debug_verify_gamma_table(mpcvr* h) { VP_OR(-2); return vp.DebugVerifyGammaTable(); }
 int32_t mpcvr_debug_set_resize_four(int32_t enable) { b200vr::SetResizeFour(enable); return MPCVR_S_OK; }
-int32_t mpcvr_debug_set_convert_two_lane(int32_t enable) { b200vr::SetConvertTwoLane(enable != 0); return MPCVR_S_OK; }
+int32_t mpcvr_debug_set_convert_two_lane(int32_t enable) { b200vr::SetConvertTwoLane(enable); return MPCVR_S_OK; }
 int32_t mpcvr_debug_set_gamma_table(int32_t enable) { b200vr::SetGammaTableEnabled(enable != 0); return MPCVR_S_OK; }
 int32_t mpcvr_debug_set_fused1x_vector(int32_t enable) { b200vr::SetFused1xVector(enable != 0); return MPCVR_S_OK; }
 int32_t mpcvr_debug_set_strip_kernel(int32_t enable, int32_t cfg) { b200vr::SetStripKernel(enable != 0, cfg); return MPCVR_S_OK; }

@@ -21,7 +21,7 @@ cudaError_t LaunchCopyPass(const SurfDesc& in, const SurfDesc& out, const int32_
 cudaError_t LaunchFinalPass(const SurfDesc& in, const SurfDesc& out, int x0, int y0, int x1, int y1, float Q, cudaStream_t st);
 long long VerifyGammaTable(cudaStream_t st);   // mismatches of table vs direct over every float of [0,1]; -1 = table unusable
 void SetResizeFour(int mode);        // debug: resize passes 0 = k_resize (one output per thread), 2 = k_resize4, 1 = default (k_resize_p where it applies)
-void SetConvertTwoLane(int on);      // debug: 0 = multipass ConvertColorPass with the scalar shader body (k_convert) instead of k_convert2
+void SetConvertTwoLane(int mode);    // debug: ConvertColorPass 0 = scalar shader body (k_convert), 2 = k_convert2, 1 = default (k_convert_bp where it applies)
 void SetGammaTableEnabled(int on);
 void SetFused1xVector(int on);      // debug: 0 = 1:1 plans one pixel per thread (k_fused1x) instead of the 128-bit span kernel (k_fused1x_bp)   // debug: 0 = the 2x PQ kernel evaluates the final pow directly instead of the threshold table
 // path-B correction shader (m_pPSCorrection) over rect, Source/DX11VideoProcessor.cpp:3354-3357

@@ -52,6 +52,138 @@ k_convert2(const __grid_constant__ SrcDesc S, const __grid_constant__ ColorParam
     }
 }
 
+// bilinear chroma sample of fetch_planar at the PX luma positions of a span whose texels [t0 - 1, t0 + PX/2] sit in T[row][.]:
+// qx = 2 (sx0 + i) + OX with 2 sx0 = 4 t0, so texel (qx >> 2) is T[.][((2 i + OX) >> 2) + 1]; OX is a template value to keep T in registers
+template <int PX, int OX>
+__device__ __forceinline__ void span_chroma(const float2 (&T)[2][PX / 2 + 2], float fy, float (&dU)[PX], float (&dV)[PX])
+{
+    #pragma unroll
+    for (int i = 0; i < PX; i++) {
+        const int q = 2 * i + OX;
+        const int j = (q >> 2) + 1;
+        const float fx = (float)(q & 3) * 0.25f;
+        const float2 c00 = T[0][j], c10 = T[0][j + 1], c01 = T[1][j], c11 = T[1][j + 1];
+        dU[i] = lerp_mad(lerp_mad(c00.x, c10.x, fx), lerp_mad(c01.x, c11.x, fx), fy);
+        dV[i] = lerp_mad(lerp_mad(c00.y, c10.y, fx), lerp_mad(c01.y, c11.y, fx), fy);
+    }
+}
+
+// ConvertColorPass for bi-planar sources (NV12 / P010 / P016 / P210 / P216) with bilinear chroma, in two phases per CTA so that the
+// source is read with 128-bit loads and the shader body still exists once in the code:
+//   phase 1  each thread fetches a span of 16 / BYTES pixels of one row: one 128-bit luma load, one 128-bit load per chroma row plus the
+//            two neighbour texels, UNORM reads, the bilinear sample of fetch_planar at every luma position -> Y, U, V floats in shared memory
+//   phase 2  the CTA walks its pixels two at a time through convert_color2 (any transfer chain) and writes texel pairs with 64/128-bit stores
+// Same device functions and the same operation order per pixel as k_convert2, so the surface is bit-identical.
+template <int BYTES>
+__global__ void __launch_bounds__(128)
+k_convert_bp(const __grid_constant__ SrcDesc S, const __grid_constant__ ColorParams P, const __grid_constant__ SurfDesc out)
+{
+    constexpr int PX = 16 / BYTES;                               // pixels per span: 16 (8-bit) or 8 (16-bit)
+    constexpr int TW = 32 * PX, TH = 4;                          // CTA tile
+    __shared__ __align__(16) float2 sY[TH][TW / 2], sU[TH][TW / 2], sV[TH][TW / 2];
+    const int bx0 = blockIdx.x * TW, by0 = blockIdx.y * TH;
+    {
+        const int x0 = bx0 + threadIdx.x * PX, y = by0 + threadIdx.y;
+        if (x0 < out.w && y < out.h) {
+            const int sy = S.rect_t + y, sx0 = S.rect_l + x0;
+            float* dY = reinterpret_cast<float*>(&sY[threadIdx.y][0]) + threadIdx.x * PX;
+            float* dU = reinterpret_cast<float*>(&sU[threadIdx.y][0]) + threadIdx.x * PX;
+            float* dV = reinterpret_cast<float*>(&sV[threadIdx.y][0]) + threadIdx.x * PX;
+            if (x0 + PX > out.w) {                               // ragged last span: per-pixel fetch
+                for (int x = x0; x < out.w; x++) { const f3 t = fetch_yuv(S, S.rect_l + x, sy); dY[x - x0] = t.x; dU[x - x0] = t.y; dV[x - x0] = t.z; }
+            } else {
+                int ox, oy, my;
+                if (S.subsampling == 420) {
+                    my = 2;
+                    if (S.siting == ChromaSub_Cosited)    { ox = 0;  oy = 0;  }
+                    else if (S.siting == ChromaSub_MPEG1) { ox = -1; oy = -1; }
+                    else                                  { ox = 0;  oy = -1; }
+                } else { my = 4; ox = 0; oy = 0; }
+                float vY[PX], vU[PX], vV[PX];
+                {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(S.pl[0] + (ptrdiff_t)sy * S.pitch[0] + (size_t)sx0 * BYTES));
+                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+                    #pragma unroll
+                    for (int i = 0; i < PX; i++)
+                        vY[i] = BYTES == 1 ? unorm8((w[i >> 2] >> (8 * (i & 3))) & 255u) : unorm16((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+                }
+                // chroma texel columns [t0 - 1, t0 + PX/2] of the two rows the bilinear sample spans (sampler CLAMP on indices)
+                constexpr int NTX = PX / 2 + 2;
+                const int t0 = sx0 >> 1;
+                const int qy = my * sy + oy;
+                const float fy = (float)(qy & 3) * 0.25f;
+                const int r0 = clampi(qy >> 2, 0, S.ch - 1), r1 = clampi((qy >> 2) + 1, 0, S.ch - 1);
+                float2 T[2][NTX];
+                #pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const uint8_t* row = S.pl[1] + (ptrdiff_t)(rr ? r1 : r0) * S.pitch[1];
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + (size_t)t0 * 2 * BYTES));
+                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+                    #pragma unroll
+                    for (int i = 0; i < PX / 2; i++) {
+                        if (BYTES == 1) { const uint32_t c = (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu; T[rr][1 + i] = make_float2(unorm8(c & 255u), unorm8(c >> 8)); }
+                        else            { const uint32_t c = w[i]; T[rr][1 + i] = make_float2(unorm16(c & 0xFFFFu), unorm16(c >> 16)); }
+                    }
+                    const int tl = clampi(t0 - 1, 0, S.cw - 1), tr = clampi(t0 + PX / 2, 0, S.cw - 1);
+                    if (BYTES == 1) {
+                        const uint32_t a = __ldg(reinterpret_cast<const uint16_t*>(row) + tl), b = __ldg(reinterpret_cast<const uint16_t*>(row) + tr);
+                        T[rr][0] = make_float2(unorm8(a & 255u), unorm8(a >> 8)); T[rr][NTX - 1] = make_float2(unorm8(b & 255u), unorm8(b >> 8));
+                    } else {
+                        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(row) + tl), b = __ldg(reinterpret_cast<const uint32_t*>(row) + tr);
+                        T[rr][0] = make_float2(unorm16(a & 0xFFFFu), unorm16(a >> 16)); T[rr][NTX - 1] = make_float2(unorm16(b & 0xFFFFu), unorm16(b >> 16));
+                    }
+                }
+                if (ox == 0) span_chroma<PX, 0>(T, fy, vU, vV); else span_chroma<PX, -1>(T, fy, vU, vV);
+                #pragma unroll
+                for (int i = 0; i < PX; i += 4) {                // 128-bit shared stores
+                    reinterpret_cast<float4*>(dY)[i >> 2] = make_float4(vY[i], vY[i + 1], vY[i + 2], vY[i + 3]);
+                    reinterpret_cast<float4*>(dU)[i >> 2] = make_float4(vU[i], vU[i + 1], vU[i + 2], vU[i + 3]);
+                    reinterpret_cast<float4*>(dV)[i >> 2] = make_float4(vV[i], vV[i + 1], vV[i + 2], vV[i + 3]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    #pragma unroll 1
+    for (int p = tid; p < TH * (TW / 2); p += 128) {
+        const int r = p / (TW / 2), c = p - r * (TW / 2);
+        const int x = bx0 + 2 * c, y = by0 + r;
+        if (x >= out.w || y >= out.h) continue;
+        f3x2 yuv; yuv.x = sY[r][c]; yuv.y = sU[r][c]; yuv.z = sV[r][c];
+        const f3x2 rgb = convert_color2(P, yuv);
+        uint8_t* row = (uint8_t*)out.ptr + (size_t)y * out.pitch;
+        if (x + 1 < out.w) {
+            if (out.fmt == MPCVR_SURF_RGBA16F) {
+                const __half2 a0 = __floats2half2_rn(rgb.x.x, rgb.y.x), b0 = __floats2half2_rn(rgb.z.x, 1.0f), a1 = __floats2half2_rn(rgb.x.y, rgb.y.y), b1 = __floats2half2_rn(rgb.z.y, 1.0f);
+                reinterpret_cast<uint4*>(row)[x >> 1] = make_uint4(*reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&b0),
+                                                                   *reinterpret_cast<const uint32_t*>(&a1), *reinterpret_cast<const uint32_t*>(&b1));
+            } else if (out.fmt == MPCVR_SURF_RGB10A2) {
+                reinterpret_cast<uint2*>(row)[x >> 1] = make_uint2(qunorm(rgb.x.x, 1023.0f) | (qunorm(rgb.y.x, 1023.0f) << 10) | (qunorm(rgb.z.x, 1023.0f) << 20) | (3u << 30),
+                                                                   qunorm(rgb.x.y, 1023.0f) | (qunorm(rgb.y.y, 1023.0f) << 10) | (qunorm(rgb.z.y, 1023.0f) << 20) | (3u << 30));
+            } else {                                             // B8G8R8A8
+                reinterpret_cast<uint2*>(row)[x >> 1] = make_uint2(qunorm(rgb.z.x, 255.0f) | (qunorm(rgb.y.x, 255.0f) << 8) | (qunorm(rgb.x.x, 255.0f) << 16) | (255u << 24),
+                                                                   qunorm(rgb.z.y, 255.0f) | (qunorm(rgb.y.y, 255.0f) << 8) | (qunorm(rgb.x.y, 255.0f) << 16) | (255u << 24));
+            }
+        } else {
+            f3 r0; r0.x = rgb.x.x; r0.y = rgb.y.x; r0.z = rgb.z.x;
+            surf_store(out, x, y, r0);
+        }
+    }
+}
+
+// 128-bit path of the convert pass: bi-planar, bilinear chroma, planes / pitches / rect origin 16-byte aligned, an 8-, 10- or fp16 target
+static bool ConvertSpanOk(const SrcDesc& S, const SurfDesc& out)
+{
+    if (S.layout != LAYOUT_BIPLANAR || S.chroma_mode != MPCVR_CHROMA_Bilinear || S.deint_blend || S.lsb_shift != 0) return false;
+    if ((S.subsampling != 420 && S.subsampling != 422) || (S.bytes != 1 && S.bytes != 2)) return false;
+    if (((uintptr_t)S.pl[0] & 15) || ((uintptr_t)S.pl[1] & 15) || S.pitch[0] <= 0 || S.pitch[1] <= 0 || (S.pitch[0] & 15) || (S.pitch[1] & 15)) return false;
+    if ((S.rect_l % (16 / S.bytes)) != 0) return false;
+    if (out.fmt != MPCVR_SURF_BGRA8 && out.fmt != MPCVR_SURF_RGB10A2 && out.fmt != MPCVR_SURF_RGBA16F) return false;
+    if (((uintptr_t)out.ptr & 15) || (out.pitch & 15)) return false;
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // TextureResizeShader along one axis: one thread per output pixel, taps from the host table
 // ---------------------------------------------------------------------------------------------
@@ -517,13 +649,19 @@ static inline dim3 Grid2D(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.
 
 static std::atomic<int> g_resizeFour{1};             // debug switch: 0 = k_resize (one output per thread), 2 = k_resize4, 1 = k_resize_p where it applies
 void SetResizeFour(int on) { g_resizeFour = on; }
-static std::atomic<int> g_convertTwoLane{1};         // debug switch: 0 = one pixel per thread (scalar shader body)
+static std::atomic<int> g_convertTwoLane{1};         // debug switch: 0 = one pixel per thread (scalar shader body), 2 = k_convert2 everywhere, 1 = k_convert_bp where it applies
 void SetConvertTwoLane(int on) { g_convertTwoLane = on; }
 
 cudaError_t LaunchConvertPass(const SrcDesc& src, const ColorParams& color, const SurfDesc& out, float4* dbg_f32, cudaStream_t st,
                               const DoviParams* dovi_dev)
 {
     const dim3 b(32, 8);
+    if (!dovi_dev && !dbg_f32 && g_convertTwoLane == 1 && ConvertSpanOk(src, out)) {      // 128-bit spans + two-lane body
+        const dim3 bs(32, 4);
+        if (src.bytes == 1) k_convert_bp<1><<<dim3((out.w + 511) / 512, (out.h + 3) / 4), bs, 0, st>>>(src, color, out);
+        else                k_convert_bp<2><<<dim3((out.w + 255) / 256, (out.h + 3) / 4), bs, 0, st>>>(src, color, out);
+        return cudaGetLastError();
+    }
     if (!dovi_dev && g_convertTwoLane) {
         k_convert2<<<Grid2D((out.w + 1) / 2, out.h, b), b, 0, st>>>(src, color, out, dbg_f32);
         return cudaGetLastError();

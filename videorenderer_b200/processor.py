@@ -239,7 +239,7 @@ class VideoProcessor:
         return self._L.mpcvr_debug_set_resize_four(int(enable))
 
     def debug_set_convert_two_lane(self, enable):
-        return self._L.mpcvr_debug_set_convert_two_lane(int(bool(enable)))
+        return self._L.mpcvr_debug_set_convert_two_lane(int(enable))
 
     def debug_set_gamma_table(self, enable):
         return self._L.mpcvr_debug_set_gamma_table(int(bool(enable)))
