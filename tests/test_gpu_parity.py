@@ -814,7 +814,8 @@ def test_convert_pass_two_lane_equals_scalar():
         vp.debug_set_convert_two_lane(1)
 
 
-@pytest.mark.parametrize("cfname,w,h,rect", [("NV12", 150, 38, None), ("P010", 150, 38, None), ("P016", 136, 22, (16, 2, 129, 21)), ("P210", 72, 20, None), ("NV12", 96, 18, (32, 0, 96, 18))])
+@pytest.mark.parametrize("cfname,w,h,rect", [("NV12", 150, 38, None), ("P010", 150, 38, None), ("P016", 136, 22, (16, 2, 129, 21)), ("P210", 72, 20, None), ("NV12", 96, 18, (32, 0, 96, 18)),
+                                             ("YUY2", 150, 22, None), ("UYVY", 136, 20, (8, 2, 129, 19)), ("YUY2", 64, 10, (56, 0, 64, 10))])
 def test_convert_pass_span_kernel_equals_two_lane_and_scalar(cfname, w, h, rect):
     """k_convert_bp (128-bit source spans staged through shared memory, then the two-lane body) against k_convert2 and k_convert:
     ragged last spans, cropped rects on span boundaries, every chroma siting, the three internal formats, transfer chains"""

@@ -12,7 +12,7 @@
 
 namespace b200vr {
 
-__device__ const uint16_t g_dither32[1024] = { MPCVR_DITHER32_VALUES };
+__device__ __align__(16) const uint16_t g_dither32[1024] = { MPCVR_DITHER32_VALUES };
 
 // ---------------------------------------------------------------------------------------------
 // ConvertColorPass: one thread per pixel of m_TexConvertOutput (= m_srcRect size)
@@ -68,17 +68,17 @@ __device__ __forceinline__ void span_chroma(const float2 (&T)[2][PX / 2 + 2], fl
     }
 }
 
-// ConvertColorPass for bi-planar sources (NV12 / P010 / P016 / P210 / P216) with bilinear chroma, in two phases per CTA so that the
+// ConvertColorPass for bi-planar sources (NV12 / P010 / P016 / P210 / P216) with bilinear chroma and for YUY2 / UYVY, in two phases per CTA so that the
 // source is read with 128-bit loads and the shader body still exists once in the code:
 //   phase 1  each thread fetches a span of 16 / BYTES pixels of one row: one 128-bit luma load, one 128-bit load per chroma row plus the
 //            two neighbour texels, UNORM reads, the bilinear sample of fetch_planar at every luma position -> Y, U, V floats in shared memory
 //   phase 2  the CTA walks its pixels two at a time through convert_color2 (any transfer chain) and writes texel pairs with 64/128-bit stores
 // Same device functions and the same operation order per pixel as k_convert2, so the surface is bit-identical.
-template <int BYTES>
+template <int BYTES, bool PACKED>
 __global__ void __launch_bounds__(128)
 k_convert_bp(const __grid_constant__ SrcDesc S, const __grid_constant__ ColorParams P, const __grid_constant__ SurfDesc out)
 {
-    constexpr int PX = 16 / BYTES;                               // pixels per span: 16 (8-bit) or 8 (16-bit)
+    constexpr int PX = PACKED ? 8 : 16 / BYTES;                  // pixels per span: 16 (8-bit planes), 8 (16-bit planes, YUY2 / UYVY words)
     constexpr int TW = 32 * PX, TH = 4;                          // CTA tile
     __shared__ __align__(16) float2 sY[TH][TW / 2], sU[TH][TW / 2], sV[TH][TW / 2];
     const int bx0 = blockIdx.x * TW, by0 = blockIdx.y * TH;
@@ -91,6 +91,33 @@ k_convert_bp(const __grid_constant__ SrcDesc S, const __grid_constant__ ColorPar
             float* dV = reinterpret_cast<float*>(&sV[threadIdx.y][0]) + threadIdx.x * PX;
             if (x0 + PX > out.w) {                               // ragged last span: per-pixel fetch
                 for (int x = x0; x < out.w; x++) { const f3 t = fetch_yuv(S, S.rect_l + x, sy); dY[x - x0] = t.x; dU[x - x0] = t.y; dV[x - x0] = t.z; }
+            } else if (PACKED) {
+                // YUY2 / UYVY (fetch_packed422): four macropixels in one 128-bit load plus the next one (CLAMP) for the last odd pixel;
+                // even pixels take their macropixel's chroma, odd pixels the mean of this and the next macropixel
+                const uint8_t* row = S.pl[0] + (ptrdiff_t)sy * S.pitch[0];
+                const int mx0 = sx0 >> 1, mw = S.W >> 1;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + (size_t)mx0 * 4));
+                const uint32_t w[5] = { v.x, v.y, v.z, v.w, __ldg(reinterpret_cast<const uint32_t*>(row) + min(mx0 + 4, mw - 1)) };
+                const bool uyvy = S.packed_kind == 1;
+                float cu[5], cv[5], vY[PX], vU[PX], vV[PX];
+                #pragma unroll
+                for (int m = 0; m < 5; m++) {
+                    const uint32_t t = uyvy ? w[m] : (w[m] >> 8);            // bytes U ? V ?
+                    cu[m] = unorm8(t & 255u); cv[m] = unorm8((t >> 16) & 255u);
+                }
+                #pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const uint32_t t = uyvy ? (w[m] >> 8) : w[m];            // bytes Y0 ? Y1 ?
+                    vY[2 * m] = unorm8(t & 255u); vY[2 * m + 1] = unorm8((t >> 16) & 255u);
+                    vU[2 * m] = cu[m]; vV[2 * m] = cv[m];
+                    vU[2 * m + 1] = __fmul_rn(__fadd_rn(cu[m], cu[m + 1]), 0.5f); vV[2 * m + 1] = __fmul_rn(__fadd_rn(cv[m], cv[m + 1]), 0.5f);
+                }
+                #pragma unroll
+                for (int i = 0; i < PX; i += 4) {
+                    reinterpret_cast<float4*>(dY)[i >> 2] = make_float4(vY[i], vY[i + 1], vY[i + 2], vY[i + 3]);
+                    reinterpret_cast<float4*>(dU)[i >> 2] = make_float4(vU[i], vU[i + 1], vU[i + 2], vU[i + 3]);
+                    reinterpret_cast<float4*>(dV)[i >> 2] = make_float4(vV[i], vV[i + 1], vV[i + 2], vV[i + 3]);
+                }
             } else {
                 int ox, oy, my;
                 if (S.subsampling == 420) {
@@ -175,6 +202,11 @@ k_convert_bp(const __grid_constant__ SrcDesc S, const __grid_constant__ ColorPar
 // 128-bit path of the convert pass: bi-planar, bilinear chroma, planes / pitches / rect origin 16-byte aligned, an 8-, 10- or fp16 target
 static bool ConvertSpanOk(const SrcDesc& S, const SurfDesc& out)
 {
+    if (out.fmt != MPCVR_SURF_BGRA8 && out.fmt != MPCVR_SURF_RGB10A2 && out.fmt != MPCVR_SURF_RGBA16F) return false;
+    if (((uintptr_t)out.ptr & 15) || (out.pitch & 15)) return false;
+    if (S.layout == LAYOUT_PACKED422)            // YUY2 / UYVY with the averaging chroma fetch
+        return S.bytes == 1 && S.packed_kind <= 1 && S.chroma_mode != MPCVR_CHROMA_CatmullRom && !S.deint_blend && !((uintptr_t)S.pl[0] & 15) &&
+               S.pitch[0] > 0 && !(S.pitch[0] & 15) && (S.rect_l % 8) == 0;
     if (S.layout != LAYOUT_BIPLANAR || S.chroma_mode != MPCVR_CHROMA_Bilinear || S.deint_blend || S.lsb_shift != 0) return false;
     if ((S.subsampling != 420 && S.subsampling != 422) || (S.bytes != 1 && S.bytes != 2)) return false;
     if (((uintptr_t)S.pl[0] & 15) || ((uintptr_t)S.pl[1] & 15) || S.pitch[0] <= 0 || S.pitch[1] <= 0 || (S.pitch[0] & 15) || (S.pitch[1] & 15)) return false;
@@ -658,8 +690,9 @@ cudaError_t LaunchConvertPass(const SrcDesc& src, const ColorParams& color, cons
     const dim3 b(32, 8);
     if (!dovi_dev && !dbg_f32 && g_convertTwoLane == 1 && ConvertSpanOk(src, out)) {      // 128-bit spans + two-lane body
         const dim3 bs(32, 4);
-        if (src.bytes == 1) k_convert_bp<1><<<dim3((out.w + 511) / 512, (out.h + 3) / 4), bs, 0, st>>>(src, color, out);
-        else                k_convert_bp<2><<<dim3((out.w + 255) / 256, (out.h + 3) / 4), bs, 0, st>>>(src, color, out);
+        if (src.layout == LAYOUT_PACKED422) k_convert_bp<1, true><<<dim3((out.w + 255) / 256, (out.h + 3) / 4), bs, 0, st>>>(src, color, out);
+        else if (src.bytes == 1)            k_convert_bp<1, false><<<dim3((out.w + 511) / 512, (out.h + 3) / 4), bs, 0, st>>>(src, color, out);
+        else                                k_convert_bp<2, false><<<dim3((out.w + 255) / 256, (out.h + 3) / 4), bs, 0, st>>>(src, color, out);
         return cudaGetLastError();
     }
     if (!dovi_dev && g_convertTwoLane) {
@@ -726,10 +759,44 @@ cudaError_t LaunchCopyPass(const SurfDesc& in, const SurfDesc& out, const int32_
     return cudaGetLastError();
 }
 
+// FinalPass with both surface formats fixed at compile time, two neighbouring pixels per thread (one 64/128-bit load, one 64-bit store,
+// one 32-bit read of the two dither thresholds).  Same per-pixel operations as k_final.
+template <int INF, int OUTF>
+__global__ void __launch_bounds__(256)
+k_final_p(const __grid_constant__ SurfDesc in, const __grid_constant__ SurfDesc out, int x0, int y0, int x1, int y1, float Q)
+{
+    const int x = x0 + 2 * (blockIdx.x * blockDim.x + threadIdx.x), y = y0 + blockIdx.y * blockDim.y + threadIdx.y;      // x0 is even
+    if (x >= x1 || y >= y1) return;
+    const uint32_t dd = *reinterpret_cast<const uint32_t*>(&g_dither32[(y & 31) * 32 + (x & 31)]);                        // thresholds of x and x + 1
+    const float d0 = (float)(dd & 0xFFFFu) * 0.0009765625f, d1 = (float)(dd >> 16) * 0.0009765625f;
+    const uint8_t* irow = (const uint8_t*)in.ptr + (size_t)y * in.pitch;
+    f3 p0, p1;
+    if (INF == MPCVR_SURF_RGBA16F) { const uint4 v = __ldg((const uint4*)(irow + (size_t)x * 8)); p0 = texel_decode<INF>(v.x, v.y); p1 = texel_decode<INF>(v.z, v.w); }
+    else                           { const uint2 v = __ldg((const uint2*)(irow + (size_t)x * 4)); p0 = texel_decode<INF>(v.x, 0u); p1 = texel_decode<INF>(v.y, 0u); }
+    f3 o0, o1;
+    o0.x = final_quant(p0.x, Q, d0); o0.y = final_quant(p0.y, Q, d0); o0.z = final_quant(p0.z, Q, d0);
+    o1.x = final_quant(p1.x, Q, d1); o1.y = final_quant(p1.y, Q, d1); o1.z = final_quant(p1.z, Q, d1);
+    uint8_t* orow = (uint8_t*)out.ptr + (size_t)y * out.pitch;
+    auto pack = [](f3 v) -> uint32_t {
+        return OUTF == MPCVR_SURF_RGB10A2 ? (qunorm(v.x, 1023.0f) | (qunorm(v.y, 1023.0f) << 10) | (qunorm(v.z, 1023.0f) << 20) | (3u << 30))
+                                          : (qunorm(v.z, 255.0f) | (qunorm(v.y, 255.0f) << 8) | (qunorm(v.x, 255.0f) << 16) | (255u << 24)); };
+    if (x + 1 < x1) *reinterpret_cast<uint2*>(orow + (size_t)x * 4) = make_uint2(pack(o0), pack(o1));
+    else            *reinterpret_cast<uint32_t*>(orow + (size_t)x * 4) = pack(o0);
+}
+
 cudaError_t LaunchFinalPass(const SurfDesc& in, const SurfDesc& out, int x0, int y0, int x1, int y1, float Q, cudaStream_t st)
 {
     if (x1 <= x0 || y1 <= y0) return cudaSuccess;
     const dim3 b(32, 8);
+    // paired variant: even start column, both row bases 16-byte aligned, and the input row readable one texel past an odd right edge
+    if (g_resizeFour == 1 && (x0 & 1) == 0 && !((uintptr_t)in.ptr & 15) && !(in.pitch & 15) && !((uintptr_t)out.ptr & 7) && !(out.pitch & 7) && ((x1 & 1) == 0 || x1 < in.w)) {
+        const dim3 g = Grid2D((x1 - x0 + 1) / 2, y1 - y0, b);
+#define MPCVR_FP(INF, OUTF) if (in.fmt == INF && out.fmt == OUTF) { k_final_p<INF, OUTF><<<g, b, 0, st>>>(in, out, x0, y0, x1, y1, Q); return cudaGetLastError(); }
+        MPCVR_FP(MPCVR_SURF_RGBA16F, MPCVR_SURF_BGRA8) MPCVR_FP(MPCVR_SURF_RGBA16F, MPCVR_SURF_RGB10A2)
+        MPCVR_FP(MPCVR_SURF_RGB10A2, MPCVR_SURF_BGRA8) MPCVR_FP(MPCVR_SURF_RGB10A2, MPCVR_SURF_RGB10A2)
+        MPCVR_FP(MPCVR_SURF_BGRA8, MPCVR_SURF_BGRA8)
+#undef MPCVR_FP
+    }
     k_final<<<Grid2D(x1 - x0, y1 - y0, b), b, 0, st>>>(in, out, x0, y0, x1, y1, Q);
     return cudaGetLastError();
 }

@@ -450,6 +450,12 @@ __device__ __forceinline__ f3 convert_color(const ColorParams& P, f3 yuv, const 
 // ---------------------------------------------------------------------------------------------
 // final pass, Shaders/d3d11/ps_final_pass.hlsl:23-31: floor(pixel*Q + dither)/Q written to a UNORM target
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float final_quant(float p, float Q, float d) { return __fdiv_rn(floorf(fma_rn(p, Q, d)), Q); }
+// the quotient is correctly rounded either way: n is an integer-valued float and Q is 255 or 1023, so the residual-corrected
+// reciprocal sequence (div_rn_safe) is exact unless n is huge / infinite (fp16 infinities in the pass input), which takes div.rn
+__device__ __forceinline__ float final_quant(float p, float Q, float d)
+{
+    const float n = floorf(fma_rn(p, Q, d));
+    return fabsf(n) < 1e30f ? div_rn_safe(n, Q) : __fdiv_rn(n, Q);
+}
 
 }  // namespace b200vr
