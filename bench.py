@@ -248,14 +248,16 @@ def impl_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 2000; 20 for --impl reference, whose step is a whole frame on the CPU)")
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-seconds", type=float, default=120.0, help="--impl reference: wall-clock target of the K timed steps")
     ap.add_argument("--path", default="auto", choices=["auto", "multipass", "fused"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
+    if args.steps is None: args.steps = 20 if args.impl == "reference" else 2000
+    if args.warmup is None: args.warmup = 3 if args.impl == "reference" else 20
     args.warmup = max(args.warmup, 3)
 
     from videorenderer_b200 import streams

@@ -48,18 +48,33 @@ def main():
         h = src[1]; ia = h.index("Instructions Executed"); isrc = h.index("Source"); isamp = h.index("# Samples")
         data = [r for r in src[2:] if len(r) > ia and r[ia].isdigit()]
         tot = sum(int(r[ia]) for r in data) or 1
-        seg = collections.Counter(); ops = collections.defaultdict(collections.Counter); nb = 0
+        roles = any("PMTRIG" in r[isrc] for r in data)       # warp-specialised kernel: split at the role markers (pmevent), else at BAR.SYNC
+        seg = collections.Counter(); ops = collections.defaultdict(collections.Counter); smp = collections.Counter(); poll = collections.Counter(); nb = "prologue" if roles else 0
+        stall_cols = [(i, n) for i, n in enumerate(h) if n.startswith("stall_") and "Not Issued" not in n]
+        stalls = collections.defaultdict(collections.Counter)
+        ROLE = {"0x2": "role P (raw codes -> floats, chroma reconstruction; issues the TMA loads)", "0x4": "role A (convert shader body)",
+                "0x8": "role B (X pass)", "0x10": "role C (Y pass, rounding, dither, stores)"}
         for r in data:
-            if "BAR.SYNC" in r[isrc]:
+            if roles:
+                m = re.search(r"PMTRIG (0x[0-9a-f]+)", r[isrc])
+                if m: nb = ROLE.get(m.group(1), m.group(1))
+            elif "BAR.SYNC" in r[isrc]:
                 nb += 1
-            seg[nb] += int(r[ia])
+            n = int(r[ia]); seg[nb] += n; smp[nb] += int(r[isamp] or 0)
             m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[isrc])
-            ops[nb][m.group(2).split(".")[0] if m else "?"] += int(r[ia])
-        lines.append("## warp instructions by code region (split at BAR.SYNC), first kernel in the report")
-        lines.append(""); lines.append("total %d warp instructions" % tot); lines.append("")
-        lines.append("| region | warp instr | share | top opcodes |"); lines.append("|---|---|---|---|")
-        for k in sorted(seg):
-            lines.append("| %d | %d | %.1f%% | %s |" % (k, seg[k], 100 * seg[k] / tot, ", ".join("%s %d" % kv for kv in ops[k].most_common(8))))
+            op = m.group(2).split(".")[0] if m else "?"
+            ops[nb][op] += n
+            if op in ("SYNCS", "NANOSLEEP"): poll[nb] += n
+            for i, name in stall_cols:
+                if i < len(r) and r[i].isdigit(): stalls[nb][name.replace("stall_", "")] += int(r[i])
+        lines.append("## warp instructions by code region (%s), first kernel in the report" % ("split at the pmevent role markers" if roles else "split at BAR.SYNC"))
+        lines.append(""); lines.append("total %d warp instructions%s" % (tot, " (source-page counters; the replay pass that collects them runs slower, so spin-wait"
+                                       " instructions are over-represented against `smsp__inst_executed.sum` above)" if roles else "")); lines.append("")
+        lines.append("| region | warp instr | share | of which mbarrier polling (SYNCS + NANOSLEEP) | samples | top stall reasons (samples) | top opcodes |"); lines.append("|---|---|---|---|---|---|---|")
+        for k in seg:
+            st = stalls[k]; stt = sum(st.values()) or 1
+            lines.append("| %s | %d | %.1f%% | %d | %d | %s | %s |" % (k, seg[k], 100 * seg[k] / tot, poll[k], smp[k],
+                         ", ".join("%s %.0f%%" % (a, 100 * b / stt) for a, b in st.most_common(5)), ", ".join("%s %d" % kv for kv in ops[k].most_common(8))))
     open(dst, "w").write("\n".join(lines) + "\n")
     print("wrote", dst)
 

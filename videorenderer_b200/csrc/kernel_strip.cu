@@ -1,6 +1,7 @@
 // kernel_strip.cu -- host side of the persistent strip kernel (kernel_strip.cuh): eligibility, TMA tensor maps, launch.
 #include <mutex>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include "kernel_strip.cuh"
 #include "kernel_strip.h"
@@ -45,7 +46,10 @@ int StripStatus(unsigned int out[8], int clear)
 }
 
 // process-wide debug switches (tests flip them between frames; atomics so a concurrent instance reads a whole value)
-static std::atomic<int> g_stripEnabled{1}, g_stripCfg{0}, g_stripSkip{0}, g_stripWaitNs{0};
+// MPCVR_DEBUG_STRIP_KERNEL=0 in the environment starts the process on the tile kernel (sanitizer runs: racecheck does not model
+// mbarrier-ordered shared-memory handoffs and reports every one of them)
+static int StripEnabledAtLoad() { const char* e = getenv("MPCVR_DEBUG_STRIP_KERNEL"); return e ? atoi(e) != 0 : 1; }
+static std::atomic<int> g_stripEnabled{StripEnabledAtLoad()}, g_stripCfg{0}, g_stripSkip{0}, g_stripWaitNs{0};
 void SetStripKernel(int enabled, int cfg) { g_stripEnabled = enabled; g_stripCfg = cfg & 0xFF; g_stripSkip = (cfg >> 8) & 0xF; g_stripWaitNs = ((cfg >> 12) & 0xF) ? (16 << ((cfg >> 12) & 0xF)) : 0; }   // cfg bits 8..11: role-skip mask (debug)
 
 bool StripEligible(const FusedPlan& p)
