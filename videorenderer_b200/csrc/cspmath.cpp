@@ -2,7 +2,7 @@
 //
 // The arithmetic (operation order, float vs double intermediates) is dictated by the reference
 // because the 12 + 9 constants must come out bit-identical (KATs: SURVEY 8 a3/a5, checked
-// against the reference's own csputils.cpp in tests/test_host_colormath.py); the structure is ours.
+// against the reference's own csputils.cpp in tests/test_oracle_pins.py and tests/test_host_logic.py); the structure is ours.
 #include <cmath>
 #include "cspmath.h"
 
