@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """tools/make_capture_json.py <report.ncu-rep> [kernel-regex] -> profiles/capture_c2.json
 Records, from one `ncu --set full` capture of the C2 frame kernel, the numbers bench.py quotes next to its live timing
-(DRAM bytes per launch, warp instructions per launch) TOGETHER WITH the sha256 of videorenderer_b200/csrc at capture time.
+(DRAM bytes per launch, warp instructions per launch) TOGETHER WITH the sha256 of the device sources (videorenderer_b200/csrc/*.cu, *.cuh, *.h) at capture time.
 bench.py recomputes that hash: if the kernel sources changed since the capture it says so ("traffic_stale": true) and drops
 the instruction-issue figure instead of quoting numbers of another binary."""
 import csv, hashlib, io, json, os, re, subprocess, sys
@@ -13,7 +13,7 @@ def csrc_sha256():
     d = os.path.join(ROOT, "videorenderer_b200", "csrc")
     h = hashlib.sha256()
     for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh", ".cpp", ".h")):
+        if name.endswith((".cu", ".cuh", ".h")):            # device code and the headers it includes; host-only .cpp files do not change a kernel
             h.update(name.encode()); h.update(open(os.path.join(d, name), "rb").read())
     return h.hexdigest()
 
