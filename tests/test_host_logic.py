@@ -172,18 +172,66 @@ def test_no_cpu_fallback_and_error_convention():
 
 
 def test_unorm_read_sequence_is_exact():
-    """q = c*r; q += fma(-q, N, c)*r  equals the IEEE quotient c/N for every code of the three UNORM widths
-    (what mpcvr_math.cuh::div_by_const_exact relies on; re-checked on the device in the GPU tests)"""
+    """t = c*lo; q = fma(c, hi, t) with hi + lo = 1/N split into two floats equals the IEEE quotient c/N for every code of the
+    three UNORM widths (what mpcvr_math.cuh::div_by_const_exact relies on; re-checked on the device in the GPU tests).
+    The residual form used until round 2 (q = c*r; q += fma(-q, N, c)*r) is checked to give the same values."""
+    from fractions import Fraction
     import math
+
+    def rn32(fr):                                  # exact rational -> nearest float32, ties to even
+        if fr == 0:
+            return 0.0
+        if fr < 0:
+            return -rn32(-fr)
+        e = math.floor(math.log2(float(fr)))
+        while Fraction(2) ** e > fr: e -= 1
+        while Fraction(2) ** (e + 1) <= fr: e += 1
+        scale = Fraction(2) ** (e - 23)
+        m = fr / scale
+        fl = m.numerator // m.denominator
+        rem = m - fl
+        if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and fl % 2 == 1): fl += 1
+        return float(Fraction(fl) * scale)
+
     for n in (255, 1023, 65535):
+        hi = float(np.float32(1.0 / n)); lo = float(np.float32(1.0 / n - hi))
+        step = 1 if n < 65535 else 7               # every code of the 8/10-bit widths; every 7th + the ends of the 16-bit one (all 65536 on the device)
+        codes = sorted(set(list(range(0, n + 1, step)) + [n - 1, n] + [64 * k for k in range(1024)] if n == 65535 else range(n + 1)))
+        for c in codes:
+            t = rn32(Fraction(c) * Fraction(lo))
+            q = rn32(Fraction(c) * Fraction(hi) + Fraction(t))
+            assert q == rn32(Fraction(c, n)), (n, c)
+        # the residual form
         N = np.float32(n); r = np.float32(1.0) / N
         c = np.arange(n + 1, dtype=np.float32)
         q = c * r
-        # fma emulated exactly in float64 (products of two float32 are exact in float64)
         e = (c.astype(np.float64) - q.astype(np.float64) * np.float64(N)).astype(np.float32)
         assert np.all(e.astype(np.float64) == c.astype(np.float64) - q.astype(np.float64) * np.float64(N)), "residual must be exact"
         q2 = (q.astype(np.float64) + e.astype(np.float64) * np.float64(r)).astype(np.float32)
         assert np.array_equal(q2, c / N)
+
+
+def test_fused_readback_final_pass_is_exact():
+    """kernel_strip.cuh OPT_C_FUSEDQ: for every 10-bit code c and every dither threshold d = k/1024 of the 32x32 table,
+    floor(fma(RN(c/1023), 255, d))  ==  floor(fma(c, RN(255/1023), d + 2^-20))  -- the UNORM10 read-back of m_TexsPostScale and
+    ps_final_pass (Shaders/d3d11/ps_final_pass.hlsl) as one multiply-add on the integer code.  All 1024 x 1024 pairs; the fma is
+    emulated exactly (products of a 10-bit and a 24-bit number plus a 20-bit addend fit float64), rounded once to float32."""
+    c = np.arange(1024, dtype=np.float64); k = np.arange(1024, dtype=np.float64)
+    p = (c / 1023.0).astype(np.float32).astype(np.float64)
+    assert np.array_equal(p.astype(np.float32), (np.arange(1024, dtype=np.float32) / np.float32(1023)))       # the correctly rounded quotient
+    d = k / 1024.0
+    spec = np.floor((p[:, None] * 255.0 + d[None, :]).astype(np.float32)).astype(np.int32)
+    K1 = np.float64(np.float32(255.0 / 1023.0)); delta = 2.0 ** -20
+    assert np.all((d + delta).astype(np.float32).astype(np.float64) == d + delta)                              # the shifted thresholds are floats
+    fused = np.floor((c[:, None] * K1 + (d[None, :] + delta)).astype(np.float32)).astype(np.int32)
+    assert np.array_equal(fused, spec)
+    # the window is narrow: without the offset, or with four times the offset, some pair differs
+    assert np.any(np.floor((c[:, None] * K1 + d[None, :]).astype(np.float32)).astype(np.int32) != spec)
+    assert np.any(np.floor((c[:, None] * K1 + (d[None, :] + 4 * delta)).astype(np.float32)).astype(np.int32) != spec)
+    # and the golden (code, threshold) -> u8 table of the final pass (minted by the oracle, tests/golden/make_golden.py) holds the same bytes
+    import hashlib, json, os
+    J = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "dither_stage.json")))
+    assert hashlib.sha256(fused.astype(np.uint8).tobytes()).hexdigest() == J["table_sha256"]
 
 
 def test_hdr_output_picks_the_convert_type():

@@ -46,6 +46,7 @@ constexpr int kGammaMaxExc = 2;
 constexpr int kGammaMaxTrans = 4096;
 __device__ float    g_gammaT[kGammaN + 2];       // T[0] = 0, T[1..N], T[N+1] = +inf
 __device__ float    g_gammaD[kGammaN + 1];       // c / 1023, correctly rounded
+__device__ GammaEntry g_gammaG[kGammaN + 2];     // the same table as one 16-byte entry per estimate: {T[c0 + 1], D[c0], D[c0 + 1], -}; entry N + 1 guards e > 1
 __device__ uint32_t g_gammaExc[kGammaMaxExc];    // float bit patterns whose code is one below the table's
 __device__ uint32_t g_gammaTransCount;
 __device__ uint2    g_gammaTrans[kGammaMaxTrans];   // (u, from << 16 | to): code(u - 1 ulp) = from, code(u) = to
@@ -824,7 +825,7 @@ static std::atomic<int> g_fused1xVector{1};                       // debug switc
 void SetFused1xVector(int on) { g_fused1xVector = on; }
 void SetGammaTableEnabled(int on) { g_useGammaTable = on; }
 
-static const float* g_gammaTdev[64]; static const float* g_gammaDdev[64]; static uint32_t g_gammaExcHost[64][2];   // per device, valid once ready
+static const float* g_gammaTdev[64]; static const float* g_gammaDdev[64]; static const GammaEntry* g_gammaGdev[64]; static uint32_t g_gammaExcHost[64][2];   // per device, valid once ready
 
 static bool EnsureGammaTable(cudaStream_t st)
 {
@@ -868,10 +869,18 @@ static bool EnsureGammaTable(cudaStream_t st)
     if (cudaMemcpyToSymbolAsync(g_gammaT, T, sizeof(T), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
     if (cudaMemcpyToSymbolAsync(g_gammaD, D, sizeof(D), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
     if (cudaMemcpyToSymbolAsync(g_gammaExc, exc, sizeof(exc), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+    static GammaEntry G[kGammaN + 2];
+    for (int c = 0; c <= kGammaN + 1; c++) {
+        const int c0 = c < kGammaN ? c : kGammaN;
+        G[c].t = T[c0 + 1]; G[c].d0 = D[c0]; G[c].d1 = D[c0 < kGammaN ? c0 + 1 : kGammaN]; G[c].pad = 0.0f;
+    }
+    if (cudaMemcpyToSymbolAsync(g_gammaG, G, sizeof(G), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
     if (cudaStreamSynchronize(st) != cudaSuccess) return false;    // T, D are function statics reused across devices
     void* pt = nullptr; void* pd = nullptr;
     if (cudaGetSymbolAddress(&pt, g_gammaT) != cudaSuccess || cudaGetSymbolAddress(&pd, g_gammaD) != cudaSuccess) return false;
-    g_gammaTdev[dev] = (const float*)pt; g_gammaDdev[dev] = (const float*)pd;
+    void* pg = nullptr;
+    if (cudaGetSymbolAddress(&pg, g_gammaG) != cudaSuccess) return false;
+    g_gammaTdev[dev] = (const float*)pt; g_gammaDdev[dev] = (const float*)pd; g_gammaGdev[dev] = (const GammaEntry*)pg;
     g_gammaExcHost[dev][0] = exc[0]; g_gammaExcHost[dev][1] = exc[1];
     state[dev] = 1;
     return true;
@@ -891,6 +900,8 @@ __global__ void __launch_bounds__(256) k_gamma_verify(uint32_t run)
         const float direct = unorm10(gamma_code(x));
         const float table = gamma_q10_thr(x, g_gammaT, g_gammaD, exc0, exc1);
         bad += (__float_as_uint(direct) != __float_as_uint(table)) ? 1u : 0u;
+        const float lut = gamma_q10_lut_g(x, g_gammaG, exc0);            // the single-lookup form (one exception float)
+        bad += (exc1 == 0xFFFFFFFFu && __float_as_uint(direct) != __float_as_uint(lut)) ? 1u : 0u;
         if (u == last) break;
     }
     if (bad) atomicAdd(&g_gammaMismatch, (unsigned long long)bad);
@@ -954,7 +965,7 @@ cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
         int dev = 0; cudaGetDevice(&dev);
         const bool ok = thr && dev >= 0 && dev < 64 && g_gammaExcHost[dev][1] == 0xFFFFFFFFu;   // the strip kernel checks one exception float
         if (launches) *launches = 1;
-        const cudaError_t e = LaunchStrip2x(p, ok ? g_gammaTdev[dev] : nullptr, ok ? g_gammaDdev[dev] : nullptr, ok ? g_gammaExcHost[dev] : nullptr, st);
+        const cudaError_t e = LaunchStrip2x(p, ok ? g_gammaTdev[dev] : nullptr, ok ? g_gammaDdev[dev] : nullptr, ok ? g_gammaGdev[dev] : nullptr, ok ? g_gammaExcHost[dev] : nullptr, st);
         if (e != cudaErrorNotSupported) return e;
     }
     if (p.out.fmt == MPCVR_SURF_RGB8) return cudaErrorNotSupported;              // the tile kernel does not write packed RGB8

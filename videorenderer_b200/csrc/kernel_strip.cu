@@ -84,12 +84,19 @@ static cudaError_t LaunchK(const StripParams& prm, int grid, cudaStream_t st)
     return cudaGetLastError();
 }
 
-// warp-role splits measured on B200 (C2 frame, us): see DESIGN.md 4.1.  Cfg0 is the default; the others stay selectable through
-// mpcvr_debug_set_strip_kernel for the role-balance experiments.
-typedef StripCfg<128, 8, 4, 12, 4, 8> Cfg0;       // 28 warps: 4 P (two teams of 2) + 12 A + 4 B + 8 C
-typedef StripCfg<128, 8, 4, 10, 4, 8> Cfg1;       // 26 warps
-typedef StripCfg<128, 8, 6, 10, 4, 8> Cfg2;       // 28 warps (P teams of 3)
-typedef StripCfg<128, 8, 8, 10, 2, 8> Cfg3;       // 28 warps (P teams of 4)
+// Configurations measured on B200 (C2 frame; DESIGN.md 4.1, profiles/r02_strip_experiments.txt).  Cfg0 is what the product runs; the
+// others stay selectable through mpcvr_debug_set_strip_kernel so that the measurements can be repeated -- every one is bit-identical.
+typedef StripCfg<128, 8, 4, 12, 4, 8, OPT_GAMMA_LUT | OPT_C_FUSEDQ> Cfg0;        // 28 warps: 4 P (two teams of 2) + 12 A + 4 B + 8 C; single-lookup gamma table
+typedef StripCfg<128, 8, 4, 10, 4, 8, OPT_GAMMA_LUT> Cfg1;        // 26 warps
+typedef StripCfg<128, 8, 6, 10, 4, 8, OPT_GAMMA_LUT> Cfg2;        // 28 warps (P teams of 3)
+typedef StripCfg<128, 8, 8, 10, 2, 8, OPT_GAMMA_LUT> Cfg3;        // 28 warps (P teams of 4)
+typedef StripCfg<128, 8, 4, 12, 4, 8, 0> Cfg6;                    // gamma through T[] / D[] (two dependent loads, F2I), read-back quotient formed: the round-2a form
+typedef StripCfg<128, 8, 4, 12, 4, 8, OPT_GAMMA_LUT> Cfg8;        // single-lookup gamma, read-back quotient formed
+typedef StripCfg<128, 8, 4, 16, 4, 8, OPT_GAMMA_LUT> Cfg7;        // 32 warps at 64 registers (role C spills)
+typedef StripCfg<128, 8, 4, 16, 4, 8, OPT_GAMMA_LUT | OPT_SETMAXNREG> Cfg9;        // 32 warps, registers P/B 40, A 64, C 88
+typedef StripCfg<128, 8, 4, 12, 4, 12, OPT_GAMMA_LUT | OPT_SETMAXNREG> Cfg10;      // 32 warps, registers P/B 40, A 64, C 80
+typedef StripCfg<128, 8, 4, 12, 4, 8, OPT_GAMMA_LUT | OPT_C_LUT> Cfg11;            // + UNORM10 read-back of role C from the table (FMA pipe -> LSU)
+typedef StripCfg<128, 8, 4, 12, 4, 8, OPT_GAMMA_LUT | OPT_C_ROLL> Cfg13;           // + rolled channel loop in role C (instruction-cache footprint)
 
 template <int NT, bool DUP>
 static cudaError_t LaunchV(const StripParams& prm, int spec, int conv, int grid, cudaStream_t st)
@@ -100,8 +107,15 @@ static cudaError_t LaunchV(const StripParams& prm, int spec, int conv, int grid,
             case 1:  return LaunchK<Cfg1, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             case 2:  return LaunchK<Cfg2, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             case 3:  return LaunchK<Cfg3, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
-            case 4:  return LaunchK<Cfg0, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR_RELAX1>(prm, grid, st);   // measurement only
-            case 5:  return LaunchK<Cfg0, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR_RELAX2>(prm, grid, st);   // measurement only
+            case 4:  return LaunchK<Cfg6, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR_RELAX1>(prm, grid, st);   // measurement only, NOT bit-exact
+            case 5:  return LaunchK<Cfg6, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR_RELAX2>(prm, grid, st);   // measurement only, NOT bit-exact
+            case 6:  return LaunchK<Cfg6, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
+            case 7:  return LaunchK<Cfg7, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
+            case 8:  return LaunchK<Cfg8, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
+            case 9:  return LaunchK<Cfg9, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
+            case 10: return LaunchK<Cfg10, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
+            case 11: return LaunchK<Cfg11, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
+            case 13: return LaunchK<Cfg13, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             default: break;
             }
         }
@@ -114,7 +128,7 @@ static cudaError_t LaunchV(const StripParams& prm, int spec, int conv, int grid,
     return LaunchK<Cfg0, NT, DUP, SSPEC_RUNTIME, SCONV_ANY>(prm, grid, st);
 }
 
-cudaError_t LaunchStrip2x(const FusedPlan& p, const float* gT, const float* gD, const uint32_t exc[2], cudaStream_t st)
+cudaError_t LaunchStrip2x(const FusedPlan& p, const float* gT, const float* gD, const GammaEntry* gG, const uint32_t exc[2], cudaStream_t st)
 {
     const SrcDesc& S = p.src;
     StripParams prm;
@@ -132,7 +146,7 @@ cudaError_t LaunchStrip2x(const FusedPlan& p, const float* gT, const float* gD, 
                    (uint64_t)S.pitch[1], cbox, (uint32_t)prm.rc_rows)) return cudaErrorNotSupported;
     prm.color = p.color; prm.out = p.out;
     for (int k = 0; k < nt; k++) { prm.wE[k] = p.wE[k]; prm.wO[k] = p.wO[k]; }
-    prm.gT = gT; prm.gD = gD; prm.exc0 = exc ? exc[0] : 0xFFFFFFFFu; prm.exc1 = exc ? exc[1] : 0xFFFFFFFFu;
+    prm.gT = gT; prm.gD = gD; prm.gG = gG; prm.exc0 = exc ? exc[0] : 0xFFFFFFFFu; prm.exc1 = exc ? exc[1] : 0xFFFFFFFFu;
     prm.b0 = p.b0;
     prm.w1 = p.ax.src_len; prm.h1 = p.ay.src_len;
     prm.rect_l = S.rect_l; prm.rect_t = S.rect_t; prm.cw = S.cw; prm.ch = S.ch; prm.bytes = S.bytes;
@@ -150,10 +164,10 @@ cudaError_t LaunchStrip2x(const FusedPlan& p, const float* gT, const float* gD, 
     int spec = SSPEC_RUNTIME;
     if (p.internal_fmt == MPCVR_SURF_RGB10A2 && p.out.fmt == MPCVR_SURF_BGRA8 && p.final_pass && p.Q == 255.0f) spec = SSPEC_10_BGRA8_DITHER;
     else if (p.internal_fmt == MPCVR_SURF_RGB10A2 && p.out.fmt == MPCVR_SURF_RGB8 && p.final_pass && p.Q == 255.0f && (p.ax.dst0 & 3) == 0 &&
-             p.color.transfer == TRANSFER_PQ_TO_SDR && S.bytes == 2 && gT && gD) spec = SSPEC_10_RGB8_DITHER;
+             p.color.transfer == TRANSFER_PQ_TO_SDR && S.bytes == 2 && gT && gD && gG) spec = SSPEC_10_RGB8_DITHER;
     else if (p.internal_fmt == MPCVR_SURF_BGRA8 && p.out.fmt == MPCVR_SURF_BGRA8 && !p.final_pass) spec = SSPEC_8_BGRA8;
     int conv = SCONV_ANY;
-    if (p.color.transfer == TRANSFER_PQ_TO_SDR && S.bytes == 2) conv = ((spec == SSPEC_10_BGRA8_DITHER || spec == SSPEC_10_RGB8_DITHER) && gT && gD) ? SCONV_PQ_THR : SCONV_PQ;
+    if (p.color.transfer == TRANSFER_PQ_TO_SDR && S.bytes == 2) conv = ((spec == SSPEC_10_BGRA8_DITHER || spec == SSPEC_10_RGB8_DITHER) && gT && gD && gG) ? SCONV_PQ_THR : SCONV_PQ;
 
     static int sms[64] = {};
     int dev = 0; cudaGetDevice(&dev);

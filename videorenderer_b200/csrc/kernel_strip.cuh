@@ -49,6 +49,7 @@ struct StripParams {
     SurfDesc    out;
     float       wE[6], wO[6];             // weights of even / odd outputs (the 2x ratio has exactly two phases)
     const float* gT; const float* gD;     // threshold table (SCONV_PQ_THR)
+    const GammaEntry* gG;                 // the same table as 16-byte entries (OPT_GAMMA_LUT)
     uint32_t    exc0, exc1;
     int32_t     b0;                       // window start relative to j (even output); odd = b0 + 1
     int32_t     w1, h1;                   // convert surface size (= m_srcRect size)
@@ -124,13 +125,33 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) { float d; a
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; }
 
 // ---- geometry ---------------------------------------------------------------------------------------------------------
-template <int SW_, int R_, int NP_, int NA_, int NB_, int NC_>
+// optional code paths of the kernel (all bit-identical; kept selectable so that each one's effect can be measured on its own)
+enum { OPT_GAMMA_LUT = 1,         // role A: gamma + UNORM10 through ONE 16-byte table access (gamma_q10_lut2) instead of estimate -> F2I -> T[] -> D[]
+       OPT_SETMAXNREG = 2,
+       OPT_C_LUT = 4,
+       OPT_C_ROLL = 8,            // role C: channel loop not unrolled (instruction-cache footprint)
+       OPT_C_FUSEDQ = 16 };       // role C: UNORM10 read-back and final pass as ONE fma on the integer code (see kFinalK1 below)
+
+// m_TexsPostScale (RGB10A2) read-back followed by ps_final_pass on an 8-bit target:  out = floor(fma(RN(c / 1023), 255, d)),  c the
+// 10-bit code, d = k / 1024 the dither threshold.  For every one of the 1024 x 1024 (c, k) pairs this equals
+// floor(fma(c, K1, d + 2^-20)) with K1 = RN(255 / 1023): the quotient never has to be formed.  (The offset has to lie in
+// [2^-21, 1.4e-6]; checked exhaustively in tests/test_host_logic.py::test_fused_readback_final_pass_is_exact.)
+constexpr float kFinalK1 = (float)(255.0 / 1023.0);
+constexpr float kFinalDelta = 9.5367431640625e-07f;           // role C: the UNORM10 read-back c/1023 of m_TexsPostScale from the 1024-entry table (LSU) instead of three packed FMA-pipe operations      // 32 warps at 64 registers; roles P and B give registers back (setmaxnreg.dec 40), role C takes them (setmaxnreg.inc)
+
+template <int SW_, int R_, int NP_, int NA_, int NB_, int NC_, int OPT_ = 0>
 struct StripCfg {
+    static constexpr int OPT = OPT_;
     static constexpr int SW = SW_;                 // convert-surface pixels per strip
     static constexpr int R = R_;                   // convert rows per row group
     static constexpr int NP = NP_, NA = NA_, NB = NB_, NC = NC_;      // warps per role
     static constexpr int CB = SW / 32;             // column blocks of 32 core pixels (= 64 outputs, one warp wide)
     static constexpr int THREADS = 32 * (NP + NA + NB + NC);
+    // register budget per role under OPT_SETMAXNREG (warp groups of four: every role's warp count is a multiple of 4)
+    static constexpr int REG_PB = 40, REG_A = 64;
+    static constexpr int REG_C = ((2048 - REG_PB * (NP + NB) - REG_A * NA) / NC) / 8 * 8;
+    static_assert(!(OPT_ & OPT_SETMAXNREG) || (NP % 4 == 0 && NA % 4 == 0 && NB % 4 == 0 && NC % 4 == 0 && NP + NA + NB + NC == 32 && REG_C >= 64 && REG_C <= 232),
+                  "setmaxnreg works on aligned groups of four warps and the launch holds 32 warps x 64 registers");
     static constexpr int WP = SW + 8;              // window pitch in pixels (window = SW + NT <= WP)
     static constexpr int PAIRS = WP / 2;
     static constexpr int CP = SW / 2 + 8;          // chroma texels per box row
@@ -146,7 +167,7 @@ struct StripCfg {
     // shared memory layout (byte offsets)
     static constexpr int oBars = 0;                                   // 28 mbarriers
     static constexpr int oT = 256;
-    static constexpr int oD = oT + align128((kGammaN + 2) * 4);
+    static constexpr int oD = oT + align128((kGammaN + 2) * ((OPT_ & OPT_GAMMA_LUT) ? 16 : 4));   // 16-byte entries with OPT_GAMMA_LUT (sD then unused)
     static constexpr int oDith = oD + align128((kGammaN + 1) * 4);
     static constexpr int oRawY = oDith + 8192;                         // dither table stored twice (64 rows): 8 consecutive rows never wrap
     // TMA boxes start on 16-byte boundaries of the plane rows (the hardware rejects other inner coordinates), so the boxes are
@@ -266,13 +287,23 @@ k_strip2x(const __grid_constant__ StripParams prm)
             mbar_init(sbase + 8 * (B_CONVFULL + i), C::NA);  mbar_init(sbase + 8 * (B_CONVEMPTY + i), C::NB);
         }
         for (int i = 0; i < 4; i++) { mbar_init(sbase + 8 * (B_XFULL + i), C::NB); mbar_init(sbase + 8 * (B_XDONE + i), C::NC); }
+        reinterpret_cast<volatile uint32_t*>(smem)[60] = sbase + (uint32_t)C::oT - (0x4B000000u << 4);       // bytes 240..247: table bases as the lookups use them
+        reinterpret_cast<volatile uint32_t*>(smem)[61] = sbase + (uint32_t)C::oD - (0x4B000000u << 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (CONV == SCONV_PQ_THR || CONV >= SCONV_PQ_THR_RELAX1) {
+    constexpr bool LUT = (C::OPT & OPT_GAMMA_LUT) && CONV == SCONV_PQ_THR;
+    constexpr bool CLUT = (C::OPT & OPT_C_LUT) && CONV == SCONV_PQ_THR && HOT;
+    if (LUT) {
+        for (int i = threadIdx.x; i < kGammaN + 2; i += C::THREADS)
+            reinterpret_cast<float4*>(sT)[i] = reinterpret_cast<const float4*>(prm.gG)[i];
+        if (CLUT) for (int i = threadIdx.x; i < kGammaN + 1; i += C::THREADS) sD[i] = prm.gD[i];
+    } else if (CONV == SCONV_PQ_THR || CONV >= SCONV_PQ_THR_RELAX1) {
         for (int i = threadIdx.x; i < kGammaN + 2; i += C::THREADS) sT[i] = prm.gT[i];
         for (int i = threadIdx.x; i < kGammaN + 1; i += C::THREADS) sD[i] = prm.gD[i];
     }
-    for (int i = threadIdx.x; i < 2048; i += C::THREADS) sDith[i] = HOT ? -g_dither32_strip.v[i & 1023] : g_dither32_strip.v[i & 1023];
+    constexpr bool FQ = (C::OPT & OPT_C_FUSEDQ) && HOT;
+    for (int i = threadIdx.x; i < 2048; i += C::THREADS)
+        sDith[i] = FQ ? -__fadd_rn(g_dither32_strip.v[i & 1023], kFinalDelta) : (HOT ? -g_dither32_strip.v[i & 1023] : g_dither32_strip.v[i & 1023]);
     __syncthreads();
 
     const long long total = (long long)prm.strips * prm.nq;
@@ -282,13 +313,15 @@ k_strip2x(const __grid_constant__ StripParams prm)
     if (warp < C::NP) {
         // ================================================================================================ TMA + role P
         asm volatile("pmevent 1;");                                      // marks the role in SASS listings / ncu source pages (PMTRIG)
+        if (C::OPT & OPT_SETMAXNREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(C::REG_PB));
         constexpr int TP = C::PT * 32;                                    // threads of one team
         const int team = warp / C::PT, tP = threadIdx.x - team * TP;
         GroupIter<C, NT> gi; gi.init(Q0, Q1, prm.nq, prm.b0, prm.h1);
         GroupIter<C, NT> iss = gi; int it_iss = 0;                       // issue cursor (thread 0 of each team, for the team's own groups)
         float* sCu = reinterpret_cast<float*>(smem + C::oCu + team * C::szScratch); float* sCv = sCu + C::szC / 4;
         float* sHU = sCv + C::szC / 4; float* sHV = sHU + C::szH / 4;
-        const int bytes = prm.bytes, ox = prm.ox, oy = prm.oy, my = prm.my, RC = prm.rc_rows;
+        // the PQ instantiations are only dispatched for 16-bit components (LaunchStrip2x): a compile-time constant halves role P's code
+        const int bytes = CONV == SCONV_ANY ? prm.bytes : 2, ox = prm.ox, oy = prm.oy, my = prm.my, RC = prm.rc_rows;
         const int lmask = 16 / bytes - 1, cmask = 8 / bytes - 1;          // box origins are multiples of 16 bytes
         const int cbox = bytes == 2 ? C::CBOX32 : C::CBOX16;
         for (int it = 0; gi.valid; it++, gi.advance()) {
@@ -387,6 +420,9 @@ k_strip2x(const __grid_constant__ StripParams prm)
         int stream = 0;                                                 // items handed out so far, modulo TA
         const uint32_t exc0 = prm.exc0;
         const float ym2s = prm.color.inv_m2 * 1.1920928955078125e-07f, ym1s = prm.color.inv_m1 * 1.1920928955078125e-07f;   // exponents * 2^-23 (exact)
+        // table address - (0x4B000000 << 4) as ONE register: read back from shared memory so that ptxas cannot split it into
+        // base + constant again (an entry's address is then a single LEA on the float's bits)
+        uint32_t K; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(K) : "r"(sbase + 240u));
 
         for (int it = 0; gi.valid; it++, gi.advance()) {
             const int slot = it % C::NS; const uint32_t ph = (it / C::NS) & 1;
@@ -407,9 +443,13 @@ k_strip2x(const __grid_constant__ StripParams prm)
                     const f3x2 g = CONV == SCONV_PQ_THR_RELAX1 ? convert_color_pq2_pre_relaxed<1>(prm.color, ym2s, ym1s, yuv)
                                  : CONV == SCONV_PQ_THR_RELAX2 ? convert_color_pq2_pre_relaxed<2>(prm.color, ym2s, ym1s, yuv)
                                  : convert_color_pq2_pre_s(prm.color, ym2s, ym1s, yuv);       // saturated gamut-mapped linear light
+                    if (LUT) {
+                        c0[k] = gamma_q10_lut2(g.x, K, exc0); c1[k] = gamma_q10_lut2(g.y, K, exc0); c2[k] = gamma_q10_lut2(g.z, K, exc0);
+                    } else {
                     c0[k] = make_float2(gamma_q10_thr1(g.x.x, sT, sD, exc0), gamma_q10_thr1(g.x.y, sT, sD, exc0));
                     c1[k] = make_float2(gamma_q10_thr1(g.y.x, sT, sD, exc0), gamma_q10_thr1(g.y.y, sT, sD, exc0));
                     c2[k] = make_float2(gamma_q10_thr1(g.z.x, sT, sD, exc0), gamma_q10_thr1(g.z.y, sT, sD, exc0));
+                    }
                 } else {
                     const f3x2 rgb = (CONV == SCONV_PQ) ? convert_color_pq2(prm.color, yuv) : convert_color2(prm.color, yuv);
                     c0[k] = rt_roundtrip2(IFMT, rgb.x); c1[k] = rt_roundtrip2(IFMT, rgb.y); c2[k] = rt_roundtrip2(IFMT, rgb.z);
@@ -422,6 +462,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
     } else if (warp < C::NP + C::NA + C::NB) {
         // ================================================================================================ role B: X pass
         asm volatile("pmevent 3;");
+        if (C::OPT & OPT_SETMAXNREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(C::REG_PB));
         const int wb = warp - C::NP - C::NA, pair = wb >> 1, tB = (wb & 1) * 32 + lane;
         __half* sX = reinterpret_cast<__half*>(smem + C::oX);
         float wE[NT], wO[NT];
@@ -450,6 +491,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
     } else {
         // ================================================================================================ role C: Y pass + final pass
         asm volatile("pmevent 4;");
+        if (C::OPT & OPT_SETMAXNREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(C::REG_C));
         const int wc = warp - C::NP - C::NA - C::NB;
         const int  OFMT  = SPEC != SSPEC_RUNTIME ? (int)MPCVR_SURF_BGRA8 : prm.out.fmt;
         const bool FINAL = HOT ? true : (SPEC == SSPEC_8_BGRA8 ? false : prm.final_pass != 0);
@@ -459,6 +501,8 @@ k_strip2x(const __grid_constant__ StripParams prm)
         for (int k = 0; k < NT; k++) { wE[k] = prm.wE[k]; wO[k] = prm.wO[k]; }
         GroupIter<C, NT> gi; gi.init(Q0, Q1, prm.nq, prm.b0, prm.h1);
         int qnext = 0, it0 = 0, turn = 0;                                // turn: items handed out so far, modulo NC
+        uint32_t KD;       // address of D[] - (0x4B000000 << 2) as one register (OPT_C_LUT), see K in role A
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(KD) : "r"(sbase + 244u));
 
         for (int it = 0; gi.valid; it++, gi.advance()) {
             if (gi.g == 0) { it0 = it; qnext = gi.qa; }
@@ -501,8 +545,10 @@ k_strip2x(const __grid_constant__ StripParams prm)
                     #pragma unroll
                     for (int r = 0; r < 8; r++) nd[r] = *reinterpret_cast<const float2*>(sDith + ((gy & 31) << 5) + (gx & 31) + 32 * r);
                     uint32_t w0[8], w1[8];
-                    #pragma unroll
-                    for (int cc = 0; cc < 3; cc++) {
+                    // OPT_C_ROLL: the three channels as a real loop (a third of the code: the SM's instruction cache holds four roles'
+                    // loops); the packing step then takes its byte selector from the channel number
+                    constexpr bool CROLL = (C::OPT & OPT_C_ROLL) != 0;
+                    auto channel = [&](const int cc, const uint32_t sel) {
                         const int c = SPEC == SSPEC_10_RGB8_DITHER ? cc : 2 - cc;
                         float2 v[NT + 4];
                         #pragma unroll
@@ -528,14 +574,40 @@ k_strip2x(const __grid_constant__ StripParams prm)
                                 const float2 val = h ? d : e;
                                 // m_TexsPostScale (RGB10A2) write + read, then ps_final_pass: floor(p*255 + dither), negated so that the
                                 // sign byte doubles as the alpha byte: fl = -(2^23 + floor(t))
-                                const float2 p = div_by_const_exact2(floor_pos2(fma2(val, 1023.0f, 0.5f)), 1023.0f, 1.0f / 1023.0f);
+                                if (FQ) {
+                                    const float2 cf = floor_pos2(fma2(val, 1023.0f, 0.5f));                      // the UNORM10 code as a float
+                                    const float2 fl = __fadd2_ru(fma2(cf, -kFinalK1, nd[r]), bc2(-8388608.0f));  // nd = -(d + 2^-20)
+                                    const uint32_t f0 = __float_as_uint(fl.x), f1 = __float_as_uint(fl.y);
+                                    if (CROLL)        { w0[r] = prmt(w0[r], f0, sel); w1[r] = prmt(w1[r], f1, sel); }
+                                    else if (cc == 0) { w0[r] = f0; w1[r] = f1; }
+                                    else if (cc == 1) { w0[r] = prmt(w0[r], f0, 0x0040); w1[r] = prmt(w1[r], f1, 0x0040); }
+                                    else              { w0[r] = prmt(w0[r], f0, 0xF410); w1[r] = prmt(w1[r], f1, 0xF410); }
+                                    continue;
+                                }
+                                float2 p;
+                                if (CLUT) {
+                                    // 2^23 + code in the low mantissa bits -> D[code] = code / 1023 (correctly rounded, the table of the gamma stage)
+                                    const float2 cb = __fadd2_rd(fma2(val, 1023.0f, 0.5f), bc2(8388608.0f));
+                                    asm("ld.shared.f32 %0, [%1];" : "=f"(p.x) : "r"((__float_as_uint(cb.x) << 2) + KD));
+                                    asm("ld.shared.f32 %0, [%1];" : "=f"(p.y) : "r"((__float_as_uint(cb.y) << 2) + KD));
+                                } else p = div_by_const_exact2<1023>(floor_pos2(fma2(val, 1023.0f, 0.5f)));
                                 const float2 fl = __fadd2_ru(fma2(p, -255.0f, nd[r]), bc2(-8388608.0f));
                                 const uint32_t f0 = __float_as_uint(fl.x), f1 = __float_as_uint(fl.y);
-                                if (cc == 0)      { w0[r] = f0; w1[r] = f1; }                                        // B       (R)
+                                if (CROLL)        { w0[r] = prmt(w0[r], f0, sel); w1[r] = prmt(w1[r], f1, sel); }          // selector per channel (below)
+                                else if (cc == 0) { w0[r] = f0; w1[r] = f1; }                                        // B       (R)
                                 else if (cc == 1) { w0[r] = prmt(w0[r], f0, 0x0040); w1[r] = prmt(w1[r], f1, 0x0040); }   // B, G    (R, G)
                                 else              { w0[r] = prmt(w0[r], f0, 0xF410); w1[r] = prmt(w1[r], f1, 0xF410); }   // B, G, R, 0xFF  (R, G, B, x)
                             }
                         }
+                    };
+                    if (CROLL) {
+                        #pragma unroll
+                        for (int r = 0; r < 8; r++) { w0[r] = 0u; w1[r] = 0u; }
+                        #pragma unroll 1
+                        for (int cc = 0; cc < 3; cc++) channel(cc, cc == 0 ? 0x4444u : (cc == 1 ? 0x0040u : 0xF410u));
+                    } else {
+                        #pragma unroll
+                        for (int cc = 0; cc < 3; cc++) channel(cc, 0u);
                     }
                     const uint32_t opitch = (uint32_t)prm.out.pitch;
                     if (SPEC == SSPEC_10_RGB8_DITHER) {

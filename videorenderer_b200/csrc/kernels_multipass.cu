@@ -667,7 +667,7 @@ __global__ void k_math_probe(int op, const float* __restrict__ x, const float* _
     case 15: r = div_rn_safe_2(make_float2(a, x[(i + 1) % n]), make_float2(y[i], y[(i + 1) % n])).x; break;
     case 16: r = div_rn_safe(a, y[i]); break;
     case 17: r = __fdiv_rn(a, y[i]); break;
-    case 18: r = unorm_roundtrip2(make_float2(a, x[(i + 1) % n]), 1023.0f, 1.0f / 1023.0f).x; break;
+    case 18: r = unorm_roundtrip2<1023>(make_float2(a, x[(i + 1) % n])).x; break;
     case 19: r = rt_roundtrip(MPCVR_SURF_RGB10A2, a); break;
     case 20: r = lg2_2(make_float2(x[(i + 1) % n], a)).y; break;
     case 21: r = powr01_ygt1_2(make_float2(x[(i + 1) % n], a), y[i]).y; break;

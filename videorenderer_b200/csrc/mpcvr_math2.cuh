@@ -138,16 +138,14 @@ __device__ __forceinline__ float2 div_rn_safe_2(float2 x, float2 y)   // == div_
 // floor(z) as an integer-valued float for 0 <= z < 2^22 (FADD.RM on both lanes)
 __device__ __forceinline__ float2 floor_pos2(float2 z) { return add2(__fadd2_rd(z, bc2(8388608.0f)), -8388608.0f); }
 
-__device__ __forceinline__ float2 div_by_const_exact2(float2 c, float n, float rn)
-{
-    const float2 q = mul2(c, rn);
-    return fma2(fma2(make_float2(-q.x, -q.y), n, c), rn, q);
-}
+template <int N>
+__device__ __forceinline__ float2 div_by_const_exact2(float2 c) { return fma2(c, RcpSplit<N>::hi, mul2(c, RcpSplit<N>::lo)); }   // == div_by_const_exact<N> per lane
 
 // float -> UNORM render-target write followed by the UNORM read (what the next pass samples)
-__device__ __forceinline__ float2 unorm_roundtrip2(float2 v, float n, float rn)
+template <int N>
+__device__ __forceinline__ float2 unorm_roundtrip2(float2 v)
 {
-    return div_by_const_exact2(floor_pos2(fma2(sat2(v), n, 0.5f)), n, rn);
+    return div_by_const_exact2<N>(floor_pos2(fma2(sat2(v), (float)N, 0.5f)));
 }
 
 }  // namespace b200vr

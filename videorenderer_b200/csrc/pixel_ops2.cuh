@@ -197,10 +197,46 @@ __device__ __forceinline__ float gamma_q10_thr1(float x, const float* __restrict
     return sD[c];
 }
 
+// gamma + UNORM10 write + read-back with ONE table access (strip kernel, OPT_GAMMA_LUT).  Entry c0 of the table is
+// {T[c0 + 1], D[c0], D[c0 + 1], -}: c0 = floor(1023 * x^(1/2.2)) from the MUFU estimate (error << 1/2 code, so the true code
+// round(1023 * pow) is c0 or c0 + 1), taken as the low mantissa bits of fma.rm(e, 1023, 2^23) -- no F2I, no second dependent
+// load.  The exception float (code one below its neighbours') has c0 = its own code, so "x >= T and x is not the exception"
+// selects for it as well.  k_gamma_verify checks every float of [0,1] against the direct evaluation.
+struct GammaEntry { float t, d0, d1, pad; };
+__device__ __forceinline__ uint32_t gamma_lut_index(float e)            // table index c0 + 0x4B000000 (the bits of 2^23 + c0)
+{
+    float z; asm("fma.rm.f32 %0, %1, 0f447FC000, 0f4B000000;" : "=f"(z) : "f"(e));      // e * 1023 + 2^23, rounded down
+    return __float_as_uint(z);
+}
+__device__ __forceinline__ float gamma_q10_lut_g(float x, const GammaEntry* __restrict__ G, uint32_t exc0)    // generic-pointer form (self-check kernel)
+{
+    float l, e;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(l, 1.0f / 2.2f)));
+    const GammaEntry g = G[gamma_lut_index(e) - 0x4B000000u];
+    return (x >= g.t && __float_as_uint(x) != exc0) ? g.d1 : g.d0;
+}
+// two values; K = shared-memory address of the table - (0x4B000000 << 4) (mod 2^32)
+__device__ __forceinline__ float2 gamma_q10_lut2(float2 x, uint32_t K, uint32_t exc0)
+{
+    float l0, l1, e0, e1;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(x.x));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(x.y));
+    const float2 l = mul2(make_float2(l0, l1), 1.0f / 2.2f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(l.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(l.y));
+    const float2 z = __ffma2_rd(make_float2(e0, e1), bc2(1023.0f), bc2(8388608.0f));
+    const uint32_t a0 = (__float_as_uint(z.x) << 4) + K, a1 = (__float_as_uint(z.y) << 4) + K;
+    float t0, p0, q0, t1, p1, q1, pad;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0), "=f"(p0), "=f"(q0), "=f"(pad) : "r"(a0));
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t1), "=f"(p1), "=f"(q1), "=f"(pad) : "r"(a1));
+    return make_float2((x.x >= t0 && __float_as_uint(x.x) != exc0) ? q0 : p0, (x.y >= t1 && __float_as_uint(x.y) != exc0) ? q1 : p1);
+}
+
 __device__ __forceinline__ float2 rt_roundtrip2(int fmt, float2 v)
 {
-    if (fmt == MPCVR_SURF_RGB10A2) return unorm_roundtrip2(v, 1023.0f, 1.0f / 1023.0f);
-    if (fmt == MPCVR_SURF_BGRA8)   return unorm_roundtrip2(v, 255.0f, 1.0f / 255.0f);
+    if (fmt == MPCVR_SURF_RGB10A2) return unorm_roundtrip2<1023>(v);
+    if (fmt == MPCVR_SURF_BGRA8)   return unorm_roundtrip2<255>(v);
     return make_float2(f16_roundtrip(v.x), f16_roundtrip(v.y));
 }
 
