@@ -92,6 +92,7 @@ typedef StripCfg<128, 8, 6, 10, 4, 8, OPT_GAMMA_LUT> Cfg2;        // 28 warps (P
 typedef StripCfg<128, 8, 8, 10, 2, 8, OPT_GAMMA_LUT> Cfg3;        // 28 warps (P teams of 4)
 typedef StripCfg<128, 8, 4, 12, 4, 8, 0> Cfg6;                    // gamma through T[] / D[] (two dependent loads, F2I), read-back quotient formed: the round-2a form
 typedef StripCfg<128, 8, 4, 12, 4, 8, OPT_GAMMA_LUT> Cfg8;        // single-lookup gamma, read-back quotient formed
+typedef StripCfg<128, 8, 4, 12, 4, 8, OPT_GAMMA_LUT | OPT_C_FUSEDQ | OPT_P_COLS> Cfg12;   // + column-per-thread role P (slower: role P's serial path per group grows)
 typedef StripCfg<128, 8, 4, 16, 4, 8, OPT_GAMMA_LUT> Cfg7;        // 32 warps at 64 registers (role C spills)
 typedef StripCfg<128, 8, 4, 16, 4, 8, OPT_GAMMA_LUT | OPT_SETMAXNREG> Cfg9;        // 32 warps, registers P/B 40, A 64, C 88
 typedef StripCfg<128, 8, 4, 12, 4, 12, OPT_GAMMA_LUT | OPT_SETMAXNREG> Cfg10;      // 32 warps, registers P/B 40, A 64, C 80
@@ -115,6 +116,7 @@ static cudaError_t LaunchV(const StripParams& prm, int spec, int conv, int grid,
             case 9:  return LaunchK<Cfg9, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             case 10: return LaunchK<Cfg10, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             case 11: return LaunchK<Cfg11, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
+            case 12: return LaunchK<Cfg12, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             case 13: return LaunchK<Cfg13, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             default: break;
             }

@@ -93,6 +93,14 @@ __device__ __forceinline__ bool mbar_try_hint(uint32_t bar, uint32_t parity)
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"((unsigned)MPCVR_STRIP_WAIT_HINT_NS) : "memory");
     return ok != 0;
 }
+// the watchdog record is cold code: kept out of line so that the roles' loops stay small (the SM's instruction cache holds four of them)
+__device__ __noinline__ void strip_wait_failed(uint32_t bar, uint32_t parity, int it)
+{
+    if (atomicAdd(&g_stripStatus[0], 1u) == 0) {
+        g_stripStatus[1] = (bar & 255u) >> 3; g_stripStatus[2] = parity; g_stripStatus[3] = (unsigned)it;
+        g_stripStatus[4] = blockIdx.x; g_stripStatus[5] = threadIdx.x >> 5;
+    }
+}
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int it, uint32_t wns)
 {
     if (mbar_try(bar, parity)) return true;
@@ -108,10 +116,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int it,
         for (int n = 0; n < (1 << 17); n++)
             if (mbar_try_hint(bar, parity)) return true;
     }
-    if (atomicAdd(&g_stripStatus[0], 1u) == 0) {
-        g_stripStatus[1] = (bar & 255u) >> 3; g_stripStatus[2] = parity; g_stripStatus[3] = (unsigned)it;
-        g_stripStatus[4] = blockIdx.x; g_stripStatus[5] = threadIdx.x >> 5;
-    }
+    strip_wait_failed(bar, parity, it);
     return false;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar)
@@ -130,7 +135,8 @@ enum { OPT_GAMMA_LUT = 1,         // role A: gamma + UNORM10 through ONE 16-byte
        OPT_SETMAXNREG = 2,
        OPT_C_LUT = 4,
        OPT_C_ROLL = 8,            // role C: channel loop not unrolled (instruction-cache footprint)
-       OPT_C_FUSEDQ = 16 };       // role C: UNORM10 read-back and final pass as ONE fma on the integer code (see kFinalK1 below)
+       OPT_C_FUSEDQ = 16,
+       OPT_P_COLS = 32 };         // role P: one column pair per thread, rows in a loop (no index divisions; the UNORM reads in the packed lanes)       // role C: UNORM10 read-back and final pass as ONE fma on the integer code (see kFinalK1 below)
 
 // m_TexsPostScale (RGB10A2) read-back followed by ps_final_pass on an 8-bit target:  out = floor(fma(RN(c / 1023), 255, d)),  c the
 // 10-bit code, d = k / 1024 the dither threshold.  For every one of the 1024 x 1024 (c, k) pairs this equals
@@ -354,6 +360,64 @@ k_strip2x(const __grid_constant__ StripParams prm)
             if (!mbar_wait(sbase + 8 * (B_RAWFULL + slot), (it / C::NRAW) & 1, it, wns)) return;
             if (!mbar_wait(sbase + 8 * (B_PREPEMPTY + pslot), ((it / C::NS) & 1) ^ 1, it, wns)) return;
             if (!(prm.dbg_skip & 1)) {
+            if constexpr ((C::OPT & OPT_P_COLS) != 0) {
+            // ---- column-per-thread form: thread tP owns column pair (texel column) tP of every row, so nothing is divided and the
+            // column terms stay in registers; the 4 (8) columns beyond the 64th are one extra pass of a few lanes.  Same operations
+            // per value as the flat loops below.
+            static_assert(C::PAIRS - TP == 4 && C::CP - TP == 8 && TP == 64, "column-per-thread role P: 64 threads, 68 pairs, 72 texels");
+            const int lp = prm.luma_pitch, cpch = prm.chroma_pitch;
+            // P0: luma codes -> floats (UNORM read)
+            auto luma = [&](int r, int p) {
+                float2 cfl;
+                if (bytes == 2) { const uint16_t* q = reinterpret_cast<const uint16_t*>(rawY + r * lp) + xoff + 2 * p; cfl = make_float2((float)q[0], (float)q[1]); pY[r * C::PAIRS + p] = div_by_const_exact2<65535>(cfl); }
+                else            { const uint8_t* q = rawY + r * lp + xoff + 2 * p; cfl = make_float2((float)q[0], (float)q[1]); pY[r * C::PAIRS + p] = div_by_const_exact2<255>(cfl); }
+            };
+            #pragma unroll 4
+            for (int r = 0; r < rows; r++) luma(r, tP);
+            if (tP >= 32 && ((tP - 32) >> 2) < rows) luma((tP - 32) >> 2, 64 + (tP & 3));
+            // P1: chroma texels -> floats, sampler CLAMP at the plane borders (interior boxes skip the clamps)
+            const bool cedge = ux0 < 0 || uy0 < 0 || ux0 + C::CP > prm.cw || uy0 + RC > prm.ch;
+            auto texel = [&](int rr, int c) {
+                int cl = c + uoff, rl = rr;
+                if (cedge) {
+                    cl = min(max(min(max(ux0 + c, 0), prm.cw - 1) - ux0 + uoff, 0), cbox - 1);
+                    rl = min(max(min(max(uy0 + rr, 0), prm.ch - 1) - uy0, 0), RC - 1);
+                }
+                float2 uv;
+                if (bytes == 2) { const uint32_t w = *reinterpret_cast<const uint32_t*>(rawC + rl * cpch + 4 * cl); uv = div_by_const_exact2<65535>(make_float2((float)(w & 0xFFFFu), (float)(w >> 16))); }
+                else            { const uint32_t w = *reinterpret_cast<const uint16_t*>(rawC + rl * cpch + 2 * cl); uv = div_by_const_exact2<255>(make_float2((float)(w & 255u), (float)(w >> 8))); }
+                sCu[rr * C::CP + c] = uv.x; sCv[rr * C::CP + c] = uv.y;
+            };
+            for (int rr = 0; rr < RC; rr++) texel(rr, tP);
+            for (int j = tP; j < 8 * RC; j += TP) texel(j >> 3, 64 + (j & 7));
+            named_bar(1 + team, TP);
+            // P2: horizontal bilinear reconstruction at the luma columns (top / bot of the bilinear sample)
+            auto hrec = [&](int rr, int p) {
+                const int qx0 = 2 * (X0 + 2 * p) + ox, qx1 = qx0 + 2;
+                const int t0 = rr * C::CP + (qx0 >> 2) - ux0, t1 = rr * C::CP + (qx1 >> 2) - ux0;
+                const float2 fx = make_float2((float)(qx0 & 3) * 0.25f, (float)(qx1 & 3) * 0.25f);
+                const float2 ua = make_float2(sCu[t0], sCu[t1]), ub = make_float2(sCu[t0 + 1], sCu[t1 + 1]);
+                const float2 va = make_float2(sCv[t0], sCv[t1]), vb = make_float2(sCv[t0 + 1], sCv[t1 + 1]);
+                reinterpret_cast<float2*>(sHU)[rr * C::PAIRS + p] = fma2(fx, sub2(ub, ua), ua);
+                reinterpret_cast<float2*>(sHV)[rr * C::PAIRS + p] = fma2(fx, sub2(vb, va), va);
+            };
+            for (int rr = 0; rr < RC; rr++) hrec(rr, tP);
+            if (tP < 4 * RC) hrec(tP >> 2, 64 + (tP & 3));
+            named_bar(1 + team, TP);
+            // P3: vertical interpolation at the luma rows
+            auto vrec = [&](int r, int p) {
+                const int qy = my * (sy0 + r) + oy;
+                const int h0 = ((qy >> 2) - uy0) * C::PAIRS + p;
+                const float fy = (float)(qy & 3) * 0.25f;
+                const float2 ut = reinterpret_cast<const float2*>(sHU)[h0], ub = reinterpret_cast<const float2*>(sHU)[h0 + C::PAIRS];
+                const float2 vt = reinterpret_cast<const float2*>(sHV)[h0], vb = reinterpret_cast<const float2*>(sHV)[h0 + C::PAIRS];
+                pU[r * C::PAIRS + p] = fma2(fy, sub2(ub, ut), ut);
+                pV[r * C::PAIRS + p] = fma2(fy, sub2(vb, vt), vt);
+            };
+            #pragma unroll 4
+            for (int r = 0; r < rows; r++) vrec(r, tP);
+            if (tP >= 32 && ((tP - 32) >> 2) < rows) vrec((tP - 32) >> 2, 64 + (tP & 3));
+            } else {
             // P0: luma codes -> floats (UNORM read)
             for (int k = tP; k < rows * C::PAIRS; k += TP) {
                 const int r = k / C::PAIRS, p = k - r * C::PAIRS;
@@ -408,6 +472,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
                 pV[k] = fma2(fy, sub2(vb, vt), vt);
             }
             }
+            }
             __syncwarp();
             if (lane == 0) { mbar_arrive(sbase + 8 * (B_RAWEMPTY + slot)); mbar_arrive(sbase + 8 * (B_PREPFULL + pslot)); }
         }
@@ -424,8 +489,8 @@ k_strip2x(const __grid_constant__ StripParams prm)
         // base + constant again (an entry's address is then a single LEA on the float's bits)
         uint32_t K; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(K) : "r"(sbase + 240u));
 
-        for (int it = 0; gi.valid; it++, gi.advance()) {
-            const int slot = it % C::NS; const uint32_t ph = (it / C::NS) & 1;
+        int slot = 0; uint32_t ph = 0;                                 // ring slot it % NS and its phase (it / NS) & 1, kept as counters
+        for (int it = 0; gi.valid; it++, gi.advance(), ph ^= (slot + 1 == C::NS), slot = (slot + 1 == C::NS) ? 0 : slot + 1) {
             const int items = gi.rows() * C::PAIRS;
             const float2* pY = reinterpret_cast<const float2*>(smem + C::oPrep + (slot * 3 + 0) * C::szPlane);
             const float2* pU = reinterpret_cast<const float2*>(smem + C::oPrep + (slot * 3 + 1) * C::szPlane);
@@ -455,7 +520,7 @@ k_strip2x(const __grid_constant__ StripParams prm)
                     c0[k] = rt_roundtrip2(IFMT, rgb.x); c1[k] = rt_roundtrip2(IFMT, rgb.y); c2[k] = rt_roundtrip2(IFMT, rgb.z);
                 }
             }
-            stream = (stream + items) % TA;
+            stream += items; while (stream >= TA) stream -= TA;
             __syncwarp();
             if (lane == 0) { mbar_arrive(sbase + 8 * (B_CONVFULL + slot)); mbar_arrive(sbase + 8 * (B_PREPEMPTY + slot)); }
         }
@@ -500,7 +565,12 @@ k_strip2x(const __grid_constant__ StripParams prm)
         #pragma unroll
         for (int k = 0; k < NT; k++) { wE[k] = prm.wE[k]; wO[k] = prm.wO[k]; }
         GroupIter<C, NT> gi; gi.init(Q0, Q1, prm.nq, prm.b0, prm.h1);
-        int qnext = 0, it0 = 0, turn = 0;                                // turn: items handed out so far, modulo NC
+        // items (quad, column block) go round the NC warps: with NC a multiple of CB a warp always takes column block wc % CB, of every
+        // (NC / CB)-th quad -- qphase counts quads modulo NC / CB
+        static_assert(C::NC % C::CB == 0, "role C hands out the column blocks of a quad to consecutive warps");
+        constexpr int QCYC = C::NC / C::CB;
+        const int myphase = wc / C::CB, cb = wc % C::CB;
+        int qnext = 0, it0 = 0, qphase = 0;
         uint32_t KD;       // address of D[] - (0x4B000000 << 2) as one register (OPT_C_LUT), see K in role A
         asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(KD) : "r"(sbase + 244u));
 
@@ -510,9 +580,9 @@ k_strip2x(const __grid_constant__ StripParams prm)
             // ---- Y pass + rounding + final pass for the quads whose rows are now complete; item = (quad, column block)
             const int cyLast = gi.cy0() + gi.rows() - 1;
             for (; qnext < gi.qb && min(4 * qnext + 3 + prm.b0 + NT, prm.h1 - 1) <= cyLast; qnext++) {
-              for (int cb = 0; cb < C::CB; cb++) {
-                const bool mine = turn == wc;
-                turn = (turn + 1 == C::NC) ? 0 : turn + 1;
+              {
+                const bool mine = qphase == myphase;
+                qphase = (qphase + 1 == QCYC) ? 0 : qphase + 1;
                 if (!mine || (prm.dbg_skip & 8)) continue;
                 const int q = qnext;
                 const int col = gi.s * C::SW + 32 * cb + lane;                     // convert-surface column of this lane's output pair
