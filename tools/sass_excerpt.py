@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""tools/sass_excerpt.py -> profiles/r02_sass_kernels.txt
+"""tools/sass_excerpt.py -> profiles/r02b_sass_kernels.txt
 Mnemonic census (cuobjdump -sass of the built library) of the kernels the bench configs run, with the first lines around the
 TMA / mbarrier / 128-bit memory instructions, so the instruction-level claims in DESIGN.md can be checked without a GPU."""
 import collections, hashlib, os, re, subprocess, sys
@@ -40,7 +40,7 @@ def main():
                 if cls in ln and shown < 3:
                     out.append(re.sub(r"\s+/\* 0x[0-9a-f]+ \*/", "", ln)); shown += 1
         out.append("")
-    open(os.path.join(ROOT, "profiles", "r02_sass_kernels.txt"), "w").write("\n".join(out))
+    open(os.path.join(ROOT, "profiles", "r02b_sass_kernels.txt"), "w").write("\n".join(out))
     print("\n".join(out)[:6000])
 
 if __name__ == "__main__":
