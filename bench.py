@@ -414,6 +414,13 @@ def main():
                 roof["issue"] = {"bound": "instruction issue", "warp_instr_per_launch": wi, "achieved": wi / (kernel_ms * 1e-3) / 1e9,
                                  "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": wi / (kernel_ms * 1e-3) / issue_peak,
                                  "source": "profiles/capture_c2.json"}
+                pk2 = cap.get("packed_warp_instr_per_launch")
+                if pk2:
+                    # measured issue cost of this instruction mix on sm_100a (tools/role_bench.cu): a packed FFMA2-class
+                    # instruction ~2.35 scheduler cycles, any other ~1.1; 148 SMs x 4 schedulers
+                    model_s = (2.35 * pk2 + 1.1 * (wi - pk2)) / (148 * 4 * sm_hz)
+                    roof["issue"]["cost_model"] = {"packed_warp_instr_per_launch": int(pk2), "model_us_per_launch": model_s * 1e6,
+                                                   "frac_of_model_rate": model_s / (kernel_ms * 1e-3)}
         except Exception as e:
             roof["traffic_source"] = "capture unreadable: %r" % (e,)
     e2e_d2h_gbs = OUT_BYTES * e2e_fps / world / 1e9     # per GPU; the D2H of the 8K frame is the e2e bottleneck (PCIe)

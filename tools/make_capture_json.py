@@ -35,6 +35,15 @@ def main():
                "issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]), "registers_per_thread": int(float(d["launch__registers_per_thread"])),
                "csrc_sha256": csrc_sha256()}
         cap["dram_bytes_per_launch"] = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+        # packed fp32 instructions (two FMA-pipe cycles each) from the source page of the same report: the input of the issue-cost model
+        # in DESIGN.md 4.1 (about 2.35 scheduler cycles per packed, 1.1 per other warp instruction; tools/role_bench.cu)
+        try:
+            src = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout)))
+            hi = [i for i, r in enumerate(src) if "Instructions Executed" in r][0]
+            ia, isrc = src[hi].index("Instructions Executed"), src[hi].index("Source")
+            cap["packed_warp_instr_per_launch"] = sum(int(r[ia]) for r in src[hi + 1:] if len(r) > ia and r[ia].isdigit() and re.search(r"\b(FFMA2|FADD2|FMUL2)\b", r[isrc]))
+        except Exception:
+            pass
         json.dump(cap, open(os.path.join(ROOT, "profiles", "capture_c2.json"), "w"), indent=1)
         print(json.dumps(cap, indent=1)); return 0
     print("no kernel matching", pat.pattern); return 1
