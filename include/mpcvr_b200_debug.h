@@ -46,9 +46,10 @@ int32_t mpcvr_debug_set_gamma_table(int32_t enable);
 int32_t mpcvr_debug_set_fused1x_vector(int32_t enable);
 /* process-wide: enable = 1 (default) lets exact-2x plans of bi-planar sources run the persistent warp-specialised kernel (TMA-staged
  * source rows), 0 keeps them on the tile kernel.  cfg, low byte: configuration of the headline variant (kernel_strip.cu) -- 0 the
- * product's; 1-3 other warp-role splits; 6 gamma through the two-array table and the read-back quotient formed (round-2a arithmetic);
+ * product's (32 warps, role P as two teams of four, setmaxnreg register budgets); 1-3 other warp-role splits; 6 gamma through the two-array table and the read-back quotient formed (round-2a arithmetic);
  * 7 32 warps at 64 registers; 8 single-lookup gamma only; 9, 10 32 warps with setmaxnreg budgets; 11 table read-back in role C;
- * 12 column-per-thread role P; 13 rolled channel loop in role C -- all bit-identical; 4, 5 = relaxed float stage, measurement only, NOT
+ * 12 column-per-thread role P; 13 rolled channel loop in role C; 14 the 28-warp kernel (72 registers, role P as two teams of two warps)
+ * -- all bit-identical; 4, 5 = relaxed float stage, measurement only, NOT
  * bit-exact.  Bits 8-11: role-isolation mask (P, A, B, C keep their handshakes but skip their arithmetic); bits 12-15: poll with
  * nanosleep(16 << n) instead of the suspend hint. */
 int32_t mpcvr_debug_set_strip_kernel(int32_t enable, int32_t cfg);

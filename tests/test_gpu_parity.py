@@ -911,11 +911,11 @@ def test_strip_kernel_equals_tile_kernel_and_oracle(case):
     assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 6, 7, 8, 9, 10, 11, 12, 13])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 6, 7, 8, 9, 10, 11, 12, 13, 14])
 def test_strip_kernel_role_splits_give_the_same_frame(cfg):
     """every selectable configuration of the strip kernel (kernel_strip.cu: warp splits 1-3; 6 = gamma through T[] / D[] with the
     read-back quotient formed; 7 = 32 warps; 8 = single-lookup gamma only; 9, 10 = setmaxnreg register budgets; 11 = table read-back in
-    role C; 12 = column-per-thread role P; 13 = rolled channel loop) renders the oracle's frame -- the measured-and-rejected variants of
+    role C; 12 = column-per-thread role P; 13 = rolled channel loop; 14 = the 28-warp kernel) renders the oracle's frame -- the measured-and-rejected variants of
     DESIGN.md 4.1 stay honest"""
     case = H.baseline_cases(scale=0.25)[1]
     codes = H.make_codes(case.cf, case.w, case.h, "natural", 77)

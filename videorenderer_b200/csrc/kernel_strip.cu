@@ -86,7 +86,7 @@ static cudaError_t LaunchK(const StripParams& prm, int grid, cudaStream_t st)
 
 // Configurations measured on B200 (C2 frame; DESIGN.md 4.1, profiles/r02_strip_experiments.txt).  Cfg0 is what the product runs; the
 // others stay selectable through mpcvr_debug_set_strip_kernel so that the measurements can be repeated -- every one is bit-identical.
-typedef StripCfg<128, 8, 4, 12, 4, 8, OPT_GAMMA_LUT | OPT_C_FUSEDQ> Cfg0;        // 28 warps: 4 P (two teams of 2) + 12 A + 4 B + 8 C; single-lookup gamma table
+typedef StripCfg<128, 8, 4, 12, 4, 8, OPT_GAMMA_LUT | OPT_C_FUSEDQ> Cfg0;        // 28 warps at 72 registers: 4 P (two teams of 2) + 12 A + 4 B + 8 C; every other instantiation runs this one
 typedef StripCfg<128, 8, 4, 10, 4, 8, OPT_GAMMA_LUT> Cfg1;        // 26 warps
 typedef StripCfg<128, 8, 6, 10, 4, 8, OPT_GAMMA_LUT> Cfg2;        // 28 warps (P teams of 3)
 typedef StripCfg<128, 8, 8, 10, 2, 8, OPT_GAMMA_LUT> Cfg3;        // 28 warps (P teams of 4)
@@ -97,6 +97,9 @@ typedef StripCfg<128, 8, 4, 16, 4, 8, OPT_GAMMA_LUT> Cfg7;        // 32 warps at
 typedef StripCfg<128, 8, 4, 16, 4, 8, OPT_GAMMA_LUT | OPT_SETMAXNREG> Cfg9;        // 32 warps, registers P/B 40, A 64, C 88
 typedef StripCfg<128, 8, 4, 12, 4, 12, OPT_GAMMA_LUT | OPT_SETMAXNREG> Cfg10;      // 32 warps, registers P/B 40, A 64, C 80
 typedef StripCfg<128, 8, 4, 12, 4, 8, OPT_GAMMA_LUT | OPT_C_LUT> Cfg11;            // + UNORM10 read-back of role C from the table (FMA pipe -> LSU)
+// the product's configuration of the two PQ / 10-bit / dithered instantiations (BASELINE C2, C5): 32 warps -- role P as two teams of FOUR
+// warps (its serial path per row group is what the other roles wait for when it slips), registers by setmaxnreg: P / B 40, A 64, C 96
+typedef StripCfg<128, 8, 8, 12, 4, 8, OPT_GAMMA_LUT | OPT_C_FUSEDQ | OPT_SETMAXNREG> CfgP;
 typedef StripCfg<128, 8, 4, 12, 4, 8, OPT_GAMMA_LUT | OPT_C_ROLL> Cfg13;           // + rolled channel loop in role C (instruction-cache footprint)
 
 template <int NT, bool DUP>
@@ -117,13 +120,14 @@ static cudaError_t LaunchV(const StripParams& prm, int spec, int conv, int grid,
             case 10: return LaunchK<Cfg10, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             case 11: return LaunchK<Cfg11, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             case 12: return LaunchK<Cfg12, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
+            case 14: return LaunchK<Cfg0, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);    // the 28-warp kernel (product until round 2b's last step)
             case 13: return LaunchK<Cfg13, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
             default: break;
             }
         }
-        return LaunchK<Cfg0, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
+        return LaunchK<CfgP, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_PQ_THR>(prm, grid, st);
     }
-    if (spec == SSPEC_10_RGB8_DITHER && conv == SCONV_PQ_THR) return LaunchK<Cfg0, NT, DUP, SSPEC_10_RGB8_DITHER, SCONV_PQ_THR>(prm, grid, st);
+    if (spec == SSPEC_10_RGB8_DITHER && conv == SCONV_PQ_THR) return LaunchK<CfgP, NT, DUP, SSPEC_10_RGB8_DITHER, SCONV_PQ_THR>(prm, grid, st);
     if (spec == SSPEC_10_BGRA8_DITHER) return LaunchK<Cfg0, NT, DUP, SSPEC_10_BGRA8_DITHER, SCONV_ANY>(prm, grid, st);
     if (spec == SSPEC_8_BGRA8)         return LaunchK<Cfg0, NT, DUP, SSPEC_8_BGRA8, SCONV_ANY>(prm, grid, st);
     if (conv == SCONV_PQ)              return LaunchK<Cfg0, NT, DUP, SSPEC_RUNTIME, SCONV_PQ>(prm, grid, st);
