@@ -42,7 +42,8 @@ int32_t mpcvr_debug_get_plan(mpcvr* vp, mpcvr_plan_info* info);
 /* PS_COLOR_TRANSFORM cm_r,cm_g,cm_b (row-major 3x3) + cm_c, and matrix_conv_prim */
 /* process-wide: 1 (default) lets the fused 2x PQ kernel use the gamma+UNORM10 threshold table, 0 forces the direct pow */
 int32_t mpcvr_debug_set_gamma_table(int32_t enable);
-/* process-wide: 1 (default) lets 1:1 plans of bi-planar sources run the 128-bit span kernel, 0 keeps one pixel per thread */
+/* process-wide: 1 (default) lets 1:1 plans of bi-planar sources run the span kernel (8 pixels per thread), 0 keeps one pixel per
+ * thread, 2 = the span kernel with 16 pixels per thread for 8-bit sources (the round-2a form) */
 int32_t mpcvr_debug_set_fused1x_vector(int32_t enable);
 /* process-wide: enable = 1 (default) lets exact-2x plans of bi-planar sources run the persistent warp-specialised kernel (TMA-staged
  * source rows), 0 keeps them on the tile kernel.  cfg, low byte: configuration of the headline variant (kernel_strip.cu) -- 0 the

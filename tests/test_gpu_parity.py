@@ -1076,12 +1076,12 @@ def test_fused_1x_span_kernel_equals_the_pixel_kernel(name, ex, siting):
             ref = H.run_oracle(case, planes, pitches)
             outs = []
             try:
-                for on in (1, 0):
+                for on in (1, 0, 2):                    # span kernel (8 pixels per thread), pixel kernel, span kernel with 16 pixels per thread
                     vp = case.make_processor(device=0, path=PATH_FUSED)
                     vp.debug_set_fused1x_vector(on)
                     vp.ProcessSample(data=buf, pitch=pitch)
                     outs.append(vp.ReadBackbuffer())
             finally:
                 vp.debug_set_fused1x_vector(1)
-            assert np.array_equal(outs[0], outs[1]), (name, siting, g, tex, bb)
+            assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]), (name, siting, g, tex, bb)
             assert H.compare(outs[0], ref, bb) == (0, 0), (name, siting, g, tex, bb)

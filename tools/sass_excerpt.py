@@ -5,7 +5,7 @@ TMA / mbarrier / 128-bit memory instructions, so the instruction-level claims in
 import collections, hashlib, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "videorenderer_b200", "libmpcvr_b200.so")
-WANT = [("k_strip2x (C2 frame kernel, product configuration: 32 warps, OPT 19 = gamma table + fused final pass + setmaxnreg)", r"k_strip2xINS_8StripCfgILi128ELi8ELi8ELi12ELi4ELi8ELi19EEELi6ELb1ELi1ELi0E"), ("k_fused1x_bp<1> (C1 frame kernel)", r"k_fused1x_bpILi1E"),
+WANT = [("k_strip2x (C2 frame kernel, product configuration: 32 warps, OPT 19 = gamma table + fused final pass + setmaxnreg)", r"k_strip2xINS_8StripCfgILi128ELi8ELi8ELi12ELi4ELi8ELi19EEELi6ELb1ELi1ELi0E"), ("k_fused1x_bp<1, 8> (C1 frame kernel)", r"k_fused1x_bpILi1ELi8E"),
         ("k_fused2x (round-1 tile kernel, 6 taps)", r"k_fused2xILi6E"), ("k_convert_bp<2,false> (C4 convert pass)", r"k_convert_bpILi2ELb0E"), ("k_convert_bp<1,true> (C3 convert pass, YUY2)", r"k_convert_bpILi1ELb1E"),
         ("k_resize_p<9,16F,16F,X,conv> (C4 X pass)", r"k_resize_pILi9ELi2ELi2ELi0ELb1E"), ("k_resize_p<4,16F,16F,Y,interp> (C3 Y pass)", r"k_resize_pILi4ELi2ELi2ELi1ELb0E"), ("k_final_p<16F,RGB10A2> (C3 final pass)", r"k_final_pILi2ELi1E")]
 KEY = ["UTMALDG", "UTMAPF", "USETMAXREG", "SYNCS", "NANOSLEEP", "BAR.SYNC", "FFMA2", "FMUL2", "FADD2", "FFMA", "FMUL", "FADD", "MUFU", "PRMT", "LDG.E.128", "LDG.E.64", "LDG.E.U16", "LDG.E.U8", "STG.E.128", "STG.E.64", "STG.E",

@@ -102,7 +102,7 @@ int64_t mpcvr_debug_verify_gamma_table(mpcvr* h) { VP_OR(-2); return vp.DebugVer
 int32_t mpcvr_debug_set_resize_four(int32_t enable) { b200vr::SetResizeFour(enable); return MPCVR_S_OK; }
 int32_t mpcvr_debug_set_convert_two_lane(int32_t enable) { b200vr::SetConvertTwoLane(enable); return MPCVR_S_OK; }
 int32_t mpcvr_debug_set_gamma_table(int32_t enable) { b200vr::SetGammaTableEnabled(enable != 0); return MPCVR_S_OK; }
-int32_t mpcvr_debug_set_fused1x_vector(int32_t enable) { b200vr::SetFused1xVector(enable != 0); return MPCVR_S_OK; }
+int32_t mpcvr_debug_set_fused1x_vector(int32_t enable) { b200vr::SetFused1xVector(enable); return MPCVR_S_OK; }    // 0 per-pixel kernel, 1 span kernel, 2 span kernel with 16 pixels per thread (8-bit sources)
 int32_t mpcvr_debug_set_strip_kernel(int32_t enable, int32_t cfg) { b200vr::SetStripKernel(enable != 0, cfg); return MPCVR_S_OK; }
 int32_t mpcvr_debug_strip_status(uint32_t out8[8], int32_t clear) { return b200vr::StripStatus(out8, clear) == 0 ? MPCVR_S_OK : MPCVR_E_FAIL; }
 int32_t mpcvr_debug_fmt_params(int32_t cformat, int32_t out[12])

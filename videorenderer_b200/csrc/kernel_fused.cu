@@ -514,11 +514,22 @@ __device__ __forceinline__ void fused1x_span(const Fused1xParams& prm, const flo
 // k_fused1x (fetch_planar's bilinear branch, convert_color, rt_roundtrip, final_quant, surf_store's quantiser), so the frame is bit-identical;
 // what changes is the number of memory instructions and of texel conversions per pixel.  Threads whose span touches the right edge of the
 // rect, and plans that are not 16-byte aligned, use k_fused1x's per-pixel path.
-template <int BYTES>
+// NB-byte load of one span's worth of a plane row (NB = 16: one 128-bit load, NB = 8: one 64-bit load) into w[0 .. NB/4)
+template <int NB>
+__device__ __forceinline__ void load_span_words(const uint8_t* p, uint32_t (&w)[4])
+{
+    if (NB == 16) { const uint4 v = __ldg(reinterpret_cast<const uint4*>(p)); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+    else          { const uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); w[0] = v.x; w[1] = v.y; w[2] = 0u; w[3] = 0u; }
+}
+
+// PX pixels per thread: 8 for both component sizes in the product (an 8-bit 1080p frame then has 260 k threads instead of 130 k -- the
+// kernel is latency-bound, ncu: 23 % issue utilisation at 16 pixels per thread); <1, 16> stays selectable (mpcvr_debug_set_fused1x_vector(2))
+template <int BYTES, int PX>
 __global__ void __launch_bounds__(128)
 k_fused1x_bp(const __grid_constant__ Fused1xParams prm)
 {
-    constexpr int PX = 16 / BYTES;                               // pixels per thread: 16 (8-bit) or 8 (16-bit)
+    static_assert(PX * BYTES == 16 || PX * BYTES == 8, "one 128-bit or 64-bit load per plane row and span");
+    constexpr int NB = PX * BYTES;
     const SrcDesc& S = prm.src;
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y;
     if (x0 >= prm.w1) return;
@@ -541,11 +552,11 @@ k_fused1x_bp(const __grid_constant__ Fused1xParams prm)
         }
         return;
     }
-    // ---- luma: one 128-bit load
+    // ---- luma: one 128-bit (64-bit) load
     float Y[PX];
     {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(S.pl[0] + (ptrdiff_t)sy * S.pitch[0] + (size_t)sx0 * BYTES));
-        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        uint32_t w[4];
+        load_span_words<NB>(S.pl[0] + (ptrdiff_t)sy * S.pitch[0] + (size_t)sx0 * BYTES, w);
         #pragma unroll
         for (int i = 0; i < PX; i++)
             Y[i] = BYTES == 1 ? unorm8((w[i >> 2] >> (8 * (i & 3))) & 255u) : unorm16((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
@@ -560,8 +571,8 @@ k_fused1x_bp(const __grid_constant__ Fused1xParams prm)
     #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
         const uint8_t* row = S.pl[1] + (ptrdiff_t)(rr ? r1 : r0) * S.pitch[1];
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + (size_t)t0 * 2 * BYTES));          // texels t0 .. t0 + PX/2 - 1
-        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        uint32_t w[4];
+        load_span_words<NB>(row + (size_t)t0 * 2 * BYTES, w);                                           // texels t0 .. t0 + PX/2 - 1
         #pragma unroll
         for (int i = 0; i < PX / 2; i++) {
             if (BYTES == 1) { const uint32_t c = (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu; T[rr][1 + i] = make_float2(unorm8(c & 255u), unorm8(c >> 8)); }
@@ -603,7 +614,7 @@ static bool Fused1xVectorOk(const FusedPlan& p)
     if (S.layout != LAYOUT_BIPLANAR || S.chroma_mode != MPCVR_CHROMA_Bilinear || S.deint_blend || S.lsb_shift != 0) return false;
     if ((S.subsampling != 420 && S.subsampling != 422) || (S.bytes != 1 && S.bytes != 2)) return false;
     if (p.color.transfer != TRANSFER_NONE) return false;          // matrix-only convert bodies (see fused1x_span)
-    const int px = 16 / S.bytes;
+    const int px = 16 / S.bytes;                                 // the alignment rule of the widest variant (16 bytes per span)
     if (((uintptr_t)S.pl[0] & 15) || ((uintptr_t)S.pl[1] & 15) || S.pitch[0] <= 0 || S.pitch[1] <= 0 || (S.pitch[0] & 15) || (S.pitch[1] & 15)) return false;
     if ((S.rect_l % px) != 0) return false;
     if (p.out.fmt != MPCVR_SURF_BGRA8 && p.out.fmt != MPCVR_SURF_RGB10A2 && p.out.fmt != MPCVR_SURF_RGBA16F) return false;
@@ -930,9 +941,11 @@ cudaError_t LaunchFused(const FusedPlan& p, cudaStream_t st, int* launches)
         q.internal_fmt = p.internal_fmt; q.final_pass = p.final_pass; q.Q = p.Q;
         if (launches) *launches = 1;
         if (g_fused1xVector && Fused1xVectorOk(p)) {
-            const int px = 16 / p.src.bytes, spans = (q.w1 + px - 1) / px;
+            const int px = (p.src.bytes == 1 && g_fused1xVector == 2) ? 16 : 8, spans = (q.w1 + px - 1) / px;
             const dim3 b(128, 1), g((spans + 127) / 128, q.h1);
-            if (p.src.bytes == 1) k_fused1x_bp<1><<<g, b, 0, st>>>(q); else k_fused1x_bp<2><<<g, b, 0, st>>>(q);
+            if (p.src.bytes == 2)  k_fused1x_bp<2, 8><<<g, b, 0, st>>>(q);
+            else if (px == 16)     k_fused1x_bp<1, 16><<<g, b, 0, st>>>(q);
+            else                   k_fused1x_bp<1, 8><<<g, b, 0, st>>>(q);
             return cudaGetLastError();
         }
         const dim3 b(32, 8), g((q.w1 + 31) / 32, (q.h1 + 7) / 8);

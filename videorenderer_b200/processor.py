@@ -248,7 +248,7 @@ class VideoProcessor:
         self._check(self._L.mpcvr_debug_render_n(self._h, int(n)), "debug_render_n")
 
     def debug_set_fused1x_vector(self, enable):
-        return self._L.mpcvr_debug_set_fused1x_vector(int(bool(enable)))
+        return self._L.mpcvr_debug_set_fused1x_vector(int(enable))
 
     def debug_set_strip_kernel(self, enable, cfg=0):
         return self._L.mpcvr_debug_set_strip_kernel(int(bool(enable)), int(cfg))
