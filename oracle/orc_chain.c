@@ -59,6 +59,24 @@ int orc_scaler_kind(int src, int dst, int bInterpolateAt50pct)
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
 
+/* The PS_DOVI_CURVE constants the oracle derives from Dolby Vision reshaping metadata (SPEC mode's build_dovi: the restatement of
+ * SetShaderDoviCurves / SetShaderDoviCurvesPoly, DX11VideoProcessor.cpp:990-1122), handed out so that tests/test_reference_dovi_pin.py
+ * can compare them with the reference's own functions compiled in place (oracle/_ref/libref_dovi.so).  par[c] = {methods, mmr_single,
+ * min_order, max_order}. */
+int orc_test_dovi_curves(const orc_dovi* dv, float piv[3][7], float coef[3][8][4], float mmr[3][48][4], int32_t par[3][4])
+{
+    static cparams_spec P;                  /* large (mmr tables): static; the tests call this from one thread */
+    memset(&P, 0, sizeof(P));
+    build_dovi_spec(dv, &P, 100);
+    for (int c = 0; c < 3; c++) {
+        for (int i = 0; i < 7; i++) piv[c][i] = (float)P.dv_pivots[c][i];
+        for (int i = 0; i < 8; i++) for (int k = 0; k < 4; k++) coef[c][i][k] = (float)P.dv_coeffs[c][i][k];
+        for (int i = 0; i < 48; i++) for (int k = 0; k < 4; k++) mmr[c][i][k] = (float)P.dv_mmr[c][i][k];
+        par[c][0] = P.dv_methods[c]; par[c][1] = P.dv_mmr_single[c]; par[c][2] = P.dv_min_order[c]; par[c][3] = P.dv_max_order[c];
+    }
+    return P.dovi_mmr;
+}
+
 /* Level 1 (+ Level 3 offsets) of the Dolby Vision extension blocks -> nits, as CopySample does before feeding
  * SetHDR10ShaderParams (DX11VideoProcessor.cpp:2347-2381, :2717-2720).  Returns 1 when a Level 1 block exists. */
 int orc_dovi_l1_nits(const orc_dovi* dv, float out_min_max_avg[3])
