@@ -59,6 +59,24 @@ int orc_scaler_kind(int src, int dst, int bInterpolateAt50pct)
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
 
+/* PS_COLOR_TRANSFORM and m_PSConvColorData.bEnable as the oracle derives them (SPEC mode's build_cparams: the restatement of
+ * SetShaderConvertColorParams, DX11VideoProcessor.cpp:813-873), handed out so that tests/test_reference_shader_pin.py can compare
+ * them with the reference's own function compiled in place (oracle/_ref/libref_shaders.so: ref_convert_color_params).  exfmt_out = the
+ * extended format after SpecifyExtendedFormat, which is what the reference's m_srcExFmt holds at that point. */
+int orc_test_convert_params(const orc_config* cfg, const orc_dovi* dv, float cm[3][3], float cc[3], int32_t* enable, uint32_t* exfmt_out)
+{
+    const orc_fmt* f = orc_get_fmt(cfg->cformat);
+    if (!f) return -10;
+    const int sw = cfg->src_rect[2] - cfg->src_rect[0], sh = cfg->src_rect[3] - cfg->src_rect[1];
+    const uint32_t exfmt = orc_specify_extended_format(f->cstype == 0 ? cfg->exfmt : 0u, f->cstype, f->subsampling, sw, sh);
+    static cparams_spec P;
+    memset(&P, 0, sizeof(P));
+    if (build_cparams_spec(cfg, f, exfmt, &P, dv)) return -11;
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) cm[i][j] = (float)P.cm[i][j]; cc[i] = (float)P.cc[i]; }
+    *enable = P.enable; *exfmt_out = exfmt;
+    return 0;
+}
+
 /* The PS_DOVI_CURVE constants the oracle derives from Dolby Vision reshaping metadata (SPEC mode's build_dovi: the restatement of
  * SetShaderDoviCurves / SetShaderDoviCurvesPoly, DX11VideoProcessor.cpp:990-1122), handed out so that tests/test_reference_dovi_pin.py
  * can compare them with the reference's own functions compiled in place (oracle/_ref/libref_dovi.so).  par[c] = {methods, mmr_single,

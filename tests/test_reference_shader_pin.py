@@ -286,3 +286,54 @@ def test_dolby_vision_body_equals_the_shader_the_reference_generates():
                                     lms=list(dv.rgb_to_lms_matrix))
             assert parse_body(text) == d["body"], (mmr, to_sdr, hdr_out, parse_body(text), d["body"])
             assert ("reshape_mmr" in text) == bool(mmr)
+
+
+def test_convert_color_constants_equal_the_references():
+    """SetShaderConvertColorParams (Source/DX11VideoProcessor.cpp:813-873) compiled where it lies (ref_convert_color_params): the
+    PS_COLOR_TRANSFORM rows -- colour matrix with ProcAmp, the GBRP column rotation, the gray rows, the Dolby Vision matrix with its
+    offsets -- and m_PSConvColorData.bEnable, against the oracle's build_cparams, bit for bit, for every format x every
+    (range, matrix) tag x a grid of ProcAmp values that are exact in DXVA2's 16.16 fixed point."""
+    import harness as H
+    R = ref(); L = O.lib()
+    R.ref_convert_color_params.restype = C.c_int
+    R.ref_convert_color_params.argtypes = [C.c_int, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                           (C.c_float * 3) * 3, C.c_float * 3, C.POINTER(C.c_int32)]
+    L.orc_test_convert_params.restype = C.c_int
+    L.orc_test_convert_params.argtypes = [C.POINTER(O.OrcConfig), C.c_void_p, (C.c_float * 3) * 3, C.c_float * 3, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
+    rng = np.random.Generator(np.random.PCG64(99))
+    n = ref().ref_fmt_count()
+    checked = enabled = 0
+    for cf in range(1, n):
+        for range_ in (0, 1, 2):
+            for matrix in (0, 1, 2, 3, 4, 7):
+                for trial in range(3):
+                    if trial == 0: b, c, h, s = 0.0, 1.0, 0.0, 1.0
+                    else:
+                        b = float(rng.integers(-100, 101)); c = float(rng.integers(0, 513)) / 256.0
+                        h = float(rng.integers(-180, 181)); s = float(rng.integers(0, 513)) / 256.0
+                    ex = O.exfmt(chroma=5, range_=range_, matrix=matrix, prim=2, trc=5)
+                    cfg = O.make_config(cf, 64, 32, 64, 32, ex, brightness=b, contrast=c, hue=h, saturation=s)
+                    ocm, occ, oen, oex = ((C.c_float * 3) * 3)(), (C.c_float * 3)(), C.c_int32(), C.c_uint32()
+                    assert L.orc_test_convert_params(C.byref(cfg), None, ocm, occ, C.byref(oen), C.byref(oex)) == 0, cf
+                    rcm, rcc, ren = ((C.c_float * 3) * 3)(), (C.c_float * 3)(), C.c_int32()
+                    assert R.ref_convert_color_params(cf, oex.value, b, c, h, s, None, None, rcm, rcc, C.byref(ren)) == 0, (cf, b, c, h, s)
+                    assert bytes(rcm) == bytes(ocm) and bytes(rcc) == bytes(occ), (cf, range_, matrix, b, c, h, s, np.array(rcm), np.array(ocm), np.array(rcc), np.array(occ))
+                    assert ren.value == oen.value, (cf, b, c)
+                    checked += 1; enabled += ren.value
+                    # ... and the PRODUCT's SetShaderConvertColorParams (csrc/video_processor.cpp) on a planning-only instance (no GPU needed)
+                    vp = H.Case(cf, 64, 32, 64, 32, ex, procamp=dict(brightness=b, contrast=c, hue=h, saturation=s)).make_processor(device=-1)
+                    pm, pc, _, _ = vp.debug_color_params()
+                    assert np.asarray(pm, np.float32).tobytes() == bytes(rcm) and np.asarray(pc, np.float32).tobytes() == bytes(rcc), (cf, range_, matrix, b, c, h, s)
+    assert checked > 2000 and 0 < enabled < checked        # RGB sources with neutral ProcAmp run without a convert pass
+    # Dolby Vision: the RPU's own matrix and offsets, with ProcAmp brightness / contrast (:817-834)
+    for seed in range(20):
+        dv = H.make_dovi(seed=seed, mmr=seed & 1)
+        b = float(rng.integers(-100, 101)); c = float(rng.integers(0, 513)) / 256.0
+        ex = O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=15)
+        cfg = O.make_config(O.CF["P010"], 64, 32, 64, 32, ex, brightness=b, contrast=c)
+        ocm, occ, oen, oex = ((C.c_float * 3) * 3)(), (C.c_float * 3)(), C.c_int32(), C.c_uint32()
+        assert L.orc_test_convert_params(C.byref(cfg), C.byref(dv), ocm, occ, C.byref(oen), C.byref(oex)) == 0
+        rcm, rcc, ren = ((C.c_float * 3) * 3)(), (C.c_float * 3)(), C.c_int32()
+        m = (C.c_double * 9)(*dv.ycc_to_rgb_matrix); off = (C.c_double * 3)(*dv.ycc_to_rgb_offset)
+        assert R.ref_convert_color_params(O.CF["P010"], oex.value, b, c, 0.0, 1.0, m, off, rcm, rcc, C.byref(ren)) == 0
+        assert bytes(rcm) == bytes(ocm) and bytes(rcc) == bytes(occ) and ren.value == oen.value == 1, (seed, np.array(rcm), np.array(ocm), np.array(rcc), np.array(occ))
