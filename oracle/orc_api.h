@@ -73,6 +73,9 @@ int orc_process_dovi(const orc_config* cfg, const void* const planes[3], const i
 int orc_describe_convert(const orc_config* cfg, const orc_dovi* dovi, char* out, int cap);
 float orc_pq_to_linear_nits(float x);   /* PqToLinearNits, DX11VideoProcessor.cpp:2329-2334 */
 int orc_dovi_l1_nits(const orc_dovi* dv, float out_min_max_avg[3]);
+/* test hook: records the draws of the resize stage of the next SPEC-mode call made from this thread (orc_types.h: orc_trace_entry) */
+void orc_test_trace_begin(orc_trace_entry* buf, int cap);
+int  orc_test_trace_end(void);
 /* test hook: the colour-transform constants build_cparams derives (compared with the reference's SetShaderConvertColorParams) */
 int orc_test_convert_params(const orc_config* cfg, const orc_dovi* dv, float cm[3][3], float cc[3], int32_t* enable, uint32_t* exfmt_out);
 /* test hook: the reshaping constants build_dovi derives (compared with the reference's SetShaderDoviCurves compiled in place) */

@@ -59,6 +59,12 @@ int orc_scaler_kind(int src, int dst, int bInterpolateAt50pct)
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
 
+/* Trace of the resize stage's draws (orc_types.h: orc_trace_entry): begin with a buffer, run ONE orc_process_from_convert / orc_process
+ * call in SPEC mode from this thread, end returns the number of records written. */
+extern orc_trace_entry* orc_g_trace; extern int orc_g_trace_cap, orc_g_trace_n;
+void orc_test_trace_begin(orc_trace_entry* buf, int cap) { orc_g_trace_n = 0; orc_g_trace_cap = cap; orc_g_trace = buf; }
+int  orc_test_trace_end(void) { orc_g_trace = NULL; return orc_g_trace_n; }
+
 /* PS_COLOR_TRANSFORM and m_PSConvColorData.bEnable as the oracle derives them (SPEC mode's build_cparams: the restatement of
  * SetShaderConvertColorParams, DX11VideoProcessor.cpp:813-873), handed out so that tests/test_reference_shader_pin.py can compare
  * them with the reference's own function compiled in place (oracle/_ref/libref_shaders.so: ref_convert_color_params).  exfmt_out = the

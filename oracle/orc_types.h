@@ -130,6 +130,20 @@ typedef struct orc_dovi {
     orc_dovi_ext ext[32];
 } orc_dovi;
 
+/* test hook (orc_test_trace_*): one record per draw of the resize stage, written by the pass functions themselves.
+ * cu / cv = the texture coordinate (in texels) the pass computed for the first and the last output index that drives u / v;
+ * u_from_x = 1 when the output column drives u (upright and half-turn quads), 0 when the output row does (quarter turns). */
+typedef struct orc_trace_entry {
+    int32_t type;            /* 0 separable shader upright (resize_pass), 1 oriented draw (oriented_pass), 2 Jinc2, 4 point copy, 5 point-sampled stretch */
+    int32_t in_id, out_id;   /* 0 = the pass input (convert output / source), 1 = m_TexResize, 2 = the render target */
+    int32_t in_w, in_h, in_rect[4], out_rect[4], rot, flip;
+    int32_t in_axis;         /* texture axis the shader filters: 0 X shader, 1 Y shader, -1 none, 2 both (Jinc2) */
+    int32_t kind, filter;    /* 1 interpolation / 2 convolution and the scaler index */
+    int32_t u_from_x;
+    float   scale;           /* the `scale` constant the convolution shader divides by (TextureResizeShader :351-354), 0 when unused */
+    float   cu[2], cv[2];
+} orc_trace_entry;
+
 /* optional taps into the pass chain for stage-wise parity tests */
 typedef struct orc_debug {
     float*    convert_f32;   /* [srcRectH][srcRectW][3]  convert pass output before the RT write    */
