@@ -134,8 +134,9 @@ typedef struct orc_dovi {
  * cu / cv = the texture coordinate (in texels) the pass computed for the first and the last output index that drives u / v;
  * u_from_x = 1 when the output column drives u (upright and half-turn quads), 0 when the output row does (quarter turns). */
 typedef struct orc_trace_entry {
-    int32_t type;            /* 0 separable shader upright (resize_pass), 1 oriented draw (oriented_pass), 2 Jinc2, 4 point copy, 5 point-sampled stretch */
-    int32_t in_id, out_id;   /* 0 = the pass input (convert output / source), 1 = m_TexResize, 2 = the render target */
+    int32_t type;            /* 0 separable shader upright (resize_pass), 1 oriented draw (oriented_pass), 2 Jinc2, 4 point copy, 5 point-sampled stretch,
+                                6 ConvertColorPass, 7 correction shader, 8 HDR10 tone-map shader, 9 FinalPass */
+    int32_t in_id, out_id;   /* the reference's textures: 0 m_TexSrcVideo, 1 m_TexResize, 2 the back buffer, 3 m_TexConvertOutput, 4 / 5 m_TexsPostScale[0 / 1] */
     int32_t in_w, in_h, in_rect[4], out_rect[4], rot, flip;
     int32_t in_axis;         /* texture axis the shader filters: 0 X shader, 1 Y shader, -1 none, 2 both (Jinc2) */
     int32_t kind, filter;    /* 1 interpolation / 2 convolution and the scaler index */

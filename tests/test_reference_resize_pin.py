@@ -44,7 +44,7 @@ def _libs():
     return R, L
 
 
-def _oracle_draws(L, cfg, sw, sh):
+def _oracle_draws(L, cfg, sw, sh, resize_stage_only=True):
     conv = np.zeros((sh, sw * 4), np.uint8)                     # m_TexConvertOutput (RGB10A2), contents irrelevant here
     buf = (TraceEntry * 8)()
     L.orc_test_trace_begin(buf, 8)
@@ -52,7 +52,7 @@ def _oracle_draws(L, cfg, sw, sh):
         O.process(cfg, None, None, from_convert=conv, threads=1)
     finally:
         n = L.orc_test_trace_end()
-    return [buf[i] for i in range(n)]
+    return [buf[i] for i in range(n) if buf[i].type <= 5 or not resize_stage_only]
 
 
 def _ref_draws(R, sw, sh, dst, win, rot, flip, interp50, up_kind):
@@ -118,7 +118,9 @@ def test_resize_stage_draws_equal_the_references():
         assert len(od) == len(rd), (cs, len(od), len(rd), [(_shader_id(e), e.type) for e in od], rd[:, 0])
         for e, d in zip(od, rd):
             assert _shader_id(e) == int(d[0]), (cs, _shader_id(e), int(d[0]))
-            assert (e.in_id, e.out_id) == (int(d[1]), int(d[4])), (cs, e.in_id, e.out_id, d[1], d[4])
+            # ResizeShaderPass alone knows "the input" (0) and "the target" (2); the oracle names them as Process() does (see test_process_*)
+            norm = {0: 0, 3: 0, 1: 1, 2: 2, 4: 2, 5: 2}
+            assert (norm[e.in_id], norm[e.out_id]) == (int(d[1]), int(d[4])), (cs, e.in_id, e.out_id, d[1], d[4])
             assert (e.in_w, e.in_h) == (int(d[2]), int(d[3])), (cs, e.in_w, e.in_h, d[2], d[3])
             ow, oh = e.out_rect[2] - e.out_rect[0], e.out_rect[3] - e.out_rect[1]
             assert (e.out_rect[0], e.out_rect[1], ow, oh) == tuple(int(v) for v in d[6:10]), (cs, list(e.out_rect), d[6:10])
@@ -141,4 +143,72 @@ def test_resize_stage_draws_equal_the_references():
         seen["stretch"] += int(any(e.type == 5 for e in od))
         seen["one_pass_quirk"] += int(turned and len(od) == 1 and od[0].type == 1 and od[0].in_axis == 1 and
                                       (cs["dst"][2] - cs["dst"][0]) != sh and (cs["dst"][3] - cs["dst"][1]) != sw)
+    assert all(v > 0 for v in seen.values()), seen
+
+
+# ---- the whole of Process() (Source/DX11VideoProcessor.cpp:3285-3424): convert pass or not, the resize stage or the "Hmm" shortcut, the
+# post-scale steps through the m_TexsPostScale ring, the last step into the back buffer ----
+def _oracle_process_draws(L, cfg, planes, pitches):
+    buf = (TraceEntry * 8)()
+    L.orc_test_trace_begin(buf, 8)
+    try:
+        O.process(cfg, planes, pitches, threads=1)
+    finally:
+        n = L.orc_test_trace_end()
+    return [buf[i] for i in range(n)]
+
+
+def test_process_chain_equals_the_references():
+    """every draw of a frame: CDX11VideoProcessor::Process, ResizeShaderPass, FinalPass, GetPostScaleSteps and the reference's own
+    CTex2DRing compiled in place (ref_process) against the oracle's chain (orc_process with the draw trace): the same draws in the same
+    order, each with the same shader, source texture, target texture and viewport -- including the shortcut that lets the first
+    post-scale step read the convert output when nothing is scaled (and loses a flip on the way, :3350-3352), the ping-pong of the two
+    post-scale textures, and RGB sources without a convert pass (the resize stage then samples m_TexSrcVideo inside m_srcRect)."""
+    import harness as H
+    R, L = _libs()
+    R.ref_process.restype = C.c_int
+    R.ref_process.argtypes = [C.c_int, C.c_int, C.c_int * 4, C.c_int, C.c_int * 4, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                              C.POINTER(C.c_float), C.c_int]
+    seen = {"hmm": 0, "lost_flip": 0, "no_convert": 0, "ring3": 0, "direct": 0, "two_pass": 0}
+    rng = np.random.Generator(np.random.PCG64(11))
+    W, Hh = 64, 48
+    for fmt, convert in (("P010", 1), ("XRGB32", 0)):
+        cf = O.CF[fmt]
+        codes = H.make_codes(cf, W, Hh, "noise", 3)
+        buf, pitch, planes, pitches = H.pack(cf, W, Hh, codes)
+        for src in ((0, 0, W, Hh), (4, 2, 60, 46)):
+            sw, sh = src[2] - src[0], src[3] - src[1]
+            for (dw, dh) in ((sw, sh), (sw * 2, sh * 2), (sw, sh * 2), (sw // 2, sh // 2), (sw * 3 // 2, sh // 2)):
+                for rot, flip in ((0, 0), (0, 1), (90, 0), (180, 1)):
+                    for steps in ("none", "final", "tonemap+final", "correction+tonemap+final", "tonemap"):
+                        at_origin = bool(rng.integers(0, 2)) or (dw, dh) == (sw, sh)
+                        ox, oy = ((src[0], src[1]) if (dw, dh) == (sw, sh) and not convert else (0, 0)) if at_origin else (int(rng.integers(1, 9)), int(rng.integers(1, 9)))
+                        dst = (ox, oy, ox + dw, oy + dh); win = (ox + dw + 3, oy + dh + 2) if not at_origin else (max(ox + dw, W), max(oy + dh, Hh))
+                        final = "final" in steps; tone = "tonemap" in steps; corr = "correction" in steps
+                        if corr and convert: continue                   # the correction shaders belong to RGB input from an upstream converter
+                        ex = O.exfmt(chroma=5, range_=2, matrix=4, prim=9, trc=15) if convert else 0
+                        hdr = dict(out=1, tonemap=1, min=0.005, max=1000.0, cll=800.0, fall=200.0, display=600.0, type=2) if tone else None
+                        # final pass <=> dither on and an internal format wider than the back buffer (UpdatePostScaleTexures); 10-bit source, 8-bit target
+                        cfg = O.make_config(cf, W, Hh, dw, dh, ex, src_rect=src, dst_rect=dst, win=win, dither=1 if final else 0,
+                                            tex=O.TEXFMT_16FLOAT if final or tone or corr else O.TEXFMT_8INT, to_sdr=0 if tone else 1,
+                                            rotation=rot, flip=flip, hdr=hdr, correction=4 if corr else 0)
+                        od = _oracle_process_draws(L, cfg, planes, pitches)
+                        out = (C.c_float * (38 * 8))()
+                        n = R.ref_process(W, Hh, (C.c_int * 4)(*src), convert, (C.c_int * 4)(*dst), win[0], win[1], rot, flip, 1, 1, int(corr), int(tone), int(final), out, 8)
+                        rd = np.array(out, np.float32).reshape(8, 38)[:n]
+                        tag = (fmt, src, dst, win, rot, flip, steps)
+                        ops = [{6: 7, 7: 9, 8: 10, 9: 8}.get(e.type, _shader_id(e)) for e in od]
+                        assert ops == [int(d[0]) for d in rd], (tag, ops, [int(d[0]) for d in rd])
+                        for e, d in zip(od, rd):
+                            assert (e.in_id, e.out_id) == (int(d[1]), int(d[4])), (tag, e.type, (e.in_id, e.out_id), (int(d[1]), int(d[4])))
+                            assert (e.in_w, e.in_h) == (int(d[2]), int(d[3])), (tag, e.type)
+                            ow, oh = e.out_rect[2] - e.out_rect[0], e.out_rect[3] - e.out_rect[1]
+                            assert (e.out_rect[0], e.out_rect[1], ow, oh) == tuple(int(v) for v in d[6:10]), (tag, e.type, list(e.out_rect), d[6:10])
+                        nres = sum(1 for e in od if e.type <= 5)
+                        seen["hmm"] += int(nres == 0 and (final or tone or corr))
+                        seen["lost_flip"] += int(nres == 0 and flip == 1)
+                        seen["no_convert"] += int(not any(e.type == 6 for e in od))
+                        seen["ring3"] += int(sum(1 for e in od if e.type >= 7) == 3)
+                        seen["direct"] += int(steps == "none" and nres >= 1)
+                        seen["two_pass"] += int(nres == 2)
     assert all(v > 0 for v in seen.values()), seen
