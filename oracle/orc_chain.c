@@ -59,6 +59,18 @@ int orc_scaler_kind(int src, int dst, int bInterpolateAt50pct)
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
 
+/* The DolbyConstants the oracle derives for a display (SPEC mode's build_dovi: Level 2 trim selection / interpolation,
+ * DX11VideoProcessor.cpp:2383-2469, and the +-0.5 of SetDolbyVisionDynamicParams :956-960): {chroma_weight, saturation_gain, slope, offset, power}.
+ * Returns l2_enabled. */
+int orc_test_dovi_trims(const orc_dovi* dv, int display_nits, float out5[5])
+{
+    static cparams_spec P;
+    memset(&P, 0, sizeof(P));
+    build_dovi_spec(dv, &P, display_nits);
+    out5[0] = (float)P.l2_chroma_weight; out5[1] = (float)P.l2_saturation_gain; out5[2] = (float)P.l2_slope; out5[3] = (float)P.l2_offset; out5[4] = (float)P.l2_power;
+    return P.l2_enabled;
+}
+
 /* Trace of the resize stage's draws (orc_types.h: orc_trace_entry): begin with a buffer, run ONE orc_process_from_convert / orc_process
  * call in SPEC mode from this thread, end returns the number of records written. */
 extern orc_trace_entry* orc_g_trace; extern int orc_g_trace_cap, orc_g_trace_n;

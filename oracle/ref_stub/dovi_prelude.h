@@ -6,5 +6,7 @@
 #include <cstdint>
 #include <cstring>
 #include <algorithm>
+#include <cmath>
 namespace DirectX { struct XMFLOAT4 { float x, y, z, w; }; }
 #define ASSERT(x) ((void)0)
+typedef unsigned int UINT;

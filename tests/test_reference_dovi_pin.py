@@ -95,3 +95,60 @@ def test_reshaping_constants_equal_the_references(allow_mmr):
         assert seen_mmr > 100 and seen_mixed > 50          # MMR pieces, and curves that mix polynomial and MMR pieces, were covered
     else:
         assert seen_mmr == 0
+
+
+def _with_levels(rng, d, kind):
+    """Level 1 / 2 / 3 extension blocks in the metadata's slots (orc_dovi_ext: level + seven 16-bit fields)"""
+    slots = list(rng.permutation(32)[:8])
+    def put(level, vals):
+        e = d.ext[int(slots.pop())]; e.level = level
+        for i, v in enumerate(vals): e.v[i] = int(v)
+    if kind != "no_l1":
+        put(1, [rng.integers(0, 300), rng.integers(1500, 4096), rng.integers(300, 1500)])
+        if rng.random() < 0.5: put(3, [rng.integers(2000, 2100), rng.integers(2000, 2100), rng.integers(2000, 2100)])
+    n2 = {"none": 0, "one": 1, "many": int(rng.integers(2, 5)), "no_l1": 2}[kind]
+    for _ in range(n2):
+        put(2, [rng.integers(1500, 3900)] + [rng.integers(1500, 2600) for _ in range(5)] + [rng.integers(0, 4096)])
+    d.source_min_pq = int(rng.integers(0, 100)); d.source_max_pq = int(rng.integers(2500, 4096))
+    return d
+
+
+def test_level_metadata_handling_equals_the_references():
+    """CopySample's Dolby Vision level block (Source/DX11VideoProcessor.cpp:2324-2469) compiled where it lies: Level 1 (+ Level 3 offsets)
+    -> nits (integer, through powf) and the Level 2 trim set chosen / interpolated for the display (between two targets, brighter than all
+    -> towards neutral by source_max_pq, dimmer than all), then the constants of SetDolbyVisionDynamicParams (:956-960) -- against the
+    oracle's orc_dovi_l1_nits and build_dovi, bit for bit, on displays from 100 to 4000 nits.  (std::lerp is this toolchain's libstdc++; the
+    oracle and the product spell its case analysis out, so the test also holds them to it.)"""
+    R, L = _libs()
+    R.ref_dovi_dynamic.restype = C.c_int
+    R.ref_dovi_dynamic.argtypes = [C.POINTER(O.OrcDovi), C.c_int, C.c_int, C.c_int, C.c_float * 3, C.POINTER(C.c_int32), C.c_float * 5, C.POINTER(C.c_int32)]
+    L.orc_test_dovi_trims.restype = C.c_int
+    L.orc_test_dovi_trims.argtypes = [C.POINTER(O.OrcDovi), C.c_int, C.c_float * 5]
+    L.orc_dovi_l1_nits.restype = C.c_int
+    L.orc_dovi_l1_nits.argtypes = [C.POINTER(O.OrcDovi), C.c_float * 3]
+    rng = np.random.Generator(np.random.PCG64(77))
+    scen = {"between": 0, "brighter": 0, "dimmer": 0, "none": 0, "l1": 0}
+    for trial in range(600):
+        kind = ("none", "one", "many", "no_l1")[trial % 4]
+        d = _with_levels(rng, _random_metadata(rng, False), kind)
+        for nits in (100, 300, 600, 1000, 2000, 4000):
+            rl1, rp, rt, re = (C.c_float * 3)(), C.c_int32(), (C.c_float * 5)(), C.c_int32()
+            assert R.ref_dovi_dynamic(C.byref(d), nits, 1, 1, rl1, C.byref(rp), rt, C.byref(re)) == 0
+            ot = (C.c_float * 5)()
+            oe = L.orc_test_dovi_trims(C.byref(d), nits, ot)
+            assert oe == re.value, (trial, kind, nits)
+            if oe:
+                assert bytes(ot) == bytes(rt), (trial, kind, nits, list(ot), list(rt))
+            ol1 = (C.c_float * 3)()
+            op = L.orc_dovi_l1_nits(C.byref(d), ol1)
+            assert op == rp.value
+            if op:
+                assert list(ol1) == list(rl1), (trial, list(ol1), list(rl1)); scen["l1"] += 1
+            # which scenario was it (for the coverage assertion below)
+            t2 = sorted(d.ext[i].v[0] for i in range(32) if d.ext[i].level == 2)
+            if not t2: scen["none"] += 1
+            else:
+                pq = (nits / 10000.0) ** 0.1593017578125; pq = ((0.8359375 + 18.8515625 * pq) / (1 + 18.6875 * pq)) ** 78.84375
+                lo = [t for t in t2 if t / 4095.0 <= pq]; hi = [t for t in t2 if t / 4095.0 > pq]
+                scen["between" if lo and hi else ("brighter" if lo else "dimmer")] += 1
+    assert all(v > 50 for v in scen.values()), scen
