@@ -73,6 +73,9 @@ int orc_process_dovi(const orc_config* cfg, const void* const planes[3], const i
 int orc_describe_convert(const orc_config* cfg, const orc_dovi* dovi, char* out, int cap);
 float orc_pq_to_linear_nits(float x);   /* PqToLinearNits, DX11VideoProcessor.cpp:2329-2334 */
 int orc_dovi_l1_nits(const orc_dovi* dv, float out_min_max_avg[3]);
+/* test hooks: the transfer pieces of the convert shader in a given arithmetic mode (compared with the reference's .hlsl files run as C++) */
+int orc_test_transfer(int fn, int mode, const float* in, float* out, int n, float param);
+int orc_test_hlg_to_linear_literal(const float* in, float* out, int n);
 /* test hook: the Level-2 trim constants build_dovi derives for a display (compared with the reference's CopySample block compiled in place) */
 int orc_test_dovi_trims(const orc_dovi* dv, int display_nits, float out5[5]);
 /* test hook: records the draws of the resize stage of the next SPEC-mode call made from this thread (orc_types.h: orc_trace_entry) */

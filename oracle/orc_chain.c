@@ -59,6 +59,38 @@ int orc_scaler_kind(int src, int dst, int bInterpolateAt50pct)
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
 
+/* The transfer pieces of the convert shader as the oracle restates them (orc_core.inc: st2084_to_linear, linear_to_st2084, inverse_hlg,
+ * hable / ToneMappingHable, the HLG OOTF lines of convert_color), in any arithmetic mode -- tests/test_reference_hlsl_pin.py runs the
+ * reference's own .hlsl include files as C++ (oracle/_ref/libref_hlsl.so) and compares LITERAL mode bit for bit.
+ * fn: 0 ST2084ToLinear(v, param)  1 LinearToST2084(v, param)  2 inverse_HLG(v)  3 ToneMappingHable(v);  mode: 0 SPEC, 1 LITERAL, 2 F64 */
+int orc_test_transfer(int fn, int mode, const float* in, float* out, int n, float param)
+{
+    for (int i = 0; i < n; i++) {
+        const float v = in[i];
+        if (mode == 0)      out[i] = fn == 0 ? st2084_to_linear_spec(v, param) : fn == 1 ? linear_to_st2084_spec(v, param) : fn == 2 ? inverse_hlg_spec(v)
+                                   : hable_spec(v) * (1.0f / hable_spec(4.8f));
+        else if (mode == 1) out[i] = fn == 0 ? st2084_to_linear_lit(v, param) : fn == 1 ? linear_to_st2084_lit(v, param) : fn == 2 ? inverse_hlg_lit(v)
+                                   : hable_lit(v) / hable_lit(4.8f);
+        else                out[i] = (float)(fn == 0 ? st2084_to_linear_f64(v, param) : fn == 1 ? linear_to_st2084_f64(v, param) : fn == 2 ? inverse_hlg_f64(v)
+                                   : hable_f64(v) / hable_f64(4.8));
+    }
+    return (fn < 0 || fn > 3) ? -1 : 0;
+}
+/* HLGtoLinear (hlg.hlsl:13-20) as convert_color states it (orc_core.inc, "hlg.hlsl:13-20"): inverse_HLG per channel, the OOTF gain from the
+ * BT.2020 luminance, n RGB triplets, LITERAL mode */
+int orc_test_hlg_to_linear_literal(const float* in, float* out, int n)
+{
+    for (int i = 0; i < n; i++) {
+        float l[3];
+        for (int k = 0; k < 3; k++) l[k] = inverse_hlg_lit(in[3 * i + k]);
+        float dt = 0.2627f * l[0]; dt = 0.6780f * l[1] + dt; dt = 0.0593f * l[2] + dt;
+        const float ys = 2000.0f * dt;
+        const float g = orc_pow_literal(ys, 0.2f);
+        for (int k = 0; k < 3; k++) out[3 * i + k] = l[k] * g;
+    }
+    return 0;
+}
+
 /* The DolbyConstants the oracle derives for a display (SPEC mode's build_dovi: Level 2 trim selection / interpolation,
  * DX11VideoProcessor.cpp:2383-2469, and the +-0.5 of SetDolbyVisionDynamicParams :956-960): {chroma_weight, saturation_gain, slope, offset, power}.
  * Returns l2_enabled. */
