@@ -392,15 +392,20 @@ def main():
             "kernel": "fused frame kernel" if plan.path == V.PATH.FUSED else "multipass chain (%d kernels/frame; bytes are per frame)" % launches_per_step,
             "secondary_ceiling": "instruction issue (exact fp32 tone-map + 6-tap resize), see DESIGN.md"}
     # Numbers that cannot be measured inside this process (DRAM bytes, warp instructions of the frame kernel) come from the committed
-    # ncu capture profiles/capture_c2.json, which also records the sha256 of videorenderer_b200/csrc at capture time.  If the kernel
-    # sources changed since, the figures belong to another binary: say so and do not quote the issue ceiling.
+    # ncu capture profiles/capture_c2.json, which also records the sha256 of videorenderer_b200/csrc and of the captured kernel's
+    # SASS at capture time.  If neither matches, the figures belong to another binary: say so and do not quote the issue ceiling.
     cap_file = os.path.join(ROOT, "profiles", "capture_c2.json")
     if os.path.exists(cap_file) and plan.path == V.PATH.FUSED:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
-            from make_capture_json import csrc_sha256
+            from make_capture_json import csrc_sha256, kernel_sass_sha256
             cap = json.load(open(cap_file))
             stale = cap.get("csrc_sha256") != csrc_sha256()
+            if stale and cap.get("kernel_sass_sha256"):
+                # some device source changed since the capture; the capture still describes this binary if the captured kernel's SASS is
+                # unchanged in the library loaded here (an edit to a code path that kernel does not instantiate)
+                stale = kernel_sass_sha256() != cap["kernel_sass_sha256"]
+                roof["traffic_identity"] = "kernel SASS sha256 " + ("matches" if not stale else "differs from") + " the capture's (device sources were edited since)"
             roof["traffic"] = cap.get("dram_bytes_per_launch")
             roof["traffic_source"] = "profiles/capture_c2.json (%s, %s)" % (cap.get("report"), cap.get("kernel", "")[:60])
             roof["traffic_stale"] = bool(stale)

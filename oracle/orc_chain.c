@@ -91,6 +91,32 @@ int orc_test_hlg_to_linear_literal(const float* in, float* out, int n)
     return 0;
 }
 
+/* One resize draw (resize_pass: TextureResizeShader with one of ps_interpolation_*.hlsl / ps_convolution.hlsl along `axis`) and the final
+ * pass (final_pass: ps_final_pass.hlsl) on RAW float surfaces, i.e. the shader's float4 result before any render-target conversion --
+ * tests/test_reference_hlsl_pin.py runs the reference's own pixel shaders as C++ (oracle/_ref/libref_hlsl_shaders.so) on the same texels and
+ * compares LITERAL mode bit for bit.  in: w*h RGB texels; out: ow*oh RGB (the out rect is the whole output surface).  mode 0 SPEC, 1 LITERAL. */
+int orc_test_resize_draw(int mode, int axis, int kind, int filter, int variant, const float* in, int w, int h, const int in_rect[4],
+                         int ow, int oh, float* out)
+{
+    const int out_rect[4] = {0, 0, ow, oh};
+    if (mode == 0) {
+        surf_spec a = {w, h, ORC_SURF_RAW, (float*)in}, b = {ow, oh, ORC_SURF_RAW, out};
+        return resize_pass_spec(&a, &b, axis, in_rect, out_rect, kind, filter, variant, 1);
+    }
+    if (mode == 1) {
+        surf_lit a = {w, h, ORC_SURF_RAW, (float*)in}, b = {ow, oh, ORC_SURF_RAW, out};
+        return resize_pass_lit(&a, &b, axis, in_rect, out_rect, kind, filter, variant, 1);
+    }
+    return -1;
+}
+int orc_test_final_pass(int mode, const float* in, int w, int h, float Q, float* out)
+{
+    const int rect[4] = {0, 0, w, h};
+    if (mode == 0) { surf_spec a = {w, h, ORC_SURF_RAW, (float*)in}, b = {w, h, ORC_SURF_RAW, out}; final_pass_spec(&a, &b, rect, Q, 1); return 0; }
+    if (mode == 1) { surf_lit a = {w, h, ORC_SURF_RAW, (float*)in}, b = {w, h, ORC_SURF_RAW, out}; final_pass_lit(&a, &b, rect, Q, 1); return 0; }
+    return -1;
+}
+
 /* The DolbyConstants the oracle derives for a display (SPEC mode's build_dovi: Level 2 trim selection / interpolation,
  * DX11VideoProcessor.cpp:2383-2469, and the +-0.5 of SetDolbyVisionDynamicParams :956-960): {chroma_weight, saturation_gain, slope, offset, power}.
  * Returns l2_enabled. */

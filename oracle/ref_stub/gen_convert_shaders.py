@@ -1,0 +1,138 @@
+#!/usr/bin/env python3
+"""oracle/ref_stub/gen_convert_shaders.py <REF> <libref_shaders.so> -- TEST INFRASTRUCTURE ONLY.
+
+Asks the reference's own GetShaderConvertColor (Source/Shaders.cpp:593-930, compiled where it lies into libref_shaders.so; its
+CompileShader is a stub that keeps the text) for the HLSL convert shader of each case below, and prints one C++ unit in which every
+generated shader sits in its own namespace and can be called per pixel.  The text is the reference's; the edits are syntax only:
+  * the three "//#include x.hlsl" marker lines the resource stub leaves are replaced by the files themselves (Shaders/convert/*.hlsl),
+  * `cbuffer NAME : register(bN) {` -> `namespace {`, register / semantic annotations off, `[unroll(n)]` off, main -> ps_main,
+  * hlg.hlsl's vector `c ? a : b` -> hlsl_select(c, a, b) (C++ has no overloadable ?:),
+  * #undef of the text's own macros (w, dx, dy, ...) after each shader.
+The texture register each Texture2D was declared with is recorded before the annotation is stripped, so the runner binds plane k of the
+frame to register tk the way CDX11VideoProcessor binds its shader resource views.  Nothing of this output is kept in the repository."""
+import ctypes as C
+import re
+import sys
+
+REF, LIB = sys.argv[1], sys.argv[2]
+R = C.CDLL(LIB)
+R.ref_convert_shader.argtypes = [C.c_int, C.c_uint, C.c_long, C.c_long, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int,
+                                 C.c_char_p, C.c_int]
+R.ref_specify_extended_format.restype = C.c_uint32
+R.ref_specify_extended_format.argtypes = [C.c_uint32, C.c_int, C.c_uint, C.c_uint]
+R.ref_fmt_params.argtypes = [C.c_int, C.POINTER(C.c_int)]
+
+CF = dict(NV12=1, P010=2, P016=3, YUY2=4, UYVY=5, P210=6, P216=7, Y210=8, Y216=9, AYUV=11, Y410=12, Y416=13, YV12=14, YV16=15, YV24=16,
+          YUV420P8=17, YUV422P8=18, YUV444P8=19, YUV420P16=21, YUV422P16=23, YUV444P16=25, XRGB32=30, RGB48=33, Y8=37, Y16=39)
+PACKED422 = ("YUY2", "UYVY", "Y210", "Y216")
+W, H = 64, 32                                     # powers of two: texel centre / size and texcoord * size are exact
+
+
+def exfmt(chroma=0, range_=0, matrix=0, prim=0, trc=0, sample=3):
+    return (sample | (chroma << 8) | (range_ << 12) | (matrix << 15) | (prim << 22) | (trc << 27)) & 0xFFFFFFFF
+
+
+SDR709, SDR2020, PQ, HLG = dict(range_=2, matrix=1, prim=2, trc=5), dict(range_=2, matrix=4, prim=9, trc=5), dict(range_=2, matrix=4, prim=9, trc=15), \
+    dict(range_=2, matrix=4, prim=9, trc=16)
+NEAREST, BILINEAR, CATMULL = 0, 1, 2
+NONE, TO_SDR, TO_PQ = 0, 1, 2
+# the RGB -> LMS matrix of the Dolby Vision cases (the text embeds dovi_lms2rgb x this as a literal): the ICtCp one scaled by 1/4096
+DOVI_LMS = [1688 / 4096, 2146 / 4096, 262 / 4096, 683 / 4096, 2951 / 4096, 462 / 4096, 99 / 4096, 309 / 4096, 3688 / 4096]
+
+CASES = []      # (name, format, exfmt fields, chroma siting, chroma scaler, convert type, blend deinterlace, dovi: -1 none / 0 poly / 1 mmr)
+for fmt in ("NV12", "P010", "YV12", "YUV420P8", "YUV420P16"):
+    for siting in (1, 5, 7):
+        for scaler in (NEAREST, BILINEAR, CATMULL):
+            CASES.append(("%s_s%d_c%d" % (fmt, siting, scaler), fmt, SDR709 if fmt != "P010" else PQ, siting, scaler, NONE, 0, -1))
+for fmt in ("P210", "P216", "YV16", "YUV422P8", "YUV422P16", "YUY2", "UYVY", "Y210", "Y216"):
+    for scaler in (NEAREST, BILINEAR, CATMULL):
+        CASES.append(("%s_c%d" % (fmt, scaler), fmt, SDR709, 5, scaler, NONE, 0, -1))
+for fmt in ("YV24", "YUV444P8", "YUV444P16", "AYUV", "Y410", "Y416", "XRGB32", "RGB48", "Y8", "Y16"):
+    CASES.append(("%s" % fmt, fmt, SDR709, 5, BILINEAR, NONE, 0, -1))
+for fmt in ("NV12", "YV12"):
+    CASES.append(("%s_blend" % fmt, fmt, SDR709, 5, BILINEAR, NONE, 1, -1))
+    CASES.append(("%s_blend_catmull" % fmt, fmt, SDR709, 5, CATMULL, NONE, 1, -1))
+for fmt in ("P010", "Y410", "YUV420P16"):
+    CASES.append(("%s_pq_to_sdr" % fmt, fmt, PQ, 5, BILINEAR, TO_SDR, 0, -1))
+    CASES.append(("%s_hlg_to_sdr" % fmt, fmt, HLG, 5, BILINEAR, TO_SDR, 0, -1))
+    CASES.append(("%s_hlg_to_pq" % fmt, fmt, HLG, 5, BILINEAR, TO_PQ, 0, -1))
+    CASES.append(("%s_hlg_as_sdr" % fmt, fmt, HLG, 5, BILINEAR, NONE, 0, -1))
+    CASES.append(("%s_pq_passthrough" % fmt, fmt, PQ, 5, BILINEAR, TO_PQ, 0, -1))
+for trc in (2, 3, 4, 5, 6, 7, 8, 14):
+    CASES.append(("P010_2020_trc%d" % trc, "P010", dict(range_=2, matrix=4, prim=9, trc=trc), 5, BILINEAR, NONE, 0, -1))
+CASES.append(("NV12_601_full", "NV12", dict(range_=1, matrix=2, prim=2, trc=5), 5, BILINEAR, NONE, 0, -1))
+for mmr in (0, 1):
+    CASES.append(("P010_dovi%d_to_sdr" % mmr, "P010", PQ, 5, BILINEAR, TO_SDR, 0, mmr))
+    CASES.append(("P010_dovi%d_to_pq" % mmr, "P010", PQ, 5, BILINEAR, TO_PQ, 0, mmr))
+
+
+def include(name):
+    s = open("%s/Shaders/convert/%s" % (REF, name)).read()
+    if name == "hlg.hlsl":      # rgb = (cond) ? a : b;  on float3 -> hlsl_select(cond, a, b)
+        s, n = re.subn(r"(\w+)\s*=\s*(\([^;?]*?\))\s*\?\s*([^;:]*?)\s*:\s*([^;]*?);", r"\1 = hlsl_select(\2, \3, \4);", s, count=1, flags=re.S)
+        assert n == 1, "hlg.hlsl: the vector conditional was not found"
+    return s
+
+
+def translate(text):
+    regs = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"Texture2D\s+(\w+)\s*:\s*register\(t(\d+)\)", text))
+    text = re.sub(r"^//#include (\S+)$", lambda m: include(m.group(1)), text, flags=re.M)
+    text = re.sub(r"cbuffer\s+\w+\s*:\s*register\(\w+\)\s*\{", "namespace {", text)
+    text = re.sub(r"\s*:\s*register\(\w+\)", "", text)
+    text = re.sub(r"\s*:\s*(SV_POSITION|TEXCOORD|SV_Target)\b", "", text)
+    text = re.sub(r"\[unroll\(\d+\)\]", "", text)
+    text = re.sub(r"\bfloat4 main\(", "float4 ps_main(", text)
+    macros = sorted(set(re.findall(r"^\s*#define\s+(\w+)", text, flags=re.M)))
+    return text, regs, macros
+
+
+print("// GENERATED by oracle/ref_stub/gen_convert_shaders.py from the text the reference's GetShaderConvertColor emits -- build product of")
+print("// oracle/Makefile, never committed.  (hlsl_vec.h precedes this text.)")
+print("struct ConvArgs { const float* tex[3]; int tw[3], th[3]; float cm[4][3]; float lum_scale; int W, H;")
+print("                  const float* piv; const float* coef; const float* mmr; const int* par; const float* trims; int l2; };")
+rows = []
+for i, (name, fmt, exf, siting, scaler, conv, blend, dovi) in enumerate(CASES):
+    cf = CF[fmt]
+    row = (C.c_int * 13)()
+    assert R.ref_fmt_params(cf, row) == 0
+    # only YUV media types carry their dwControlFlags into m_decExFmt (InitMediaType, DX11VideoProcessor.cpp:1763-1766): RGB and gray start from 0
+    ex = R.ref_specify_extended_format(exfmt(chroma=siting, **exf) if row[3] == 0 else 0, cf, W, H)
+    texw = W // 2 if fmt in PACKED422 else W
+    buf = C.create_string_buffer(1 << 17)
+    lms = (C.c_double * 9)(*DOVI_LMS)
+    n = R.ref_convert_shader(1, W, texw, H, cf, ex, dovi, lms if dovi >= 0 else None, scaler, conv, blend, buf, len(buf))
+    assert 0 < n < len(buf) - 1, name
+    text, regs, macros = translate(buf.value.decode())
+    ns = "cs_%s" % name
+    print("// ======== %s: format %s exfmt %#010x chroma scaler %d convert type %d blend %d dovi %d" % (name, fmt, ex, scaler, conv, blend, dovi))
+    print("namespace %s {" % ns)
+    print(text)
+    for m in macros:
+        print("#undef %s" % m)
+    print("static float4 run(const ConvArgs& A, float u, float v) {")
+    for t, r in sorted(regs.items(), key=lambda kv: kv[1]):
+        print("    %s.bind(A.tex[%d], A.tw[%d], A.th[%d]);" % (t, r, r, r))
+    print("    samp.linear = 0; sampL.linear = 1;")
+    for k, row in enumerate(("cm_r", "cm_g", "cm_b", "cm_c")):
+        print("    %s = float3(A.cm[%d][0], A.cm[%d][1], A.cm[%d][2]);" % (row, k, k, k))
+    if "LuminanceScale" in text:
+        print("    LuminanceScale = A.lum_scale; param2 = 0;")
+    if dovi >= 0:
+        print("    for (int c = 0; c < 3; c++) {")
+        print("        for (int k = 0; k < 7; k++) curves[c].pivots_data[k] = A.piv[c * 7 + k];")
+        print("        for (int k = 0; k < 8; k++) curves[c].coeffs_data[k] = float4(A.coef[(c * 8 + k) * 4], A.coef[(c * 8 + k) * 4 + 1], A.coef[(c * 8 + k) * 4 + 2], A.coef[(c * 8 + k) * 4 + 3]);")
+        if dovi == 1:
+            print("        for (int k = 0; k < 48; k++) curves[c].mmr_data[k] = float4(A.mmr[(c * 48 + k) * 4], A.mmr[(c * 48 + k) * 4 + 1], A.mmr[(c * 48 + k) * 4 + 2], A.mmr[(c * 48 + k) * 4 + 3]);")
+            print("        curves[c].params.methods = A.par[c * 4]; curves[c].params.mmr_single = A.par[c * 4 + 1];")
+            print("        curves[c].params.min_order = A.par[c * 4 + 2]; curves[c].params.max_order = A.par[c * 4 + 3];")
+        print("    }")
+        print("    ChromaWeight = A.trims[0]; SaturationGain = A.trims[1]; TrimSlope = A.trims[2]; TrimOffset = A.trims[3]; TrimPower = A.trims[4]; L2Enabled = A.l2;")
+    print("    PS_INPUT in; in.Tex = float2(u, v);")
+    print("    return ps_main(in);")
+    print("}")
+    print("}  // namespace %s" % ns)
+    rows.append('{ "%s", %d, %#010xu, %d, %d, %d, %d, %d, %d, %d, %s::run }' % (name, cf, ex, siting, scaler, conv, blend, dovi, W, H, ns))
+print("struct ConvCase { const char* name; int cformat; unsigned exfmt; int siting, scaler, convert_type, blend, dovi, W, H; float4 (*run)(const ConvArgs&, float, float); };")
+print("static const ConvCase g_cases[] = {\n    %s\n};" % ",\n    ".join(rows))
+print("static const int g_ncases = %d;" % len(rows))
+print("static const double g_dovi_lms[9] = { %s };" % ", ".join(repr(float(x)) for x in DOVI_LMS))

@@ -12,12 +12,29 @@
 #include <cmath>
 #include <cstdlib>
 static inline float hlsl_pow(float x, float y) { return exp2f(y * log2f(x)); }
+struct float4 {
+    float x, y, z, w;
+    float4() : x(0), y(0), z(0), w(0) {}
+    float4(double v) : x((float)v), y((float)v), z((float)v), w((float)v) {}
+    float4(double a, double b, double c, double d) : x((float)a), y((float)b), z((float)c), w((float)d) {}
+    float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
+    float4& operator+=(const float4& o) { x += o.x; y += o.y; z += o.z; w += o.w; return *this; }
+    float4& operator*=(const float4& o) { x *= o.x; y *= o.y; z *= o.z; w *= o.w; return *this; }
+    float4& operator/=(const float4& o) { x /= o.x; y /= o.y; z /= o.z; w /= o.w; return *this; }
+};
+static inline float4 operator+(const float4& a, const float4& b) { float4 r; r.x = a.x + b.x; r.y = a.y + b.y; r.z = a.z + b.z; r.w = a.w + b.w; return r; }
+static inline float4 operator-(const float4& a, const float4& b) { float4 r; r.x = a.x - b.x; r.y = a.y - b.y; r.z = a.z - b.z; r.w = a.w - b.w; return r; }
+static inline float4 operator*(const float4& a, const float4& b) { float4 r; r.x = a.x * b.x; r.y = a.y * b.y; r.z = a.z * b.z; r.w = a.w * b.w; return r; }
+static inline float4 operator/(const float4& a, const float4& b) { float4 r; r.x = a.x / b.x; r.y = a.y / b.y; r.z = a.z / b.z; r.w = a.w / b.w; return r; }
+static inline float4 pow(const float4& a, const float4& b) { float4 r; r.x = hlsl_pow(a.x, b.x); r.y = hlsl_pow(a.y, b.y); r.z = hlsl_pow(a.z, b.z); r.w = hlsl_pow(a.w, b.w); return r; }
+static inline float4 max(const float4& a, const float4& b) { float4 r; r.x = a.x > b.x ? a.x : b.x; r.y = a.y > b.y ? a.y : b.y; r.z = a.z > b.z ? a.z : b.z; r.w = a.w > b.w ? a.w : b.w; return r; }
 struct bool3 { bool x, y, z; operator bool() const { if (x != y || y != z) abort(); return x; } };
 struct float3 {
     float x, y, z;
+    float4 yxyz;                    // the swizzle ps_interpolation_lanczos2.hlsl takes of a freshly constructed float3(a, b, c)
     float3() : x(0), y(0), z(0) {}
     float3(double v) : x((float)v), y((float)v), z((float)v) {}
-    float3(double a, double b, double c) : x((float)a), y((float)b), z((float)c) {}
+    float3(double a, double b, double c) : x((float)a), y((float)b), z((float)c), yxyz(b, a, b, c) {}
     float3& operator*=(const float3& o) { x *= o.x; y *= o.y; z *= o.z; return *this; }
     float3& operator/=(const float3& o) { x /= o.x; y /= o.y; z /= o.z; return *this; }
 };
@@ -31,16 +48,3 @@ static inline float3 max(const float3& a, const float3& b) { float3 r; r.x = a.x
 static inline float3 exp(const float3& a) { float3 r; r.x = expf(a.x); r.y = expf(a.y); r.z = expf(a.z); return r; }
 static inline float  dot(const float3& a, const float3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }      // DP3: mul, mad, mad -- unfused here (LITERAL)
 static inline float  pow(float a, float b) { return hlsl_pow(a, b); }
-struct float4 {
-    float x, y, z, w;
-    float4() : x(0), y(0), z(0), w(0) {}
-    float4(double v) : x((float)v), y((float)v), z((float)v), w((float)v) {}
-    float4& operator*=(const float4& o) { x *= o.x; y *= o.y; z *= o.z; w *= o.w; return *this; }
-    float4& operator/=(const float4& o) { x /= o.x; y /= o.y; z /= o.z; w /= o.w; return *this; }
-};
-static inline float4 operator+(const float4& a, const float4& b) { float4 r; r.x = a.x + b.x; r.y = a.y + b.y; r.z = a.z + b.z; r.w = a.w + b.w; return r; }
-static inline float4 operator-(const float4& a, const float4& b) { float4 r; r.x = a.x - b.x; r.y = a.y - b.y; r.z = a.z - b.z; r.w = a.w - b.w; return r; }
-static inline float4 operator*(const float4& a, const float4& b) { float4 r; r.x = a.x * b.x; r.y = a.y * b.y; r.z = a.z * b.z; r.w = a.w * b.w; return r; }
-static inline float4 operator/(const float4& a, const float4& b) { float4 r; r.x = a.x / b.x; r.y = a.y / b.y; r.z = a.z / b.z; r.w = a.w / b.w; return r; }
-static inline float4 pow(const float4& a, const float4& b) { float4 r; r.x = hlsl_pow(a.x, b.x); r.y = hlsl_pow(a.y, b.y); r.z = hlsl_pow(a.z, b.z); r.w = hlsl_pow(a.w, b.w); return r; }
-static inline float4 max(const float4& a, const float4& b) { float4 r; r.x = a.x > b.x ? a.x : b.x; r.y = a.y > b.y ? a.y : b.y; r.z = a.z > b.z ? a.z : b.z; r.w = a.w > b.w ? a.w : b.w; return r; }

@@ -1,0 +1,140 @@
+// oracle/ref_stub/hlsl_vec.h -- TEST INFRASTRUCTURE ONLY.
+// HLSL's vector vocabulary for C++, complete enough for the convert shader the reference GENERATES (Source/Shaders.cpp:593-930,
+// GetShaderConvertColor -> ShaderGetPixels + the Shaders/convert/*.hlsl include files) to compile as the text it is and run on the CPU:
+//   * float2 / float3 / float4 with x y z w / r g b a and the swizzles the text uses, readable and ASSIGNABLE (color.rgb = ...,
+//     sigX.xyz = ...), component indexing, the constructors float4(float, float2, float), float4(float3, float), scalar broadcast;
+//   * componentwise + - * / against vectors and scalars (an int operand converts to float, as in HLSL), compound assignment;
+//   * intrinsics with HLSL's meaning: saturate, frac, max, exp, dot, mul(vector, vector) = dot, mul(float3x3, float3) = one dot per row
+//     (each dot: mul, mad, mad in component order), pow(x, y) as fxc lowers it = exp2(y * log2(x)), fmod;
+//   * Texture2D::Sample with a point or a bilinear SamplerState (CLAMP addressing, optional integer texel offset).  The bilinear filter
+//     is a MODEL of the D3D11 sampler, not reference code: texel fractions from u * size - 0.5, result a*(1-f) + b*f horizontally, then
+//     vertically.  The chroma positions the reference's shaders ask for are multiples of a quarter texel, which D3D11's 8-bit
+//     fraction represents exactly;
+//   * `cond ? a : b` on a bool VECTOR cannot be spelled in C++: the generator rewrites the one such statement (hlg.hlsl:8-10) to
+//     hlsl_select(cond, a, b), both sides evaluated for every lane, which is what fxc emits (movc).
+// The unit is compiled with -fsingle-precision-constant -ffp-contract=off: unsuffixed literals are floats and every operation is one
+// IEEE single-precision operation in the order the text states -- the meaning of the oracle's LITERAL mode.
+#include <cmath>
+#include <cstdlib>
+#include <cstddef>
+#include <cstring>
+typedef unsigned int uint;
+static inline float hlsl_pow(float x, float y) { return exp2f(y * log2f(x)); }
+// D3D11 functional spec, min / max / saturate with NaN: max(NaN, b) = b, max(a, NaN) = a, saturate(NaN) = 0.  (The Dolby Vision trims
+// produce NaN on pixels whose trimmed luminance is 0 -- 0 / 0 in DolbyVisionTrims, Shaders.cpp:787-795 -- and the following saturate /
+// max turn it into 0 on the GPU.)
+static inline float hlsl_max(float a, float b) { return (a >= b || b != b) ? a : b; }
+static inline float hlsl_saturate(float a) { return !(a > 0.0f) ? 0.0f : (a > 1.0f ? 1.0f : a); }
+
+template<int N> struct vec;
+template<int N, int... I> struct swz {                     // a view of components I... of the N floats it overlays (member of vec<N>'s union)
+    float v[N];
+    static constexpr int M = (int)sizeof...(I);
+    operator vec<M>() const { vec<M> r; const int idx[M] = { I... }; for (int k = 0; k < M; k++) r.v[k] = v[idx[k]]; return r; }
+    swz& operator=(const vec<M>& o) { const int idx[M] = { I... }; for (int k = 0; k < M; k++) v[idx[k]] = o.v[k]; return *this; }
+    swz& operator=(const swz& o) { const vec<M> t = o; return *this = t; }
+};
+
+template<> struct vec<2> {
+    union { float v[2]; struct { float x, y; }; struct { float r, g; }; };
+    vec() : v{0, 0} {}
+    vec(float s) : v{s, s} {}
+    vec(float a, float b) : v{a, b} {}
+    vec(const vec& o) : v{o.v[0], o.v[1]} {}
+    vec& operator=(const vec& o) { v[0] = o.v[0]; v[1] = o.v[1]; return *this; }
+    float& operator[](int i) { return v[i]; }
+    const float& operator[](int i) const { return v[i]; }
+};
+template<> struct vec<3> {
+    union { float v[3]; struct { float x, y, z; }; struct { float r, g, b; };
+            swz<3, 0, 0, 1> xxy; swz<3, 1, 2, 2> yzz; swz<3, 0, 1> xy, rg; swz<3, 0, 1, 2> xyz, rgb; };
+    vec() : v{0, 0, 0} {}
+    vec(float s) : v{s, s, s} {}
+    vec(float a, float b, float c) : v{a, b, c} {}
+    vec(const vec& o) : v{o.v[0], o.v[1], o.v[2]} {}
+    vec& operator=(const vec& o) { v[0] = o.v[0]; v[1] = o.v[1]; v[2] = o.v[2]; return *this; }
+    float& operator[](int i) { return v[i]; }
+    const float& operator[](int i) const { return v[i]; }
+};
+template<> struct vec<4> {
+    union { float v[4]; struct { float x, y, z, w; }; struct { float r, g, b, a; };
+            swz<4, 0, 1> xy, rg; swz<4, 0, 2> xz; swz<4, 1, 3> yw; swz<4, 2, 0> zx;
+            swz<4, 0, 1, 2> xyz, rgb; swz<4, 1, 0, 2> yxz; swz<4, 0, 1, 3> xyw; swz<4, 1, 2, 0> yzx; swz<4, 2, 1, 3> zyw;
+            swz<4, 2, 1, 0, 3> zyxw; swz<4, 1, 0, 2, 3> yxzw; swz<4, 0, 1, 2, 3> xyzw; };
+    vec() : v{0, 0, 0, 0} {}
+    vec(float s) : v{s, s, s, s} {}
+    vec(float a, float b, float c, float d) : v{a, b, c, d} {}
+    vec(float a, const vec<2>& bc, float d) : v{a, bc.v[0], bc.v[1], d} {}
+    vec(const vec<3>& abc, float d) : v{abc.v[0], abc.v[1], abc.v[2], d} {}
+    vec(const vec& o) : v{o.v[0], o.v[1], o.v[2], o.v[3]} {}
+    vec& operator=(const vec& o) { for (int k = 0; k < 4; k++) v[k] = o.v[k]; return *this; }
+    float& operator[](int i) { return v[i]; }
+    const float& operator[](int i) const { return v[i]; }
+};
+typedef vec<2> float2; typedef vec<3> float3; typedef vec<4> float4;
+struct int2 { int x, y; int2(int a, int b) : x(a), y(b) {} };
+struct float3x3 { float m[9]; };
+
+#define HLSL_BINOP(N, OP) \
+    static inline vec<N> operator OP(const vec<N>& a, const vec<N>& b) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = a.v[k] OP b.v[k]; return r; } \
+    static inline vec<N> operator OP(const vec<N>& a, float b) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = a.v[k] OP b; return r; } \
+    static inline vec<N> operator OP(float a, const vec<N>& b) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = a OP b.v[k]; return r; } \
+    static inline vec<N>& operator OP##=(vec<N>& a, const vec<N>& b) { for (int k = 0; k < N; k++) a.v[k] = a.v[k] OP b.v[k]; return a; } \
+    static inline vec<N>& operator OP##=(vec<N>& a, float b) { for (int k = 0; k < N; k++) a.v[k] = a.v[k] OP b; return a; }
+#define HLSL_VEC(N) \
+    HLSL_BINOP(N, +) HLSL_BINOP(N, -) HLSL_BINOP(N, *) HLSL_BINOP(N, /) \
+    struct bool##N { bool v[N]; }; \
+    static inline bool##N operator<=(const vec<N>& a, float b) { bool##N r; for (int k = 0; k < N; k++) r.v[k] = a.v[k] <= b; return r; } \
+    static inline vec<N> hlsl_select(const bool##N& c, const vec<N>& a, const vec<N>& b) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = c.v[k] ? a.v[k] : b.v[k]; return r; } \
+    static inline vec<N> operator-(const vec<N>& a) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = -a.v[k]; return r; } \
+    static inline vec<N> pow(const vec<N>& a, float b) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = hlsl_pow(a.v[k], b); return r; } \
+    static inline vec<N> pow(const vec<N>& a, const vec<N>& b) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = hlsl_pow(a.v[k], b.v[k]); return r; } \
+    static inline vec<N> max(const vec<N>& a, float b) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = hlsl_max(a.v[k], b); return r; } \
+    static inline vec<N> max(const vec<N>& a, const vec<N>& b) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = hlsl_max(a.v[k], b.v[k]); return r; } \
+    static inline vec<N> exp(const vec<N>& a) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = expf(a.v[k]); return r; } \
+    static inline vec<N> frac(const vec<N>& a) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = a.v[k] - floorf(a.v[k]); return r; } \
+    static inline vec<N> saturate(const vec<N>& a) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = hlsl_saturate(a.v[k]); return r; } \
+    static inline float  dot(const vec<N>& a, const vec<N>& b) { float d = a.v[0] * b.v[0]; for (int k = 1; k < N; k++) d = a.v[k] * b.v[k] + d; return d; } \
+    static inline float  mul(const vec<N>& a, const vec<N>& b) { return dot(a, b); }
+HLSL_VEC(2) HLSL_VEC(3) HLSL_VEC(4)
+static inline float  pow(float a, float b) { return hlsl_pow(a, b); }
+static inline float  saturate(float a) { return hlsl_saturate(a); }
+static inline float  frac(float a) { return a - floorf(a); }
+static inline float3 mul(const float3x3& M, const float3& a)
+{
+    float3 r;
+    for (int i = 0; i < 3; i++) r.v[i] = dot(float3(M.m[3 * i], M.m[3 * i + 1], M.m[3 * i + 2]), a);
+    return r;
+}
+
+struct SamplerState { int linear = 0; };
+struct hlsl_sample : float4 {                               // what Sample returns: a float4 that also truncates to its first component
+    hlsl_sample(float a, float b, float c, float d) : float4(a, b, c, d) {}      // ("float y1 = texY.Sample(...)", Shaders.cpp:234-235)
+    operator float() const { return v[0]; }
+};
+struct Texture2D {
+    const float* data = nullptr; int tw = 0, th = 0;                          // RGBA float texels as the UNORM view returns them, row-major
+    void bind(const float* d, int w_, int h_) { data = d; tw = w_; th = h_; }
+    const float* texel(int ix, int iy) const
+    {
+        ix = ix < 0 ? 0 : (ix >= tw ? tw - 1 : ix); iy = iy < 0 ? 0 : (iy >= th ? th - 1 : iy);
+        return data + ((size_t)iy * tw + ix) * 4;
+    }
+    hlsl_sample Sample(const SamplerState& s, const float2& uv, const int2& off = int2(0, 0)) const
+    {
+        if (!s.linear) {
+            const float* p = texel((int)floorf(uv.v[0] * (float)tw) + off.x, (int)floorf(uv.v[1] * (float)th) + off.y);
+            return hlsl_sample(p[0], p[1], p[2], p[3]);
+        }
+        const float px = uv.v[0] * (float)tw - 0.5f, py = uv.v[1] * (float)th - 0.5f;
+        const float x0 = floorf(px), y0 = floorf(py), fx = px - x0, fy = py - y0;
+        const int ix = (int)x0 + off.x, iy = (int)y0 + off.y;
+        const float *c00 = texel(ix, iy), *c10 = texel(ix + 1, iy), *c01 = texel(ix, iy + 1), *c11 = texel(ix + 1, iy + 1);
+        float r[4];
+        for (int k = 0; k < 4; k++) {
+            const float top = c00[k] * (1.0f - fx) + c10[k] * fx, bot = c01[k] * (1.0f - fx) + c11[k] * fx;
+            r[k] = top * (1.0f - fy) + bot * fy;
+        }
+        return hlsl_sample(r[0], r[1], r[2], r[3]);
+    }
+};

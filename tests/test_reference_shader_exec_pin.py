@@ -1,0 +1,144 @@
+"""Eighth pin: the reference's resize and final-pass PIXEL SHADERS, executed.
+
+Shaders/d3d11/ps_interpolation_spline4.hlsl (Mitchell, Catmull-Rom), ps_interpolation_lanczos2.hlsl, ps_interpolation_lanczos3.hlsl,
+ps_convolution.hlsl with each filter of Shaders/resize/convolution_filters.hlsl (box, bilinear, Hamming, bicubic A=-0.5 / -1.5, Lanczos3),
+both AXIS builds of each, and ps_final_pass.hlsl for QUANTIZATION 255 / 1023 -- the 22 shader builds the reference's resize and final stages
+choose from -- are assembled where they lie into one C++ unit (oracle/ref_stub/gen_hlsl_shaders.py applies syntax edits only: register /
+semantic annotations off, cbuffer -> namespace, [loop] off, file-scope `static const` -> macro, the #include spliced in; the arithmetic
+lines reach g++ as written) over a Texture2D / point SamplerState model (oracle/ref_stub/hlsl_compat_shaders.h), compiled with
+-fsingle-precision-constant -ffp-contract=off into oracle/_ref/libref_hlsl_shaders.so.  Nothing is copied into the repo.
+
+Each shader then draws whole rectangles of random texels (offset source rects, rects that touch the texture border so CLAMP addressing
+takes part, non-integer ratios) and the oracle's LITERAL mode draws the same rectangles through resize_pass / final_pass
+(oracle/orc_core.inc) on RAW surfaces.  LITERAL claims to be the shader text in written order, one IEEE operation per operation, libm sin /
+cos: so the float4 results must be BIT-EQUAL, the D3D11 lanczos3 shader's Q1 := Q0 quirk (ps_interpolation_lanczos3.hlsl:33-34) included.
+SPEC mode -- the contract the CUDA kernels are bit-exact with (tests/test_gpu_parity.py) -- differs from LITERAL by fused mads, folded
+literal quotients and the fixed sin / cos polynomials; its distance from the executed reference text is asserted too.
+
+Texture sizes are powers of two so that texcoord = texel coordinate / size and texcoord * wh are exact: the test then feeds the shaders the
+interpolated TEXCOORD an ideal rasteriser produces (origin + (i + .5) * srcLen / dstLen), which is what the oracle states."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import orclib as O
+
+REF = os.path.join(O.ORC_DIR, "_ref", "libref_hlsl_shaders.so")
+pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libref_hlsl_shaders.so not built (reference tree absent at build time)")
+
+FP = C.POINTER(C.c_float)
+f32 = np.float32
+U, D = O.UPSCALE, O.DOWNSCALE
+
+
+def _libs():
+    R = C.CDLL(REF); L = O.lib()
+    R.ref_hlsl_run.argtypes = [C.c_char_p, FP, C.c_int, C.c_int, C.c_int, FP, C.c_int, C.c_int, FP, C.c_int, C.c_float, C.c_float, FP]
+    R.ref_hlsl_shader_count.restype = C.c_int
+    R.ref_hlsl_shader_name.restype = C.c_char_p; R.ref_hlsl_shader_name.argtypes = [C.c_int]
+    L.orc_test_resize_draw.argtypes = [C.c_int] * 5 + [FP, C.c_int, C.c_int, C.c_int * 4, C.c_int, C.c_int, FP]
+    L.orc_test_final_pass.argtypes = [C.c_int, FP, C.c_int, C.c_int, C.c_float, FP]
+    L.orc_dither_thresholds.restype = C.POINTER(C.c_uint16)
+    return R, L
+
+
+def _p(a):
+    return a.ctypes.data_as(FP)
+
+
+def _draw(R, L, name, axis, kind, filt, W, H, rect, ow, oh, seed):
+    """-> (reference shader's RGB, oracle LITERAL RGB, oracle SPEC RGB) for one draw of in-rect `rect` of a W x H texture to ow x oh pixels"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tex = rng.uniform(0, 1, (H, W, 4)).astype(f32)
+    l, t, r, b = rect
+    gx = f32(r - l) / f32(ow); gy = f32(b - t) / f32(oh)                       # TextureResizeShader :351-354: scale = src size / dst size
+    cx = (np.arange(ow, dtype=f32) + f32(.5)) * gx + f32(l)
+    cy = (np.arange(oh, dtype=f32) + f32(.5)) * gy + f32(t)
+    uv = np.empty((oh, ow, 2), f32); uv[..., 0] = (cx / f32(W))[None, :]; uv[..., 1] = (cy / f32(H))[:, None]
+    ref = np.empty((oh, ow, 4), f32)
+    assert R.ref_hlsl_run(name.encode(), _p(tex), W, H, 0, None, 0, 0, _p(uv), ow * oh, gx, gy, _p(ref)) == 0
+    rgb = np.ascontiguousarray(tex[..., :3])
+    outs = []
+    for mode in (1, 0):
+        o = np.empty((oh, ow, 3), f32)
+        assert L.orc_test_resize_draw(mode, axis, kind, filt, O.VARIANT_D3D11, _p(rgb), W, H, (C.c_int * 4)(*rect), ow, oh, _p(o)) == 0
+        outs.append(o)
+    return np.ascontiguousarray(ref[..., :3]), outs[0], outs[1]
+
+
+INTERP = [("mitchell4", U["Mitchell"]), ("catmull4", U["CatmullRom"]), ("lanczos2", U["Lanczos2"]), ("lanczos3", U["Lanczos3"])]
+CONV = [("box", D["Box"]), ("bilinear", D["Bilinear"]), ("hamming", D["Hamming"]), ("bicubic05", D["Bicubic"]), ("bicubic15", D["BicubicSharp"]),
+        ("lanczos", D["Lanczos"])]
+# (W, H, in rect, out w, out h): the filtered axis is stretched / shrunk, the other one is point sampled (sizes equal or not)
+UP_X = [(64, 32, (0, 0, 64, 32), 128, 32), (64, 32, (3, 2, 61, 30), 97, 28), (64, 32, (0, 0, 64, 32), 173, 32), (32, 16, (5, 1, 30, 16), 25, 15),
+        (128, 8, (0, 0, 128, 8), 640, 8)]
+DN_X = [(128, 32, (0, 0, 128, 32), 64, 32), (128, 32, (3, 2, 125, 30), 37, 28), (256, 8, (0, 0, 256, 8), 61, 8), (128, 16, (1, 0, 128, 16), 100, 16),
+        (512, 4, (0, 0, 512, 4), 43, 4)]
+SPEC_ABS_TOL = 4 * 2.0 ** -23        # SPEC vs the executed text, texels in [0, 1]: measured <= 1.2e-7 (1 ULP at 1.0) on these draws; asserted at 4 ULP
+
+
+def _transpose(g):
+    W, H, (l, t, r, b), ow, oh = g
+    return (H, W, (t, l, b, r), oh, ow)
+
+
+@pytest.mark.parametrize("name,filt", INTERP, ids=[n for n, _ in INTERP])
+@pytest.mark.parametrize("axis", [0, 1], ids=["x", "y"])
+def test_interpolation_shaders_equal_the_reference_hlsl(name, filt, axis):
+    R, L = _libs()
+    worst = 0.0
+    for k, g in enumerate(UP_X):
+        W, H, rect, ow, oh = g if axis == 0 else _transpose(g)
+        ref, lit, spec = _draw(R, L, "%s_%s" % (name, "xy"[axis]), axis, 1, filt, W, H, rect, ow, oh, seed=10 + k)
+        assert np.array_equal(ref.view(np.uint32), lit.view(np.uint32)), (name, axis, g, int((ref.view(np.uint32) != lit.view(np.uint32)).sum()))
+        worst = max(worst, float(np.abs(ref.astype(np.float64) - spec).max()))
+    assert worst <= SPEC_ABS_TOL, worst
+
+
+@pytest.mark.parametrize("name,filt", CONV, ids=[n for n, _ in CONV])
+@pytest.mark.parametrize("axis", [0, 1], ids=["x", "y"])
+def test_convolution_shaders_equal_the_reference_hlsl(name, filt, axis):
+    R, L = _libs()
+    worst = 0.0
+    for k, g in enumerate(DN_X):
+        W, H, rect, ow, oh = g if axis == 0 else _transpose(g)
+        ref, lit, spec = _draw(R, L, "conv_%s_%s" % (name, "xy"[axis]), axis, 2, filt, W, H, rect, ow, oh, seed=40 + k)
+        assert np.array_equal(ref.view(np.uint32), lit.view(np.uint32)), (name, axis, g, int((ref.view(np.uint32) != lit.view(np.uint32)).sum()))
+        worst = max(worst, float(np.abs(ref.astype(np.float64) - spec).max()))
+    assert worst <= SPEC_ABS_TOL, worst
+
+
+def test_every_assembled_shader_is_exercised():
+    R, _ = _libs()
+    names = {R.ref_hlsl_shader_name(i).decode() for i in range(R.ref_hlsl_shader_count())}
+    want = {"%s_%s" % (n, a) for n, _ in INTERP for a in "xy"} | {"conv_%s_%s" % (n, a) for n, _ in CONV for a in "xy"} | {"final_8", "final_10"}
+    assert names == want
+
+
+@pytest.mark.parametrize("name,Q", [("final_8", 255.0), ("final_10", 1023.0)])
+def test_final_pass_equals_the_reference_hlsl(name, Q):
+    """ps_final_pass.hlsl: floor(pixel * QUANTIZATION + dither) / QUANTIZATION with the 32x32 dither texture addressed by
+    Tex * (size / 32) through a WRAP sampler (FinalPass, DX11VideoProcessor.cpp:3204) -- the shader's float4 against final_pass in LITERAL
+    and SPEC mode (bit-equal both: the mad's fusion cannot move a floor here unless the sum sits within half an ULP of an integer), and
+    the 8 / 10 bit codes after the render-target conversion."""
+    R, L = _libs()
+    K = np.ctypeslib.as_array(L.orc_dither_thresholds(), (1024,)).astype(f32) / f32(1024)
+    dither = np.ascontiguousarray(np.repeat(K.reshape(32, 32, 1), 4, axis=2))
+    W, H = 128, 64
+    rng = np.random.Generator(np.random.PCG64(5))
+    tex = rng.uniform(-0.05, 1.05, (H, W, 4)).astype(f32)
+    tex[:8] = rng.integers(0, 1024, (8, W, 4)).astype(f32) / f32(1023)           # the values a 10-bit intermediate texture returns
+    tex[8:16] = rng.integers(0, 256, (8, W, 4)).astype(f32) / f32(255)
+    uv = np.empty((H, W, 2), f32)
+    uv[..., 0] = ((np.arange(W, dtype=f32) + f32(.5)) / f32(W))[None, :]; uv[..., 1] = ((np.arange(H, dtype=f32) + f32(.5)) / f32(H))[:, None]
+    ref = np.empty((H, W, 4), f32)
+    assert R.ref_hlsl_run(name.encode(), _p(tex), W, H, 0, _p(dither), 32, 32, _p(uv), W * H, f32(W) / f32(32), f32(H) / f32(32), _p(ref)) == 0
+    rgb = np.ascontiguousarray(tex[..., :3])
+    for mode in (1, 0):
+        o = np.empty((H, W, 3), f32)
+        assert L.orc_test_final_pass(mode, _p(rgb), W, H, Q, _p(o)) == 0
+        assert np.array_equal(np.ascontiguousarray(ref[..., :3]).view(np.uint32), o.view(np.uint32)), (name, mode)
+    codes = np.floor(np.clip(ref[..., :3].astype(np.float64), 0, 1) * Q + 0.5)     # D3D11 float -> UNORM
+    assert codes.min() == 0 and codes.max() == Q                                    # the sample covers the whole code range

@@ -18,6 +18,27 @@ def csrc_sha256():
     return h.hexdigest()
 
 
+def kernel_sass_sha256(kernel_regex=r"k_strip2xINS_8StripCfgILi128ELi8ELi8ELi12ELi4ELi8ELi19EEELi6ELb1ELi1ELi0E"):
+    """sha256 over the SASS instruction text (cuobjdump -sass, addresses and encodings stripped) of the captured frame kernel as it sits in
+    the built library: the identity of the BINARY the capture's counters belong to.  An edit to a header that the kernel does not
+    instantiate leaves it unchanged; None when cuobjdump or the library is missing."""
+    lib = os.path.join(ROOT, "videorenderer_b200", "libmpcvr_b200.so")
+    try:
+        sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, timeout=300).stdout
+    except Exception:
+        return None
+    h = hashlib.sha256(); cur = False; n = 0
+    for ln in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", ln)
+        if m:
+            cur = bool(re.search(kernel_regex, m.group(1))); continue
+        if cur:
+            m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?)\s*/\* 0x[0-9a-f]+ \*/", ln)
+            if m:
+                h.update(m.group(1).encode()); h.update(b"\n"); n += 1
+    return h.hexdigest() if n else None
+
+
 def main():
     rep = sys.argv[1]; pat = re.compile(sys.argv[2] if len(sys.argv) > 2 else "k_strip2x|k_fused2x")
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -33,7 +54,7 @@ def main():
         cap = {"kernel": d["Kernel Name"], "report": os.path.basename(rep), "dram_bytes_read": b("dram__bytes_read.sum"), "dram_bytes_write": b("dram__bytes_write.sum"),
                "warp_instr_per_launch": int(float(d["smsp__inst_executed.sum"])), "gpu_time_us": float(d["gpu__time_duration.sum"]),
                "issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]), "registers_per_thread": int(float(d["launch__registers_per_thread"])),
-               "csrc_sha256": csrc_sha256()}
+               "csrc_sha256": csrc_sha256(), "kernel_sass_sha256": kernel_sass_sha256()}
         cap["dram_bytes_per_launch"] = cap["dram_bytes_read"] + cap["dram_bytes_write"]
         # packed fp32 instructions (two FMA-pipe cycles each) from the source page of the same report: the input of the issue-cost model
         # in DESIGN.md 4.1 (about 2.35 scheduler cycles per packed, 1.1 per other warp instruction; tools/role_bench.cu)

@@ -428,14 +428,25 @@ __device__ __forceinline__ f3 convert_color(const ColorParams& P, f3 yuv, const 
         }
         c.x = sat(c.x); c.y = sat(c.y); c.z = sat(c.z);                              // :870-872
         if (D && D->l2_enabled) {                                                   // DolbyVisionTrims, :787-795, :873-877
-            c.x = powr(fma_rn(c.x, D->l2_slope, D->l2_offset), D->l2_power);
-            c.y = powr(fma_rn(c.y, D->l2_slope, D->l2_offset), D->l2_power);
-            c.z = powr(fma_rn(c.z, D->l2_slope, D->l2_offset), D->l2_power);
+            // The shader's text has no guard here: a negative pow base, a zero luminance (0 / 0), a zero channel under a non-positive
+            // saturation gain (0 * inf) or a value past the pole of ST2084ToLinear (c2 - c3 * v^(1/m2) <= 0) make NaN, which
+            // mul(matrix_conv_prim, ...) spreads over the pixel and the final saturate turns into 0: the reference's pixel is (0, 0, 0).
+            // powr returns 0 for such bases, so the cases are flagged explicitly (same tests as the oracle's dovi_trims).
+            const float b0 = fma_rn(c.x, D->l2_slope, D->l2_offset), b1 = fma_rn(c.y, D->l2_slope, D->l2_offset), b2 = fma_rn(c.z, D->l2_slope, D->l2_offset);
+            bool poisoned = (b0 < 0.0f) || (b1 < 0.0f) || (b2 < 0.0f);
+            c.x = powr(b0, D->l2_power);
+            c.y = powr(b1, D->l2_power);
+            c.z = powr(b2, D->l2_power);
             const float Y = fma_rn(0.0593f, c.z, fma_rn(0.6780f, c.y, __fmul_rn(0.2627f, c.x)));
             const float g = __fadd_rn(1.0f, D->l2_chroma_weight);
+            poisoned = poisoned || (Y == 0.0f) || (!(D->l2_saturation_gain > 0.0f) && (c.x == 0.0f || c.y == 0.0f || c.z == 0.0f));
             c.x = __fmul_rn(c.x, powr(__fdiv_rn(__fmul_rn(g, c.x), Y), D->l2_saturation_gain));
             c.y = __fmul_rn(c.y, powr(__fdiv_rn(__fmul_rn(g, c.y), Y), D->l2_saturation_gain));
             c.z = __fmul_rn(c.z, powr(__fdiv_rn(__fmul_rn(g, c.z), Y), D->l2_saturation_gain));
+            poisoned = poisoned || !(fma_rn(-ST2084_C3, powr(c.x, P.inv_m2), ST2084_C2) > 0.0f)
+                                || !(fma_rn(-ST2084_C3, powr(c.y, P.inv_m2), ST2084_C2) > 0.0f)
+                                || !(fma_rn(-ST2084_C3, powr(c.z, P.inv_m2), ST2084_C2) > 0.0f);
+            if (poisoned) { f3 z; z.x = 0.0f; z.y = 0.0f; z.z = 0.0f; return z; }
         }
         f3 h;                                                                       // :878-880; x / HABLE_DIV -> x * (1/HABLE_DIV)
         h.x = __fmul_rn(hable(P, st2084_to_linear(P, c.x, P.lum_scale)), P.hable_rdiv);
