@@ -606,6 +606,26 @@ def test_dolby_vision_l2_trims(scenario):
     _check(case, "natural", 71)
 
 
+@pytest.mark.parametrize("trims", ["negative_offset", "bright", "bright_sat", "zero_satgain"])
+def test_dolby_vision_l2_trims_nan_pixels(trims):
+    """DolbyVisionTrims has no guard in the reference's shader: a negative pow base, a zero luminance or a value past ST2084ToLinear's pole
+    make NaN, the gamut matrix spreads it over the pixel and the final saturate writes (0, 0, 0).  tests/test_reference_convert_exec_pin.py
+    shows it on the executed shader text and holds the oracle to it; here the kernel against the oracle, with trim sets that provoke each
+    cause on full-range noise (1:1 so the black pixels reach the output unfiltered)."""
+    l2 = dict(negative_offset=[(3079, 2048, 1200, 2048, 2048, 2300)], bright=[(3079, 4095, 4095, 4095, 2048, 2048)],
+              bright_sat=[(3079, 4095, 3500, 4095, 4095, 4095)], zero_satgain=[(3079, 2100, 2000, 2048, 2200, 2048)])[trims]
+    ex = O.exfmt(chroma=5, range_=1, matrix=0, prim=0, trc=0)
+    case = H.Case(O.CF["P010"], 64, 36, 64, 36, ex, up=O.UPSCALE["Nearest"], dovi=H.make_dovi(72, mmr=1, l2=l2, source_max_pq=3696),
+                  hdr=dict(out=0, display=1000), name="dovi_l2_nan_" + trims)
+    _check(case, "fullnoise", 72)
+    if trims != "zero_satgain":
+        codes = H.make_codes(case.cf, case.w, case.h, "fullnoise", 72)
+        _, _, planes, pitches = H.pack(case.cf, case.w, case.h, codes)
+        rgb = H.rgb_view(H.run_oracle(case, planes, pitches), case.backbuffer)
+        black = int(np.all(rgb == 0, axis=2).sum())
+        assert 0 < black < rgb.shape[0] * rgb.shape[1], black
+
+
 def _rpu_mastering(dv):
     """m_DoviMaxMasteringLuminance / m_DoviMinMasteringLuminance as CopySample derives them from the RPU (:2472-2490)"""
     import ctypes as C
