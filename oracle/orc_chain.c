@@ -117,6 +117,26 @@ int orc_test_final_pass(int mode, const float* in, int w, int h, float Q, float*
     return -1;
 }
 
+/* tm_pixel (ps_hdr10_tonemap.hlsl's main) on n RGB PQ pixels with the constant-buffer values given directly: hp = MasteringMinLuminanceNits,
+ * MasteringMaxLuminanceNits, maxCLL, maxFALL, displayMaxNits, selection; l2 = {ChromaWeight, SaturationGain, TrimSlope, TrimOffset, TrimPower}
+ * or NULL -- tests/test_reference_convert_exec_pin.py runs the reference's shader file as C++ on the same pixels.  mode 0 SPEC, 1 LITERAL. */
+int orc_test_tonemap(int mode, const float hp[6], const float* l2, const float* in, float* out, int n)
+{
+    if (mode == 0) {
+        tmparams_spec T = { hp[0], hp[1], hp[2], hp[3], hp[4], (int)hp[5], l2 != NULL, 0, 0, 0, 0, 0 };
+        if (l2) { T.l2_cw = l2[0]; T.l2_sg = l2[1]; T.l2_slope = l2[2]; T.l2_offset = l2[3]; T.l2_power = l2[4]; }
+        for (int i = 0; i < n; i++) tm_pixel_spec(&T, in + 3 * i, out + 3 * i);
+        return 0;
+    }
+    if (mode == 1) {
+        tmparams_lit T = { hp[0], hp[1], hp[2], hp[3], hp[4], (int)hp[5], l2 != NULL, 0, 0, 0, 0, 0 };
+        if (l2) { T.l2_cw = l2[0]; T.l2_sg = l2[1]; T.l2_slope = l2[2]; T.l2_offset = l2[3]; T.l2_power = l2[4]; }
+        for (int i = 0; i < n; i++) tm_pixel_lit(&T, in + 3 * i, out + 3 * i);
+        return 0;
+    }
+    return -1;
+}
+
 /* The DolbyConstants the oracle derives for a display (SPEC mode's build_dovi: Level 2 trim selection / interpolation,
  * DX11VideoProcessor.cpp:2383-2469, and the +-0.5 of SetDolbyVisionDynamicParams :956-960): {chroma_weight, saturation_gain, slope, offset, power}.
  * Returns l2_enabled. */

@@ -77,6 +77,7 @@ def include(name):
 def translate(text):
     regs = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"Texture2D\s+(\w+)\s*:\s*register\(t(\d+)\)", text))
     text = re.sub(r"^//#include (\S+)$", lambda m: include(m.group(1)), text, flags=re.M)
+    text = re.sub(r'^#include "\.\./convert/(\S+)"\s*$', lambda m: include(m.group(1)), text, flags=re.M)
     text = re.sub(r"cbuffer\s+\w+\s*:\s*register\(\w+\)\s*\{", "namespace {", text)
     text = re.sub(r"\s*:\s*register\(\w+\)", "", text)
     text = re.sub(r"\s*:\s*(SV_POSITION|TEXCOORD|SV_Target)\b", "", text)
@@ -132,6 +133,20 @@ for i, (name, fmt, exf, siting, scaler, conv, blend, dovi) in enumerate(CASES):
     print("}")
     print("}  // namespace %s" % ns)
     rows.append('{ "%s", %d, %#010xu, %d, %d, %d, %d, %d, %d, %d, %s::run }' % (name, cf, ex, siting, scaler, conv, blend, dovi, W, H, ns))
+# ---- Shaders/d3d11/ps_hdr10_tonemap.hlsl (the HDR10 local tone-mapping post-scale step), a file of the tree rather than generated text
+text, regs, macros = translate(open("%s/Shaders/d3d11/ps_hdr10_tonemap.hlsl" % REF, encoding="utf-8", errors="replace").read())
+print("// ======== ps_hdr10_tonemap.hlsl")
+print("namespace tm_shader {")
+print(text)
+print("static float4 run(const float* rgba, int tw, int th, const float* hp, const float* l2, float u, float v) {")
+print("    tex.bind(rgba, tw, th); samp.linear = 0;")
+print("    MasteringMinLuminanceNits = hp[0]; MasteringMaxLuminanceNits = hp[1]; maxCLL = hp[2]; maxFALL = hp[3]; displayMaxNits = hp[4]; selection = (uint)hp[5];")
+print("    L2Enabled = l2 ? 1u : 0u;")
+print("    if (l2) { ChromaWeight = l2[0]; SaturationGain = l2[1]; TrimSlope = l2[2]; TrimOffset = l2[3]; TrimPower = l2[4]; }")
+print("    PS_INPUT in; in.Tex = float2(u, v);")
+print("    return ps_main(in);")
+print("}")
+print("}  // namespace tm_shader")
 print("struct ConvCase { const char* name; int cformat; unsigned exfmt; int siting, scaler, convert_type, blend, dovi, W, H; float4 (*run)(const ConvArgs&, float, float); };")
 print("static const ConvCase g_cases[] = {\n    %s\n};" % ",\n    ".join(rows))
 print("static const int g_ncases = %d;" % len(rows))

@@ -33,6 +33,7 @@ template<int N, int... I> struct swz {                     // a view of componen
     operator vec<M>() const { vec<M> r; const int idx[M] = { I... }; for (int k = 0; k < M; k++) r.v[k] = v[idx[k]]; return r; }
     swz& operator=(const vec<M>& o) { const int idx[M] = { I... }; for (int k = 0; k < M; k++) v[idx[k]] = o.v[k]; return *this; }
     swz& operator=(const swz& o) { const vec<M> t = o; return *this = t; }
+    swz& operator*=(float s) { const int idx[M] = { I... }; for (int k = 0; k < M; k++) v[idx[k]] = v[idx[k]] * s; return *this; }
 };
 
 template<> struct vec<2> {
@@ -47,7 +48,7 @@ template<> struct vec<2> {
 };
 template<> struct vec<3> {
     union { float v[3]; struct { float x, y, z; }; struct { float r, g, b; };
-            swz<3, 0, 0, 1> xxy; swz<3, 1, 2, 2> yzz; swz<3, 0, 1> xy, rg; swz<3, 0, 1, 2> xyz, rgb; };
+            swz<3, 0, 0, 1> xxy; swz<3, 1, 2, 2> yzz; swz<3, 0, 1> xy, rg; swz<3, 1, 2> yz; swz<3, 0, 1, 2> xyz, rgb; };
     vec() : v{0, 0, 0} {}
     vec(float s) : v{s, s, s} {}
     vec(float a, float b, float c) : v{a, b, c} {}
@@ -100,6 +101,10 @@ HLSL_VEC(2) HLSL_VEC(3) HLSL_VEC(4)
 static inline float  pow(float a, float b) { return hlsl_pow(a, b); }
 static inline float  saturate(float a) { return hlsl_saturate(a); }
 static inline float  frac(float a) { return a - floorf(a); }
+static inline float  max(float a, float b) { return hlsl_max(a, b); }
+static inline float  min(float a, float b) { return (a <= b || b != b) ? a : b; }                 // D3D11: min(NaN, b) = b
+static inline float  clamp(float x, float lo, float hi) { return min(max(x, lo), hi); }
+static inline float  lerp(float a, float b, float t) { return t * (b - a) + a; }                  // fxc: mad(t, b - a, a)
 static inline float3 mul(const float3x3& M, const float3& a)
 {
     float3 r;
