@@ -109,6 +109,14 @@ int orc_test_resize_draw(int mode, int axis, int kind, int filter, int variant, 
     }
     return -1;
 }
+/* one Jinc2 draw (jinc_pass: ps_resize_onepass_jinc2.hlsl) of in_rect of a w x h RAW surface onto ow x oh pixels, mode 0 SPEC / 1 LITERAL */
+int orc_test_jinc_draw(int mode, const float* in, int w, int h, const int in_rect[4], int ow, int oh, float* out)
+{
+    const int out_rect[4] = {0, 0, ow, oh};
+    if (mode == 0) { surf_spec a = {w, h, ORC_SURF_RAW, (float*)in}, b = {ow, oh, ORC_SURF_RAW, out}; return jinc_pass_spec(&a, &b, in_rect, out_rect, 1); }
+    if (mode == 1) { surf_lit a = {w, h, ORC_SURF_RAW, (float*)in}, b = {ow, oh, ORC_SURF_RAW, out}; return jinc_pass_lit(&a, &b, in_rect, out_rect, 1); }
+    return -1;
+}
 int orc_test_final_pass(int mode, const float* in, int w, int h, float Q, float* out)
 {
     const int rect[4] = {0, 0, w, h};

@@ -147,6 +147,22 @@ print("    PS_INPUT in; in.Tex = float2(u, v);")
 print("    return ps_main(in);")
 print("}")
 print("}  // namespace tm_shader")
+# ---- Shaders/examples/ps_resize_onepass_jinc2.hlsl (the "Jinc2m" upscaler, resource IDF_PS_11_INTERP_JINC2)
+src = open("%s/Shaders/examples/ps_resize_onepass_jinc2.hlsl" % REF, encoding="utf-8", errors="replace").read()
+src, n = re.subn(r"return \((x == float4\(0, 0, 0, 0\))\)\s*\?\s*(.*?)\s*:\s*(.*?);", r"return hlsl_select(\1, \2, \3);", src, count=1, flags=re.S)
+assert n == 1, "jinc2: the vector conditional of resampler() was not found"
+text, regs, macros = translate(src)
+print("// ======== ps_resize_onepass_jinc2.hlsl")
+print("namespace jinc2_shader {")
+print(text)
+for m in macros:
+    print("#undef %s" % m)
+print("static float4 run(const float* rgba, int tw, int th, float u, float v) {")
+print("    tex.bind(rgba, tw, th); samp.linear = 0; wh = float2((float)tw, (float)th); dxdy = float2(1.0f / (float)tw, 1.0f / (float)th);")
+print("    PS_INPUT in; in.Tex = float2(u, v);")
+print("    return ps_main(in);")
+print("}")
+print("}  // namespace jinc2_shader")
 print("struct ConvCase { const char* name; int cformat; unsigned exfmt; int siting, scaler, convert_type, blend, dovi, W, H; float4 (*run)(const ConvArgs&, float, float); };")
 print("static const ConvCase g_cases[] = {\n    %s\n};" % ",\n    ".join(rows))
 print("static const int g_ncases = %d;" % len(rows))

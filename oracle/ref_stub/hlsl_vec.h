@@ -24,6 +24,7 @@ static inline float hlsl_pow(float x, float y) { return exp2f(y * log2f(x)); }
 // produce NaN on pixels whose trimmed luminance is 0 -- 0 / 0 in DolbyVisionTrims, Shaders.cpp:787-795 -- and the following saturate /
 // max turn it into 0 on the GPU.)
 static inline float hlsl_max(float a, float b) { return (a >= b || b != b) ? a : b; }
+static inline float hlsl_min(float a, float b) { return (a <= b || b != b) ? a : b; }
 static inline float hlsl_saturate(float a) { return !(a > 0.0f) ? 0.0f : (a > 1.0f ? 1.0f : a); }
 
 template<int N> struct vec;
@@ -85,6 +86,12 @@ struct float3x3 { float m[9]; };
 #define HLSL_VEC(N) \
     HLSL_BINOP(N, +) HLSL_BINOP(N, -) HLSL_BINOP(N, *) HLSL_BINOP(N, /) \
     struct bool##N { bool v[N]; }; \
+    static inline bool##N operator==(const vec<N>& a, const vec<N>& b) { bool##N r; for (int k = 0; k < N; k++) r.v[k] = a.v[k] == b.v[k]; return r; } \
+    static inline vec<N> sin(const vec<N>& a) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = sinf(a.v[k]); return r; } \
+    static inline vec<N> floor(const vec<N>& a) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = floorf(a.v[k]); return r; } \
+    static inline vec<N> min(const vec<N>& a, const vec<N>& b) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = hlsl_min(a.v[k], b.v[k]); return r; } \
+    static inline vec<N> clamp(const vec<N>& x, const vec<N>& lo, const vec<N>& hi) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = hlsl_min(hlsl_max(x.v[k], lo.v[k]), hi.v[k]); return r; } \
+    static inline vec<N> lerp(const vec<N>& a, const vec<N>& b, float t) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = t * (b.v[k] - a.v[k]) + a.v[k]; return r; } \
     static inline bool##N operator<=(const vec<N>& a, float b) { bool##N r; for (int k = 0; k < N; k++) r.v[k] = a.v[k] <= b; return r; } \
     static inline vec<N> hlsl_select(const bool##N& c, const vec<N>& a, const vec<N>& b) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = c.v[k] ? a.v[k] : b.v[k]; return r; } \
     static inline vec<N> operator-(const vec<N>& a) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = -a.v[k]; return r; } \
@@ -102,7 +109,7 @@ static inline float  pow(float a, float b) { return hlsl_pow(a, b); }
 static inline float  saturate(float a) { return hlsl_saturate(a); }
 static inline float  frac(float a) { return a - floorf(a); }
 static inline float  max(float a, float b) { return hlsl_max(a, b); }
-static inline float  min(float a, float b) { return (a <= b || b != b) ? a : b; }                 // D3D11: min(NaN, b) = b
+static inline float  min(float a, float b) { return hlsl_min(a, b); }                              // D3D11: min(NaN, b) = b
 static inline float  clamp(float x, float lo, float hi) { return min(max(x, lo), hi); }
 static inline float  lerp(float a, float b, float t) { return t * (b - a) + a; }                  // fxc: mad(t, b - a, a)
 static inline float3 mul(const float3x3& M, const float3& a)
@@ -111,6 +118,18 @@ static inline float3 mul(const float3x3& M, const float3& a)
     for (int i = 0; i < 3; i++) r.v[i] = dot(float3(M.m[3 * i], M.m[3 * i + 1], M.m[3 * i + 2]), a);
     return r;
 }
+
+// matrices of ps_resize_onepass_jinc2.hlsl: float4x4 = four float4 rows, float4x3 = four float3 rows; mul(row vector, matrix) and
+// mul(matrix, column vector), each component a mul followed by mads in row order
+struct float4x4 { float4 r[4]; float4& operator[](int i) { return r[i]; } const float4& operator[](int i) const { return r[i]; } };
+struct float4x3 { float3 r[4]; float4x3(const float3& a, const float3& b, const float3& c, const float3& d) : r{a, b, c, d} {} };
+static inline float3 mul(const float4& w, const float4x3& M)
+{
+    float3 o;
+    for (int k = 0; k < 3; k++) { float d = w.v[0] * M.r[0].v[k]; for (int i = 1; i < 4; i++) d = w.v[i] * M.r[i].v[k] + d; o.v[k] = d; }
+    return o;
+}
+static inline float4 mul(const float4x4& M, const float4& a) { float4 o; for (int i = 0; i < 4; i++) o.v[i] = dot(M.r[i], a); return o; }
 
 struct SamplerState { int linear = 0; };
 struct hlsl_sample : float4 {                               // what Sample returns: a float4 that also truncates to its first component

@@ -142,3 +142,38 @@ def test_final_pass_equals_the_reference_hlsl(name, Q):
         assert np.array_equal(np.ascontiguousarray(ref[..., :3]).view(np.uint32), o.view(np.uint32)), (name, mode)
     codes = np.floor(np.clip(ref[..., :3].astype(np.float64), 0, 1) * Q + 0.5)     # D3D11 float -> UNORM
     assert codes.min() == 0 and codes.max() == Q                                    # the sample covers the whole code range
+
+
+# ---- the one-pass Jinc2 upscaler (Shaders/examples/ps_resize_onepass_jinc2.hlsl, resource IDF_PS_11_INTERP_JINC2) ----
+REF_C = os.path.join(O.ORC_DIR, "_ref", "libref_hlsl_convert.so")       # the unit built over hlsl_vec.h also holds this shader
+
+
+@pytest.mark.skipif(not os.path.exists(REF_C), reason="oracle/_ref/libref_hlsl_convert.so not built")
+@pytest.mark.parametrize("geom", [(64, 32, (0, 0, 64, 32), 128, 64), (64, 32, (3, 2, 61, 30), 97, 45), (32, 32, (0, 0, 32, 32), 83, 71),
+                                  (16, 64, (1, 0, 16, 63), 40, 150), (64, 32, (0, 0, 64, 32), 64, 32)],
+                         ids=["2x", "offset_rect", "odd_ratio", "tall", "1to1"])
+def test_jinc2_shader_equals_the_reference_hlsl(geom):
+    """The two-dimensional 4x4 Jinc2 resampler with anti-ringing: distances to the 16 texels around floor(pc - .5), the windowed-jinc weight
+    of each (sin * sin / d^2, wa * wb at d = 0), mul(weights[r], float4x3(...)) row by row, the weight total, clamp to the four central
+    texels, lerp by 0.8 -- the shader text compiled as C++ (float4x4 / float4x3 / mul in hlsl_vec.h; resampler()'s vector conditional
+    rewritten to hlsl_select) against the oracle's jinc_pass in LITERAL mode, bit for bit, border clamping included."""
+    R = C.CDLL(REF_C); L = O.lib()
+    R.ref_jinc2_run.argtypes = [FP, C.c_int, C.c_int, FP, C.c_int, FP]
+    L.orc_test_jinc_draw.argtypes = [C.c_int, FP, C.c_int, C.c_int, C.c_int * 4, C.c_int, C.c_int, FP]
+    W, H, rect, ow, oh = geom
+    rng = np.random.Generator(np.random.PCG64(90 + ow))
+    tex = rng.uniform(0, 1, (H, W, 4)).astype(f32)
+    l, t, r, b = rect
+    gx = f32(r - l) / f32(ow); gy = f32(b - t) / f32(oh)
+    cx = (np.arange(ow, dtype=f32) + f32(.5)) * gx + f32(l); cy = (np.arange(oh, dtype=f32) + f32(.5)) * gy + f32(t)
+    uv = np.empty((oh, ow, 2), f32); uv[..., 0] = (cx / f32(W))[None, :]; uv[..., 1] = (cy / f32(H))[:, None]
+    ref = np.empty((oh, ow, 4), f32)
+    assert R.ref_jinc2_run(_p(tex), W, H, _p(uv), ow * oh, _p(ref)) == 0
+    rgb = np.ascontiguousarray(tex[..., :3])
+    lit = np.empty((oh, ow, 3), f32); spec = np.empty((oh, ow, 3), f32)
+    assert L.orc_test_jinc_draw(1, _p(rgb), W, H, (C.c_int * 4)(*rect), ow, oh, _p(lit)) == 0
+    assert L.orc_test_jinc_draw(0, _p(rgb), W, H, (C.c_int * 4)(*rect), ow, oh, _p(spec)) == 0
+    a = np.ascontiguousarray(ref[..., :3])
+    assert np.array_equal(a.view(np.uint32), lit.view(np.uint32)), (geom, int((a.view(np.uint32) != lit.view(np.uint32)).sum()))
+    assert np.all(ref[..., 3] == 1)
+    assert float(np.abs(a.astype(np.float64) - spec).max()) <= 1e-6            # SPEC: fused mads and the sin polynomial
