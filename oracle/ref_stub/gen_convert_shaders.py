@@ -163,6 +163,48 @@ print("    PS_INPUT in; in.Tex = float2(u, v);")
 print("    return ps_main(in);")
 print("}")
 print("}  // namespace jinc2_shader")
+# ---- the Direct3D 9 twins of the resize shaders (Shaders/d3d9/*.hlsl): same filters, texel-space texcoords that carry -0.5
+# (CDX9VideoProcessor::TextureResizeShader, DX9VideoProcessor.cpp:2853-2937), no duplicate Lanczos3 tap, no half-texel shift
+def adapt9(src):
+    src = src.replace('#include "../resize/convolution_filters.hlsl"', open("%s/Shaders/resize/convolution_filters.hlsl" % REF, encoding="utf-8", errors="replace").read())
+    src = src.replace("\r\n", "\n")
+    src = re.sub(r"\s*:\s*register\(\w+\)", "", src)
+    src = re.sub(r"\s*:\s*(TEXCOORD0|COLOR)\b", "", src)
+    src = src.replace("[loop] ", "")
+    src = re.sub(r"\bfloat4 main\s*\(", "float4 ps_main(", src)
+    src = re.sub(r"^static const float (\w+) = (.*);$", r"#define \1 (\2)", src, flags=re.M)
+    return src
+
+
+D9 = [("d9_mitchell4_x", "interpolation_spline4.hlsl", {"METHOD": "0", "AXIS": "0"}), ("d9_mitchell4_y", "interpolation_spline4.hlsl", {"METHOD": "0", "AXIS": "1"}),
+      ("d9_catmull4_x", "interpolation_spline4.hlsl", {"METHOD": "1", "AXIS": "0"}), ("d9_catmull4_y", "interpolation_spline4.hlsl", {"METHOD": "1", "AXIS": "1"}),
+      ("d9_lanczos2_x", "interpolation_lanczos2.hlsl", {"AXIS": "0"}), ("d9_lanczos2_y", "interpolation_lanczos2.hlsl", {"AXIS": "1"}),
+      ("d9_lanczos3_x", "interpolation_lanczos3.hlsl", {"AXIS": "0"}), ("d9_lanczos3_y", "interpolation_lanczos3.hlsl", {"AXIS": "1"})]
+for fname, fid, extra in (("box", "0", {}), ("bilinear", "1", {}), ("hamming", "2", {}), ("bicubic05", "3", {"A": "-0.5"}), ("bicubic15", "3", {"A": "-1.5"}), ("lanczos", "4", {})):
+    for ax in ("0", "1"):
+        dd = {"FILTER": fid, "AXIS": ax}; dd.update(extra)
+        D9.append(("d9_conv_%s_%s" % (fname, "xy"[int(ax)]), "convolution.hlsl", dd))
+SYMS9 = ["AXIS", "METHOD", "FILTER", "A", "PI", "filter_support", "support", "ss"]
+for ns, fname, defs in D9:
+    print("// ======== %s  <- Shaders/d3d9/%s  %s" % (ns, fname, " ".join("/D%s=%s" % kv for kv in defs.items())))
+    for sym in SYMS9:
+        print("#undef %s" % sym)
+    for kv in defs.items():
+        print("#define %s %s" % kv)
+    print("namespace %s {" % ns)
+    print(adapt9(open("%s/Shaders/d3d9/%s" % (REF, fname), encoding="utf-8", errors="replace").read()))
+    print("static float4 run(const float* rgba, int tw, int th, float tx, float ty, float sx, float sy) {")
+    print("    s0.bind(rgba, tw, th); dxdy = float2(1.0f / (float)tw, 1.0f / (float)th);")
+    if fname == "convolution.hlsl":
+        print("    scale = float2(sx, sy);")
+    print("    return ps_main(float2(tx, ty));")
+    print("}")
+    print("}  // namespace %s" % ns)
+for sym in SYMS9:
+    print("#undef %s" % sym)
+print("struct D9Entry { const char* name; float4 (*run)(const float*, int, int, float, float, float, float); };")
+print("static const D9Entry g_d9[] = { %s };" % ", ".join('{ "%s", %s::run }' % (ns, ns) for ns, _, _ in D9))
+print("static const int g_nd9 = %d;" % len(D9))
 print("struct ConvCase { const char* name; int cformat; unsigned exfmt; int siting, scaler, convert_type, blend, dovi, W, H; float4 (*run)(const ConvArgs&, float, float); };")
 print("static const ConvCase g_cases[] = {\n    %s\n};" % ",\n    ".join(rows))
 print("static const int g_ncases = %d;" % len(rows))

@@ -38,7 +38,7 @@ template<int N, int... I> struct swz {                     // a view of componen
 };
 
 template<> struct vec<2> {
-    union { float v[2]; struct { float x, y; }; struct { float r, g; }; };
+    union { float v[2]; struct { float x, y; }; struct { float r, g; }; swz<2, 0, 0, 1, 1> xxyy; };
     vec() : v{0, 0} {}
     vec(float s) : v{s, s} {}
     vec(float a, float b) : v{a, b} {}
@@ -49,7 +49,7 @@ template<> struct vec<2> {
 };
 template<> struct vec<3> {
     union { float v[3]; struct { float x, y, z; }; struct { float r, g, b; };
-            swz<3, 0, 0, 1> xxy; swz<3, 1, 2, 2> yzz; swz<3, 0, 1> xy, rg; swz<3, 1, 2> yz; swz<3, 0, 1, 2> xyz, rgb; };
+            swz<3, 0, 0, 1> xxy; swz<3, 1, 2, 2> yzz; swz<3, 0, 1> xy, rg; swz<3, 1, 2> yz; swz<3, 0, 1, 2> xyz, rgb; swz<3, 1, 0, 1, 2> yxyz; };
     vec() : v{0, 0, 0} {}
     vec(float s) : v{s, s, s} {}
     vec(float a, float b, float c) : v{a, b, c} {}
@@ -87,8 +87,8 @@ struct float3x3 { float m[9]; };
     HLSL_BINOP(N, +) HLSL_BINOP(N, -) HLSL_BINOP(N, *) HLSL_BINOP(N, /) \
     struct bool##N { bool v[N]; }; \
     static inline bool##N operator==(const vec<N>& a, const vec<N>& b) { bool##N r; for (int k = 0; k < N; k++) r.v[k] = a.v[k] == b.v[k]; return r; } \
-    static inline vec<N> sin(const vec<N>& a) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = sinf(a.v[k]); return r; } \
-    static inline vec<N> floor(const vec<N>& a) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = floorf(a.v[k]); return r; } \
+    static inline vec<N> hlsl_sin(const vec<N>& a) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = sinf(a.v[k]); return r; } \
+    static inline vec<N> hlsl_floor(const vec<N>& a) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = floorf(a.v[k]); return r; } \
     static inline vec<N> min(const vec<N>& a, const vec<N>& b) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = hlsl_min(a.v[k], b.v[k]); return r; } \
     static inline vec<N> clamp(const vec<N>& x, const vec<N>& lo, const vec<N>& hi) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = hlsl_min(hlsl_max(x.v[k], lo.v[k]), hi.v[k]); return r; } \
     static inline vec<N> lerp(const vec<N>& a, const vec<N>& b, float t) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = t * (b.v[k] - a.v[k]) + a.v[k]; return r; } \
@@ -162,3 +162,32 @@ struct Texture2D {
         return hlsl_sample(r[0], r[1], r[2], r[3]);
     }
 };
+
+// D3D9 flavour (Shaders/d3d9/*.hlsl): a `sampler` is a texture with its sampling state, read by tex2D(s, uv [, ddx, ddy])
+struct sampler {
+    const float* data = nullptr; int tw = 0, th = 0, wrap = 0;
+    void bind(const float* d, int w_, int h_, int wrap_ = 0) { data = d; tw = w_; th = h_; wrap = wrap_; }
+};
+static inline float4 tex2D(const sampler& s, const float2& uv)
+{
+    int ix = (int)floorf(uv.v[0] * (float)s.tw), iy = (int)floorf(uv.v[1] * (float)s.th);
+    if (s.wrap) { ix %= s.tw; if (ix < 0) ix += s.tw; iy %= s.th; if (iy < 0) iy += s.th; }
+    else { ix = ix < 0 ? 0 : (ix >= s.tw ? s.tw - 1 : ix); iy = iy < 0 ? 0 : (iy >= s.th ? s.th - 1 : iy); }
+    const float* p = s.data + ((size_t)iy * s.tw + ix) * 4;
+    return float4(p[0], p[1], p[2], p[3]);
+}
+static inline float4 tex2D(const sampler& s, const float2& uv, const float2&, const float2&) { return tex2D(s, uv); }   // explicit gradients: no mip levels here
+
+// scalar intrinsics whose C names would pick the double-precision C functions: HLSL's are single precision (libm's sinf, cosf, ...)
+static inline float hlsl_sin(float x) { return sinf(x); }
+static inline float hlsl_cos(float x) { return cosf(x); }
+static inline float hlsl_acos(float x) { return acosf(x); }
+static inline float hlsl_sqrt(float x) { return sqrtf(x); }
+static inline float hlsl_floor(float x) { return floorf(x); }
+static inline float hlsl_ceil(float x) { return ceilf(x); }
+#define sin hlsl_sin
+#define cos hlsl_cos
+#define acos hlsl_acos
+#define sqrt hlsl_sqrt
+#define floor hlsl_floor
+#define ceil hlsl_ceil

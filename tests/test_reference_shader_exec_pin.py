@@ -177,3 +177,45 @@ def test_jinc2_shader_equals_the_reference_hlsl(geom):
     assert np.array_equal(a.view(np.uint32), lit.view(np.uint32)), (geom, int((a.view(np.uint32) != lit.view(np.uint32)).sum()))
     assert np.all(ref[..., 3] == 1)
     assert float(np.abs(a.astype(np.float64) - spec).max()) <= 1e-6            # SPEC: fused mads and the sin polynomial
+
+
+# ---- the Direct3D 9 twins (Shaders/d3d9/*.hlsl) against the oracle's variant = D3D9 ----
+D9_INTERP = [("mitchell4", U["Mitchell"]), ("catmull4", U["CatmullRom"]), ("lanczos2", U["Lanczos2"]), ("lanczos3", U["Lanczos3"])]
+
+
+def _draw9(R, L, name, axis, kind, filt, W, H, rect, ow, oh, seed):
+    """as _draw, for a D3D9 shader: TEXCOORD0 is in texel units and carries the -0.5 CDX9VideoProcessor::TextureResizeShader gives the quad
+    (DX9VideoProcessor.cpp:2880-2883: tx0 = srcRect.left - 0.5, ...), i.e. tex = (origin + (i + .5) * scale) - 0.5"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tex = rng.uniform(0, 1, (H, W, 4)).astype(f32)
+    l, t, r, b = rect
+    gx = f32(r - l) / f32(ow); gy = f32(b - t) / f32(oh)
+    cx = ((np.arange(ow, dtype=f32) + f32(.5)) * gx + f32(l)) - f32(.5)
+    cy = ((np.arange(oh, dtype=f32) + f32(.5)) * gy + f32(t)) - f32(.5)
+    txy = np.empty((oh, ow, 2), f32); txy[..., 0] = cx[None, :]; txy[..., 1] = cy[:, None]
+    ref = np.empty((oh, ow, 4), f32)
+    assert R.ref_d3d9_run(name.encode(), _p(tex), W, H, _p(txy), ow * oh, gx, gy, _p(ref)) == 0, name
+    rgb = np.ascontiguousarray(tex[..., :3])
+    lit = np.empty((oh, ow, 3), f32)
+    assert L.orc_test_resize_draw(1, axis, kind, filt, O.VARIANT_D3D9, _p(rgb), W, H, (C.c_int * 4)(*rect), ow, oh, _p(lit)) == 0
+    return np.ascontiguousarray(ref[..., :3]), lit
+
+
+@pytest.mark.skipif(not os.path.exists(REF_C), reason="oracle/_ref/libref_hlsl_convert.so not built")
+@pytest.mark.parametrize("axis", [0, 1], ids=["x", "y"])
+@pytest.mark.parametrize("family", ["interpolation", "convolution"])
+def test_d3d9_resize_shaders_equal_the_reference_hlsl(family, axis):
+    """The reference keeps a Direct3D 9 renderer whose resize shaders differ from the D3D11 files in the conventions SURVEY Appendix B
+    lists: texel-space texcoords carrying -0.5, Lanczos3 reads six different texels (no Q1 := Q0), the convolution is centred (no half-texel
+    shift).  The oracle and the kernels implement both (`variant`); here the 20 D3D9 shader builds run as C++ and the oracle's LITERAL mode
+    with variant = D3D9 equals them bit for bit."""
+    R = C.CDLL(REF_C); L = O.lib()
+    R.ref_d3d9_run.argtypes = [C.c_char_p, FP, C.c_int, C.c_int, FP, C.c_int, C.c_float, C.c_float, FP]
+    L.orc_test_resize_draw.argtypes = [C.c_int] * 5 + [FP, C.c_int, C.c_int, C.c_int * 4, C.c_int, C.c_int, FP]
+    table, geoms, kind = (D9_INTERP, UP_X, 1) if family == "interpolation" else (CONV, DN_X, 2)
+    for name, filt in table:
+        for k, g in enumerate(geoms):
+            W, H, rect, ow, oh = g if axis == 0 else _transpose(g)
+            full = "d9_%s%s_%s" % ("" if kind == 1 else "conv_", name, "xy"[axis])
+            ref, lit = _draw9(R, L, full, axis, kind, filt, W, H, rect, ow, oh, seed=200 + k)
+            assert np.array_equal(ref.view(np.uint32), lit.view(np.uint32)), (full, g, int((ref.view(np.uint32) != lit.view(np.uint32)).sum()))
