@@ -145,6 +145,27 @@ int orc_test_tonemap(int mode, const float hp[6], const float* l2, const float* 
     return -1;
 }
 
+/* corr_pixel (the six post-scale correction shaders) on n RGB pixels; consts (18 floats, optional) = the fix-BT.2020 / fix-YCgCo matrix of the
+ * mode and the 2020 -> 709 gamut matrix as corr_constants evaluates them -- tests/test_reference_convert_exec_pin.py runs the shader files. */
+int orc_test_correction(int mode, int corr, float lum_scale, const float* in, float* out, int n, float* consts)
+{
+    if (mode == 0) {
+        float f20[3][3], fyc[3][3], gm[3][3];
+        corr_constants_spec(f20, fyc, gm);
+        if (consts) for (int i = 0; i < 9; i++) { consts[i] = corr == ORC_CORR_FIX_YCGCO ? fyc[i / 3][i % 3] : f20[i / 3][i % 3]; consts[9 + i] = gm[i / 3][i % 3]; }
+        for (int i = 0; i < n; i++) corr_pixel_spec(corr, lum_scale, f20, fyc, gm, in + 3 * i, out + 3 * i);
+        return 0;
+    }
+    if (mode == 1) {
+        float f20[3][3], fyc[3][3], gm[3][3];
+        corr_constants_lit(f20, fyc, gm);
+        if (consts) for (int i = 0; i < 9; i++) { consts[i] = corr == ORC_CORR_FIX_YCGCO ? fyc[i / 3][i % 3] : f20[i / 3][i % 3]; consts[9 + i] = gm[i / 3][i % 3]; }
+        for (int i = 0; i < n; i++) corr_pixel_lit(corr, lum_scale, f20, fyc, gm, in + 3 * i, out + 3 * i);
+        return 0;
+    }
+    return -1;
+}
+
 /* The DolbyConstants the oracle derives for a display (SPEC mode's build_dovi: Level 2 trim selection / interpolation,
  * DX11VideoProcessor.cpp:2383-2469, and the +-0.5 of SetDolbyVisionDynamicParams :956-960): {chroma_weight, saturation_gain, slope, offset, power}.
  * Returns l2_enabled. */

@@ -77,7 +77,7 @@ def include(name):
 def translate(text):
     regs = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"Texture2D\s+(\w+)\s*:\s*register\(t(\d+)\)", text))
     text = re.sub(r"^//#include (\S+)$", lambda m: include(m.group(1)), text, flags=re.M)
-    text = re.sub(r'^#include "\.\./convert/(\S+)"\s*$', lambda m: include(m.group(1)), text, flags=re.M)
+    text = re.sub(r'^#include "\.\./convert/(\S+)"\s*$', lambda m: include(m.group(1)), text.replace("\r\n", "\n"), flags=re.M)
     text = re.sub(r"cbuffer\s+\w+\s*:\s*register\(\w+\)\s*\{", "namespace {", text)
     text = re.sub(r"\s*:\s*register\(\w+\)", "", text)
     text = re.sub(r"\s*:\s*(SV_POSITION|TEXCOORD|SV_Target)\b", "", text)
@@ -163,6 +163,51 @@ print("    PS_INPUT in; in.Tex = float2(u, v);")
 print("    return ps_main(in);")
 print("}")
 print("}  // namespace jinc2_shader")
+# ---- the post-scale correction shaders of the D3D11-video-processor path (m_pPSCorrection, DX11VideoProcessor.cpp:1893-1931)
+CORR = [("corr_convert_pq_to_sdr", "ps_convert_pq_to_sdr.hlsl", 1), ("corr_fixconvert_pq_to_sdr", "ps_fixconvert_pq_to_sdr.hlsl", 2),
+        ("corr_fixconvert_hlg_to_sdr", "ps_fixconvert_hlg_to_sdr.hlsl", 3), ("corr_fix_bt2020", "ps_fix_bt2020.hlsl", 4),
+        ("corr_convert_hlg_to_pq", "ps_convert_hlg_to_pq.hlsl", 5), ("corr_fix_ycgco", "ps_fix_ycgco.hlsl", 6)]
+for ns, fname, mode in CORR:
+    text, regs, macros = translate(open("%s/Shaders/d3d11/%s" % (REF, fname), encoding="utf-8", errors="replace").read())
+    print("// ======== %s  <- Shaders/d3d11/%s" % (ns, fname))
+    print("namespace %s {" % ns)
+    print(text)
+    for m in macros:
+        print("#undef %s" % m)
+    print("static float4 run(const float* rgba, int tw, int th, float lum, float u, float v) {")
+    print("    tex.bind(rgba, tw, th); samp.linear = 0;")
+    if "LuminanceScale" in text:
+        print("    LuminanceScale = lum; param2 = 0;")
+    print("    PS_INPUT in; in.Tex = float2(u, v);")
+    print("    return ps_main(in);")
+    print("}")
+    # the matrices the text folds at shader-compile time, for a side-by-side look at the constants
+    print("static void constants(float* o) {")
+    if "fix_bt2020_matrix" in text:
+        print("    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[i * 3 + j] = fix_bt2020_matrix[i][j];")
+    elif "fix_ycgco_matrix" in text:
+        print("    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[i * 3 + j] = fix_ycgco_matrix[i][j];")
+    else:
+        print("    for (int k = 0; k < 9; k++) o[k] = 0;")
+    if "convert_matrix_2020_to_709" in text:
+        print("    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[9 + i * 3 + j] = convert_matrix_2020_to_709[i][j];")
+    else:
+        print("    for (int k = 0; k < 9; k++) o[9 + k] = 0;")
+    print("}")
+    # ... and a way to run the per-pixel text with GIVEN matrices (the test separates "which constants" from "which operations")
+    print("static void set_constants(const float* o) {")
+    if "fix_bt2020_matrix" in text:
+        print("    float4x4& F = const_cast<float4x4&>(fix_bt2020_matrix); for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F[i][j] = o[i * 3 + j];")
+    elif "fix_ycgco_matrix" in text:
+        print("    float4x4& F = const_cast<float4x4&>(fix_ycgco_matrix); for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F[i][j] = o[i * 3 + j];")
+    if "convert_matrix_2020_to_709" in text:
+        print("    float3x3& G = const_cast<float3x3&>(convert_matrix_2020_to_709); for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) G[i][j] = o[9 + i * 3 + j];")
+    print("}")
+    print("}  // namespace %s" % ns)
+print("struct CorrEntry { int mode; float4 (*run)(const float*, int, int, float, float, float); void (*constants)(float*); void (*set_constants)(const float*); };")
+print("static const CorrEntry g_corr[] = { %s };" % ", ".join("{ %d, %s::run, %s::constants, %s::set_constants }" % (mode, ns, ns, ns) for ns, _, mode in CORR))
+print("static const int g_ncorr = %d;" % len(CORR))
+
 # ---- the Direct3D 9 twins of the resize shaders (Shaders/d3d9/*.hlsl): same filters, texel-space texcoords that carry -0.5
 # (CDX9VideoProcessor::TextureResizeShader, DX9VideoProcessor.cpp:2853-2937), no duplicate Lanczos3 tap, no half-texel shift
 def adapt9(src):

@@ -75,7 +75,14 @@ template<> struct vec<4> {
 };
 typedef vec<2> float2; typedef vec<3> float3; typedef vec<4> float4;
 struct int2 { int x, y; int2(int a, int b) : x(a), y(b) {} };
-struct float3x3 { float m[9]; };
+struct float3x3 {                                          // three float3 rows; built from 9 scalars (row-major) or from 3 rows, as HLSL allows
+    float3 r[3];
+    float3x3() {}
+    float3x3(float a, float b, float c, float d, float e, float f, float g, float h, float i) : r{float3(a, b, c), float3(d, e, f), float3(g, h, i)} {}
+    float3x3(const float3& a, const float3& b, const float3& c) : r{a, b, c} {}
+    float3& operator[](int i) { return r[i]; }
+    const float3& operator[](int i) const { return r[i]; }
+};
 
 #define HLSL_BINOP(N, OP) \
     static inline vec<N> operator OP(const vec<N>& a, const vec<N>& b) { vec<N> r; for (int k = 0; k < N; k++) r.v[k] = a.v[k] OP b.v[k]; return r; } \
@@ -115,13 +122,34 @@ static inline float  lerp(float a, float b, float t) { return t * (b - a) + a; }
 static inline float3 mul(const float3x3& M, const float3& a)
 {
     float3 r;
-    for (int i = 0; i < 3; i++) r.v[i] = dot(float3(M.m[3 * i], M.m[3 * i + 1], M.m[3 * i + 2]), a);
+    for (int i = 0; i < 3; i++) r.v[i] = dot(M.r[i], a);
     return r;
+}
+static inline float3x3 transpose(const float3x3& M)
+{
+    float3x3 t;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) t.r[i].v[j] = M.r[j].v[i];
+    return t;
+}
+static inline float3x3 mul(const float3x3& A, const float3x3& B)                   // (A B)[i][j] = dot(row i of A, column j of B)
+{
+    const float3x3 Bt = transpose(B);
+    float3x3 o;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o.r[i].v[j] = dot(A.r[i], Bt.r[j]);
+    return o;
 }
 
 // matrices of ps_resize_onepass_jinc2.hlsl: float4x4 = four float4 rows, float4x3 = four float3 rows; mul(row vector, matrix) and
 // mul(matrix, column vector), each component a mul followed by mads in row order
-struct float4x4 { float4 r[4]; float4& operator[](int i) { return r[i]; } const float4& operator[](int i) const { return r[i]; } };
+struct float4x4 {
+    float4 r[4];
+    float4x4() {}
+    float4x4(const float4& a, const float4& b, const float4& c, const float4& d) : r{a, b, c, d} {}
+    float4x4(float a0, float a1, float a2, float a3, float b0, float b1, float b2, float b3, float c0, float c1, float c2, float c3, float d0, float d1, float d2, float d3)
+        : r{float4(a0, a1, a2, a3), float4(b0, b1, b2, b3), float4(c0, c1, c2, c3), float4(d0, d1, d2, d3)} {}
+    float4& operator[](int i) { return r[i]; }
+    const float4& operator[](int i) const { return r[i]; }
+};
 struct float4x3 { float3 r[4]; float4x3(const float3& a, const float3& b, const float3& c, const float3& d) : r{a, b, c, d} {} };
 static inline float3 mul(const float4& w, const float4x3& M)
 {
@@ -130,6 +158,12 @@ static inline float3 mul(const float4& w, const float4x3& M)
     return o;
 }
 static inline float4 mul(const float4x4& M, const float4& a) { float4 o; for (int i = 0; i < 4; i++) o.v[i] = dot(M.r[i], a); return o; }
+static inline float4x4 mul(const float4x4& A, const float4x4& B)
+{
+    float4x4 o;
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) o.r[i].v[j] = dot(A.r[i], float4(B.r[0].v[j], B.r[1].v[j], B.r[2].v[j], B.r[3].v[j]));
+    return o;
+}
 
 struct SamplerState { int linear = 0; };
 struct hlsl_sample : float4 {                               // what Sample returns: a float4 that also truncates to its first component
