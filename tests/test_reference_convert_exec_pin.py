@@ -55,6 +55,8 @@ def _libs():
         RC.ref_convert_case.restype = C.c_char_p; RC.ref_convert_case.argtypes = [C.c_int, C.c_uint * 9]
         RC.ref_convert_dovi_lms.argtypes = [C.c_double * 9]
         RC.ref_convert_run.argtypes = [C.c_int, FP * 3, C.c_int * 3, C.c_int * 3, C.c_float * 12, C.c_float, FP, FP, FP, C.POINTER(C.c_int32), FP, C.c_int, FP]
+        RC.ref_convert_run_rect.argtypes = [C.c_int, FP * 3, C.c_int * 3, C.c_int * 3, C.c_float * 12, C.c_float, FP, FP, FP, C.POINTER(C.c_int32), FP, C.c_int,
+                                            C.c_int * 4, FP]
         RS.ref_convert_color_params.argtypes = [C.c_int, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                                 (C.c_float * 3) * 3, C.c_float * 3, C.POINTER(C.c_int32)]
         RD.ref_dovi_curves.argtypes = [C.POINTER(O.OrcDovi), PIV, COEF, MMR, PAR]
@@ -135,7 +137,7 @@ def textures(cf, w, h, planes, pitches):
 DEFAULT_L2 = [(2851, 2200, 1900, 2100, 2000, 2150), (3300, 1950, 2100, 2000, 2120, 1990)]
 
 
-def run_case(i, l2=DEFAULT_L2):
+def run_case(i, l2=DEFAULT_L2, src_rect=None):
     RC, RS, RD = _libs()
     info = (C.c_uint * 9)()
     name = RC.ref_convert_case(i, info).decode()
@@ -146,8 +148,9 @@ def run_case(i, l2=DEFAULT_L2):
     _, _, planes, pitches = H.pack(cf, W, Hh, codes)
     # RGB sources only get a convert pass with a non-neutral ProcAmp (m_PSConvColorData.bEnable, DX11VideoProcessor.cpp:846-850)
     pa = dict(brightness=10.0, contrast=1.25) if f.cstype == 1 else {}
-    cfg = O.make_config(cf, W, Hh, W, Hh, ex, chroma=scaler, to_sdr=1 if conv == 1 else 0, deint_blend=blend,
-                        hdr={"out": 1} if conv == 2 else None, **pa)
+    x0, y0, x1, y1 = src_rect or (0, 0, W, Hh)
+    cfg = O.make_config(cf, W, Hh, x1 - x0, y1 - y0, ex, chroma=scaler, to_sdr=1 if conv == 1 else 0, deint_blend=blend,
+                        hdr={"out": 1} if conv == 2 else None, src_rect=src_rect, **pa)
     dv = None; dvargs = [None] * 5 + [0]; dm = doff = None; keep = None
     if dovi >= 0:
         # two Level-2 trim sets bracketing the 1000-nit display (PQ code 3079): the reference interpolates between them
@@ -172,9 +175,9 @@ def run_case(i, l2=DEFAULT_L2):
     assert RS.ref_convert_color_params(cf, ex, pa.get("brightness", 0.0), pa.get("contrast", 1.0), 0.0, 1.0, dm, doff, cm, cc, C.byref(en)) == 0
     assert en.value == 1, name
     cm12 = (C.c_float * 12)(*([cm[r][c] for r in range(3) for c in range(3)] + list(cc)))
-    ref = np.empty((Hh, W, 4), f32)
-    assert RC.ref_convert_run(i, (FP * 3)(*[_p(t) for t in tex]), (C.c_int * 3)(*[t.shape[1] for t in tex]), (C.c_int * 3)(*[t.shape[0] for t in tex]),
-                              cm12, f32(10000.0) / f32(125.0), *dvargs, _p(ref)) == 0
+    ref = np.empty((y1 - y0, x1 - x0, 4), f32)
+    assert RC.ref_convert_run_rect(i, (FP * 3)(*[_p(t) for t in tex]), (C.c_int * 3)(*[t.shape[1] for t in tex]), (C.c_int * 3)(*[t.shape[0] for t in tex]),
+                                   cm12, f32(10000.0) / f32(125.0), *dvargs, (C.c_int * 4)(x0, y0, x1, y1), _p(ref)) == 0
     return name, conv, dovi, int(info[1]), np.ascontiguousarray(ref[..., :3]), lit, spec
 
 
@@ -193,6 +196,23 @@ def test_generated_convert_shader_equals_the_oracle(i, name):
         assert err.max() <= 6e-7, (name, err.max())
     else:
         assert np.percentile(err, 99.9) <= 3e-4 and err.max() <= 5e-3, (name, np.percentile(err, 99.9), err.max())
+
+
+@pytest.mark.parametrize("rect", [(3, 5, 61, 30), (1, 0, 64, 31), (2, 2, 34, 18)], ids=["odd_offsets", "odd_x", "even"])
+def test_generated_convert_shader_on_a_cropped_source(rect):
+    """m_srcRect with odd offsets moves every chroma phase (frac(Tex * wh / 2), the fmod(Tex.x * w, 2) test of the 4:2:2 branches, the blend
+    deinterlace rows): the draw's texcoords start inside the texture and the neighbours it fetches are real texels, not clamped ones"""
+    n = 0
+    for i, name in CASES:
+        if "dovi" in name or "trc" in name or name.split("_")[0] in ("XRGB32", "RGB48", "Y8", "Y16"):
+            continue
+        x0, y0, x1, y1 = rect
+        name, conv, dovi, ex, ref, lit, spec = run_case(i, src_rect=rect)
+        assert ref.shape == lit.shape
+        bad = np.nonzero(ref.view(np.uint32) != lit.view(np.uint32))
+        assert bad[0].size == 0, (name, rect, bad[0].size)
+        n += 1
+    assert n >= 70
 
 
 # (target_max_pq, slope, offset, power, chroma_weight, saturation_gain) raw 12-bit fields; the display is 1000 nits = PQ code 3079
