@@ -137,14 +137,14 @@ def textures(cf, w, h, planes, pitches):
 DEFAULT_L2 = [(2851, 2200, 1900, 2100, 2000, 2150), (3300, 1950, 2100, 2000, 2120, 1990)]
 
 
-def run_case(i, l2=DEFAULT_L2, src_rect=None):
+def run_case(i, l2=DEFAULT_L2, src_rect=None, kind="fullnoise", seed=None):
     RC, RS, RD = _libs()
     info = (C.c_uint * 9)()
     name = RC.ref_convert_case(i, info).decode()
     cf, ex, siting, scaler, conv, blend, dovi, W, Hh = [int(x) for x in info]
     dovi = dovi if dovi < 2 else -1                                       # (unsigned)-1
     f = H.fmt(cf)
-    codes = H.make_codes(cf, W, Hh, "fullnoise", seed=i)
+    codes = H.make_codes(cf, W, Hh, kind, seed=i if seed is None else seed)
     _, _, planes, pitches = H.pack(cf, W, Hh, codes)
     # RGB sources only get a convert pass with a non-neutral ProcAmp (m_PSConvColorData.bEnable, DX11VideoProcessor.cpp:846-850)
     pa = dict(brightness=10.0, contrast=1.25) if f.cstype == 1 else {}
@@ -196,6 +196,15 @@ def test_generated_convert_shader_equals_the_oracle(i, name):
         assert err.max() <= 6e-7, (name, err.max())
     else:
         assert np.percentile(err, 99.9) <= 3e-4 and err.max() <= 5e-3, (name, np.percentile(err, 99.9), err.max())
+
+
+@pytest.mark.parametrize("kind", ["natural", "noise", "ramp"])
+def test_generated_convert_shader_on_other_content(kind):
+    """legal-range noise, smooth "natural" frames and ramps (the per-case test uses full-range noise): all 114 cases again"""
+    for i, name in CASES:
+        name, conv, dovi, ex, ref, lit, spec = run_case(i, kind=kind, seed=1000 + i)
+        bad = np.nonzero(ref.view(np.uint32) != lit.view(np.uint32))
+        assert bad[0].size == 0, (name, kind, bad[0].size)
 
 
 @pytest.mark.parametrize("rect", [(3, 5, 61, 30), (1, 0, 64, 31), (2, 2, 34, 18)], ids=["odd_offsets", "odd_x", "even"])
