@@ -58,6 +58,8 @@ for fmt in ("P010", "Y410", "YUV420P16"):
     CASES.append(("%s_hlg_to_pq" % fmt, fmt, HLG, 5, BILINEAR, TO_PQ, 0, -1))
     CASES.append(("%s_hlg_as_sdr" % fmt, fmt, HLG, 5, BILINEAR, NONE, 0, -1))
     CASES.append(("%s_pq_passthrough" % fmt, fmt, PQ, 5, BILINEAR, TO_PQ, 0, -1))
+CASES.append(("YUY2_hlg_to_sdr", "YUY2", HLG, 5, CATMULL, TO_SDR, 0, -1))
+CASES.append(("P016_2020_sdr", "P016", SDR2020, 5, BILINEAR, NONE, 0, -1))
 for trc in (2, 3, 4, 5, 6, 7, 8, 14):
     CASES.append(("P010_2020_trc%d" % trc, "P010", dict(range_=2, matrix=4, prim=9, trc=trc), 5, BILINEAR, NONE, 0, -1))
 CASES.append(("NV12_601_full", "NV12", dict(range_=1, matrix=2, prim=2, trc=5), 5, BILINEAR, NONE, 0, -1))
