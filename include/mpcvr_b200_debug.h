@@ -65,6 +65,14 @@ int32_t mpcvr_debug_set_resize_four(int32_t enable);
  * returns the number of mismatching floats (0 expected), -1 if the table was found unusable, -2 on a CUDA error */
 int64_t mpcvr_debug_verify_gamma_table(mpcvr* vp);
 int32_t mpcvr_debug_get_color_params(mpcvr* vp, float m9[9], float c3[3], float gamut9[9], float* luminance_scale);
+/* The constant blocks the kernels receive, byte for byte as the host built them (videorenderer_b200/csrc/frame_plan.h): which 0 = ColorParams,
+ * 1 = DoviParams (MPCVR_E_UNEXPECTED without Dolby Vision data), 2 = TonemapParams.  Copies min(size, cap) bytes, returns the struct's size.
+ * Works on a planning-only instance (cuda_device -1): tests/test_device_code_on_host.py feeds them to the device pixel functions compiled
+ * for the host. */
+int32_t mpcvr_debug_get_device_params(mpcvr* vp, int32_t which, void* dst, size_t cap);
+/* Takes Dolby Vision metadata the way CopySample takes it from a sample (acceptance check, SetShaderDoviCurves, SetShaderConvertColorParams)
+ * without a frame -- so that the blocks above can be inspected without a GPU. */
+int32_t mpcvr_debug_set_dovi(mpcvr* vp, const mpcvr_dovi_metadata* md);
 /* per-axis resize table entry of output index i (host table the kernels consume) */
 int32_t mpcvr_debug_axis_taps(mpcvr* vp, int32_t axis, int32_t i, int32_t* base, float* weights, int32_t max_w, float* wsum);
 

@@ -202,6 +202,30 @@ int orc_test_convert_params(const orc_config* cfg, const orc_dovi* dv, float cm[
     return 0;
 }
 
+/* convert_color (the body of the generated convert shader) on n yuv triplets, with the constants build_cparams derives for cfg / dv exactly as
+ * orc_process does -- tests/test_device_code_on_host.py runs the product's device function convert_color() compiled for the host on the same
+ * triplets.  mode 0 SPEC, 1 LITERAL. */
+int orc_test_convert_pixels(const orc_config* cfg, const orc_dovi* dv, int mode, const float* yuv, float* out, int n)
+{
+    const orc_fmt* f = orc_get_fmt(cfg->cformat);
+    if (!f) return -10;
+    const int sw = cfg->src_rect[2] - cfg->src_rect[0], sh = cfg->src_rect[3] - cfg->src_rect[1];
+    const uint32_t exfmt = orc_specify_extended_format(f->cstype == 0 ? cfg->exfmt : 0u, f->cstype, f->subsampling, sw, sh);
+    if (mode == 0) {
+        static cparams_spec P; memset(&P, 0, sizeof(P));
+        if (build_cparams_spec(cfg, f, exfmt, &P, dv)) return -11;
+        for (int i = 0; i < n; i++) convert_color_spec(&P, yuv + 3 * i, out + 3 * i);
+        return 0;
+    }
+    if (mode == 1) {
+        static cparams_lit P; memset(&P, 0, sizeof(P));
+        if (build_cparams_lit(cfg, f, exfmt, &P, dv)) return -11;
+        for (int i = 0; i < n; i++) convert_color_lit(&P, yuv + 3 * i, out + 3 * i);
+        return 0;
+    }
+    return -1;
+}
+
 /* The PS_DOVI_CURVE constants the oracle derives from Dolby Vision reshaping metadata (SPEC mode's build_dovi: the restatement of
  * SetShaderDoviCurves / SetShaderDoviCurvesPoly, DX11VideoProcessor.cpp:990-1122), handed out so that tests/test_reference_dovi_pin.py
  * can compare them with the reference's own functions compiled in place (oracle/_ref/libref_dovi.so).  par[c] = {methods, mmr_single,

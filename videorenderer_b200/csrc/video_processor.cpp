@@ -1377,6 +1377,32 @@ int32_t CB200VideoProcessor::DebugGetColorParams(float m9[9], float c3[3], float
     return MPCVR_S_OK;
 }
 
+int32_t CB200VideoProcessor::DebugGetDeviceParams(int which, void* dst, size_t cap)
+{
+    if (!m_bInit) return Fail(MPCVR_E_UNEXPECTED, "no media type");
+    const void* src = nullptr; size_t n = 0;
+    switch (which) {
+    case 0: src = &m_color; n = sizeof(m_color); break;
+    case 1: if (!m_Dovi.bValid) return Fail(MPCVR_E_UNEXPECTED, "no Dolby Vision data"); src = &m_doviHost; n = sizeof(m_doviHost); break;
+    case 2: src = &m_tm; n = sizeof(m_tm); break;
+    default: return Fail(MPCVR_E_INVALIDARG, "which: 0 ColorParams, 1 DoviParams, 2 TonemapParams");
+    }
+    if (dst && cap) memcpy(dst, src, std::min(cap, n));
+    return (int32_t)n;
+}
+
+int32_t CB200VideoProcessor::DebugSetDovi(const mpcvr_dovi_metadata* md)
+{
+    if (!m_bInit) return Fail(MPCVR_E_UNEXPECTED, "no media type");
+    if (!md) return Fail(MPCVR_E_POINTER, "null metadata");
+    if (m_srcParams.CSType != CS_YUV || !CheckDoviMetadata(md)) return Fail(MPCVR_E_INVALIDARG, "metadata not accepted (CopySample would ignore it)");
+    m_Dovi.msd = *md; m_Dovi.bValid = true;
+    const int32_t hr = SetShaderDoviCurves();
+    if (hr != MPCVR_S_OK) return hr;
+    SetShaderConvertColorParams();
+    return MPCVR_S_OK;
+}
+
 int32_t CB200VideoProcessor::DebugAxisTaps(int axis, int i, int32_t* base, float* w, int maxw, float* wsum)
 {
     int32_t hr = UpdatePlan();

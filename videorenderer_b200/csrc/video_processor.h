@@ -123,6 +123,8 @@ public:
     int64_t DebugVerifyGammaTable() { if (m_device < 0) return -2; cudaSetDevice(m_device); return VerifyGammaTable(m_stream); }
     int32_t DebugGetPlan(mpcvr_plan_info* info);
     int32_t DebugGetColorParams(float m9[9], float c3[3], float g9[9], float* lum);
+    int32_t DebugGetDeviceParams(int which, void* dst, size_t cap);
+    int32_t DebugSetDovi(const mpcvr_dovi_metadata* md);
     int32_t DebugAxisTaps(int axis, int i, int32_t* base, float* w, int maxw, float* wsum);
     int32_t DebugCaptureF32(bool enable);
     int32_t DebugReadSurface(int which, void* host, size_t pitch, int32_t* w, int32_t* h, int32_t* fmt);

@@ -273,6 +273,16 @@ class VideoProcessor:
         self._check(self._L.mpcvr_debug_get_color_params(self._h, m.ctypes.data, c.ctypes.data, g.ctypes.data, C.byref(lum)), "debug_color")
         return m, c, g, lum.value
 
+    def debug_device_params(self, which):
+        """bytes of the ColorParams (0) / DoviParams (1) / TonemapParams (2) block the kernels receive (csrc/frame_plan.h)"""
+        n = self._check(self._L.mpcvr_debug_get_device_params(self._h, int(which), None, 0), "debug_device_params")
+        buf = C.create_string_buffer(n)
+        self._check(self._L.mpcvr_debug_get_device_params(self._h, int(which), buf, n), "debug_device_params")
+        return buf.raw
+
+    def debug_set_dovi(self, md):
+        self._check(self._L.mpcvr_debug_set_dovi(self._h, C.addressof(md)), "debug_set_dovi")
+
     def debug_axis_taps(self, axis, i):
         base = C.c_int32(); wsum = C.c_float(); w = np.zeros(1024, np.float32)
         n = self._check(self._L.mpcvr_debug_axis_taps(self._h, axis, i, C.byref(base), w.ctypes.data, 1024, C.byref(wsum)), "debug_axis_taps")
