@@ -16,3 +16,18 @@ int host_convert_color(const ColorParams* P, const DoviParams* D, const float* y
     return 0;
 }
 }
+
+#include "tonemap_ops.cuh"
+extern "C" {
+int host_sizeof_tonemap_params(void) { return (int)sizeof(TonemapParams); }
+// tm::pixel (the body of k_tonemap) on n PQ texels
+int host_tonemap_pixel(const ColorParams* P, const TonemapParams* T, const float* in, float* out, int n)
+{
+    for (int i = 0; i < n; i++) {
+        f3 v; v.x = in[3 * i]; v.y = in[3 * i + 1]; v.z = in[3 * i + 2];
+        const f3 r = tm::pixel(*P, *T, v);
+        out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+    }
+    return 0;
+}
+}

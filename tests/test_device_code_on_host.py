@@ -143,3 +143,53 @@ def test_convert_color_with_dolby_vision_equals_the_contract(name):
     if name in ("trims_negative_offset", "trims_bright", "trims_bright_sat"):
         black = int(np.all(want == 0, axis=1).sum())
         assert 0 < black < yuv.shape[0], black                           # the NaN pixels of the reference's unguarded trims are in the sample
+
+
+# ---- the HDR10 local tone-mapping pass: tm::pixel (tonemap_ops.cuh, the body of k_tonemap) ----
+class TonemapParams(C.Structure):          # csrc/frame_plan.h
+    _fields_ = [("min_nits", C.c_float), ("max_nits", C.c_float), ("max_cll", C.c_float), ("max_fall", C.c_float), ("display", C.c_float),
+                ("sel", C.c_int32), ("l2_enabled", C.c_int32), ("l2_chroma_weight", C.c_float), ("l2_saturation_gain", C.c_float),
+                ("l2_slope", C.c_float), ("l2_offset", C.c_float), ("l2_power", C.c_float)]
+
+
+TM_METADATA = {
+    "typical": (0.005, 1000.0, 1000.0, 400.0, 300.0), "bright_master": (0.0, 4000.0, 2500.0, 120.0, 600.0),
+    "display_covers_content": (0.01, 1000.0, 800.0, 200.0, 1000.0), "cll_below_10": (0.005, 1000.0, 5.0, 400.0, 500.0),
+    "no_fall": (0.005, 1200.0, 1100.0, 0.0, 400.0), "knee_clamps": (0.05, 1000.0, 1000.0, 990.0, 150.0),
+}
+TM_TRIMS = {None: None, "mild": (0.05, 0.1, 1.02, 0.004, 0.97), "negative_offset": (0.05, 0.1, 1.02, -0.004, 0.97), "negative_satgain": (-0.1, -0.1, 0.95, 0.01, 1.1),
+            "bright": (0.0, 0.0, 1.5, 0.5, 1.5)}
+
+
+def _pq_pixels(seed, n=40000):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.uniform(-0.02, 1.02, (n, 3)).astype(f32)
+    a[:4000] = rng.integers(0, 1024, (4000, 3)).astype(f32) / f32(1023)
+    a[4000:6000] = (rng.uniform(0, 1, (2000, 1)) ** 3).astype(f32)
+    a[6000:6050] = 0; a[6050:6100] = 1
+    return np.ascontiguousarray(a)
+
+
+@pytest.mark.parametrize("sel", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("trims", [None, "mild", "negative_offset", "negative_satgain", "bright"])
+def test_tonemap_device_function_equals_the_contract(sel, trims):
+    HL = host_lib()
+    HL.host_tonemap_pixel.argtypes = [C.c_char_p, C.POINTER(TonemapParams), FP, FP, C.c_int]
+    assert HL.host_sizeof_tonemap_params() == C.sizeof(TonemapParams)
+    L = O.lib()
+    L.orc_test_tonemap.argtypes = [C.c_int, C.c_float * 6, FP, FP, FP, C.c_int]
+    # the ColorParams a Dolby-Vision-less PQ stream on an HDR display gets (only the shader literals in it matter to this pass)
+    P, _ = _product_params(H.Case(O.CF["P010"], 64, 36, 64, 36, H.EX_2020_PQ, hdr=dict(out=1, tonemap=1, type=sel), name="tm"))
+    px = _pq_pixels(500 + sel)
+    for meta, hp in sorted(TM_METADATA.items()):
+        T = TonemapParams(*hp, sel, 0, 0, 0, 0, 0, 0)
+        l2 = TM_TRIMS[trims]
+        if l2:
+            T.l2_enabled = 1; T.l2_chroma_weight, T.l2_saturation_gain, T.l2_slope, T.l2_offset, T.l2_power = l2
+        got = np.empty_like(px)
+        assert HL.host_tonemap_pixel(P, C.byref(T), _p(px), _p(got), px.shape[0]) == 0
+        want = np.empty_like(px)
+        l2a = np.array(l2, f32) if l2 else None
+        assert L.orc_test_tonemap(0, (C.c_float * 6)(*hp, sel), _p(l2a) if l2 else None, _p(px), _p(want), px.shape[0]) == 0
+        same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+        assert same.all(), (sel, trims, meta, int((~same).sum()), px[np.nonzero(~same)[0][:3]], got[~same][:3], want[~same][:3])
