@@ -9,11 +9,13 @@ Here it runs over frames of PQ texels -- uniform noise with values outside [0, 1
 maxFALL absent, a knee that clamps), and the oracle's tm_pixel (oracle/orc_core.inc) must reproduce it in LITERAL mode BIT FOR BIT.
 SPEC mode (the contract of the CUDA kernel k_tonemap, tests/test_gpu_parity.py) is held to a measured distance.
 
-With the Dolby Vision trims bound (cbuffer b1), the same holds on every pixel whose trims stay finite.  The shader's DolbyVisionTrims has no
-guard (see tests/test_reference_convert_exec_pin.py): where it makes NaN the reference writes 0 (curves 1-4, through saturate) or NaN
-(curves 5 / 6) -- the oracle and the kernel return the per-channel clamped value there.  That deviation of the HDR-display + local
-tone-mapping + Level-2 path is OPEN; the convert-shader form of the same issue is fixed.  The test finds those
-pixels with the shader itself (selection 6 on a display brighter than the content is trims only) and asserts how many there are."""
+With the Dolby Vision trims bound (cbuffer b1) the same holds, NaN pixels included.  The shader's DolbyVisionTrims has no guard (see
+tests/test_reference_convert_exec_pin.py): a negative pow base or a zero luminance make every channel NaN, a zero channel under a
+non-positive saturation gain or a value past ST2084ToLinear's pole make that channel NaN.  Curves 1-4 saturate the NaN to 0 and carry on;
+BT.2390 spreads it over the pixel when its curve is active and passes it through per channel otherwise; ST 2094-10 always passes it through
+per channel (the NaN luminance fails `x_nits > 0`).  tm_pixel reproduces each case (a NaN result is held as 0, which is what a UNORM
+target stores); the test finds the poisoned pixels with the shader itself (selection 6 on a display brighter than the content is trims
+only) and checks every pixel of every curve."""
 import ctypes as C
 import os
 
@@ -108,24 +110,36 @@ TRIMS = {       # ChromaWeight, SaturationGain, TrimSlope, TrimOffset, TrimPower
     "mild":            (0.05, 0.1, 1.02, 0.004, 0.97),
     "negative_offset": (0.05, 0.1, 1.02, -0.004, 0.97),
     "negative_satgain": (-0.1, -0.1, 0.95, 0.01, 1.1),
+    "zero_satgain":    (0.1, 0.0, 1.0, -0.001, 1.0),
+    "bright":          (0.0, 0.0, 1.5, 0.5, 1.5),           # values past the pole of ST2084ToLinear (~1.99)
+    "bright_sat":      (0.5, 0.5, 1.4, 0.3, 1.5),
 }
 
 
-@pytest.mark.parametrize("sel", [1, 3, 5, 6])
+@pytest.mark.parametrize("sel", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("meta", ["typical", "display_covers_content"])
 @pytest.mark.parametrize("trims", sorted(TRIMS))
-def test_tonemap_shader_with_dolby_vision_trims(sel, trims):
+def test_tonemap_shader_with_dolby_vision_trims(sel, meta, trims):
+    """every pixel, the NaN ones included: where the reference's float is NaN the oracle holds 0 (or LinearToST2084(0)), both code 0 in any
+    UNORM target; where the reference saturates its NaN to 0 and carries on (curves 1-4) the oracle must produce the very same number"""
     R, L = _libs()
     tex = _frame(40 + sel)
-    hp = METADATA["typical"]
+    hp = METADATA[meta]
     # the pixels whose trims make NaN in the reference's text: selection 6 on a display brighter than maxCLL is PQ -> linear -> trims -> PQ
     probe, _ = _run(R, L, tex, (hp[0], hp[1], hp[2], hp[3], 10000.0), 6, TRIMS[trims], 1)
     poisoned = np.isnan(probe).any(axis=2)
     ref, lit = _run(R, L, tex, hp, sel, TRIMS[trims], 1)
-    live = ~poisoned
-    same = _equal_or_nan_black(ref, lit, _pq0(L))
-    assert same[live].all(), (sel, trims, int((~same[live]).sum()))
+    pq0 = _pq0(L)
+    same = (ref.view(np.uint32) == lit.view(np.uint32)) | (np.isnan(ref) & ((lit == pq0) | (lit == 0)))
+    assert same.all(), (sel, meta, trims, int((~same).sum()), tex[np.nonzero(~same)[:2]][:3], ref[~same][:4], lit[~same][:4])
+    if sel <= 4:
+        assert not np.isnan(ref).any()          # saturate() has swallowed the NaN: the comparison above was on numbers
     n = int(poisoned.sum())
     if trims == "mild":
-        assert n == 0                   # positive offset: every base stays positive, nothing is poisoned and the whole frame is equal
-    elif trims == "negative_offset":
-        assert 0 < n < W * H // 4, n    # the OPEN deviation (module docstring): pixels with a channel darker than -offset / slope in PQ
+        assert n == 0
+    elif trims in ("negative_offset", "bright"):
+        assert 0 < n < W * H, n
+    # SPEC takes the same decisions
+    _, spec = _run(R, L, tex, hp, sel, TRIMS[trims], 0)
+    nanpix = np.isnan(ref)
+    assert np.all((spec[nanpix] == 0) | (np.abs(spec[nanpix] - pq0) < 1e-8))

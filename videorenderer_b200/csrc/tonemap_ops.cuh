@@ -98,21 +98,51 @@ __device__ __forceinline__ float curve(const ColorParams& P, const TonemapParams
 __device__ __forceinline__ f3 pixel(const ColorParams& P, const TonemapParams& T, f3 p)
 {
     f3 c; c.x = pq2l(P, sat(p.x)); c.y = pq2l(P, sat(p.y)); c.z = pq2l(P, sat(p.z));     // main, :265-336
-    if (T.l2_enabled) {                                                                                // DolbyVisionTrims, :245-263
-        c.x = powr(fma_rn(l2pq(c.x), T.l2_slope, T.l2_offset), T.l2_power);
-        c.y = powr(fma_rn(l2pq(c.y), T.l2_slope, T.l2_offset), T.l2_power);
-        c.z = powr(fma_rn(l2pq(c.z), T.l2_slope, T.l2_offset), T.l2_power);
-        const float Y = dot2020(c);
+    // DolbyVisionTrims, :245-263.  Like its twin in the convert shader the text has no guard: a negative pow base (trimmed PQ value * slope +
+    // offset < 0) or a zero trimmed luminance make EVERY channel NaN (through Y); a zero channel under a non-positive saturation gain
+    // (0 * inf) or a value past ST2084ToLinear's pole (negative quotient) make THAT channel NaN.  nx / ny / nz: the channel is NaN in the
+    // reference.  powr returns 0 for a non-positive base, so the cases are flagged explicitly -- the same tests as the oracle's tm_pixel.
+    bool nx = false, ny = false, nz = false;
+    if (T.l2_enabled) {
+        const float b0 = fma_rn(l2pq(c.x), T.l2_slope, T.l2_offset), b1 = fma_rn(l2pq(c.y), T.l2_slope, T.l2_offset), b2 = fma_rn(l2pq(c.z), T.l2_slope, T.l2_offset);
+        bool all = (b0 < 0.0f) || (b1 < 0.0f) || (b2 < 0.0f);
+        f3 t; t.x = powr(b0, T.l2_power); t.y = powr(b1, T.l2_power); t.z = powr(b2, T.l2_power);
+        const float Y = dot2020(t);
         const float g = __fadd_rn(1.0f, T.l2_chroma_weight);
-        c.x = pq2l(P, __fmul_rn(c.x, powr(__fdiv_rn(__fmul_rn(g, c.x), Y), T.l2_saturation_gain)));
-        c.y = pq2l(P, __fmul_rn(c.y, powr(__fdiv_rn(__fmul_rn(g, c.y), Y), T.l2_saturation_gain)));
-        c.z = pq2l(P, __fmul_rn(c.z, powr(__fdiv_rn(__fmul_rn(g, c.z), Y), T.l2_saturation_gain)));
+        all = all || (Y == 0.0f);
+        const bool sg_pos = T.l2_saturation_gain > 0.0f;
+        nx = (t.x == 0.0f) && !sg_pos; ny = (t.y == 0.0f) && !sg_pos; nz = (t.z == 0.0f) && !sg_pos;
+        const float s0 = __fmul_rn(t.x, powr(__fdiv_rn(__fmul_rn(g, t.x), Y), T.l2_saturation_gain));
+        const float s1 = __fmul_rn(t.y, powr(__fdiv_rn(__fmul_rn(g, t.y), Y), T.l2_saturation_gain));
+        const float s2 = __fmul_rn(t.z, powr(__fdiv_rn(__fmul_rn(g, t.z), Y), T.l2_saturation_gain));
+        nx = nx || (fma_rn(-ST2084_C3, powr(s0, P.inv_m2), ST2084_C2) < 0.0f);
+        ny = ny || (fma_rn(-ST2084_C3, powr(s1, P.inv_m2), ST2084_C2) < 0.0f);
+        nz = nz || (fma_rn(-ST2084_C3, powr(s2, P.inv_m2), ST2084_C2) < 0.0f);
+        c.x = pq2l(P, s0); c.y = pq2l(P, s1); c.z = pq2l(P, s2);
+        if (all) { nx = true; ny = true; nz = true; }
     }
     f3 o;
     if (T.sel == 5 || T.sel == 6) {
+        if (nx || ny || nz) {
+            // BT.2390: with the curve active the NaN reaches the luminance and from there every channel; on a display that covers the content
+            // the colour is returned as it is, NaN channels included.  ST 2094-10: the NaN luminance fails `x_nits > 0`, the factor is 1 and
+            // the colour passes through unchanged, NaN channels included.  A NaN result is 0 in a UNORM target: 0 stands for it.
+            bool whole = false;
+            if (T.sel == 5) {
+                float safe = T.max_cll;
+                if (safe <= 10.0f) safe = T.max_nits;
+                if (safe <= 10.0f) safe = 1000.0f;
+                whole = !(T.display >= safe);
+            }
+            o.x = (whole || nx) ? 0.0f : l2pq(c.x); o.y = (whole || ny) ? 0.0f : l2pq(c.y); o.z = (whole || nz) ? 0.0f : l2pq(c.z);
+            return o;
+        }
         c = (T.sel == 5) ? bt2390(P, T, c) : st2094(P, T, c);
         o.x = l2pq(c.x); o.y = l2pq(c.y); o.z = l2pq(c.z);
     } else {
+        if (nx) c.x = 0.0f;                                   // curves 1-4: color.rgb = saturate(color.rgb * ...) turns NaN into 0
+        if (ny) c.y = 0.0f;
+        if (nz) c.z = 0.0f;
         const float base = fmaxf(T.display, T.max_nits);
         const float eff = fminf(base, T.max_cll);
         const float fall_adj = fminf(__fdiv_rn(base, T.max_fall), 1.0f);
