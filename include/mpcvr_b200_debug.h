@@ -73,6 +73,11 @@ int32_t mpcvr_debug_get_device_params(mpcvr* vp, int32_t which, void* dst, size_
 /* Takes Dolby Vision metadata the way CopySample takes it from a sample (acceptance check, SetShaderDoviCurves, SetShaderConvertColorParams)
  * without a frame -- so that the blocks above can be inspected without a GPU. */
 int32_t mpcvr_debug_set_dovi(mpcvr* vp, const mpcvr_dovi_metadata* md);
+/* The SrcDesc block (frame_plan.h) the convert kernels would receive for a sample whose planes lie at planes[] / pitches[] (the
+ * MPCVR_SAMPLE_DEVICE_MEMORY form of mpcvr_process_sample), without touching a GPU: which 3 of mpcvr_debug_get_device_params, built from
+ * the current media type and settings.  The pointers are stored as given (host addresses are fine for the host-compiled pixel functions).
+ * Copies min(size, cap) bytes into dst, returns the struct's size. */
+int32_t mpcvr_debug_build_src_desc(mpcvr* vp, const void* const planes[3], const int32_t pitches[3], void* dst, size_t cap);
 /* per-axis resize table entry of output index i (host table the kernels consume) */
 int32_t mpcvr_debug_axis_taps(mpcvr* vp, int32_t axis, int32_t i, int32_t* base, float* weights, int32_t max_w, float* wsum);
 

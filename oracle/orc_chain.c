@@ -125,6 +125,20 @@ int orc_test_final_pass(int mode, const float* in, int w, int h, float Q, float*
     return -1;
 }
 
+/* The D3D11 render-target write followed by the read a later pass performs (rt_roundtrip, SPEC), and the final pass's quantiser
+ * floor(p * Q + d) / Q (final_pass) -- tests/test_device_code_on_host.py holds the product's surf_store / surf_load / final_quant, compiled for
+ * the host, to them.  fmt = ORC_SURF_* */
+int orc_test_rt_roundtrip(int fmt, const float* in, float* out, int n)
+{
+    for (int i = 0; i < n; i++) out[i] = rt_roundtrip_spec(fmt, in[i]);
+    return 0;
+}
+int orc_test_final_quant(const float* p, const float* d, float Q, float* out, int n)
+{
+    for (int i = 0; i < n; i++) out[i] = floorf(fmaf(p[i], Q, d[i])) / Q;
+    return 0;
+}
+
 /* tm_pixel (ps_hdr10_tonemap.hlsl's main) on n RGB PQ pixels with the constant-buffer values given directly: hp = MasteringMinLuminanceNits,
  * MasteringMaxLuminanceNits, maxCLL, maxFALL, displayMaxNits, selection; l2 = {ChromaWeight, SaturationGain, TrimSlope, TrimOffset, TrimPower}
  * or NULL -- tests/test_reference_convert_exec_pin.py runs the reference's shader file as C++ on the same pixels.  mode 0 SPEC, 1 LITERAL. */

@@ -193,3 +193,88 @@ def test_tonemap_device_function_equals_the_contract(sel, trims):
         assert L.orc_test_tonemap(0, (C.c_float * 6)(*hp, sel), _p(l2a) if l2 else None, _p(px), _p(want), px.shape[0]) == 0
         same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
         assert same.all(), (sel, trims, meta, int((~same).sum()), px[np.nonzero(~same)[0][:3]], got[~same][:3], want[~same][:3])
+
+
+# ---- the whole convert pass per pixel: fetch_yuv (every sample layout, chroma reconstruction) + convert_color, as k_convert runs them ----
+def _host_convert_frame(case, buf, pitch, planes, pitches):
+    HL = host_lib()
+    HL.host_convert_frame.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, FP]
+    vp = case.make_processor(device=-1)
+    f = H.fmt(case.cf)
+    if f.layout == 5 or f.name.decode() == "v210":            # RGB samples and v210 are read in the sample's own byte layout
+        S = vp.debug_build_src_desc([buf.ctypes.data], [pitch])
+    else:
+        S = vp.debug_build_src_desc([p.ctypes.data for p in planes], list(pitches))
+    assert len(S) == HL.host_sizeof_src_desc()
+    P = vp.debug_device_params(0)
+    sw, sh = (case.src_rect[2] - case.src_rect[0], case.src_rect[3] - case.src_rect[1]) if case.src_rect else (case.w, case.h)
+    out = np.empty((sh, sw, 3), f32)
+    assert HL.host_convert_frame(S, P, None, _p(out)) == 0
+    return out
+
+
+FORMATS = [n for n in O.CF if n != "NONE"]
+
+
+@pytest.mark.parametrize("name", FORMATS)
+def test_fetch_and_convert_of_every_format_equal_the_contract(name):
+    """every sample layout the product accepts x chroma scaler x chroma siting (4:2:0) x blend deinterlace x a cropped source rect:
+    fetch_yuv + convert_color compiled for the host against the oracle's convert pass (debug tap convert_f32, SPEC), bit for bit"""
+    cf = O.CF[name]
+    f = H.fmt(cf)
+    n = 0
+    for chroma in (O.CHROMA_Nearest, O.CHROMA_Bilinear, O.CHROMA_CatmullRom):
+        for siting in ((1, 5, 7) if f.subsampling == 420 else (5,)):
+            for rect, interlaced in ((None, 0), ((2, 2, 58, 30), 0), ((3, 1, 61, 35), 1)):
+                if rect and f.layout == 3 and (rect[0] & 1):
+                    rect = (rect[0] + 1,) + rect[1:]
+                ex = O.exfmt(chroma=siting, range_=2, matrix=1, prim=2, trc=5)
+                pa = dict(procamp=dict(brightness=4.0, contrast=1.125)) if f.cstype == 1 else {}
+                case = H.Case(cf, 64, 36, 64, 36, ex, chroma=chroma, src_rect=rect, interlaced=interlaced, deint_blend=interlaced, name=name, **pa)
+                codes = H.make_codes(cf, 64, 36, "fullnoise", seed=7 * n + cf)
+                buf, pitch, planes, pitches = H.pack(cf, 64, 36, codes)
+                got = _host_convert_frame(case, buf, pitch, planes, pitches)
+                want = H.run_oracle(case, planes, pitches, want_debug=True)[1]["convert_f32"]
+                assert got.shape == want.shape, (name, got.shape, want.shape)
+                bad = np.nonzero(got.view(np.uint32) != want.view(np.uint32))
+                assert bad[0].size == 0, (name, chroma, siting, rect, interlaced, bad[0].size, got[bad][:3], want[bad][:3])
+                n += 1
+    assert n >= 9
+
+
+# ---- render-target conversions and the final pass's quantiser ----
+@pytest.mark.parametrize("fmt", [O.SURF_BGRA8, O.SURF_RGB10A2, O.SURF_RGBA16F], ids=["bgra8", "rgb10a2", "rgba16f"])
+def test_surface_store_and_load_equal_the_contract(fmt):
+    """surf_store + surf_load (pixel_ops.cuh): float -> UNORM8 / UNORM10 / half and back, against rt_roundtrip -- on every 10-bit and 8-bit code,
+    values at the rounding boundaries, out-of-range values, infinities and NaN"""
+    HL = host_lib(); L = O.lib()
+    HL.host_surface_roundtrip.argtypes = [C.c_int, FP, FP, C.c_int]
+    L.orc_test_rt_roundtrip.argtypes = [C.c_int, FP, FP, C.c_int]
+    rng = np.random.Generator(np.random.PCG64(12 + fmt))
+    codes = np.arange(1024, dtype=f32)
+    halfway = (codes[:, None] + np.array([0.5, 0.49999997, 0.50000006], f32)[None, :]).reshape(-1) / f32(1023)
+    x = np.concatenate([rng.uniform(-0.25, 1.25, 60000).astype(f32), codes / f32(1023), np.arange(256, dtype=f32) / f32(255), halfway,
+                        np.array([0, -0.0, 1, np.inf, -np.inf, np.nan, 1e-30, 65504.0, 70000.0, 1e-8, 5.96e-8, 2.98e-8], f32)])
+    x = np.ascontiguousarray(np.resize(x, (x.size // 3) * 3))
+    got = np.empty_like(x); want = np.empty_like(x)
+    assert HL.host_surface_roundtrip(fmt, _p(x), _p(got), x.size // 3) == 0
+    assert L.orc_test_rt_roundtrip(fmt, _p(x), _p(want), x.size) == 0
+    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), (fmt, x[~same][:5], got[~same][:5], want[~same][:5])
+
+
+@pytest.mark.parametrize("Q", [255.0, 1023.0])
+def test_final_pass_quantiser_equals_the_contract(Q):
+    HL = host_lib(); L = O.lib()
+    HL.host_final_quant.argtypes = [FP, FP, C.c_float, FP, C.c_int]
+    L.orc_test_final_quant.argtypes = [FP, FP, C.c_float, FP, C.c_int]
+    # every (10-bit code, dither threshold) pair, and random floats
+    c = (np.arange(1024, dtype=f32) / f32(1023))[:, None].repeat(1024, 1).reshape(-1)
+    d = (np.arange(1024, dtype=f32) / f32(1024))[None, :].repeat(1024, 0).reshape(-1)
+    rng = np.random.Generator(np.random.PCG64(3))
+    p = np.ascontiguousarray(np.concatenate([c, rng.uniform(-0.1, 1.1, 200000).astype(f32)]))
+    dd = np.ascontiguousarray(np.concatenate([d, (rng.integers(0, 1024, 200000).astype(f32) / f32(1024))]))
+    got = np.empty_like(p); want = np.empty_like(p)
+    assert HL.host_final_quant(_p(p), _p(dd), Q, _p(got), p.size) == 0
+    assert L.orc_test_final_quant(_p(p), _p(dd), Q, _p(want), p.size) == 0
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

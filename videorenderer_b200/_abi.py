@@ -215,6 +215,7 @@ SIGNATURES = {
     "mpcvr_debug_get_color_params": (C.c_int32, [vp, vp, vp, vp, P(C.c_float)]),
     "mpcvr_debug_get_device_params": (C.c_int32, [vp, C.c_int32, vp, C.c_size_t]),
     "mpcvr_debug_set_dovi": (C.c_int32, [vp, vp]),
+    "mpcvr_debug_build_src_desc": (C.c_int32, [vp, vp, vp, vp, C.c_size_t]),
     "mpcvr_debug_axis_taps": (C.c_int32, [vp, C.c_int32, C.c_int32, P(C.c_int32), vp, C.c_int32, P(C.c_float)]),
     "mpcvr_debug_capture_f32": (C.c_int32, [vp, C.c_int32]),
     "mpcvr_debug_read_surface": (C.c_int32, [vp, C.c_int32, vp, C.c_size_t, P(C.c_int32), P(C.c_int32), P(C.c_int32)]),

@@ -130,6 +130,7 @@ int32_t mpcvr_debug_get_plan(mpcvr* h, mpcvr_plan_info* info) { VP_OR(MPCVR_E_PO
 int32_t mpcvr_debug_get_color_params(mpcvr* h, float m9[9], float c3[3], float g9[9], float* lum) { VP_OR(MPCVR_E_POINTER); return vp.DebugGetColorParams(m9, c3, g9, lum); }
 int32_t mpcvr_debug_get_device_params(mpcvr* h, int32_t which, void* dst, size_t cap) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugGetDeviceParams(which, dst, cap)); }
 int32_t mpcvr_debug_set_dovi(mpcvr* h, const mpcvr_dovi_metadata* md) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugSetDovi(md)); }
+int32_t mpcvr_debug_build_src_desc(mpcvr* h, const void* const planes[3], const int32_t pitches[3], void* dst, size_t cap) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugBuildSrcDesc(planes, pitches, dst, cap)); }
 int32_t mpcvr_debug_axis_taps(mpcvr* h, int32_t axis, int32_t i, int32_t* base, float* w, int32_t maxw, float* wsum) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugAxisTaps(axis, i, base, w, maxw, wsum)); }
 int32_t mpcvr_debug_capture_f32(mpcvr* h, int32_t en) { VP_OR(MPCVR_E_POINTER); return vp.DebugCaptureF32(en != 0); }
 int32_t mpcvr_debug_read_surface(mpcvr* h, int32_t which, void* dst, size_t pitch, int32_t* w, int32_t* hh, int32_t* fmt) { VP_OR(MPCVR_E_POINTER); GUARD(vp.DebugReadSurface(which, dst, pitch, w, hh, fmt)); }

@@ -1403,6 +1403,30 @@ int32_t CB200VideoProcessor::DebugSetDovi(const mpcvr_dovi_metadata* md)
     return MPCVR_S_OK;
 }
 
+int32_t CB200VideoProcessor::DebugBuildSrcDesc(const void* const planes[3], const int32_t pitches[3], void* dst, size_t cap)
+{
+    if (!m_bInit) return Fail(MPCVR_E_UNEXPECTED, "no media type");
+    if (!planes || !pitches) return Fail(MPCVR_E_POINTER, "null planes");
+    // the assignments CopySample makes for a device-memory sample (see there), on a local block
+    const FmtConvParams& f = m_srcParams;
+    SrcDesc S;
+    memset(&S, 0, sizeof(S));
+    S.W = m_srcWidth; S.H = m_srcHeight;
+    S.cw = m_srcWidth / f.div_chroma_w; S.ch = m_srcHeight / f.div_chroma_h;
+    S.layout = f.layout; S.bytes = f.bytes; S.lsb_shift = f.lsb_shift; S.packed_kind = f.packed_kind; S.subsampling = f.Subsampling;
+    S.chroma_mode = m_iChromaScaling; S.siting = m_srcExFmt.ChromaSubsampling();
+    S.deint_blend = (m_bDeintBlend && m_bInterlaced && f.Subsampling == 420) ? 1 : 0;
+    S.rect_l = m_srcRect.left; S.rect_t = m_srcRect.top; S.rect_w = m_srcRectWidth; S.rect_h = m_srcRectHeight;
+    const int np = f.layout == LAYOUT_BIPLANAR ? 2 : (f.layout == LAYOUT_PLANAR3 ? 3 : 1);
+    for (int i = 0; i < np; i++) {
+        if (!planes[i] || pitches[i] == 0) return Fail(MPCVR_E_POINTER, "missing plane");
+        S.pl[i] = (const uint8_t*)planes[i]; S.pitch[i] = pitches[i];
+    }
+    if (f.layout == LAYOUT_PLANAR3 && f.v_before_u) { std::swap(S.pl[1], S.pl[2]); std::swap(S.pitch[1], S.pitch[2]); }
+    if (dst && cap) memcpy(dst, &S, std::min(cap, sizeof(S)));
+    return (int32_t)sizeof(S);
+}
+
 int32_t CB200VideoProcessor::DebugAxisTaps(int axis, int i, int32_t* base, float* w, int maxw, float* wsum)
 {
     int32_t hr = UpdatePlan();

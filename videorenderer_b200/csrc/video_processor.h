@@ -125,6 +125,7 @@ public:
     int32_t DebugGetColorParams(float m9[9], float c3[3], float g9[9], float* lum);
     int32_t DebugGetDeviceParams(int which, void* dst, size_t cap);
     int32_t DebugSetDovi(const mpcvr_dovi_metadata* md);
+    int32_t DebugBuildSrcDesc(const void* const planes[3], const int32_t pitches[3], void* dst, size_t cap);
     int32_t DebugAxisTaps(int axis, int i, int32_t* base, float* w, int maxw, float* wsum);
     int32_t DebugCaptureF32(bool enable);
     int32_t DebugReadSurface(int which, void* host, size_t pitch, int32_t* w, int32_t* h, int32_t* fmt);

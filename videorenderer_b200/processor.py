@@ -280,6 +280,14 @@ class VideoProcessor:
         self._check(self._L.mpcvr_debug_get_device_params(self._h, int(which), buf, n), "debug_device_params")
         return buf.raw
 
+    def debug_build_src_desc(self, planes, pitches):
+        """bytes of the SrcDesc block (csrc/frame_plan.h) for planes at these addresses, built without a GPU"""
+        pl = (C.c_void_p * 3)(*(list(planes) + [None] * 3)[:3]); pi = (C.c_int32 * 3)(*(list(pitches) + [0] * 3)[:3])
+        n = self._check(self._L.mpcvr_debug_build_src_desc(self._h, pl, pi, None, 0), "debug_build_src_desc")
+        buf = C.create_string_buffer(n)
+        self._check(self._L.mpcvr_debug_build_src_desc(self._h, pl, pi, buf, n), "debug_build_src_desc")
+        return buf.raw
+
     def debug_set_dovi(self, md):
         self._check(self._L.mpcvr_debug_set_dovi(self._h, C.addressof(md)), "debug_set_dovi")
 
