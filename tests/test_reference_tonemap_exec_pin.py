@@ -117,7 +117,7 @@ TRIMS = {       # ChromaWeight, SaturationGain, TrimSlope, TrimOffset, TrimPower
 
 
 @pytest.mark.parametrize("sel", [1, 2, 3, 4, 5, 6])
-@pytest.mark.parametrize("meta", ["typical", "display_covers_content"])
+@pytest.mark.parametrize("meta", sorted(METADATA))
 @pytest.mark.parametrize("trims", sorted(TRIMS))
 def test_tonemap_shader_with_dolby_vision_trims(sel, meta, trims):
     """every pixel, the NaN ones included: where the reference's float is NaN the oracle holds 0 (or LinearToST2084(0)), both code 0 in any
