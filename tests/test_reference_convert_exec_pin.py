@@ -18,7 +18,7 @@ Here every case's shader runs over a whole frame of full-range random codes, fed
     (oracle/_ref/libref_dovi.so),
 and the result is compared with the convert-pass output of the oracle (orc_process, debug tap convert_f32 = the pixel before the render
 target write) in LITERAL mode -- the mode that claims to be the shader text, one IEEE operation per written operation: BIT-EQUAL, all
-114 cases.  SPEC mode (what the CUDA kernels are bit-exact with) is held to a measured distance from the executed text.
+116 cases.  SPEC mode (what the CUDA kernels are bit-exact with) is held to a measured distance from the executed text.
 
 So the fetch arithmetic (chroma positions, Catmull-Rom weights and tap order, 4:2:2 interpolation, the packed-format swizzles, the blend
 deinterlace), the order of matrix / saturate / transfer / gamut steps, the Dolby Vision reshaping (pivot search, polynomial, MMR orders)
