@@ -278,3 +278,21 @@ def test_final_pass_quantiser_equals_the_contract(Q):
     assert HL.host_final_quant(_p(p), _p(dd), Q, _p(got), p.size) == 0
     assert L.orc_test_final_quant(_p(p), _p(dd), Q, _p(want), p.size) == 0
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_the_shim_is_test_infrastructure_only():
+    """nothing under videorenderer_b200/ (or bench.py, or the C ABI headers) refers to the host shim or to the oracle: the product has no CPU path"""
+    import re
+    bad = []
+    roots = [os.path.join(ROOT, "videorenderer_b200"), os.path.join(ROOT, "include")]
+    for r in roots:
+        for d, _, files in os.walk(r):
+            if os.path.basename(d) in ("build", "__pycache__"):
+                continue
+            for fn in files:
+                if not fn.endswith((".py", ".h", ".cuh", ".cu", ".cpp")):
+                    continue
+                text = open(os.path.join(d, fn), encoding="utf-8", errors="replace").read()
+                if re.search(r"host_shim|cuda_host_shim|liborc|orc_api\.h|orc_core", text):
+                    bad.append(os.path.join(d, fn))
+    assert not bad, bad
