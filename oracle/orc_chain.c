@@ -117,6 +117,22 @@ int orc_test_jinc_draw(int mode, const float* in, int w, int h, const int in_rec
     if (mode == 1) { surf_lit a = {w, h, ORC_SURF_RAW, (float*)in}, b = {ow, oh, ORC_SURF_RAW, out}; return jinc_pass_lit(&a, &b, in_rect, out_rect, 1); }
     return -1;
 }
+/* the first draw of a turned frame (oriented_pass: SetRotation / SetFlip, FillVertices DX11VideoProcessor.cpp:130-179) with the X shader
+ * (in_axis 0), the Y shader (1) or ps_simple (-1), and the turned Jinc2 draw (in_axis 2) -- RAW surfaces, mode 0 SPEC / 1 LITERAL */
+int orc_test_oriented_draw(int mode, int in_axis, int kind, int filter, int variant, int rot, int flip, const float* in, int w, int h,
+                           const int in_rect[4], int ow, int oh, float* out)
+{
+    const int out_rect[4] = {0, 0, ow, oh};
+    if (mode == 0) {
+        surf_spec a = {w, h, ORC_SURF_RAW, (float*)in}, b = {ow, oh, ORC_SURF_RAW, out};
+        return in_axis == 2 ? jinc_pass_o_spec(&a, &b, in_rect, out_rect, rot, flip, 1) : oriented_pass_spec(&a, &b, in_rect, out_rect, rot, flip, in_axis, kind, filter, variant, 1);
+    }
+    if (mode == 1) {
+        surf_lit a = {w, h, ORC_SURF_RAW, (float*)in}, b = {ow, oh, ORC_SURF_RAW, out};
+        return in_axis == 2 ? jinc_pass_o_lit(&a, &b, in_rect, out_rect, rot, flip, 1) : oriented_pass_lit(&a, &b, in_rect, out_rect, rot, flip, in_axis, kind, filter, variant, 1);
+    }
+    return -1;
+}
 int orc_test_final_pass(int mode, const float* in, int w, int h, float Q, float* out)
 {
     const int rect[4] = {0, 0, w, h};

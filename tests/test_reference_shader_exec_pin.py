@@ -219,3 +219,56 @@ def test_d3d9_resize_shaders_equal_the_reference_hlsl(family, axis):
             full = "d9_%s%s_%s" % ("" if kind == 1 else "conv_", name, "xy"[axis])
             ref, lit = _draw9(R, L, full, axis, kind, filt, W, H, rect, ow, oh, seed=200 + k)
             assert np.array_equal(ref.view(np.uint32), lit.view(np.uint32)), (full, g, int((ref.view(np.uint32) != lit.view(np.uint32)).sum()))
+
+
+# ---- turned draws: SetRotation / SetFlip (FillVertices, DX11VideoProcessor.cpp:130-179) ----
+def _turned_uv(rect, W, H, ow, oh, rot, flip):
+    """TEXCOORD of every output pixel of a turned quad: u comes from x (rot 0 / 180) or y (90 / 270) and runs backwards for 180 / 270 (xor flip);
+    v comes from the other index and runs backwards for 90 / 180 (the reference's vertex table; tests/test_reference_resize_pin.py holds the
+    oracle's reading of it to FillVertices compiled in place)"""
+    l, t, r, b = rect
+    rotated = rot in (90, 270)
+    u_len, v_len = (oh, ow) if rotated else (ow, oh)
+    u_rev = (rot in (180, 270)) ^ bool(flip); v_rev = rot in (90, 180)
+    su = f32(r - l) / f32(u_len); sv = f32(b - t) / f32(v_len)
+    iu = np.arange(u_len, dtype=f32) + f32(.5); iv = np.arange(v_len, dtype=f32) + f32(.5)
+    cu = (f32(r) - iu * su) if u_rev else (iu * su + f32(l))
+    cv = (f32(b) - iv * sv) if v_rev else (iv * sv + f32(t))
+    uv = np.empty((oh, ow, 2), f32)
+    if rotated:
+        uv[..., 0] = (cu / f32(W))[:, None]; uv[..., 1] = (cv / f32(H))[None, :]
+    else:
+        uv[..., 0] = (cu / f32(W))[None, :]; uv[..., 1] = (cv / f32(H))[:, None]
+    return uv
+
+
+@pytest.mark.skipif(not os.path.exists(REF_C), reason="oracle/_ref/libref_hlsl_convert.so not built")
+@pytest.mark.parametrize("rot,flip", [(90, 0), (180, 0), (270, 0), (0, 1), (90, 1), (180, 1)])
+def test_turned_draws_equal_the_reference_hlsl(rot, flip):
+    """the X / Y shaders and Jinc2 on rotated and mirrored quads: interpolation (Lanczos3, incl. the Q1 := Q0 tap on a reversed axis), the
+    convolution with the reference's same-named-axis `scale` constant on a rotated quad, and the two-dimensional Jinc2"""
+    R, L = _libs()
+    RJ = C.CDLL(REF_C); RJ.ref_jinc2_run.argtypes = [FP, C.c_int, C.c_int, FP, C.c_int, FP]
+    L.orc_test_oriented_draw.argtypes = [C.c_int] * 7 + [FP, C.c_int, C.c_int, C.c_int * 4, C.c_int, C.c_int, FP]
+    W, H, rect = 64, 32, (3, 2, 61, 30)
+    rng = np.random.Generator(np.random.PCG64(500 + rot + flip))
+    tex = rng.uniform(0, 1, (H, W, 4)).astype(f32)
+    rgb = np.ascontiguousarray(tex[..., :3])
+    rotated = rot in (90, 270)
+    for label, in_axis, kind, filt, ow, oh in (("lanczos3_x", 0, 1, U["Lanczos3"], 45, 97) if rotated else ("lanczos3_x", 0, 1, U["Lanczos3"], 97, 45),
+                                               ("catmull4_y", 1, 1, U["CatmullRom"], 70, 29) if rotated else ("catmull4_y", 1, 1, U["CatmullRom"], 29, 70),
+                                               ("conv_hamming_x", 0, 2, D["Hamming"], 28, 20) if rotated else ("conv_hamming_x", 0, 2, D["Hamming"], 20, 28),
+                                               ("conv_bicubic05_y", 1, 2, D["Bicubic"], 9, 58) if rotated else ("conv_bicubic05_y", 1, 2, D["Bicubic"], 58, 9),
+                                               ("jinc2", 2, 1, U["Jinc2"], 101, 77)):
+        uv = _turned_uv(rect, W, H, ow, oh, rot, flip)
+        ref = np.empty((oh, ow, 4), f32)
+        if in_axis == 2:
+            assert RJ.ref_jinc2_run(_p(tex), W, H, _p(uv), ow * oh, _p(ref)) == 0
+        else:
+            # TextureResizeShader's constant: scale = srcRect size / dstRect size of the same-named axes, rotated quad or not (:351-354)
+            sx = f32(rect[2] - rect[0]) / f32(ow); sy = f32(rect[3] - rect[1]) / f32(oh)
+            assert R.ref_hlsl_run(label.encode(), _p(tex), W, H, 0, None, 0, 0, _p(uv), ow * oh, sx, sy, _p(ref)) == 0
+        lit = np.empty((oh, ow, 3), f32)
+        assert L.orc_test_oriented_draw(1, in_axis, kind, filt, O.VARIANT_D3D11, rot, flip, _p(rgb), W, H, (C.c_int * 4)(*rect), ow, oh, _p(lit)) == 0, label
+        a = np.ascontiguousarray(ref[..., :3])
+        assert np.array_equal(a.view(np.uint32), lit.view(np.uint32)), (label, rot, flip, int((a.view(np.uint32) != lit.view(np.uint32)).sum()))
