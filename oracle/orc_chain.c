@@ -346,6 +346,22 @@ int orc_axis_taps(int kind, int filter, int variant, int src_origin, int src_len
     return axis_taps_export_spec(kind, filter, variant, src_origin, src_len, dst_len, i, base, weights, wsum);
 }
 
+/* vector forms of the scalar contract for exhaustive sweeps: op 0 lg2, 1 ex2, 2 pow(x, y), 3 sin, 4 ex2p(x, y), 5 x / y (IEEE) */
+int orc_test_math_vec(int op, const float* x, const float* y, float* out, int64_t n)
+{
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        switch (op) {
+        case 0: out[i] = orc_lg2_spec(x[i]); break;
+        case 1: out[i] = orc_ex2_spec(x[i]); break;
+        case 2: out[i] = orc_pow_spec(x[i], y[i]); break;
+        case 3: out[i] = orc_sin_spec(x[i]); break;
+        case 4: out[i] = orc_ex2p_spec(x[i], y[i]); break;
+        default: out[i] = x[i] / y[i]; break;
+        }
+    }
+    return 0;
+}
 float orc_test_lg2(float x) { return orc_lg2_spec(x); }
 float orc_test_sin(float x) { return orc_sin_spec(x); }
 float orc_test_ex2(float x) { return orc_ex2_spec(x); }

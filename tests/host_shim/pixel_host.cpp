@@ -68,3 +68,24 @@ int host_final_quant(const float* p, const float* d, float Q, float* out, int n)
     return 0;
 }
 }
+
+extern "C" {
+// the scalar math of mpcvr_math.cuh: op 0 lg2, 1 ex2, 2 powr(x, y), 3 sin_spec, 4 ex2p(x, y), 5 div_rn_safe(x, y), 6 unorm8 / 7 unorm10 / 8 unorm16 of (uint)x
+int host_math(int op, const float* x, const float* y, float* out, long long n)
+{
+    for (long long i = 0; i < n; i++) {
+        switch (op) {
+        case 0: out[i] = lg2(x[i]); break;
+        case 1: out[i] = ex2(x[i]); break;
+        case 2: out[i] = powr(x[i], y[i]); break;
+        case 3: out[i] = sin_spec(x[i]); break;
+        case 4: out[i] = ex2p(x[i], y[i]); break;
+        case 5: out[i] = div_rn_safe(x[i], y[i]); break;
+        case 6: out[i] = unorm8((uint32_t)x[i]); break;
+        case 7: out[i] = unorm10((uint32_t)x[i]); break;
+        default: out[i] = unorm16((uint32_t)x[i]); break;
+        }
+    }
+    return 0;
+}
+}

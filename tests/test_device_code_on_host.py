@@ -296,3 +296,51 @@ def test_the_shim_is_test_infrastructure_only():
                 if re.search(r"host_shim|cuda_host_shim|liborc|orc_api\.h|orc_core", text):
                     bad.append(os.path.join(d, fn))
     assert not bad, bad
+
+
+# ---- the scalar arithmetic contract itself: mpcvr_math.cuh against oracle/orc_math.h ----
+def _floats_between(lo, hi, stride):
+    a = np.array([lo, hi], f32).view(np.uint32)
+    return np.arange(int(a[0]), int(a[1]) + 1, stride, dtype=np.uint64).astype(np.uint32).view(f32)
+
+
+def _math(op, x, y=None):
+    HL = host_lib(); L = O.lib()
+    HL.host_math.argtypes = [C.c_int, FP, FP, FP, C.c_longlong]
+    L.orc_test_math_vec.argtypes = [C.c_int, FP, FP, FP, C.c_int64]
+    x = np.ascontiguousarray(x, f32); y = np.ascontiguousarray(y if y is not None else x, f32)
+    got = np.empty_like(x); want = np.empty_like(x)
+    assert HL.host_math(op, _p(x), _p(y), _p(got), x.size) == 0
+    assert L.orc_test_math_vec(min(op, 5), _p(x), _p(y), _p(want), x.size) == 0
+    return got, want
+
+
+def test_lg2_ex2_sin_equal_the_contract_on_dense_sweeps():
+    """every 61st float of the ranges the shader chain feeds them with (lg2: all positive normals; ex2: [-150, 130]; sin: [0, 16))"""
+    for op, xs in ((0, _floats_between(1.17549435e-38, 3.0e38, 61)), (1, np.concatenate([_floats_between(1e-30, 130.0, 61), -_floats_between(1e-30, 150.0, 61)])),
+                   (3, _floats_between(1e-30, 16.0, 61))):
+        got, want = _math(op, xs)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (op, int((got.view(np.uint32) != want.view(np.uint32)).sum()))
+
+
+def test_pow_and_division_equal_the_contract():
+    rng = np.random.Generator(np.random.PCG64(21))
+    n = 4_000_000
+    x = np.concatenate([rng.uniform(0, 1.2, n).astype(f32), (rng.uniform(0, 1, n) ** 8).astype(f32), np.array([0, -1, 1, np.inf, 1e-40, np.nan], f32)])
+    ys = np.array([1 / 2.2, 2.2, 2.4, 1 / 78.84375, 1 / 0.1593017578125, 0.1593017578125, 78.84375, 0.2, 1.8, 2.6, 2.8, 0.5, 1.5], f32)
+    y = ys[rng.integers(0, ys.size, x.size)]
+    got, want = _math(2, x, y)
+    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), (int((~same).sum()), x[~same][:4], y[~same][:4], got[~same][:4], want[~same][:4])
+    # div_rn_safe: the reciprocal + residual-correction quotient, on the operand ranges the tone-map quotients have (den in [0.16, 19])
+    num = rng.uniform(0, 1000, n).astype(f32); den = rng.uniform(0.16, 19, n).astype(f32)
+    got, want = _math(5, num, den)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_unorm_reads_equal_correctly_rounded_division():
+    """unorm8 / unorm10 / unorm16: the two-operation exact forms (mpcvr_math.cuh) against code / (2^n - 1) in IEEE arithmetic, every code"""
+    for op, top in ((6, 255), (7, 1023), (8, 65535)):
+        c = np.arange(top + 1, dtype=f32)
+        got, _ = _math(op, c)
+        assert np.array_equal(got.view(np.uint32), (c / f32(top)).astype(f32).view(np.uint32)), top
