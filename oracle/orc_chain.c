@@ -234,7 +234,7 @@ int orc_test_convert_params(const orc_config* cfg, const orc_dovi* dv, float cm[
 
 /* convert_color (the body of the generated convert shader) on n yuv triplets, with the constants build_cparams derives for cfg / dv exactly as
  * orc_process does -- tests/test_device_code_on_host.py runs the product's device function convert_color() compiled for the host on the same
- * triplets.  mode 0 SPEC, 1 LITERAL. */
+ * triplets.  mode 0 SPEC, 1 LITERAL, 2 F64. */
 int orc_test_convert_pixels(const orc_config* cfg, const orc_dovi* dv, int mode, const float* yuv, float* out, int n)
 {
     const orc_fmt* f = orc_get_fmt(cfg->cformat);
@@ -251,6 +251,16 @@ int orc_test_convert_pixels(const orc_config* cfg, const orc_dovi* dv, int mode,
         static cparams_lit P; memset(&P, 0, sizeof(P));
         if (build_cparams_lit(cfg, f, exfmt, &P, dv)) return -11;
         for (int i = 0; i < n; i++) convert_color_lit(&P, yuv + 3 * i, out + 3 * i);
+        return 0;
+    }
+    if (mode == 2) {                                        /* float64 twin: the same text evaluated in double, rounded to float at the end */
+        static cparams_f64 P; memset(&P, 0, sizeof(P));
+        if (build_cparams_f64(cfg, f, exfmt, &P, dv)) return -11;
+        for (int i = 0; i < n; i++) {
+            const double in[3] = { yuv[3 * i], yuv[3 * i + 1], yuv[3 * i + 2] }; double o[3];
+            convert_color_f64(&P, in, o);
+            out[3 * i] = (float)o[0]; out[3 * i + 1] = (float)o[1]; out[3 * i + 2] = (float)o[2];
+        }
         return 0;
     }
     return -1;
