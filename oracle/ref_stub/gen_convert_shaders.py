@@ -63,6 +63,8 @@ CASES.append(("P016_2020_sdr", "P016", SDR2020, 5, BILINEAR, NONE, 0, -1))
 for trc in (2, 3, 4, 5, 6, 7, 8, 14):
     CASES.append(("P010_2020_trc%d" % trc, "P010", dict(range_=2, matrix=4, prim=9, trc=trc), 5, BILINEAR, NONE, 0, -1))
 CASES.append(("NV12_601_full", "NV12", dict(range_=1, matrix=2, prim=2, trc=5), 5, BILINEAR, NONE, 0, -1))
+CASES.append(("P010_pq_to_sdr_1024x512", "P010", PQ, 5, BILINEAR, TO_SDR, 0, -1))      # a C2-shaped frame of some size for the whole-chain test
+SIZES = {"P010_pq_to_sdr_1024x512": (1024, 512)}
 for mmr in (0, 1):
     CASES.append(("P010_dovi%d_to_sdr" % mmr, "P010", PQ, 5, BILINEAR, TO_SDR, 0, mmr))
     CASES.append(("P010_dovi%d_to_pq" % mmr, "P010", PQ, 5, BILINEAR, TO_PQ, 0, mmr))
@@ -96,6 +98,7 @@ print("                  const float* piv; const float* coef; const float* mmr; 
 rows = []
 for i, (name, fmt, exf, siting, scaler, conv, blend, dovi) in enumerate(CASES):
     cf = CF[fmt]
+    W, H = SIZES.get(name, (64, 32))
     row = (C.c_int * 13)()
     assert R.ref_fmt_params(cf, row) == 0
     # only YUV media types carry their dwControlFlags into m_decExFmt (InitMediaType, DX11VideoProcessor.cpp:1763-1766): RGB and gray start from 0

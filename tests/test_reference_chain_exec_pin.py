@@ -72,6 +72,7 @@ CHAINS = {
     "c1_nv12_709_copy_bgra8":              ("NV12_s5_c1", 64, 32, dict(to_sdr=0, backbuffer=O.SURF_BGRA8)),
     "x_up_y_down_mitchell_hamming_rgb10":  ("P010_pq_to_sdr", 128, 8, dict(up=O.UPSCALE["Mitchell"], down=O.DOWNSCALE["Hamming"], to_sdr=1, backbuffer=O.SURF_RGB10A2)),
     "x_down_lanczos_y_up_lanczos3_bgra8":  ("P010_pq_to_sdr", 24, 64, dict(up=O.UPSCALE["Lanczos3"], down=O.DOWNSCALE["Lanczos"], to_sdr=1, backbuffer=O.SURF_BGRA8)),
+    "c2_shaped_1024x512_to_2048x1024_natural": ("P010_pq_to_sdr_1024x512", 2048, 1024, dict(up=O.UPSCALE["Lanczos3"], to_sdr=1, backbuffer=O.SURF_BGRA8, kind="natural")),
     "lanczos2_no_dither_8int":             ("NV12_s5_c1", 128, 64, dict(up=O.UPSCALE["Lanczos2"], to_sdr=0, backbuffer=O.SURF_BGRA8, dither=0, tex=O.TEXFMT_8INT)),
 }
 
@@ -79,16 +80,17 @@ CHAINS = {
 @pytest.mark.parametrize("chain", sorted(CHAINS))
 def test_frame_through_the_executed_reference_shaders_equals_the_oracle(chain):
     case_name, ow, oh, kw = CHAINS[chain]
+    kw = dict(kw); kind = kw.pop("kind", "fullnoise")
     i = [k for k, n in TC.CASES if n == case_name][0]
     RC, _, _ = TC._libs()
     info = (C.c_uint * 9)(); RC.ref_convert_case(i, info)
     cf, ex, siting, scaler, conv, blend, dovi, W, Hh = [int(x) for x in info]
     assert kw.get("chroma", O.CHROMA_Bilinear) == scaler and int(kw["to_sdr"]) == int(conv == 1)
     # 1. the convert draw: the reference's generated shader on the frame run_case builds (full-range noise, seed = case index)
-    conv_ref = TC.run_case(i)[4]
+    conv_ref = TC.run_case(i, kind=kind, seed=i)[4]
     conv_rgba = np.concatenate([conv_ref, np.ones(conv_ref.shape[:2] + (1,), f32)], axis=2)
     # the oracle on the same planes, with this chain's settings
-    codes = H.make_codes(cf, W, Hh, "fullnoise", seed=i)
+    codes = H.make_codes(cf, W, Hh, kind, seed=i)
     _, _, planes, pitches = H.pack(cf, W, Hh, codes)
     cfg = O.make_config(cf, W, Hh, ow, oh, ex, **kw)
     out_lit, dbg = O.process(cfg, planes, pitches, mode=O.MODE_LITERAL, want_debug=True)

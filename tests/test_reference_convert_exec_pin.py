@@ -4,7 +4,7 @@ CDX11VideoProcessor does not ship its convert shader: GetShaderConvertColor (Sou
 ShaderGetPixels' fetch branch for the format / chroma siting / chroma scaler / blend-deinterlace, the Dolby Vision reshaping, the colour
 matrix, and the transfer steps spliced from Shaders/convert/{st2084,hlg,hdr_tone_mapping}.hlsl -- and hands it to D3DCompile.  That
 generator is compiled where it lies (oracle/_ref/libref_shaders.so, CompileShader stubbed to keep the text).  oracle/Makefile asks it for
-the text of 116 cases (oracle/ref_stub/gen_convert_shaders.py: every planar / bi-planar / packed layout x chroma scaler x siting,
+the text of 117 cases (oracle/ref_stub/gen_convert_shaders.py: every planar / bi-planar / packed layout x chroma scaler x siting,
 blend deinterlace, PQ and HLG to SDR, HLG to PQ, pass-through, the BT.2020 SDR gammas, RGB and gray sources, Dolby Vision with polynomial
 and MMR curves) and compiles each text AS C++ over an HLSL vector / swizzle / Texture2D vocabulary (oracle/ref_stub/hlsl_vec.h) into
 oracle/_ref/libref_hlsl_convert.so; the edits to the text are syntax only and listed in the generator.  Nothing is copied into the repo.
@@ -18,7 +18,7 @@ Here every case's shader runs over a whole frame of full-range random codes, fed
     (oracle/_ref/libref_dovi.so),
 and the result is compared with the convert-pass output of the oracle (orc_process, debug tap convert_f32 = the pixel before the render
 target write) in LITERAL mode -- the mode that claims to be the shader text, one IEEE operation per written operation: BIT-EQUAL, all
-116 cases.  SPEC mode (what the CUDA kernels are bit-exact with) is held to a measured distance from the executed text.
+117 cases.  SPEC mode (what the CUDA kernels are bit-exact with) is held to a measured distance from the executed text.
 
 So the fetch arithmetic (chroma positions, Catmull-Rom weights and tap order, 4:2:2 interpolation, the packed-format swizzles, the blend
 deinterlace), the order of matrix / saturate / transfer / gamut steps, the Dolby Vision reshaping (pivot search, polynomial, MMR orders)
@@ -200,7 +200,7 @@ def test_generated_convert_shader_equals_the_oracle(i, name):
 
 @pytest.mark.parametrize("kind", ["natural", "noise", "ramp"])
 def test_generated_convert_shader_on_other_content(kind):
-    """legal-range noise, smooth "natural" frames and ramps (the per-case test uses full-range noise): all 116 cases again"""
+    """legal-range noise, smooth "natural" frames and ramps (the per-case test uses full-range noise): all 117 cases again"""
     for i, name in CASES:
         name, conv, dovi, ex, ref, lit, spec = run_case(i, kind=kind, seed=1000 + i)
         bad = np.nonzero(ref.view(np.uint32) != lit.view(np.uint32))
