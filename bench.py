@@ -203,6 +203,62 @@ def run_cpu_sample(case, frame, budget_s=12.0, threads=0):
             "sample": "%d band(s) of %d/%d source rows (7680x%d output), scaled to full frames, oracle SPEC mode, OpenMP over rows" % (n, band_rows, case.h, 2 * band_rows)}
 
 
+def run_reference_shader_sample():
+    """The reference's OWN shaders on one host core: the HLSL text GetShaderConvertColor generates for the C2 media type, the Lanczos3 X / Y resize
+    shaders and ps_final_pass, compiled as C++ from the reference tree into oracle/_ref (oracle/Makefile; built where /root/reference exists, the
+    libraries travel) and chained as CDX11VideoProcessor::Process chains its draws, on a C2-shaped 1024x512 -> 2048x1024 frame (power-of-two
+    textures, the size that case's shader text was generated for), scaled to C2 frames by the pixel ratio.  An emulation layer compiled at -O1,
+    one thread (its constant buffers are globals): context for what "the reference's shader text on a CPU" costs, next to the optimised
+    multi-threaded port of cpu_baseline.  Returns None when oracle/_ref is not there."""
+    import numpy as np
+    import orclib as O
+    if not all(os.path.exists(os.path.join(O.ORC_DIR, "_ref", n)) for n in ("libref_hlsl_convert.so", "libref_hlsl_shaders.so", "libref_shaders.so")):
+        return None
+    import harness as H
+    import test_reference_convert_exec_pin as TC
+    import test_reference_chain_exec_pin as CH
+    C = ctypes; f32 = np.float32; FP = C.POINTER(C.c_float)
+    RC, RS, _ = TC._libs()
+    i = [k for k, n in TC.CASES if n == "P010_pq_to_sdr_1024x512"][0]
+    info = (C.c_uint * 9)(); RC.ref_convert_case(i, info)
+    cf, ex, W, Hh = int(info[0]), int(info[1]), int(info[7]), int(info[8])
+    ow, oh = 2 * W, 2 * Hh
+    codes = H.make_codes(cf, W, Hh, "natural", seed=100)
+    _, _, planes, pitches = H.pack(cf, W, Hh, codes)
+    tex = TC.textures(cf, W, Hh, planes, pitches)
+    while len(tex) < 3:
+        tex.append(tex[0])
+    cm, cc, en = ((C.c_float * 3) * 3)(), (C.c_float * 3)(), C.c_int32()
+    assert RS.ref_convert_color_params(cf, ex, 0.0, 1.0, 0.0, 1.0, None, None, cm, cc, C.byref(en)) == 0
+    cm12 = (C.c_float * 12)(*([cm[r][c] for r in range(3) for c in range(3)] + list(cc)))
+    p = lambda a: a.ctypes.data_as(FP)
+    R = CH._shader_lib()
+    O.lib().orc_dither_thresholds.restype = C.POINTER(C.c_uint16)
+    K = np.ctypeslib.as_array(O.lib().orc_dither_thresholds(), (1024,)).astype(f32) / f32(1024)
+    dither = np.ascontiguousarray(np.repeat(K.reshape(32, 32, 1), 4, axis=2))
+    t = {}
+    t0 = time.time()
+    conv = np.empty((Hh, W, 4), f32)
+    assert RC.ref_convert_run(i, (FP * 3)(*[p(x) for x in tex]), (C.c_int * 3)(*[x.shape[1] for x in tex]), (C.c_int * 3)(*[x.shape[0] for x in tex]),
+                              cm12, f32(10000.0) / f32(125.0), None, None, None, None, None, 0, p(conv)) == 0
+    t["convert"] = time.time() - t0; t0 = time.time()
+    _, a = CH.rt_roundtrip(conv, O.SURF_RGB10A2)
+    x = CH._draw(R, "lanczos3_x", a, ow, Hh)
+    t["resize_x"] = time.time() - t0; t0 = time.time()
+    _, a = CH.rt_roundtrip(x, O.SURF_RGBA16F)
+    y = CH._draw(R, "lanczos3_y", a, ow, oh)
+    t["resize_y"] = time.time() - t0; t0 = time.time()
+    _, a = CH.rt_roundtrip(y, O.SURF_RGB10A2)
+    fin = CH._draw(R, "final_8", a, ow, oh, tex2=dither, sx=f32(ow) / f32(32), sy=f32(oh) / f32(32))
+    CH.rt_roundtrip(fin, O.SURF_BGRA8)
+    t["final"] = time.time() - t0
+    total = sum(t.values())
+    ratio = (3840 * 2160) / float(W * Hh)
+    return {"value": 1.0 / (total * ratio), "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": "one C2-shaped %dx%d -> %dx%d frame through the reference's shader text compiled as C++ (oracle/_ref), scaled by %.2f to C2 frames; one thread" % (W, Hh, ow, oh, ratio),
+            "stage_seconds": {k: round(v, 3) for k, v in t.items()}}
+
+
 def impl_reference(args, rank, world):
     """The reference's own implementation of this path is HLSL on D3D11 and cannot run here; this arm times the CPU
     port of its shaders (the oracle, SPEC arithmetic) with all host threads.  Rank 0 only."""
@@ -459,6 +515,12 @@ def main():
             line["cpu_baseline"] = run_cpu_sample(case, frames[0], budget_s=args.cpu_seconds)
         except Exception as e:   # the checker is not the product: report, do not fail the bench
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        try:                     # informative: the reference's own shader text executed on one core (see the function)
+            r = run_reference_shader_sample()
+            if r:
+                line["cpu_reference_shaders"] = r
+        except Exception as e:
+            line["cpu_reference_shaders"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
     if rank == 0:
         print(json.dumps(line))
     if dist:
