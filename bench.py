@@ -14,6 +14,8 @@ bilinear chroma, ordered dither.  One "step" = one frame through CVideoProcessor
              kernel's average duration from CUDA events on the launching stream, vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the CPU oracle (restatement of the reference's shaders; the reference has no CPU path) on the
              host cores, bounded sample, rank 0 / N=1 only
+  cpu_reference_shaders  (informative) the reference's own shader text, compiled as C++ from the reference tree into oracle/_ref, chained
+             on a C2-shaped 1024x512 -> 2048x1024 frame on ONE core and scaled to C2 frames; rank 0 / N=1 only
 
 Multi-GPU (torchrun): one independent stream per GPU, no collective on the data path; the only
 torch.distributed traffic is the barrier and the max-over-ranks of the timed interval.  scaling = weak.
