@@ -12,16 +12,17 @@ bilinear chroma, ordered dither.  One "step" = one frame through CVideoProcessor
              a separate row, never the headline
   roofline   algorithmic bytes of one frame (input read once + output written once) / the frame
              kernel's average duration from CUDA events on the launching stream, vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the CPU oracle (restatement of the reference's shaders; the reference has no CPU path) on the
-             host cores, bounded sample, rank 0 / N=1 only
-  cpu_reference_shaders  (informative) the reference's own shader text, compiled as C++ from the reference tree into oracle/_ref, chained
-             on a C2-shaped 1024x512 -> 2048x1024 frame on ONE core and scaled to C2 frames; rank 0 / N=1 only
+  cpu_baseline  the reference's own shader text (generated convert shader, Lanczos3 X / Y, ps_final_pass) compiled as C++ from the reference
+             tree into oracle/_ref and chained like Process on C2-shaped 1024x512 -> 2048x1024 frames, all host threads, scaled to C2 frames
+             (kind "reference"); without oracle/_ref: the CPU oracle, kind "port".  Bounded sample, rank 0 / N=1 only
+  cpu_port   the CPU oracle (the repo's restatement of the shaders in SPEC arithmetic) on the host cores, for continuity with round 1
 
 Multi-GPU (torchrun): one independent stream per GPU, no collective on the data path; the only
 torch.distributed traffic is the barrier and the max-over-ranks of the timed interval.  scaling = weak.
 
---impl reference: the reference's own implementation of this path cannot run here (HLSL on D3D11); the arm
-times the CPU oracle port on all host threads (kind "port"), rank 0 only.
+--impl reference: the reference's own implementation of this path is HLSL on D3D11; the arm times the reference's shader text
+compiled as C++ (oracle/_ref, kind "reference") on all host threads, or the CPU oracle port (kind "port") when oracle/_ref is
+absent; rank 0 only.
 """
 import argparse
 import ctypes
@@ -205,13 +206,13 @@ def run_cpu_sample(case, frame, budget_s=12.0, threads=0):
             "sample": "%d band(s) of %d/%d source rows (7680x%d output), scaled to full frames, oracle SPEC mode, OpenMP over rows" % (n, band_rows, case.h, 2 * band_rows)}
 
 
-def run_reference_shader_sample():
-    """The reference's OWN shaders on one host core: the HLSL text GetShaderConvertColor generates for the C2 media type, the Lanczos3 X / Y resize
+def reference_shader_chain(threads=0):
+    """The reference's OWN shaders on the host cores: the HLSL text GetShaderConvertColor generates for the C2 media type, the Lanczos3 X / Y resize
     shaders and ps_final_pass, compiled as C++ from the reference tree into oracle/_ref (oracle/Makefile; built where /root/reference exists, the
-    libraries travel) and chained as CDX11VideoProcessor::Process chains its draws, on a C2-shaped 1024x512 -> 2048x1024 frame (power-of-two
-    textures, the size that case's shader text was generated for), scaled to C2 frames by the pixel ratio.  An emulation layer compiled at -O1,
-    one thread (its constant buffers are globals): context for what "the reference's shader text on a CPU" costs, next to the optimised
-    multi-threaded port of cpu_baseline.  Returns None when oracle/_ref is not there."""
+    libraries travel) and chained as CDX11VideoProcessor::Process chains its draws, with the D3D11 render-target conversions between them, on a
+    C2-shaped 1024x512 -> 2048x1024 frame (power-of-two textures, the size that case's shader text was generated for).  Each draw is an OpenMP
+    loop over its pixels; the conversions between draws are numpy.  Returns (step, info) -- step() renders one sample frame and returns the
+    seconds per stage -- or None when oracle/_ref is not there."""
     import numpy as np
     import orclib as O
     if not all(os.path.exists(os.path.join(O.ORC_DIR, "_ref", n)) for n in ("libref_hlsl_convert.so", "libref_hlsl_shaders.so", "libref_shaders.so")):
@@ -220,6 +221,11 @@ def run_reference_shader_sample():
     import test_reference_convert_exec_pin as TC
     import test_reference_chain_exec_pin as CH
     C = ctypes; f32 = np.float32; FP = C.POINTER(C.c_float)
+    cores = host_threads() if threads <= 0 else threads
+    try:                                                   # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(cores))
+    except OSError:
+        cores = 1
     RC, RS, _ = TC._libs()
     i = [k for k, n in TC.CASES if n == "P010_pq_to_sdr_1024x512"][0]
     info = (C.c_uint * 9)(); RC.ref_convert_case(i, info)
@@ -238,33 +244,93 @@ def run_reference_shader_sample():
     O.lib().orc_dither_thresholds.restype = C.POINTER(C.c_uint16)
     K = np.ctypeslib.as_array(O.lib().orc_dither_thresholds(), (1024,)).astype(f32) / f32(1024)
     dither = np.ascontiguousarray(np.repeat(K.reshape(32, 32, 1), 4, axis=2))
-    t = {}
-    t0 = time.time()
-    conv = np.empty((Hh, W, 4), f32)
-    assert RC.ref_convert_run(i, (FP * 3)(*[p(x) for x in tex]), (C.c_int * 3)(*[x.shape[1] for x in tex]), (C.c_int * 3)(*[x.shape[0] for x in tex]),
-                              cm12, f32(10000.0) / f32(125.0), None, None, None, None, None, 0, p(conv)) == 0
-    t["convert"] = time.time() - t0; t0 = time.time()
-    _, a = CH.rt_roundtrip(conv, O.SURF_RGB10A2)
-    x = CH._draw(R, "lanczos3_x", a, ow, Hh)
-    t["resize_x"] = time.time() - t0; t0 = time.time()
-    _, a = CH.rt_roundtrip(x, O.SURF_RGBA16F)
-    y = CH._draw(R, "lanczos3_y", a, ow, oh)
-    t["resize_y"] = time.time() - t0; t0 = time.time()
-    _, a = CH.rt_roundtrip(y, O.SURF_RGB10A2)
-    fin = CH._draw(R, "final_8", a, ow, oh, tex2=dither, sx=f32(ow) / f32(32), sy=f32(oh) / f32(32))
-    CH.rt_roundtrip(fin, O.SURF_BGRA8)
-    t["final"] = time.time() - t0
-    total = sum(t.values())
+    targs = ((FP * 3)(*[p(x) for x in tex]), (C.c_int * 3)(*[x.shape[1] for x in tex]), (C.c_int * 3)(*[x.shape[0] for x in tex]))
+
+    R.ref_hlsl_draw.argtypes = [C.c_char_p, FP, C.c_int, C.c_int, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, FP]
+    R.ref_rt_roundtrip.argtypes = [C.c_int, FP, C.c_longlong, FP]
+    conv = np.empty((Hh, W, 4), f32); xs = np.empty((Hh, ow, 4), f32); ys = np.empty((oh, ow, 4), f32); fin = np.empty((oh, ow, 4), f32)
+
+    def rt(fmt, a):                                            # render-target write + the next draw's read, in place
+        assert R.ref_rt_roundtrip(fmt, p(a), a.size // 4, p(a)) == 0
+
+    def step(_keep=(tex, dither, planes)):                 # the ctypes pointers above point into these arrays
+        t = {}; t0 = time.time()
+        assert RC.ref_convert_run(i, *targs, cm12, f32(10000.0) / f32(125.0), None, None, None, None, None, 0, p(conv)) == 0
+        rt(1, conv)                                            # m_TexConvertOutput, R10G10B10A2
+        t["convert"] = time.time() - t0; t0 = time.time()
+        assert R.ref_hlsl_draw(b"lanczos3_x", p(conv), W, Hh, None, 0, 0, ow, Hh, f32(W) / f32(ow), f32(1), p(xs)) == 0
+        rt(2, xs)                                              # m_TexResize, R16G16B16A16_FLOAT
+        t["resize_x"] = time.time() - t0; t0 = time.time()
+        assert R.ref_hlsl_draw(b"lanczos3_y", p(xs), ow, Hh, None, 0, 0, ow, oh, f32(1), f32(Hh) / f32(oh), p(ys)) == 0
+        rt(1, ys)                                              # post-scale texture, R10G10B10A2
+        t["resize_y"] = time.time() - t0; t0 = time.time()
+        assert R.ref_hlsl_draw(b"final_8", p(ys), ow, oh, p(dither), 32, 32, ow, oh, f32(ow) / f32(32), f32(oh) / f32(32), p(fin)) == 0
+        rt(0, fin)                                             # back buffer, B8G8R8A8
+        t["final"] = time.time() - t0
+        return t
+
     ratio = (3840 * 2160) / float(W * Hh)
-    return {"value": 1.0 / (total * ratio), "unit": UNIT, "cores": 1, "kind": "reference",
-            "sample": "one C2-shaped %dx%d -> %dx%d frame through the reference's shader text compiled as C++ (oracle/_ref), scaled by %.2f to C2 frames; one thread" % (W, Hh, ow, oh, ratio),
-            "stage_seconds": {k: round(v, 3) for k, v in t.items()}}
+    sample = ("a C2-shaped %dx%d -> %dx%d frame through the reference's own shader text compiled as C++ (oracle/_ref: generated convert shader, "
+              "ps_interpolation_lanczos3 X / Y, ps_final_pass, D3D11 target conversions between the draws), %d OpenMP threads; 1 / %.2f of a C2 frame"
+              % (W, Hh, ow, oh, cores, ratio))
+    return step, {"cores": cores, "frame_fraction": 1.0 / ratio, "sample": sample,
+                  # for tests/test_reference_chain_exec_pin.py: the frame the chain renders (codes / 255 after the B8G8R8A8 write) and how to redo it with the oracle
+                  "final_rgba": fin, "oracle_case": (cf, W, Hh, ow, oh, ex, planes, pitches)}
+
+
+def run_reference_shader_sample(threads=0, budget_s=6.0):
+    """cpu_baseline of the bench line (kind "reference"): reference_shader_chain() timed on a bounded number of sample frames, scaled to C2 frames"""
+    r = reference_shader_chain(threads)
+    if r is None:
+        return None
+    step, info = r
+    step()                                                 # warm-up (page faults, OpenMP team)
+    n = 0; t0 = time.time(); stages = {}
+    while n < 1 or (time.time() - t0 < budget_s and n < 50):
+        for k, v in step().items():
+            stages[k] = stages.get(k, 0.0) + v
+        n += 1
+    dt = time.time() - t0
+    return {"value": n * info["frame_fraction"] / dt, "unit": UNIT, "cores": info["cores"], "kind": "reference",
+            "sample": "%d x %s" % (n, info["sample"]), "stage_seconds_per_sample": {k: round(v / n, 4) for k, v in stages.items()}}
 
 
 def impl_reference(args, rank, world):
-    """The reference's own implementation of this path is HLSL on D3D11 and cannot run here; this arm times the CPU
-    port of its shaders (the oracle, SPEC arithmetic) with all host threads.  Rank 0 only."""
+    """The reference's own implementation of this path is HLSL on D3D11.  When oracle/_ref holds the reference's shader text compiled as C++
+    (reference_shader_chain), this arm times THAT on all host threads (kind "reference"); otherwise the CPU port of its shaders (the oracle,
+    SPEC arithmetic; kind "port").  Rank 0 only."""
     if rank != 0:
+        return 0
+    try:
+        r = None if os.environ.get("MPCVR_BENCH_FORCE_PORT") else reference_shader_chain(0)
+    except Exception:
+        r = None
+    if r is not None:
+        step, info = r
+        step()                                                               # first touch
+        t0 = time.time()
+        for _ in range(max(1, min(args.warmup, 3))):
+            step()
+        t_sample = (time.time() - t0) / max(1, min(args.warmup, 3))
+        # sample frames per step: one C2 frame's worth of pixels when the K steps then fit --ref-seconds, fewer otherwise (never less than one)
+        per_step = int(round(1.0 / info["frame_fraction"]))
+        per_step = max(1, min(per_step, int((args.ref_seconds / max(1, args.steps)) / max(t_sample, 1e-6))))
+        t0 = time.time()
+        for _ in range(args.steps * per_step):
+            step()
+        dt = time.time() - t0
+        fps = args.steps * per_step * info["frame_fraction"] / dt
+        sample = "each step = %d x %s" % (per_step, info["sample"])
+        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+                "cpu_baseline": {"value": fps, "unit": UNIT, "cores": info["cores"], "kind": "reference", "sample": sample},
+                "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "the reference's path is HLSL on D3D11; this arm runs the reference's own shader text (the generated convert shader, the resize and "
+                        "final-pass .hlsl files) compiled as C++ from the reference tree into oracle/_ref, on all host threads; the frame it renders equals "
+                        "the oracle's LITERAL frame byte for byte (tests/test_reference_chain_exec_pin.py)"}
+        print(json.dumps(line))
         return 0
     import harness as H
     import orclib as O
@@ -514,15 +580,19 @@ def main():
         try:
             if all_cpus:                                   # the CPU leg gets every host core back (the GPU legs ran bound to one NUMA node)
                 os.sched_setaffinity(0, all_cpus)
-            line["cpu_baseline"] = run_cpu_sample(case, frames[0], budget_s=args.cpu_seconds)
+            port = run_cpu_sample(case, frames[0], budget_s=args.cpu_seconds)
         except Exception as e:   # the checker is not the product: report, do not fail the bench
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
-        try:                     # informative: the reference's own shader text executed on one core (see the function)
-            r = run_reference_shader_sample()
-            if r:
-                line["cpu_reference_shaders"] = r
+            port = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        ref = None
+        try:                     # the reference's own shader text compiled as C++ (oracle/_ref), when it was built
+            ref = run_reference_shader_sample(budget_s=min(8.0, args.cpu_seconds))
         except Exception as e:
-            line["cpu_reference_shaders"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+            port["reference_shaders_failed"] = repr(e)
+        if ref:
+            line["cpu_baseline"] = ref       # kind "reference"
+            line["cpu_port"] = port          # the repo's optimised-for-exactness restatement (oracle, SPEC arithmetic), for continuity with round 1
+        else:
+            line["cpu_baseline"] = port
     if rank == 0:
         print(json.dumps(line))
     if dist:

@@ -115,7 +115,7 @@ for i, (name, fmt, exf, siting, scaler, conv, blend, dovi) in enumerate(CASES):
     print(text)
     for m in macros:
         print("#undef %s" % m)
-    print("static float4 run(const ConvArgs& A, float u, float v) {")
+    print("static void setup(const ConvArgs& A) {              // constant buffers and bindings: once per draw")
     for t, r in sorted(regs.items(), key=lambda kv: kv[1]):
         print("    %s.bind(A.tex[%d], A.tw[%d], A.th[%d]);" % (t, r, r, r))
     print("    samp.linear = 0; sampL.linear = 1;")
@@ -133,11 +133,10 @@ for i, (name, fmt, exf, siting, scaler, conv, blend, dovi) in enumerate(CASES):
             print("        curves[c].params.min_order = A.par[c * 4 + 2]; curves[c].params.max_order = A.par[c * 4 + 3];")
         print("    }")
         print("    ChromaWeight = A.trims[0]; SaturationGain = A.trims[1]; TrimSlope = A.trims[2]; TrimOffset = A.trims[3]; TrimPower = A.trims[4]; L2Enabled = A.l2;")
-    print("    PS_INPUT in; in.Tex = float2(u, v);")
-    print("    return ps_main(in);")
     print("}")
+    print("static float4 shade(float u, float v) { PS_INPUT in; in.Tex = float2(u, v); return ps_main(in); }   // reads the globals only: callable from many threads")
     print("}  // namespace %s" % ns)
-    rows.append('{ "%s", %d, %#010xu, %d, %d, %d, %d, %d, %d, %d, %s::run }' % (name, cf, ex, siting, scaler, conv, blend, dovi, W, H, ns))
+    rows.append('{ "%s", %d, %#010xu, %d, %d, %d, %d, %d, %d, %d, %s::setup, %s::shade }' % (name, cf, ex, siting, scaler, conv, blend, dovi, W, H, ns, ns))
 # ---- Shaders/d3d11/ps_hdr10_tonemap.hlsl (the HDR10 local tone-mapping post-scale step), a file of the tree rather than generated text
 text, regs, macros = translate(open("%s/Shaders/d3d11/ps_hdr10_tonemap.hlsl" % REF, encoding="utf-8", errors="replace").read())
 print("// ======== ps_hdr10_tonemap.hlsl")
@@ -255,7 +254,7 @@ for sym in SYMS9:
 print("struct D9Entry { const char* name; float4 (*run)(const float*, int, int, float, float, float, float); };")
 print("static const D9Entry g_d9[] = { %s };" % ", ".join('{ "%s", %s::run }' % (ns, ns) for ns, _, _ in D9))
 print("static const int g_nd9 = %d;" % len(D9))
-print("struct ConvCase { const char* name; int cformat; unsigned exfmt; int siting, scaler, convert_type, blend, dovi, W, H; float4 (*run)(const ConvArgs&, float, float); };")
+print("struct ConvCase { const char* name; int cformat; unsigned exfmt; int siting, scaler, convert_type, blend, dovi, W, H; void (*setup)(const ConvArgs&); float4 (*shade)(float, float); };")
 print("static const ConvCase g_cases[] = {\n    %s\n};" % ",\n    ".join(rows))
 print("static const int g_ncases = %d;" % len(rows))
 print("static const double g_dovi_lms[9] = { %s };" % ", ".join(repr(float(x)) for x in DOVI_LMS))

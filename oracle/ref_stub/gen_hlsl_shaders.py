@@ -57,7 +57,7 @@ for ns, fname, defs in SHADERS:
     out.append("}  // namespace %s" % ns)
 out += ["#undef %s" % s for s in SYMS]
 # the dispatch table the wrapper uses
-out.append("struct ShaderEntry { const char* name; float4 (*run)(const float* tex, int w, int h, int wrap, const float* tex2, int w2, int h2, float u, float v, float sx, float sy); };")
+out.append("struct ShaderEntry { const char* name; void (*setup)(const float* tex, int w, int h, int wrap, const float* tex2, int w2, int h2, float sx, float sy); float4 (*shade)(float u, float v); };")
 for ns, fname, defs in SHADERS:
     final = fname == "ps_final_pass.hlsl"
     body = ("%s::tex.bind(tex, w, h); %s::samp.wrap = wrap; " % (ns, ns))
@@ -65,8 +65,8 @@ for ns, fname, defs in SHADERS:
         body += "%s::texDither.bind(tex2, w2, h2); %s::sampDither.wrap = 1; %s::ditherCoordScale = float2(sx, sy); " % (ns, ns, ns)
     else:
         body += "%s::wh = float2((float)w, (float)h); %s::dxdy = float2(1.0f / (float)w, 1.0f / (float)h); %s::scale = float2(sx, sy); " % (ns, ns, ns)
-    body += "%s::PS_INPUT in; in.Tex = float2(u, v); return %s::ps_main(in);" % (ns, ns)
-    out.append("static float4 run_%s(const float* tex, int w, int h, int wrap, const float* tex2, int w2, int h2, float u, float v, float sx, float sy) { %s }" % (ns, body))
-out.append("static const ShaderEntry g_shaders[] = { %s };" % ", ".join('{ "%s", run_%s }' % (ns, ns) for ns, _, _ in SHADERS))
+    out.append("static void setup_%s(const float* tex, int w, int h, int wrap, const float* tex2, int w2, int h2, float sx, float sy) { %s }" % (ns, body))
+    out.append("static float4 shade_%s(float u, float v) { %s::PS_INPUT in; in.Tex = float2(u, v); return %s::ps_main(in); }" % (ns, ns, ns))
+out.append("static const ShaderEntry g_shaders[] = { %s };" % ", ".join('{ "%s", setup_%s, shade_%s }' % (ns, ns, ns) for ns, _, _ in SHADERS))
 out.append("static const int g_nshaders = %d;" % len(SHADERS))
 sys.stdout.write("\n".join(out) + "\n")

@@ -129,3 +129,18 @@ def test_frame_through_the_executed_reference_shaders_equals_the_oracle(chain):
     print("CHAIN %-40s internal fmt %d final %d resize (%d, %d)  SPEC vs executed reference: %d of %d bytes differ (%.3f %%), max |delta| %d"
           % (chain, fmt_int, final, rx, ry, int((d != 0).sum()), d.size, 100.0 * float((d != 0).mean()), int(d.max())))
     assert d.max() <= 1 and (d != 0).mean() <= 0.01, (chain, int(d.max()), float((d != 0).mean()))
+
+
+def test_the_chain_bench_times_renders_the_oracles_frame():
+    """bench.py's `--impl reference` / cpu_reference_shaders leg runs the same executed shaders through whole-draw C entry points (OpenMP over
+    pixels, the target conversions in C): the frame it renders must be the oracle's LITERAL frame, byte for byte -- what is timed is the path"""
+    import bench
+    r = bench.reference_shader_chain(threads=4)
+    assert r is not None
+    step, info = r
+    step()
+    cf, W, Hh, ow, oh, ex, planes, pitches = info["oracle_case"]
+    cfg = O.make_config(cf, W, Hh, ow, oh, ex, up=O.UPSCALE["Lanczos3"], to_sdr=1, backbuffer=O.SURF_BGRA8)
+    want = H.rgb_view(O.process(cfg, planes, pitches, mode=O.MODE_LITERAL), O.SURF_BGRA8)
+    got = np.rint(info["final_rgba"][..., :3] * f32(255)).astype(np.int32)
+    assert np.array_equal(got, want), int((got != want).sum())
